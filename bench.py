@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame rendering hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one boosted frame (`Network.forward`) of the configuration BASELINE.json's metric is
+quoted on: ENeRF + BoostMVSNeRFs, K=4 cost volumes, 960x540 run as 960x544 (H and W must be
+multiples of 32), N=6 synthetic source views, random-init weights.
+Rank 0 prints ONE JSON line; see DESIGN.md §Measurement for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, n_views, K, view-selection indices into C(n_views,3))
+    "C1": dict(H=256, W=320, n_views=3, K=1, k_best=[0]),
+    "C2": dict(H=544, W=960, n_views=6, K=4, k_best=[0, 7, 12, 19]),
+    "C4": dict(H=1088, W=1920, n_views=6, K=8, k_best=[0, 3, 7, 9, 12, 15, 17, 19]),
+}
+CPU_SAMPLE_SIZES = [(544, 960), (384, 640), (288, 480), (256, 320), (128, 192), (64, 96)]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--stage-report", action="store_true", help="print the per-stage table to stderr")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = str(index), [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", self.index], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._pump, daemon=True).start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm, reasons, mx, pw = [], set(), None, []
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2]); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------ stage timing
+class StageTimer:
+    """CUDA-event brackets around the named stages of Network._render_frame, recorded on torch's
+    current stream (the one libbmv launches on)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.records, self.enabled = [], False
+
+    def __call__(self, name):
+        return _Stage(self, name)
+
+    def summary(self):
+        agg = {}
+        for name, e0, e1 in self.records:
+            a = agg.setdefault(name, [0.0, 0])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+        return agg
+
+
+class _Stage:
+    def __init__(self, timer, name):
+        self.t, self.name = timer, name
+
+    def __enter__(self):
+        if self.t.enabled:
+            self.e0 = self.t.torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.t.enabled:
+            e1 = self.t.torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.t.records.append((self.name, self.e0, e1))
+        return False
+
+
+def algorithmic_bytes(wl, rc):
+    """Compulsory HBM traffic per LAUNCH of each hand-written kernel."""
+    H, W, K = wl["H"], wl["W"], wl["K"]
+    S_v = rc.cost_volume_input_views
+    out = {}
+    for i in range(rc.num):
+        C = int(32 * 2 ** (-i))
+        hs, ws = int(H * rc.im_feat_scale[i]), int(W * rc.im_feat_scale[i])
+        h, w, D = int(H * rc.volume_scale[i]), int(W * rc.volume_scale[i]), rc.volume_planes[i]
+        planes = 0 if i == 0 else D * h * w * 4
+        out[f"cost_volume_l{i}"] = S_v * C * hs * ws * 4 + planes + C * D * h * w * 4
+        out[f"depth_regression_l{i}"] = D * h * w * 4 + (planes if i else D * 4) + 2 * h * w * 4
+        if rc.render_if[i]:
+            rs = rc.render_scale[i]
+            Hr, Wr = int(H * rs), int(W * rs)
+            R, S = Hr * Wr, rc.num_samples[i]
+            Cf = rc.nerf_model_feat_ch[i]
+            reads = 8 * D * h * w * 4 + S_v * (Cf + 3) * Hr * Wr * 4 + 4 * h * w * 4 + R * 8 * 4
+            writes = R * S * 8 * 4 + R * S * S_v * (Cf + 7) * 4 + 2 * R * S * 4
+            out[f"raygen_fetch_l{i}"] = reads + writes
+            out[f"composite_blend_l{i}"] = R * (K * S * 24 + 12 + 4 + 4 * S)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_rate(wl, rc, steps, warmup, budget_s):
+    """Times the oracle restatement of the reference's CPU path (oracle/enerf_oracle.py,
+    kind="port": the reference is pure Python/PyTorch and cannot travel to the GPU box) with all
+    host threads, on a bounded sample: the same K/N configuration at the largest listed
+    resolution whose estimated cost fits the budget.  Returns (rays_per_s, ms_per_step, sample, cores)."""
+    import torch
+    from boostmvsnerfs_b200.modules import EnerfModules
+    from boostmvsnerfs_b200.synth import make_scene
+    from oracle import enerf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = EnerfModules(rc).eval()
+    kb = torch.tensor([wl["k_best"]])
+
+    def run(h, w):
+        scene = make_scene(H=h, W=w, n_views=wl["n_views"], seed=0)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.boost_enerf_forward(net, scene, rc, kb)
+        return time.perf_counter() - t0
+
+    run(64, 96)                                   # thread-pool / allocator warm-up
+    t_probe = run(128, 192)
+    rate = 128 * 192 / t_probe                    # rays/s estimate (roughly resolution independent)
+    per_step_budget = budget_s / max(1, steps + warmup)
+    size = CPU_SAMPLE_SIZES[-1]
+    for h, w in CPU_SAMPLE_SIZES:
+        if h <= wl["H"] and w <= wl["W"] and 2.5 * h * w / rate <= per_step_budget:  # 2.5x: large frames run slower per ray
+            size = (h, w)
+            break
+    for _ in range(warmup):
+        run(*size)
+    ts = [run(*size) for _ in range(steps)]
+    dt = sum(ts) / len(ts)
+    sample = (f"{steps} frame(s) of K={wl['K']} N={wl['n_views']} at {size[1]}x{size[0]} "
+              f"({size[0] * size[1]} rays) through oracle.boost_enerf_forward, torch {torch.__version__} CPU")
+    return size[0] * size[1] / dt, dt * 1e3, sample, cores
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from boostmvsnerfs_b200.config import RenderConfig
+    wl = WORKLOADS[args.workload]
+    rc = RenderConfig.enerf_eval(wl["K"])
+    rate, ms, sample, cores = cpu_reference_rate(wl, rc, max(1, args.steps), args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": "rays_per_sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, wl),
+            "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(name, wl):
+    return {"workload": f"{name}: ENeRF + BoostMVSNeRFs K={wl['K']} cost volumes, {wl['W']}x{wl['H']} "
+                        f"(960x540 padded to /32 for C2), N={wl['n_views']} source views, 3 views per volume, "
+                        "levels (64 planes @1/8, 8 planes @1/2), 2 samples/ray, random-init weights",
+            "l2": "no explicit flush: one frame streams ~3 GB through HBM (volumes 4x67 MB per level, fetched "
+                  "features 4x221 MB), far above the 126 MB L2",
+            "timing": "CUDA events on the launch stream around exactly `steps` frames, max over ranks"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from boostmvsnerfs_b200 import _lib, network
+    from boostmvsnerfs_b200.config import RenderConfig
+    from boostmvsnerfs_b200.synth import batch_to, make_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    wl = WORKLOADS[args.workload]
+    rc = RenderConfig.enerf_eval(wl["K"])
+    torch.manual_seed(0)
+    net = network.BoostEnerfNetwork(preprocess=True, rc=rc).eval().to(dev)
+    net.view_selection_outputs = {"synth_0": wl["k_best"]}
+    timer = StageTimer()
+    net.stage_timer = timer
+    # replicas: every rank renders its own frames (different seeds) — SURVEY.md §8(e) "sequence mode"
+    host = make_scene(H=wl["H"], W=wl["W"], n_views=wl["n_views"], seed=rank)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    batch = batch_to(host, dev)
+    rays_per_frame = wl["H"] * wl["W"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        net(batch)
+    # ---- device-resident timing
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    timer.enabled, timer.records = True, []
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = net(batch)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = (_lib.launch_count() - l0) / args.steps
+    timer.enabled = False
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clk = clocks.stop(t_wall0, t_wall1)
+    stages = timer.summary()
+
+    # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the frame, every step
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v))
+    res_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in ("rgb_level1", "depth_level1")}
+    d2h = sum(v.numel() * v.element_size() for v in res_host.values())
+    for _ in range(2):
+        o = net(batch_to(host, dev, non_blocking=True))
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        o = net(batch_to(host, dev, non_blocking=True))
+        for k, v in res_host.items():
+            v.copy_(o[k], non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant hand-written kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    alg = algorithmic_bytes(wl, rc)
+    launches_per_stage = {k: (wl["K"] if not k.startswith("composite") else 1) for k in alg}
+    kernels, step_ms_stage = {}, {}
+    for name, (tot_ms, cnt) in stages.items():
+        step_ms_stage[name] = tot_ms / args.steps
+        if name in alg:
+            per_launch_ms = tot_ms / (args.steps * launches_per_stage[name])
+            gbs = alg[name] / (per_launch_ms * 1e-3) / 1e9
+            kernels[name] = {"ms_per_launch": per_launch_ms, "launches_per_step": launches_per_stage[name],
+                             "algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac": gbs / peak_gbs,
+                             "share_of_step": tot_ms / args.steps / ms}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"]) if kernels else None
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak_gbs,
+                    "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "launch_ms": kernels[dom]["ms_per_launch"]}
+    hand_ms = sum(step_ms_stage.get(k, 0.0) for k in alg)
+    line = {
+        "metric": "rays_per_sec", "value": world * rays_per_frame / (ms * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "ms_per_frame": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args.workload, wl),
+                       parallelism=("single GPU" if world == 1 else f"{world} frame replicas, no data-path collective")),
+        "e2e": {"value": world * rays_per_frame / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
+        "stage_ms_per_step": step_ms_stage, "hand_written_ms_per_step": hand_ms,
+        "kept_library_ms_per_step": {k: v for k, v in step_ms_stage.items() if k.startswith(("cost_reg", "nerf", "feature"))},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cms, sample, cores = cpu_reference_rate(wl, rc, 1, 0, args.cpu_budget_s)
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample,
+                                "ms_per_step": cms}
+    if args.stage_report:
+        for k, v in sorted(step_ms_stage.items(), key=lambda kv: -kv[1]):
+            print(f"  {k:24s} {v:9.3f} ms/step", file=sys.stderr)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -1,0 +1,141 @@
+"""ctypes binding of libbmv.so — a 1:1 mirror of include/bmv.h.
+
+There is NO fallback: if the shared library is missing or an entry point fails, an exception is
+raised (north_star: "no CPU fallback, no multi-backend dispatch").
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbmv.so")
+
+MAX_VIEWS = 8
+MAX_VOLUMES = 16
+
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int32)
+i64, i32, f32 = C.c_int64, C.c_int32, C.c_float
+
+
+class CostVolumeParams(C.Structure):
+    _fields_ = [("feat", C.c_void_p), ("feat_view_stride", i64),
+                ("feat_c_stride", i64), ("feat_y_stride", i64), ("feat_x_stride", i64),
+                ("view", i32 * MAX_VIEWS), ("S", i32), ("C", i32), ("Hs", i32), ("Ws", i32),
+                ("proj", C.c_void_p), ("planes", C.c_void_p),
+                ("planes_d_stride", i64), ("planes_pix_stride", i64),
+                ("D", i32), ("h", i32), ("w", i32),
+                ("out", C.c_void_p),
+                ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
+                ("out_bf16", i32)]
+
+
+class DepthPlanesFirstParams(C.Structure):
+    _fields_ = [("near_far", C.c_void_p), ("t", C.c_void_p),
+                ("D", i32), ("h", i32), ("w", i32), ("depth_inv", i32),
+                ("planes", C.c_void_p), ("near_far_out", C.c_void_p)]
+
+
+class DepthPlanesNextParams(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("std", C.c_void_p), ("near_far", C.c_void_p), ("t", C.c_void_p),
+                ("h0", i32), ("w0", i32), ("h", i32), ("w", i32), ("D", i32), ("cur_inv", i32),
+                ("planes", C.c_void_p), ("near_far_out", C.c_void_p)]
+
+
+class DepthRegressionParams(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("planes", C.c_void_p),
+                ("planes_d_stride", i64), ("planes_pix_stride", i64),
+                ("D", i32), ("h", i32), ("w", i32), ("depth_inv", i32),
+                ("depth", C.c_void_p), ("std", C.c_void_p)]
+
+
+class RaygenFetchParams(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("std", C.c_void_p), ("near_far", C.c_void_p),
+                ("hv", i32), ("wv", i32), ("H", i32), ("W", i32), ("depth_inv", i32),
+                ("rays", C.c_void_p), ("ray_begin", i64), ("n_rays", i64),
+                ("rays12_in", C.c_void_p), ("xyz_in", C.c_void_p), ("uvd_in", C.c_void_p),
+                ("t", C.c_void_p), ("S", i32),
+                ("volume", C.c_void_p), ("Cv", i32), ("Dv", i32),
+                ("vol_c_stride", i64), ("vol_d_stride", i64), ("vol_y_stride", i64), ("vol_x_stride", i64),
+                ("V", i32), ("view", i32 * MAX_VIEWS),
+                ("im_feat", C.c_void_p), ("Cf", i32), ("Hf", i32), ("Wf", i32),
+                ("imf_view_stride", i64), ("imf_c_stride", i64), ("imf_y_stride", i64), ("imf_x_stride", i64),
+                ("rgb", C.c_void_p), ("rgb_view_stride", i64), ("rgb_scale", f32), ("rgb_shift", f32),
+                ("src_exts", C.c_void_p), ("src_ixts", C.c_void_p), ("src_centers", C.c_void_p),
+                ("tar_center", C.c_void_p), ("render_scale", f32),
+                ("rays12", C.c_void_p), ("z_vals", C.c_void_p), ("xyz", C.c_void_p), ("uvd", C.c_void_p),
+                ("vox_feat", C.c_void_p), ("img_feat", C.c_void_p),
+                ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
+
+
+class VisibilityParams(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("n_pts", i64), ("V", i32), ("view", i32 * MAX_VIEWS),
+                ("src_exts", C.c_void_p), ("src_ixts", C.c_void_p),
+                ("inv_scale_x", f32), ("inv_scale_y", f32),
+                ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
+
+
+class CompositeBlendParams(C.Structure):
+    _fields_ = [("K", i32), ("S", i32), ("R", i64),
+                ("raw", C.c_void_p * MAX_VOLUMES), ("mask", C.c_void_p * MAX_VOLUMES),
+                ("z", C.c_void_p * MAX_VOLUMES),
+                ("rgb", C.c_void_p), ("depth", C.c_void_p), ("weights", C.c_void_p)]
+
+
+class CompositeParams(C.Structure):
+    _fields_ = [("S", i32), ("R", i64), ("raw", C.c_void_p), ("z", C.c_void_p), ("white_bkgd", i32),
+                ("rgb", C.c_void_p), ("depth", C.c_void_p), ("weights", C.c_void_p)]
+
+
+ENTRY_POINTS = {
+    "bmv_cost_volume_var": CostVolumeParams,
+    "bmv_depth_planes_first": DepthPlanesFirstParams,
+    "bmv_depth_planes_next": DepthPlanesNextParams,
+    "bmv_depth_regression": DepthRegressionParams,
+    "bmv_raygen_sample_fetch": RaygenFetchParams,
+    "bmv_mask_viewport": VisibilityParams,
+    "bmv_composite_blend": CompositeBlendParams,
+    "bmv_composite": CompositeParams,
+}
+PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params")
+
+_lib = None
+
+
+class BmvError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libbmv.so (raises if it has not been built: `python -m boostmvsnerfs_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BmvError(f"{LIB_PATH} not found — build it with `python -m boostmvsnerfs_b200.build`; "
+                       "there is no CPU fallback for the rendering kernels")
+    lib = C.CDLL(LIB_PATH)
+    lib.bmv_version.restype = C.c_int
+    lib.bmv_last_error_string.restype = C.c_char_p
+    lib.bmv_launch_count.restype = C.c_uint64
+    lib.bmv_sizeof_params.restype = C.c_int
+    lib.bmv_sizeof_params.argtypes = [C.c_char_p]
+    for name, struct in ENTRY_POINTS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        fn.restype = C.c_int
+        native = lib.bmv_sizeof_params(name.encode())
+        if native != C.sizeof(struct):
+            raise BmvError(f"ABI mismatch for {name}: library struct is {native} B, binding is {C.sizeof(struct)} B")
+    _lib = lib
+    return lib
+
+
+def call(name, params, stream):
+    lib = load()
+    rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
+    if rc != 0:
+        raise BmvError(f"{name} failed with status {rc}: {lib.bmv_last_error_string().decode()}")
+
+
+def launch_count():
+    return int(load().bmv_launch_count())

@@ -1,0 +1,66 @@
+"""Builds libbmv.so (the C-ABI CUDA library, include/bmv.h) in-tree with nvcc for sm_100a.
+
+    python -m boostmvsnerfs_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so stays next to this file (git-ignored, shipped to the
+GPU box with the working tree).
+"""
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbmv.so")
+STAMP = os.path.join(HERE, ".libbmv.stamp")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+         "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177"]
+
+
+def _sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
+            os.path.join(os.path.dirname(HERE), "include", "bmv.h")]:
+        h.update(f.encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in _sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + [f for f in FLAGS if f != "--shared"] + ["-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out:
+            print(out)
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB] + objs + ["-lcudart"])
+    with open(STAMP, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,93 @@
+// Shared host/device helpers for libbmv (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/bmv.h"
+
+namespace bmv {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return BMV_ERR_CUDA_LAUNCH;
+  }
+  return BMV_OK;
+}
+
+#define BMV_REQUIRE(cond, code, ...)      \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::bmv::set_error(__VA_ARGS__);      \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- device helpers
+// Exactly-rounded primitives where the reference has SEPARATE torch ops (no FMA contraction).
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+// 3-term dot product the way an SGEMM inner loop accumulates it (k ascending, acc starts at 0):
+// acc = a0*b0; acc = fma(a1,b1,acc); acc = fma(a2,b2,acc).  Verified bit-identical to torch.bmm
+// on CPU (MKL) — tests/test_oracle_golden.py::test_visibility pins the CPU side.
+__device__ __forceinline__ float dot3_gemm(float a0, float a1, float a2, float b0, float b1, float b2) {
+  float acc = __fmul_rn(a0, b0);
+  acc = __fmaf_rn(a1, b1, acc);
+  acc = __fmaf_rn(a2, b2, acc);
+  return acc;
+}
+__device__ __forceinline__ float dot4_gemm(float a0, float a1, float a2, float a3,
+                                           float b0, float b1, float b2, float b3) {
+  float acc = __fmul_rn(a0, b0);
+  acc = __fmaf_rn(a1, b1, acc);
+  acc = __fmaf_rn(a2, b2, acc);
+  acc = __fmaf_rn(a3, b3, acc);
+  return acc;
+}
+
+// ATen grid_sampler unnormalize with align_corners=True: ((g + 1) / 2) * (size - 1).
+__device__ __forceinline__ float unnormalize_ac(float g, int size) {
+  return mul_rn(div_rn(add_rn(g, 1.f), 2.f), (float)(size - 1));
+}
+
+// A coordinate ATen's CUDA sampler would send to "-100" (non-finite or outside int range).
+__device__ __forceinline__ bool coord_ok(float v) { return fabsf(v) < 1.0e9f; }  // false for NaN/inf
+
+// align_corners=True bilinear upsample source position (ATen upsample_bilinear2d):
+// scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, i1 = i0 + (i0 < in-1), lambda = src-i0.
+struct UpCoord { int i0, i1; float l0, l1; };
+__device__ __forceinline__ UpCoord up_coord(int dst, int in_size, int out_size) {
+  float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  float src = mul_rn(scale, (float)dst);
+  UpCoord u;
+  u.i0 = (int)src;
+  u.i1 = u.i0 + ((u.i0 < in_size - 1) ? 1 : 0);
+  u.l1 = sub_rn(src, (float)u.i0);
+  u.l0 = sub_rn(1.f, u.l1);
+  return u;
+}
+__device__ __forceinline__ float up_sample(const float* __restrict__ m, int w_in, const UpCoord& uy, const UpCoord& ux) {
+  float a = __ldg(m + (int64_t)uy.i0 * w_in + ux.i0), b = __ldg(m + (int64_t)uy.i0 * w_in + ux.i1);
+  float c = __ldg(m + (int64_t)uy.i1 * w_in + ux.i0), d = __ldg(m + (int64_t)uy.i1 * w_in + ux.i1);
+  // ATen: h0l*(w0l*a + w1l*b) + h1l*(w0l*c + w1l*d)
+  float top = add_rn(mul_rn(ux.l0, a), mul_rn(ux.l1, b));
+  float bot = add_rn(mul_rn(ux.l0, c), mul_rn(ux.l1, d));
+  return add_rn(mul_rn(uy.l0, top), mul_rn(uy.l1, bot));
+}
+
+}  // namespace bmv

@@ -1,0 +1,210 @@
+// K1: fused plane-sweep cost volume (homography warp of S source maps + variance) and the
+// depth-hypothesis generators that feed it.  Reference semantics: lib/networks/enerf/utils.py
+// :57-95 (homo_warp), :98-153 (get_depth_values), :324-351 (build_feature_volume).
+#include "bmv_internal.cuh"
+
+namespace bmv {
+
+struct WarpTap {
+  int off[4];     // element offsets (x,y part) of nw, ne, sw, se taps, clamped in-bounds
+  float w[4];     // bilinear weights, 0 for out-of-bounds taps (padding_mode='zeros')
+};
+
+// Homography of pixel (x,y) at depth `dep` into one source map, then ATen's bilinear tap set.
+__device__ __forceinline__ WarpTap homography_taps(const float* __restrict__ P, float x, float y, float dep,
+                                                   int Hs, int Ws, int64_t ys, int64_t xs) {
+  // rot @ [x,y,1] accumulated like the reference's bmm, translation / depth added separately
+  float cx = add_rn(dot3_gemm(P[0], P[1], P[2], x, y, 1.f), div_rn(P[3], dep));
+  float cy = add_rn(dot3_gemm(P[4], P[5], P[6], x, y, 1.f), div_rn(P[7], dep));
+  float cz = add_rn(dot3_gemm(P[8], P[9], P[10], x, y, 1.f), div_rn(P[11], dep));
+  float zc = fmaxf(cz, 1e-6f);
+  if (cz != cz) zc = cz;  // clamp_min propagates NaN
+  float u = div_rn(cx, zc), v = div_rn(cy, zc);
+  float gx = sub_rn(div_rn(u, (float)(Ws - 1) / 2.f), 1.f);
+  float gy = sub_rn(div_rn(v, (float)(Hs - 1) / 2.f), 1.f);
+  float ix = unnormalize_ac(gx, Ws), iy = unnormalize_ac(gy, Hs);
+  WarpTap t;
+  if (!(coord_ok(ix) && coord_ok(iy))) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { t.off[i] = 0; t.w[i] = 0.f; }
+    return t;
+  }
+  float x0 = floorf(ix), y0 = floorf(iy);
+  float x1 = x0 + 1.f, y1 = y0 + 1.f;
+  float wx1 = ix - x0, wx0 = x1 - ix, wy1 = iy - y0, wy0 = y1 - iy;
+  bool vx0 = x0 >= 0.f && x0 <= (float)(Ws - 1), vx1 = x1 >= 0.f && x1 <= (float)(Ws - 1);
+  bool vy0 = y0 >= 0.f && y0 <= (float)(Hs - 1), vy1 = y1 >= 0.f && y1 <= (float)(Hs - 1);
+  int ix0 = min(max((int)x0, 0), Ws - 1), ix1 = min(max((int)x1, 0), Ws - 1);
+  int iy0 = min(max((int)y0, 0), Hs - 1), iy1 = min(max((int)y1, 0), Hs - 1);
+  t.off[0] = (int)(iy0 * ys + ix0 * xs); t.w[0] = (vx0 && vy0) ? wx0 * wy0 : 0.f;
+  t.off[1] = (int)(iy0 * ys + ix1 * xs); t.w[1] = (vx1 && vy0) ? wx1 * wy0 : 0.f;
+  t.off[2] = (int)(iy1 * ys + ix0 * xs); t.w[2] = (vx0 && vy1) ? wx0 * wy1 : 0.f;
+  t.off[3] = (int)(iy1 * ys + ix1 * xs); t.w[3] = (vx1 && vy1) ? wx1 * wy1 : 0.f;
+  return t;
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_out(OutT* p, float v);
+template <>
+__device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// v1: one thread per voxel (flat index over D*h*w, x fastest -> coalesced planar stores),
+// S views x 4 taps gathered per channel straight from L2/L1.
+template <int S, typename OutT>
+__global__ void __launch_bounds__(256) cost_volume_var_kernel(bmv_cost_volume_params p) {
+  __shared__ float sP[S * 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const int64_t nvox = (int64_t)p.D * p.h * p.w;
+  const int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vox >= nvox) return;
+  const int x = (int)(vox % p.w);
+  const int y = (int)((vox / p.w) % p.h);
+  const int d = (int)(vox / ((int64_t)p.w * p.h));
+  const float dep = __ldg(p.planes + (int64_t)d * p.planes_d_stride + ((int64_t)y * p.w + x) * p.planes_pix_stride);
+
+  WarpTap tap[S];
+  const float* base[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    tap[s] = homography_taps(sP + s * 12, (float)x, (float)y, dep, p.Hs, p.Ws, p.feat_y_stride, p.feat_x_stride);
+    base[s] = p.feat + (int64_t)p.view[s] * p.feat_view_stride;
+  }
+  OutT* out = reinterpret_cast<OutT*>(p.out) + (int64_t)d * p.out_d_stride + (int64_t)y * p.out_y_stride +
+              (int64_t)x * p.out_x_stride;
+  const float invS = 1.f;  // division kept exact below
+  (void)invS;
+#pragma unroll 4
+  for (int c = 0; c < p.C; ++c) {
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float* f = base[s] + (int64_t)c * p.feat_c_stride;
+      float v = tap[s].w[0] * __ldg(f + tap[s].off[0]);
+      v = fmaf(tap[s].w[1], __ldg(f + tap[s].off[1]), v);
+      v = fmaf(tap[s].w[2], __ldg(f + tap[s].off[2]), v);
+      v = fmaf(tap[s].w[3], __ldg(f + tap[s].off[3]), v);
+      sum = (s == 0) ? v : add_rn(sum, v);
+      sq = (s == 0) ? mul_rn(v, v) : add_rn(sq, mul_rn(v, v));
+    }
+    float mean = div_rn(sum, (float)S);
+    float var = sub_rn(div_rn(sq, (float)S), mul_rn(mean, mean));
+    store_out<OutT>(out + (int64_t)c * p.out_c_stride, var);
+  }
+}
+
+// ---------------------------------------------------------------- depth hypotheses, level 0
+__global__ void depth_planes_first_kernel(bmv_depth_planes_first_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float nr = __ldg(p.near_far), fr = __ldg(p.near_far + 1);
+  auto plane = [&](int d) {
+    float t = __ldg(p.t + d);
+    if (p.depth_inv) {
+      float dn = div_rn(1.f, nr), df = div_rn(1.f, fr);
+      return div_rn(1.f, add_rn(dn, mul_rn(t, sub_rn(df, dn))));
+    }
+    return add_rn(nr, mul_rn(sub_rn(fr, nr), t));
+  };
+  if (i < p.D) p.planes[i] = plane(i);
+  const int hw = p.h * p.w;
+  if (i < hw) {
+    float a = plane(0), b = plane(p.D - 1);
+    if (p.depth_inv) { a = div_rn(1.f, fmaxf(a, 1e-6f)); b = div_rn(1.f, fmaxf(b, 1e-6f)); }
+    p.near_far_out[i] = a;
+    p.near_far_out[hw + i] = b;
+  }
+}
+
+// ---------------------------------------------------------------- depth hypotheses, level >= 1
+__global__ void depth_planes_next_kernel(bmv_depth_planes_next_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = p.h * p.w;
+  if (i >= hw) return;
+  const int x = i % p.w, y = i / p.w;
+  UpCoord uy = up_coord(y, p.h0, p.h), ux = up_coord(x, p.w0, p.w);
+  const int hw0 = p.h0 * p.w0;
+  float dep = up_sample(p.depth, p.w0, uy, ux);
+  float sd = up_sample(p.std, p.w0, uy, ux);
+  float nf0 = up_sample(p.near_far, p.w0, uy, ux);
+  float nf1 = up_sample(p.near_far + hw0, p.w0, uy, ux);
+  // previous level is in disparity: [d+s, d-s] clamped into [nf0, nf1], then inverted
+  float lo = add_rn(dep, sd), hi = sub_rn(dep, sd);
+  lo = lo > nf0 ? nf0 : lo;
+  hi = hi < nf1 ? nf1 : hi;
+  float nr = div_rn(1.f, lo), fr = div_rn(1.f, hi);
+  float first = 0.f, last = 0.f;
+  for (int d = 0; d < p.D; ++d) {
+    float t = __ldg(p.t + d), v;
+    if (p.cur_inv) {
+      float dn = div_rn(1.f, nr), df = div_rn(1.f, fr);
+      v = div_rn(1.f, add_rn(dn, mul_rn(t, sub_rn(df, dn))));
+    } else {
+      v = add_rn(nr, mul_rn(t, sub_rn(fr, nr)));
+    }
+    p.planes[(int64_t)d * hw + i] = v;
+    if (d == 0) first = v;
+    last = v;
+  }
+  if (p.cur_inv) { first = div_rn(1.f, fmaxf(first, 1e-6f)); last = div_rn(1.f, fmaxf(last, 1e-6f)); }
+  p.near_far_out[i] = first;
+  p.near_far_out[hw + i] = last;
+}
+
+template <typename OutT>
+static int launch_cost_volume(const bmv_cost_volume_params& p, cudaStream_t st) {
+  const int64_t nvox = (int64_t)p.D * p.h * p.w;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ceil_div64(nvox, threads);
+  switch (p.S) {
+    case 1: cost_volume_var_kernel<1, OutT><<<blocks, threads, 0, st>>>(p); break;
+    case 2: cost_volume_var_kernel<2, OutT><<<blocks, threads, 0, st>>>(p); break;
+    case 3: cost_volume_var_kernel<3, OutT><<<blocks, threads, 0, st>>>(p); break;
+    case 4: cost_volume_var_kernel<4, OutT><<<blocks, threads, 0, st>>>(p); break;
+    default:
+      set_error("bmv_cost_volume_var: S=%d views per volume not supported (1..4)", p.S);
+      return BMV_ERR_UNSUPPORTED_SHAPE;
+  }
+  return check_launch("bmv_cost_volume_var");
+}
+
+}  // namespace bmv
+
+extern "C" BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var: null params");
+  BMV_REQUIRE(p->feat && p->proj && p->planes && p->out, BMV_ERR_INVALID_ARGUMENT,
+              "bmv_cost_volume_var: null device pointer");
+  BMV_REQUIRE(p->S >= 1 && p->S <= BMV_MAX_VIEWS && p->C >= 1 && p->Hs >= 1 && p->Ws >= 1 && p->D >= 1 &&
+                  p->h >= 1 && p->w >= 1,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var: non-positive size");
+  for (int s = 0; s < p->S; ++s)
+    BMV_REQUIRE(p->view[s] >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var: negative view index");
+  // tap offsets are kept in 32-bit
+  BMV_REQUIRE((int64_t)p->Hs * llabs(p->feat_y_stride) + (int64_t)p->Ws * llabs(p->feat_x_stride) < (1ll << 31),
+              BMV_ERR_UNSUPPORTED_SHAPE, "bmv_cost_volume_var: source map too large for 32-bit tap offsets");
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->out_bf16 ? launch_cost_volume<__nv_bfloat16>(*p, st) : launch_cost_volume<float>(*p, st);
+}
+
+extern "C" BMV_API int bmv_depth_planes_first(const bmv_depth_planes_first_params* p, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(p && p->near_far && p->t && p->planes && p->near_far_out, BMV_ERR_INVALID_ARGUMENT,
+              "bmv_depth_planes_first: null pointer");
+  BMV_REQUIRE(p->D >= 1 && p->h >= 1 && p->w >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_depth_planes_first: bad size");
+  int n = max(p->D, p->h * p->w);
+  depth_planes_first_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("bmv_depth_planes_first");
+}
+
+extern "C" BMV_API int bmv_depth_planes_next(const bmv_depth_planes_next_params* p, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(p && p->depth && p->std && p->near_far && p->t && p->planes && p->near_far_out,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_depth_planes_next: null pointer");
+  BMV_REQUIRE(p->D >= 1 && p->h >= 1 && p->w >= 1 && p->h0 >= 1 && p->w0 >= 1, BMV_ERR_INVALID_ARGUMENT,
+              "bmv_depth_planes_next: bad size");
+  int n = p->h * p->w;
+  depth_planes_next_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("bmv_depth_planes_next");
+}

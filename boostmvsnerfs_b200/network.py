@@ -1,0 +1,277 @@
+"""Drop-in `Network` classes for the reference's plugin factory.
+
+`BoostEnerfNetwork` mirrors `lib/networks/boost_enerf/network.py:Network` of the reference:
+constructor `Network(preprocess=False)` semantics, sub-module attribute names fixed by the
+checkpoints (`feature_net`, `cost_reg_{i}`, `nerf_{i}`; reference lib/networks/enerf/network.py:14-22),
+`forward(batch) -> {rgb,depth,weights,depth_mvs,std}_level{i}` (reference
+lib/networks/boost_enerf/network.py:172-237).  The per-frame work between the kept NN modules
+runs in the hand-written sm_100a kernels of libbmv (ops.py); there is no CPU / eager fallback.
+
+B200-first differences from the reference's control flow (results unchanged):
+  * the K cost-volume chains advance level by level TOGETHER, so the 3-D CNN and the MLP see one
+    batched call (K volumes / K*R*S samples) instead of K small ones;
+  * no gather copies of the triple's images/features: kernels take base pointers + view ids;
+  * camera algebra (tiny) is hoisted to the top of the frame; nothing inside the frame syncs.
+"""
+import itertools
+import json
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import RenderConfig
+from .modules import CostRegNet, FeatureNet, MinCostRegNet, NeRF
+
+
+def _combinations(n, r):
+    """torch.combinations(arange(n), r) as a host list (lexicographic; reference
+    lib/networks/boost_enerf/network.py:176)."""
+    return list(itertools.combinations(range(n), r))
+
+
+class EnerfNetwork(nn.Module):
+    """Single-volume ENeRF (reference lib/networks/enerf/network.py:11-113)."""
+
+    def __init__(self, rc: RenderConfig = None):
+        super().__init__()
+        self.rc = rc or RenderConfig.enerf_eval(1)
+        self.feature_net = FeatureNet()
+        for i in range(self.rc.num):
+            ch = int(32 * (2 ** (-i)))
+            setattr(self, f'cost_reg_{i}', MinCostRegNet(ch) if i == 0 else CostRegNet(ch))
+            setattr(self, f'nerf_{i}', NeRF(feat_ch=self.rc.nerf_model_feat_ch[i] + 3,
+                                            viewdir_agg=self.rc.viewdir_agg))
+        self.volume_channels_last = False      # emit NDHWC volumes for cuDNN (set by tuning)
+        self.stage_timer = None                # optional callable(name) -> context manager
+
+    # ------------------------------------------------------------------ helpers
+    def _check_mode(self, batch):
+        if self.training:
+            raise RuntimeError("boostmvsnerfs_b200 networks are inference-only (call .eval()); the "
+                               "hand-written kernels have no backward")
+        dev = batch['all_src_inps'].device if 'all_src_inps' in batch else batch['src_inps'].device
+        if dev.type != 'cuda':
+            raise RuntimeError("boostmvsnerfs_b200 has no CPU path: move the batch and the module to a CUDA device")
+
+    def _stage(self, name):
+        if self.stage_timer is None:
+            return _NullCtx()
+        return self.stage_timer(name)
+
+    def forward_feat(self, x):
+        """x (N,3,H,W) -> dict level_{0,1,2} of (N,C,h,w)
+        (reference lib/networks/enerf/network.py:58-67, batch dim squeezed)."""
+        quarter, half, full = self.feature_net(x)
+        return {'level_0': quarter, 'level_1': half, 'level_2': full}
+
+    @staticmethod
+    def _proj_all(exts, ixts, tar_ext, tar_ixt, src_scale, tar_scale):
+        """get_proj_mats for ALL N views at once (reference lib/networks/enerf/utils.py:35-55);
+        same torch ops as the reference (incl. torch.inverse of the 4x4) so the matrices match it."""
+        k_src = ixts.clone()
+        k_src[:, :2] *= src_scale
+        p_src = k_src @ exts[:, :3]                              # (N,3,4)
+        k_tar = tar_ixt.clone()
+        k_tar[:2] *= tar_scale
+        p_tar = k_tar @ tar_ext[:3]
+        last = torch.zeros((1, 4), device=p_tar.device, dtype=p_tar.dtype)
+        last[:, 3] = 1
+        inv = torch.inverse(torch.cat((p_tar, last), dim=0)[None])[0]
+        return (p_src @ inv).contiguous()
+
+    # ------------------------------------------------------------------ the K-chain engine
+    def _render_frame(self, inps, exts, ixts, tar_ext, tar_ixt, near_far, rays_by_level, triples):
+        """One batch element.  inps (N,3,H,W); triples: list of K tuples of view ids.
+        Returns per rendered level: dict(raws, masks, zs lists over K, depth/std of chain 0)."""
+        rc = self.rc
+        K = len(triples)
+        N, _, Hh, Ww = inps.shape
+        dev = inps.device
+        with self._stage('feature_net'):
+            feats = self.forward_feat(inps)
+        with self._stage('camera'):
+            cams = ops.CameraBlock(exts, ixts, tar_ext)
+            projs = [self._proj_all(exts, ixts, tar_ext, tar_ixt, rc.im_feat_scale[i], rc.volume_scale[i])
+                     for i in range(rc.num)]
+        depth = std = nf = None              # per chain lists
+        out = {}
+        for i in range(rc.num):
+            D, vs = rc.volume_planes[i], rc.volume_scale[i]
+            h, w = int(Hh * vs), int(Ww * vs)
+            f = feats[f'level_{i}']
+            C = f.shape[1]
+            with self._stage(f'cost_volume_l{i}'):
+                if self.volume_channels_last:
+                    vols = torch.empty((K, D, h, w, C), device=dev).permute(0, 4, 1, 2, 3)
+                else:
+                    vols = torch.empty((K, C, D, h, w), device=dev)
+                if depth is None:
+                    planes0, nf0 = ops.depth_planes_first(near_far, D, h, w, rc.depth_inv[i])
+                    planes = [planes0] * K
+                    nf = [nf0] * K
+                    for k in range(K):
+                        ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
+                else:
+                    planes, nf_new = [], []
+                    for k in range(K):
+                        pl, nfk = ops.depth_planes_next(depth[k], std[k], nf[k], D, h, w, rc.depth_inv[i])
+                        planes.append(pl)
+                        nf_new.append(nfk)
+                        ops.cost_volume_var(f, triples[k], projs[i], pl, out=vols[k])
+                    nf = nf_new
+            with self._stage(f'cost_reg_{i}'):
+                feat_vol, logits = getattr(self, f'cost_reg_{i}')(vols)
+                del vols
+            with self._stage(f'depth_regression_l{i}'):
+                depth, std = [], []
+                for k in range(K):
+                    d, s = ops.depth_regression(logits[k], planes[k], rc.depth_inv[i])
+                    depth.append(d)
+                    std.append(s)
+            if not rc.render_if[i]:
+                continue
+            out[i] = self._render_level(i, feats, inps, feat_vol, depth, std, nf, rays_by_level[i], cams,
+                                        triples, Hh, Ww)
+            out[i]['depth0'], out[i]['std0'] = depth[0], std[0]
+        return out
+
+    def _render_level(self, i, feats, inps, feat_vol, depth, std, nf, rays, cams, triples, Hh, Ww):
+        rc = self.rc
+        K = len(triples)
+        S = rc.num_samples[i]
+        rs = rc.render_scale[i]
+        H, W = int(Hh * rs), int(Ww * rs)
+        im_feat = feats[f'level_{rc.render_im_feat_level[i]}']
+        up = rs / rc.im_ibr_scale[i]
+        if up != 1.:   # never taken by the shipped configs (reference boost_enerf/network.py:128-131)
+            im_feat = torch.nn.functional.interpolate(
+                im_feat, size=(int(im_feat.shape[-2] * up), int(im_feat.shape[-1] * up)),
+                align_corners=True, mode='bilinear')
+        if rs == 1.:
+            rgb, affine = inps, (0.5, 0.5)          # unpreprocess folded into the fetch
+        else:          # level-0 rendering of the pre-train configs: resized colours (enerf/utils.py:669-676)
+            rgb = torch.nn.functional.interpolate(inps * 0.5 + 0.5, size=(H, W), align_corners=True, mode='bilinear')
+            affine = (1.0, 0.0)
+        R = rays.shape[0]
+        dev = rays.device
+        nerf = getattr(self, f'nerf_{i}')
+        V, Cf, Cv = len(triples[0]), im_feat.shape[1], feat_vol.shape[1]
+        raw_all = torch.empty((K, R, S, 4), device=dev)
+        mask_all = torch.empty((K, R, S), device=dev)
+        z_all = torch.empty((K, R, S), device=dev)
+        for r0 in range(0, R, rc.chunk_size):
+            n = min(rc.chunk_size, R - r0)
+            vox = torch.empty((K, n * S, Cv), device=dev)
+            img = torch.empty((K, n * S, V, Cf + 7), device=dev)
+            with self._stage(f'raygen_fetch_l{i}'):
+                for k in range(K):
+                    ops.raygen_sample_fetch(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S,
+                                            feat_vol[k], im_feat, rgb, cams, triples[k], render_scale=rs,
+                                            rgb_affine=affine, ray_begin=r0, n_rays=n, want=(),
+                                            out={'z_vals': z_all[k, r0:r0 + n], 'vis_mask': mask_all[k, r0:r0 + n],
+                                                 'vox_feat': vox[k], 'img_feat': img[k]})
+            with self._stage(f'nerf_{i}'):
+                net = nerf(vox, img)                                     # (K, n*S, 4)
+                del vox, img
+                if n == R:
+                    raw_all = net.view(K, R, S, 4)
+                else:
+                    raw_all[:, r0:r0 + n] = net.view(K, n, S, 4)
+        return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
+
+    # ------------------------------------------------------------------ public API
+    def forward(self, batch):
+        self._check_mode(batch)
+        rc = self.rc
+        inps = batch['src_inps']
+        B, N = inps.shape[:2]
+        ret = {}
+        per_b = []
+        with torch.no_grad():
+            for b in range(B):
+                lv = self._render_frame(inps[b], batch['src_exts'][b], batch['src_ixts'][b], batch['tar_ext'][b],
+                                        batch['tar_ixt'][b], batch['near_far'][b],
+                                        [batch[f'rays_{i}'][b] for i in range(rc.num)], [tuple(range(N))])
+                per_b.append(lv)
+            for i in range(rc.num):
+                if not rc.render_if[i]:
+                    continue
+                rgb, dep, wts, dmvs, sd = [], [], [], [], []
+                for lv in per_b:
+                    with self._stage(f'composite_l{i}'):
+                        r, d, w = ops.composite(lv[i]['raws'][0], lv[i]['zs'][0], rc.white_bkgd)
+                    rgb.append(r); dep.append(d); wts.append(w)
+                    dmvs.append(1. / lv[i]['depth0'] if rc.depth_inv[i] else lv[i]['depth0'])
+                    sd.append(lv[i]['std0'])
+                ret.update({f'rgb_level{i}': torch.stack(rgb), f'depth_level{i}': torch.stack(dep),
+                            f'weights_level{i}': torch.stack(wts), f'depth_mvs_level{i}': torch.stack(dmvs),
+                            f'std_level{i}': torch.stack(sd)})
+        return ret
+
+
+class BoostEnerfNetwork(EnerfNetwork):
+    """ENeRF + BoostMVSNeRFs K-volume blend (reference lib/networks/boost_enerf/network.py:10-237)."""
+
+    def __init__(self, preprocess=False, rc: RenderConfig = None, view_selection_file=None):
+        super().__init__(rc or RenderConfig.enerf_eval())
+        self.view_selection_outputs = {}
+        if not preprocess:
+            # reference lib/networks/boost_enerf/network.py:14-20: the JSON written by the
+            # view-selection pre-process is mandatory (the reference `raise`s a str -> TypeError)
+            if view_selection_file is None or not os.path.exists(view_selection_file):
+                raise FileNotFoundError("View selection file not found. Please run view selection first.")
+            with open(view_selection_file, 'r') as fh:
+                self.view_selection_outputs = json.load(fh)
+
+    def forward(self, batch):
+        self._check_mode(batch)
+        rc = self.rc
+        inps = batch['all_src_inps']
+        B, N = inps.shape[:2]
+        I, K = rc.cost_volume_input_views, rc.k_best
+        table = _combinations(N, I)
+        scenes, views = batch['meta']['scene'], batch['meta']['tar_view']
+        k_best = [self.view_selection_outputs[f'{s}_{v}'] for s, v in zip(scenes, views)]
+        ret = {}
+        per_b = []
+        with torch.no_grad():
+            for b in range(B):
+                triples = [table[int(j)] for j in k_best[b][:K]]
+                if len(triples) != K:
+                    raise ValueError(f"view selection for {scenes[b]}_{views[b]} holds {len(triples)} volumes, "
+                                     f"cfg.enerf.cas_config.k_best is {K}")
+                per_b.append(self._render_frame(inps[b], batch['all_src_exts'][b], batch['all_src_ixts'][b],
+                                                batch['tar_ext'][b], batch['tar_ixt'][b], batch['near_far'][b],
+                                                [batch[f'rays_{i}'][b] for i in range(rc.num)], triples))
+            # the reference leaves the LAST triple in the batch (evaluators read batch['src_inps'].shape)
+            last = torch.tensor([table[int(k_best[b][K - 1])] for b in range(B)], device=inps.device)
+            bidx = torch.arange(B, device=inps.device).unsqueeze(-1).expand(-1, I)
+            batch['src_inps'] = inps[bidx, last]
+            batch['src_exts'] = batch['all_src_exts'][bidx, last]
+            batch['src_ixts'] = batch['all_src_ixts'][bidx, last]
+            if rc.white_bkgd:
+                raise NotImplementedError   # reference lib/networks/enerf/utils.py:660-661
+            for i in range(rc.num):
+                if not rc.render_if[i]:
+                    continue
+                rgb, dep, wts, dmvs, sd = [], [], [], [], []
+                for lv in per_b:
+                    with self._stage(f'composite_blend_l{i}'):
+                        r, d, w = ops.composite_blend(lv[i]['raws'], lv[i]['masks'], lv[i]['zs'])
+                    rgb.append(r); dep.append(d); wts.append(w)
+                    dmvs.append(1. / lv[i]['depth0'] if rc.depth_inv[i] else lv[i]['depth0'])
+                    sd.append(lv[i]['std0'])
+                ret.update({f'rgb_level{i}': torch.stack(rgb), f'depth_level{i}': torch.stack(dep),
+                            f'weights_level{i}': torch.stack(wts), f'depth_mvs_level{i}': torch.stack(dmvs),
+                            f'std_level{i}': torch.stack(sd)})
+        return ret
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -1,0 +1,381 @@
+"""Torch-facing wrappers of the libbmv C ABI (include/bmv.h).
+
+PyTorch is used for device memory and streams only: every function allocates its outputs with
+torch, extracts raw device pointers, fills the POD params struct and enqueues the kernel on the
+current CUDA stream.  Inputs must already live on the GPU; nothing here has a CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BmvError, MAX_VIEWS, MAX_VOLUMES
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
+        raise BmvError(f"{name}: expected a CUDA float32 tensor, got "
+                       f"{type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}")
+    return t
+
+
+def _cf32(t, name):
+    return _f32(t, name).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _views(arr_type_holder, views):
+    if len(views) > MAX_VIEWS:
+        raise BmvError(f"at most {MAX_VIEWS} views per volume, got {len(views)}")
+    for i, v in enumerate(views):
+        arr_type_holder[i] = int(v)
+
+
+_linspace_cache = {}
+
+
+def _linspace(n, device):
+    # taken from torch so that the fractions carry torch's own rounding
+    key = (n, str(device))
+    if key not in _linspace_cache:
+        _linspace_cache[key] = torch.linspace(0., 1., n, device=device, dtype=torch.float32)
+    return _linspace_cache[key]
+
+
+# ------------------------------------------------------------------------------------------ K1
+def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float32, channels_last=False):
+    """Fused plane-sweep cost volume for ONE batch element.
+
+    feats  (N,C,Hs,Ws) feature maps of all views, any strides (NCHW or channels_last)
+    views  list of S view indices forming this volume
+    proj   (N,3,4) homographies of ALL views, indexed by view id like `feats`
+           (get_proj_mats, reference lib/networks/enerf/utils.py:35-55)
+    planes (D,h,w) per-pixel hypotheses or (D,) shared
+    -> (C,D,h,w) variance volume (reference lib/networks/enerf/utils.py:324-351)
+    """
+    _f32(feats, "feats")
+    proj = _cf32(proj, "proj")
+    planes = _cf32(planes, "planes")
+    N, Cc, Hs, Ws = feats.shape
+    S = len(views)
+    assert proj.shape == (N, 3, 4), proj.shape
+    p = _lib.CostVolumeParams()
+    p.feat = feats.data_ptr()
+    p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
+    _views(p.view, views)
+    p.S, p.C, p.Hs, p.Ws = S, Cc, Hs, Ws
+    p.proj, p.planes = proj.data_ptr(), planes.data_ptr()
+    if planes.dim() == 1:
+        raise BmvError("shared planes need the volume size: pass planes.view(D,1,1).expand(D,h,w) "
+                       "or use cost_volume_var_shared")
+    D, h, w = planes.shape
+    p.planes_d_stride, p.planes_pix_stride = h * w, 1
+    p.D, p.h, p.w = D, h, w
+    return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
+
+
+def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dtype=torch.float32,
+                           channels_last=False):
+    """Same as cost_volume_var with D hypotheses shared by every pixel (cascade level 0)."""
+    _f32(feats, "feats")
+    proj = _cf32(proj, "proj")
+    planes_d = _cf32(planes_d, "planes")
+    N, Cc, Hs, Ws = feats.shape
+    S = len(views)
+    p = _lib.CostVolumeParams()
+    p.feat = feats.data_ptr()
+    p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
+    _views(p.view, views)
+    p.S, p.C, p.Hs, p.Ws = S, Cc, Hs, Ws
+    p.proj, p.planes = proj.data_ptr(), planes_d.data_ptr()
+    D = planes_d.numel()
+    p.planes_d_stride, p.planes_pix_stride = 1, 0
+    p.D, p.h, p.w = D, h, w
+    return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
+
+
+def _cost_volume_launch(p, Cc, D, h, w, device, out, out_dtype, channels_last):
+    if out is None:
+        if channels_last:   # physical (D,h,w,C), logical (C,D,h,w)
+            out = torch.empty((D, h, w, Cc), device=device, dtype=out_dtype).permute(3, 0, 1, 2)
+        else:
+            out = torch.empty((Cc, D, h, w), device=device, dtype=out_dtype)
+    assert out.shape == (Cc, D, h, w) and out.dtype in (torch.float32, torch.bfloat16)
+    p.out = out.data_ptr()
+    p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride()
+    p.out_bf16 = 1 if out.dtype == torch.bfloat16 else 0
+    _lib.call("bmv_cost_volume_var", p, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a3
+def depth_planes_first(near_far, D, h, w, depth_inv):
+    """near_far (2,) -> planes (D,), near_far_out (2,h,w)
+    (reference lib/networks/enerf/utils.py:103-111,149-153)."""
+    near_far = _cf32(near_far, "near_far")
+    dev = near_far.device
+    t = _linspace(D, dev)
+    planes = torch.empty(D, device=dev)
+    nf = torch.empty((2, h, w), device=dev)
+    p = _lib.DepthPlanesFirstParams()
+    p.near_far, p.t = near_far.data_ptr(), t.data_ptr()
+    p.D, p.h, p.w, p.depth_inv = D, h, w, int(depth_inv)
+    p.planes, p.near_far_out = planes.data_ptr(), nf.data_ptr()
+    _lib.call("bmv_depth_planes_first", p, _stream())
+    return planes, nf
+
+
+def depth_planes_next(depth, std, near_far, D, h, w, cur_inv):
+    """depth/std (h0,w0), near_far (2,h0,w0) [disparities] -> planes (D,h,w), near_far_out (2,h,w)
+    (reference lib/networks/enerf/utils.py:112-153)."""
+    depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
+    dev = depth.device
+    h0, w0 = depth.shape
+    t = _linspace(D, dev)
+    planes = torch.empty((D, h, w), device=dev)
+    nf = torch.empty((2, h, w), device=dev)
+    p = _lib.DepthPlanesNextParams()
+    p.depth, p.std, p.near_far, p.t = depth.data_ptr(), std.data_ptr(), near_far.data_ptr(), t.data_ptr()
+    p.h0, p.w0, p.h, p.w, p.D, p.cur_inv = h0, w0, h, w, D, int(cur_inv)
+    p.planes, p.near_far_out = planes.data_ptr(), nf.data_ptr()
+    _lib.call("bmv_depth_planes_next", p, _stream())
+    return planes, nf
+
+
+# ------------------------------------------------------------------------------------------ K2
+def depth_regression(logits, planes, depth_inv):
+    """logits (D,h,w); planes (D,h,w) or (D,) -> depth (h,w), std (h,w)
+    (reference lib/networks/enerf/utils.py:722-727)."""
+    logits, planes = _cf32(logits, "logits"), _cf32(planes, "planes")
+    D, h, w = logits.shape
+    dev = logits.device
+    depth = torch.empty((h, w), device=dev)
+    std = torch.empty((h, w), device=dev)
+    p = _lib.DepthRegressionParams()
+    p.logits, p.planes = logits.data_ptr(), planes.data_ptr()
+    if planes.dim() == 1:
+        assert planes.numel() == D
+        p.planes_d_stride, p.planes_pix_stride = 1, 0
+    else:
+        assert planes.shape == (D, h, w)
+        p.planes_d_stride, p.planes_pix_stride = h * w, 1
+    p.D, p.h, p.w, p.depth_inv = D, h, w, int(depth_inv)
+    p.depth, p.std = depth.data_ptr(), std.data_ptr()
+    _lib.call("bmv_depth_regression", p, _stream())
+    return depth, std
+
+
+# ------------------------------------------------------------------------------------------ K3
+class CameraBlock:
+    """Device-resident camera data of one frame (all N source views + target centre)."""
+
+    def __init__(self, src_exts, src_ixts, tar_ext):
+        self.exts = _cf32(src_exts, "src_exts")            # (N,4,4)
+        self.ixts = _cf32(src_ixts, "src_ixts")            # (N,3,3)
+        # camera centres exactly as the reference gets them: inverse(ext)[:3,3]
+        # (reference lib/networks/enerf/utils.py:771-772)
+        self.centers = torch.stack([e.inverse()[:3, 3] for e in self.exts]).contiguous()
+        self.tar_center = tar_ext.inverse()[:3, 3].contiguous()
+
+
+def raygen_sample_fetch(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat, rgb, cams, views,
+                        render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None,
+                        want=("z_vals", "vox_feat", "img_feat", "vis_mask"), out=None):
+    """Fused K3 for one cost-volume chain of one batch element.
+
+    depth,std (hv,wv); near_far (2,hv,wv); rays (R,8); volume (Cv,Dv,hv,wv) any strides;
+    im_feat (N,Cf,Hf,Wf) any strides; rgb (N,3,Hf,Wf) contiguous; cams CameraBlock; views triple.
+    Returns a dict with the requested outputs among
+    rays12 (n,12), z_vals (n,S), xyz (n,S,3), uvd (n,S,3), vox_feat (n*S,Cv), img_feat (n*S,V,Cf+7),
+    vis_mask (n,S) fp32, vis_count (n,S) int32.  `out` may hold preallocated contiguous tensors for
+    some of them (written in place, e.g. slices of a K-stacked buffer).
+    """
+    depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
+    rays = _cf32(rays, "rays")
+    dev = rays.device
+    R = rays.shape[0]
+    n = R - ray_begin if n_rays is None else n_rays
+    assert rays.shape[1] == 8 and 0 <= ray_begin and ray_begin + n <= R
+    hv, wv = depth.shape
+    V = len(views)
+    p = _lib.RaygenFetchParams()
+    p.depth, p.std, p.near_far = depth.data_ptr(), std.data_ptr(), near_far.data_ptr()
+    p.hv, p.wv, p.H, p.W, p.depth_inv = hv, wv, H, W, int(depth_inv)
+    p.rays, p.ray_begin, p.n_rays = rays.data_ptr(), ray_begin, n
+    t = _linspace(S, dev) if S > 1 else None
+    p.t, p.S = (t.data_ptr() if t is not None else 0), S
+    out = dict(out) if out else {}
+    _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_affine, want)
+    _alloc_fetch_outputs(p, out, want, n, S, V, dev, p.Cv, p.Cf)
+    _lib.call("bmv_raygen_sample_fetch", p, _stream())
+    return out
+
+
+def _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_affine, want):
+    V = len(views)
+    p.V = V
+    _views(p.view, views)
+    if volume is not None:
+        _f32(volume, "volume")
+        p.volume = volume.data_ptr()
+        p.Cv, p.Dv = volume.shape[0], volume.shape[1]
+        p.vol_c_stride, p.vol_d_stride, p.vol_y_stride, p.vol_x_stride = volume.stride()
+        if p.hv == 0:
+            p.hv, p.wv = volume.shape[2], volume.shape[3]
+    if im_feat is not None:
+        _f32(im_feat, "im_feat")
+        rgb = _cf32(rgb, "rgb")
+        p.im_feat = im_feat.data_ptr()
+        p.Cf, p.Hf, p.Wf = im_feat.shape[1], im_feat.shape[2], im_feat.shape[3]
+        p.imf_view_stride, p.imf_c_stride, p.imf_y_stride, p.imf_x_stride = im_feat.stride()
+        assert rgb.shape[1:] == (3, p.Hf, p.Wf), (rgb.shape, p.Hf, p.Wf)
+        p.rgb, p.rgb_view_stride = rgb.data_ptr(), rgb.stride(0)
+        p.rgb_scale, p.rgb_shift = rgb_affine
+        p._keep = (rgb,)
+    p.src_exts, p.src_ixts = cams.exts.data_ptr(), cams.ixts.data_ptr()
+    p.src_centers, p.tar_center = cams.centers.data_ptr(), cams.tar_center.data_ptr()
+    p.render_scale = render_scale
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+def _alloc_fetch_outputs(p, out, want, n, S, V, dev, Cv, Cf):
+    def mk(name, shape, dtype=torch.float32):
+        if name in out:
+            t = out[name]
+            if not (t.is_cuda and t.dtype == dtype and t.is_contiguous() and t.numel() == _numel(shape)):
+                raise BmvError(f"preallocated output {name}: need contiguous {dtype} with {_numel(shape)} elements")
+            setattr(p, name, t.data_ptr())
+        elif name in want:
+            out[name] = torch.empty(shape, device=dev, dtype=dtype)
+            setattr(p, name, out[name].data_ptr())
+    mk("rays12", (n, 12))
+    mk("z_vals", (n, S))
+    mk("xyz", (n, S, 3))
+    mk("uvd", (n, S, 3))
+    mk("vox_feat", (n * S, Cv))
+    mk("img_feat", (n * S, V, Cf + 7))
+    mk("vis_mask", (n, S))
+    mk("vis_count", (n, S), torch.int32)
+
+
+def sample_rays12(rays12, S, depth_inv, H, W, want=("xyz", "uvd", "z_vals")):
+    """sample_along_depth on rays that already carry their interval
+    (reference lib/networks/enerf/utils.py:424-443).  rays12 (R,12)."""
+    rays12 = _cf32(rays12, "rays12")
+    dev = rays12.device
+    n = rays12.shape[0]
+    p = _lib.RaygenFetchParams()
+    p.rays12_in, p.ray_begin, p.n_rays = rays12.data_ptr(), 0, n
+    p.H, p.W, p.hv, p.wv, p.depth_inv = H, W, 1, 1, int(depth_inv)
+    t = _linspace(S, dev) if S > 1 else None
+    p.t, p.S = (t.data_ptr() if t is not None else 0), S
+    p.V = 1
+    dummy = torch.zeros(16, device=dev)
+    p.src_exts = p.src_ixts = dummy.data_ptr()
+    out = {}
+    _alloc_fetch_outputs(p, out, want, n, S, 1, dev, 0, 0)
+    _lib.call("bmv_raygen_sample_fetch", p, _stream())
+    return out
+
+
+def fetch_points(xyz, uvd_norm, H, W, volume, im_feat, rgb, cams, views, render_scale=1.0,
+                 rgb_affine=(0.5, 0.5), want=("vox_feat", "img_feat", "vis_mask")):
+    """Pointwise mode: xyz (P,3) world points, uvd_norm (P,3) in [0,1] (needed for vox_feat).
+    Function-level get_vox_feat / get_img_feat / mask_viewport on arbitrary points."""
+    xyz = _cf32(xyz, "xyz")
+    dev = xyz.device
+    n = xyz.shape[0]
+    p = _lib.RaygenFetchParams()
+    p.xyz_in, p.n_rays, p.S = xyz.data_ptr(), n, 1
+    if uvd_norm is not None:
+        uvd_norm = _cf32(uvd_norm, "uvd_norm")
+        p.uvd_in = uvd_norm.data_ptr()
+    p.H, p.W = H, W
+    out = {}
+    _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_affine, want)
+    if p.hv == 0:
+        p.hv = p.wv = 1
+    _alloc_fetch_outputs(p, out, want, n, 1, len(views), dev, p.Cv, p.Cf)
+    _lib.call("bmv_raygen_sample_fetch", p, _stream())
+    return out
+
+
+def mask_viewport(xyz, src_exts, src_ixts, views, inv_scale, want_count=False):
+    """xyz (P,3); src_exts (N,4,4); src_ixts (N,3,3); inv_scale (W-1,H-1) ->
+    fp32 mask (P,) in {0,1/V,..,1} [and int32 count] (reference lib/networks/enerf/utils.py:490-520)."""
+    xyz = _cf32(xyz, "xyz")
+    src_exts, src_ixts = _cf32(src_exts, "src_exts"), _cf32(src_ixts, "src_ixts")
+    n = xyz.shape[0]
+    dev = xyz.device
+    mask = torch.empty(n, device=dev)
+    count = torch.empty(n, device=dev, dtype=torch.int32) if want_count else None
+    p = _lib.VisibilityParams()
+    p.xyz, p.n_pts, p.V = xyz.data_ptr(), n, len(views)
+    _views(p.view, views)
+    p.src_exts, p.src_ixts = src_exts.data_ptr(), src_ixts.data_ptr()
+    p.inv_scale_x, p.inv_scale_y = float(inv_scale[0]), float(inv_scale[1])
+    p.vis_mask = mask.data_ptr()
+    p.vis_count = count.data_ptr() if want_count else 0
+    _lib.call("bmv_mask_viewport", p, _stream())
+    return (mask, count) if want_count else mask
+
+
+# ------------------------------------------------------------------------------------------ K4
+def composite_blend(raws, masks, zs):
+    """K-volume visibility-weighted compositing.  raws: K tensors (R,S,4); masks, zs: K tensors (R,S)
+    (UN-normalised visibility scores; the 1/sum normalisation of merge_mlp_outputs happens in-kernel).
+    -> rgb (R,3), depth (R,), weights (R,S)
+    (reference lib/networks/boost_enerf/network.py:163-170, lib/networks/enerf/utils.py:639-667)."""
+    K = len(raws)
+    if not (1 <= K <= MAX_VOLUMES and len(masks) == K and len(zs) == K):
+        raise BmvError(f"composite_blend: need 1..{MAX_VOLUMES} volumes with matching lists")
+    raws = [_cf32(r, "raw") for r in raws]
+    masks = [_cf32(m, "mask") for m in masks]
+    zs = [_cf32(z, "z") for z in zs]
+    R, S = raws[0].shape[0], raws[0].shape[1]
+    dev = raws[0].device
+    rgb = torch.empty((R, 3), device=dev)
+    depth = torch.empty((R,), device=dev)
+    weights = torch.empty((R, S), device=dev)
+    p = _lib.CompositeBlendParams()
+    p.K, p.S, p.R = K, S, R
+    for k in range(K):
+        assert raws[k].shape == (R, S, 4) and masks[k].shape == (R, S) and zs[k].shape == (R, S)
+        p.raw[k], p.mask[k], p.z[k] = raws[k].data_ptr(), masks[k].data_ptr(), zs[k].data_ptr()
+    p.rgb, p.depth, p.weights = rgb.data_ptr(), depth.data_ptr(), weights.data_ptr()
+    _lib.call("bmv_composite_blend", p, _stream())
+    return rgb, depth, weights
+
+
+def composite(raw, z, white_bkgd=False):
+    """Single-volume compositing.  raw (R,S,4), z (R,S) or None -> rgb, depth (None if z is None), weights
+    (reference lib/networks/enerf/utils.py:605-637)."""
+    raw = _cf32(raw, "raw")
+    R, S = raw.shape[:2]
+    dev = raw.device
+    rgb = torch.empty((R, 3), device=dev)
+    depth = torch.empty((R,), device=dev) if z is not None else None
+    weights = torch.empty((R, S), device=dev)
+    p = _lib.CompositeParams()
+    p.S, p.R, p.raw = S, R, raw.data_ptr()
+    if z is not None:
+        z = _cf32(z, "z")
+        p.z = z.data_ptr()
+    p.white_bkgd = int(bool(white_bkgd))
+    p.rgb, p.weights = rgb.data_ptr(), weights.data_ptr()
+    p.depth = depth.data_ptr() if depth is not None else 0
+    _lib.call("bmv_composite", p, _stream())
+    return rgb, depth, weights

@@ -1,0 +1,218 @@
+/*
+ * bmv.h — C ABI of the B200-native (sm_100a) BoostMVSNeRFs per-frame rendering kernels.
+ *
+ * Drop-in boundary: the reference has no native code; its "operator interface" for
+ * this path is the set of pure Python renderer functions in lib/networks/enerf/utils.py and
+ * lib/networks/boost_enerf/network.py.  Each entry point below replaces one or more of those
+ * functions (cited per entry as reference file:line) and is what a ctypes binding on the reference
+ * side would bind.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers, sizes, element strides and scalars; no torch types.
+ *  - the caller owns every buffer; the library never allocates, frees or keeps a pointer after
+ *    the enqueue returns.
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); no host syncs; every entry
+ *    is CUDA-graph capturable; the caller selects the device (cudaSetDevice) beforehand.
+ *  - return value: BMV_OK (0) or a negative bmv_status; bmv_last_error_string() gives detail
+ *    (thread-local).  No C++ exception crosses the ABI.
+ *  - all tensors are fp32 and contiguous in the stated layout unless strides are given.
+ *    Strides are in ELEMENTS.
+ *  - camera matrices are read from DEVICE memory (they change every frame; keeping them out of
+ *    the kernel parameters keeps a captured graph replayable).
+ */
+#ifndef BMV_H_
+#define BMV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BMV_API __attribute__((visibility("default")))
+#else
+#define BMV_API
+#endif
+
+#define BMV_VERSION 100          /* 0.1.0 */
+#define BMV_MAX_VIEWS 8          /* source views per cost volume (reference uses 3) */
+#define BMV_MAX_VOLUMES 16       /* K cost volumes blended per frame */
+
+typedef enum bmv_status {
+  BMV_OK = 0,
+  BMV_ERR_INVALID_ARGUMENT = -1,
+  BMV_ERR_UNSUPPORTED_SHAPE = -2,
+  BMV_ERR_CUDA_LAUNCH = -3,
+  BMV_ERR_NOT_IMPLEMENTED = -4
+} bmv_status;
+
+typedef void* bmv_stream_t;      /* cudaStream_t */
+
+BMV_API int bmv_version(void);
+BMV_API const char* bmv_last_error_string(void);
+/* Number of kernel launches enqueued by this library in the calling process so far
+ * (bench.py reports the per-step delta as "gpu_launches"). */
+BMV_API uint64_t bmv_launch_count(void);
+/* sizeof() of the params struct of entry point `entry` ("bmv_cost_volume_var", ...), -1 if unknown:
+ * lets a foreign-language binding verify its struct layout at load time. */
+BMV_API int bmv_sizeof_params(const char* entry);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  cost-volume build: per-plane homography warp of S source feature maps + variance.
+ * Replaces homo_warp + build_feature_volume (reference lib/networks/enerf/utils.py:57-95,324-351).
+ *   vol[c,d,y,x] = (sum_s f_s^2)/S - ((sum_s f_s)/S)^2,
+ *   f_s = bilinear_zeros(feat_s[c], homography_s(x, y, planes[d,y,x]))
+ * The S maps are addressed as feat + view[s]*feat_view_stride (no gather copy of the triple,
+ * cf. reference lib/networks/boost_enerf/network.py:196-201).
+ */
+typedef struct bmv_cost_volume_params {
+  const float* feat;            /* source feature maps of ALL views */
+  int64_t feat_view_stride;     /* elements between consecutive views */
+  int64_t feat_c_stride, feat_y_stride, feat_x_stride; /* NCHW: Hs*Ws, Ws, 1; NHWC: 1, Ws*C, C */
+  int32_t view[BMV_MAX_VIEWS];  /* which views form this volume */
+  int32_t S, C, Hs, Ws;         /* views per volume, channels, source map size */
+  const float* proj;            /* DEVICE (N,3,4) row-major, indexed by view[s] like feat:
+                                   src_proj @ inv(tar_proj) of get_proj_mats */
+  const float* planes;          /* DEVICE depth hypotheses */
+  int64_t planes_d_stride;      /* h*w for per-pixel planes (B,D,h,w); 1 with planes_pix_stride 0 for (D,) */
+  int64_t planes_pix_stride;    /* 1 for per-pixel planes, 0 when every pixel shares the D values */
+  int32_t D, h, w;              /* volume size */
+  float* out;                   /* (C,D,h,w) with the strides below */
+  int64_t out_c_stride, out_d_stride, out_y_stride, out_x_stride;
+  int32_t out_bf16;             /* 0: fp32 out, 1: out points to bf16 storage (round-to-nearest-even) */
+} bmv_cost_volume_params;
+BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  depth hypotheses.
+ * bmv_depth_planes_first: reference lib/networks/enerf/utils.py:103-111,149-153 — D planes shared by
+ *   all pixels: planes (D,) and near_far (2,h,w).  `t` = torch.linspace(0,1,D) (DEVICE, taken from
+ *   torch rather than recomputed so both sides share the same rounding).
+ * bmv_depth_planes_next: reference lib/networks/enerf/utils.py:112-153 — bilinear (align_corners)
+ *   upsample of the previous level's depth/std/near_far (disparities), clamp, invert, per-pixel planes.
+ */
+typedef struct bmv_depth_planes_first_params {
+  const float* near_far;        /* DEVICE (2,) scene near, far */
+  const float* t;               /* DEVICE (D,) */
+  int32_t D, h, w, depth_inv;
+  float* planes;                /* (D,) */
+  float* near_far_out;          /* (2,h,w) */
+} bmv_depth_planes_first_params;
+BMV_API int bmv_depth_planes_first(const bmv_depth_planes_first_params* p, bmv_stream_t stream);
+
+typedef struct bmv_depth_planes_next_params {
+  const float* depth;           /* (h0,w0) previous level expectation (a disparity) */
+  const float* std;             /* (h0,w0) */
+  const float* near_far;        /* (2,h0,w0) previous level near/far (disparities) */
+  const float* t;               /* DEVICE (D,) */
+  int32_t h0, w0, h, w, D, cur_inv;
+  float* planes;                /* (D,h,w) */
+  float* near_far_out;          /* (2,h,w) */
+} bmv_depth_planes_next_params;
+BMV_API int bmv_depth_planes_next(const bmv_depth_planes_next_params* p, bmv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  depth regression: softmax over D, expectation and standard deviation.
+ * Replaces depth_regression (reference lib/networks/enerf/utils.py:722-727).
+ */
+typedef struct bmv_depth_regression_params {
+  const float* logits;          /* (D,h,w) */
+  const float* planes;          /* per-pixel (D,h,w) or shared (D,) */
+  int64_t planes_d_stride, planes_pix_stride;
+  int32_t D, h, w, depth_inv;
+  float* depth;                 /* (h,w) */
+  float* std;                   /* (h,w) */
+} bmv_depth_regression_params;
+BMV_API int bmv_depth_regression(const bmv_depth_regression_params* p, bmv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  depth-guided ray generation + sampling + feature fetch + 3-D visibility, fused.
+ * Replaces build_rays, sample_along_depth, get_vox_feat, unpreprocess(scale 1), get_img_feat,
+ * get_ndc_coords, mask_viewport (reference lib/networks/enerf/utils.py:392-443,458-460,490-520,
+ * 669-676,753-786) and the glue of render_rays (reference lib/networks/boost_enerf/network.py:123-149).
+ * One launch handles rays [ray_begin, ray_begin+n_rays) of one cost-volume chain.
+ */
+typedef struct bmv_raygen_fetch_params {
+  /* per-pixel maps at VOLUME resolution (hv,wv), upsampled on the fly to the render grid (H,W) */
+  const float* depth; const float* std; const float* near_far;   /* (hv,wv),(hv,wv),(2,hv,wv) */
+  int32_t hv, wv, H, W;         /* H,W = render grid = int(H_img*render_scale) */
+  int32_t depth_inv;            /* cfg.enerf.cas_config.depth_inv[level] */
+  const float* rays;            /* (R,8) [o,d,x,y] */
+  int64_t ray_begin, n_rays;
+  /* alternative input modes for function-level use (normally NULL):
+   *   rays12_in (R,12): rays that already carry [ray_near ray_far vol_near vol_far] (sample_along_depth)
+   *   xyz_in (n_rays,3) [+ uvd_in (n_rays,3) normalised to [0,1]]: explicit points, one per "ray", S ignored
+   *     (get_vox_feat / get_img_feat / mask_viewport on arbitrary points) */
+  const float* rays12_in; const float* xyz_in; const float* uvd_in;
+  const float* t; int32_t S;    /* DEVICE (S,) sample fractions; S==1 -> midpoint (t ignored) */
+  /* regularised feature volume (Cv=8 channels) */
+  const float* volume; int32_t Cv, Dv;                 /* spatial size = (hv,wv) */
+  int64_t vol_c_stride, vol_d_stride, vol_y_stride, vol_x_stride;
+  /* per-view image features + colours */
+  int32_t V; int32_t view[BMV_MAX_VIEWS];
+  const float* im_feat; int32_t Cf; int32_t Hf, Wf;    /* (N,Cf,Hf,Wf)-like with strides below */
+  int64_t imf_view_stride, imf_c_stride, imf_y_stride, imf_x_stride;
+  const float* rgb;             /* (N,3,Hf,Wf) planar */
+  int64_t rgb_view_stride;
+  float rgb_scale, rgb_shift;   /* colour = rgb*scale+shift (0.5,0.5 folds unpreprocess; 1,0 if pre-resized) */
+  /* cameras, DEVICE memory */
+  const float* src_exts;        /* (N,4,4) world->cam */
+  const float* src_ixts;        /* (N,3,3) full-resolution intrinsics (visibility uses them unscaled) */
+  const float* src_centers;     /* (N,3) = inverse(ext)[:3,3] */
+  const float* tar_center;      /* (3,) */
+  float render_scale;           /* intrinsics rows 0,1 scaled by this for the colour fetch */
+  /* outputs (any may be NULL to skip) */
+  float* rays12;                /* (n_rays,12)  build_rays output */
+  float* z_vals;                /* (n_rays,S) */
+  float* xyz;                   /* (n_rays,S,3) */
+  float* uvd;                   /* (n_rays,S,3) [pixel x, pixel y, normalised depth] */
+  float* vox_feat;              /* (n_rays*S,Cv) */
+  float* img_feat;              /* (n_rays*S,V,Cf+3+4) */
+  float* vis_mask;              /* (n_rays,S) fp32 count/V */
+  int32_t* vis_count;           /* (n_rays,S) integer count */
+} bmv_raygen_fetch_params;
+BMV_API int bmv_raygen_sample_fetch(const bmv_raygen_fetch_params* p, bmv_stream_t stream);
+
+/* Stand-alone 3-D visibility of given world points (op-level parity with mask_viewport,
+ * reference lib/networks/enerf/utils.py:490-520). */
+typedef struct bmv_visibility_params {
+  const float* xyz; int64_t n_pts;                     /* (n_pts,3) */
+  int32_t V; int32_t view[BMV_MAX_VIEWS];
+  const float* src_exts; const float* src_ixts;        /* (N,4,4), (N,3,3) DEVICE */
+  float inv_scale_x, inv_scale_y;                      /* (W-1, H-1) */
+  float* vis_mask; int32_t* vis_count;                 /* (n_pts,) each, either may be NULL */
+} bmv_visibility_params;
+BMV_API int bmv_mask_viewport(const bmv_visibility_params* p, bmv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  alpha compositing.
+ * bmv_composite_blend replaces merge_mlp_outputs + raw2outputs_blend (reference
+ *   lib/networks/boost_enerf/network.py:163-170, lib/networks/enerf/utils.py:639-667): takes K
+ *   pointers, no stacking.  Also emits the visibility-weighted 2-D coverage when asked.
+ * bmv_composite replaces raw2outputs (reference lib/networks/enerf/utils.py:605-637).
+ */
+typedef struct bmv_composite_blend_params {
+  int32_t K, S; int64_t R;
+  const float* raw[BMV_MAX_VOLUMES];    /* each (R,S,4) [rgb,sigma] */
+  const float* mask[BMV_MAX_VOLUMES];   /* each (R,S) un-normalised visibility score */
+  const float* z[BMV_MAX_VOLUMES];      /* each (R,S) */
+  float* rgb;                           /* (R,3) */
+  float* depth;                         /* (R,) */
+  float* weights;                       /* (R,S) */
+} bmv_composite_blend_params;
+BMV_API int bmv_composite_blend(const bmv_composite_blend_params* p, bmv_stream_t stream);
+
+typedef struct bmv_composite_params {
+  int32_t S; int64_t R;
+  const float* raw;                     /* (R,S,4) */
+  const float* z;                       /* (R,S) or NULL */
+  int32_t white_bkgd;
+  float* rgb; float* depth; float* weights;
+} bmv_composite_params;
+BMV_API int bmv_composite(const bmv_composite_params* p, bmv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMV_H_ */

@@ -1,0 +1,275 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against
+  (1) the golden vectors produced by the UNMODIFIED reference (tests/golden, oracle/gen_golden.py),
+  (2) the CPU oracle (oracle/enerf_oracle.py) on fresh seeded inputs.
+
+Tolerances (north_star): bit-exact for ray indices, sample counts and visibility counts; fp32
+values within 1e-4 relative.  "Relative" is taken against the tensor's dynamic range
+(|a-b| <= 1e-4 * max|ref|) plus elementwise rtol 1e-4, because interpolated noise features
+cross zero.
+"""
+import numpy as np
+import pytest
+import torch
+
+from boostmvsnerfs_b200.config import RenderConfig
+from conftest import load_golden
+from oracle import enerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+H, W = 64, 96
+TRIPLE = [0, 1, 2]
+RTOL = 1e-4
+
+
+def close(a, b, what, rtol=RTOL, scale=None):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    scale = float(np.abs(b).max()) if scale is None else scale
+    err = np.abs(a - b)
+    tol = rtol * scale + rtol * np.abs(b)
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{a.size} outside tolerance; max abs err {err.max():.3e} "
+                           f"(scale {scale:.3e}), worst at {np.unravel_index(err.argmax(), err.shape)}")
+    return float(err.max())
+
+
+def exact(a, b, what):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    n = int((a != b).sum())
+    assert n == 0, f"{what}: {n}/{a.size} entries differ"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from boostmvsnerfs_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def g():
+    return load_golden("enerf_ops.npz")
+
+
+def _cams(ops, g):
+    return ops.CameraBlock(g.t("in_src_exts", "cuda")[0], g.t("in_src_ixts", "cuda")[0], g.t("in_tar_ext", "cuda")[0])
+
+
+# ------------------------------------------------------------------------------------------ K1 / a3 / K2
+def test_depth_planes_vs_reference(ops, g):
+    planes, nf = ops.depth_planes_first(g.t("in_near_far", "cuda")[0], 64, H // 8, W // 8, True)
+    close(planes, g.np("planes_l0")[0, :, 0, 0], "planes l0", rtol=1e-6)
+    close(nf, g.np("near_far_l0")[0], "near_far l0", rtol=1e-6)
+    planes1, nf1 = ops.depth_planes_next(g.t("depth_l0", "cuda")[0], g.t("std_l0", "cuda")[0],
+                                         g.t("near_far_l0", "cuda")[0], 8, H // 2, W // 2, False)
+    close(planes1, g.np("planes_l1")[0], "planes l1", rtol=2e-6)
+    close(nf1, g.np("near_far_l1")[0], "near_far l1", rtol=2e-6)
+
+
+@pytest.mark.parametrize("channels_last_in", [False, True])
+@pytest.mark.parametrize("channels_last_out", [False, True])
+def test_cost_volume_vs_reference(ops, g, channels_last_in, channels_last_out):
+    for lvl, (feat_key, planes_key) in enumerate([("in_feat0", "planes_l0"), ("in_feat1", "planes_l1")]):
+        feats = g.t(feat_key, "cuda")[0]
+        if channels_last_in:
+            feats = feats.contiguous(memory_format=torch.channels_last)
+        proj = g.t(f"proj_mats_l{lvl}", "cuda")[0]
+        planes = g.t(planes_key, "cuda")[0]
+        vol = ops.cost_volume_var(feats, TRIPLE, proj, planes, channels_last=channels_last_out)
+        close(vol, g.np(f"volume_l{lvl}")[0], f"cost volume l{lvl}")
+        if lvl == 0:     # shared-plane entry must agree with the per-pixel one bit for bit
+            vol_s = ops.cost_volume_var_shared(feats, TRIPLE, proj, planes[:, 0, 0].contiguous(), H // 8, W // 8)
+            exact(vol_s, vol, "shared planes == per-pixel planes")
+
+
+def test_cost_volume_view_indexing_and_bf16(ops, g):
+    feats = g.t("in_feat1", "cuda")[0]
+    proj = g.t("proj_mats_l1", "cuda")[0]
+    planes = g.t("planes_l1", "cuda")[0]
+    ref = ops.cost_volume_var(feats, TRIPLE, proj, planes)
+    # same triple addressed inside a larger view table: no gather copy needed
+    big = torch.randn(5, *feats.shape[1:], device="cuda")
+    bigp = torch.randn(5, 3, 4, device="cuda")
+    idx = [4, 0, 2]
+    for j, v in enumerate(idx):
+        big[v], bigp[v] = feats[j], proj[j]
+    exact(ops.cost_volume_var(big, idx, bigp, planes), ref, "view-indexed volume")
+    bf = ops.cost_volume_var(feats, TRIPLE, proj, planes, out_dtype=torch.bfloat16)
+    assert bf.dtype == torch.bfloat16
+    exact(bf, ref.to(torch.bfloat16), "bf16 volume == rn(fp32 volume)")
+    close(bf, ref, "bf16 volume", rtol=1e-2)
+
+
+def test_cost_volume_identical_views_has_zero_variance(ops, g):
+    feats = g.t("in_feat1", "cuda")[0][:1].repeat(3, 1, 1, 1)
+    proj = g.t("proj_mats_l1", "cuda")[0][:1].repeat(3, 1, 1)
+    vol = ops.cost_volume_var(feats, TRIPLE, proj, g.t("planes_l1", "cuda")[0])
+    assert float(vol.abs().max()) < 1e-5
+
+
+def test_depth_regression_vs_reference(ops, g):
+    d, s = ops.depth_regression(g.t("in_logits0", "cuda")[0], g.t("planes_l0", "cuda")[0], True)
+    close(d, g.np("depth_l0")[0], "depth l0", rtol=1e-5)
+    close(s, g.np("std_l0")[0], "std l0")
+    d2, s2 = ops.depth_regression(g.t("in_logits0", "cuda")[0], g.t("planes_l0", "cuda")[0, :, 0, 0].contiguous(), True)
+    exact(d2, d, "shared-plane regression"); exact(s2, s, "shared-plane regression std")
+    d, s = ops.depth_regression(g.t("in_logits1", "cuda")[0], g.t("planes_l1", "cuda")[0], False)
+    close(d, g.np("depth_l1")[0], "depth l1", rtol=1e-5)
+    close(s, g.np("std_l1")[0], "std l1")
+
+
+# ------------------------------------------------------------------------------------------ K3
+def _fused(ops, g, lvl, want):
+    cams = _cams(ops, g)
+    if lvl == 1:
+        S, inv, rs, hv, wv = 2, False, 1.0, H // 2, W // 2
+        im_feat, rgb, affine = g.t("in_imfeat2", "cuda")[0], g.t("in_src_inps", "cuda")[0], (0.5, 0.5)
+        vol = g.t("in_regvol1", "cuda")[0]
+    else:
+        S, inv, rs, hv, wv = 8, True, 0.25, H // 8, W // 8
+        im_feat, rgb, affine = g.t("in_feat0", "cuda")[0], g.t("unpreprocess_l0", "cuda")[0], (1.0, 0.0)
+        vol = g.t("in_regvol0", "cuda")[0]
+    Hr, Wr = int(H * rs), int(W * rs)
+    return ops.raygen_sample_fetch(g.t(f"depth_l{lvl}", "cuda")[0], g.t(f"std_l{lvl}", "cuda")[0],
+                                   g.t(f"near_far_l{lvl}", "cuda")[0], g.t(f"in_rays_{lvl}", "cuda")[0],
+                                   Hr, Wr, inv, S, vol, im_feat, rgb, cams, TRIPLE, render_scale=rs,
+                                   rgb_affine=affine, want=want)
+
+
+@pytest.mark.parametrize("lvl", [1, 0])
+def test_fused_raygen_fetch_vs_reference(ops, g, lvl):
+    want = ("rays12", "z_vals", "xyz", "uvd", "vox_feat", "img_feat", "vis_mask", "vis_count")
+    o = _fused(ops, g, lvl, want)
+    r12 = g.np(f"rays12_l{lvl}")[0]
+    exact(o["rays12"][:, :8], r12[:, :8], "ray origin/direction/pixel passthrough")
+    exact(o["rays12"][:, 6:8].long(), torch.from_numpy(r12[:, 6:8]).long(), "ray pixel indices")
+    close(o["rays12"][:, 8:], r12[:, 8:], "ray/volume near-far", rtol=2e-6)
+    close(o["z_vals"], g.np(f"z_l{lvl}")[0], "z_vals", rtol=2e-6)
+    close(o["xyz"], g.np(f"xyz_l{lvl}")[0], "xyz", rtol=1e-5)
+    exact(o["uvd"][..., :2], g.np(f"uvd_l{lvl}")[0][..., :2], "uvd pixel part")
+    close(o["uvd"][..., 2], g.np(f"uvd_l{lvl}")[0][..., 2], "normalised depth", rtol=1e-4, scale=1.0)
+    close(o["vox_feat"], g.np(f"vox_feat_l{lvl}")[0], "vox_feat")
+    close(o["img_feat"], g.np(f"img_feat_l{lvl}")[0], "img_feat_rgb_dir")
+    S = o["z_vals"].shape[1]
+    assert o["z_vals"].shape == (r12.shape[0], S) and o["vox_feat"].shape[0] == r12.shape[0] * S   # sample counts
+    if lvl == 1:
+        exact(o["vis_mask"].reshape(-1), g.np("mask_l1")[0, :, 0], "visibility mask (fp32 value set)")
+        exact(o["vis_count"].float() / 3, o["vis_mask"], "count/V == mask")
+
+
+def test_function_level_modes_match_fused(ops, g):
+    """sample_along_depth / get_vox_feat / get_img_feat / mask_viewport as separate calls on the
+    reference's own intermediate tensors."""
+    cams = _cams(ops, g)
+    r12 = g.t("rays12_l1", "cuda")[0]
+    s = ops.sample_rays12(r12, 2, False, H, W)
+    exact(s["z_vals"], g.np("z_l1")[0], "sample_along_depth z (bit-exact: same separately-rounded ops)")
+    exact(s["xyz"], g.np("xyz_l1")[0], "sample_along_depth xyz")
+    exact(s["uvd"], g.np("uvd_l1")[0], "sample_along_depth uvd")
+    s1 = ops.sample_rays12(r12, 1, False, H, W)
+    exact(s1["z_vals"], g.np("z_l1_s1")[0], "S=1 midpoint z")
+    exact(s1["xyz"], g.np("xyz_l1_s1")[0], "S=1 midpoint xyz")
+    s0 = ops.sample_rays12(g.t("rays12_l0", "cuda")[0], 8, True, H // 4, W // 4)
+    exact(s0["z_vals"], g.np("z_l0")[0], "inverse-depth z")
+    exact(s0["xyz"], g.np("xyz_l0")[0], "inverse-depth xyz")
+    exact(s0["uvd"], g.np("uvd_l0")[0], "inverse-depth uvd")
+    xyz = g.t("xyz_l1", "cuda")[0].reshape(-1, 3)
+    uvd = g.t("uvd_l1", "cuda")[0].reshape(-1, 3).clone()
+    uvd[:, 0] /= (W - 1); uvd[:, 1] /= (H - 1)
+    o = ops.fetch_points(xyz, uvd, H, W, g.t("in_regvol1", "cuda")[0], g.t("in_imfeat2", "cuda")[0],
+                         g.t("in_src_inps", "cuda")[0], cams, TRIPLE, want=("vox_feat", "img_feat", "vis_mask", "vis_count"))
+    close(o["vox_feat"], g.np("vox_feat_l1")[0], "get_vox_feat")
+    close(o["img_feat"], g.np("img_feat_l1")[0], "get_img_feat")
+    exact(o["vis_mask"].reshape(-1), g.np("mask_l1")[0, :, 0], "mask_viewport")
+
+
+def test_visibility_bit_exact_vs_reference(ops, g):
+    wide = g.t("in_xyz_wide", "cuda")[0].reshape(-1, 3)
+    mask, cnt = ops.mask_viewport(wide, g.t("in_src_exts", "cuda")[0], g.t("in_src_ixts", "cuda")[0], TRIPLE,
+                                  (W - 1, H - 1), want_count=True)
+    ref = g.np("mask_wide")[0, :, 0]
+    exact(mask, ref, "visibility mask vs reference")
+    assert sorted(np.unique(cnt.cpu().numpy()).tolist()) == [0, 1, 2, 3]
+    exact(cnt, np.rint(ref * 3).astype(np.int32), "visibility count vs reference")
+
+
+def test_visibility_bit_exact_large_random_cloud(ops):
+    """1M points straddling every frustum face: CUDA kernel == CPU oracle == torch-CUDA op chain."""
+    from boostmvsnerfs_b200.synth import make_scene
+    sc = make_scene(H=544, W=960, n_views=6, seed=1, render_scales=())
+    gen = torch.Generator().manual_seed(5)
+    pts = (torch.rand(1, 500000, 2, 3, generator=gen) - 0.5) * torch.tensor([16.0, 10.0, 24.0]) + torch.tensor([0, 0, 4.0])
+    views = [1, 3, 5]
+    exts, ixts = sc["all_src_exts"][:, views], sc["all_src_ixts"][:, views]
+    inv = torch.tensor([[959.0, 543.0]])
+    ref_cpu = O.visibility_count(pts, exts, ixts, inv)[0]
+    ref_gpu = O.visibility_count(pts.cuda(), exts.cuda(), ixts.cuda(), inv.cuda())[0]
+    _, cnt = ops.mask_viewport(pts.cuda().reshape(-1, 3), sc["all_src_exts"][0].cuda(), sc["all_src_ixts"][0].cuda(),
+                               views, (959.0, 543.0), want_count=True)
+    exact(cnt, ref_cpu, "kernel vs CPU oracle")
+    exact(cnt, ref_gpu, "kernel vs torch-CUDA op chain (reference GPU path)")
+    hist = torch.bincount(cnt.long().cpu(), minlength=4)
+    assert (hist > 1000).all(), f"cloud must populate every count: {hist.tolist()}"
+
+
+# ------------------------------------------------------------------------------------------ K4
+def test_composite_blend_vs_reference(ops, g):
+    raws, masks, zs = g.t("in_blend_raws", "cuda")[0], g.t("in_blend_masks", "cuda")[0], g.t("in_blend_z", "cuda")[0]
+    K = raws.shape[0]
+    rgb, depth, w = ops.composite_blend(list(raws.unbind(0)), list(masks.unbind(0)), list(zs.unbind(0)))
+    close(rgb, g.np("blend_rgb")[0], "blend rgb", rtol=1e-5)
+    close(depth, g.np("blend_depth")[0], "blend depth", rtol=1e-5)
+    close(w, g.np("blend_weights")[0], "blend weights", rtol=1e-5)
+    assert K == 3
+
+
+def test_composite_vs_reference(ops, g):
+    rgb, depth, w = ops.composite(g.t("in_comp_raw", "cuda")[0], g.t("in_comp_z", "cuda")[0])
+    close(rgb, g.np("comp_rgb")[0], "rgb", rtol=1e-5)
+    close(depth, g.np("comp_depth")[0], "depth", rtol=1e-5)
+    close(w, g.np("comp_weights")[0], "weights", rtol=1e-5)
+
+
+@pytest.mark.parametrize("S", [2, 8, 16, 32, 100, 128])
+@pytest.mark.parametrize("K", [1, 4, 8])
+def test_composite_blend_vs_oracle_all_paths(ops, S, K):
+    """serial (S<=16) and warp-scan (S>16) kernels against the CPU oracle, incl. ragged S."""
+    gen = torch.Generator().manual_seed(S * 100 + K)
+    R = 3001
+    raws = torch.rand(1, K, R, S, 4, generator=gen)
+    raws[..., 3] = torch.nn.functional.softplus(torch.randn(1, K, R, S, generator=gen) * 2 - 1)
+    masks = torch.randint(0, 4, (1, K, R, S), generator=gen).float() / 3
+    masks[:, :, :17] = 0
+    zs = torch.sort(torch.rand(1, K, R, S, generator=gen) * 6 + 2, dim=-1).values
+    ref = O.composite_blend(raws, O.merge_masks(masks, K), zs)
+    rgb, depth, w = ops.composite_blend([raws[0, k].cuda() for k in range(K)], [masks[0, k].cuda() for k in range(K)],
+                                        [zs[0, k].cuda() for k in range(K)])
+    close(rgb, ref["rgb"][0], "rgb", rtol=2e-5)
+    close(depth, ref["depth"][0], "depth", rtol=2e-5)
+    close(w, ref["weights"][0], "weights", rtol=2e-5)
+    assert torch.allclose(w.sum(-1), torch.ones(R, device="cuda"), atol=1e-5)   # softmax property
+    if K == 1:
+        ref1 = O.composite(raws[:, 0], zs[:, 0])
+        r1, d1, w1 = ops.composite(raws[0, 0].cuda(), zs[0, 0].cuda())
+        close(r1, ref1["rgb"][0], "single rgb", rtol=2e-5)
+        close(d1, ref1["depth"][0], "single depth", rtol=2e-5)
+        close(w1, ref1["weights"][0], "single weights", rtol=2e-5)
+
+
+def test_composite_edge_cases(ops):
+    e = torch.empty((0, 2, 4), device="cuda")
+    rgb, depth, w = ops.composite(e, torch.empty((0, 2), device="cuda"))
+    assert rgb.shape == (0, 3) and depth.shape == (0,) and w.shape == (0, 2)
+    raw = torch.rand(5, 1, 4, device="cuda")
+    z = torch.rand(5, 1, device="cuda") + 1
+    rgb, depth, w = ops.composite(raw, z)          # S=1: softmax weight is exactly 1, depth == z
+    exact(w, torch.ones_like(w), "single-sample weight")
+    exact(depth, z[:, 0], "single-sample depth")
+    ref = O.composite(raw.cpu()[None], z.cpu()[None], white_bkgd=True)
+    rgbw, _, _ = ops.composite(raw, z, white_bkgd=True)
+    close(rgbw, ref["rgb"][0], "white background", rtol=1e-5)
+    with pytest.raises(Exception):
+        ops.composite_blend([], [], [])
