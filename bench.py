@@ -149,6 +149,7 @@ def algorithmic_bytes(wl, rc):
             reads = 8 * D * h * w * 4 + S_v * (Cf + 3) * Hr * Wr * 4 + 4 * h * w * 4 + R * 8 * 4
             writes = R * S * 8 * 4 + R * S * S_v * (Cf + 7) * 4 + 2 * R * S * 4
             out[f"raygen_fetch_l{i}"] = reads + writes
+            out[f"render_fused_l{i}"] = reads + R * S * (16 + 4 + 4)
             out[f"composite_blend_l{i}"] = R * (K * S * 24 + 12 + 4 + 4 * S)
     return out
 
@@ -327,7 +328,21 @@ def main_ours(args):
             kernels[name] = {"ms_per_launch": per_launch_ms, "launches_per_step": launches_per_stage[name],
                              "algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac": gbs / peak_gbs,
                              "share_of_step": tot_ms / args.steps / ms}
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"]) if kernels else None
+    for name, k in kernels.items():
+        if name.startswith("render_fused"):
+            # the fused gather+MLP kernel is FP32-FMA bound, not HBM bound: 14.6 kFMA per sample
+            # (csrc/nerf_mlp.cuh) against 148 SMs x 128 FMA/clk x clocks.max.sm
+            lvl = int(name[-1])
+            samples = int(wl["H"] * rc.render_scale[lvl]) * int(wl["W"] * rc.render_scale[lvl]) * rc.num_samples[lvl]
+            flops = samples * 2 * 14600.0
+            peak_tf = 148 * 128 * 2 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+            k.update({"bound": "fp32_fma", "tflops": flops / (k["ms_per_launch"] * 1e-3) / 1e12,
+                      "peak_tflops_fp32": peak_tf})
+            k["frac_fp32_peak"] = k["tflops"] / peak_tf
+        else:
+            k["bound"] = "hbm"
+    hbm_kernels = {n: k for n, k in kernels.items() if k["bound"] == "hbm"}
+    dom = max(hbm_kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"]) if hbm_kernels else None
     roofline = None
     if dom:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak_gbs,

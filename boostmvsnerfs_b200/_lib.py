@@ -86,6 +86,15 @@ class CompositeParams(C.Structure):
                 ("rgb", C.c_void_p), ("depth", C.c_void_p), ("weights", C.c_void_p)]
 
 
+class NerfMlpParams(C.Structure):
+    _fields_ = [("vox_feat", C.c_void_p), ("img_feat", C.c_void_p), ("weights", C.c_void_p),
+                ("P", i64), ("feat_ch", i32), ("V", i32), ("raw", C.c_void_p)]
+
+
+class RenderRaysParams(C.Structure):
+    _fields_ = [("g", RaygenFetchParams), ("mlp_weights", C.c_void_p), ("raw", C.c_void_p)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
@@ -95,8 +104,11 @@ ENTRY_POINTS = {
     "bmv_mask_viewport": VisibilityParams,
     "bmv_composite_blend": CompositeBlendParams,
     "bmv_composite": CompositeParams,
+    "bmv_nerf_mlp": NerfMlpParams,
+    "bmv_render_rays": RenderRaysParams,
 }
-PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params")
+PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
+                 "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported")
 
 _lib = None
 
@@ -117,6 +129,10 @@ def load():
     lib.bmv_version.restype = C.c_int
     lib.bmv_last_error_string.restype = C.c_char_p
     lib.bmv_launch_count.restype = C.c_uint64
+    lib.bmv_nerf_mlp_weight_count.restype = C.c_int
+    lib.bmv_nerf_mlp_weight_count.argtypes = [C.c_int]
+    lib.bmv_render_rays_supported.restype = C.c_int
+    lib.bmv_render_rays_supported.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.bmv_sizeof_params.restype = C.c_int
     lib.bmv_sizeof_params.argtypes = [C.c_char_p]
     for name, struct in ENTRY_POINTS.items():

@@ -31,5 +31,7 @@ extern "C" BMV_API int bmv_sizeof_params(const char* entry) {
   if (!strcmp(entry, "bmv_mask_viewport")) return (int)sizeof(bmv_visibility_params);
   if (!strcmp(entry, "bmv_composite_blend")) return (int)sizeof(bmv_composite_blend_params);
   if (!strcmp(entry, "bmv_composite")) return (int)sizeof(bmv_composite_params);
+  if (!strcmp(entry, "bmv_nerf_mlp")) return (int)sizeof(bmv_nerf_mlp_params);
+  if (!strcmp(entry, "bmv_render_rays")) return (int)sizeof(bmv_render_rays_params);
   return -1;
 }

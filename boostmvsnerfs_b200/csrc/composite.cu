@@ -258,9 +258,9 @@ extern "C" BMV_API int bmv_composite_blend(const bmv_composite_blend_params* p, 
   BMV_REQUIRE(p->K >= 1 && p->K <= BMV_MAX_VOLUMES, BMV_ERR_INVALID_ARGUMENT, "bmv_composite_blend: K=%d out of 1..%d",
               p->K, BMV_MAX_VOLUMES);
   BMV_REQUIRE(p->S >= 1 && p->R >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_composite_blend: bad S/R");
+  if (p->R == 0) return BMV_OK;                       // empty ray set: nothing to enqueue
   for (int k = 0; k < p->K; ++k)
     BMV_REQUIRE(p->raw[k] && p->mask[k] && p->z[k], BMV_ERR_INVALID_ARGUMENT, "bmv_composite_blend: null input %d", k);
-  if (p->R == 0) return BMV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->S <= kMaxSerialS) {
     composite_blend_serial_kernel<<<(unsigned)ceil_div64(p->R, 256), 256, 0, st>>>(*p);
@@ -274,9 +274,10 @@ extern "C" BMV_API int bmv_composite_blend(const bmv_composite_blend_params* p, 
 
 extern "C" BMV_API int bmv_composite(const bmv_composite_params* p, bmv_stream_t stream) {
   using namespace bmv;
-  BMV_REQUIRE(p != nullptr && p->raw != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_composite: null input");
+  BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_composite: null params");
   BMV_REQUIRE(p->S >= 1 && p->R >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_composite: bad S/R");
-  if (p->R == 0) return BMV_OK;
+  if (p->R == 0) return BMV_OK;                       // empty ray set: nothing to enqueue
+  BMV_REQUIRE(p->raw != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_composite: null input");
   cudaStream_t st = (cudaStream_t)stream;
   if (p->S <= kMaxSerialS) {
     composite_serial_kernel<<<(unsigned)ceil_div64(p->R, 256), 256, 0, st>>>(*p);

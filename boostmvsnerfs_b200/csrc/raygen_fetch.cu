@@ -2,65 +2,9 @@
 // Reference semantics (lib/networks/enerf/utils.py): build_rays :392-422, sample_along_depth
 // :424-443, get_vox_feat :458-460, get_ndc_coords/mask_viewport :490-520, unpreprocess :669-676,
 // get_img_feat :753-786; glue lib/networks/boost_enerf/network.py:123-149.
-#include "bmv_internal.cuh"
+#include "raygen_common.cuh"
 
 namespace bmv {
-
-struct ViewCam {
-  float E[12];   // rows 0..2 of world->cam
-  float K[9];    // full-resolution intrinsics
-  float c[3];    // camera centre in world space
-};
-
-// ------------------------------------------------------------------ 3-D visibility of one point
-// c = xyz @ R^T (bmm), c += T, q = c @ K^T (bmm), q.xy /= q.z, q.xy /= (W-1,H-1); inside test.
-// Every step is a separately rounded fp32 op in the reference; reproduced 1:1 so the integer
-// count is bit-exact for identical xyz.
-__device__ __forceinline__ bool point_visible(const ViewCam& cam, float x, float y, float z, float isx, float isy) {
-  float cx = add_rn(dot3_gemm(x, y, z, cam.E[0], cam.E[1], cam.E[2]), cam.E[3]);
-  float cy = add_rn(dot3_gemm(x, y, z, cam.E[4], cam.E[5], cam.E[6]), cam.E[7]);
-  float cz = add_rn(dot3_gemm(x, y, z, cam.E[8], cam.E[9], cam.E[10]), cam.E[11]);
-  float qx = dot3_gemm(cx, cy, cz, cam.K[0], cam.K[1], cam.K[2]);
-  float qy = dot3_gemm(cx, cy, cz, cam.K[3], cam.K[4], cam.K[5]);
-  float qz = dot3_gemm(cx, cy, cz, cam.K[6], cam.K[7], cam.K[8]);
-  float u = div_rn(div_rn(qx, qz), isx);
-  float v = div_rn(div_rn(qy, qz), isy);
-  return (u >= 0.f) && (u <= 1.f) && (v >= 0.f) && (v <= 1.f) && (qz > 0.f);
-}
-
-__device__ __forceinline__ void load_cam(ViewCam* dst, const float* exts, const float* ixts, const float* centers,
-                                         int view, int lane) {
-  // 24 values per view, one per thread
-  if (lane < 12) dst->E[lane] = exts[view * 16 + lane];
-  else if (lane < 21) dst->K[lane - 12] = ixts[view * 9 + (lane - 12)];
-  else if (lane < 24) dst->c[lane - 21] = centers ? centers[view * 3 + (lane - 21)] : 0.f;
-}
-
-struct Tap2 { int o00, o01, o10, o11; float w00, w01, w10, w11; };
-
-// bilinear, padding_mode='border', align_corners=True, ATen order of operations
-__device__ __forceinline__ Tap2 border_taps(float gx, float gy, int H, int W, int64_t ys, int64_t xs) {
-  float ix = unnormalize_ac(gx, W), iy = unnormalize_ac(gy, H);
-  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
-  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
-  Tap2 t;
-  float x0 = floorf(ix), y0 = floorf(iy), x1 = x0 + 1.f, y1 = y0 + 1.f;
-  float wx1 = ix - x0, wx0 = x1 - ix, wy1 = iy - y0, wy0 = y1 - iy;
-  bool vx1 = x1 <= (float)(W - 1), vy1 = y1 <= (float)(H - 1);
-  int ix0 = (int)x0, iy0 = (int)y0, ix1 = vx1 ? ix0 + 1 : ix0, iy1 = vy1 ? iy0 + 1 : iy0;
-  t.o00 = (int)(iy0 * ys + ix0 * xs); t.w00 = wx0 * wy0;
-  t.o01 = (int)(iy0 * ys + ix1 * xs); t.w01 = vx1 ? wx1 * wy0 : 0.f;
-  t.o10 = (int)(iy1 * ys + ix0 * xs); t.w10 = vy1 ? wx0 * wy1 : 0.f;
-  t.o11 = (int)(iy1 * ys + ix1 * xs); t.w11 = (vx1 && vy1) ? wx1 * wy1 : 0.f;
-  return t;
-}
-__device__ __forceinline__ float tap2_fetch(const float* __restrict__ f, const Tap2& t) {
-  float v = t.w00 * __ldg(f + t.o00);
-  v = fmaf(t.w01, __ldg(f + t.o01), v);
-  v = fmaf(t.w10, __ldg(f + t.o10), v);
-  v = fmaf(t.w11, __ldg(f + t.o11), v);
-  return v;
-}
 
 // Everything that happens to ONE sample once its world position is known: trilinear volume fetch,
 // per-view colour/feature fetch + direction features, visibility count.
@@ -198,66 +142,25 @@ __global__ void __launch_bounds__(128) raygen_fetch_kernel(bmv_raygen_fetch_para
     return;
   }
 
-  float4 ra, rb;
-  float rn, rf, nf0, nf1;
-  if (p.rays12_in) {
-    const float4* q = reinterpret_cast<const float4*>(p.rays12_in + (p.ray_begin + li) * 12);
-    ra = __ldg(q); rb = __ldg(q + 1);
-    const float4 rc = __ldg(q + 2);
-    rn = rc.x; rf = rc.y; nf0 = rc.z; nf1 = rc.w;
-  } else {
-    const int64_t r = p.ray_begin + li;
-    ra = __ldg(reinterpret_cast<const float4*>(p.rays + r * 8));
-    rb = __ldg(reinterpret_cast<const float4*>(p.rays + r * 8 + 4));
-    int px = (int)rb.z, py = (int)rb.w;                 // .long(): truncation toward zero
-    px = min(max(px, 0), p.W - 1);
-    py = min(max(py, 0), p.H - 1);
-    // ---- build_rays: upsample the per-pixel depth interval to the render grid and clamp it
-    const UpCoord uy = up_coord(py, p.hv, p.H), ux = up_coord(px, p.wv, p.W);
-    const int hwv = p.hv * p.wv;
-    const float dep = up_sample(p.depth, p.wv, uy, ux);
-    const float sd = up_sample(p.std, p.wv, uy, ux);
-    nf0 = up_sample(p.near_far, p.wv, uy, ux);
-    nf1 = up_sample(p.near_far + hwv, p.wv, uy, ux);
-    if (p.depth_inv) {
-      rn = add_rn(dep, sd); rf = sub_rn(dep, sd);
-      rn = rn > nf0 ? nf0 : rn;
-      rf = rf < nf1 ? nf1 : rf;
-    } else {
-      rn = sub_rn(dep, sd); rf = add_rn(dep, sd);
-      rn = rn < nf0 ? nf0 : rn;
-      rf = rf > nf1 ? nf1 : rf;
-    }
-  }
-  const float ox = ra.x, oy = ra.y, oz = ra.z, dx = ra.w, dy = rb.x, dz = rb.y, fx = rb.z, fy = rb.w;
+  const RaySetup r = ray_setup(p, li);
   if (p.rays12) {
     float4* o = reinterpret_cast<float4*>(p.rays12 + li * 12);
-    o[0] = ra; o[1] = rb; o[2] = make_float4(rn, rf, nf0, nf1);
+    o[0] = make_float4(r.ox, r.oy, r.oz, r.dx);
+    o[1] = make_float4(r.dy, r.dz, r.fx, r.fy);
+    o[2] = make_float4(r.rn, r.rf, r.nf0, r.nf1);
   }
   const int S = p.S;
-  const float un = div_rn(fx, (float)(p.W - 1)), vn = div_rn(fy, (float)(p.H - 1));
+  const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
   const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
   const bool need_fetch = p.vox_feat || p.img_feat || p.vis_count || p.vis_mask;
   if (!(need_fetch || p.z_vals || p.xyz || p.uvd)) return;
-
   for (int s = 0; s < S; ++s) {
-    // ---- sample_along_depth
-    const float t = (S == 1) ? 0.5f : __ldg(p.t + s);
-    const float z = add_rn(rn, mul_rn(sub_rn(rf, rn), t));
-    float x, y, zz, dn;
-    if (p.depth_inv) {
-      const float iz = div_rn(1.f, fmaxf(z, 1e-6f));
-      x = add_rn(ox, mul_rn(dx, iz)); y = add_rn(oy, mul_rn(dy, iz)); zz = add_rn(oz, mul_rn(dz, iz));
-      dn = div_rn(sub_rn(nf0, z), fmaxf(sub_rn(nf0, nf1), 1e-6f));
-    } else {
-      x = add_rn(ox, mul_rn(dx, z)); y = add_rn(oy, mul_rn(dy, z)); zz = add_rn(oz, mul_rn(dz, z));
-      dn = div_rn(sub_rn(z, nf0), fmaxf(sub_rn(nf1, nf0), 1e-6f));
-    }
+    const SamplePoint q = sample_point(p, r, s);
     const int64_t si = li * S + s;
-    if (p.z_vals) p.z_vals[si] = z;
-    if (p.xyz) { p.xyz[si * 3] = x; p.xyz[si * 3 + 1] = y; p.xyz[si * 3 + 2] = zz; }
-    if (p.uvd) { p.uvd[si * 3] = fx; p.uvd[si * 3 + 1] = fy; p.uvd[si * 3 + 2] = dn; }
-    if (need_fetch) fetch_sample<MAXV>(p, cams, s_view, s_tar_c, si, x, y, zz, gxv, gyv, dn);
+    if (p.z_vals) p.z_vals[si] = q.z;
+    if (p.xyz) { p.xyz[si * 3] = q.x; p.xyz[si * 3 + 1] = q.y; p.xyz[si * 3 + 2] = q.zz; }
+    if (p.uvd) { p.uvd[si * 3] = r.fx; p.uvd[si * 3 + 1] = r.fy; p.uvd[si * 3 + 2] = q.dn; }
+    if (need_fetch) fetch_sample<MAXV>(p, cams, s_view, s_tar_c, si, q.x, q.y, q.zz, gxv, gyv, q.dn);
   }
 }
 

@@ -1,0 +1,101 @@
+"""Host-side packing of the per-sample MLP weights for the fused kernels (csrc/nerf_mlp.cuh).
+
+The kernel reads every weight as a 16-byte broadcast from shared memory, so each layer is stored
+row by row with the row padded to a multiple of 4 floats and the row's bias (and the weight of the
+following 1-output layer) appended.  Parameter names are the reference's
+(lib/networks/enerf/nerf.py:6-89): agg.view_fc.0, agg.global_fc.0, agg.agg_w_fc.0, agg.fc.0, lr0.0,
+sigma.0, color.0, color.2.
+"""
+import torch
+
+
+def layout(feat_ch):
+    """Offsets (in floats) of each section; mirrors MlpLayout<F> in csrc/nerf_mlp.cuh."""
+    F = feat_ch
+    FP = (F + 3) // 4 * 4
+    FV = F + 4
+    FVP = (FV + 3) // 4 * 4
+    L = dict(F=F, FP=FP, FV=FV, FVP=FVP, GROW=3 * FP + 4, CROW=88 + FVP + 4)
+    L["OFF_VIEW"] = 0
+    L["OFF_GLOB"] = L["OFF_VIEW"] + F * 8
+    L["OFF_AGGB"] = L["OFF_GLOB"] + 32 * L["GROW"]
+    L["OFF_FC"] = L["OFF_AGGB"] + 4
+    L["OFF_FCB"] = L["OFF_FC"] + 32 * 16
+    L["OFF_LR0"] = L["OFF_FCB"] + 16
+    L["OFF_SIGB"] = L["OFF_LR0"] + 64 * 28
+    L["OFF_COL"] = L["OFF_SIGB"] + 4
+    L["OFF_COLB"] = L["OFF_COL"] + 64 * L["CROW"]
+    L["TOTAL"] = L["OFF_COLB"] + 4
+    return L
+
+
+def pack_nerf_weights(nerf):
+    """nerf: a `modules.NeRF` (or the reference's NeRF) -> flat fp32 tensor on the module's device."""
+    sd = {k: v.detach().float() for k, v in nerf.state_dict().items()}
+    if "agg.view_fc.0.weight" not in sd:
+        raise ValueError("fused MLP requires cfg.enerf.viewdir_agg=True (the shipped configs)")
+    F = sd["agg.view_fc.0.weight"].shape[0]
+    if sd["lr0.0.weight"].shape != (64, 24) or sd["color.0.weight"].shape != (64, 88 + F + 4) or len(nerf.lrs) != 0:
+        raise ValueError("unexpected NeRF MLP shape")
+    L = layout(F)
+    dev = sd["lr0.0.weight"].device
+    buf = torch.zeros(L["TOTAL"], dtype=torch.float32, device=dev)
+    FP, GROW, CROW = L["FP"], L["GROW"], L["CROW"]
+    view = buf[L["OFF_VIEW"]:L["OFF_GLOB"]].view(F, 8)
+    view[:, :4] = sd["agg.view_fc.0.weight"]
+    view[:, 4] = sd["agg.view_fc.0.bias"]
+    glob = buf[L["OFF_GLOB"]:L["OFF_AGGB"]].view(32, GROW)
+    wg = sd["agg.global_fc.0.weight"]                    # (32, 3F): [x | var | mean]
+    glob[:, 0:F] = wg[:, 0:F]
+    glob[:, FP:FP + F] = wg[:, F:2 * F]
+    glob[:, 2 * FP:2 * FP + F] = wg[:, 2 * F:3 * F]
+    glob[:, 3 * FP] = sd["agg.global_fc.0.bias"]
+    glob[:, 3 * FP + 1] = sd["agg.agg_w_fc.0.weight"][0]
+    buf[L["OFF_AGGB"]] = sd["agg.agg_w_fc.0.bias"][0]
+    buf[L["OFF_FC"]:L["OFF_FCB"]].view(32, 16).copy_(sd["agg.fc.0.weight"].t())
+    buf[L["OFF_FCB"]:L["OFF_LR0"]] = sd["agg.fc.0.bias"]
+    lr0 = buf[L["OFF_LR0"]:L["OFF_SIGB"]].view(64, 28)
+    lr0[:, :24] = sd["lr0.0.weight"]
+    lr0[:, 24] = sd["lr0.0.bias"]
+    lr0[:, 25] = sd["sigma.0.weight"][0]
+    buf[L["OFF_SIGB"]] = sd["sigma.0.bias"][0]
+    col = buf[L["OFF_COL"]:L["OFF_COLB"]].view(64, CROW)
+    wc = sd["color.0.weight"]                            # (64, 88+F+4)
+    col[:, :88] = wc[:, :88]
+    col[:, 88:88 + F + 4] = wc[:, 88:]
+    col[:, 88 + L["FVP"]] = sd["color.0.bias"]
+    col[:, 88 + L["FVP"] + 1] = sd["color.2.weight"][0]
+    buf[L["OFF_COLB"]] = sd["color.2.bias"][0]
+    return buf
+
+
+def eval_packed(packed, vox, img):
+    """Torch restatement of nerf_mlp_eval() reading the PACKED buffer (layout check on CPU; the
+    product path never calls this).  vox (P,8), img (P,V,F+4) -> (P,4)."""
+    P, V, FV = img.shape
+    F = FV - 4
+    L = layout(F)
+    FP = L["FP"]
+    view = packed[L["OFF_VIEW"]:L["OFF_GLOB"]].view(F, 8)
+    x = img[..., :F] + torch.relu(img[..., F:] @ view[:, :4].t() + view[:, 4])
+    mean = x.mean(1)
+    var = ((x - mean[:, None]) ** 2).sum(1) / (V - 1)
+    glob = packed[L["OFF_GLOB"]:L["OFF_AGGB"]].view(32, L["GROW"])
+    shared = var @ glob[:, FP:FP + F].t() + mean @ glob[:, 2 * FP:2 * FP + F].t() + glob[:, 3 * FP]
+    g = torch.relu(x @ glob[:, :F].t() + shared[:, None])                     # (P,V,32)
+    logit = torch.relu(g @ glob[:, 3 * FP + 1] + packed[L["OFF_AGGB"]])       # (P,V)
+    w = torch.softmax(logit, dim=1)
+    im = (g * w[..., None]).sum(1)
+    fc = packed[L["OFF_FC"]:L["OFF_FCB"]].view(32, 16)
+    pooled = torch.relu(im @ fc + packed[L["OFF_FCB"]:L["OFF_LR0"]])
+    base = torch.cat([vox, pooled], -1)
+    lr0 = packed[L["OFF_LR0"]:L["OFF_SIGB"]].view(64, 28)
+    hid = torch.relu(base @ lr0[:, :24].t() + lr0[:, 24])
+    sig = torch.nn.functional.softplus(hid @ lr0[:, 25] + packed[L["OFF_SIGB"]])
+    col = packed[L["OFF_COL"]:L["OFF_COLB"]].view(64, L["CROW"])
+    shared = torch.cat([hid, base], -1) @ col[:, :88].t() + col[:, 88 + L["FVP"]]
+    a = torch.relu(img @ col[:, 88:88 + FV].t() + shared[:, None])
+    cl = torch.relu(a @ col[:, 88 + L["FVP"] + 1] + packed[L["OFF_COLB"]])
+    beta = torch.softmax(cl, dim=1)
+    rgb = (img[..., F - 3:F] * beta[..., None]).sum(1)
+    return torch.cat([rgb, sig[:, None]], -1)

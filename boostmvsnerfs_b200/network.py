@@ -44,7 +44,9 @@ class EnerfNetwork(nn.Module):
             setattr(self, f'nerf_{i}', NeRF(feat_ch=self.rc.nerf_model_feat_ch[i] + 3,
                                             viewdir_agg=self.rc.viewdir_agg))
         self.volume_channels_last = False      # emit NDHWC volumes for cuDNN (set by tuning)
+        self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
         self.stage_timer = None                # optional callable(name) -> context manager
+        self._packed = {}                      # level -> (param versions, packed weight tensor)
 
     # ------------------------------------------------------------------ helpers
     def _check_mode(self, batch):
@@ -59,6 +61,16 @@ class EnerfNetwork(nn.Module):
         if self.stage_timer is None:
             return _NullCtx()
         return self.stage_timer(name)
+
+    def _packed_mlp(self, i):
+        """Packed weights of nerf_{i} for the fused kernel; re-packed when a parameter changes."""
+        nerf = getattr(self, f'nerf_{i}')
+        key = tuple((p.data_ptr(), p._version) for p in nerf.parameters())
+        hit = self._packed.get(i)
+        if hit is None or hit[0] != key:
+            from .mlp_pack import pack_nerf_weights
+            self._packed[i] = (key, pack_nerf_weights(nerf))
+        return self._packed[i][1]
 
     def forward_feat(self, x):
         """x (N,3,H,W) -> dict level_{0,1,2} of (N,C,h,w)
@@ -161,6 +173,14 @@ class EnerfNetwork(nn.Module):
         raw_all = torch.empty((K, R, S, 4), device=dev)
         mask_all = torch.empty((K, R, S), device=dev)
         z_all = torch.empty((K, R, S), device=dev)
+        if self.fused_mlp and rc.viewdir_agg and ops.render_rays_supported(Cv, Cf, V):
+            packed = self._packed_mlp(i)
+            with self._stage(f'render_fused_l{i}'):
+                for k in range(K):
+                    ops.render_rays(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S, feat_vol[k], im_feat,
+                                    rgb, cams, triples[k], packed, render_scale=rs, rgb_affine=affine,
+                                    out={'raw': raw_all[k], 'z_vals': z_all[k], 'vis_mask': mask_all[k]})
+            return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
         for r0 in range(0, R, rc.chunk_size):
             n = min(rc.chunk_size, R - r0)
             vox = torch.empty((K, n * S, Cv), device=dev)

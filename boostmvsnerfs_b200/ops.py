@@ -379,3 +379,67 @@ def composite(raw, z, white_bkgd=False):
     p.depth = depth.data_ptr() if depth is not None else 0
     _lib.call("bmv_composite", p, _stream())
     return rgb, depth, weights
+
+
+# ------------------------------------------------------------------------------------------ K5
+def nerf_mlp(vox_feat, img_feat, packed_weights):
+    """Fused per-sample MLP.  vox_feat (P,8), img_feat (P,V,feat_ch+4), packed_weights from
+    mlp_pack.pack_nerf_weights -> raw (P,4) [rgb, sigma]
+    (reference lib/networks/enerf/nerf.py:29-43)."""
+    vox_feat, img_feat = _cf32(vox_feat, "vox_feat"), _cf32(img_feat, "img_feat")
+    w = _cf32(packed_weights, "packed_weights")
+    P, V, FV = img_feat.shape
+    n = _lib.load().bmv_nerf_mlp_weight_count(FV - 4)
+    if n != w.numel():
+        raise BmvError(f"nerf_mlp: packed weight length {w.numel()} does not match feat_ch={FV - 4} (expects {n})")
+    assert vox_feat.shape == (P, 8)
+    raw = torch.empty((P, 4), device=vox_feat.device)
+    p = _lib.NerfMlpParams()
+    p.vox_feat, p.img_feat, p.weights = vox_feat.data_ptr(), img_feat.data_ptr(), w.data_ptr()
+    p.P, p.feat_ch, p.V = P, FV - 4, V
+    p.raw = raw.data_ptr()
+    _lib.call("bmv_nerf_mlp", p, _stream())
+    return raw
+
+
+# ------------------------------------------------------------------------------------------ K3+K5
+def render_rays_supported(Cv, Cf, V):
+    return bool(_lib.load().bmv_render_rays_supported(int(Cv), int(Cf), int(V)))
+
+
+def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat, rgb, cams, views, packed_weights,
+                render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False):
+    """Fused per-chain render (K3 gather + per-sample MLP, nothing materialised in HBM).
+    Same inputs as raygen_sample_fetch plus the packed MLP weights.
+    Returns dict(raw (n,S,4), z_vals (n,S), vis_mask (n,S) [, vis_count (n,S) int32]); `out` may
+    supply preallocated contiguous tensors for any of them."""
+    depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
+    rays = _cf32(rays, "rays")
+    w = _cf32(packed_weights, "packed_weights")
+    dev = rays.device
+    R = rays.shape[0]
+    n = R - ray_begin if n_rays is None else n_rays
+    assert rays.shape[1] == 8 and 0 <= ray_begin and ray_begin + n <= R
+    rp = _lib.RenderRaysParams()
+    p = rp.g
+    hv, wv = depth.shape
+    p.depth, p.std, p.near_far = depth.data_ptr(), std.data_ptr(), near_far.data_ptr()
+    p.hv, p.wv, p.H, p.W, p.depth_inv = hv, wv, H, W, int(depth_inv)
+    p.rays, p.ray_begin, p.n_rays = rays.data_ptr(), ray_begin, n
+    t = _linspace(S, dev) if S > 1 else None
+    p.t, p.S = (t.data_ptr() if t is not None else 0), S
+    _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_affine, ())
+    if _lib.load().bmv_nerf_mlp_weight_count(p.Cf + 3) != w.numel():
+        raise BmvError(f"render_rays: packed weight length {w.numel()} does not match feat_ch={p.Cf + 3}")
+    res = dict(out) if out else {}
+    want = ("z_vals", "vis_mask") + (("vis_count",) if want_count else ())
+    _alloc_fetch_outputs(p, res, want, n, S, len(views), dev, p.Cv, p.Cf)
+    if "raw" in res:
+        raw = res["raw"]
+        if not (raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous() and raw.numel() == n * S * 4):
+            raise BmvError("preallocated output raw: need contiguous float32 with n*S*4 elements")
+    else:
+        raw = res["raw"] = torch.empty((n, S, 4), device=dev)
+    rp.mlp_weights, rp.raw = w.data_ptr(), raw.data_ptr()
+    _lib.call("bmv_render_rays", rp, _stream())
+    return res

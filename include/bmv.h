@@ -212,6 +212,38 @@ typedef struct bmv_composite_params {
 } bmv_composite_params;
 BMV_API int bmv_composite(const bmv_composite_params* p, bmv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K5  fused per-sample MLP.
+ * Replaces NeRF.forward + Agg.forward (reference lib/networks/enerf/nerf.py:29-43,73-89) for
+ * feat_ch = nerf_model_feat_ch+3 and V views: one thread per sample, fp32 FMA, weights packed by the
+ * host (layout in csrc/nerf_mlp.cuh; bmv_nerf_mlp_weight_count gives the packed length or -1).
+ */
+typedef struct bmv_nerf_mlp_params {
+  const float* vox_feat;        /* (P,8) */
+  const float* img_feat;        /* (P,V,feat_ch+4) */
+  const float* weights;         /* packed, DEVICE, 16-byte aligned */
+  int64_t P; int32_t feat_ch, V;
+  float* raw;                   /* (P,4) [r,g,b,sigma] */
+} bmv_nerf_mlp_params;
+BMV_API int bmv_nerf_mlp(const bmv_nerf_mlp_params* p, bmv_stream_t stream);
+BMV_API int bmv_nerf_mlp_weight_count(int feat_ch);
+
+/* ------------------------------------------------------------------------------------------
+ * K3+K5 fused per-chain render: ray generation + sampling + gather + visibility + MLP in one launch
+ * (replaces render_rays, reference lib/networks/boost_enerf/network.py:123-149, without ever
+ * materialising vox_feat / img_feat_rgb_dir).  `g` carries the K3 inputs (fused or rays12_in mode);
+ * of its outputs only z_vals, vis_mask and vis_count are honoured.  raw is (n_rays,S,4).
+ * bmv_render_rays_supported tells whether a (Cv,Cf,V) combination is instantiated; callers fall
+ * back to bmv_raygen_sample_fetch + the cuBLAS modules otherwise.
+ */
+typedef struct bmv_render_rays_params {
+  bmv_raygen_fetch_params g;
+  const float* mlp_weights;     /* packed (csrc/nerf_mlp.cuh), DEVICE, 16-byte aligned */
+  float* raw;                   /* (n_rays,S,4) [r,g,b,sigma], 16-byte aligned */
+} bmv_render_rays_params;
+BMV_API int bmv_render_rays(const bmv_render_rays_params* p, bmv_stream_t stream);
+BMV_API int bmv_render_rays_supported(int Cv, int Cf, int V);
+
 #ifdef __cplusplus
 }
 #endif

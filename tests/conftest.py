@@ -16,6 +16,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Keep libbmv.so in step with the sources (nvcc cross-compiles without a GPU); a stale or
+    missing library must never be what the GPU tests exercise."""
+    import shutil
+    from boostmvsnerfs_b200 import build as _build
+    if os.path.exists(_build.NVCC) or shutil.which("nvcc"):
+        _build.build()
+
+
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
         return

@@ -78,6 +78,17 @@ def test_single_volume_forward_vs_reference(strict_fp32):
         _report(out[k], g.np(f"out_{k}"), f"single {k}", 1e-4)
 
 
+def test_fused_and_unfused_network_paths_agree(strict_fp32):
+    g = load_golden("enerf_chain_eval.npz")
+    net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
+    assert net.fused_mlp
+    fused = net(dict(batch))
+    net.fused_mlp = False
+    unfused = net(dict(batch))
+    for k in fused:
+        _report(fused[k], unfused[k].cpu().numpy(), f"fused vs unfused {k}", 2e-5)
+
+
 def test_boost_forward_default_tf32_is_close():
     """torch defaults (cuDNN TF32 convs): the kept CNNs add ~1e-3 noise on both sides of any
     comparison; the frame must still agree with the reference to 1e-2."""
