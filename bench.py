@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--stage-report", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference's op sequence (oracle restatement) as eager PyTorch on this GPU")
     return ap.parse_args()
 
 
@@ -361,6 +363,26 @@ def main_ours(args):
         "stage_ms_per_step": step_ms_stage, "hand_written_ms_per_step": hand_ms,
         "kept_library_ms_per_step": {k: v for k, v in step_ms_stage.items() if k.startswith(("cost_reg", "nerf", "feature"))},
     }
+    if world == 1 and args.torch_gpu_baseline:
+        # the reference's own eager-PyTorch op sequence on the same GPU, batch and weights: the
+        # "reference single-GPU PyTorch path" of north_star; informational.
+        from oracle import enerf_oracle as O
+        kb = torch.tensor([wl["k_best"]], device=dev)
+        with torch.no_grad():
+            for _ in range(2):
+                O.boost_enerf_forward(net, dict(batch), rc, kb)
+            torch.cuda.synchronize()
+            e0.record()
+            n_ref = max(3, min(args.steps, 10))
+            for _ in range(n_ref):
+                O.boost_enerf_forward(net, dict(batch), rc, kb)
+            e1.record()
+            torch.cuda.synchronize()
+        ms_ref = e0.elapsed_time(e1) / n_ref
+        line["torch_gpu_reference_path"] = {"ms_per_step": ms_ref, "value": rays_per_frame / (ms_ref * 1e-3),
+                                            "unit": "rays/s", "steps": n_ref,
+                                            "what": "oracle.boost_enerf_forward (reference op sequence, eager PyTorch, "
+                                                    "cuDNN/cuBLAS defaults) on cuda", "speedup_vs_it": ms_ref / ms}
     if world == 1 and not args.no_cpu_baseline:
         rate, cms, sample, cores = cpu_reference_rate(wl, rc, 1, 0, args.cpu_budget_s)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample,

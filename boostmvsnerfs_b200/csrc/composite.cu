@@ -8,68 +8,47 @@ namespace bmv {
 constexpr int kMaxSerialS = 16;   // rays with <= 16 samples: one thread per ray, registers only
 
 // ---------------------------------------------------------------- K-blend, short rays (ENeRF: S=2..8)
-// One thread per ray.  Inputs are read once: K*S*(16+4+4) B; outputs 12+4+4S B.
+// One thread per ray, nothing indexed by k is kept: per sample the K masks are summed first, then
+// one pass over k accumulates A = sum_k alpha_k w_k, the colour and mean z.  Inputs are read once
+// from HBM (the second mask read hits L1): K*S*(16+4+4) B in, 12+4+4S B out per ray.
+template <int MAXS>
 __global__ void __launch_bounds__(256) composite_blend_serial_kernel(bmv_composite_blend_params p) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= p.R) return;
   const int K = p.K, S = p.S;
+  const float invK = div_rn(1.f, (float)K);
   float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
-  float wts[kMaxSerialS], zm[kMaxSerialS];
-  // reference sums rgb over samples first, then over k: keep per-k partial colours when K is small
-  float pr[BMV_MAX_VOLUMES], pg[BMV_MAX_VOLUMES], pb[BMV_MAX_VOLUMES];
+  float wts[MAXS], zm[MAXS];
 #pragma unroll
-  for (int k = 0; k < BMV_MAX_VOLUMES; ++k) { pr[k] = 0.f; pg[k] = 0.f; pb[k] = 0.f; }
-#pragma unroll
-  for (int s = 0; s < kMaxSerialS; ++s) {
+  for (int s = 0; s < MAXS; ++s) {
     if (s >= S) break;
+    const int64_t i = r * S + s;
     float msum = 0.f;
-    float m[BMV_MAX_VOLUMES];
-#pragma unroll
-    for (int k = 0; k < BMV_MAX_VOLUMES; ++k) {
-      if (k >= K) break;
-      m[k] = __ldg(p.mask[k] + r * S + s);
-      msum = add_rn(msum, m[k]);
+    for (int k = 0; k < K; ++k) msum = add_rn(msum, __ldg(p.mask[k] + i));
+    float A = 0.f, zacc = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float4 raw = __ldg(reinterpret_cast<const float4*>(p.raw[k]) + i);
+      const float wk = msum > 0.f ? div_rn(__ldg(p.mask[k] + i), msum) : invK;
+      const float aw = mul_rn(sub_rn(1.f, expf(-raw.w)), wk);
+      A = add_rn(A, aw);
+      sr = fmaf(aw, raw.x, sr); sg = fmaf(aw, raw.y, sg); sb = fmaf(aw, raw.z, sb);
+      zacc = add_rn(zacc, __ldg(p.z[k] + i));
     }
-    float A = 0.f, zacc = 0.f;
-    float alpha[BMV_MAX_VOLUMES];
-    float4 raw[BMV_MAX_VOLUMES];
-#pragma unroll
-    for (int k = 0; k < BMV_MAX_VOLUMES; ++k) {
-      if (k >= K) break;
-      raw[k] = __ldg(reinterpret_cast<const float4*>(p.raw[k]) + r * S + s);
-      const float wk = msum > 0.f ? div_rn(m[k], msum) : div_rn(1.f, (float)K);
-      m[k] = wk;
-      alpha[k] = sub_rn(1.f, expf(-raw[k].w));
-      A = add_rn(A, mul_rn(alpha[k], wk));
-      zacc = add_rn(zacc, __ldg(p.z[k] + r * S + s));
-    }
-#pragma unroll
-    for (int k = 0; k < BMV_MAX_VOLUMES; ++k) {
-      if (k >= K) break;
-      const float w = mul_rn(mul_rn(T, alpha[k]), m[k]);
-      pr[k] = add_rn(pr[k], mul_rn(w, raw[k].x));
-      pg[k] = add_rn(pg[k], mul_rn(w, raw[k].y));
-      pb[k] = add_rn(pb[k], mul_rn(w, raw[k].z));
-    }
+    cr = fmaf(T, sr, cr); cg = fmaf(T, sg, cg); cb = fmaf(T, sb, cb);
     wts[s] = mul_rn(A, T);
     zm[s] = div_rn(zacc, (float)K);
     T = mul_rn(T, sub_rn(1.f, A));       // cumprod([1, 1-A]) — no epsilon in the blend
   }
-#pragma unroll
-  for (int k = 0; k < BMV_MAX_VOLUMES; ++k) {
-    if (k >= K) break;
-    cr = add_rn(cr, pr[k]); cg = add_rn(cg, pg[k]); cb = add_rn(cb, pb[k]);
-  }
   // weights <- softmax_s(A*T); depth = sum softmax * mean_k z
   float mx = -INFINITY;
 #pragma unroll
-  for (int s = 0; s < kMaxSerialS; ++s) { if (s >= S) break; mx = fmaxf(mx, wts[s]); }
+  for (int s = 0; s < MAXS; ++s) { if (s >= S) break; mx = fmaxf(mx, wts[s]); }
   float den = 0.f;
 #pragma unroll
-  for (int s = 0; s < kMaxSerialS; ++s) { if (s >= S) break; wts[s] = expf(wts[s] - mx); den += wts[s]; }
+  for (int s = 0; s < MAXS; ++s) { if (s >= S) break; wts[s] = expf(wts[s] - mx); den += wts[s]; }
   float depth = 0.f;
 #pragma unroll
-  for (int s = 0; s < kMaxSerialS; ++s) {
+  for (int s = 0; s < MAXS; ++s) {
     if (s >= S) break;
     const float w = div_rn(wts[s], den);
     if (p.weights) p.weights[r * S + s] = w;
@@ -262,8 +241,12 @@ extern "C" BMV_API int bmv_composite_blend(const bmv_composite_blend_params* p, 
   for (int k = 0; k < p->K; ++k)
     BMV_REQUIRE(p->raw[k] && p->mask[k] && p->z[k], BMV_ERR_INVALID_ARGUMENT, "bmv_composite_blend: null input %d", k);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->S <= kMaxSerialS) {
-    composite_blend_serial_kernel<<<(unsigned)ceil_div64(p->R, 256), 256, 0, st>>>(*p);
+  if (p->S <= 2) {
+    composite_blend_serial_kernel<2><<<(unsigned)ceil_div64(p->R, 256), 256, 0, st>>>(*p);
+  } else if (p->S <= 8) {
+    composite_blend_serial_kernel<8><<<(unsigned)ceil_div64(p->R, 256), 256, 0, st>>>(*p);
+  } else if (p->S <= kMaxSerialS) {
+    composite_blend_serial_kernel<kMaxSerialS><<<(unsigned)ceil_div64(p->R, 256), 256, 0, st>>>(*p);
   } else {
     BMV_REQUIRE(p->weights != nullptr, BMV_ERR_INVALID_ARGUMENT,
                 "bmv_composite_blend: weights output is required when S > %d (used as scratch)", kMaxSerialS);

@@ -95,6 +95,72 @@ __global__ void __launch_bounds__(256) cost_volume_var_kernel(bmv_cost_volume_pa
   }
 }
 
+// v2 (channels-last fast path): feature maps stored [H][W][C] and the volume [D][h][w][C]
+// (torch channels_last / channels_last_3d).  CG = C/CPT adjacent lanes share one voxel, each lane
+// owns CPT consecutive channels: every bilinear tap is one 16-byte load per lane and the CG lanes
+// of a voxel read one contiguous 64..128 B segment; the result is one 16-byte store per lane
+// (8-byte for bf16), again contiguous across the voxel's lanes and across x.
+template <int S, int CPT, typename OutT>
+__global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume_params p, int CG) {
+  __shared__ float sP[S * 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const int64_t nvox = (int64_t)p.D * p.h * p.w;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t vox = gid / CG;
+  const int c0 = (int)(gid % CG) * CPT;
+  if (vox >= nvox) return;
+  const int x = (int)(vox % p.w);
+  const int y = (int)((vox / p.w) % p.h);
+  const int d = (int)(vox / ((int64_t)p.w * p.h));
+  const float dep = __ldg(p.planes + (int64_t)d * p.planes_d_stride + ((int64_t)y * p.w + x) * p.planes_pix_stride);
+  float sum[CPT], sq[CPT];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const WarpTap t = homography_taps(sP + s * 12, (float)x, (float)y, dep, p.Hs, p.Ws, p.feat_y_stride, p.feat_x_stride);
+    const float* base = p.feat + (int64_t)p.view[s] * p.feat_view_stride + c0;
+    float v[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT; q += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(base + t.off[0] + q));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(base + t.off[1] + q));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(base + t.off[2] + q));
+      const float4 e = __ldg(reinterpret_cast<const float4*>(base + t.off[3] + q));
+      v[q + 0] = fmaf(t.w[3], e.x, fmaf(t.w[2], c.x, fmaf(t.w[1], b.x, t.w[0] * a.x)));
+      v[q + 1] = fmaf(t.w[3], e.y, fmaf(t.w[2], c.y, fmaf(t.w[1], b.y, t.w[0] * a.y)));
+      v[q + 2] = fmaf(t.w[3], e.z, fmaf(t.w[2], c.z, fmaf(t.w[1], b.z, t.w[0] * a.z)));
+      v[q + 3] = fmaf(t.w[3], e.w, fmaf(t.w[2], c.w, fmaf(t.w[1], b.w, t.w[0] * a.w)));
+    }
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      sum[q] = (s == 0) ? v[q] : add_rn(sum[q], v[q]);
+      sq[q] = (s == 0) ? mul_rn(v[q], v[q]) : add_rn(sq[q], mul_rn(v[q], v[q]));
+    }
+  }
+  float var[CPT];
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) {
+    const float mean = div_rn(sum[q], (float)S);
+    var[q] = sub_rn(div_rn(sq[q], (float)S), mul_rn(mean, mean));
+  }
+  OutT* out = reinterpret_cast<OutT*>(p.out) + (int64_t)d * p.out_d_stride + (int64_t)y * p.out_y_stride +
+              (int64_t)x * p.out_x_stride + c0;
+  if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+    for (int q = 0; q < CPT; q += 4)
+      *reinterpret_cast<float4*>(out + q) = make_float4(var[q], var[q + 1], var[q + 2], var[q + 3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < CPT; q += 4) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(var[q], var[q + 1]), hi = __floats2bfloat162_rn(var[q + 2], var[q + 3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out + q) = pk;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- depth hypotheses, level 0
 __global__ void depth_planes_first_kernel(bmv_depth_planes_first_params p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,21 +218,40 @@ __global__ void depth_planes_next_kernel(bmv_depth_planes_next_params p) {
   p.near_far_out[hw + i] = last;
 }
 
-template <typename OutT>
-static int launch_cost_volume(const bmv_cost_volume_params& p, cudaStream_t st) {
+template <int S, typename OutT>
+static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st) {
   const int64_t nvox = (int64_t)p.D * p.h * p.w;
   const int threads = 256;
-  const unsigned blocks = (unsigned)ceil_div64(nvox, threads);
+  // channels-last fast path: unit channel stride on both sides, 16-byte aligned rows
+  const bool cl = p.feat_c_stride == 1 && p.out_c_stride == 1 && p.C % 4 == 0 && p.feat_x_stride % 4 == 0 &&
+                  p.feat_y_stride % 4 == 0 && p.feat_view_stride % 4 == 0 && ((uintptr_t)p.feat & 15) == 0 &&
+                  p.out_x_stride % 4 == 0 && p.out_y_stride % 4 == 0 && p.out_d_stride % 4 == 0 &&
+                  ((uintptr_t)p.out & (sizeof(OutT) == 4 ? 15 : 7)) == 0;
+  if (cl) {
+    if (p.C % 8 == 0 && p.C >= 32) {
+      const int CG = p.C / 8;
+      cost_volume_var_cl_kernel<S, 8, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
+    } else {
+      const int CG = p.C / 4;
+      cost_volume_var_cl_kernel<S, 4, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
+    }
+  } else {
+    cost_volume_var_kernel<S, OutT><<<(unsigned)ceil_div64(nvox, threads), threads, 0, st>>>(p);
+  }
+  return check_launch("bmv_cost_volume_var");
+}
+
+template <typename OutT>
+static int launch_cost_volume(const bmv_cost_volume_params& p, cudaStream_t st) {
   switch (p.S) {
-    case 1: cost_volume_var_kernel<1, OutT><<<blocks, threads, 0, st>>>(p); break;
-    case 2: cost_volume_var_kernel<2, OutT><<<blocks, threads, 0, st>>>(p); break;
-    case 3: cost_volume_var_kernel<3, OutT><<<blocks, threads, 0, st>>>(p); break;
-    case 4: cost_volume_var_kernel<4, OutT><<<blocks, threads, 0, st>>>(p); break;
+    case 1: return launch_cost_volume_s<1, OutT>(p, st);
+    case 2: return launch_cost_volume_s<2, OutT>(p, st);
+    case 3: return launch_cost_volume_s<3, OutT>(p, st);
+    case 4: return launch_cost_volume_s<4, OutT>(p, st);
     default:
       set_error("bmv_cost_volume_var: S=%d views per volume not supported (1..4)", p.S);
       return BMV_ERR_UNSUPPORTED_SHAPE;
   }
-  return check_launch("bmv_cost_volume_var");
 }
 
 }  // namespace bmv

@@ -22,6 +22,7 @@ import torch.nn as nn
 
 from . import ops
 from .config import RenderConfig
+from .inference_plan import PlanCache
 from .modules import CostRegNet, FeatureNet, MinCostRegNet, NeRF
 
 
@@ -43,8 +44,13 @@ class EnerfNetwork(nn.Module):
             setattr(self, f'cost_reg_{i}', MinCostRegNet(ch) if i == 0 else CostRegNet(ch))
             setattr(self, f'nerf_{i}', NeRF(feat_ch=self.rc.nerf_model_feat_ch[i] + 3,
                                             viewdir_agg=self.rc.viewdir_agg))
-        self.volume_channels_last = False      # emit NDHWC volumes for cuDNN (set by tuning)
+        # call-side preparation of the kept cuDNN modules (inference_plan.py); both are exact up to
+        # fp32 rounding and measured in profiles/round1_conv_variants.md
+        self.fold_bn = True                    # eval-mode BN folded into the convolutions
+        self.channels_last = True              # NHWC / NDHWC activations, volumes emitted channels-last
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
+        self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
+        self._plans = PlanCache()
         self.stage_timer = None                # optional callable(name) -> context manager
         self._packed = {}                      # level -> (param versions, packed weight tensor)
 
@@ -72,10 +78,22 @@ class EnerfNetwork(nn.Module):
             self._packed[i] = (key, pack_nerf_weights(nerf))
         return self._packed[i][1]
 
+    def _kept(self, name):
+        """The cuDNN module `name`, through the inference plan when enabled."""
+        mod = getattr(self, name)
+        if not self.fold_bn:
+            return mod
+        fmt = None
+        if self.channels_last:
+            fmt = torch.channels_last if name == 'feature_net' else torch.channels_last_3d
+        return self._plans.get(name, mod, fmt)
+
     def forward_feat(self, x):
         """x (N,3,H,W) -> dict level_{0,1,2} of (N,C,h,w)
         (reference lib/networks/enerf/network.py:58-67, batch dim squeezed)."""
-        quarter, half, full = self.feature_net(x)
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        quarter, half, full = self._kept('feature_net')(x)
         return {'level_0': quarter, 'level_1': half, 'level_2': full}
 
     @staticmethod
@@ -93,6 +111,34 @@ class EnerfNetwork(nn.Module):
         inv = torch.inverse(torch.cat((p_tar, last), dim=0)[None])[0]
         return (p_src @ inv).contiguous()
 
+    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt):
+        """All per-frame camera algebra, hoisted: homographies of every view for every cascade level
+        and the camera centres.  With host_camera_algebra the ~1 KB of camera data makes one
+        round trip to the host and the reference's own torch op sequence (incl. torch.inverse,
+        LAPACK) runs there: ~40 tiny GPU launches and ~9 stream syncs become one copy each way."""
+        rc = self.rc
+        N = exts.shape[0]
+        dev = exts.device
+        if not self.host_camera_algebra:
+            projs = [self._proj_all(exts, ixts, tar_ext, tar_ixt, rc.im_feat_scale[i], rc.volume_scale[i])
+                     for i in range(rc.num)]
+            return ops.CameraBlock(exts, ixts, tar_ext), projs
+        flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
+        h_exts = flat[:N * 16].view(N, 4, 4)
+        h_ixts = flat[N * 16:N * 25].view(N, 3, 3)
+        h_text = flat[N * 25:N * 25 + 16].view(4, 4)
+        h_tixt = flat[N * 25 + 16:N * 25 + 25].view(3, 3)
+        parts = [self._proj_all(h_exts, h_ixts, h_text, h_tixt, rc.im_feat_scale[i], rc.volume_scale[i]).reshape(-1)
+                 for i in range(rc.num)]
+        parts.append(torch.stack([e.inverse()[:3, 3] for e in h_exts]).reshape(-1))
+        parts.append(h_text.inverse()[:3, 3])
+        packed = torch.cat(parts).pin_memory().to(dev, non_blocking=True)
+        projs = [packed[i * N * 12:(i + 1) * N * 12].view(N, 3, 4) for i in range(rc.num)]
+        off = rc.num * N * 12
+        cams = ops.CameraBlock(exts, ixts, centers=packed[off:off + N * 3].view(N, 3),
+                               tar_center=packed[off + N * 3:off + N * 3 + 3])
+        return cams, projs
+
     # ------------------------------------------------------------------ the K-chain engine
     def _render_frame(self, inps, exts, ixts, tar_ext, tar_ixt, near_far, rays_by_level, triples):
         """One batch element.  inps (N,3,H,W); triples: list of K tuples of view ids.
@@ -104,9 +150,7 @@ class EnerfNetwork(nn.Module):
         with self._stage('feature_net'):
             feats = self.forward_feat(inps)
         with self._stage('camera'):
-            cams = ops.CameraBlock(exts, ixts, tar_ext)
-            projs = [self._proj_all(exts, ixts, tar_ext, tar_ixt, rc.im_feat_scale[i], rc.volume_scale[i])
-                     for i in range(rc.num)]
+            cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt)
         depth = std = nf = None              # per chain lists
         out = {}
         for i in range(rc.num):
@@ -115,7 +159,7 @@ class EnerfNetwork(nn.Module):
             f = feats[f'level_{i}']
             C = f.shape[1]
             with self._stage(f'cost_volume_l{i}'):
-                if self.volume_channels_last:
+                if self.channels_last:
                     vols = torch.empty((K, D, h, w, C), device=dev).permute(0, 4, 1, 2, 3)
                 else:
                     vols = torch.empty((K, C, D, h, w), device=dev)
@@ -134,7 +178,7 @@ class EnerfNetwork(nn.Module):
                         ops.cost_volume_var(f, triples[k], projs[i], pl, out=vols[k])
                     nf = nf_new
             with self._stage(f'cost_reg_{i}'):
-                feat_vol, logits = getattr(self, f'cost_reg_{i}')(vols)
+                feat_vol, logits = self._kept(f'cost_reg_{i}')(vols)
                 del vols
             with self._stage(f'depth_regression_l{i}'):
                 depth, std = [], []

@@ -174,15 +174,21 @@ def depth_regression(logits, planes, depth_inv):
 
 # ------------------------------------------------------------------------------------------ K3
 class CameraBlock:
-    """Device-resident camera data of one frame (all N source views + target centre)."""
+    """Device-resident camera data of one frame (all N source views + target centre).
 
-    def __init__(self, src_exts, src_ixts, tar_ext):
+    The centres are `inverse(ext)[:3,3]` exactly as the reference computes them
+    (reference lib/networks/enerf/utils.py:771-772); pass `centers`/`tar_center` when they were
+    already computed (Network hoists all camera algebra to the top of the frame)."""
+
+    def __init__(self, src_exts, src_ixts, tar_ext=None, centers=None, tar_center=None):
         self.exts = _cf32(src_exts, "src_exts")            # (N,4,4)
         self.ixts = _cf32(src_ixts, "src_ixts")            # (N,3,3)
-        # camera centres exactly as the reference gets them: inverse(ext)[:3,3]
-        # (reference lib/networks/enerf/utils.py:771-772)
-        self.centers = torch.stack([e.inverse()[:3, 3] for e in self.exts]).contiguous()
-        self.tar_center = tar_ext.inverse()[:3, 3].contiguous()
+        if centers is None:
+            centers = torch.stack([e.inverse()[:3, 3] for e in self.exts])
+        if tar_center is None:
+            tar_center = tar_ext.inverse()[:3, 3]
+        self.centers = _cf32(centers, "centers")
+        self.tar_center = _cf32(tar_center, "tar_center")
 
 
 def raygen_sample_fetch(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat, rgb, cams, views,

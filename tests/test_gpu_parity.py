@@ -121,6 +121,19 @@ def test_depth_regression_vs_reference(ops, g):
     close(s, g.np("std_l1")[0], "std l1")
 
 
+@pytest.mark.parametrize("D", [8, 12, 64])
+@pytest.mark.parametrize("inv", [False, True])
+def test_depth_regression_vs_oracle_all_kernels(ops, D, inv):
+    """register-resident (D in 8/16/32/64) and generic (other D) kernels vs the CPU oracle."""
+    gen = torch.Generator().manual_seed(D)
+    logits = torch.randn(1, D, 37, 53, generator=gen) * 3
+    planes = torch.sort(torch.rand(1, D, 37, 53, generator=gen) * 6 + 2, dim=1).values
+    rd, rs = O.depth_regression(logits, planes, inv)
+    d, s = ops.depth_regression(logits[0].cuda(), planes[0].cuda(), inv)
+    close(d, rd[0], "depth", rtol=1e-5)
+    close(s, rs[0], "std", rtol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------ K3
 def _fused(ops, g, lvl, want):
     cams = _cams(ops, g)
