@@ -29,7 +29,7 @@ def _digest():
     h = hashlib.sha256()
     for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
             os.path.join(os.path.dirname(HERE), "include", "bmv.h")]:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # relative: the tree moves between machines
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(FLAGS).encode())

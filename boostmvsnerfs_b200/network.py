@@ -68,6 +68,13 @@ class EnerfNetwork(nn.Module):
             return _NullCtx()
         return self.stage_timer(name)
 
+    def invalidate_plans(self):
+        """Drop the derived inference copies (folded convs, packed MLP weights).  They are rebuilt
+        automatically after load_state_dict / in-place parameter updates (tensor version counters);
+        call this after editing `param.data` directly, which bypasses the counters."""
+        self._packed.clear()
+        self._plans = PlanCache()
+
     def _packed_mlp(self, i):
         """Packed weights of nerf_{i} for the fused kernel; re-packed when a parameter changes."""
         nerf = getattr(self, f'nerf_{i}')

@@ -23,7 +23,7 @@ def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "networks"))
 
 
-def load_reference(cfg_file="configs/exps/evaluate/enerf_ours/free_eval.yaml", opts=()):
+def load_reference(cfg_file="configs/exps/evaluate/enerf_ours/free_eval.yaml", opts=(), family=None):
     """Import the reference with the given yaml + CLI-style overrides; returns a namespace dict.
 
     The reference keeps ONE global cfg per process, so a process can hold exactly one
@@ -54,7 +54,9 @@ def load_reference(cfg_file="configs/exps/evaluate/enerf_ours/free_eval.yaml", o
         from lib.networks.enerf import network as enerf_network
         from lib.datasets import enerf_utils as data_utils
         ns = dict(cfg=cfg, enerf_utils=enerf_utils, enerf_network=enerf_network, data_utils=data_utils)
-        if "mvsnerf" in cfg.network_module:
+        if family is None:
+            family = "mvsnerf" if "mvsnerf" in cfg_file else "enerf"
+        if family == "mvsnerf":
             from lib.networks.mvsnerf import network as mvs_network
             from lib.networks.mvsnerf import utils as mvs_utils
             from lib.networks.mvsnerf import renderer as mvs_renderer
