@@ -306,6 +306,26 @@ def main_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
 
+    # ---- single-frame latency mode: the SAME frame sharded over the ranks
+    sharded = None
+    if world > 1:
+        from boostmvsnerfs_b200.dist import ShardedFrameRenderer
+        net.stage_timer = None
+        same = batch_to(make_scene(H=wl["H"], W=wl["W"], n_views=wl["n_views"], seed=0), dev)
+        sr = ShardedFrameRenderer(net)
+        for _ in range(max(2, args.warmup)):
+            sr.forward(same)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            sr.forward(same)
+        e1.record()
+        barrier()
+        ms_sh = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        sharded = {"ms_per_frame": ms_sh, "rays_per_sec": rays_per_frame / (ms_sh * 1e-3), "scaling": "strong",
+                   "what": "one frame: views/chains/row-tiles sharded over ranks, 3 NCCL all-gathers "
+                           "(features, chain states, frame)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,7 +379,7 @@ def main_ours(args):
                        parallelism=("single GPU" if world == 1 else f"{world} frame replicas, no data-path collective")),
         "e2e": {"value": world * rays_per_frame / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels, "frame_sharded": sharded,
         "stage_ms_per_step": step_ms_stage, "hand_written_ms_per_step": hand_ms,
         "kept_library_ms_per_step": {k: v for k, v in step_ms_stage.items() if k.startswith(("cost_reg", "nerf", "feature"))},
     }

@@ -151,15 +151,28 @@ class EnerfNetwork(nn.Module):
         """One batch element.  inps (N,3,H,W); triples: list of K tuples of view ids.
         Returns per rendered level: dict(raws, masks, zs lists over K, depth/std of chain 0)."""
         rc = self.rc
-        K = len(triples)
-        N, _, Hh, Ww = inps.shape
-        dev = inps.device
+        Hh, Ww = inps.shape[-2:]
         with self._stage('feature_net'):
             feats = self.forward_feat(inps)
         with self._stage('camera'):
             cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt)
-        depth = std = nf = None              # per chain lists
+        states = self._chain_levels(feats, projs, near_far, triples, Hh, Ww)
         out = {}
+        for i, st in states.items():
+            out[i] = self._render_level(i, feats, inps, st, rays_by_level[i], cams, triples, Hh, Ww)
+            out[i]['depth0'], out[i]['std0'] = st['depth'][0], st['std'][0]
+        return out
+
+    def _chain_levels(self, feats, projs, near_far, triples, Hh, Ww):
+        """The coarse-to-fine cascade of the given cost-volume chains (reference
+        lib/networks/boost_enerf/network.py:189-209): K1 -> 3-D CNN -> K2 per level, all chains of a
+        level batched through the CNN.  Returns {level: dict(feat_vol (Kc,8,D,h,w), depth, std, nf
+        lists)} for the levels that are rendered."""
+        rc = self.rc
+        K = len(triples)
+        dev = feats['level_0'].device
+        depth = std = nf = None              # per chain lists
+        states = {}
         for i in range(rc.num):
             D, vs = rc.volume_planes[i], rc.volume_scale[i]
             h, w = int(Hh * vs), int(Ww * vs)
@@ -193,16 +206,16 @@ class EnerfNetwork(nn.Module):
                     d, s = ops.depth_regression(logits[k], planes[k], rc.depth_inv[i])
                     depth.append(d)
                     std.append(s)
-            if not rc.render_if[i]:
-                continue
-            out[i] = self._render_level(i, feats, inps, feat_vol, depth, std, nf, rays_by_level[i], cams,
-                                        triples, Hh, Ww)
-            out[i]['depth0'], out[i]['std0'] = depth[0], std[0]
-        return out
+            if rc.render_if[i]:
+                states[i] = {'feat_vol': feat_vol, 'depth': depth, 'std': std, 'nf': nf}
+        return states
 
-    def _render_level(self, i, feats, inps, feat_vol, depth, std, nf, rays, cams, triples, Hh, Ww):
+    def _render_level(self, i, feats, inps, state, rays, cams, triples, Hh, Ww, ray_begin=0, n_rays=None):
+        """K3 (+MLP) for rays [ray_begin, ray_begin+n_rays) of every chain at cascade level i
+        (reference lib/networks/boost_enerf/network.py:123-161, 212-222)."""
         rc = self.rc
         K = len(triples)
+        feat_vol, depth, std, nf = state['feat_vol'], state['depth'], state['std'], state['nf']
         S = rc.num_samples[i]
         rs = rc.render_scale[i]
         H, W = int(Hh * rs), int(Ww * rs)
@@ -217,7 +230,7 @@ class EnerfNetwork(nn.Module):
         else:          # level-0 rendering of the pre-train configs: resized colours (enerf/utils.py:669-676)
             rgb = torch.nn.functional.interpolate(inps * 0.5 + 0.5, size=(H, W), align_corners=True, mode='bilinear')
             affine = (1.0, 0.0)
-        R = rays.shape[0]
+        R = rays.shape[0] - ray_begin if n_rays is None else n_rays
         dev = rays.device
         nerf = getattr(self, f'nerf_{i}')
         V, Cf, Cv = len(triples[0]), im_feat.shape[1], feat_vol.shape[1]
@@ -230,6 +243,7 @@ class EnerfNetwork(nn.Module):
                 for k in range(K):
                     ops.render_rays(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S, feat_vol[k], im_feat,
                                     rgb, cams, triples[k], packed, render_scale=rs, rgb_affine=affine,
+                                    ray_begin=ray_begin, n_rays=R,
                                     out={'raw': raw_all[k], 'z_vals': z_all[k], 'vis_mask': mask_all[k]})
             return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
         for r0 in range(0, R, rc.chunk_size):
@@ -240,7 +254,7 @@ class EnerfNetwork(nn.Module):
                 for k in range(K):
                     ops.raygen_sample_fetch(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S,
                                             feat_vol[k], im_feat, rgb, cams, triples[k], render_scale=rs,
-                                            rgb_affine=affine, ray_begin=r0, n_rays=n, want=(),
+                                            rgb_affine=affine, ray_begin=ray_begin + r0, n_rays=n, want=(),
                                             out={'z_vals': z_all[k, r0:r0 + n], 'vis_mask': mask_all[k, r0:r0 + n],
                                                  'vox_feat': vox[k], 'img_feat': img[k]})
             with self._stage(f'nerf_{i}'):
