@@ -7,6 +7,8 @@ Run in the build container (the GPU box has no /root/reference):
     python oracle/gen_golden.py chain_eval     # Network.forward    -> tests/golden/enerf_chain_eval.npz
     python oracle/gen_golden.py chain_pretrain # both levels render -> tests/golden/enerf_chain_pretrain.npz
     python oracle/gen_golden.py single         # enerf.Network      -> tests/golden/enerf_single.npz
+    python oracle/gen_golden.py mvs_ops        # MVSNeRF op-level   -> tests/golden/mvsnerf_ops.npz
+    python oracle/gen_golden.py mvs_chain      # boost_mvsnerf.Network.forward -> tests/golden/mvsnerf_chain.npz
     python oracle/gen_golden.py all            # each of the above in its own process
 
 Every stored array is either an INPUT handed to a reference function or the OUTPUT the reference
@@ -202,11 +204,115 @@ def gen_single():
     _save("enerf_single.npz", out)
 
 
+MVS_CFG = "configs/exps/evaluate/mvsnerf_ours/free_eval.yaml"
+
+
+class _ZeroedEmpty:
+    """The reference allocates the 41-channel volume with torch.empty and never writes channels 0:3 of
+    the 24-px border (mvsnerf/network.py:906) -> nondeterministic bytes.  While the reference runs we
+    make torch.empty return zero-filled memory (an allocator property, not a change to the reference),
+    which is the value the oracle and the kernels define for those bytes."""
+
+    def __enter__(self):
+        self._orig = torch.empty
+        torch.empty = lambda *a, **k: self._orig(*a, **k).zero_()
+
+    def __exit__(self, *a):
+        torch.empty = self._orig
+
+
+def _mvs_scene(seed):
+    return make_scene(seed=seed, smooth=True, mvs_near_far_cols=True, render_scales=(1.0,), **TINY)
+
+
+def gen_mvs_ops():
+    ns = load_reference(MVS_CFG, ["enerf.cas_config.k_best", 2, "enerf.cas_config.num_samples", "[8]"])
+    MU, MN, BN_, EU = ns["mvs_utils"], ns["mvs_network"], ns["boost_mvs_network"], ns["enerf_utils"]
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    scene = _mvs_scene(8)
+    H, W = TINY["H"], TINY["W"]
+    h, w, D, S = H // 4, W // 4, 8, 8
+    triple = [1, 0, 3]
+    batch = dict(scene)
+    batch["src_inps"] = scene["all_src_inps"][:, triple]
+    batch["src_exts"] = scene["all_src_exts"][:, triple]
+    batch["src_ixts"] = scene["all_src_ixts"][:, triple]
+    for k in ("src_inps", "src_exts", "src_ixts", "rays_0", "depth_ranges"):
+        out[f"in_{k}"] = _np(batch[k])
+    torch.manual_seed(1)
+    net = BN_.Network(preprocess=True).eval()
+    pm = net.get_proj_mats(batch)
+    out["proj_mats"] = _np(pm)
+    feats = torch.randn(1, 3, 32, h, w, generator=g)
+    out["in_feats"] = _np(feats)
+    t = torch.linspace(0., 1., steps=D)
+    near, far = batch["depth_ranges"][:, triple].min() * 0.8, batch["depth_ranges"][:, triple].max() * 1.2
+    planes = (near * (1. - t) + far * t).unsqueeze(0)
+    out["planes"] = _np(planes)
+    out["near_far"] = _np(torch.stack([near, far]))
+    with _ZeroedEmpty():
+        vol = net.build_volume_costvar_img(batch["src_inps"], feats, pm, planes, pad=24)
+    out["volume41"] = _np(vol)
+    # ---- marching, NDC, fetches, MLP input (every 8th ray keeps the fixture small)
+    rays = batch["rays_0"][:, ::8].contiguous()
+    out["in_rays_sub"] = _np(rays)
+    xyz, z = net.ray_marcher(rays, S)
+    out["march_xyz"], out["march_z"] = _np(xyz), _np(z)
+    inv_scale = torch.tensor([W - 1, H - 1], dtype=torch.float32)
+    ndc = MU.get_ndc_coordinate(batch["src_exts"][0][0], batch["src_ixts"][0][0], xyz[0], inv_scale,
+                                near=near, far=far, pad=24)[None]
+    out["ndc"] = _np(ndc)
+    regvol = torch.randn(1, 8, D, h + 48, w + 48, generator=g)
+    out["in_regvol"] = _np(regvol)
+    batch["near_far"] = torch.stack([near, far])
+    raw_in = net.rendering(batch, xyz[0], ndc, z, rays[..., :3], rays[..., 3:6], regvol)
+    out["mlp_input"] = _np(raw_in)
+    out["mask"] = _np(EU.mask_viewport(xyz, batch["src_exts"], batch["src_ixts"], inv_scale))
+    with torch.no_grad():
+        out["mlp_output"] = _np(net.nerf(raw_in))
+        for name, tns in net.nerf.state_dict().items():
+            out[f"sd_nerf.{name}"] = _np(tns)
+    # ---- view-selection coverage mask (no network involved, boost_mvsnerf/network.py:23-45)
+    m = net.calc_mask(torch.tensor(triple), dict(scene))
+    out["calc_mask"] = _np(m["mask_level0"])
+    _save("mvsnerf_ops.npz", out)
+
+
+def gen_mvs_chain():
+    ns = load_reference(MVS_CFG, ["enerf.cas_config.k_best", 2, "enerf.cas_config.num_samples", "[8]"])
+    torch.manual_seed(13)
+    net = ns["boost_mvs_network"].Network(preprocess=True).eval()
+    g = torch.Generator().manual_seed(17)
+    for name, buf in net.named_buffers():
+        if name.endswith("running_mean"):
+            buf.copy_(torch.randn(buf.shape, generator=g) * 0.1)
+        elif name.endswith("running_var"):
+            buf.copy_(torch.rand(buf.shape, generator=g) * 0.5 + 0.75)
+    scene = _mvs_scene(9)
+    k_best = [2, 1]
+    net.view_selection_outputs = {"synth_0": k_best}
+    batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in scene.items()}
+    with torch.no_grad(), _ZeroedEmpty():
+        ret = net(batch)
+        sel = net.forward_view_selection({k: (v.clone() if torch.is_tensor(v) else v) for k, v in scene.items()})
+    out = {f"out_{k}": _np(v) for k, v in ret.items()}
+    for k in ("all_src_inps", "all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt", "depth_ranges", "rays_0"):
+        out[f"in_{k}"] = _np(scene[k])
+    out["k_best"] = np.array(k_best, dtype=np.int64)
+    out["view_selection"] = np.array(sel["synth_0"], dtype=np.int64)
+    for k in ("src_inps", "src_exts", "src_ixts", "near_far"):
+        out[f"after_{k}"] = _np(batch[k])
+    for name, t in net.state_dict().items():
+        out[f"sd_{name}"] = _np(t)
+    _save("mvsnerf_chain.npz", out)
+
+
 if __name__ == "__main__":
     case = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if case == "all":
-        for c in ("ops", "chain_eval", "chain_pretrain", "single"):
+        for c in ("ops", "chain_eval", "chain_pretrain", "single", "mvs_ops", "mvs_chain"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), c])
     elif case == "ops":
         gen_ops()
@@ -214,5 +320,9 @@ if __name__ == "__main__":
         _chain(case)
     elif case == "single":
         gen_single()
+    elif case == "mvs_ops":
+        gen_mvs_ops()
+    elif case == "mvs_chain":
+        gen_mvs_chain()
     else:
         raise SystemExit(f"unknown case {case}")
