@@ -113,6 +113,32 @@ class StageTimer:
         return agg
 
 
+class KernelTimer:
+    """CUDA events recorded right around each libbmv enqueue (hook: _lib.kernel_timer), so a kernel's
+    duration is not inflated by host-side gaps when the stream runs dry."""
+
+    def __init__(self, torch):
+        self.torch, self.records, self.enabled, self._e0 = torch, [], False, None
+
+    def before(self, name):
+        if self.enabled:
+            self._e0 = self.torch.cuda.Event(enable_timing=True)
+            self._e0.record()
+
+    def after(self, name):
+        if self.enabled:
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.records.append((name, self._e0, e1))
+
+    def summary(self):
+        agg = {}
+        for name, e0, e1 in self.records:
+            a = agg.setdefault(name, [])
+            a.append(e0.elapsed_time(e1))
+        return agg
+
+
 class _Stage:
     def __init__(self, timer, name):
         self.t, self.name = timer, name
@@ -250,6 +276,8 @@ def main_ours(args):
     net.view_selection_outputs = {"synth_0": wl["k_best"]}
     timer = StageTimer()
     net.stage_timer = timer
+    ktimer = KernelTimer(torch)
+    _lib.kernel_timer = ktimer
     # replicas: every rank renders its own frames (different seeds) — SURVEY.md §8(e) "sequence mode"
     host = make_scene(H=wl["H"], W=wl["W"], n_views=wl["n_views"], seed=rank)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
@@ -275,6 +303,7 @@ def main_ours(args):
     clocks.start()
     barrier()
     timer.enabled, timer.records = True, []
+    ktimer.enabled, ktimer.records = True, []
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
@@ -286,6 +315,7 @@ def main_ours(args):
     t_wall1 = time.time()
     launches = (_lib.launch_count() - l0) / args.steps
     timer.enabled = False
+    ktimer.enabled = False
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     clk = clocks.stop(t_wall0, t_wall1)
     stages = timer.summary()
@@ -342,10 +372,29 @@ def main_ours(args):
     alg = algorithmic_bytes(wl, rc)
     launches_per_stage = {k: (wl["K"] if not k.startswith("composite") else 1) for k in alg}
     kernels, step_ms_stage = {}, {}
+    # per-launch kernel durations by (entry point, order within the frame) -> stage name
+    ksum = ktimer.summary()
+    per_kernel = {}
+    order = {"bmv_cost_volume_var": ["cost_volume_l0", "cost_volume_l1"],
+             "bmv_depth_regression": ["depth_regression_l0", "depth_regression_l1"],
+             "bmv_render_rays": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
+             "bmv_raygen_sample_fetch": [f"raygen_fetch_l{i}" for i in range(rc.num) if rc.render_if[i]],
+             "bmv_composite_blend": [f"composite_blend_l{i}" for i in range(rc.num) if rc.render_if[i]]}
+    for entry, names in order.items():
+        ts = ksum.get(entry, [])
+        per_frame = len(ts) // max(1, args.steps)
+        if not ts or per_frame % len(names):
+            continue
+        per_name = per_frame // len(names)
+        for f in range(args.steps):
+            for j, nm in enumerate(names):
+                per_kernel.setdefault(nm, []).extend(ts[f * per_frame + j * per_name:f * per_frame + (j + 1) * per_name])
     for name, (tot_ms, cnt) in stages.items():
         step_ms_stage[name] = tot_ms / args.steps
         if name in alg:
             per_launch_ms = tot_ms / (args.steps * launches_per_stage[name])
+            if per_kernel.get(name):
+                per_launch_ms = sum(per_kernel[name]) / len(per_kernel[name])
             gbs = alg[name] / (per_launch_ms * 1e-3) / 1e9
             kernels[name] = {"ms_per_launch": per_launch_ms, "launches_per_step": launches_per_stage[name],
                              "algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac": gbs / peak_gbs,

@@ -26,7 +26,7 @@ class CostVolumeParams(C.Structure):
                 ("D", i32), ("h", i32), ("w", i32),
                 ("out", C.c_void_p),
                 ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
-                ("out_bf16", i32)]
+                ("out_bf16", i32), ("exact_coords", i32)]
 
 
 class DepthPlanesFirstParams(C.Structure):
@@ -146,9 +146,18 @@ def load():
     return lib
 
 
+# Optional per-launch profiler: an object with before(name) / after(name) called right around the
+# enqueue (bench.py records CUDA events there, so a kernel's time excludes host-side gaps).
+kernel_timer = None
+
+
 def call(name, params, stream):
     lib = load()
+    if kernel_timer is not None:
+        kernel_timer.before(name)
     rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
+    if kernel_timer is not None:
+        kernel_timer.after(name)
     if rc != 0:
         raise BmvError(f"{name} failed with status {rc}: {lib.bmv_last_error_string().decode()}")
 

@@ -161,6 +161,117 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume
   }
 }
 
+// v3 (channels-last, the per-frame path).  Two measured problems of v2 (profiles/round1b_*):
+//  (a) issue-bound: 1036 instructions per lane, ~75 % of them the op-for-op emulation of the
+//      reference's coordinate arithmetic (9 IEEE divisions per view) repeated by every lane of a voxel;
+//  (b) 10x more L2->SM traffic than compulsory because consecutive planes of a pixel — which
+//      re-touch almost the same source texels — ran in different CTAs.
+// v3: one CTA owns VPB consecutive x of ONE row and loops over a group of DG planes, so the sliding
+// window of source texels stays in L1; R*[x,y,1] is hoisted out of the plane loop; divisions become
+// one correctly-rounded reciprocal each (T/d -> T*rcp(d), x/z -> x*rcp(z), /((W-1)/2) -> *2/(W-1)).
+// The coordinate differs from the reference's by <= 2 ulp (~1e-5 px), the same order as the
+// reference's own CPU-vs-CUDA difference (ATen multiplies by the reciprocal of scalar divisors on CUDA).
+struct FastTap { int off[4]; float w[4]; };
+
+__device__ __forceinline__ FastTap fast_taps(float ax, float ay, float az, const float* __restrict__ P, float idep,
+                                             float sx, float sy, int Hs, int Ws, int ys, int xs) {
+  const float cx = fmaf(P[3], idep, ax), cy = fmaf(P[7], idep, ay), cz = fmaf(P[11], idep, az);
+  const float iz = __frcp_rn(fmaxf(cz, 1e-6f));
+  // g = u/((W-1)/2) - 1 ; ix = ((g+1)/2)*(W-1)
+  const float gx = fmaf(cx * iz, sx, -1.f), gy = fmaf(cy * iz, sy, -1.f);
+  const float ix = (gx + 1.f) * 0.5f * (float)(Ws - 1), iy = (gy + 1.f) * 0.5f * (float)(Hs - 1);
+  FastTap t;
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  const float wx1 = ix - x0, wy1 = iy - y0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  // NaN / huge coordinates fail every comparison -> all four taps invalid (zeros padding)
+  const bool vx0 = x0 >= 0.f && x0 <= (float)(Ws - 1), vx1 = x0 >= -1.f && x0 <= (float)(Ws - 2);
+  const bool vy0 = y0 >= 0.f && y0 <= (float)(Hs - 1), vy1 = y0 >= -1.f && y0 <= (float)(Hs - 2);
+  const int ix0 = vx0 ? (int)x0 : 0, ix1 = vx1 ? (int)x0 + 1 : 0;
+  const int iy0 = vy0 ? (int)y0 : 0, iy1 = vy1 ? (int)y0 + 1 : 0;
+  t.off[0] = iy0 * ys + ix0 * xs; t.w[0] = (vx0 && vy0) ? wx0 * wy0 : 0.f;
+  t.off[1] = iy0 * ys + ix1 * xs; t.w[1] = (vx1 && vy0) ? wx1 * wy0 : 0.f;
+  t.off[2] = iy1 * ys + ix0 * xs; t.w[2] = (vx0 && vy1) ? wx0 * wy1 : 0.f;
+  t.off[3] = iy1 * ys + ix1 * xs; t.w[3] = (vx1 && vy1) ? wx1 * wy1 : 0.f;
+  return t;
+}
+
+template <int S, int CPT, typename OutT>
+__global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volume_params p, int CG, int DG) {
+  __shared__ float sP[S * 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const int vpb = blockDim.x / CG;                       // voxels (consecutive x) per CTA
+  const int x = blockIdx.x * vpb + (int)threadIdx.x / CG;
+  const int c0 = ((int)threadIdx.x % CG) * CPT;
+  const int y = blockIdx.y;
+  if (x >= p.w) return;
+  const int d_begin = blockIdx.z * DG, d_end = min(p.D, d_begin + DG);
+  const float fx = (float)x, fy = (float)y;
+  float ax[S], ay[S], az[S];
+  const float* base[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const float* P = sP + s * 12;
+    ax[s] = dot3_gemm(P[0], P[1], P[2], fx, fy, 1.f);
+    ay[s] = dot3_gemm(P[4], P[5], P[6], fx, fy, 1.f);
+    az[s] = dot3_gemm(P[8], P[9], P[10], fx, fy, 1.f);
+    base[s] = p.feat + (int64_t)p.view[s] * p.feat_view_stride + c0;
+  }
+  const float sx = 2.f / (float)(p.Ws - 1), sy = 2.f / (float)(p.Hs - 1);
+  const int ys = (int)p.feat_y_stride, xs = (int)p.feat_x_stride;
+  const float* pl = p.planes + ((int64_t)y * p.w + x) * p.planes_pix_stride;
+  OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)x * p.out_x_stride + c0;
+  for (int d = d_begin; d < d_end; ++d) {
+    const float idep = __frcp_rn(__ldg(pl + (int64_t)d * p.planes_d_stride));
+    float sum[CPT], sq[CPT];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const FastTap t = fast_taps(ax[s], ay[s], az[s], sP + s * 12, idep, sx, sy, p.Hs, p.Ws, ys, xs);
+#pragma unroll
+      for (int q = 0; q < CPT; q += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base[s] + t.off[0] + q));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(base[s] + t.off[1] + q));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(base[s] + t.off[2] + q));
+        const float4 e = __ldg(reinterpret_cast<const float4*>(base[s] + t.off[3] + q));
+        const float v0 = fmaf(t.w[3], e.x, fmaf(t.w[2], c.x, fmaf(t.w[1], b.x, t.w[0] * a.x)));
+        const float v1 = fmaf(t.w[3], e.y, fmaf(t.w[2], c.y, fmaf(t.w[1], b.y, t.w[0] * a.y)));
+        const float v2 = fmaf(t.w[3], e.z, fmaf(t.w[2], c.z, fmaf(t.w[1], b.z, t.w[0] * a.z)));
+        const float v3 = fmaf(t.w[3], e.w, fmaf(t.w[2], c.w, fmaf(t.w[1], b.w, t.w[0] * a.w)));
+        if (s == 0) {
+          sum[q] = v0; sum[q + 1] = v1; sum[q + 2] = v2; sum[q + 3] = v3;
+          sq[q] = v0 * v0; sq[q + 1] = v1 * v1; sq[q + 2] = v2 * v2; sq[q + 3] = v3 * v3;
+        } else {
+          sum[q] += v0; sum[q + 1] += v1; sum[q + 2] += v2; sum[q + 3] += v3;
+          sq[q] = fmaf(v0, v0, sq[q]); sq[q + 1] = fmaf(v1, v1, sq[q + 1]);
+          sq[q + 2] = fmaf(v2, v2, sq[q + 2]); sq[q + 3] = fmaf(v3, v3, sq[q + 3]);
+        }
+      }
+    }
+    constexpr float invS = 1.f / S;
+    float var[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      const float mean = sum[q] * invS;
+      var[q] = fmaf(-mean, mean, sq[q] * invS);
+    }
+    OutT* out = outp + (int64_t)d * p.out_d_stride;
+    if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+      for (int q = 0; q < CPT; q += 4)
+        *reinterpret_cast<float4*>(out + q) = make_float4(var[q], var[q + 1], var[q + 2], var[q + 3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < CPT; q += 4) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(var[q], var[q + 1]), hi = __floats2bfloat162_rn(var[q + 2], var[q + 3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + q) = pk;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- depth hypotheses, level 0
 __global__ void depth_planes_first_kernel(bmv_depth_planes_first_params p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,14 +338,22 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
                   p.feat_y_stride % 4 == 0 && p.feat_view_stride % 4 == 0 && ((uintptr_t)p.feat & 15) == 0 &&
                   p.out_x_stride % 4 == 0 && p.out_y_stride % 4 == 0 && p.out_d_stride % 4 == 0 &&
                   ((uintptr_t)p.out & (sizeof(OutT) == 4 ? 15 : 7)) == 0;
-  if (cl) {
-    if (p.C % 8 == 0 && p.C >= 32) {
-      const int CG = p.C / 8;
-      cost_volume_var_cl_kernel<S, 8, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
-    } else {
-      const int CG = p.C / 4;
-      cost_volume_var_cl_kernel<S, 4, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
-    }
+  const int cpt = (p.C % 8 == 0 && p.C >= 32) ? 8 : 4;
+  const int CG = p.C / cpt;
+  const bool v3 = cl && p.exact_coords == 0 && threads % CG == 0 && CG <= threads && p.h <= 65535 &&
+                  (int64_t)p.Hs * p.feat_y_stride < (1ll << 31);
+  if (v3) {
+    // plane groups: enough CTAs to fill 148 SMs x 8 CTAs, but as deep as possible for L1 reuse
+    const int vpb = threads / CG;
+    const int xchunks = (p.w + vpb - 1) / vpb;
+    int DG = p.D;
+    while (DG > 4 && (int64_t)xchunks * p.h * ((p.D + DG - 1) / DG) < 2 * 148 * 4) DG = (DG + 1) / 2;
+    dim3 grid(xchunks, p.h, (p.D + DG - 1) / DG);
+    if (cpt == 8) cost_volume_var_cl3_kernel<S, 8, OutT><<<grid, threads, 0, st>>>(p, CG, DG);
+    else cost_volume_var_cl3_kernel<S, 4, OutT><<<grid, threads, 0, st>>>(p, CG, DG);
+  } else if (cl) {
+    if (cpt == 8) cost_volume_var_cl_kernel<S, 8, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
+    else cost_volume_var_cl_kernel<S, 4, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
   } else {
     cost_volume_var_kernel<S, OutT><<<(unsigned)ceil_div64(nvox, threads), threads, 0, st>>>(p);
   }

@@ -42,6 +42,15 @@ struct MlpLayout {
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// acc[0..3] += w . x[0..3] lane-wise: four INDEPENDENT FMA chains per dot product, so a warp keeps
+// 4 FMAs in flight per weight quad instead of one 4-deep dependent chain (the v1 kernel stalled on
+// exactly that: short-scoreboard/FMA-latency bound at 3 warps per scheduler, profiles/round1b).
+__device__ __forceinline__ void fma4(float (&acc)[4], const float4 w, float x0, float x1, float x2, float x3) {
+  acc[0] = fmaf(w.x, x0, acc[0]); acc[1] = fmaf(w.y, x1, acc[1]);
+  acc[2] = fmaf(w.z, x2, acc[2]); acc[3] = fmaf(w.w, x3, acc[3]);
+}
+__device__ __forceinline__ float sum4(const float (&a)[4]) { return (a[0] + a[1]) + (a[2] + a[3]); }
+
 // f[v][0:F] = fetched per-view features (image feature channels + rgb), f[v][F:F+4] = direction
 // features; vox[8] = cost-volume feature.  Returns (r,g,b,sigma).
 template <int F, int V>
@@ -92,27 +101,21 @@ __device__ __forceinline__ float4 nerf_mlp_eval(const float* __restrict__ sw, co
   for (int j = 0; j < 32; ++j) {
     const float* row = sw + L::OFF_GLOB + j * L::GROW;
     const float4 tail = lds4(row + 3 * L::FP);           // bias, agg_w
-    float shared = tail.x;
+    float sh[4] = {tail.x, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 2 * L::FP; i += 4) {
-      const float4 w = lds4(row + L::FP + i);
-      shared = fmaf(w.x, vm[i], shared); shared = fmaf(w.y, vm[i + 1], shared);
-      shared = fmaf(w.z, vm[i + 2], shared); shared = fmaf(w.w, vm[i + 3], shared);
-    }
-    float g[V];
+    for (int i = 0; i < 2 * L::FP; i += 4) fma4(sh, lds4(row + L::FP + i), vm[i], vm[i + 1], vm[i + 2], vm[i + 3]);
+    float ga[V][4];
 #pragma unroll
-    for (int v = 0; v < V; ++v) g[v] = shared;
+    for (int v = 0; v < V; ++v) { ga[v][0] = 0.f; ga[v][1] = 0.f; ga[v][2] = 0.f; ga[v][3] = 0.f; }
 #pragma unroll
     for (int i = 0; i < L::FP; i += 4) {
       const float4 w = lds4(row + i);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        g[v] = fmaf(w.x, x[v][i], g[v]); g[v] = fmaf(w.y, x[v][i + 1], g[v]);
-        g[v] = fmaf(w.z, x[v][i + 2], g[v]); g[v] = fmaf(w.w, x[v][i + 3], g[v]);
-      }
+      for (int v = 0; v < V; ++v) fma4(ga[v], w, x[v][i], x[v][i + 1], x[v][i + 2], x[v][i + 3]);
     }
+    const float shared = sum4(sh);
 #pragma unroll
-    for (int v = 0; v < V; ++v) logit[v] = fmaf(tail.y, fmaxf(g[v], 0.f), logit[v]);
+    for (int v = 0; v < V; ++v) logit[v] = fmaf(tail.y, fmaxf(shared + sum4(ga[v]), 0.f), logit[v]);
   }
   float wsm[V];
   {
@@ -135,28 +138,22 @@ __device__ __forceinline__ float4 nerf_mlp_eval(const float* __restrict__ sw, co
 #pragma unroll 1
   for (int j = 0; j < 32; ++j) {
     const float* row = sw + L::OFF_GLOB + j * L::GROW;
-    float shared = row[3 * L::FP];
+    float sh[4] = {row[3 * L::FP], 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 2 * L::FP; i += 4) {
-      const float4 w = lds4(row + L::FP + i);
-      shared = fmaf(w.x, vm[i], shared); shared = fmaf(w.y, vm[i + 1], shared);
-      shared = fmaf(w.z, vm[i + 2], shared); shared = fmaf(w.w, vm[i + 3], shared);
-    }
-    float g[V];
+    for (int i = 0; i < 2 * L::FP; i += 4) fma4(sh, lds4(row + L::FP + i), vm[i], vm[i + 1], vm[i + 2], vm[i + 3]);
+    float ga[V][4];
 #pragma unroll
-    for (int v = 0; v < V; ++v) g[v] = shared;
+    for (int v = 0; v < V; ++v) { ga[v][0] = 0.f; ga[v][1] = 0.f; ga[v][2] = 0.f; ga[v][3] = 0.f; }
 #pragma unroll
     for (int i = 0; i < L::FP; i += 4) {
       const float4 w = lds4(row + i);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        g[v] = fmaf(w.x, x[v][i], g[v]); g[v] = fmaf(w.y, x[v][i + 1], g[v]);
-        g[v] = fmaf(w.z, x[v][i + 2], g[v]); g[v] = fmaf(w.w, x[v][i + 3], g[v]);
-      }
+      for (int v = 0; v < V; ++v) fma4(ga[v], w, x[v][i], x[v][i + 1], x[v][i + 2], x[v][i + 3]);
     }
+    const float shared = sum4(sh);
     float im = 0.f;
 #pragma unroll
-    for (int v = 0; v < V; ++v) im = fmaf(wsm[v], fmaxf(g[v], 0.f), im);
+    for (int v = 0; v < V; ++v) im = fmaf(wsm[v], fmaxf(shared + sum4(ga[v]), 0.f), im);
     const float* fc = sw + L::OFF_FC + j * 16;
 #pragma unroll
     for (int o = 0; o < 16; o += 4) {
@@ -174,14 +171,10 @@ __device__ __forceinline__ float4 nerf_mlp_eval(const float* __restrict__ sw, co
   for (int j = 0; j < 64; ++j) {
     const float* row = sw + L::OFF_LR0 + j * 28;
     const float4 tail = lds4(row + 24);                  // bias, sigma weight
-    float a = tail.x;
+    float a4[4] = {tail.x, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 24; i += 4) {
-      const float4 w = lds4(row + i);
-      a = fmaf(w.x, base[i], a); a = fmaf(w.y, base[i + 1], a);
-      a = fmaf(w.z, base[i + 2], a); a = fmaf(w.w, base[i + 3], a);
-    }
-    hid[j] = fmaxf(a, 0.f);
+    for (int i = 0; i < 24; i += 4) fma4(a4, lds4(row + i), base[i], base[i + 1], base[i + 2], base[i + 3]);
+    hid[j] = fmaxf(sum4(a4), 0.f);
     sig = fmaf(tail.y, hid[j], sig);
   }
   sig = sig > 20.f ? sig : log1pf(expf(sig));            // nn.Softplus(beta=1, threshold=20)
@@ -194,35 +187,28 @@ __device__ __forceinline__ float4 nerf_mlp_eval(const float* __restrict__ sw, co
   for (int j = 0; j < 64; ++j) {
     const float* row = sw + L::OFF_COL + j * L::CROW;
     const float4 tail = lds4(row + 88 + L::FVP);         // bias, color.2 weight
-    float shared = tail.x;
+    float sh[4] = {tail.x, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 64; i += 4) {
-      const float4 w = lds4(row + i);
-      shared = fmaf(w.x, hid[i], shared); shared = fmaf(w.y, hid[i + 1], shared);
-      shared = fmaf(w.z, hid[i + 2], shared); shared = fmaf(w.w, hid[i + 3], shared);
-    }
+    for (int i = 0; i < 64; i += 4) fma4(sh, lds4(row + i), hid[i], hid[i + 1], hid[i + 2], hid[i + 3]);
 #pragma unroll
-    for (int i = 0; i < 24; i += 4) {
-      const float4 w = lds4(row + 64 + i);
-      shared = fmaf(w.x, base[i], shared); shared = fmaf(w.y, base[i + 1], shared);
-      shared = fmaf(w.z, base[i + 2], shared); shared = fmaf(w.w, base[i + 3], shared);
-    }
-    float a[V];
+    for (int i = 0; i < 24; i += 4) fma4(sh, lds4(row + 64 + i), base[i], base[i + 1], base[i + 2], base[i + 3]);
+    float av[V][4];
 #pragma unroll
-    for (int v = 0; v < V; ++v) a[v] = shared;
+    for (int v = 0; v < V; ++v) { av[v][0] = 0.f; av[v][1] = 0.f; av[v][2] = 0.f; av[v][3] = 0.f; }
 #pragma unroll
     for (int i = 0; i < L::FVP; i += 4) {
       const float4 w = lds4(row + 88 + i);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        a[v] = fmaf(w.x, f[v][i], a[v]);
-        if (i + 1 < L::FV) a[v] = fmaf(w.y, f[v][i + 1], a[v]);
-        if (i + 2 < L::FV) a[v] = fmaf(w.z, f[v][i + 2], a[v]);
-        if (i + 3 < L::FV) a[v] = fmaf(w.w, f[v][i + 3], a[v]);
+        av[v][0] = fmaf(w.x, f[v][i], av[v][0]);
+        if (i + 1 < L::FV) av[v][1] = fmaf(w.y, f[v][i + 1], av[v][1]);
+        if (i + 2 < L::FV) av[v][2] = fmaf(w.z, f[v][i + 2], av[v][2]);
+        if (i + 3 < L::FV) av[v][3] = fmaf(w.w, f[v][i + 3], av[v][3]);
       }
     }
+    const float shared = sum4(sh);
 #pragma unroll
-    for (int v = 0; v < V; ++v) cl[v] = fmaf(tail.y, fmaxf(a[v], 0.f), cl[v]);
+    for (int v = 0; v < V; ++v) cl[v] = fmaf(tail.y, fmaxf(shared + sum4(av[v]), 0.f), cl[v]);
   }
   float r = 0.f, g = 0.f, b = 0.f;
   {

@@ -330,12 +330,6 @@ class BoostEnerfNetwork(EnerfNetwork):
                 per_b.append(self._render_frame(inps[b], batch['all_src_exts'][b], batch['all_src_ixts'][b],
                                                 batch['tar_ext'][b], batch['tar_ixt'][b], batch['near_far'][b],
                                                 [batch[f'rays_{i}'][b] for i in range(rc.num)], triples))
-            # the reference leaves the LAST triple in the batch (evaluators read batch['src_inps'].shape)
-            last = torch.tensor([table[int(k_best[b][K - 1])] for b in range(B)], device=inps.device)
-            bidx = torch.arange(B, device=inps.device).unsqueeze(-1).expand(-1, I)
-            batch['src_inps'] = inps[bidx, last]
-            batch['src_exts'] = batch['all_src_exts'][bidx, last]
-            batch['src_ixts'] = batch['all_src_ixts'][bidx, last]
             if rc.white_bkgd:
                 raise NotImplementedError   # reference lib/networks/enerf/utils.py:660-661
             for i in range(rc.num):
@@ -351,6 +345,19 @@ class BoostEnerfNetwork(EnerfNetwork):
                 ret.update({f'rgb_level{i}': torch.stack(rgb), f'depth_level{i}': torch.stack(dep),
                             f'weights_level{i}': torch.stack(wts), f'depth_mvs_level{i}': torch.stack(dmvs),
                             f'std_level{i}': torch.stack(sd)})
+            # the reference leaves the LAST triple in the batch (evaluators read batch['src_inps'].shape);
+            # done last so the index upload cannot stall the kernels above
+            last = [list(table[int(k_best[b][K - 1])]) for b in range(B)]
+            if B == 1:
+                batch['src_inps'] = inps[:, last[0]]
+                batch['src_exts'] = batch['all_src_exts'][:, last[0]]
+                batch['src_ixts'] = batch['all_src_ixts'][:, last[0]]
+            else:
+                lt = torch.tensor(last, device=inps.device)
+                bidx = torch.arange(B, device=inps.device).unsqueeze(-1).expand(-1, I)
+                batch['src_inps'] = inps[bidx, lt]
+                batch['src_exts'] = batch['all_src_exts'][bidx, lt]
+                batch['src_ixts'] = batch['all_src_ixts'][bidx, lt]
         return ret
 
 

@@ -50,7 +50,8 @@ def _linspace(n, device):
 
 
 # ------------------------------------------------------------------------------------------ K1
-def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float32, channels_last=False):
+def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float32, channels_last=False,
+                    exact_coords=False):
     """Fused plane-sweep cost volume for ONE batch element.
 
     feats  (N,C,Hs,Ws) feature maps of all views, any strides (NCHW or channels_last)
@@ -78,11 +79,12 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
     D, h, w = planes.shape
     p.planes_d_stride, p.planes_pix_stride = h * w, 1
     p.D, p.h, p.w = D, h, w
+    p.exact_coords = int(exact_coords)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
 def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dtype=torch.float32,
-                           channels_last=False):
+                           channels_last=False, exact_coords=False):
     """Same as cost_volume_var with D hypotheses shared by every pixel (cascade level 0)."""
     _f32(feats, "feats")
     proj = _cf32(proj, "proj")
@@ -98,6 +100,7 @@ def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dty
     D = planes_d.numel()
     p.planes_d_stride, p.planes_pix_stride = 1, 0
     p.D, p.h, p.w = D, h, w
+    p.exact_coords = int(exact_coords)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 

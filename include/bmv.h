@@ -81,6 +81,8 @@ typedef struct bmv_cost_volume_params {
   float* out;                   /* (C,D,h,w) with the strides below */
   int64_t out_c_stride, out_d_stride, out_y_stride, out_x_stride;
   int32_t out_bf16;             /* 0: fp32 out, 1: out points to bf16 storage (round-to-nearest-even) */
+  int32_t exact_coords;         /* 1: reproduce the reference's coordinate arithmetic op for op (IEEE divisions,
+                                   slower); 0: reciprocal-multiply form, coordinates within 2 ulp (default) */
 } bmv_cost_volume_params;
 BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream);
 
