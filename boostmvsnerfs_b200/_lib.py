@@ -95,6 +95,25 @@ class RenderRaysParams(C.Structure):
     _fields_ = [("g", RaygenFetchParams), ("mlp_weights", C.c_void_p), ("raw", C.c_void_p)]
 
 
+class CostVolumeImgParams(C.Structure):
+    _fields_ = [("feat", C.c_void_p), ("feat_view_stride", i64), ("feat_c_stride", i64), ("feat_y_stride", i64),
+                ("feat_x_stride", i64), ("img", C.c_void_p), ("view", i32 * MAX_VIEWS),
+                ("V", i32), ("C", i32), ("h", i32), ("w", i32), ("D", i32), ("pad", i32),
+                ("proj", C.c_void_p), ("planes", C.c_void_p), ("out", C.c_void_p),
+                ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
+                ("out_bf16", i32)]
+
+
+class MvsMarchParams(C.Structure):
+    _fields_ = [("rays", C.c_void_p), ("ray_begin", i64), ("n_rays", i64), ("t", C.c_void_p), ("S", i32),
+                ("V", i32), ("view", i32 * MAX_VIEWS), ("src_exts", C.c_void_p), ("src_ixts", C.c_void_p),
+                ("H", i32), ("W", i32), ("near", f32), ("far", f32), ("pad", i32),
+                ("volume", C.c_void_p), ("Cv", i32), ("Dv", i32), ("hv", i32), ("wv", i32),
+                ("vol_c_stride", i64), ("vol_d_stride", i64), ("vol_y_stride", i64), ("vol_x_stride", i64),
+                ("rgb", C.c_void_p), ("rgb_scale", f32), ("rgb_shift", f32),
+                ("mlp_in", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
@@ -106,6 +125,8 @@ ENTRY_POINTS = {
     "bmv_composite": CompositeParams,
     "bmv_nerf_mlp": NerfMlpParams,
     "bmv_render_rays": RenderRaysParams,
+    "bmv_cost_volume_var_img": CostVolumeImgParams,
+    "bmv_mvs_march_fetch": MvsMarchParams,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported")

@@ -340,17 +340,18 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
                   ((uintptr_t)p.out & (sizeof(OutT) == 4 ? 15 : 7)) == 0;
   const int cpt = (p.C % 8 == 0 && p.C >= 32) ? 8 : 4;
   const int CG = p.C / cpt;
-  const bool v3 = cl && p.exact_coords == 0 && threads % CG == 0 && CG <= threads && p.h <= 65535 &&
+  const int CG3 = p.C / 4;                               // v3 always uses 4 channels per lane
+  const bool v3 = cl && p.exact_coords == 0 && threads % CG3 == 0 && CG3 <= threads && p.h <= 65535 &&
                   (int64_t)p.Hs * p.feat_y_stride < (1ll << 31);
   if (v3) {
-    // plane groups: enough CTAs to fill 148 SMs x 8 CTAs, but as deep as possible for L1 reuse
-    const int vpb = threads / CG;
+    // plane groups as deep as possible (L1 reuse of the sliding texel window along d) while still
+    // launching >= ~250k lanes (148 SMs x 2048 threads = 303k resident)
+    const int vpb = threads / CG3;
     const int xchunks = (p.w + vpb - 1) / vpb;
     int DG = p.D;
-    while (DG > 4 && (int64_t)xchunks * p.h * ((p.D + DG - 1) / DG) < 2 * 148 * 4) DG = (DG + 1) / 2;
+    while (DG > 2 && (int64_t)p.w * p.h * CG3 * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
     dim3 grid(xchunks, p.h, (p.D + DG - 1) / DG);
-    if (cpt == 8) cost_volume_var_cl3_kernel<S, 8, OutT><<<grid, threads, 0, st>>>(p, CG, DG);
-    else cost_volume_var_cl3_kernel<S, 4, OutT><<<grid, threads, 0, st>>>(p, CG, DG);
+    cost_volume_var_cl3_kernel<S, 4, OutT><<<grid, threads, 0, st>>>(p, CG3, DG);
   } else if (cl) {
     if (cpt == 8) cost_volume_var_cl_kernel<S, 8, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
     else cost_volume_var_cl_kernel<S, 4, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);

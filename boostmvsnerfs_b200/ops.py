@@ -452,3 +452,79 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
     rp.mlp_weights, rp.raw = w.data_ptr(), raw.data_ptr()
     _lib.call("bmv_render_rays", rp, _stream())
     return res
+
+
+# ------------------------------------------------------------------------------------------ K1b / K3b (MVSNeRF)
+def cost_volume_var_img(feats, imgs_small, views, proj, planes, pad=24, out=None, out_dtype=torch.float32,
+                        channels_last=False):
+    """MVSNeRF 41-channel cost volume for one chain.
+    feats (N,C,h,w) any strides; imgs_small (N,3,h,w) source images resized to the feature grid;
+    views: the triple (views[0] = reference view); proj (V,3,4) in triple order; planes (D,)
+    -> (3V+C, D, h+2pad, w+2pad)  (reference lib/networks/mvsnerf/network.py:887-942)."""
+    _f32(feats, "feats")
+    imgs_small, proj, planes = _cf32(imgs_small, "imgs_small"), _cf32(proj, "proj"), _cf32(planes, "planes")
+    N, Cc, h, w = feats.shape
+    V, D = len(views), planes.numel()
+    assert imgs_small.shape == (N, 3, h, w) and proj.shape == (V, 3, 4)
+    hp, wp, Ct = h + 2 * pad, w + 2 * pad, 3 * V + Cc
+    if out is None:
+        if channels_last:
+            out = torch.empty((D, hp, wp, Ct), device=feats.device, dtype=out_dtype).permute(3, 0, 1, 2)
+        else:
+            out = torch.empty((Ct, D, hp, wp), device=feats.device, dtype=out_dtype)
+    assert out.shape == (Ct, D, hp, wp) and out.dtype in (torch.float32, torch.bfloat16)
+    p = _lib.CostVolumeImgParams()
+    p.feat = feats.data_ptr()
+    p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
+    p.img = imgs_small.data_ptr()
+    _views(p.view, views)
+    p.V, p.C, p.h, p.w, p.D, p.pad = V, Cc, h, w, D, pad
+    p.proj, p.planes, p.out = proj.data_ptr(), planes.data_ptr(), out.data_ptr()
+    p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride()
+    p.out_bf16 = 1 if out.dtype == torch.bfloat16 else 0
+    _lib.call("bmv_cost_volume_var_img", p, _stream())
+    return out
+
+
+def mvs_march_fetch(rays, S, views, src_exts, src_ixts, H, W, near, far, volume, rgb, pad=24,
+                    rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, want=("mlp_in", "z_vals", "vis_mask"), out=None):
+    """MVSNeRF marching + fetch for one chain: rays (R,8) with near/far in columns 6,7; volume
+    (8,D,h+2pad,w+2pad) any strides; rgb (N,3,H,W) raw source images.
+    Returns dict with mlp_in (n,S,86), z_vals (n,S), vis_mask (n,S) [, vis_count]."""
+    rays = _cf32(rays, "rays")
+    src_exts, src_ixts = _cf32(src_exts, "src_exts"), _cf32(src_ixts, "src_ixts")
+    dev = rays.device
+    R = rays.shape[0]
+    n = R - ray_begin if n_rays is None else n_rays
+    p = _lib.MvsMarchParams()
+    p.rays, p.ray_begin, p.n_rays = rays.data_ptr(), ray_begin, n
+    t = _linspace(S, dev)
+    p.t, p.S, p.V = t.data_ptr(), S, len(views)
+    _views(p.view, views)
+    p.src_exts, p.src_ixts = src_exts.data_ptr(), src_ixts.data_ptr()
+    p.H, p.W, p.near, p.far, p.pad = H, W, float(near), float(far), pad
+    if volume is not None:
+        _f32(volume, "volume")
+        rgb = _cf32(rgb, "rgb")
+        p.volume = volume.data_ptr()
+        p.Cv, p.Dv, p.hv, p.wv = volume.shape
+        p.vol_c_stride, p.vol_d_stride, p.vol_y_stride, p.vol_x_stride = volume.stride()
+        p.rgb = rgb.data_ptr()
+        p.rgb_scale, p.rgb_shift = rgb_affine
+    res = dict(out) if out else {}
+
+    def mk(name, shape, dtype=torch.float32):
+        if name in res:
+            tns = res[name]
+            if not (tns.is_cuda and tns.dtype == dtype and tns.is_contiguous() and tns.numel() == _numel(shape)):
+                raise BmvError(f"preallocated output {name}: need contiguous {dtype} with {_numel(shape)} elements")
+            setattr(p, name, tns.data_ptr())
+        elif name in want:
+            res[name] = torch.empty(shape, device=dev, dtype=dtype)
+            setattr(p, name, res[name].data_ptr())
+    mk("mlp_in", (n, S, 86))
+    mk("z_vals", (n, S))
+    mk("vis_mask", (n, S))
+    mk("vis_count", (n, S), torch.int32)
+    _lib.call("bmv_mvs_march_fetch", p, _stream())
+    return res

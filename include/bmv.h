@@ -246,6 +246,55 @@ typedef struct bmv_render_rays_params {
 BMV_API int bmv_render_rays(const bmv_render_rays_params* p, bmv_stream_t stream);
 BMV_API int bmv_render_rays_supported(int Cv, int Cf, int V);
 
+/* ------------------------------------------------------------------------------------------
+ * K1b  MVSNeRF cost volume with colour channels.
+ * Replaces build_volume_costvar_img + homo_warp(pad) (reference lib/networks/mvsnerf/network.py:887-942,
+ * lib/networks/mvsnerf/utils.py:580-630).  View view[0] is the reference view (unwarped, zero-padded by
+ * `pad` pixels); out = (3V + C, D, h+2pad, w+2pad): [ref rgb | warped src rgb x(V-1) | feature variance
+ * over the views whose strict in-mask holds].  Channels 0:3 are 0 in the border (the reference leaves
+ * them uninitialised).
+ */
+typedef struct bmv_cost_volume_img_params {
+  const float* feat;            /* (N,C,h,w)-like feature maps, strides below */
+  int64_t feat_view_stride, feat_c_stride, feat_y_stride, feat_x_stride;
+  const float* img;             /* (N,3,h,w) planar: source images resized to the feature grid */
+  int32_t view[BMV_MAX_VIEWS];
+  int32_t V, C, h, w, D, pad;
+  const float* proj;            /* DEVICE (V,3,4) in TRIPLE order; row 0 (reference) unused */
+  const float* planes;          /* DEVICE (D,) */
+  float* out;
+  int64_t out_c_stride, out_d_stride, out_y_stride, out_x_stride;
+  int32_t out_bf16;
+} bmv_cost_volume_img_params;
+BMV_API int bmv_cost_volume_var_img(const bmv_cost_volume_img_params* p, bmv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3b  MVSNeRF ray marching + fetch: builds the 86-wide MLP input of every sample.
+ * Replaces ray_marcher, get_ndc_coordinate(pad), index_point_feature, build_color_volume,
+ * gen_dir_feature, Embedder.embed, run_network_mvs and mask_viewport (reference
+ * lib/networks/mvsnerf/network.py:945-1001, utils.py:112-146,300-383, renderer.py:111-137,
+ * lib/networks/boost_mvsnerf/network.py:97-135).  near/far of a ray are its columns 6,7.
+ */
+typedef struct bmv_mvs_march_params {
+  const float* rays;            /* (R,8) */
+  int64_t ray_begin, n_rays;
+  const float* t; int32_t S;    /* DEVICE (S,) = torch.linspace(0,1,S) */
+  int32_t V; int32_t view[BMV_MAX_VIEWS];              /* view[0] = reference view of the volume */
+  const float* src_exts; const float* src_ixts;        /* (N,4,4), (N,3,3) DEVICE */
+  int32_t H, W;                 /* image size (render scale 1) */
+  float near, far;              /* volume depth range of this chain (NDC z normalisation) */
+  int32_t pad;
+  const float* volume; int32_t Cv, Dv, hv, wv;         /* regularised volume (8, D, h+2pad, w+2pad) */
+  int64_t vol_c_stride, vol_d_stride, vol_y_stride, vol_x_stride;
+  const float* rgb;             /* (N,3,H,W) planar source images */
+  float rgb_scale, rgb_shift;   /* 0.5,0.5 folds unpreprocess */
+  float* mlp_in;                /* (n_rays,S,86) or NULL */
+  float* z_vals;                /* (n_rays,S) or NULL */
+  float* vis_mask;              /* (n_rays,S) or NULL */
+  int32_t* vis_count;           /* (n_rays,S) or NULL */
+} bmv_mvs_march_params;
+BMV_API int bmv_mvs_march_fetch(const bmv_mvs_march_params* p, bmv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

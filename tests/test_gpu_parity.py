@@ -81,7 +81,8 @@ def test_cost_volume_vs_reference(ops, g, channels_last_in, channels_last_out):
         vol = ops.cost_volume_var(feats, TRIPLE, proj, planes, channels_last=channels_last_out)
         close(vol, g.np(f"volume_l{lvl}")[0], f"cost volume l{lvl}")
         if lvl == 0:     # shared-plane entry must agree with the per-pixel one bit for bit
-            vol_s = ops.cost_volume_var_shared(feats, TRIPLE, proj, planes[:, 0, 0].contiguous(), H // 8, W // 8)
+            vol_s = ops.cost_volume_var_shared(feats, TRIPLE, proj, planes[:, 0, 0].contiguous(), H // 8, W // 8,
+                                               channels_last=channels_last_out)
             exact(vol_s, vol, "shared planes == per-pixel planes")
 
 
