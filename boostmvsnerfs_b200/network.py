@@ -361,6 +361,51 @@ class BoostEnerfNetwork(EnerfNetwork):
         return ret
 
 
+    # ------------------------------------------------------------------ view selection
+    def forward_view_selection(self, batch, max_chains_per_pass=32):
+        """reference lib/networks/boost_enerf/network.py:22-121 (calc_mask + search_k_best_views +
+        forward_view_selection): for EVERY triple of source views run the cost-volume cascade, render the
+        per-sample visibility score into a 2-D coverage mask, then pick K triples greedily by newly
+        covered area.  Here the FPN runs once for all views (the reference re-runs it per triple), all
+        triples go through the cascade as batched chains, the MLP (whose output the reference
+        discards) is skipped, and the greedy search stays on the GPU."""
+        from .network_mvs import greedy_coverage
+        self._check_mode(batch)
+        rc = self.rc
+        inps_all = batch['all_src_inps']
+        B, N = inps_all.shape[:2]
+        if B != 1:
+            raise ValueError("view selection is defined per frame (B=1), as in the reference (network.py:118)")
+        table = _combinations(N, 3)
+        inps = inps_all[0]
+        Hh, Ww = inps.shape[-2:]
+        picked = None
+        with torch.no_grad():
+            feats = self.forward_feat(inps)
+            cams, projs = self._camera_stage(batch['all_src_exts'][0], batch['all_src_ixts'][0], batch['tar_ext'][0],
+                                             batch['tar_ixt'][0])
+            masks = {i: [] for i in range(rc.num) if rc.render_if[i]}
+            for c0 in range(0, len(table), max_chains_per_pass):
+                part = table[c0:c0 + max_chains_per_pass]
+                states = self._chain_levels(feats, projs, batch['near_far'][0], part, Hh, Ww)
+                for i, st in states.items():
+                    S, rs = rc.num_samples[i], rc.render_scale[i]
+                    H, W = int(Hh * rs), int(Ww * rs)
+                    rays = batch[f'rays_{i}'][0]
+                    for k, tr in enumerate(part):
+                        o = ops.raygen_sample_fetch(st['depth'][k], st['std'][k], st['nf'][k], rays, H, W,
+                                                    rc.depth_inv[i], S, None, None, None, cams, tr,
+                                                    want=("z_vals", "vis_mask"))
+                        m = (o['vis_mask'] / S).unsqueeze(-1).expand(-1, -1, 4).contiguous()
+                        rgbm, _, _ = ops.composite(m, o['z_vals'], rc.white_bkgd)
+                        masks[i].append(rgbm.mean(-1).view(1, H, W))
+                del states
+            for i in masks:                      # the reference keeps the LAST rendered level's pick
+                picked = greedy_coverage(torch.stack(masks[i]), rc.k_best)
+        keys = [f"{s}_{v}" for s, v in zip(batch['meta']['scene'], batch['meta']['tar_view'])]
+        return {key: picked for key in keys}
+
+
 class _NullCtx:
     def __enter__(self):
         return self

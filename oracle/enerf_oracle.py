@@ -441,3 +441,57 @@ def enerf_forward(net, batch, rc):
         out['std'] = std
         ret.update({f'{key}_level{i}': val for key, val in out.items()})
     return ret
+
+
+# --------------------------------------------------------------------------- view selection (pre-process)
+def calc_mask(net, triple, batch, rc):
+    """reference lib/networks/boost_enerf/network.py:22-69 (calc_mask): one full single-volume cascade
+    for the given triple; the per-sample visibility score is volume-rendered into a 2-D coverage
+    mask per rendered level.  (The reference also evaluates the MLP and discards its output.)"""
+    inps = batch['all_src_inps'][:, triple]
+    exts, ixts = batch['all_src_exts'][:, triple], batch['all_src_ixts'][:, triple]
+    B, N = inps.shape[:2]
+    Hh, Ww = inps.shape[-2:]
+    f2, f1, f0 = net.feature_net(inps.reshape(B * N, *inps.shape[2:]))
+    feats = {'level_1': f1.reshape(B, N, f1.shape[1], Hh // 2, Ww // 2),
+             'level_0': f2.reshape(B, N, f2.shape[1], Hh // 4, Ww // 4)}
+    depth = std = nf = None
+    out = {}
+    for i in range(rc.num):
+        D, vs = rc.volume_planes[i], rc.volume_scale[i]
+        h, w = int(Hh * vs), int(Ww * vs)
+        if depth is None:
+            planes, nf = depth_planes_first(batch['near_far'], D, h, w, rc.depth_inv[i])
+        else:
+            planes, nf = depth_planes_next(depth, std, nf, D, vs / rc.volume_scale[i - 1], rc.depth_inv[i - 1],
+                                           rc.depth_inv[i])
+        pm = proj_mats(exts, ixts, batch['tar_ext'], batch['tar_ixt'], rc.im_feat_scale[i], vs)
+        vol = cost_volume_var(feats[f'level_{i}'], pm, planes)
+        vol, logits = getattr(net, f'cost_reg_{i}')(vol)
+        depth, std = depth_regression(logits, planes, rc.depth_inv[i])
+        if not rc.render_if[i]:
+            continue
+        rays12 = build_rays(depth, std, nf, batch[f'rays_{i}'], rc.render_scale[i] / vs, rc.depth_inv[i])
+        S = rc.num_samples[i]
+        xyz, _, z = sample_along_depth(rays12, S, rc.depth_inv[i])
+        H, W = int(Hh * rc.render_scale[i]), int(Ww * rc.render_scale[i])
+        inv_scale = torch.tensor([W - 1, H - 1], dtype=torch.float32, device=xyz.device).unsqueeze(0).expand(B, -1)
+        m = mask_viewport(xyz, exts, ixts, inv_scale).reshape(B, -1, S, 1) / S
+        m = composite(m.repeat(1, 1, 1, 4), z, rc.white_bkgd)['rgb'].mean(-1)
+        out[f'mask_level{i}'] = m.reshape(B, H, W)
+    return out
+
+
+def forward_view_selection(net, batch, rc):
+    """reference lib/networks/boost_enerf/network.py:97-121 -> {"<scene>_<view>": [indices]}."""
+    from oracle.mvsnerf_oracle import search_k_best_views
+    N = batch['all_src_inps'].shape[1]
+    per_triple = [calc_mask(net, t, batch, rc) for t in torch.combinations(torch.arange(N), 3)]
+    result = {}
+    for i in range(rc.num):
+        if not rc.render_if[i]:
+            continue
+        picked = search_k_best_views([m[f'mask_level{i}'] for m in per_triple], rc.k_best)
+        for j in range(len(batch['meta']['scene'])):
+            result[f"{batch['meta']['scene'][j]}_{batch['meta']['tar_view'][j]}"] = picked
+    return result

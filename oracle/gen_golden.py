@@ -174,7 +174,14 @@ def _chain(case):
     batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in scene.items()}
     with torch.no_grad():
         ret = net(batch)
+        # view-selection pre-process of the reference (boost_enerf/network.py:22-121) on the same scene
+        vs_batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in scene.items()}
+        sel = net.forward_view_selection(vs_batch)
+        cm = net.calc_mask(torch.tensor([0, 1, 3]), {k: (v.clone() if torch.is_tensor(v) else v) for k, v in scene.items()})
     out = {f"out_{k}": _np(v) for k, v in ret.items()}
+    out["view_selection"] = np.array(sel["synth_0"], dtype=np.int64)
+    for k, v in cm.items():
+        out[f"calc_mask_013_{k}"] = _np(v)
     for k in ("all_src_inps", "all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt", "near_far", "rays_0", "rays_1"):
         out[f"in_{k}"] = _np(scene[k])
     out["k_best"] = np.array(k_best, dtype=np.int64)

@@ -118,6 +118,16 @@ def test_forward_vs_oracle_medium_scene(strict_fp32):
         _report(out[k], ref[k].numpy(), f"medium {k}", 1e-4)
 
 
+@pytest.mark.parametrize("case,rc", [("chain_eval", RenderConfig.enerf_eval(2)),
+                                     ("chain_pretrain", RenderConfig.enerf_pretrain(2))])
+def test_view_selection_matches_reference(case, rc, strict_fp32):
+    """forward_view_selection (GPU, batched over all triples, MLP skipped) picks the reference's triples."""
+    g = load_golden(f"enerf_{case}.npz")
+    net, batch = _net_and_batch(g, rc, "boost")
+    assert net.forward_view_selection(batch) == {"synth_0": g.np("view_selection").tolist()}
+    assert net.forward_view_selection(batch, max_chains_per_pass=3) == {"synth_0": g.np("view_selection").tolist()}
+
+
 def test_training_mode_and_cpu_are_refused():
     from boostmvsnerfs_b200 import network
     from boostmvsnerfs_b200.synth import make_scene

@@ -143,6 +143,19 @@ def test_boost_forward_chain(case, rc):
         same(batch[k], g.np(f"after_{k}"), f"batch[{k}] after forward")
 
 
+@pytest.mark.parametrize("case,rc", [("chain_eval", RenderConfig.enerf_eval(2)),
+                                     ("chain_pretrain", RenderConfig.enerf_pretrain(2))])
+def test_view_selection_preprocess(case, rc):
+    g = load_golden(f"enerf_{case}.npz")
+    net, batch = _load_modules(g, rc), _batch(g)
+    with torch.no_grad():
+        cm = O.calc_mask(net, torch.tensor([0, 1, 3]), batch, rc)
+        for k, v in cm.items():
+            same(v, g.np(f"calc_mask_013_{k}"), f"{case} calc_mask {k}")
+        sel = O.forward_view_selection(net, batch, rc)
+    assert sel == {"synth_0": g.np("view_selection").tolist()}
+
+
 def test_single_volume_chain():
     g = load_golden("enerf_single.npz")
     rc = RenderConfig.enerf_eval(1)
