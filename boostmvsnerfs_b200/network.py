@@ -118,7 +118,7 @@ class EnerfNetwork(nn.Module):
         inv = torch.inverse(torch.cat((p_tar, last), dim=0)[None])[0]
         return (p_src @ inv).contiguous()
 
-    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt):
+    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt, after=None):
         """All per-frame camera algebra, hoisted: homographies of every view for every cascade level
         and the camera centres.  With host_camera_algebra the ~1 KB of camera data makes one
         round trip to the host and the reference's own torch op sequence (incl. torch.inverse,
@@ -130,7 +130,14 @@ class EnerfNetwork(nn.Module):
             projs = [self._proj_all(exts, ixts, tar_ext, tar_ixt, rc.im_feat_scale[i], rc.volume_scale[i])
                      for i in range(rc.num)]
             return ops.CameraBlock(exts, ixts, tar_ext), projs
-        flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
+        if after is not None:
+            if getattr(self, '_side_stream', None) is None or self._side_stream.device != dev:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            self._side_stream.wait_event(after)
+            with torch.cuda.stream(self._side_stream):
+                flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
+        else:
+            flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
         h_exts = flat[:N * 16].view(N, 4, 4)
         h_ixts = flat[N * 16:N * 25].view(N, 3, 3)
         h_text = flat[N * 25:N * 25 + 16].view(4, 4)
@@ -152,10 +159,12 @@ class EnerfNetwork(nn.Module):
         Returns per rendered level: dict(raws, masks, zs lists over K, depth/std of chain 0)."""
         rc = self.rc
         Hh, Ww = inps.shape[-2:]
+        ready = torch.cuda.current_stream().record_event()      # camera tensors are valid from here on
         with self._stage('feature_net'):
             feats = self.forward_feat(inps)
         with self._stage('camera'):
-            cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt)
+            # the host round trip runs on a side stream that only waits for `ready`, so it overlaps the FPN
+            cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt, after=ready)
         states = self._chain_levels(feats, projs, near_far, triples, Hh, Ww)
         out = {}
         for i, st in states.items():
