@@ -272,88 +272,82 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volum
   }
 }
 
-// v4: as v3, but the bilinear tap set of a (voxel, view, plane) is computed ONCE by one thread and
-// shared through shared memory instead of once per channel lane (ncu on v3: issue-bound, 406
-// instructions per lane and plane, ~60 % of them the tap arithmetic repeated by all CG lanes).
-// Per round the CTA handles PB planes: phase 1, VPB*S*PB threads fill the tap table (int4 offsets +
-// float4 weights); phase 2, all 256 threads (VPB voxels x CG lanes) gather 4 x float4 per view and
-// write one float4 of variance.  Two barriers per round.
-template <int S, int VPB, int PB, typename OutT>
-__global__ void __launch_bounds__(256) cost_volume_var_cl4_kernel(bmv_cost_volume_params p, int DG) {
-  constexpr int CG = 256 / VPB;                          // lanes per voxel, 4 channels each
+// v5: as v3, but the bilinear tap set of a (voxel, view, plane) is computed ONCE per warp and handed
+// to the channel lanes with warp shuffles (ncu on v3: issue-bound, 406 instructions per lane and
+// plane, ~2/3 of them the tap arithmetic repeated by all CG lanes of a voxel; a CTA-level tap table
+// in shared memory (v4, two barriers per plane) fixed the instruction count but exposed barrier
+// latency on the 8-plane level: 84 us vs 75 us).
+// A warp owns VW = 32/CG consecutive x; per round it handles PB planes so that VW*S*PB <= 32 tap
+// tasks fill the warp: lane L computes task (plane slot, view, voxel) = (L / (VW*S), (L % (VW*S)) / VW,
+// L % VW); the consumer lane of voxel v fetches its 4 offsets + 4 weights per view with 8 shuffles.
+template <int S, int CG, int PB, typename OutT>
+__global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volume_params p, int DG) {
+  constexpr int VW = 32 / CG;                            // voxels per warp
+  constexpr int TASKS = VW * S * PB;
+  static_assert(TASKS <= 32, "tap tasks must fit one warp");
   __shared__ float sP[S * 12];
-  __shared__ int4 s_off[PB][S][VPB];
-  __shared__ float4 s_w[PB][S][VPB];
   if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
   __syncthreads();
-  const int tid = threadIdx.x;
-  const int x_base = blockIdx.x * VPB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x_base = (blockIdx.x * 8 + warp) * VW;
   const int y = blockIdx.y;
+  if (x_base >= p.w) return;                             // whole warp out of the row
   const int d_begin = blockIdx.z * DG, d_end = min(p.D, d_begin + DG);
   const float sx = 2.f / (float)(p.Ws - 1), sy = 2.f / (float)(p.Hs - 1);
   const int ys = (int)p.feat_y_stride, xs = (int)p.feat_x_stride;
-  // phase-1 role: (plane slot, view, voxel)
-  const bool tapper = tid < VPB * S * PB;
-  const int t_pl = tid / (VPB * S), t_s = (tid % (VPB * S)) / VPB, t_v = tid % VPB;
-  const int t_x = x_base + t_v;
-  float ax = 0.f, ay = 0.f, az = 0.f;
-  const float* tP = sP + t_s * 12;
-  if (tapper) {
-    ax = dot3_gemm(tP[0], tP[1], tP[2], (float)t_x, (float)y, 1.f);
-    ay = dot3_gemm(tP[4], tP[5], tP[6], (float)t_x, (float)y, 1.f);
-    az = dot3_gemm(tP[8], tP[9], tP[10], (float)t_x, (float)y, 1.f);
-  }
-  const float* t_planes = p.planes + ((int64_t)y * p.w + min(t_x, p.w - 1)) * p.planes_pix_stride;
-  // phase-2 role: (voxel, channel lane)
-  const int v = tid / CG, c0 = (tid % CG) * 4;
+  // ---- tap-task role of this lane
+  const bool tapper = lane < TASKS;
+  const int t_pl = lane / (VW * S), t_s = (lane % (VW * S)) / VW, t_v = lane % VW;
+  const int t_x = min(x_base + t_v, p.w - 1);
+  const float* tP = sP + (tapper ? t_s : 0) * 12;
+  const float ax = dot3_gemm(tP[0], tP[1], tP[2], (float)t_x, (float)y, 1.f);
+  const float ay = dot3_gemm(tP[4], tP[5], tP[6], (float)t_x, (float)y, 1.f);
+  const float az = dot3_gemm(tP[8], tP[9], tP[10], (float)t_x, (float)y, 1.f);
+  const float* t_planes = p.planes + ((int64_t)y * p.w + t_x) * p.planes_pix_stride;
+  // ---- consumer role: voxel v of the warp, 4 channels starting at c0
+  const int v = lane / CG, c0 = (lane % CG) * 4;
   const int x = x_base + v;
   const bool active = x < p.w;
   const float* base[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) base[s] = p.feat + (int64_t)p.view[s] * p.feat_view_stride + c0;
-  OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)x * p.out_x_stride + c0;
+  OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   constexpr float invS = 1.f / S;
   for (int d0 = d_begin; d0 < d_end; d0 += PB) {
-    if (tapper) {
-      const int d = d0 + t_pl;
-      FastTap t;
-      if (d < d_end && t_x < p.w) {
-        const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
-        t = fast_taps(ax, ay, az, tP, idep, sx, sy, p.Hs, p.Ws, ys, xs);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { t.off[i] = 0; t.w[i] = 0.f; }
-      }
-      s_off[t_pl][t_s][t_v] = make_int4(t.off[0], t.off[1], t.off[2], t.off[3]);
-      s_w[t_pl][t_s][t_v] = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+    FastTap t;
+    {
+      const int d = min(d0 + t_pl, d_end - 1);
+      const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
+      t = fast_taps(ax, ay, az, tP, idep, sx, sy, p.Hs, p.Ws, ys, xs);
     }
-    __syncthreads();
-    if (active) {
 #pragma unroll
-      for (int pl = 0; pl < PB; ++pl) {
-        const int d = d0 + pl;
-        if (d >= d_end) break;
-        float4 sum, sq;
+    for (int pl = 0; pl < PB; ++pl) {
+      const int d = d0 + pl;
+      float4 sum, sq;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const int4 o = s_off[pl][s][v];
-          const float4 w = s_w[pl][s][v];
-          const float4 a = __ldg(reinterpret_cast<const float4*>(base[s] + o.x));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(base[s] + o.y));
-          const float4 c = __ldg(reinterpret_cast<const float4*>(base[s] + o.z));
-          const float4 e = __ldg(reinterpret_cast<const float4*>(base[s] + o.w));
-          const float v0 = fmaf(w.w, e.x, fmaf(w.z, c.x, fmaf(w.y, b.x, w.x * a.x)));
-          const float v1 = fmaf(w.w, e.y, fmaf(w.z, c.y, fmaf(w.y, b.y, w.x * a.y)));
-          const float v2 = fmaf(w.w, e.z, fmaf(w.z, c.z, fmaf(w.y, b.z, w.x * a.z)));
-          const float v3 = fmaf(w.w, e.w, fmaf(w.z, c.w, fmaf(w.y, b.w, w.x * a.w)));
-          if (s == 0) {
-            sum = make_float4(v0, v1, v2, v3);
-            sq = make_float4(v0 * v0, v1 * v1, v2 * v2, v3 * v3);
-          } else {
-            sum.x += v0; sum.y += v1; sum.z += v2; sum.w += v3;
-            sq.x = fmaf(v0, v0, sq.x); sq.y = fmaf(v1, v1, sq.y); sq.z = fmaf(v2, v2, sq.z); sq.w = fmaf(v3, v3, sq.w);
-          }
+      for (int s = 0; s < S; ++s) {
+        const int src = pl * VW * S + s * VW + v;
+        const int o0 = __shfl_sync(0xffffffffu, t.off[0], src), o1 = __shfl_sync(0xffffffffu, t.off[1], src);
+        const int o2 = __shfl_sync(0xffffffffu, t.off[2], src), o3 = __shfl_sync(0xffffffffu, t.off[3], src);
+        const float w0 = __shfl_sync(0xffffffffu, t.w[0], src), w1 = __shfl_sync(0xffffffffu, t.w[1], src);
+        const float w2 = __shfl_sync(0xffffffffu, t.w[2], src), w3 = __shfl_sync(0xffffffffu, t.w[3], src);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base[s] + o0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(base[s] + o1));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(base[s] + o2));
+        const float4 e = __ldg(reinterpret_cast<const float4*>(base[s] + o3));
+        const float v0 = fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x)));
+        const float v1 = fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y)));
+        const float v2 = fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z)));
+        const float v3 = fmaf(w3, e.w, fmaf(w2, c.w, fmaf(w1, b.w, w0 * a.w)));
+        if (s == 0) {
+          sum = make_float4(v0, v1, v2, v3);
+          sq = make_float4(v0 * v0, v1 * v1, v2 * v2, v3 * v3);
+        } else {
+          sum.x += v0; sum.y += v1; sum.z += v2; sum.w += v3;
+          sq.x = fmaf(v0, v0, sq.x); sq.y = fmaf(v1, v1, sq.y); sq.z = fmaf(v2, v2, sq.z); sq.w = fmaf(v3, v3, sq.w);
         }
+      }
+      if (active && d < d_end) {
         float4 var;
         { const float m = sum.x * invS; var.x = fmaf(-m, m, sq.x * invS); }
         { const float m = sum.y * invS; var.y = fmaf(-m, m, sq.y * invS); }
@@ -371,7 +365,6 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl4_kernel(bmv_cost_volum
         }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -454,12 +447,17 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
     int DG = p.D;
     while (DG > 2 && (int64_t)p.w * p.h * CG3 * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
     dim3 grid(xchunks, p.h, (p.D + DG - 1) / DG);
-    if (CG3 == 8 && S <= 4)        // C = 32: 32 voxels x 8 lanes, 2 planes per round (S*32*2 <= 256 tap threads)
-      cost_volume_var_cl4_kernel<S, 32, 2, OutT><<<grid, threads, 0, st>>>(p, DG);
-    else if (CG3 == 4 && S <= 4)   // C = 16: 64 voxels x 4 lanes, 1 plane per round
-      cost_volume_var_cl4_kernel<S, 64, 1, OutT><<<grid, threads, 0, st>>>(p, DG);
-    else
-      cost_volume_var_cl3_kernel<S, 4, OutT><<<grid, threads, 0, st>>>(p, CG3, DG);
+    if constexpr (S <= 4) {
+      if (CG3 == 8) {              // C = 32: warp = 4 voxels x 8 lanes, 2 planes per round
+        cost_volume_var_cl5_kernel<S, 8, 2, OutT><<<grid, threads, 0, st>>>(p, DG);
+        return check_launch("bmv_cost_volume_var");
+      }
+      if (CG3 == 4) {              // C = 16: warp = 8 voxels x 4 lanes, 1 plane per round
+        cost_volume_var_cl5_kernel<S, 4, 1, OutT><<<grid, threads, 0, st>>>(p, DG);
+        return check_launch("bmv_cost_volume_var");
+      }
+    }
+    cost_volume_var_cl3_kernel<S, 4, OutT><<<grid, threads, 0, st>>>(p, CG3, DG);
   } else if (cl) {
     if (cpt == 8) cost_volume_var_cl_kernel<S, 8, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);
     else cost_volume_var_cl_kernel<S, 4, OutT><<<(unsigned)ceil_div64(nvox * CG, threads), threads, 0, st>>>(p, CG);

@@ -183,7 +183,7 @@ __device__ __forceinline__ float4 nerf_mlp_eval(const float* __restrict__ sw, co
   const float colb = sw[L::OFF_COLB];
 #pragma unroll
   for (int v = 0; v < V; ++v) cl[v] = colb;
-#pragma unroll 1
+#pragma unroll 2
   for (int j = 0; j < 64; ++j) {
     const float* row = sw + L::OFF_COL + j * L::CROW;
     const float4 tail = lds4(row + 88 + L::FVP);         // bias, color.2 weight
