@@ -114,6 +114,11 @@ class MvsMarchParams(C.Structure):
                 ("mlp_in", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
 
 
+class FpnTopdownParams(C.Structure):
+    _fields_ = [("prev", C.c_void_p), ("lateral_in", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("N", i32), ("H", i32), ("W", i32), ("Cin", i32), ("out", C.c_void_p)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
@@ -127,6 +132,7 @@ ENTRY_POINTS = {
     "bmv_render_rays": RenderRaysParams,
     "bmv_cost_volume_var_img": CostVolumeImgParams,
     "bmv_mvs_march_fetch": MvsMarchParams,
+    "bmv_fpn_topdown": FpnTopdownParams,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported")

@@ -33,6 +33,37 @@ def _fold_pair(conv, bn, transposed=False):
     conv.bias = nn.Parameter(b, requires_grad=False)
 
 
+class S2DConv5x5(nn.Module):
+    """A 5x5 / stride-2 / pad-2 convolution (+bias, +ReLU) evaluated as space-to-depth(2) followed by a
+    3x3 / stride-1 / pad-1 convolution on 4x the channels — the same products, regrouped:
+        y[i] = sum_ky W[ky] x[2i+ky-2],  ky = 2a+p  ->  sum_{a in 0..2} sum_{p in 0,1} W6[2a+p] z[i+a-1, p],
+    z[i,p] = x[2i+p], W6 = W zero-padded to 6 taps.  Why: cuDNN's heuristics pick an FFT-tiling algorithm
+    for the FPN's 16->32 5x5/s2 layer at 272x480 (181 launches, 2.3 ms of the 4.9 ms FPN on B200,
+    profiles/round1_fpn_layers.md); the regrouped 64->32 3x3 layer runs on its tensor-core path."""
+
+    def __init__(self, conv, relu=True):
+        super().__init__()
+        assert conv.kernel_size == (5, 5) and conv.stride == (2, 2) and conv.padding == (2, 2) and conv.groups == 1
+        w = conv.weight.detach()
+        o, c = w.shape[:2]
+        w6 = torch.zeros((o, c, 6, 6), dtype=w.dtype, device=w.device)
+        w6[:, :, :5, :5] = w
+        # channel order of the space-to-depth tensor: (py, px, c)
+        w3 = w6.view(o, c, 3, 2, 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(o, 4 * c, 3, 3)
+        self.weight = nn.Parameter(w3.contiguous(), requires_grad=False)
+        self.bias = None if conv.bias is None else nn.Parameter(conv.bias.detach().clone(), requires_grad=False)
+        self.relu = relu
+
+    def forward(self, x):
+        N, C, H, W = x.shape
+        if H % 2 or W % 2:
+            raise ValueError("space-to-depth needs even H and W")
+        z = x.permute(0, 2, 3, 1).reshape(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5)
+        z = z.reshape(N, H // 2, W // 2, 4 * C).permute(0, 3, 1, 2)          # NCHW view, channels-last memory
+        y = torch.nn.functional.conv2d(z, self.weight, self.bias, stride=1, padding=1)
+        return torch.relu_(y) if self.relu else y
+
+
 def folded_copy(module, memory_format=None):
     """Deep copy of a FeatureNet / (Min)CostRegNet with every conv+BN pair folded."""
     m = copy.deepcopy(module).eval()
@@ -45,11 +76,38 @@ def folded_copy(module, memory_format=None):
                   and isinstance(mod[1], nn.BatchNorm3d)):
                 _fold_pair(mod[0], mod[1], transposed=True)
                 mod[1] = nn.Identity()
+        if memory_format == torch.channels_last:
+            # FPN: regroup the stride-2 5x5 layers (after folding they are conv+bias followed by ReLU)
+            for parent in list(m.modules()):
+                for name, child in list(parent.named_children()):
+                    if (isinstance(child, _CBR) and isinstance(child.conv, nn.Conv2d) and isinstance(child.bn, nn.Identity)
+                            and child.conv.kernel_size == (5, 5) and child.conv.stride == (2, 2)):
+                        setattr(parent, name, S2DConv5x5(child.conv, relu=True))
     if memory_format is not None:
         m = m.to(memory_format=memory_format)
     for p in m.parameters():
         p.requires_grad_(False)
     return m
+
+
+class FusedTopDownFPN(nn.Module):
+    """FeatureNet forward with each `_upsample_add(x, lat(c))` step done by one libbmv launch
+    (csrc/fpn.cu).  Wraps a folded, channels-last FeatureNet copy; CUDA only."""
+
+    def __init__(self, fpn):
+        super().__init__()
+        self.fpn = fpn
+
+    def forward(self, x):
+        from . import ops
+        f = self.fpn
+        c0 = f.conv0(x)
+        c1 = f.conv1(c0)
+        c2 = f.conv2(c1)
+        quarter = f.toplayer(c2)
+        half = ops.fpn_topdown(quarter, c1, f.lat1.weight, f.lat1.bias)
+        full = ops.fpn_topdown(half, c0, f.lat0.weight, f.lat0.bias)
+        return quarter, f.smooth1(half), f.smooth0(full)
 
 
 class PlanCache:
@@ -66,5 +124,10 @@ class PlanCache:
         key = (self._key(module), memory_format)
         hit = self._c.get(name)
         if hit is None or hit[0] != key:
-            self._c[name] = (key, folded_copy(module, memory_format))
+            plan = folded_copy(module, memory_format)
+            from .modules import FeatureNet
+            if isinstance(module, FeatureNet) and memory_format == torch.channels_last and \
+                    next(module.parameters()).is_cuda:
+                plan = FusedTopDownFPN(plan)
+            self._c[name] = (key, plan)
         return self._c[name][1]

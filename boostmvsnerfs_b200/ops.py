@@ -528,3 +528,25 @@ def mvs_march_fetch(rays, S, views, src_exts, src_ixts, H, W, near, far, volume,
     mk("vis_count", (n, S), torch.int32)
     _lib.call("bmv_mvs_march_fetch", p, _stream())
     return res
+
+
+# ------------------------------------------------------------------------------------------ FPN top-down fusion
+def fpn_topdown(prev, lateral_in, weight, bias):
+    """out = bilinear_up2x(prev, align_corners=True) + conv1x1(lateral_in, weight, bias)
+    (reference lib/networks/enerf/feature_net.py:24-33).  prev (N,32,H/2,W/2) and lateral_in (N,Cin,H,W)
+    must be channels_last; weight (32,Cin[,1,1]); returns (N,32,H,W) channels_last."""
+    _f32(prev, "prev"); _f32(lateral_in, "lateral_in")
+    N, Cin, H, W = lateral_in.shape
+    if not (prev.is_contiguous(memory_format=torch.channels_last) and lateral_in.is_contiguous(memory_format=torch.channels_last)):
+        raise BmvError("fpn_topdown: inputs must be channels_last")
+    assert prev.shape == (N, 32, H // 2, W // 2), prev.shape
+    w = _cf32(weight.reshape(32, Cin), "weight")
+    b = _cf32(bias, "bias") if bias is not None else None
+    out = torch.empty((N, 32, H, W), device=prev.device, memory_format=torch.channels_last)
+    p = _lib.FpnTopdownParams()
+    p.prev, p.lateral_in, p.weight = prev.data_ptr(), lateral_in.data_ptr(), w.data_ptr()
+    p.bias = b.data_ptr() if b is not None else 0
+    p.N, p.H, p.W, p.Cin = N, H, W, Cin
+    p.out = out.data_ptr()
+    _lib.call("bmv_fpn_topdown", p, _stream())
+    return out

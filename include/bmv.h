@@ -295,6 +295,18 @@ typedef struct bmv_mvs_march_params {
 } bmv_mvs_march_params;
 BMV_API int bmv_mvs_march_fetch(const bmv_mvs_march_params* p, bmv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused top-down step of the feature pyramid: out = up2x(prev) + conv1x1(lateral_in) + bias
+ * (`_upsample_add(x, lat(c))`, reference lib/networks/enerf/feature_net.py:24-33).  All tensors
+ * channels-last (N,H,W,C) fp32, 32 output channels; prev is (N,H/2,W/2,32); weight (32,Cin) row-major.
+ */
+typedef struct bmv_fpn_topdown_params {
+  const float* prev; const float* lateral_in; const float* weight; const float* bias;
+  int32_t N, H, W, Cin;
+  float* out;                   /* (N,H,W,32) */
+} bmv_fpn_topdown_params;
+BMV_API int bmv_fpn_topdown(const bmv_fpn_topdown_params* p, bmv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -347,3 +347,39 @@ def test_fused_render_matches_unfused_path(ops, g):
     # a ray sub-range lands in the same place
     part = ops.render_rays(*args, mlp_pack.pack_nerf_weights(net), ray_begin=1000, n_rays=777)
     exact(part["raw"], f["raw"][1000:1777], "ray sub-range")
+
+
+# ------------------------------------------------------------------------------------------ FPN fusion
+@pytest.mark.parametrize("cin,hw", [(8, (64, 96)), (16, (34, 50))])
+def test_fpn_topdown_vs_torch(ops, cin, hw):
+    H_, W_ = hw
+    torch.manual_seed(cin)
+    prev = torch.randn(2, 32, H_ // 2, W_ // 2, device="cuda").contiguous(memory_format=torch.channels_last)
+    lat_in = torch.randn(2, cin, H_, W_, device="cuda").contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(cin, 32, 1).cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        ref = torch.nn.functional.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=True) + conv(lat_in)
+    torch.backends.cudnn.allow_tf32 = old
+    out = ops.fpn_topdown(prev, lat_in, conv.weight, conv.bias)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    close(out, ref, "fused top-down step", rtol=1e-5)
+
+
+def test_inference_plan_fpn_matches_stock_module():
+    from boostmvsnerfs_b200.inference_plan import PlanCache
+    from boostmvsnerfs_b200.modules import FeatureNet
+    torch.manual_seed(1)
+    net = FeatureNet().cuda().eval()
+    x = torch.randn(3, 3, 64, 96, device="cuda")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        ref = net(x)
+        plan = PlanCache().get("feature_net", net, torch.channels_last)
+        got = plan(x.contiguous(memory_format=torch.channels_last))
+    torch.backends.cudnn.allow_tf32 = old
+    assert type(plan).__name__ == "FusedTopDownFPN"
+    for a, b in zip(got, ref):
+        close(a, b, "planned FPN vs stock FPN", rtol=1e-5)
