@@ -1,0 +1,96 @@
+"""CUDA-graph replay of one boosted frame.
+
+The reference's frame cannot be captured: it has ~100 implicit host syncs per frame.
+Ours has none once the camera algebra is hoisted, so the whole frame — FPN, K cost-volume chains,
+3-D CNNs, K3+K5, K4: ~300 launches — is captured once per (shape, selected triples) and replayed.
+Per frame the host then only (1) copies the new batch into the static input buffers (for a host
+batch this IS the H2D upload), (2) runs the ~1 KB camera algebra and uploads it, (3) replays.
+Kernels read cameras from device memory (include/bmv.h conventions), which is what keeps the captured
+graph valid across frames.
+"""
+import torch
+
+from .network import BoostEnerfNetwork, _combinations
+
+_STATIC_KEYS = ("all_src_inps", "all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt", "near_far")
+
+
+class FrameGraph:
+    def __init__(self, net: BoostEnerfNetwork):
+        if not isinstance(net, BoostEnerfNetwork):
+            raise TypeError("FrameGraph wraps a BoostEnerfNetwork")
+        self.net = net
+        self._cache = {}
+
+    def _key(self, batch, triples):
+        return (tuple(batch["all_src_inps"].shape), tuple(triples),
+                tuple(tuple(batch[f"rays_{i}"].shape) for i in range(self.net.rc.num)))
+
+    def _triples(self, batch):
+        net, rc = self.net, self.net.rc
+        N = batch["all_src_inps"].shape[1]
+        table = _combinations(N, rc.cost_volume_input_views)
+        key = f"{batch['meta']['scene'][0]}_{batch['meta']['tar_view'][0]}"
+        return [table[int(j)] for j in net.view_selection_outputs[key][:rc.k_best]]
+
+    def _build(self, batch, triples):
+        net, rc = self.net, self.net.rc
+        dev = next(net.parameters()).device
+        st = {k: torch.empty_like(batch[k], device=dev) for k in _STATIC_KEYS}
+        for i in range(rc.num):
+            st[f"rays_{i}"] = torch.empty_like(batch[f"rays_{i}"], device=dev)
+        N = st["all_src_inps"].shape[1]
+        n_cam = rc.num * N * 12 + N * 3 + 3
+        cam_dev = torch.zeros(n_cam, device=dev)
+        cam_host = torch.zeros(n_cam).pin_memory()
+        entry = {"static": st, "cam_dev": cam_dev, "cam_host": cam_host, "graph": None, "out": None}
+
+        def body():
+            camera = net._camera_views(cam_dev, st["all_src_exts"][0], st["all_src_ixts"][0])
+            lv = net._render_frame(st["all_src_inps"][0], st["all_src_exts"][0], st["all_src_ixts"][0], st["tar_ext"][0],
+                                   st["tar_ixt"][0], st["near_far"][0], [st[f"rays_{i}"][0] for i in range(rc.num)],
+                                   triples, camera=camera)
+            return net._assemble([lv])
+
+        self._load(entry, batch)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                      # warm-up: plan caches, cuDNN handles, allocator pools
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            entry["out"] = body()
+        entry["graph"] = g
+        return entry
+
+    def _load(self, entry, batch):
+        net = self.net
+        st = entry["static"]
+        for k, t in st.items():
+            t.copy_(batch[k], non_blocking=True)
+        N = st["all_src_inps"].shape[1]
+        cams = [batch[k] for k in ("all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt")]
+        if all(c.device.type == "cpu" for c in cams):
+            flat = torch.cat([c.reshape(-1) for c in cams])
+        else:
+            flat = torch.cat([c.reshape(-1).to(st["near_far"].device) for c in cams]).cpu()
+        entry["cam_host"].copy_(net._camera_host(flat, N))
+        entry["cam_dev"].copy_(entry["cam_host"], non_blocking=True)
+
+    def __call__(self, batch):
+        """batch: tensors on the GPU or in (pinned) host memory; B must be 1.  Returns the output dict;
+        the tensors are the graph's static outputs and are overwritten by the next call."""
+        if self.net.training:
+            raise RuntimeError("inference-only")
+        if batch["all_src_inps"].shape[0] != 1:
+            raise ValueError("FrameGraph renders one frame (B=1) per call")
+        triples = self._triples(batch)
+        key = self._key(batch, triples)
+        entry = self._cache.get(key)
+        if entry is None:
+            entry = self._cache[key] = self._build(batch, triples)
+        self._load(entry, batch)
+        entry["graph"].replay()
+        return entry["out"]

@@ -138,6 +138,13 @@ class EnerfNetwork(nn.Module):
                 flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
         else:
             flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
+        packed = self._camera_host(flat, N).pin_memory().to(dev, non_blocking=True)
+        return self._camera_views(packed, exts, ixts)
+
+    def _camera_host(self, flat, N):
+        """Host part of the camera stage: flat = [exts (N*16), ixts (N*9), tar_ext (16), tar_ixt (9)] on the
+        CPU -> packed [homographies per level (N*12 each), source centres (N*3), target centre (3)]."""
+        rc = self.rc
         h_exts = flat[:N * 16].view(N, 4, 4)
         h_ixts = flat[N * 16:N * 25].view(N, 3, 3)
         h_text = flat[N * 25:N * 25 + 16].view(4, 4)
@@ -146,7 +153,11 @@ class EnerfNetwork(nn.Module):
                  for i in range(rc.num)]
         parts.append(torch.stack([e.inverse()[:3, 3] for e in h_exts]).reshape(-1))
         parts.append(h_text.inverse()[:3, 3])
-        packed = torch.cat(parts).pin_memory().to(dev, non_blocking=True)
+        return torch.cat(parts)
+
+    def _camera_views(self, packed, exts, ixts):
+        rc = self.rc
+        N = exts.shape[0]
         projs = [packed[i * N * 12:(i + 1) * N * 12].view(N, 3, 4) for i in range(rc.num)]
         off = rc.num * N * 12
         cams = ops.CameraBlock(exts, ixts, centers=packed[off:off + N * 3].view(N, 3),
@@ -154,17 +165,23 @@ class EnerfNetwork(nn.Module):
         return cams, projs
 
     # ------------------------------------------------------------------ the K-chain engine
-    def _render_frame(self, inps, exts, ixts, tar_ext, tar_ixt, near_far, rays_by_level, triples):
+    def _render_frame(self, inps, exts, ixts, tar_ext, tar_ixt, near_far, rays_by_level, triples, camera=None):
         """One batch element.  inps (N,3,H,W); triples: list of K tuples of view ids.
-        Returns per rendered level: dict(raws, masks, zs lists over K, depth/std of chain 0)."""
+        Returns per rendered level: dict(raws, masks, zs lists over K, depth/std of chain 0).
+        `camera` = (cams, projs) precomputed by the caller (CUDA-graph replay, graph.py) skips the
+        host round trip, which makes this function capturable."""
         rc = self.rc
         Hh, Ww = inps.shape[-2:]
-        ready = torch.cuda.current_stream().record_event()      # camera tensors are valid from here on
+        if camera is None:
+            ready = torch.cuda.current_stream().record_event()      # camera tensors are valid from here on
         with self._stage('feature_net'):
             feats = self.forward_feat(inps)
         with self._stage('camera'):
-            # the host round trip runs on a side stream that only waits for `ready`, so it overlaps the FPN
-            cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt, after=ready)
+            if camera is not None:
+                cams, projs = camera
+            else:
+                # the host round trip runs on a side stream that only waits for `ready`, so it overlaps the FPN
+                cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt, after=ready)
         states = self._chain_levels(feats, projs, near_far, triples, Hh, Ww)
         out = {}
         for i, st in states.items():
@@ -339,21 +356,7 @@ class BoostEnerfNetwork(EnerfNetwork):
                 per_b.append(self._render_frame(inps[b], batch['all_src_exts'][b], batch['all_src_ixts'][b],
                                                 batch['tar_ext'][b], batch['tar_ixt'][b], batch['near_far'][b],
                                                 [batch[f'rays_{i}'][b] for i in range(rc.num)], triples))
-            if rc.white_bkgd:
-                raise NotImplementedError   # reference lib/networks/enerf/utils.py:660-661
-            for i in range(rc.num):
-                if not rc.render_if[i]:
-                    continue
-                rgb, dep, wts, dmvs, sd = [], [], [], [], []
-                for lv in per_b:
-                    with self._stage(f'composite_blend_l{i}'):
-                        r, d, w = ops.composite_blend(lv[i]['raws'], lv[i]['masks'], lv[i]['zs'])
-                    rgb.append(r); dep.append(d); wts.append(w)
-                    dmvs.append(1. / lv[i]['depth0'] if rc.depth_inv[i] else lv[i]['depth0'])
-                    sd.append(lv[i]['std0'])
-                ret.update({f'rgb_level{i}': torch.stack(rgb), f'depth_level{i}': torch.stack(dep),
-                            f'weights_level{i}': torch.stack(wts), f'depth_mvs_level{i}': torch.stack(dmvs),
-                            f'std_level{i}': torch.stack(sd)})
+            ret = self._assemble(per_b)
             # the reference leaves the LAST triple in the batch (evaluators read batch['src_inps'].shape);
             # done last so the index upload cannot stall the kernels above
             last = [list(table[int(k_best[b][K - 1])]) for b in range(B)]
@@ -369,6 +372,28 @@ class BoostEnerfNetwork(EnerfNetwork):
                 batch['src_ixts'] = batch['all_src_ixts'][bidx, lt]
         return ret
 
+
+    def _assemble(self, per_b):
+        """K4 over the K chains of every batch element + the reference's output dict
+        (reference lib/networks/boost_enerf/network.py:226-235)."""
+        rc = self.rc
+        if rc.white_bkgd:
+            raise NotImplementedError   # reference lib/networks/enerf/utils.py:660-661
+        ret = {}
+        for i in range(rc.num):
+            if not rc.render_if[i]:
+                continue
+            rgb, dep, wts, dmvs, sd = [], [], [], [], []
+            for lv in per_b:
+                with self._stage(f'composite_blend_l{i}'):
+                    r, d, w = ops.composite_blend(lv[i]['raws'], lv[i]['masks'], lv[i]['zs'])
+                rgb.append(r); dep.append(d); wts.append(w)
+                dmvs.append(1. / lv[i]['depth0'] if rc.depth_inv[i] else lv[i]['depth0'])
+                sd.append(lv[i]['std0'])
+            ret.update({f'rgb_level{i}': torch.stack(rgb), f'depth_level{i}': torch.stack(dep),
+                        f'weights_level{i}': torch.stack(wts), f'depth_mvs_level{i}': torch.stack(dmvs),
+                        f'std_level{i}': torch.stack(sd)})
+        return ret
 
     # ------------------------------------------------------------------ view selection (SURVEY.md §8 f1)
     def forward_view_selection(self, batch, max_chains_per_pass=32):
