@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--stage-report", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--mlp-engine", default=None, choices=["mma", "fma"], help="override Network.mlp_engine")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
                     help="also time the reference's op sequence (oracle restatement) as eager PyTorch on this GPU")
     return ap.parse_args()
@@ -274,6 +275,8 @@ def main_ours(args):
     torch.manual_seed(0)
     net = network.BoostEnerfNetwork(preprocess=True, rc=rc).eval().to(dev)
     net.view_selection_outputs = {"synth_0": wl["k_best"]}
+    if args.mlp_engine:
+        net.mlp_engine = args.mlp_engine
     timer = StageTimer()
     net.stage_timer = timer
     ktimer = KernelTimer(torch)
@@ -425,6 +428,7 @@ def main_ours(args):
     order = {"bmv_cost_volume_var": ["cost_volume_l0", "cost_volume_l1"],
              "bmv_depth_regression": ["depth_regression_l0", "depth_regression_l1"],
              "bmv_render_rays": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
+             "bmv_render_rays_mma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_raygen_sample_fetch": [f"raygen_fetch_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_composite_blend": [f"composite_blend_l{i}" for i in range(rc.num) if rc.render_if[i]]}
     for entry, names in order.items():

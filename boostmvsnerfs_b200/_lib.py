@@ -130,12 +130,13 @@ ENTRY_POINTS = {
     "bmv_composite": CompositeParams,
     "bmv_nerf_mlp": NerfMlpParams,
     "bmv_render_rays": RenderRaysParams,
+    "bmv_render_rays_mma": RenderRaysParams,
     "bmv_cost_volume_var_img": CostVolumeImgParams,
     "bmv_mvs_march_fetch": MvsMarchParams,
     "bmv_fpn_topdown": FpnTopdownParams,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
-                 "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported")
+                 "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words")
 
 _lib = None
 
@@ -158,6 +159,7 @@ def load():
     lib.bmv_launch_count.restype = C.c_uint64
     lib.bmv_nerf_mlp_weight_count.restype = C.c_int
     lib.bmv_nerf_mlp_weight_count.argtypes = [C.c_int]
+    lib.bmv_render_rays_mma_weight_words.restype = C.c_int
     lib.bmv_render_rays_supported.restype = C.c_int
     lib.bmv_render_rays_supported.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.bmv_sizeof_params.restype = C.c_int
@@ -166,7 +168,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(struct), C.c_void_p]
         fn.restype = C.c_int
-        native = lib.bmv_sizeof_params(name.encode())
+        native = lib.bmv_sizeof_params(name.replace("_mma", "").encode())
         if native != C.sizeof(struct):
             raise BmvError(f"ABI mismatch for {name}: library struct is {native} B, binding is {C.sizeof(struct)} B")
     _lib = lib

@@ -1,0 +1,397 @@
+// K3+K5 on tensor cores: the fused gather + per-sample MLP of render_fused.cu with every Linear layer
+// evaluated by warp-level MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulate) instead of fp32
+// FMAs.  ncu on the fp32-FMA kernel (profiles/round1c): 790 M warp instructions per launch, FMA pipe
+// 49 %, LDS-latency bound at 12 warps/SM — 0.37 of the fp32 peak and 37 % of the frame.
+//
+// Accuracy: each fp32 operand x is split as x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
+// (22 significant bits); a product uses three MMAs (hi*hi + hi*lo + lo*hi), accumulation is fp32.
+// The dropped lo*lo term is 2^-22 relative; results agree with the fp32 path to ~1e-6, well inside
+// the 1e-4 parity bar (no TF32/bf16-style precision loss).
+//
+// Data flow per warp and round (32 samples = two 16-row MMA tiles):
+//   gather (one lane per sample, same arithmetic as render_fused.cu) -> staging rows in shared memory
+//   -> per tile: Agg.view_fc (elementwise, fragment domain) -> global_fc (MMA) -> view softmax -> fc
+//   (MMA) -> lr0 (MMA) -> sigma -> color.0 (MMA: shared part once, per-view part on top) -> color.2
+//   -> view softmax -> rgb.  Layer outputs (C fragments) are re-used directly as the next layer's A
+//   fragments: for m16n8k16 two adjacent 8-column C tiles form one 16-wide K tile with no data movement.
+// Weights are pre-split and pre-arranged in B-fragment order by mlp_pack.pack_nerf_weights_mma(): one
+// 16-byte shared-memory load per lane per (k-tile, n-tile) = {b0_hi, b1_hi, b0_lo, b1_lo}.
+#include "raygen_common.cuh"
+
+namespace bmv {
+
+constexpr int kMmaWarps = 8;
+constexpr int kStageStride = 72;        // floats per staged sample: vox 8 | 3 x (f_v 15 + pad) ; 72 = 8 mod 32
+
+// fragment-ordered weight blocks (128 words each), in this order
+constexpr int BLK_GS = 0;               // global_fc, [var | mean] part : KT=2, NT=4
+constexpr int BLK_GV = BLK_GS + 2 * 4;  // global_fc, per-view x part   : KT=1, NT=4
+constexpr int BLK_FC = BLK_GV + 1 * 4;  // agg.fc                       : KT=2, NT=2
+constexpr int BLK_L0 = BLK_FC + 2 * 2;  // lr0  [pooled | vox]          : KT=2, NT=8
+constexpr int BLK_CS = BLK_L0 + 2 * 8;  // color.0 [hid | pooled | vox] : KT=6, NT=8
+constexpr int BLK_CV = BLK_CS + 6 * 8;  // color.0 per-view f_v         : KT=1, NT=8
+constexpr int NUM_BLK = BLK_CV + 1 * 8;
+// fp32 vectors after the blocks (word offsets)
+constexpr int V_BG = NUM_BLK * 128;     // global_fc.bias[32]
+constexpr int V_WA = V_BG + 32;         // agg_w_fc.weight[32]
+constexpr int V_BFC = V_WA + 32;        // fc.bias[16]
+constexpr int V_BL = V_BFC + 16;        // lr0.bias[64]
+constexpr int V_WS = V_BL + 64;         // sigma.weight[64]
+constexpr int V_BC = V_WS + 64;         // color.0.bias[64]
+constexpr int V_W2 = V_BC + 64;         // color.2.weight[64]
+constexpr int V_WV = V_W2 + 64;         // view_fc.weight[12][4]
+constexpr int V_BV = V_WV + 48;         // view_fc.bias[12]
+constexpr int V_SC = V_BV + 12;         // agg_w_fc.bias, sigma.bias, color.2.bias, 0
+constexpr int MMA_PACK_WORDS = V_SC + 4;
+
+__device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+  const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+  __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+  hi = *reinterpret_cast<uint32_t*>(&hh);
+  lo = *reinterpret_cast<uint32_t*>(&ll);
+}
+
+struct AFrag { uint32_t hi[4], lo[4]; };
+
+// fr[row 0/1][slot 0..3] = values at (row g / g+8, cols 2t, 2t+1, 2t+8, 2t+9) of a 16-wide K tile
+__device__ __forceinline__ AFrag make_afrag(const float (&fr)[2][4]) {
+  AFrag a;
+  split_pack(fr[0][0], fr[0][1], a.hi[0], a.lo[0]);
+  split_pack(fr[1][0], fr[1][1], a.hi[1], a.lo[1]);
+  split_pack(fr[0][2], fr[0][3], a.hi[2], a.lo[2]);
+  split_pack(fr[1][2], fr[1][3], a.hi[3], a.lo[3]);
+  return a;
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// c += A * B for one (k-tile, n-tile) with split operands: hi*hi + hi*lo + lo*hi
+__device__ __forceinline__ void mma3(float (&c)[4], const AFrag& a, const uint32_t* __restrict__ sW, int blk, int lane) {
+  const uint4 b = *reinterpret_cast<const uint4*>(sW + blk * 128 + lane * 4);
+  mma16816(c, a.lo, b.x, b.y);
+  mma16816(c, a.hi, b.z, b.w);
+  mma16816(c, a.hi, b.x, b.y);
+}
+
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_render_rays_params rp) {
+  constexpr int V = 3, CF = 8;
+  const bmv_raygen_fetch_params& p = rp.g;
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  uint32_t* sW = smem_u;
+  const float* sV = reinterpret_cast<const float*>(smem_u);
+  float* stage_all = reinterpret_cast<float*>(smem_u + MMA_PACK_WORDS);
+  __shared__ ViewCam cams[V];
+  __shared__ float s_tar_c[3];
+  __shared__ int s_view[V];
+  for (int i = threadIdx.x * 4; i < MMA_PACK_WORDS; i += blockDim.x * 4)
+    *reinterpret_cast<uint4*>(sW + i) = __ldg(reinterpret_cast<const uint4*>(rp.mlp_weights) + i / 4);
+  if (threadIdx.x < V) s_view[threadIdx.x] = p.view[threadIdx.x];
+  __syncthreads();
+  for (int v = 0; v < V; ++v) load_cam(&cams[v], p.src_exts, p.src_ixts, p.src_centers, s_view[v], threadIdx.x);
+  if (threadIdx.x < 3) s_tar_c[threadIdx.x] = p.tar_center[threadIdx.x];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float* stage = stage_all + warp * 32 * kStageStride;
+  const int S = p.S;
+  const int64_t n_samples = p.n_rays * S;
+  const float ba = sV[V_SC], bs = sV[V_SC + 1], b2 = sV[V_SC + 2];
+
+  for (int64_t base = ((int64_t)blockIdx.x * kMmaWarps + warp) * 32; base < n_samples;
+       base += (int64_t)gridDim.x * kMmaWarps * 32) {
+    // ------------------------------------------------------------ gather: one lane per sample
+    {
+      const int64_t si = base + lane;
+      float vox[8];
+      float f[V][CF + 7];
+      if (si < n_samples) {
+        const int64_t li = si / S;
+        const int s = (int)(si % S);
+        const RaySetup r = ray_setup(p, li);
+        const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
+        const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
+        const SamplePoint q = sample_point(p, r, s);
+        const int cnt = gather_sample_regs<CF, V>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
+        if (p.z_vals) p.z_vals[si] = q.z;
+        if (p.vis_mask) p.vis_mask[si] = div_rn((float)cnt, (float)V);
+        if (p.vis_count) p.vis_count[si] = cnt;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vox[c] = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int c = 0; c < CF + 7; ++c) f[v][c] = 0.f;
+      }
+      float* row = stage + lane * kStageStride;
+      *reinterpret_cast<float4*>(row) = make_float4(vox[0], vox[1], vox[2], vox[3]);
+      *reinterpret_cast<float4*>(row + 4) = make_float4(vox[4], vox[5], vox[6], vox[7]);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float* fr = row + 8 + v * 16;
+        *reinterpret_cast<float4*>(fr) = make_float4(f[v][0], f[v][1], f[v][2], f[v][3]);
+        *reinterpret_cast<float4*>(fr + 4) = make_float4(f[v][4], f[v][5], f[v][6], f[v][7]);
+        *reinterpret_cast<float4*>(fr + 8) = make_float4(f[v][8], f[v][9], f[v][10], f[v][11]);
+        *reinterpret_cast<float4*>(fr + 12) = make_float4(f[v][12], f[v][13], f[v][14], 0.f);
+      }
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------ MLP on two 16-sample tiles
+#pragma unroll 1
+    for (int tile = 0; tile < 2; ++tile) {
+      const float* row0 = stage + (tile * 16 + g) * kStageStride;
+      const float* row1 = row0 + 8 * kStageStride;
+      const int cols[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+      // per-view feature tiles f_v (cols 0..15 of the view block) and view_fc -> x_v
+      AFrag fA[V];
+      float x[V][2][4];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float* r0 = row0 + 8 + v * 16;
+        const float* r1 = row1 + 8 + v * 16;
+        float fr[2][4];
+        const float2 a0 = *reinterpret_cast<const float2*>(r0 + 2 * t), a2 = *reinterpret_cast<const float2*>(r0 + 2 * t + 8);
+        const float2 a1 = *reinterpret_cast<const float2*>(r1 + 2 * t), a3 = *reinterpret_cast<const float2*>(r1 + 2 * t + 8);
+        fr[0][0] = a0.x; fr[0][1] = a0.y; fr[0][2] = a2.x; fr[0][3] = a2.y;
+        fr[1][0] = a1.x; fr[1][1] = a1.y; fr[1][2] = a3.x; fr[1][3] = a3.y;
+        fA[v] = make_afrag(fr);
+        // x = feat + relu(Wv . dir + bv) for the feature columns (< 11); 0 in the padding columns
+        const float d0[4] = {r0[11], r0[12], r0[13], r0[14]};
+        const float d1[4] = {r1[11], r1[12], r1[13], r1[14]};
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int c = cols[sl];
+          if (c < 11) {
+            const float4 w = *reinterpret_cast<const float4*>(sV + V_WV + c * 4);
+            const float b = sV[V_BV + c];
+            const float e0 = fmaf(w.w, d0[3], fmaf(w.z, d0[2], fmaf(w.y, d0[1], fmaf(w.x, d0[0], b))));
+            const float e1 = fmaf(w.w, d1[3], fmaf(w.z, d1[2], fmaf(w.y, d1[1], fmaf(w.x, d1[0], b))));
+            x[v][0][sl] = fr[0][sl] + fmaxf(e0, 0.f);
+            x[v][1][sl] = fr[1][sl] + fmaxf(e1, 0.f);
+          } else {
+            x[v][0][sl] = 0.f; x[v][1][sl] = 0.f;
+          }
+        }
+      }
+      // mean / unbiased variance over the views (elementwise), then global_fc
+      float G[V][4][4];                                   // [view][n-tile][c-frag]
+      {
+        float var[2][4], mean[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const float m = (x[0][r][sl] + x[1][r][sl] + x[2][r][sl]) * (1.f / 3.f);
+            const float e0 = x[0][r][sl] - m, e1 = x[1][r][sl] - m, e2 = x[2][r][sl] - m;
+            mean[r][sl] = m;
+            var[r][sl] = fmaf(e2, e2, fmaf(e1, e1, e0 * e0)) * 0.5f;
+          }
+        const AFrag aVar = make_afrag(var), aMean = make_afrag(mean);
+        AFrag aX[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) aX[v] = make_afrag(x[v]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          float sh[4];
+          const float bg0 = sV[V_BG + nt * 8 + 2 * t], bg1 = sV[V_BG + nt * 8 + 2 * t + 1];
+          sh[0] = bg0; sh[1] = bg1; sh[2] = bg0; sh[3] = bg1;
+          mma3(sh, aVar, sW, BLK_GS + 0 * 4 + nt, lane);
+          mma3(sh, aMean, sW, BLK_GS + 1 * 4 + nt, lane);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) G[v][nt][i] = sh[i];
+            mma3(G[v][nt], aX[v], sW, BLK_GV + nt, lane);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) G[v][nt][i] = fmaxf(G[v][nt][i], 0.f);
+          }
+        }
+      }
+      // agg_w_fc + softmax over views, im = sum_v w_v G_v
+      float im[4][4];
+      {
+        float lg[V][2];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const float w0 = sV[V_WA + nt * 8 + 2 * t], w1 = sV[V_WA + nt * 8 + 2 * t + 1];
+            s0 = fmaf(w1, G[v][nt][1], fmaf(w0, G[v][nt][0], s0));
+            s1 = fmaf(w1, G[v][nt][3], fmaf(w0, G[v][nt][2], s1));
+          }
+          lg[v][0] = fmaxf(quad_sum(s0) + ba, 0.f);
+          lg[v][1] = fmaxf(quad_sum(s1) + ba, 0.f);
+        }
+        float wv[V][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float mx = fmaxf(lg[0][r], fmaxf(lg[1][r], lg[2][r]));
+          const float e0 = expf(lg[0][r] - mx), e1 = expf(lg[1][r] - mx), e2 = expf(lg[2][r] - mx);
+          const float inv = 1.f / (e0 + e1 + e2);
+          wv[0][r] = e0 * inv; wv[1][r] = e1 * inv; wv[2][r] = e2 * inv;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i >> 1;
+            im[nt][i] = fmaf(wv[2][r], G[2][nt][i], fmaf(wv[1][r], G[1][nt][i], wv[0][r] * G[0][nt][i]));
+          }
+      }
+      // fc: 32 -> 16 (+ReLU) ; pooled as the next layer's K tile
+      AFrag aPooled;
+      {
+        AFrag aIm[2];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          float fr[2][4] = {{im[2 * kt][0], im[2 * kt][1], im[2 * kt + 1][0], im[2 * kt + 1][1]},
+                            {im[2 * kt][2], im[2 * kt][3], im[2 * kt + 1][2], im[2 * kt + 1][3]}};
+          aIm[kt] = make_afrag(fr);
+        }
+        float pc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const float b0 = sV[V_BFC + nt * 8 + 2 * t], b1 = sV[V_BFC + nt * 8 + 2 * t + 1];
+          pc[nt][0] = b0; pc[nt][1] = b1; pc[nt][2] = b0; pc[nt][3] = b1;
+          mma3(pc[nt], aIm[0], sW, BLK_FC + 0 * 2 + nt, lane);
+          mma3(pc[nt], aIm[1], sW, BLK_FC + 1 * 2 + nt, lane);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pc[nt][i] = fmaxf(pc[nt][i], 0.f);
+        }
+        float fr[2][4] = {{pc[0][0], pc[0][1], pc[1][0], pc[1][1]}, {pc[0][2], pc[0][3], pc[1][2], pc[1][3]}};
+        aPooled = make_afrag(fr);
+      }
+      // vox K tile: cols 0..7 = vox, 8..15 = 0
+      AFrag aVox;
+      {
+        const float2 v0 = *reinterpret_cast<const float2*>(row0 + 2 * t), v1 = *reinterpret_cast<const float2*>(row1 + 2 * t);
+        float fr[2][4] = {{v0.x, v0.y, 0.f, 0.f}, {v1.x, v1.y, 0.f, 0.f}};
+        aVox = make_afrag(fr);
+      }
+      // lr0: [pooled | vox] -> 64 (+ReLU), sigma = softplus(ws . hid + bs); hid as 4 K tiles
+      AFrag aHid[4];
+      float sig0 = 0.f, sig1 = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        float hc[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int nt = 2 * kt + h;
+          const float b0 = sV[V_BL + nt * 8 + 2 * t], b1 = sV[V_BL + nt * 8 + 2 * t + 1];
+          hc[h][0] = b0; hc[h][1] = b1; hc[h][2] = b0; hc[h][3] = b1;
+          mma3(hc[h], aPooled, sW, BLK_L0 + 0 * 8 + nt, lane);
+          mma3(hc[h], aVox, sW, BLK_L0 + 1 * 8 + nt, lane);
+          const float w0 = sV[V_WS + nt * 8 + 2 * t], w1 = sV[V_WS + nt * 8 + 2 * t + 1];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hc[h][i] = fmaxf(hc[h][i], 0.f);
+          sig0 = fmaf(w1, hc[h][1], fmaf(w0, hc[h][0], sig0));
+          sig1 = fmaf(w1, hc[h][3], fmaf(w0, hc[h][2], sig1));
+        }
+        float fr[2][4] = {{hc[0][0], hc[0][1], hc[1][0], hc[1][1]}, {hc[0][2], hc[0][3], hc[1][2], hc[1][3]}};
+        aHid[kt] = make_afrag(fr);
+      }
+      sig0 = quad_sum(sig0) + bs;
+      sig1 = quad_sum(sig1) + bs;
+      sig0 = sig0 > 20.f ? sig0 : log1pf(expf(sig0));
+      sig1 = sig1 > 20.f ? sig1 : log1pf(expf(sig1));
+      // color.0 (shared part once per n-tile, per-view part on top) + color.2 partial dot
+      float cl[V][2];
+#pragma unroll
+      for (int v = 0; v < V; ++v) { cl[v][0] = 0.f; cl[v][1] = 0.f; }
+#pragma unroll 2
+      for (int nt = 0; nt < 8; ++nt) {
+        float sh[4];
+        const float b0 = sV[V_BC + nt * 8 + 2 * t], b1 = sV[V_BC + nt * 8 + 2 * t + 1];
+        sh[0] = b0; sh[1] = b1; sh[2] = b0; sh[3] = b1;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) mma3(sh, aHid[kt], sW, BLK_CS + kt * 8 + nt, lane);
+        mma3(sh, aPooled, sW, BLK_CS + 4 * 8 + nt, lane);
+        mma3(sh, aVox, sW, BLK_CS + 5 * 8 + nt, lane);
+        const float w0 = sV[V_W2 + nt * 8 + 2 * t], w1 = sV[V_W2 + nt * 8 + 2 * t + 1];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float c[4] = {sh[0], sh[1], sh[2], sh[3]};
+          mma3(c, fA[v], sW, BLK_CV + nt, lane);
+          cl[v][0] = fmaf(w1, fmaxf(c[1], 0.f), fmaf(w0, fmaxf(c[0], 0.f), cl[v][0]));
+          cl[v][1] = fmaf(w1, fmaxf(c[3], 0.f), fmaf(w0, fmaxf(c[2], 0.f), cl[v][1]));
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        cl[v][0] = fmaxf(quad_sum(cl[v][0]) + b2, 0.f);
+        cl[v][1] = fmaxf(quad_sum(cl[v][1]) + b2, 0.f);
+      }
+      // softmax over views, rgb = sum_v beta_v rgb_v ; lane t == 0 of each quad writes rows g and g+8
+      if (t == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float* rw = r ? row1 : row0;
+          const float mx = fmaxf(cl[0][r], fmaxf(cl[1][r], cl[2][r]));
+          const float e0 = expf(cl[0][r] - mx), e1 = expf(cl[1][r] - mx), e2 = expf(cl[2][r] - mx);
+          const float inv = 1.f / (e0 + e1 + e2);
+          float4 o;
+          o.x = (e0 * rw[8 + 0 * 16 + 8] + e1 * rw[8 + 1 * 16 + 8] + e2 * rw[8 + 2 * 16 + 8]) * inv;
+          o.y = (e0 * rw[8 + 0 * 16 + 9] + e1 * rw[8 + 1 * 16 + 9] + e2 * rw[8 + 2 * 16 + 9]) * inv;
+          o.z = (e0 * rw[8 + 0 * 16 + 10] + e1 * rw[8 + 1 * 16 + 10] + e2 * rw[8 + 2 * 16 + 10]) * inv;
+          o.w = r ? sig1 : sig0;
+          const int64_t si = base + tile * 16 + g + 8 * r;
+          if (si < n_samples) reinterpret_cast<float4*>(rp.raw)[si] = o;
+        }
+      }
+    }
+    __syncwarp();                                           // staging rows are rewritten next round
+  }
+}
+
+}  // namespace bmv
+
+extern "C" BMV_API int bmv_render_rays_mma_weight_words(void) { return bmv::MMA_PACK_WORDS; }
+
+extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(rp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: null params");
+  const bmv_raygen_fetch_params* p = &rp->g;
+  BMV_REQUIRE(p->n_rays >= 0 && p->ray_begin >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: bad ray range");
+  if (p->n_rays == 0) return BMV_OK;
+  BMV_REQUIRE(!p->xyz_in, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: pointwise mode is not supported here");
+  BMV_REQUIRE(p->rays12_in || (p->depth && p->std && p->near_far && p->rays), BMV_ERR_INVALID_ARGUMENT,
+              "bmv_render_rays_mma: null ray inputs");
+  BMV_REQUIRE(p->volume && p->im_feat && p->rgb && p->src_exts && p->src_ixts && p->src_centers && p->tar_center &&
+                  rp->mlp_weights && rp->raw,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: null device pointer");
+  BMV_REQUIRE(((uintptr_t)rp->mlp_weights & 15) == 0 && ((uintptr_t)rp->raw & 15) == 0, BMV_ERR_INVALID_ARGUMENT,
+              "bmv_render_rays_mma: weights/raw must be 16-byte aligned");
+  BMV_REQUIRE(p->S >= 1 && (p->S == 1 || p->t), BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: bad S / t");
+  BMV_REQUIRE(p->H >= 2 && p->W >= 2 && p->hv >= 1 && p->wv >= 1 && p->Hf >= 2 && p->Wf >= 2 && p->Dv >= 1,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: bad grid size");
+  BMV_REQUIRE(p->Cv == 8 && p->Cf == 8 && p->V == 3, BMV_ERR_UNSUPPORTED_SHAPE,
+              "bmv_render_rays_mma: (Cv=%d, Cf=%d, V=%d) not instantiated (8, 8, 3)", p->Cv, p->Cf, p->V);
+  const size_t smem = (size_t)(MMA_PACK_WORDS + kMmaWarps * 32 * kStageStride) * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(render_rays_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("bmv_render_rays_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+      return BMV_ERR_CUDA_LAUNCH;
+    }
+    configured = true;
+  }
+  const int64_t rounds = ceil_div64(p->n_rays * p->S, kMmaWarps * 32);
+  const unsigned blocks = (unsigned)(rounds < kNumSMs ? rounds : kNumSMs);   // persistent: one CTA per SM
+  render_rays_mma_kernel<<<blocks, kMmaWarps * 32, smem, (cudaStream_t)stream>>>(*rp);
+  return check_launch("bmv_render_rays_mma");
+}

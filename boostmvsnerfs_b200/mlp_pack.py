@@ -99,3 +99,57 @@ def eval_packed(packed, vox, img):
     beta = torch.softmax(cl, dim=1)
     rgb = (img[..., F - 3:F] * beta[..., None]).sum(1)
     return torch.cat([rgb, sig[:, None]], -1)
+
+
+# ------------------------------------------------------------------------------------------ tensor-core packing
+MMA_BLOCKS = dict(GS=(2, 4), GV=(1, 4), FC=(2, 2), L0=(2, 8), CS=(6, 8), CV=(1, 8))   # (k-tiles, n-tiles), kernel order
+
+
+def _fragment_blocks(w_pad):
+    """w_pad (N, K) fp32 with N % 8 == 0 and K % 16 == 0 -> int32 tensor (K/16 * N/8 * 128,) in the
+    B-fragment order of mma.sync.m16n8k16: block (kt, nt), lane = 4*g + t holds
+    b0 = W[nt*8+g][kt*16 + 2t, +1], b1 = W[nt*8+g][kt*16 + 2t+8, +9]; words {b0_hi, b1_hi, b0_lo, b1_lo}
+    with x = hi + lo, hi = fp16(x), lo = fp16(x - hi)."""
+    N, K = w_pad.shape
+    hi = w_pad.half()
+    lo = (w_pad - hi.float()).half()
+    KT, NT = K // 16, N // 8
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((KT, NT, 32, 4, 2), dtype=torch.float16)
+    for kt in range(KT):
+        for nt in range(NT):
+            n = nt * 8 + g
+            k0 = kt * 16 + 2 * t
+            for j, src in enumerate((hi, hi, lo, lo)):
+                kk = k0 + (8 if j % 2 else 0)
+                out[kt, nt, :, j, 0] = src[n, kk]
+                out[kt, nt, :, j, 1] = src[n, kk + 1]
+    return out.reshape(-1).view(torch.int32)
+
+
+def pack_nerf_weights_mma(nerf):
+    """Weights of the level-1 NeRF MLP (feat_ch = 11, 3 views) for the tensor-core kernel
+    (csrc/render_mma.cu): fragment-ordered split-fp16 blocks followed by the fp32 bias / 1-output
+    vectors.  Returns an int32 tensor (MMA_PACK_WORDS,) on the module's device."""
+    sd = {k: v.detach().float().cpu() for k, v in nerf.state_dict().items()}
+    if "agg.view_fc.0.weight" not in sd:
+        raise ValueError("fused MLP requires cfg.enerf.viewdir_agg=True (the shipped configs)")
+    F = sd["agg.view_fc.0.weight"].shape[0]
+    if F != 11 or sd["lr0.0.weight"].shape != (64, 24) or sd["color.0.weight"].shape != (64, 103):
+        raise ValueError("tensor-core MLP is instantiated for feat_ch=11 (nerf_model_feat_ch=8) only")
+    wg, wfc, wl, wc = sd["agg.global_fc.0.weight"], sd["agg.fc.0.weight"], sd["lr0.0.weight"], sd["color.0.weight"]
+    gs = torch.zeros(32, 32); gs[:, 0:F] = wg[:, F:2 * F]; gs[:, 16:16 + F] = wg[:, 2 * F:3 * F]     # [var | mean]
+    gv = torch.zeros(32, 16); gv[:, 0:F] = wg[:, 0:F]
+    l0 = torch.zeros(64, 32); l0[:, 0:16] = wl[:, 8:24]; l0[:, 16:24] = wl[:, 0:8]                  # [pooled | vox]
+    cs = torch.zeros(64, 96); cs[:, 0:64] = wc[:, 0:64]; cs[:, 64:80] = wc[:, 72:88]; cs[:, 80:88] = wc[:, 64:72]
+    cv = torch.zeros(64, 16); cv[:, 0:15] = wc[:, 88:103]
+    blocks = torch.cat([_fragment_blocks(m) for m in (gs, gv, wfc.clone(), l0, cs, cv)])
+    wv = torch.zeros(12, 4); wv[:F] = sd["agg.view_fc.0.weight"]
+    bv = torch.zeros(12); bv[:F] = sd["agg.view_fc.0.bias"]
+    vec = torch.cat([sd["agg.global_fc.0.bias"], sd["agg.agg_w_fc.0.weight"][0], sd["agg.fc.0.bias"], sd["lr0.0.bias"],
+                     sd["sigma.0.weight"][0], sd["color.0.bias"], sd["color.2.weight"][0], wv.reshape(-1), bv,
+                     torch.stack([sd["agg.agg_w_fc.0.bias"][0], sd["sigma.0.bias"][0], sd["color.2.bias"][0],
+                                  torch.tensor(0.)])])
+    packed = torch.cat([blocks, vec.contiguous().view(torch.int32)])
+    return packed.to(next(nerf.parameters()).device)

@@ -49,6 +49,7 @@ class EnerfNetwork(nn.Module):
         self.fold_bn = True                    # eval-mode BN folded into the convolutions
         self.channels_last = True              # NHWC / NDHWC activations, volumes emitted channels-last
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
+        self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
         self._plans = PlanCache()
         self.stage_timer = None                # optional callable(name) -> context manager
@@ -75,15 +76,15 @@ class EnerfNetwork(nn.Module):
         self._packed.clear()
         self._plans = PlanCache()
 
-    def _packed_mlp(self, i):
-        """Packed weights of nerf_{i} for the fused kernel; re-packed when a parameter changes."""
+    def _packed_mlp(self, i, engine='fma'):
+        """Packed weights of nerf_{i} for the fused kernels; re-packed when a parameter changes."""
         nerf = getattr(self, f'nerf_{i}')
         key = tuple((p.data_ptr(), p._version) for p in nerf.parameters())
-        hit = self._packed.get(i)
+        hit = self._packed.get((i, engine))
         if hit is None or hit[0] != key:
-            from .mlp_pack import pack_nerf_weights
-            self._packed[i] = (key, pack_nerf_weights(nerf))
-        return self._packed[i][1]
+            from .mlp_pack import pack_nerf_weights, pack_nerf_weights_mma
+            self._packed[(i, engine)] = (key, pack_nerf_weights_mma(nerf) if engine == 'mma' else pack_nerf_weights(nerf))
+        return self._packed[(i, engine)][1]
 
     def _kept(self, name):
         """The cuDNN module `name`, through the inference plan when enabled."""
@@ -264,12 +265,13 @@ class EnerfNetwork(nn.Module):
         mask_all = torch.empty((K, R, S), device=dev)
         z_all = torch.empty((K, R, S), device=dev)
         if self.fused_mlp and rc.viewdir_agg and ops.render_rays_supported(Cv, Cf, V):
-            packed = self._packed_mlp(i)
+            engine = self.mlp_engine if (Cf == 8 and V == 3) else 'fma'
+            packed = self._packed_mlp(i, engine)
             with self._stage(f'render_fused_l{i}'):
                 for k in range(K):
                     ops.render_rays(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S, feat_vol[k], im_feat,
                                     rgb, cams, triples[k], packed, render_scale=rs, rgb_affine=affine,
-                                    ray_begin=ray_begin, n_rays=R,
+                                    ray_begin=ray_begin, n_rays=R, engine=engine,
                                     out={'raw': raw_all[k], 'z_vals': z_all[k], 'vis_mask': mask_all[k]})
             return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
         for r0 in range(0, R, rc.chunk_size):

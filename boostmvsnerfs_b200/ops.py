@@ -417,14 +417,23 @@ def render_rays_supported(Cv, Cf, V):
 
 
 def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat, rgb, cams, views, packed_weights,
-                render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False):
+                render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False,
+                engine="fma"):
     """Fused per-chain render (K3 gather + per-sample MLP, nothing materialised in HBM).
     Same inputs as raygen_sample_fetch plus the packed MLP weights.
     Returns dict(raw (n,S,4), z_vals (n,S), vis_mask (n,S) [, vis_count (n,S) int32]); `out` may
     supply preallocated contiguous tensors for any of them."""
     depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
     rays = _cf32(rays, "rays")
-    w = _cf32(packed_weights, "packed_weights")
+    if engine not in ("fma", "mma"):
+        raise BmvError(f"render_rays: unknown engine {engine!r}")
+    w = packed_weights
+    if engine == "mma":
+        if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()
+                and w.numel() == _lib.load().bmv_render_rays_mma_weight_words()):
+            raise BmvError("render_rays(engine='mma'): weights must come from mlp_pack.pack_nerf_weights_mma")
+    else:
+        w = _cf32(w, "packed_weights")
     dev = rays.device
     R = rays.shape[0]
     n = R - ray_begin if n_rays is None else n_rays
@@ -438,7 +447,7 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
     t = _linspace(S, dev) if S > 1 else None
     p.t, p.S = (t.data_ptr() if t is not None else 0), S
     _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_affine, ())
-    if _lib.load().bmv_nerf_mlp_weight_count(p.Cf + 3) != w.numel():
+    if engine == "fma" and _lib.load().bmv_nerf_mlp_weight_count(p.Cf + 3) != w.numel():
         raise BmvError(f"render_rays: packed weight length {w.numel()} does not match feat_ch={p.Cf + 3}")
     res = dict(out) if out else {}
     want = ("z_vals", "vis_mask") + (("vis_count",) if want_count else ())
@@ -450,7 +459,7 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
     else:
         raw = res["raw"] = torch.empty((n, S, 4), device=dev)
     rp.mlp_weights, rp.raw = w.data_ptr(), raw.data_ptr()
-    _lib.call("bmv_render_rays", rp, _stream())
+    _lib.call("bmv_render_rays_mma" if engine == "mma" else "bmv_render_rays", rp, _stream())
     return res
 
 

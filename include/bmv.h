@@ -245,6 +245,12 @@ typedef struct bmv_render_rays_params {
 } bmv_render_rays_params;
 BMV_API int bmv_render_rays(const bmv_render_rays_params* p, bmv_stream_t stream);
 BMV_API int bmv_render_rays_supported(int Cv, int Cf, int V);
+/* Tensor-core variant (csrc/render_mma.cu): same contract, every Linear layer on warp-level MMAs
+ * (fp16 hi/lo split operands, fp32 accumulate, ~1e-6 agreement with the fp32-FMA kernel);
+ * mlp_weights must come from the MMA packing (bmv_render_rays_mma_weight_words 32-bit words).
+ * Instantiated for Cv=8, Cf=8, V=3 (the ENeRF level-1 MLP). */
+BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* p, bmv_stream_t stream);
+BMV_API int bmv_render_rays_mma_weight_words(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1b  MVSNeRF cost volume with colour channels.

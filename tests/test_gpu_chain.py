@@ -81,12 +81,15 @@ def test_single_volume_forward_vs_reference(strict_fp32):
 def test_fused_and_unfused_network_paths_agree(strict_fp32):
     g = load_golden("enerf_chain_eval.npz")
     net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
-    assert net.fused_mlp
+    assert net.fused_mlp and net.mlp_engine == "mma"
     fused = net(dict(batch))
+    net.mlp_engine = "fma"
+    fma = net(dict(batch))
     net.fused_mlp = False
     unfused = net(dict(batch))
     for k in fused:
-        _report(fused[k], unfused[k].cpu().numpy(), f"fused vs unfused {k}", 2e-5)
+        _report(fused[k], unfused[k].cpu().numpy(), f"tensor-core fused vs unfused {k}", 2e-5)
+        _report(fma[k], unfused[k].cpu().numpy(), f"fp32-FMA fused vs unfused {k}", 2e-5)
 
 
 def test_boost_forward_default_tf32_is_close():

@@ -326,6 +326,36 @@ def test_fused_mlp_rejects_bad_shapes(ops):
     assert ops.nerf_mlp(torch.zeros(0, 8, device="cuda"), torch.zeros(0, 3, 15, device="cuda"), w).shape == (0, 4)
 
 
+@pytest.mark.parametrize("seed", [4, 5])
+def test_tensor_core_render_matches_fp32_paths(ops, g, seed):
+    """bmv_render_rays_mma (MLP on mma.sync, split-fp16 operands) vs the fp32-FMA fused kernel and vs
+    fetch + torch cuBLAS module; ragged ray ranges."""
+    from boostmvsnerfs_b200 import mlp_pack
+    from boostmvsnerfs_b200.modules import NeRF
+    torch.manual_seed(seed)
+    net = NeRF(feat_ch=11).eval().cuda()
+    for prm in net.parameters():
+        if prm.dim() == 1:
+            prm.data.normal_(0, 0.2)
+    cams = _cams(ops, g)
+    args = (g.t("depth_l1", "cuda")[0], g.t("std_l1", "cuda")[0], g.t("near_far_l1", "cuda")[0],
+            g.t("in_rays_1", "cuda")[0], H, W, False, 2, g.t("in_regvol1", "cuda")[0], g.t("in_imfeat2", "cuda")[0],
+            g.t("in_src_inps", "cuda")[0], cams, TRIPLE)
+    o = ops.raygen_sample_fetch(*args, want=("z_vals", "vox_feat", "img_feat", "vis_mask"))
+    with torch.no_grad():
+        ref = net(o["vox_feat"][None], o["img_feat"][None])[0].view(-1, 2, 4)
+    fma = ops.render_rays(*args, mlp_pack.pack_nerf_weights(net))
+    mma = ops.render_rays(*args, mlp_pack.pack_nerf_weights_mma(net), engine="mma", want_count=True)
+    close(mma["raw"], ref, "tensor-core raw vs fetch + cuBLAS MLP", rtol=2e-5)
+    close(mma["raw"], fma["raw"], "tensor-core raw vs fp32-FMA kernel", rtol=2e-5)
+    exact(mma["z_vals"], fma["z_vals"], "z_vals")
+    exact(mma["vis_mask"], fma["vis_mask"], "visibility")
+    part = ops.render_rays(*args, mlp_pack.pack_nerf_weights_mma(net), engine="mma", ray_begin=1003, n_rays=777)
+    exact(part["raw"], mma["raw"][1003:1780], "ray sub-range (ragged tiles)")
+    one = ops.render_rays(*args, mlp_pack.pack_nerf_weights_mma(net), engine="mma", ray_begin=5, n_rays=1)
+    exact(one["raw"], mma["raw"][5:6], "single ray")
+
+
 def test_fused_render_matches_unfused_path(ops, g):
     """bmv_render_rays (gather + MLP in one kernel) == bmv_raygen_sample_fetch -> torch NeRF module."""
     from boostmvsnerfs_b200 import mlp_pack
