@@ -168,7 +168,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(struct), C.c_void_p]
         fn.restype = C.c_int
-        native = lib.bmv_sizeof_params(name.replace("_mma", "").encode())
+        native = lib.bmv_sizeof_params(name.encode())
         if native != C.sizeof(struct):
             raise BmvError(f"ABI mismatch for {name}: library struct is {native} B, binding is {C.sizeof(struct)} B")
     _lib = lib

@@ -20,7 +20,7 @@
 
 namespace bmv {
 
-constexpr int kMmaWarps = 8;
+constexpr int kMmaWarps = 12;
 constexpr int kStageStride = 72;        // floats per staged sample: vox 8 | 3 x (f_v 15 + pad) ; 72 = 8 mod 32
 
 // fragment-ordered weight blocks (128 words each), in this order
@@ -65,7 +65,7 @@ __device__ __forceinline__ AFrag make_afrag(const float (&fr)[2][4]) {
 }
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -203,22 +203,31 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
         AFrag aX[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) aX[v] = make_afrag(x[v]);
+        float sh[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          float sh[4];
           const float bg0 = sV[V_BG + nt * 8 + 2 * t], bg1 = sV[V_BG + nt * 8 + 2 * t + 1];
-          sh[0] = bg0; sh[1] = bg1; sh[2] = bg0; sh[3] = bg1;
-          mma3(sh, aVar, sW, BLK_GS + 0 * 4 + nt, lane);
-          mma3(sh, aMean, sW, BLK_GS + 1 * 4 + nt, lane);
+          sh[nt][0] = bg0; sh[nt][1] = bg1; sh[nt][2] = bg0; sh[nt][3] = bg1;
+        }
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
+        for (int nt = 0; nt < 4; ++nt) mma3(sh[nt], aVar, sW, BLK_GS + 0 * 4 + nt, lane);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) G[v][nt][i] = sh[i];
+        for (int nt = 0; nt < 4; ++nt) mma3(sh[nt], aMean, sW, BLK_GS + 1 * 4 + nt, lane);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) G[v][nt][i] = sh[nt][i];
             mma3(G[v][nt], aX[v], sW, BLK_GV + nt, lane);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) G[v][nt][i] = fmaxf(G[v][nt][i], 0.f);
           }
         }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) G[v][nt][i] = fmaxf(G[v][nt][i], 0.f);
       }
       // agg_w_fc + softmax over views, im = sum_v w_v G_v
       float im[4][4];
@@ -267,11 +276,15 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
         for (int nt = 0; nt < 2; ++nt) {
           const float b0 = sV[V_BFC + nt * 8 + 2 * t], b1 = sV[V_BFC + nt * 8 + 2 * t + 1];
           pc[nt][0] = b0; pc[nt][1] = b1; pc[nt][2] = b0; pc[nt][3] = b1;
-          mma3(pc[nt], aIm[0], sW, BLK_FC + 0 * 2 + nt, lane);
-          mma3(pc[nt], aIm[1], sW, BLK_FC + 1 * 2 + nt, lane);
+        }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma3(pc[nt], aIm[kt], sW, BLK_FC + kt * 2 + nt, lane);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) pc[nt][i] = fmaxf(pc[nt][i], 0.f);
-        }
         float fr[2][4] = {{pc[0][0], pc[0][1], pc[1][0], pc[1][1]}, {pc[0][2], pc[0][3], pc[1][2], pc[1][3]}};
         aPooled = make_afrag(fr);
       }
@@ -285,24 +298,31 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
       // lr0: [pooled | vox] -> 64 (+ReLU), sigma = softplus(ws . hid + bs); hid as 4 K tiles
       AFrag aHid[4];
       float sig0 = 0.f, sig1 = 0.f;
+      {
+        float hc[8][4];
 #pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        float hc[2][4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int nt = 2 * kt + h;
+        for (int nt = 0; nt < 8; ++nt) {
           const float b0 = sV[V_BL + nt * 8 + 2 * t], b1 = sV[V_BL + nt * 8 + 2 * t + 1];
-          hc[h][0] = b0; hc[h][1] = b1; hc[h][2] = b0; hc[h][3] = b1;
-          mma3(hc[h], aPooled, sW, BLK_L0 + 0 * 8 + nt, lane);
-          mma3(hc[h], aVox, sW, BLK_L0 + 1 * 8 + nt, lane);
+          hc[nt][0] = b0; hc[nt][1] = b1; hc[nt][2] = b0; hc[nt][3] = b1;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma3(hc[nt], aPooled, sW, BLK_L0 + 0 * 8 + nt, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma3(hc[nt], aVox, sW, BLK_L0 + 1 * 8 + nt, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
           const float w0 = sV[V_WS + nt * 8 + 2 * t], w1 = sV[V_WS + nt * 8 + 2 * t + 1];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hc[h][i] = fmaxf(hc[h][i], 0.f);
-          sig0 = fmaf(w1, hc[h][1], fmaf(w0, hc[h][0], sig0));
-          sig1 = fmaf(w1, hc[h][3], fmaf(w0, hc[h][2], sig1));
+          for (int i = 0; i < 4; ++i) hc[nt][i] = fmaxf(hc[nt][i], 0.f);
+          sig0 = fmaf(w1, hc[nt][1], fmaf(w0, hc[nt][0], sig0));
+          sig1 = fmaf(w1, hc[nt][3], fmaf(w0, hc[nt][2], sig1));
         }
-        float fr[2][4] = {{hc[0][0], hc[0][1], hc[1][0], hc[1][1]}, {hc[0][2], hc[0][3], hc[1][2], hc[1][3]}};
-        aHid[kt] = make_afrag(fr);
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+          float fr[2][4] = {{hc[2 * kt][0], hc[2 * kt][1], hc[2 * kt + 1][0], hc[2 * kt + 1][1]},
+                            {hc[2 * kt][2], hc[2 * kt][3], hc[2 * kt + 1][2], hc[2 * kt + 1][3]}};
+          aHid[kt] = make_afrag(fr);
+        }
       }
       sig0 = quad_sum(sig0) + bs;
       sig1 = quad_sum(sig1) + bs;
@@ -312,22 +332,37 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
       float cl[V][2];
 #pragma unroll
       for (int v = 0; v < V; ++v) { cl[v][0] = 0.f; cl[v][1] = 0.f; }
-#pragma unroll 2
-      for (int nt = 0; nt < 8; ++nt) {
-        float sh[4];
-        const float b0 = sV[V_BC + nt * 8 + 2 * t], b1 = sV[V_BC + nt * 8 + 2 * t + 1];
-        sh[0] = b0; sh[1] = b1; sh[2] = b0; sh[3] = b1;
+#pragma unroll 1
+      for (int n0 = 0; n0 < 8; n0 += 4) {
+        float sh[4][4];
 #pragma unroll
-        for (int kt = 0; kt < 4; ++kt) mma3(sh, aHid[kt], sW, BLK_CS + kt * 8 + nt, lane);
-        mma3(sh, aPooled, sW, BLK_CS + 4 * 8 + nt, lane);
-        mma3(sh, aVox, sW, BLK_CS + 5 * 8 + nt, lane);
-        const float w0 = sV[V_W2 + nt * 8 + 2 * t], w1 = sV[V_W2 + nt * 8 + 2 * t + 1];
+        for (int j = 0; j < 4; ++j) {
+          const float b0 = sV[V_BC + (n0 + j) * 8 + 2 * t], b1 = sV[V_BC + (n0 + j) * 8 + 2 * t + 1];
+          sh[j][0] = b0; sh[j][1] = b1; sh[j][2] = b0; sh[j][3] = b1;
+        }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma3(sh[j], aHid[kt], sW, BLK_CS + kt * 8 + n0 + j, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma3(sh[j], aPooled, sW, BLK_CS + 4 * 8 + n0 + j, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma3(sh[j], aVox, sW, BLK_CS + 5 * 8 + n0 + j, lane);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          float c[4] = {sh[0], sh[1], sh[2], sh[3]};
-          mma3(c, fA[v], sW, BLK_CV + nt, lane);
-          cl[v][0] = fmaf(w1, fmaxf(c[1], 0.f), fmaf(w0, fmaxf(c[0], 0.f), cl[v][0]));
-          cl[v][1] = fmaf(w1, fmaxf(c[3], 0.f), fmaf(w0, fmaxf(c[2], 0.f), cl[v][1]));
+          float c[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[j][i] = sh[j][i];
+            mma3(c[j], fA[v], sW, BLK_CV + n0 + j, lane);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float w0 = sV[V_W2 + (n0 + j) * 8 + 2 * t], w1 = sV[V_W2 + (n0 + j) * 8 + 2 * t + 1];
+            cl[v][0] = fmaf(w1, fmaxf(c[j][1], 0.f), fmaf(w0, fmaxf(c[j][0], 0.f), cl[v][0]));
+            cl[v][1] = fmaf(w1, fmaxf(c[j][3], 0.f), fmaf(w0, fmaxf(c[j][2], 0.f), cl[v][1]));
+          }
         }
       }
 #pragma unroll
