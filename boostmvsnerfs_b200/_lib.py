@@ -52,7 +52,7 @@ class RaygenFetchParams(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("std", C.c_void_p), ("near_far", C.c_void_p),
                 ("hv", i32), ("wv", i32), ("H", i32), ("W", i32), ("depth_inv", i32),
                 ("rays", C.c_void_p), ("ray_begin", i64), ("n_rays", i64),
-                ("rays12_in", C.c_void_p), ("xyz_in", C.c_void_p), ("uvd_in", C.c_void_p),
+                ("rays12_in", C.c_void_p), ("xyz_in", C.c_void_p), ("uvd_in", C.c_void_p), ("ray_gen", C.c_void_p),
                 ("t", C.c_void_p), ("S", i32),
                 ("volume", C.c_void_p), ("Cv", i32), ("Dv", i32),
                 ("vol_c_stride", i64), ("vol_d_stride", i64), ("vol_y_stride", i64), ("vol_x_stride", i64),

@@ -81,8 +81,19 @@ __device__ __forceinline__ RaySetup ray_setup(const bmv_raygen_fetch_params& p, 
     r.rn = rc.x; r.rf = rc.y; r.nf0 = rc.z; r.nf1 = rc.w;
   } else {
     const int64_t ri = p.ray_begin + li;
-    ra = __ldg(reinterpret_cast<const float4*>(p.rays + ri * 8));
-    rb = __ldg(reinterpret_cast<const float4*>(p.rays + ri * 8 + 4));
+    if (p.rays) {
+      ra = __ldg(reinterpret_cast<const float4*>(p.rays + ri * 8));
+      rb = __ldg(reinterpret_cast<const float4*>(p.rays + ri * 8 + 4));
+    } else {                                              // generate the ray of pixel (ri % W, ri / W)
+      const double* G = p.ray_gen;
+      const int gx = (int)(ri % p.W), gy = (int)(ri / p.W);
+      const double dxp = (double)gx, dyp = (double)gy;
+      const double d0 = __fma_rn(dyp, __ldg(G + 6), __dmul_rn(dxp, __ldg(G + 3))) + __ldg(G + 9);
+      const double d1 = __fma_rn(dyp, __ldg(G + 7), __dmul_rn(dxp, __ldg(G + 4))) + __ldg(G + 10);
+      const double d2 = __fma_rn(dyp, __ldg(G + 8), __dmul_rn(dxp, __ldg(G + 5))) + __ldg(G + 11);
+      ra = make_float4((float)__ldg(G), (float)__ldg(G + 1), (float)__ldg(G + 2), (float)d0);
+      rb = make_float4((float)d1, (float)d2, (float)gx, (float)gy);
+    }
     int px = (int)rb.z, py = (int)rb.w;                 // .long(): truncation toward zero
     px = min(max(px, 0), p.W - 1);
     py = min(max(py, 0), p.H - 1);

@@ -188,7 +188,7 @@ extern "C" BMV_API int bmv_raygen_sample_fetch(const bmv_raygen_fetch_params* p,
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_raygen_sample_fetch: null params");
   BMV_REQUIRE(p->src_exts && p->src_ixts, BMV_ERR_INVALID_ARGUMENT, "bmv_raygen_sample_fetch: null camera pointer");
   if (!p->xyz_in && !p->rays12_in)
-    BMV_REQUIRE(p->depth && p->std && p->near_far && p->rays, BMV_ERR_INVALID_ARGUMENT,
+    BMV_REQUIRE(p->depth && p->std && p->near_far && (p->rays || p->ray_gen), BMV_ERR_INVALID_ARGUMENT,
                 "bmv_raygen_sample_fetch: null input pointer");
   if (p->xyz_in && p->vox_feat)
     BMV_REQUIRE(p->uvd_in != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_raygen_sample_fetch: vox_feat needs uvd_in");

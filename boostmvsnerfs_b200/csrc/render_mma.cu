@@ -403,7 +403,7 @@ extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv
   BMV_REQUIRE(p->n_rays >= 0 && p->ray_begin >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: bad ray range");
   if (p->n_rays == 0) return BMV_OK;
   BMV_REQUIRE(!p->xyz_in, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: pointwise mode is not supported here");
-  BMV_REQUIRE(p->rays12_in || (p->depth && p->std && p->near_far && p->rays), BMV_ERR_INVALID_ARGUMENT,
+  BMV_REQUIRE(p->rays12_in || (p->depth && p->std && p->near_far && (p->rays || p->ray_gen)), BMV_ERR_INVALID_ARGUMENT,
               "bmv_render_rays_mma: null ray inputs");
   BMV_REQUIRE(p->volume && p->im_feat && p->rgb && p->src_exts && p->src_ixts && p->src_centers && p->tar_center &&
                   rp->mlp_weights && rp->raw,

@@ -170,8 +170,8 @@ class ShardedFrameRenderer:
             with net._stage('gather_features'):
                 feats = self.gather_features(inps, local, views_of)
             with net._stage('camera'):
-                cams, projs = net._camera_stage(batch['all_src_exts'][0], batch['all_src_ixts'][0],
-                                                batch['tar_ext'][0], batch['tar_ixt'][0])
+                cams, projs, _ = net._camera_stage(batch['all_src_exts'][0], batch['all_src_ixts'][0],
+                                                   batch['tar_ext'][0], batch['tar_ixt'][0])
             states_local = self.compute_chains(feats, projs, batch['near_far'][0],
                                                [triples[k] for k in chains_of[r]], H, W)
             shapes = {i: (8, rc.volume_planes[i], int(H * rc.volume_scale[i]), int(W * rc.volume_scale[i]))

@@ -23,8 +23,9 @@ class FrameGraph:
         self._cache = {}
 
     def _key(self, batch, triples):
-        return (tuple(batch["all_src_inps"].shape), tuple(triples),
-                tuple(tuple(batch[f"rays_{i}"].shape) for i in range(self.net.rc.num)))
+        return (tuple(batch["all_src_inps"].shape), tuple(triples), bool(self.net.generate_rays),
+                tuple(tuple(batch[f"rays_{i}"].shape) if f"rays_{i}" in batch else None
+                      for i in range(self.net.rc.num)))
 
     def _triples(self, batch):
         net, rc = self.net, self.net.rc
@@ -37,19 +38,26 @@ class FrameGraph:
         net, rc = self.net, self.net.rc
         dev = next(net.parameters()).device
         st = {k: torch.empty_like(batch[k], device=dev) for k in _STATIC_KEYS}
-        for i in range(rc.num):
-            st[f"rays_{i}"] = torch.empty_like(batch[f"rays_{i}"], device=dev)
+        gen_rays = net.generate_rays or any(f"rays_{i}" not in batch for i in range(rc.num))
+        if not gen_rays:
+            for i in range(rc.num):
+                st[f"rays_{i}"] = torch.empty_like(batch[f"rays_{i}"], device=dev)
         N = st["all_src_inps"].shape[1]
         n_cam = rc.num * N * 12 + N * 3 + 3
         cam_dev = torch.zeros(n_cam, device=dev)
         cam_host = torch.zeros(n_cam).pin_memory()
-        entry = {"static": st, "cam_dev": cam_dev, "cam_host": cam_host, "graph": None, "out": None}
+        gen_dev = torch.zeros(rc.num * 12, device=dev, dtype=torch.float64)
+        gen_host = torch.zeros(rc.num * 12, dtype=torch.float64).pin_memory()
+        H, W = st["all_src_inps"].shape[-2:]
+        entry = {"static": st, "cam_dev": cam_dev, "cam_host": cam_host, "gen_dev": gen_dev, "gen_host": gen_host,
+                 "graph": None, "out": None}
 
         def body():
-            camera = net._camera_views(cam_dev, st["all_src_exts"][0], st["all_src_ixts"][0])
+            gens = net._raygen_views(gen_dev, (H, W)) if gen_rays else None
+            camera = net._camera_views(cam_dev, st["all_src_exts"][0], st["all_src_ixts"][0]) + (gens,)
+            rays = [None] * rc.num if gen_rays else [st[f"rays_{i}"][0] for i in range(rc.num)]
             lv = net._render_frame(st["all_src_inps"][0], st["all_src_exts"][0], st["all_src_ixts"][0], st["tar_ext"][0],
-                                   st["tar_ixt"][0], st["near_far"][0], [st[f"rays_{i}"][0] for i in range(rc.num)],
-                                   triples, camera=camera)
+                                   st["tar_ixt"][0], st["near_far"][0], rays, triples, camera=camera)
             return net._assemble([lv])
 
         self._load(entry, batch)
@@ -78,6 +86,8 @@ class FrameGraph:
             flat = torch.cat([c.reshape(-1).to(st["near_far"].device) for c in cams]).cpu()
         entry["cam_host"].copy_(net._camera_host(flat, N))
         entry["cam_dev"].copy_(entry["cam_host"], non_blocking=True)
+        entry["gen_host"].copy_(net._raygen_host(flat, N))
+        entry["gen_dev"].copy_(entry["gen_host"], non_blocking=True)
 
     def __call__(self, batch):
         """batch: tensors on the GPU or in (pinned) host memory; B must be 1.  Returns the output dict;

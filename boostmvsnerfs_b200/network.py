@@ -51,6 +51,8 @@ class EnerfNetwork(nn.Module):
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
+        self.generate_rays = False             # True: rays of full target images are generated on the device
+                                               # from tar_ext/tar_ixt; batch['rays_i'] may be absent
         self._plans = PlanCache()
         self.stage_timer = None                # optional callable(name) -> context manager
         self._packed = {}                      # level -> (param versions, packed weight tensor)
@@ -119,7 +121,7 @@ class EnerfNetwork(nn.Module):
         inv = torch.inverse(torch.cat((p_tar, last), dim=0)[None])[0]
         return (p_src @ inv).contiguous()
 
-    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt, after=None):
+    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt, after=None, image_hw=None):
         """All per-frame camera algebra, hoisted: homographies of every view for every cascade level
         and the camera centres.  With host_camera_algebra the ~1 KB of camera data makes one
         round trip to the host and the reference's own torch op sequence (incl. torch.inverse,
@@ -130,7 +132,11 @@ class EnerfNetwork(nn.Module):
         if not self.host_camera_algebra:
             projs = [self._proj_all(exts, ixts, tar_ext, tar_ixt, rc.im_feat_scale[i], rc.volume_scale[i])
                      for i in range(rc.num)]
-            return ops.CameraBlock(exts, ixts, tar_ext), projs
+            gens = None
+            if image_hw is not None:
+                gens = [ops.RayGenerator.from_cameras(tar_ext.cpu(), tar_ixt.cpu(), image_hw[0], image_hw[1],
+                                                      rc.render_scale[i], dev) for i in range(rc.num)]
+            return ops.CameraBlock(exts, ixts, tar_ext), projs, gens
         if after is not None:
             if getattr(self, '_side_stream', None) is None or self._side_stream.device != dev:
                 self._side_stream = torch.cuda.Stream(device=dev)
@@ -140,7 +146,24 @@ class EnerfNetwork(nn.Module):
         else:
             flat = torch.cat([exts.reshape(-1), ixts.reshape(-1), tar_ext.reshape(-1), tar_ixt.reshape(-1)]).cpu()
         packed = self._camera_host(flat, N).pin_memory().to(dev, non_blocking=True)
-        return self._camera_views(packed, exts, ixts)
+        gens = None
+        if image_hw is not None:
+            gp = self._raygen_host(flat, N).pin_memory().to(dev, non_blocking=True)
+            gens = self._raygen_views(gp, image_hw)
+        return self._camera_views(packed, exts, ixts) + (gens,)
+
+    def _raygen_host(self, flat, N):
+        """fp64 ray-generation parameters of every cascade level (ops.RayGenerator), (num*12,) on the host."""
+        rc = self.rc
+        h_text = flat[N * 25:N * 25 + 16].view(4, 4)
+        h_tixt = flat[N * 25 + 16:N * 25 + 25].view(3, 3)
+        return torch.cat([ops.RayGenerator.host_params(h_text.numpy(), h_tixt.numpy(), rc.render_scale[i])
+                          for i in range(rc.num)])
+
+    def _raygen_views(self, gp, image_hw):
+        rc = self.rc
+        return [ops.RayGenerator(int(image_hw[0] * rc.render_scale[i]) * int(image_hw[1] * rc.render_scale[i]),
+                                 gp[i * 12:(i + 1) * 12]) for i in range(rc.num)]
 
     def _camera_host(self, flat, N):
         """Host part of the camera stage: flat = [exts (N*16), ixts (N*9), tar_ext (16), tar_ixt (9)] on the
@@ -178,11 +201,15 @@ class EnerfNetwork(nn.Module):
         with self._stage('feature_net'):
             feats = self.forward_feat(inps)
         with self._stage('camera'):
+            need_gen = self.generate_rays or any(r is None for r in rays_by_level)
             if camera is not None:
-                cams, projs = camera
+                cams, projs, gens = camera
             else:
                 # the host round trip runs on a side stream that only waits for `ready`, so it overlaps the FPN
-                cams, projs = self._camera_stage(exts, ixts, tar_ext, tar_ixt, after=ready)
+                cams, projs, gens = self._camera_stage(exts, ixts, tar_ext, tar_ixt, after=ready,
+                                                       image_hw=(Hh, Ww) if need_gen else None)
+            if need_gen:
+                rays_by_level = list(gens)
         states = self._chain_levels(feats, projs, near_far, triples, Hh, Ww)
         out = {}
         for i, st in states.items():
@@ -257,8 +284,9 @@ class EnerfNetwork(nn.Module):
         else:          # level-0 rendering of the pre-train configs: resized colours (enerf/utils.py:669-676)
             rgb = torch.nn.functional.interpolate(inps * 0.5 + 0.5, size=(H, W), align_corners=True, mode='bilinear')
             affine = (1.0, 0.0)
-        R = rays.shape[0] - ray_begin if n_rays is None else n_rays
-        dev = rays.device
+        R_all = rays.n_rays if isinstance(rays, ops.RayGenerator) else rays.shape[0]
+        R = R_all - ray_begin if n_rays is None else n_rays
+        dev = inps.device
         nerf = getattr(self, f'nerf_{i}')
         V, Cf, Cv = len(triples[0]), im_feat.shape[1], feat_vol.shape[1]
         raw_all = torch.empty((K, R, S, 4), device=dev)
@@ -306,7 +334,8 @@ class EnerfNetwork(nn.Module):
             for b in range(B):
                 lv = self._render_frame(inps[b], batch['src_exts'][b], batch['src_ixts'][b], batch['tar_ext'][b],
                                         batch['tar_ixt'][b], batch['near_far'][b],
-                                        [batch[f'rays_{i}'][b] for i in range(rc.num)], [tuple(range(N))])
+                                        [batch[f'rays_{i}'][b] if f'rays_{i}' in batch else None
+                                         for i in range(rc.num)], [tuple(range(N))])
                 per_b.append(lv)
             for i in range(rc.num):
                 if not rc.render_if[i]:
@@ -357,7 +386,8 @@ class BoostEnerfNetwork(EnerfNetwork):
                                      f"cfg.enerf.cas_config.k_best is {K}")
                 per_b.append(self._render_frame(inps[b], batch['all_src_exts'][b], batch['all_src_ixts'][b],
                                                 batch['tar_ext'][b], batch['tar_ixt'][b], batch['near_far'][b],
-                                                [batch[f'rays_{i}'][b] for i in range(rc.num)], triples))
+                                                [batch[f'rays_{i}'][b] if f'rays_{i}' in batch else None
+                                                 for i in range(rc.num)], triples))
             ret = self._assemble(per_b)
             # the reference leaves the LAST triple in the batch (evaluators read batch['src_inps'].shape);
             # done last so the index upload cannot stall the kernels above
@@ -418,8 +448,8 @@ class BoostEnerfNetwork(EnerfNetwork):
         picked = None
         with torch.no_grad():
             feats = self.forward_feat(inps)
-            cams, projs = self._camera_stage(batch['all_src_exts'][0], batch['all_src_ixts'][0], batch['tar_ext'][0],
-                                             batch['tar_ixt'][0])
+            cams, projs, _ = self._camera_stage(batch['all_src_exts'][0], batch['all_src_ixts'][0], batch['tar_ext'][0],
+                                                batch['tar_ixt'][0])
             masks = {i: [] for i in range(rc.num) if rc.render_if[i]}
             for c0 in range(0, len(table), max_chains_per_pass):
                 part = table[c0:c0 + max_chains_per_pass]

@@ -194,6 +194,45 @@ class CameraBlock:
         self.tar_center = _cf32(tar_center, "tar_center")
 
 
+class RayGenerator:
+    """On-device ray generation: the 12 doubles the kernels need to produce ray r of a
+    full target image instead of reading the (R,8) tensor the reference's loader builds on the host
+    (reference lib/datasets/enerf_utils.py:25-31,62-71: origin = c2w[:3,3], direction =
+    [x,y,1] @ (inv(K)^T @ R_c2w^T) in fp64, one cast to fp32).  `params` may be a slice of a larger
+    device buffer (CUDA-graph replay refreshes it in place)."""
+
+    def __init__(self, n_rays, params):
+        assert params.dtype == torch.float64 and params.is_cuda and params.numel() == 12 and params.is_contiguous()
+        self.n_rays, self.params = int(n_rays), params
+
+    @staticmethod
+    def host_params(tar_ext, tar_ixt, scale=1.0):
+        """tar_ext (4,4), tar_ixt (3,3) host tensors/arrays -> float64 tensor (12,) on the host."""
+        import numpy as np
+        ixt = np.array(tar_ixt, dtype=np.float64)
+        if scale != 1.0:
+            ixt[:2] *= scale
+        c2w = np.linalg.inv(np.asarray(tar_ext, dtype=np.float64))
+        M = np.linalg.inv(ixt).T @ c2w[:3, :3].T
+        return torch.from_numpy(np.concatenate([c2w[:3, 3], M.reshape(-1)]))
+
+    @classmethod
+    def from_cameras(cls, tar_ext, tar_ixt, H, W, scale=1.0, device="cuda"):
+        Hs, Ws = int(H * scale), int(W * scale)
+        return cls(Hs * Ws, cls.host_params(tar_ext, tar_ixt, scale).to(device))
+
+
+def _bind_rays(p, rays):
+    """rays: (R,8) CUDA tensor or RayGenerator -> sets p.rays / p.ray_gen, returns (R, keepalive)."""
+    if isinstance(rays, RayGenerator):
+        p.ray_gen = rays.params.data_ptr()
+        return rays.n_rays, rays.params
+    rays = _cf32(rays, "rays")
+    assert rays.shape[1] == 8
+    p.rays = rays.data_ptr()
+    return rays.shape[0], rays
+
+
 def raygen_sample_fetch(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat, rgb, cams, views,
                         render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None,
                         want=("z_vals", "vox_feat", "img_feat", "vis_mask"), out=None):
@@ -207,17 +246,16 @@ def raygen_sample_fetch(depth, std, near_far, rays, H, W, depth_inv, S, volume, 
     some of them (written in place, e.g. slices of a K-stacked buffer).
     """
     depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
-    rays = _cf32(rays, "rays")
-    dev = rays.device
-    R = rays.shape[0]
-    n = R - ray_begin if n_rays is None else n_rays
-    assert rays.shape[1] == 8 and 0 <= ray_begin and ray_begin + n <= R
+    dev = depth.device
     hv, wv = depth.shape
     V = len(views)
     p = _lib.RaygenFetchParams()
+    R, _keep = _bind_rays(p, rays)
+    n = R - ray_begin if n_rays is None else n_rays
+    assert 0 <= ray_begin and ray_begin + n <= R
     p.depth, p.std, p.near_far = depth.data_ptr(), std.data_ptr(), near_far.data_ptr()
     p.hv, p.wv, p.H, p.W, p.depth_inv = hv, wv, H, W, int(depth_inv)
-    p.rays, p.ray_begin, p.n_rays = rays.data_ptr(), ray_begin, n
+    p.ray_begin, p.n_rays = ray_begin, n
     t = _linspace(S, dev) if S > 1 else None
     p.t, p.S = (t.data_ptr() if t is not None else 0), S
     out = dict(out) if out else {}
@@ -424,7 +462,6 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
     Returns dict(raw (n,S,4), z_vals (n,S), vis_mask (n,S) [, vis_count (n,S) int32]); `out` may
     supply preallocated contiguous tensors for any of them."""
     depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
-    rays = _cf32(rays, "rays")
     if engine not in ("fma", "mma"):
         raise BmvError(f"render_rays: unknown engine {engine!r}")
     w = packed_weights
@@ -434,16 +471,16 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
             raise BmvError("render_rays(engine='mma'): weights must come from mlp_pack.pack_nerf_weights_mma")
     else:
         w = _cf32(w, "packed_weights")
-    dev = rays.device
-    R = rays.shape[0]
-    n = R - ray_begin if n_rays is None else n_rays
-    assert rays.shape[1] == 8 and 0 <= ray_begin and ray_begin + n <= R
+    dev = depth.device
     rp = _lib.RenderRaysParams()
     p = rp.g
+    R, _keep = _bind_rays(p, rays)
+    n = R - ray_begin if n_rays is None else n_rays
+    assert 0 <= ray_begin and ray_begin + n <= R
     hv, wv = depth.shape
     p.depth, p.std, p.near_far = depth.data_ptr(), std.data_ptr(), near_far.data_ptr()
     p.hv, p.wv, p.H, p.W, p.depth_inv = hv, wv, H, W, int(depth_inv)
-    p.rays, p.ray_begin, p.n_rays = rays.data_ptr(), ray_begin, n
+    p.ray_begin, p.n_rays = ray_begin, n
     t = _linspace(S, dev) if S > 1 else None
     p.t, p.S = (t.data_ptr() if t is not None else 0), S
     _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_affine, ())

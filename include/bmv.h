@@ -147,6 +147,11 @@ typedef struct bmv_raygen_fetch_params {
    *   xyz_in (n_rays,3) [+ uvd_in (n_rays,3) normalised to [0,1]]: explicit points, one per "ray", S ignored
    *     (get_vox_feat / get_img_feat / mask_viewport on arbitrary points) */
   const float* rays12_in; const float* xyz_in; const float* uvd_in;
+  /* on-device ray generation (replaces the (R,8) tensor of
+   * lib/datasets/enerf_utils.py:62-71 when rays == NULL): DEVICE, 12 doubles = camera origin (3) followed
+   * by the 3x3 matrix M = inv(K)^T R_c2w^T (row-major); ray r is pixel (x, y) = (r % W, r / W) of the
+   * render grid, direction = [x, y, 1] M evaluated in fp64 and rounded once to fp32 like the loader. */
+  const double* ray_gen;
   const float* t; int32_t S;    /* DEVICE (S,) sample fractions; S==1 -> midpoint (t ignored) */
   /* regularised feature volume (Cv=8 channels) */
   const float* volume; int32_t Cv, Dv;                 /* spatial size = (hv,wv) */

@@ -49,7 +49,7 @@ class FakeNet:
         return _Ctx()
 
     def _camera_stage(self, exts, ixts, tar_ext, tar_ixt):
-        return None, None
+        return None, None, None
 
     def parameters(self):
         return iter([torch.zeros(1)])

@@ -153,6 +153,22 @@ def test_frame_graph_replay_matches_eager(strict_fp32):
         _report(replay2[k], eager2[k].cpu().numpy(), f"graph vs eager, second frame {k}", 1e-6)
 
 
+def test_generated_rays_give_the_same_frame(strict_fp32):
+    """net.generate_rays: no rays in the batch, same frame; also through the graph."""
+    from boostmvsnerfs_b200.graph import FrameGraph
+    g = load_golden("enerf_chain_pretrain.npz")
+    net, batch = _net_and_batch(g, RenderConfig.enerf_pretrain(2), "boost")
+    ref = net(dict(batch))
+    norays = {k: v for k, v in batch.items() if not k.startswith("rays_")}
+    out = net(dict(norays))
+    for k in ref:
+        _report(out[k], ref[k].cpu().numpy(), f"generated rays {k}", 1e-6)
+    net.generate_rays = True
+    out2 = FrameGraph(net)(dict(batch))
+    for k in ref:
+        _report(out2[k], ref[k].cpu().numpy(), f"generated rays, graph {k}", 1e-6)
+
+
 def test_training_mode_and_cpu_are_refused():
     from boostmvsnerfs_b200 import network
     from boostmvsnerfs_b200.synth import make_scene

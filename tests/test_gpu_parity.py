@@ -413,3 +413,27 @@ def test_inference_plan_fpn_matches_stock_module():
     assert type(plan).__name__ == "FusedTopDownFPN"
     for a, b in zip(got, ref):
         close(a, b, "planned FPN vs stock FPN", rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ f3: rays on device
+def test_on_device_ray_generation_matches_loader(ops):
+    """RayGenerator (12 doubles) reproduces the host loader's (R,8) ray tensor (synth.full_image_rays, the
+    restatement of reference lib/datasets/enerf_utils.py:62-71): pixel indices exactly, directions to
+    the last fp32 bit except for rare fp64 double-rounding ties."""
+    from boostmvsnerfs_b200.synth import make_scene
+    sc = make_scene(H=96, W=160, n_views=3, seed=11)
+    for lvl, scale in ((1, 1.0), (0, 0.25)):
+        Hs, Ws = int(96 * scale), int(160 * scale)
+        gen = ops.RayGenerator.from_cameras(sc["tar_ext"][0], sc["tar_ixt"][0], 96, 160, scale)
+        rays = sc[f"rays_{lvl}"][0].cuda()
+        assert gen.n_rays == rays.shape[0] == Hs * Ws
+        z = torch.zeros((Hs, Ws), device="cuda")
+        cams = ops.CameraBlock(torch.zeros(1, 4, 4, device="cuda"), torch.zeros(1, 3, 3, device="cuda"),
+                               centers=torch.zeros(1, 3, device="cuda"), tar_center=torch.zeros(3, device="cuda"))
+        nf = torch.zeros((2, Hs, Ws), device="cuda")
+        a = ops.raygen_sample_fetch(z, z, nf, gen, Hs, Ws, False, 1, None, None, None, cams, [0], want=("rays12",))["rays12"]
+        exact(a[:, 6:8], rays[:, 6:8], "pixel coordinates")
+        exact(a[:, :3], rays[:, :3], "origin")
+        diff = (a[:, 3:6] != rays[:, 3:6]).float().mean().item()
+        assert diff < 1e-4, f"{diff:.2e} of the direction components differ"
+        close(a[:, 3:6], rays[:, 3:6], "directions", rtol=1e-7)
