@@ -209,6 +209,10 @@ class RayGenerator:
     def host_params(tar_ext, tar_ixt, scale=1.0):
         """tar_ext (4,4), tar_ixt (3,3) host tensors/arrays -> float64 tensor (12,) on the host."""
         import numpy as np
+        if torch.is_tensor(tar_ixt):
+            tar_ixt = tar_ixt.detach().cpu().numpy()
+        if torch.is_tensor(tar_ext):
+            tar_ext = tar_ext.detach().cpu().numpy()
         ixt = np.array(tar_ixt, dtype=np.float64)
         if scale != 1.0:
             ixt[:2] *= scale
