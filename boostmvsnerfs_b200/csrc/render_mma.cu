@@ -45,9 +45,9 @@ constexpr int V_SC = V_BV + 12;         // agg_w_fc.bias, sigma.bias, color.2.bi
 constexpr int MMA_PACK_WORDS = V_SC + 4;
 
 __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-  const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
-  __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+  __half2 hh = __floats2half2_rn(v0, v1);                 // one cvt.rn.f16x2.f32
+  const float2 back = __half22float2(hh);
+  __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
   hi = *reinterpret_cast<uint32_t*>(&hh);
   lo = *reinterpret_cast<uint32_t*>(&ll);
 }
@@ -109,8 +109,14 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
   const int64_t n_samples = p.n_rays * S;
   const float ba = sV[V_SC], bs = sV[V_SC + 1], b2 = sV[V_SC + 2];
 
-  for (int64_t base = ((int64_t)blockIdx.x * kMmaWarps + warp) * 32; base < n_samples;
-       base += (int64_t)gridDim.x * kMmaWarps * 32) {
+  // All warps of the CTA run the same number of rounds and meet at a barrier each round: the round body is
+  // ~90 KB of straight-line code, and warps that drift apart thrash the instruction cache (ncu: no_instruction).
+  const int64_t per_round = (int64_t)gridDim.x * kMmaWarps * 32;
+  const int64_t rounds = (n_samples + per_round - 1) / per_round;
+  for (int64_t rd = 0; rd < rounds; ++rd) {
+    const int64_t base = rd * per_round + ((int64_t)blockIdx.x * kMmaWarps + warp) * 32;
+    __syncthreads();
+    if (base >= n_samples) continue;
     // ------------------------------------------------------------ gather: one lane per sample
     {
       const int64_t si = base + lane;
