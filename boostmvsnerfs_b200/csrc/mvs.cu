@@ -127,8 +127,13 @@ __global__ void __launch_bounds__(128) mvs_march_fetch_kernel(bmv_mvs_march_para
     for (int v = 0; v < V; ++v) load_cam(&cams[v], p.src_exts, p.src_ixts, nullptr, p.view[v], threadIdx.x);
   }
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_rays * p.S) return;
+  // the 86-float rows of a warp's 32 consecutive samples are contiguous in the output: stage them in
+  // shared memory (stride 87: conflict-free) and write them back with coalesced 8-byte stores
+  __shared__ float s_rows[128][87];
+  const int64_t total = p.n_rays * p.S;
+  const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i_raw < total;
+  const int64_t i = live ? i_raw : total - 1;
   const int64_t li = i / p.S;
   const int s = (int)(i % p.S);
   const int64_t r = p.ray_begin + li;
@@ -138,16 +143,16 @@ __global__ void __launch_bounds__(128) mvs_march_fetch_kernel(bmv_mvs_march_para
   const float t = __ldg(p.t + s);
   const float z = add_rn(mul_rn(near, sub_rn(1.f, t)), mul_rn(far, t));
   const float x = add_rn(ra.x, mul_rn(ra.w, z)), y = add_rn(ra.y, mul_rn(rb.x, z)), zz = add_rn(ra.z, mul_rn(rb.y, z));
-  if (p.z_vals) p.z_vals[li * p.S + s] = z;
+  if (p.z_vals && live) p.z_vals[li * p.S + s] = z;
   const float isx = (float)(p.W - 1), isy = (float)(p.H - 1);
   // ---- visibility over the triple (same arithmetic as the ENeRF path)
   int cnt = 0;
 #pragma unroll
   for (int v = 0; v < V; ++v) cnt += point_visible(cams[v], x, y, zz, isx, isy) ? 1 : 0;
-  if (p.vis_mask) p.vis_mask[li * p.S + s] = div_rn((float)cnt, (float)V);
-  if (p.vis_count) p.vis_count[li * p.S + s] = cnt;
+  if (p.vis_mask && live) p.vis_mask[li * p.S + s] = div_rn((float)cnt, (float)V);
+  if (p.vis_count && live) p.vis_count[li * p.S + s] = cnt;
   if (!p.mlp_in) return;
-  float* o = p.mlp_in + (li * p.S + s) * 86;
+  float* o = s_rows[threadIdx.x];
   // ---- NDC in the padded frustum of reference view 0: matmul(R^T)+T, @K^T, /z, /inv_scale, pad rescale
   const ViewCam& c0 = cams[0];
   float ndc[3];
@@ -244,6 +249,17 @@ __global__ void __launch_bounds__(128) mvs_march_fetch_kernel(bmv_mvs_march_para
     o[83] = dot3_gemm(ux, uy, uz, c0.E[0], c0.E[1], c0.E[2]);
     o[84] = dot3_gemm(ux, uy, uz, c0.E[4], c0.E[5], c0.E[6]);
     o[85] = dot3_gemm(ux, uy, uz, c0.E[8], c0.E[9], c0.E[10]);
+  }
+  __syncwarp();
+  {
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + wbase;            // first sample of this warp
+    const int rows = (int)min((int64_t)32, total - i0);
+    float2* dst = reinterpret_cast<float2*>(p.mlp_in + i0 * 86);             // 344 B rows: 8-byte aligned
+    for (int j = lane; j < rows * 43; j += 32) {
+      const int e = 2 * j, r = e / 86, c = e - r * 86;
+      dst[j] = make_float2(s_rows[wbase + r][c], s_rows[wbase + r][c + 1]);
+    }
   }
 }
 
