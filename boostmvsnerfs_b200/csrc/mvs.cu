@@ -180,8 +180,10 @@ __global__ void __launch_bounds__(128) mvs_march_fetch_kernel(bmv_mvs_march_para
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float arg = mul_rn(ndc[a], f);
-        o[3 + k * 3 + a] = sinf(arg);
-        o[33 + k * 3 + a] = cosf(arg);
+        float sn, cs;
+        sincosf(arg, &sn, &cs);                 // same accuracy as sinf/cosf, one range reduction
+        o[3 + k * 3 + a] = sn;
+        o[33 + k * 3 + a] = cs;
       }
       f *= 2.f;
     }
