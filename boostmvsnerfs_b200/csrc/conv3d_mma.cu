@@ -1,0 +1,299 @@
+// Tensor-core 3x3x3 / stride-1 / pad-1 convolution for the FULL-RESOLUTION layers of the kept 3-D
+// cost regularisers (conv0: C->8, and the merged output heads 8->9), channels-last fp32 in and out.
+//
+// Why (north_star: "unless ncu shows a hand-written tensor-core tile pays off"): with every other stage
+// optimised these cuDNN layers dominate the frame and run at 3 % of the TF32 peak AND 6 % of the HBM
+// bandwidth (profiles/round1_fpn_layers.md: cost_reg_1.conv0 0.93 ms for 14.4 GMAC / 401 MB; heads
+// 0.6 ms) — cuDNN has no good kernel for 8..32-channel 3-D convolutions.
+//
+// Precision contract: operands are rounded to fp16 (11-bit significand), accumulation is fp32 — the
+// same class as cuDNN's TF32 path (10+1 bits), which is what PyTorch uses for convolutions by default
+// (torch.backends.cudnn.allow_tf32 = True).  The host side (inference_plan.py) therefore routes a layer
+// here ONLY when allow_tf32 is True; with TF32 disabled (the strict 1e-4 parity tests) cuDNN's fp32
+// path runs instead.
+//
+// Implicit GEMM on mma.sync.m16n8k16: M = 16 consecutive x voxels, N = 8 output channels per n-tile,
+// K = one 32-byte segment of a staged input row (a "k-step"):
+//     Cin 16: the 16 channels of voxel x+dx                         (3 k-steps per (dz,dy))
+//     Cin 32: 16 of the 32 channels of voxel x+dx                   (6 k-steps)
+//     Cin  8: the 8+8 channels of voxels x+dx, x+dx+1 — two taps per MMA; the third tap is paired with
+//             zero weights                                          (2 k-steps)
+// A CTA stages an (8+2)x(TH+2)x(32+2) input tile as fp16 in shared memory (zero outside the volume = the
+// convolution's padding).  A warp owns WD x TH x 16 output voxels and walks the INPUT rows: each A
+// fragment (one ldmatrix.x4) is used for every (dz,dy) whose output row the warp owns, so shared-memory
+// traffic per MMA drops ~3x against a per-output-tile loop; weights (host-arranged B fragments) stay in
+// registers when they fit.  Bias + ReLU are fused in the epilogue; channels >= `split` can go to a
+// second tensor (the depth logits of the merged heads).
+#include <cuda_fp16.h>
+
+#include "bmv_internal.cuh"
+
+namespace bmv {
+
+constexpr int kConvThreads = 256;
+constexpr int kConvWarps = kConvThreads / 32;
+
+template <int CIN> struct ConvCfg;
+// Shared-memory voxel v (index in its staged row) holds its 16-byte chunk c at chunk c ^ swz(v): with
+// 32- and 64-byte voxels this makes the 8 rows of every ldmatrix 8x8 block hit 8 distinct 16-byte bank groups.
+template <> struct ConvCfg<16> {
+  static constexpr int VS = 32, KS = 3, NT = 1, TH = 4, WD = 2, EXTRA = 0;
+  static constexpr bool BREG = true;
+  __device__ static __forceinline__ int swz(int v) { return (v >> 2) & 1; }
+  // k-step j: voxel offset and first 16-byte chunk of the lane's row segment (hi = lane / 16)
+  __device__ static __forceinline__ int step_voxel(int j, int hi) { return j; }
+  __device__ static __forceinline__ int step_chunk(int j, int hi) { return hi; }
+};
+template <> struct ConvCfg<32> {
+  static constexpr int VS = 64, KS = 6, NT = 1, TH = 2, WD = 2, EXTRA = 0;
+  static constexpr bool BREG = false;
+  __device__ static __forceinline__ int swz(int v) { return (v >> 1) & 3; }
+  __device__ static __forceinline__ int step_voxel(int j, int hi) { return j >> 1; }
+  __device__ static __forceinline__ int step_chunk(int j, int hi) { return (j & 1) * 2 + hi; }
+};
+template <> struct ConvCfg<8> {
+  static constexpr int VS = 16, KS = 2, NT = 2, TH = 4, WD = 1, EXTRA = 1;   // +1 voxel: the unpaired tap reads x+3
+  static constexpr bool BREG = false;
+  __device__ static __forceinline__ int swz(int v) { return 0; }
+  __device__ static __forceinline__ int step_voxel(int j, int hi) { return 2 * j + hi; }
+  __device__ static __forceinline__ int step_chunk(int j, int hi) { return 0; }
+};
+
+template <int CIN>
+struct ConvTile {
+  using Cfg = ConvCfg<CIN>;
+  static constexpr int TD = 8, TW = 32, TH = Cfg::TH;
+  static constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
+  static constexpr int ROWV = HW + Cfg::EXTRA;                          // staged voxels per row
+  static constexpr int ROWB = ROWV * Cfg::VS;                           // bytes per staged row
+  static constexpr int TILE_BYTES = HD * HH * ROWB;
+  static constexpr int W_WORDS = 9 * Cfg::KS * Cfg::NT * 32 * 2;
+  static constexpr int JOBS = (TD / Cfg::WD) * (TW / 16);
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void hmma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
+  using T = ConvTile<CIN>;
+  using Cfg = ConvCfg<CIN>;
+  constexpr int NT = Cfg::NT, KS = Cfg::KS, WD = Cfg::WD, TH = T::TH;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* tile = smem;
+  const uint2* wfrag = reinterpret_cast<const uint2*>(smem + T::TILE_BYTES);
+  // ---- weights -> shared memory
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
+    uint4* dst = reinterpret_cast<uint4*>(smem + T::TILE_BYTES);
+    for (int i = threadIdx.x; i < T::W_WORDS / 4; i += kConvThreads) dst[i] = __ldg(src + i);
+  }
+  // ---- which output tile
+  const int tiles_w = (p.W + T::TW - 1) / T::TW, tiles_h = (p.H + TH - 1) / TH, tiles_d = (p.D + T::TD - 1) / T::TD;
+  int b = blockIdx.x;
+  const int tw = b % tiles_w; b /= tiles_w;
+  const int th = b % tiles_h; b /= tiles_h;
+  const int td = b % tiles_d; b /= tiles_d;
+  const int n = b;
+  const int x0 = tw * T::TW, y0 = th * TH, d0 = td * T::TD;
+  // ---- stage the input tile with halo as fp16; loads are issued in batches of 8 per thread.
+  // Element i = threadIdx.x + k*256 of the flattened (row = hd*HH+hy, col = hx*CH4+c4) tile; (row, col)
+  // advance incrementally (no divisions in the loop).
+  {
+    const float* xin = p.x + (int64_t)n * p.x_n_stride;
+    constexpr int CH4 = CIN / 4;                                        // float4 chunks per voxel (power of two)
+    constexpr int PER_ROW = T::ROWV * CH4;
+    constexpr int ROWS = T::HD * T::HH;
+    constexpr int BATCH = 8;
+    constexpr int STEP_ROW = kConvThreads / PER_ROW, STEP_COL = kConvThreads % PER_ROW;
+    int row = threadIdx.x / PER_ROW, col = threadIdx.x % PER_ROW;
+    while (row < ROWS) {
+      float4 val[BATCH];
+      int srow[BATCH], scol[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        srow[j] = row; scol[j] = col;
+        const int hd = row / T::HH, hy = row - hd * T::HH;
+        const int hx = col / CH4, c4 = col % CH4;
+        const int gx = x0 + hx - 1, gy = y0 + hy - 1, gd = d0 + hd - 1;
+        val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < ROWS && hx < T::HW && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H && gd >= 0 && gd < p.D)
+          val[j] = __ldg(reinterpret_cast<const float4*>(xin + (int64_t)gd * p.x_d_stride + (int64_t)gy * p.x_y_stride +
+                                                         (int64_t)gx * p.x_x_stride + c4 * 4));
+        row += STEP_ROW; col += STEP_COL;
+        if (col >= PER_ROW) { col -= PER_ROW; ++row; }
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        if (srow[j] < ROWS) {
+          const int hx = scol[j] / CH4, c4 = scol[j] % CH4;
+          __half2 lo = __floats2half2_rn(val[j].x, val[j].y), hi = __floats2half2_rn(val[j].z, val[j].w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(tile + srow[j] * T::ROWB + hx * Cfg::VS + (((c4 >> 1) ^ Cfg::swz(hx)) << 4) + (c4 & 1) * 8) = pk;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  // ldmatrix row of this lane: matrix m = lane/8 -> rows (m&1)*8 + lane%8; m>>1 selects the upper 8 k (next 16 bytes)
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhi = lane >> 4;
+  // ---- weights to registers when they fit
+  uint2 breg[Cfg::BREG ? 9 * KS * NT : 1];
+  if (Cfg::BREG) {
+#pragma unroll
+    for (int i = 0; i < 9 * KS * NT; ++i) breg[i] = wfrag[i * 32 + lane];
+  }
+  float bias0[NT], bias1[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    bias0[nt] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+    bias1[nt] = (p.bias && c + 1 < p.Cout) ? __ldg(p.bias + c + 1) : 0.f;
+  }
+  float* out = p.out + (int64_t)n * p.o_n_stride;
+  float* out2 = p.out2 ? p.out2 + (int64_t)n * p.o2_n_stride : nullptr;
+  const int split = p.out2 ? p.split : p.Cout;
+  const bool vec2 = (NT == 1) && p.Cout == 8 && split == 8 && (p.o_x_stride % 2 == 0) && (p.o_y_stride % 2 == 0) &&
+                    (p.o_d_stride % 2 == 0) && (p.o_n_stride % 2 == 0) && (((uintptr_t)p.out & 7) == 0);
+
+  // ---- each warp owns WD x TH output rows of 16 voxels and walks the input rows they touch
+  for (int job = warp; job < T::JOBS; job += kConvWarps) {
+    const int mx = job % (T::TW / 16), db = (job / (T::TW / 16)) * WD;
+    if (d0 + db >= p.D || x0 + mx * 16 >= p.W) continue;                // warp-uniform
+    float acc[WD][TH][NT][4];
+#pragma unroll
+    for (int od = 0; od < WD; ++od)
+#pragma unroll
+      for (int oy = 0; oy < TH; ++oy)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          acc[od][oy][nt][0] = bias0[nt]; acc[od][oy][nt][1] = bias1[nt];
+          acc[od][oy][nt][2] = bias0[nt]; acc[od][oy][nt][3] = bias1[nt];
+        }
+    uint32_t aoff[KS];                                                  // this lane's byte offset in a staged row, per k-step
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+      const int v = mx * 16 + lrow + Cfg::step_voxel(j, lhi);
+      aoff[j] = tile_s + v * Cfg::VS + ((Cfg::step_chunk(j, lhi) ^ Cfg::swz(v)) << 4);
+    }
+#pragma unroll
+    for (int pd = 0; pd < WD + 2; ++pd) {
+#pragma unroll
+      for (int py = 0; py < TH + 2; ++py) {
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          uint32_t a[4];
+          ldmatrix_x4(a, aoff[j] + ((db + pd) * T::HH + py) * T::ROWB);
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz) {
+            const int od = pd - dz;
+            if (od < 0 || od >= WD) continue;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int oy = py - dy;
+              if (oy < 0 || oy >= TH) continue;
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) {
+                const int wi = ((dz * 3 + dy) * KS + j) * NT + nt;
+                const uint2 bw = Cfg::BREG ? breg[Cfg::BREG ? wi : 0] : wfrag[wi * 32 + lane];
+                hmma16816(acc[od][oy][nt], a, bw.x, bw.y);
+              }
+            }
+          }
+        }
+      }
+    }
+    // ---- epilogue: ReLU, store fp32 channels-last
+    const int gx0 = x0 + mx * 16 + g, gx1 = gx0 + 8;
+#pragma unroll
+    for (int od = 0; od < WD; ++od) {
+      const int gd = d0 + db + od;
+      if (gd >= p.D) continue;
+#pragma unroll
+      for (int oy = 0; oy < TH; ++oy) {
+        const int gy = y0 + oy;
+        if (gy >= p.H) continue;
+        float* orow = out + (int64_t)gd * p.o_d_stride + (int64_t)gy * p.o_y_stride;
+        float* orow2 = out2 ? out2 + (int64_t)gd * p.o2_d_stride + (int64_t)gy * p.o2_y_stride : nullptr;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          float v0 = acc[od][oy][nt][0], v1 = acc[od][oy][nt][1], v2 = acc[od][oy][nt][2], v3 = acc[od][oy][nt][3];
+          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+          if (vec2) {
+            if (gx0 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
+            if (gx1 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int ce = c + e;
+              if (ce >= p.Cout) continue;
+              float* r0 = ce < split ? orow : orow2;
+              const int64_t xs = ce < split ? p.o_x_stride : p.o2_x_stride;
+              const int cc = ce < split ? ce : ce - split;
+              if (gx0 < p.W) r0[(int64_t)gx0 * xs + cc] = e ? v1 : v0;
+              if (gx1 < p.W) r0[(int64_t)gx1 * xs + cc] = e ? v3 : v2;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int CIN>
+static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
+  using T = ConvTile<CIN>;
+  const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) {
+      set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+      return BMV_ERR_CUDA_LAUNCH;
+    }
+    configured = true;
+  }
+  const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
+  conv3d_k3_mma_kernel<CIN><<<(unsigned)blocks, kConvThreads, smem, st>>>(p);
+  return check_launch("bmv_conv3d_k3");
+}
+
+}  // namespace bmv
+
+extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: null pointer");
+  BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad size");
+  BMV_REQUIRE(p->x_x_stride % 4 == 0 && p->x_y_stride % 4 == 0 && p->x_d_stride % 4 == 0 && p->x_n_stride % 4 == 0 &&
+                  ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->wfrag & 15) == 0,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: input must be channels-last with 16-byte aligned voxels");
+  BMV_REQUIRE(!p->out2 || (p->split >= 1 && p->split < p->Cout), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad split");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->Cin == 16 && p->Cout <= 8) return launch_conv<16>(*p, st);
+  if (p->Cin == 32 && p->Cout <= 8) return launch_conv<32>(*p, st);
+  if (p->Cin == 8 && p->Cout <= 16) return launch_conv<8>(*p, st);
+  set_error("bmv_conv3d_k3: (Cin=%d, Cout=%d) not instantiated (16->8, 32->8, 8->16)", p->Cin, p->Cout);
+  return BMV_ERR_UNSUPPORTED_SHAPE;
+}
+
+// words (uint32) of the fragment-ordered weight buffer for a (Cin, Cout) pair, -1 if not instantiated
+extern "C" BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout) {
+  if (Cin == 16 && Cout <= 8) return bmv::ConvTile<16>::W_WORDS;
+  if (Cin == 32 && Cout <= 8) return bmv::ConvTile<32>::W_WORDS;
+  if (Cin == 8 && Cout <= 16) return bmv::ConvTile<8>::W_WORDS;
+  return -1;
+}

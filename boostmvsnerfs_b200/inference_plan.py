@@ -97,16 +97,43 @@ class MergedHeadsCostReg(nn.Module):
     cost_reg_1, 0.26+0.26 ms for cost_reg_0; profiles/round1_costreg_layers.md).  Same products and
     sums per output channel, so the result is unchanged."""
 
+    # Full-resolution layers on libbmv's tensor-core kernel (csrc/conv3d_mma.cu) instead of cuDNN.  Its
+    # fp16-operand / fp32-accumulate arithmetic is TF32-class, so it is used only where PyTorch itself
+    # would run the convolution in TF32 (torch.backends.cudnn.allow_tf32, the default); strict-fp32
+    # runs keep cuDNN's fp32 kernels.
+    tensor_core_convs = True
+
     def __init__(self, net):
         super().__init__()
         self.net = net
         w = torch.cat([net.feat_conv[0].weight.detach(), net.depth_conv[0].weight.detach()], dim=0)
         self.heads = nn.Conv3d(8, 9, 3, padding=1, bias=False)
         self.heads.weight = nn.Parameter(w.contiguous(), requires_grad=False)
+        self._packed = None
+
+    def _use_tensor_core_convs(self, x):
+        from .mlp_pack import CONV3D_K3_SHAPES
+        return (self.tensor_core_convs and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+                and torch.backends.cudnn.allow_tf32 and x.shape[1] in CONV3D_K3_SHAPES
+                and isinstance(self.net.conv0.bn, nn.Identity))
+
+    def _packed_weights(self, device):
+        if self._packed is None or self._packed[0].device != device:
+            from .mlp_pack import pack_conv3d_k3
+            c0 = self.net.conv0.conv
+            self._packed = (pack_conv3d_k3(c0.weight).to(device), c0.bias.detach().float().contiguous().to(device),
+                            pack_conv3d_k3(self.heads.weight).to(device))
+        return self._packed
 
     def forward(self, x):
         n = self.net
-        s0 = n.conv0(x)
+        fast = self._use_tensor_core_convs(x)
+        if fast:
+            from . import ops
+            w0, b0, wh = self._packed_weights(x.device)
+            s0 = ops.conv3d_k3(x, w0, b0, 8, relu=True)
+        else:
+            s0 = n.conv0(x)
         s1 = n.conv2(n.conv1(s0))
         s2 = n.conv4(n.conv3(s1))
         y = s2
@@ -114,6 +141,11 @@ class MergedHeadsCostReg(nn.Module):
             y = s2 + n.conv7(n.conv6(n.conv5(s2)))
         y = s1 + n.conv9(y)
         y = s0 + n.conv11(y)
+        if fast and y.stride(1) == 1:
+            # feature volume and depth logits as two dense tensors (32-byte voxels for the trilinear fetch)
+            logits = torch.empty((y.shape[0], 1) + tuple(y.shape[2:]), device=y.device)
+            feat = ops.conv3d_k3(y, wh, None, 9, relu=False, out2=logits, split=8)
+            return feat, logits[:, 0]
         out = self.heads(y)
         return out[:, :8], out[:, 8]
 

@@ -153,3 +153,49 @@ def pack_nerf_weights_mma(nerf):
                                   torch.tensor(0.)])])
     packed = torch.cat([blocks, vec.contiguous().view(torch.int32)])
     return packed.to(next(nerf.parameters()).device)
+
+
+# ------------------------------------------------------------------------------------------ conv3d (csrc/conv3d_mma.cu)
+CONV3D_K3_SHAPES = {16: 8, 32: 8, 8: 16}     # Cin -> largest Cout instantiated
+
+
+def _conv3d_ksteps(cin):
+    """k-steps of one (dz,dy) input row: list over steps of 16 (dx, channel) pairs, None = zero weight."""
+    if cin == 16:
+        return [[(dx, c) for c in range(16)] for dx in range(3)]
+    if cin == 32:
+        return [[(dx, half * 16 + c) for c in range(16)] for dx in range(3) for half in range(2)]
+    if cin == 8:
+        return [[(0, c) for c in range(8)] + [(1, c) for c in range(8)],
+                [(2, c) for c in range(8)] + [None] * 8]
+    raise ValueError(cin)
+
+
+def pack_conv3d_k3(weight):
+    """weight (Cout, Cin, 3, 3, 3) fp32 -> int32 tensor in the order bmv_conv3d_k3 reads:
+    [dz][dy][k-step j][n-tile][lane = 4g+t] x {b0, b1}; b0 = fp16 pair at K indices (2t, 2t+1) of the k-step,
+    b1 at (2t+8, 2t+9), output channel n = nt*8+g (mma.sync.m16n8k16 B fragment); absent channels are zero."""
+    Cout, Cin = weight.shape[:2]
+    if Cin not in CONV3D_K3_SHAPES or Cout > CONV3D_K3_SHAPES[Cin] or tuple(weight.shape[2:]) != (3, 3, 3):
+        raise ValueError(f"conv3d_k3 is not instantiated for weight {tuple(weight.shape)}")
+    steps = _conv3d_ksteps(Cin)
+    NT = (CONV3D_K3_SHAPES[Cin] + 7) // 8
+    w = torch.zeros(NT * 8, Cin, 3, 3, 3)
+    w[:Cout] = weight.detach().float().cpu()
+    # B[dz][dy][j][k][n]
+    B = torch.zeros(3, 3, len(steps), 16, NT * 8)
+    for j, step in enumerate(steps):
+        for k, src in enumerate(step):
+            if src is not None:
+                dx, c = src
+                B[:, :, j, k, :] = w[:, c, :, :, dx].permute(1, 2, 0)
+    B = B.half()
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((3, 3, len(steps), NT, 32, 2, 2), dtype=torch.float16)
+    for nt in range(NT):
+        n = nt * 8 + g
+        for r in range(2):
+            for e in range(2):
+                out[:, :, :, nt, :, r, e] = B[:, :, :, 2 * t + 8 * r + e, n]
+    return out.reshape(-1).view(torch.int32).to(weight.device)

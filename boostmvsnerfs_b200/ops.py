@@ -600,3 +600,39 @@ def fpn_topdown(prev, lateral_in, weight, bias):
     p.out = out.data_ptr()
     _lib.call("bmv_fpn_topdown", p, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------ tensor-core 3-D convolution
+def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0):
+    """3x3x3 / stride 1 / pad 1 convolution (+bias, optional ReLU) of a channels_last_3d fp32 volume
+    on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
+    lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
+    returns (N,cout,D,H,W) channels_last_3d (or writes `out`, any voxel-major strides).  With `out2`
+    (N,cout-split,D,H,W) channels >= split go there instead (`out` then holds `split` channels)."""
+    _f32(x, "x")
+    N, Cin, D, H, W = x.shape
+    if x.stride(1) != 1:
+        raise BmvError("conv3d_k3: x must be channels_last_3d")
+    if out is None:
+        out = torch.empty((N, split if out2 is not None else cout, D, H, W), device=x.device,
+                          memory_format=torch.channels_last_3d)
+    if out.stride(1) != 1 or (out2 is not None and out2.shape[1] > 1 and out2.stride(1) != 1):
+        raise BmvError("conv3d_k3: out must be channels_last_3d")
+    need = _lib.load().bmv_conv3d_k3_weight_words(Cin, cout)
+    if need < 0 or wfrag.numel() != need or wfrag.dtype != torch.int32:
+        raise BmvError(f"conv3d_k3: weight buffer does not match (Cin={Cin}, Cout={cout}): {wfrag.numel()} vs {need}")
+    p = _lib.Conv3dParams()
+    p.x = x.data_ptr()
+    p.x_n_stride, p.x_d_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3), x.stride(4)
+    p.wfrag = wfrag.data_ptr()
+    p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
+    p.N, p.D, p.H, p.W, p.Cin, p.Cout, p.relu = N, D, H, W, Cin, cout, int(bool(relu))
+    p.out = out.data_ptr()
+    p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
+    if out2 is not None:
+        _f32(out2, "out2")
+        p.out2, p.split = out2.data_ptr(), split
+        p.o2_n_stride, p.o2_d_stride, p.o2_y_stride, p.o2_x_stride = (out2.stride(0), out2.stride(2), out2.stride(3),
+                                                                      out2.stride(4))
+    _lib.call("bmv_conv3d_k3", p, _stream())
+    return out

@@ -318,6 +318,29 @@ typedef struct bmv_fpn_topdown_params {
 } bmv_fpn_topdown_params;
 BMV_API int bmv_fpn_topdown(const bmv_fpn_topdown_params* p, bmv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core 3x3x3 / stride 1 / padding 1 convolution (+bias, optional ReLU) for the full-resolution
+ * layers of the kept 3-D cost regularisers: conv0 = ConvBnReLU3D(C,8) and the output heads
+ * (reference lib/networks/enerf/cost_reg_net.py:7-13,27-35 MinCostRegNet, 39-62 CostRegNet; BN folded).
+ * Operands rounded to fp16, fp32 accumulation: TF32-class accuracy, so hosts route a layer here only
+ * where the framework would use TF32 convolutions (torch.backends.cudnn.allow_tf32).
+ * x (N,D,H,W,Cin) channels-last fp32 via strides (in floats, multiples of 4); out likewise (any
+ * strides, Cout channels written at out + ... + c).  wfrag: bmv_conv3d_k3_weight_words(Cin,Cout)
+ * uint32 words in mma B-fragment order [dz][dy][k-step][n-tile][lane][2] (mlp_pack.pack_conv3d_k3; the
+ * k-steps of each Cin are described in csrc/conv3d_mma.cu).
+ * Instantiated (Cin,Cout<=): (16,8) (32,8) (8,16).
+ */
+typedef struct bmv_conv3d_params {
+  const float* x; int64_t x_n_stride, x_d_stride, x_y_stride, x_x_stride;
+  const uint32_t* wfrag; const float* bias;   /* bias (Cout) or NULL */
+  int32_t N, D, H, W, Cin, Cout, relu;
+  float* out; int64_t o_n_stride, o_d_stride, o_y_stride, o_x_stride;
+  float* out2; int64_t o2_n_stride, o2_d_stride, o2_y_stride, o2_x_stride;   /* optional: channels >= split */
+  int32_t split;                /* with out2: channel c >= split is written to out2 at channel c - split */
+} bmv_conv3d_params;
+BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
+BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,105 @@
+"""bmv_conv3d_k3 (tensor-core 3x3x3 convolution of the kept cost regularisers) against cuDNN fp32.
+
+Two bars:  (1) with operands that are exactly representable in fp16 the kernel's only difference from an
+fp32 convolution is summation order -> 1e-5 relative;  (2) with arbitrary fp32 operands the fp16 operand
+rounding gives TF32-class error -> 2e-3 of the output scale (tolerances per north_star: 1e-2 wherever
+reduced-precision operands are enabled)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (N, Cin, Cout, D, H, W, bias, relu)
+    (2, 16, 8, 8, 12, 64, True, True),
+    (1, 16, 8, 5, 7, 45, True, True),        # ragged in every dimension
+    (2, 32, 8, 16, 6, 40, True, True),
+    (1, 32, 8, 9, 5, 33, False, False),
+    (2, 8, 9, 8, 8, 64, False, False),       # merged output heads
+    (1, 8, 9, 3, 9, 17, True, True),
+    (1, 8, 16, 8, 4, 32, True, False),
+]
+
+
+def _reference(x, w, b, relu):
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = torch.nn.functional.conv3d(x, w, b, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("exact_operands", [True, False])
+def test_conv3d_k3_matches_cudnn(shape, exact_operands):
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3
+    N, Cin, Cout, D, H, W, bias, relu = shape
+    g = torch.Generator().manual_seed(Cin * 100 + W)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3, 3), generator=g) * 0.1
+    b = torch.randn(Cout, generator=g) if bias else None
+    if exact_operands:
+        x, w = x.half().float(), w.half().float()
+    x = x.cuda().contiguous(memory_format=torch.channels_last_3d)
+    w = w.cuda()
+    b = b.cuda() if bias else None
+    y = ops.conv3d_k3(x, pack_conv3d_k3(w), b, Cout, relu)
+    ref = _reference(x, w, b, relu)
+    assert y.shape == ref.shape and y.stride(1) == 1
+    scale = ref.abs().max().item()
+    tol = (1e-5 if exact_operands else 2e-3) * scale
+    assert (y - ref).abs().max().item() <= tol, ((y - ref).abs().max().item(), scale)
+
+
+def test_conv3d_k3_strided_output_and_errors():
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200._lib import BmvError
+    from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3
+    x = torch.randn((1, 16, 4, 6, 20), device="cuda").half().float().contiguous(memory_format=torch.channels_last_3d)
+    w = (torch.randn((8, 16, 3, 3, 3), device="cuda") * 0.1).half().float()
+    big = torch.zeros((1, 12, 4, 6, 20), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    ops.conv3d_k3(x, pack_conv3d_k3(w), None, 8, False, out=big[:, 2:10])       # channel slice of a wider volume
+    ref = _reference(x, w, None, False)
+    assert torch.allclose(big[:, 2:10], ref, atol=1e-5 * ref.abs().max().item())
+    assert big[:, :2].abs().max().item() == 0 and big[:, 10:].abs().max().item() == 0
+    # channel split: the merged heads write 8 feature channels and the depth logits to two tensors
+    x8 = torch.randn((2, 8, 5, 6, 37), device="cuda").half().float().contiguous(memory_format=torch.channels_last_3d)
+    w9 = (torch.randn((9, 8, 3, 3, 3), device="cuda") * 0.1).half().float()
+    logits = torch.empty((2, 1, 5, 6, 37), device="cuda")
+    feat = ops.conv3d_k3(x8, pack_conv3d_k3(w9), None, 9, False, out2=logits, split=8)
+    ref9 = _reference(x8, w9, None, False)
+    assert feat.shape == (2, 8, 5, 6, 37)
+    assert torch.allclose(feat, ref9[:, :8], atol=1e-5 * ref9.abs().max().item())
+    assert torch.allclose(logits, ref9[:, 8:], atol=1e-5 * ref9.abs().max().item())
+    with pytest.raises(BmvError):
+        ops.conv3d_k3(x.contiguous(), pack_conv3d_k3(w), None, 8, False)        # not channels-last
+    with pytest.raises(ValueError):
+        pack_conv3d_k3(torch.zeros(8, 24, 3, 3, 3))
+
+
+def test_cost_reg_plan_tensor_core_convs_match_cudnn_tf32_class():
+    """Whole regulariser: plan with libbmv convolutions vs the same plan on cuDNN fp32."""
+    from boostmvsnerfs_b200.inference_plan import MergedHeadsCostReg, PlanCache
+    from boostmvsnerfs_b200.modules import MinCostRegNet
+    torch.manual_seed(3)
+    net = MinCostRegNet(16).eval().cuda()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    plan = PlanCache().get("cr", net, torch.channels_last_3d)
+    assert isinstance(plan, MergedHeadsCostReg)
+    x = torch.rand((2, 16, 8, 32, 64), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        with torch.no_grad():
+            f_tc, d_tc = plan(x)
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            f_ref, d_ref = plan(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    for a, b in ((f_tc, f_ref), (d_tc, d_ref)):
+        assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()

@@ -1,0 +1,38 @@
+"""Times bmv_conv3d_k3 against cuDNN (TF32 and fp32) at the C2 layer shapes.  Run on a B200."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from boostmvsnerfs_b200 import ops
+from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3
+
+SHAPES = [("cost_reg_1.conv0", 4, 16, 8, 8, 272, 480, True), ("cost_reg_1.heads", 4, 8, 9, 8, 272, 480, False),
+          ("cost_reg_0.conv0", 4, 32, 8, 64, 68, 120, True), ("cost_reg_0.heads", 4, 8, 9, 64, 68, 120, False)]
+
+
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3
+
+
+for name, N, Cin, Cout, D, H, W, relu in SHAPES:
+    x = torch.randn((N, Cin, D, H, W), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    w = torch.randn((Cout, Cin, 3, 3, 3), device="cuda") * 0.1
+    wcl = w.contiguous(memory_format=torch.channels_last_3d)
+    b = torch.randn(Cout, device="cuda")
+    wf = pack_conv3d_k3(w)
+    t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, relu))
+    torch.backends.cudnn.allow_tf32 = True
+    t_tf32 = timeit(lambda: torch.nn.functional.conv3d(x, wcl, b, padding=1))
+    torch.backends.cudnn.allow_tf32 = False
+    t_fp32 = timeit(lambda: torch.nn.functional.conv3d(x, wcl, b, padding=1))
+    torch.backends.cudnn.allow_tf32 = True
+    mb = (x.numel() + N * Cout * D * H * W) * 4 / 1e6
+    print(f"{name:18s} ours {t_ours:8.1f} us ({mb / t_ours * 1e3:7.0f} GB/s algorithmic)   cudnn tf32 {t_tf32:8.1f} us   cudnn fp32 {t_fp32:8.1f} us")
