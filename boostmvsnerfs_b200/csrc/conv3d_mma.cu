@@ -81,7 +81,7 @@ __device__ __forceinline__ void hmma16816(float (&c)[4], const uint32_t (&a)[4],
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
+__global__ void __launch_bounds__(kConvThreads, CIN == 8 ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
   using T = ConvTile<CIN>;
   using Cfg = ConvCfg<CIN>;
   constexpr int NT = Cfg::NT, KS = Cfg::KS, WD = Cfg::WD, TH = T::TH;
@@ -102,42 +102,51 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3_mma_kernel(bmv_conv
   const int td = b % tiles_d; b /= tiles_d;
   const int n = b;
   const int x0 = tw * T::TW, y0 = th * TH, d0 = td * T::TD;
-  // ---- stage the input tile with halo as fp16; loads are issued in batches of 8 per thread.
-  // Element i = threadIdx.x + k*256 of the flattened (row = hd*HH+hy, col = hx*CH4+c4) tile; (row, col)
-  // advance incrementally (no divisions in the loop).
+  // ---- stage the input tile with halo as fp16.  One warp per staged row (a contiguous run of float4 in
+  // channels-last memory): lane l covers float4 l, l+32, ... of the row, so its channel chunk c4 is fixed,
+  // its voxel advances by 32/CH4 per pass, and everything row-dependent is warp-uniform.
   {
     const float* xin = p.x + (int64_t)n * p.x_n_stride;
     constexpr int CH4 = CIN / 4;                                        // float4 chunks per voxel (power of two)
     constexpr int PER_ROW = T::ROWV * CH4;
     constexpr int ROWS = T::HD * T::HH;
-    constexpr int BATCH = 8;
-    constexpr int STEP_ROW = kConvThreads / PER_ROW, STEP_COL = kConvThreads % PER_ROW;
-    int row = threadIdx.x / PER_ROW, col = threadIdx.x % PER_ROW;
-    while (row < ROWS) {
-      float4 val[BATCH];
-      int srow[BATCH], scol[BATCH];
+    constexpr int P = (PER_ROW + 31) / 32;                              // passes per row
+    constexpr int VPP = 32 / CH4;                                       // voxels per pass
+    constexpr int RB = P >= 8 ? 1 : 2;                                  // rows in flight per warp
+    const int sl = threadIdx.x & 31, sw = threadIdx.x >> 5;
+    const int c4 = sl % CH4, hx0 = sl / CH4;
+    const int64_t lane_off = (int64_t)(x0 - 1 + hx0) * p.x_x_stride + c4 * 4, pass_off = (int64_t)VPP * p.x_x_stride;
+    for (int row = sw; row < ROWS; row += RB * kConvWarps) {
+      float4 val[RB][P];
 #pragma unroll
-      for (int j = 0; j < BATCH; ++j) {
-        srow[j] = row; scol[j] = col;
-        const int hd = row / T::HH, hy = row - hd * T::HH;
-        const int hx = col / CH4, c4 = col % CH4;
-        const int gx = x0 + hx - 1, gy = y0 + hy - 1, gd = d0 + hd - 1;
-        val[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < ROWS && hx < T::HW && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H && gd >= 0 && gd < p.D)
-          val[j] = __ldg(reinterpret_cast<const float4*>(xin + (int64_t)gd * p.x_d_stride + (int64_t)gy * p.x_y_stride +
-                                                         (int64_t)gx * p.x_x_stride + c4 * 4));
-        row += STEP_ROW; col += STEP_COL;
-        if (col >= PER_ROW) { col -= PER_ROW; ++row; }
+      for (int rr = 0; rr < RB; ++rr) {
+        const int r = row + rr * kConvWarps;
+        const int hd = r / T::HH, hy = r - hd * T::HH;
+        const int gy = y0 + hy - 1, gd = d0 + hd - 1;
+        const bool row_ok = r < ROWS && gy >= 0 && gy < p.H && gd >= 0 && gd < p.D;
+        const float* src = xin + (int64_t)gd * p.x_d_stride + (int64_t)gy * p.x_y_stride + lane_off;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int hx = hx0 + VPP * k, gx = x0 - 1 + hx;
+          val[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && hx < T::HW && gx >= 0 && gx < p.W) val[rr][k] = __ldg(reinterpret_cast<const float4*>(src + k * pass_off));
+        }
       }
 #pragma unroll
-      for (int j = 0; j < BATCH; ++j) {
-        if (srow[j] < ROWS) {
-          const int hx = scol[j] / CH4, c4 = scol[j] % CH4;
-          __half2 lo = __floats2half2_rn(val[j].x, val[j].y), hi = __floats2half2_rn(val[j].z, val[j].w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(tile + srow[j] * T::ROWB + hx * Cfg::VS + (((c4 >> 1) ^ Cfg::swz(hx)) << 4) + (c4 & 1) * 8) = pk;
+      for (int rr = 0; rr < RB; ++rr) {
+        const int r = row + rr * kConvWarps;
+        if (r < ROWS) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            const int hx = hx0 + VPP * k;
+            if (hx < T::ROWV) {
+              __half2 lo = __floats2half2_rn(val[rr][k].x, val[rr][k].y), hi = __floats2half2_rn(val[rr][k].z, val[rr][k].w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(tile + r * T::ROWB + hx * Cfg::VS + (((c4 >> 1) ^ Cfg::swz(hx)) << 4) + (c4 & 1) * 8) = pk;
+            }
+          }
         }
       }
     }
@@ -164,8 +173,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3_mma_kernel(bmv_conv
   float* out = p.out + (int64_t)n * p.o_n_stride;
   float* out2 = p.out2 ? p.out2 + (int64_t)n * p.o2_n_stride : nullptr;
   const int split = p.out2 ? p.split : p.Cout;
-  const bool vec2 = (NT == 1) && p.Cout == 8 && split == 8 && (p.o_x_stride % 2 == 0) && (p.o_y_stride % 2 == 0) &&
-                    (p.o_d_stride % 2 == 0) && (p.o_n_stride % 2 == 0) && (((uintptr_t)p.out & 7) == 0);
+  const bool vec_ok = (p.o_x_stride % 2 == 0) && (p.o_y_stride % 2 == 0) && (p.o_d_stride % 2 == 0) &&
+                      (p.o_n_stride % 2 == 0) && (((uintptr_t)p.out & 7) == 0);
 
   // ---- each warp owns WD x TH output rows of 16 voxels and walks the input rows they touch
   for (int job = warp; job < T::JOBS; job += kConvWarps) {
@@ -231,7 +240,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3_mma_kernel(bmv_conv
           const int c = nt * 8 + 2 * t;
           float v0 = acc[od][oy][nt][0], v1 = acc[od][oy][nt][1], v2 = acc[od][oy][nt][2], v3 = acc[od][oy][nt][3];
           if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-          if (vec2) {
+          if (vec_ok && nt * 8 + 8 <= split) {                          // whole n-tile lands in `out`: 8-byte stores
             if (gx0 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
             if (gx1 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
           } else {

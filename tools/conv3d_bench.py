@@ -28,7 +28,11 @@ for name, N, Cin, Cout, D, H, W, relu in SHAPES:
     wcl = w.contiguous(memory_format=torch.channels_last_3d)
     b = torch.randn(Cout, device="cuda")
     wf = pack_conv3d_k3(w)
-    t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, relu))
+    if Cout == 9:       # the merged heads: 8 feature channels + depth logits to two dense tensors
+        logits = torch.empty((N, 1, D, H, W), device="cuda")
+        t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, relu, out2=logits, split=8))
+    else:
+        t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, relu))
     torch.backends.cudnn.allow_tf32 = True
     t_tf32 = timeit(lambda: torch.nn.functional.conv3d(x, wcl, b, padding=1))
     torch.backends.cudnn.allow_tf32 = False
