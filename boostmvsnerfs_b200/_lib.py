@@ -128,6 +128,14 @@ class Conv3dParams(C.Structure):
                 ("o2_x_stride", i64), ("split", i32)]
 
 
+class ConvT3dParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_n_stride", i64), ("x_d_stride", i64), ("x_y_stride", i64), ("x_x_stride", i64),
+                ("wfrag", C.c_void_p), ("bias", C.c_void_p),
+                ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
+                ("skip", C.c_void_p), ("s_n_stride", i64), ("s_d_stride", i64), ("s_y_stride", i64), ("s_x_stride", i64),
+                ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
@@ -144,10 +152,11 @@ ENTRY_POINTS = {
     "bmv_mvs_march_fetch": MvsMarchParams,
     "bmv_fpn_topdown": FpnTopdownParams,
     "bmv_conv3d_k3": Conv3dParams,
+    "bmv_convT3d_k3s2": ConvT3dParams,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",
-                 "bmv_conv3d_k3_weight_words")
+                 "bmv_conv3d_k3_weight_words", "bmv_convT3d_k3s2_weight_words")
 
 _lib = None
 
@@ -175,6 +184,8 @@ def load():
     lib.bmv_render_rays_supported.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.bmv_conv3d_k3_weight_words.restype = C.c_int
     lib.bmv_conv3d_k3_weight_words.argtypes = [C.c_int, C.c_int]
+    lib.bmv_convT3d_k3s2_weight_words.restype = C.c_int
+    lib.bmv_convT3d_k3s2_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_sizeof_params.restype = C.c_int
     lib.bmv_sizeof_params.argtypes = [C.c_char_p]
     for name, struct in ENTRY_POINTS.items():

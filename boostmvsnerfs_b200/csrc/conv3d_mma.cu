@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 
 #include "bmv_internal.cuh"
+#include "conv_mma.cuh"
 
 namespace bmv {
 
@@ -70,15 +71,6 @@ struct ConvTile {
   static constexpr int W_WORDS = 9 * Cfg::KS * Cfg::NT * 32 * 2;
   static constexpr int JOBS = (TD / Cfg::WD) * (TW / 16);
 };
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-__device__ __forceinline__ void hmma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 template <int CIN>
 __global__ void __launch_bounds__(kConvThreads, CIN == 8 ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {

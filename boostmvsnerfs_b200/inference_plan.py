@@ -119,10 +119,12 @@ class MergedHeadsCostReg(nn.Module):
 
     def _packed_weights(self, device):
         if self._packed is None or self._packed[0].device != device:
-            from .mlp_pack import pack_conv3d_k3
-            c0 = self.net.conv0.conv
+            from .mlp_pack import pack_conv3d_k3, pack_convT3d_k3s2
+            c0, t9, t11 = self.net.conv0.conv, self.net.conv9[0], self.net.conv11[0]
             self._packed = (pack_conv3d_k3(c0.weight).to(device), c0.bias.detach().float().contiguous().to(device),
-                            pack_conv3d_k3(self.heads.weight).to(device))
+                            pack_conv3d_k3(self.heads.weight).to(device),
+                            pack_convT3d_k3s2(t9.weight).to(device), t9.bias.detach().float().contiguous().to(device),
+                            pack_convT3d_k3s2(t11.weight).to(device), t11.bias.detach().float().contiguous().to(device))
         return self._packed
 
     def forward(self, x):
@@ -130,7 +132,7 @@ class MergedHeadsCostReg(nn.Module):
         fast = self._use_tensor_core_convs(x)
         if fast:
             from . import ops
-            w0, b0, wh = self._packed_weights(x.device)
+            w0, b0, wh, w9, b9, w11, b11 = self._packed_weights(x.device)
             s0 = ops.conv3d_k3(x, w0, b0, 8, relu=True)
         else:
             s0 = n.conv0(x)
@@ -139,8 +141,12 @@ class MergedHeadsCostReg(nn.Module):
         y = s2
         if n.depth_levels == 3:
             y = s2 + n.conv7(n.conv6(n.conv5(s2)))
-        y = s1 + n.conv9(y)
-        y = s0 + n.conv11(y)
+        if fast and y.stride(1) == 1 and s1.stride(1) == 1:
+            y = ops.convT3d_k3s2_add(y, w9, b9, 16, skip=s1)
+            y = ops.convT3d_k3s2_add(y, w11, b11, 8, skip=s0)
+        else:
+            y = s1 + n.conv9(y)
+            y = s0 + n.conv11(y)
         if fast and y.stride(1) == 1:
             # feature volume and depth logits as two dense tensors (32-byte voxels for the trilinear fetch)
             logits = torch.empty((y.shape[0], 1) + tuple(y.shape[2:]), device=y.device)

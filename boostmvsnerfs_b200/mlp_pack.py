@@ -199,3 +199,26 @@ def pack_conv3d_k3(weight):
             for e in range(2):
                 out[:, :, :, nt, :, r, e] = B[:, :, :, 2 * t + 8 * r + e, n]
     return out.reshape(-1).view(torch.int32).to(weight.device)
+
+
+CONVT3D_K3S2_SHAPES = ((16, 8), (32, 16))
+
+
+def pack_convT3d_k3s2(weight):
+    """ConvTranspose3d weight (Cin, Cout, 3, 3, 3) -> int32 tensor in the order bmv_convT3d_k3s2 reads:
+    [tap = (kz*3+ky)*3+kx][k-tile][n-tile][lane = 4g+t] x {b0, b1}: b0 = fp16 pair W[cin = kt*16+2t, +1][cout = nt*8+g],
+    b1 the pair at cin + 8."""
+    Cin, Cout = weight.shape[:2]
+    if (Cin, Cout) not in CONVT3D_K3S2_SHAPES or tuple(weight.shape[2:]) != (3, 3, 3):
+        raise ValueError(f"convT3d_k3s2 is not instantiated for weight {tuple(weight.shape)}")
+    w = weight.detach().float().cpu().reshape(Cin, Cout, 27).half()
+    KT, NT = Cin // 16, Cout // 8
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((27, KT, NT, 32, 2, 2), dtype=torch.float16)
+    for kt in range(KT):
+        for nt in range(NT):
+            for r in range(2):
+                for e in range(2):
+                    out[:, kt, nt, :, r, e] = w[kt * 16 + 2 * t + 8 * r + e, nt * 8 + g].T
+    return out.reshape(-1).view(torch.int32).to(weight.device)

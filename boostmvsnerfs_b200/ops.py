@@ -636,3 +636,34 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0):
                                                                       out2.stride(4))
     _lib.call("bmv_conv3d_k3", p, _stream())
     return out
+
+
+def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None):
+    """out = skip + ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1)(x) + bias on tensor cores
+    (fp16 operands, fp32 accumulation; reference `x = conv0 + self.conv11(x)`,
+    lib/networks/enerf/cost_reg_net.py:40-44,80-82).  x (N,Cin,D,H,W) and skip (N,cout,2D,2H,2W)
+    channels_last_3d; wfrag from mlp_pack.pack_convT3d_k3s2."""
+    _f32(x, "x")
+    N, Cin, D, H, W = x.shape
+    if x.stride(1) != 1:
+        raise BmvError("convT3d_k3s2_add: x must be channels_last_3d")
+    need = _lib.load().bmv_convT3d_k3s2_weight_words(Cin, cout)
+    if need < 0 or wfrag.numel() != need or wfrag.dtype != torch.int32:
+        raise BmvError(f"convT3d_k3s2_add: weight buffer does not match (Cin={Cin}, Cout={cout})")
+    out = torch.empty((N, cout, 2 * D, 2 * H, 2 * W), device=x.device, memory_format=torch.channels_last_3d)
+    p = _lib.ConvT3dParams()
+    p.x = x.data_ptr()
+    p.x_n_stride, p.x_d_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3), x.stride(4)
+    p.wfrag = wfrag.data_ptr()
+    p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
+    p.N, p.D, p.H, p.W, p.Cin, p.Cout = N, D, H, W, Cin, cout
+    if skip is not None:
+        _f32(skip, "skip")
+        if tuple(skip.shape) != tuple(out.shape) or skip.stride(1) != 1:
+            raise BmvError(f"convT3d_k3s2_add: skip must be channels_last_3d of shape {tuple(out.shape)}")
+        p.skip = skip.data_ptr()
+        p.s_n_stride, p.s_d_stride, p.s_y_stride, p.s_x_stride = skip.stride(0), skip.stride(2), skip.stride(3), skip.stride(4)
+    p.out = out.data_ptr()
+    p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
+    _lib.call("bmv_convT3d_k3s2", p, _stream())
+    return out

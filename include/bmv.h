@@ -341,6 +341,26 @@ typedef struct bmv_conv3d_params {
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) + bias + skip add:
+ *     out = skip + convT(x) + bias
+ * the decoder steps `x = conv0 + self.conv11(x)` / `x = conv2 + self.conv9(x)` of the kept cost
+ * regularisers (reference lib/networks/enerf/cost_reg_net.py:23-31,40-44,62-70,80-82; BN folded).
+ * x (N,D,H,W,Cin) channels-last fp32 (strides in floats); skip/out (N,2D,2H,2W,Cout) channels-last.
+ * fp16 operands, fp32 accumulation (TF32-class; same gating as bmv_conv3d_k3).
+ * wfrag: bmv_convT3d_k3s2_weight_words(Cin,Cout) words, B-fragment order [tap][k-tile][n-tile][lane][2]
+ * (mlp_pack.pack_convT3d_k3s2).  Instantiated (Cin,Cout): (16,8) (32,16).
+ */
+typedef struct bmv_convT3d_params {
+  const float* x; int64_t x_n_stride, x_d_stride, x_y_stride, x_x_stride;
+  const uint32_t* wfrag; const float* bias;   /* bias (Cout) or NULL */
+  int32_t N, D, H, W, Cin, Cout;              /* D,H,W: INPUT size */
+  const float* skip; int64_t s_n_stride, s_d_stride, s_y_stride, s_x_stride;   /* or NULL */
+  float* out; int64_t o_n_stride, o_d_stride, o_y_stride, o_x_stride;
+} bmv_convT3d_params;
+BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_t stream);
+BMV_API int bmv_convT3d_k3s2_weight_words(int Cin, int Cout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,18 +79,51 @@ def test_conv3d_k3_strided_output_and_errors():
         pack_conv3d_k3(torch.zeros(8, 24, 3, 3, 3))
 
 
-def test_cost_reg_plan_tensor_core_convs_match_cudnn_tf32_class():
+@pytest.mark.parametrize("shape", [(2, 16, 8, 4, 8, 32), (1, 16, 8, 3, 5, 21), (2, 32, 16, 2, 6, 40), (1, 32, 16, 5, 3, 9)])
+@pytest.mark.parametrize("exact_operands", [True, False])
+@pytest.mark.parametrize("with_skip", [True, False])
+def test_convT3d_k3s2_add_matches_cudnn(shape, exact_operands, with_skip):
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_convT3d_k3s2
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator().manual_seed(Cin + W)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    w = torch.randn((Cin, Cout, 3, 3, 3), generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    skip = torch.randn((N, Cout, 2 * D, 2 * H, 2 * W), generator=g)
+    if exact_operands:
+        x, w = x.half().float(), w.half().float()
+    x = x.cuda().contiguous(memory_format=torch.channels_last_3d)
+    w, b = w.cuda(), b.cuda()
+    skip = skip.cuda().contiguous(memory_format=torch.channels_last_3d)
+    y = ops.convT3d_k3s2_add(x, pack_convT3d_k3s2(w), b, Cout, skip=skip if with_skip else None)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    if with_skip:
+        ref = ref + skip
+    assert y.shape == ref.shape and y.stride(1) == 1
+    scale = ref.abs().max().item()
+    tol = (1e-5 if exact_operands else 2e-3) * scale
+    assert (y - ref).abs().max().item() <= tol, ((y - ref).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("minimal", [True, False])
+def test_cost_reg_plan_tensor_core_convs_match_cudnn_tf32_class(minimal):
     """Whole regulariser: plan with libbmv convolutions vs the same plan on cuDNN fp32."""
     from boostmvsnerfs_b200.inference_plan import MergedHeadsCostReg, PlanCache
-    from boostmvsnerfs_b200.modules import MinCostRegNet
+    from boostmvsnerfs_b200.modules import CostRegNet, MinCostRegNet
     torch.manual_seed(3)
-    net = MinCostRegNet(16).eval().cuda()
+    net = (MinCostRegNet(16) if minimal else CostRegNet(32)).eval().cuda()
     for m in net.modules():
         if isinstance(m, torch.nn.BatchNorm3d):
             m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
     plan = PlanCache().get("cr", net, torch.channels_last_3d)
     assert isinstance(plan, MergedHeadsCostReg)
-    x = torch.rand((2, 16, 8, 32, 64), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    x = torch.rand((2, 16 if minimal else 32, 8, 32, 64), device="cuda").contiguous(memory_format=torch.channels_last_3d)
     prev = torch.backends.cudnn.allow_tf32
     try:
         torch.backends.cudnn.allow_tf32 = True

@@ -40,3 +40,17 @@ for name, N, Cin, Cout, D, H, W, relu in SHAPES:
     torch.backends.cudnn.allow_tf32 = True
     mb = (x.numel() + N * Cout * D * H * W) * 4 / 1e6
     print(f"{name:18s} ours {t_ours:8.1f} us ({mb / t_ours * 1e3:7.0f} GB/s algorithmic)   cudnn tf32 {t_tf32:8.1f} us   cudnn fp32 {t_fp32:8.1f} us")
+
+from boostmvsnerfs_b200.mlp_pack import pack_convT3d_k3s2
+for name, N, Cin, Cout, D, H, W in [("cost_reg_1.conv11T+add", 4, 16, 8, 4, 136, 240), ("cost_reg_1.conv9T+add", 4, 32, 16, 2, 68, 120),
+                                    ("cost_reg_0.conv11T+add", 4, 16, 8, 32, 34, 60), ("cost_reg_0.conv9T+add", 4, 32, 16, 16, 17, 30)]:
+    x = torch.randn((N, Cin, D, H, W), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    w = (torch.randn((Cin, Cout, 3, 3, 3), device="cuda") * 0.1)
+    wcl = w.contiguous(memory_format=torch.channels_last_3d)
+    b = torch.randn(Cout, device="cuda")
+    skip = torch.randn((N, Cout, 2 * D, 2 * H, 2 * W), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    wf = pack_convT3d_k3s2(w)
+    t_ours = timeit(lambda: ops.convT3d_k3s2_add(x, wf, b, Cout, skip=skip))
+    t_lib = timeit(lambda: skip + torch.nn.functional.conv_transpose3d(x, wcl, b, stride=2, padding=1, output_padding=1))
+    mb = (x.numel() + 2 * skip.numel()) * 4 / 1e6
+    print(f"{name:24s} ours {t_ours:8.1f} us ({mb / t_ours * 1e3:7.0f} GB/s algorithmic)   cudnn tf32 + add {t_lib:8.1f} us")
