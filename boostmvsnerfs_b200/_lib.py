@@ -136,6 +136,13 @@ class ConvT3dParams(C.Structure):
                 ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64)]
 
 
+class FpnFusedParams(C.Structure):
+    _fields_ = [("prev", C.c_void_p), ("lateral_in", C.c_void_p), ("lat_weight", C.c_void_p), ("lat_bias", C.c_void_p),
+                ("wfrag", C.c_void_p), ("bias", C.c_void_p),
+                ("N", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
+                ("mid", C.c_void_p), ("out", C.c_void_p)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
@@ -153,10 +160,12 @@ ENTRY_POINTS = {
     "bmv_fpn_topdown": FpnTopdownParams,
     "bmv_conv3d_k3": Conv3dParams,
     "bmv_convT3d_k3s2": ConvT3dParams,
+    "bmv_fpn_topdown_smooth": FpnFusedParams,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",
-                 "bmv_conv3d_k3_weight_words", "bmv_convT3d_k3s2_weight_words")
+                 "bmv_conv3d_k3_weight_words", "bmv_convT3d_k3s2_weight_words",
+                 "bmv_fpn_topdown_smooth_weight_words")
 
 _lib = None
 
@@ -186,6 +195,8 @@ def load():
     lib.bmv_conv3d_k3_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_convT3d_k3s2_weight_words.restype = C.c_int
     lib.bmv_convT3d_k3s2_weight_words.argtypes = [C.c_int, C.c_int]
+    lib.bmv_fpn_topdown_smooth_weight_words.restype = C.c_int
+    lib.bmv_fpn_topdown_smooth_weight_words.argtypes = [C.c_int]
     lib.bmv_sizeof_params.restype = C.c_int
     lib.bmv_sizeof_params.argtypes = [C.c_char_p]
     for name, struct in ENTRY_POINTS.items():

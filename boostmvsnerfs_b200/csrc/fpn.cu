@@ -10,16 +10,16 @@ namespace bmv {
 
 template <int CIN>
 __global__ void __launch_bounds__(256) fpn_topdown_kernel(bmv_fpn_topdown_params p) {
-  __shared__ float sW[32 * CIN + 32];
-  for (int i = threadIdx.x; i < 32 * CIN; i += blockDim.x) sW[i] = p.weight[i];
+  // weights transposed to [input][32 outputs]: the 8 channel groups of a warp read 128 contiguous bytes
+  __shared__ __align__(16) float sW[32 * CIN + 32];
+  for (int i = threadIdx.x; i < 32 * CIN; i += blockDim.x) sW[(i % CIN) * 32 + i / CIN] = p.weight[i];
   if (threadIdx.x < 32) sW[32 * CIN + threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   __syncthreads();
-  const int64_t total = (int64_t)p.N * p.H * p.W * 8;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid & 7);
-  const int64_t pix = gid >> 3;
-  const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), n = (int)(pix / ((int64_t)p.W * p.H));
+  // grid (x blocks, y, n): no integer division on the per-thread path
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gx >= p.W * 8) return;
+  const int cg = gx & 7, x = gx >> 3, y = blockIdx.y, n = blockIdx.z;
+  const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
   // 1x1 lateral conv for 4 output channels
   const float* in = p.lateral_in + pix * CIN;
   float v[CIN];
@@ -29,13 +29,15 @@ __global__ void __launch_bounds__(256) fpn_topdown_kernel(bmv_fpn_topdown_params
     v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
   }
   float acc[4];
+  {
+    const float4 bb = *reinterpret_cast<const float4*>(sW + 32 * CIN + cg * 4);
+    acc[0] = bb.x; acc[1] = bb.y; acc[2] = bb.z; acc[3] = bb.w;
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    const float* w = sW + (cg * 4 + o) * CIN;
-    float a = sW[32 * CIN + cg * 4 + o];
-#pragma unroll
-    for (int i = 0; i < CIN; ++i) a = fmaf(w[i], v[i], a);
-    acc[o] = a;
+    for (int i = 0; i < CIN; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(sW + i * 32 + cg * 4);
+      acc[0] = fmaf(w.x, v[i], acc[0]); acc[1] = fmaf(w.y, v[i], acc[1]);
+      acc[2] = fmaf(w.z, v[i], acc[2]); acc[3] = fmaf(w.w, v[i], acc[3]);
+    }
   }
   // bilinear x2 upsample of prev (align_corners=True), ATen order of operations
   const int Hp = p.H / 2, Wp = p.W / 2;
@@ -62,8 +64,8 @@ extern "C" BMV_API int bmv_fpn_topdown(const bmv_fpn_topdown_params* p, bmv_stre
               "bmv_fpn_topdown: H, W must be even and >= 2");
   BMV_REQUIRE(((uintptr_t)p->prev & 15) == 0 && ((uintptr_t)p->lateral_in & 15) == 0 && ((uintptr_t)p->out & 15) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown: tensors must be 16-byte aligned");
-  const int64_t total = (int64_t)p->N * p->H * p->W * 8;
-  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  BMV_REQUIRE(p->H <= 65535 && p->N <= 65535, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown: H and N must be <= 65535");
+  const dim3 blocks((unsigned)ceil_div64((int64_t)p->W * 8, 256), (unsigned)p->H, (unsigned)p->N);
   cudaStream_t st = (cudaStream_t)stream;
   if (p->Cin == 8) fpn_topdown_kernel<8><<<blocks, 256, 0, st>>>(*p);
   else if (p->Cin == 16) fpn_topdown_kernel<16><<<blocks, 256, 0, st>>>(*p);

@@ -160,9 +160,22 @@ class FusedTopDownFPN(nn.Module):
     """FeatureNet forward with each `_upsample_add(x, lat(c))` step done by one libbmv launch
     (csrc/fpn.cu).  Wraps a folded, channels-last FeatureNet copy; CUDA only."""
 
+    # With TF32-class convolutions allowed (torch.backends.cudnn.allow_tf32, the default) each top-down
+    # step AND its smoothing 3x3 convolution run as one launch (csrc/fpn_fused.cu): the 32-channel
+    # full-resolution tensor never reaches HBM.
+    fused_smooth = True
+
     def __init__(self, fpn):
         super().__init__()
         self.fpn = fpn
+        self._packed = None
+
+    def _smooth_weights(self, device):
+        if self._packed is None or self._packed[0].device != device:
+            from .mlp_pack import pack_conv2d_k3_c32
+            self._packed = (pack_conv2d_k3_c32(self.fpn.smooth1.weight).to(device),
+                            pack_conv2d_k3_c32(self.fpn.smooth0.weight).to(device))
+        return self._packed
 
     def forward(self, x):
         from . import ops
@@ -171,6 +184,11 @@ class FusedTopDownFPN(nn.Module):
         c1 = f.conv1(c0)
         c2 = f.conv2(c1)
         quarter = f.toplayer(c2)
+        if self.fused_smooth and torch.backends.cudnn.allow_tf32:
+            w1, w0 = self._smooth_weights(x.device)
+            half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
+            _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)
+            return quarter, feat1, feat0
         half = ops.fpn_topdown(quarter, c1, f.lat1.weight, f.lat1.bias)
         full = ops.fpn_topdown(half, c0, f.lat0.weight, f.lat0.bias)
         return quarter, f.smooth1(half), f.smooth0(full)

@@ -222,3 +222,23 @@ def pack_convT3d_k3s2(weight):
                 for e in range(2):
                     out[:, kt, nt, :, r, e] = w[kt * 16 + 2 * t + 8 * r + e, nt * 8 + g].T
     return out.reshape(-1).view(torch.int32).to(weight.device)
+
+
+def pack_conv2d_k3_c32(weight):
+    """Conv2d weight (Cout in {8,16}, 32, 3, 3) -> int32 tensor in the order bmv_fpn_topdown_smooth reads:
+    [dy][j = dx*2 + half][n-tile][lane = 4g+t] x {b0, b1}; K index kk of k-step j is input channel half*16 + kk."""
+    Cout, Cin = weight.shape[:2]
+    if Cin != 32 or Cout not in (8, 16) or tuple(weight.shape[2:]) != (3, 3):
+        raise ValueError(f"conv2d_k3_c32 is not instantiated for weight {tuple(weight.shape)}")
+    w = weight.detach().float().cpu().half()                  # (Cout, 32, dy, dx)
+    NT = Cout // 8
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((3, 6, NT, 32, 2, 2), dtype=torch.float16)
+    for j in range(6):
+        dx, half = j // 2, j % 2
+        for nt in range(NT):
+            for r in range(2):
+                for e in range(2):
+                    out[:, j, nt, :, r, e] = w[nt * 8 + g, half * 16 + 2 * t + 8 * r + e, :, dx].T
+    return out.reshape(-1).view(torch.int32).to(weight.device)

@@ -667,3 +667,31 @@ def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None):
     p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
     _lib.call("bmv_convT3d_k3s2", p, _stream())
     return out
+
+
+def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smooth_bias, cout, write_mid):
+    """mid = up2x(prev) + conv1x1(lateral_in) + lat_bias; out = conv3x3(mid) + smooth_bias in ONE launch
+    (reference lib/networks/enerf/feature_net.py:24-47; the 3x3 runs on tensor cores with fp16 operands).
+    Returns (mid or None, out); tensors channels_last, smooth_wfrag from mlp_pack.pack_conv2d_k3_c32."""
+    _f32(prev, "prev"); _f32(lateral_in, "lateral_in")
+    N, Cin, H, W = lateral_in.shape
+    if not (prev.is_contiguous(memory_format=torch.channels_last) and lateral_in.is_contiguous(memory_format=torch.channels_last)):
+        raise BmvError("fpn_topdown_smooth: inputs must be channels_last")
+    assert prev.shape == (N, 32, H // 2, W // 2), prev.shape
+    if smooth_wfrag.dtype != torch.int32 or smooth_wfrag.numel() != _lib.load().bmv_fpn_topdown_smooth_weight_words(cout):
+        raise BmvError(f"fpn_topdown_smooth: weight buffer does not match Cout={cout}")
+    w = _cf32(lat_weight.reshape(32, Cin), "lat_weight")
+    lb = _cf32(lat_bias, "lat_bias") if lat_bias is not None else None
+    sb = _cf32(smooth_bias, "smooth_bias") if smooth_bias is not None else None
+    out = torch.empty((N, cout, H, W), device=prev.device, memory_format=torch.channels_last)
+    mid = torch.empty((N, 32, H, W), device=prev.device, memory_format=torch.channels_last) if write_mid else None
+    p = _lib.FpnFusedParams()
+    p.prev, p.lateral_in, p.lat_weight = prev.data_ptr(), lateral_in.data_ptr(), w.data_ptr()
+    p.lat_bias = lb.data_ptr() if lb is not None else 0
+    p.wfrag = smooth_wfrag.data_ptr()
+    p.bias = sb.data_ptr() if sb is not None else 0
+    p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, Cin, cout
+    p.mid = mid.data_ptr() if mid is not None else 0
+    p.out = out.data_ptr()
+    _lib.call("bmv_fpn_topdown_smooth", p, _stream())
+    return mid, out

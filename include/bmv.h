@@ -361,6 +361,26 @@ typedef struct bmv_convT3d_params {
 BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_convT3d_k3s2_weight_words(int Cin, int Cout);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused top-down step + 3x3 smoothing convolution of the feature pyramid:
+ *     mid = up2x(prev) + conv1x1(lateral_in) + lat_bias   (32 channels; as bmv_fpn_topdown, exact fp32)
+ *     out = conv3x3(mid, padding 1) + bias                 (Cout = 8 or 16)
+ * (`_upsample_add` + `smooth0/smooth1`, reference lib/networks/enerf/feature_net.py:24-47.)
+ * The 3x3 convolution uses fp16 operands / fp32 accumulation (TF32-class; same gating as bmv_conv3d_k3).
+ * All tensors channels-last fp32; mid (N,H,W,32) is written only when non-NULL.
+ * wfrag: bmv_fpn_topdown_smooth_weight_words(Cout) words, order [dy][dx*2+half][n-tile][lane][2]
+ * (mlp_pack.pack_conv2d_k3_c32).
+ */
+typedef struct bmv_fpn_fused_params {
+  const float* prev; const float* lateral_in; const float* lat_weight; const float* lat_bias;
+  const uint32_t* wfrag; const float* bias;
+  int32_t N, H, W, Cin, Cout;
+  float* mid;                   /* (N,H,W,32) or NULL */
+  float* out;                   /* (N,H,W,Cout) */
+} bmv_fpn_fused_params;
+BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream);
+BMV_API int bmv_fpn_topdown_smooth_weight_words(int Cout);
+
 #ifdef __cplusplus
 }
 #endif

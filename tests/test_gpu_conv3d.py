@@ -136,3 +136,53 @@ def test_cost_reg_plan_tensor_core_convs_match_cudnn_tf32_class(minimal):
         torch.backends.cudnn.allow_tf32 = prev
     for a, b in ((f_tc, f_ref), (d_tc, d_ref)):
         assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------ fused FPN step
+@pytest.mark.parametrize("cin,cout,hw", [(8, 8, (64, 96)), (16, 16, (34, 50)), (16, 8, (16, 130)), (8, 16, (10, 18))])
+@pytest.mark.parametrize("write_mid", [True, False])
+def test_fpn_topdown_smooth_vs_torch(cin, cout, hw, write_mid):
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3_c32
+    H, W = hw
+    torch.manual_seed(cin + cout)
+    prev = torch.randn(2, 32, H // 2, W // 2, device="cuda").contiguous(memory_format=torch.channels_last)
+    lat_in = torch.randn(2, cin, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    lat = torch.nn.Conv2d(cin, 32, 1).cuda()
+    smooth = torch.nn.Conv2d(32, cout, 3, padding=1).cuda()
+    prev_flag = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            mid_ref = torch.nn.functional.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=True) + lat(lat_in)
+            out_ref = smooth(mid_ref)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev_flag
+    mid, out = ops.fpn_topdown_smooth(prev, lat_in, lat.weight, lat.bias, pack_conv2d_k3_c32(smooth.weight), smooth.bias,
+                                      cout, write_mid)
+    assert (mid is not None) == write_mid
+    if write_mid:                                   # the materialised intermediate is exact fp32 arithmetic
+        assert torch.allclose(mid, mid_ref, rtol=1e-5, atol=1e-5 * mid_ref.abs().max().item())
+    assert out.shape == out_ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert (out - out_ref).abs().max().item() <= 2e-3 * out_ref.abs().max().item()
+
+
+def test_fpn_plan_fused_smooth_matches_unfused():
+    from boostmvsnerfs_b200.inference_plan import PlanCache
+    from boostmvsnerfs_b200.modules import FeatureNet
+    torch.manual_seed(1)
+    net = FeatureNet().cuda().eval()
+    x = torch.randn(3, 3, 64, 96, device="cuda").contiguous(memory_format=torch.channels_last)
+    plan = PlanCache().get("feature_net", net, torch.channels_last)
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        with torch.no_grad():
+            torch.backends.cudnn.allow_tf32 = False
+            ref = plan(x)
+            torch.backends.cudnn.allow_tf32 = True
+            got = plan(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
