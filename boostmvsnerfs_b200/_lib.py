@@ -143,6 +143,12 @@ class FpnFusedParams(C.Structure):
                 ("mid", C.c_void_p), ("out", C.c_void_p)]
 
 
+class FpnStemParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_n_stride", i64), ("x_c_stride", i64), ("x_y_stride", i64), ("x_x_stride", i64),
+                ("w0", C.c_void_p), ("b0", C.c_void_p), ("wfrag1", C.c_void_p), ("b1", C.c_void_p),
+                ("N", i32), ("H", i32), ("W", i32), ("out", C.c_void_p)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
@@ -161,6 +167,7 @@ ENTRY_POINTS = {
     "bmv_conv3d_k3": Conv3dParams,
     "bmv_convT3d_k3s2": ConvT3dParams,
     "bmv_fpn_topdown_smooth": FpnFusedParams,
+    "bmv_fpn_stem": FpnStemParams,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",

@@ -172,20 +172,26 @@ class FusedTopDownFPN(nn.Module):
 
     def _smooth_weights(self, device):
         if self._packed is None or self._packed[0].device != device:
-            from .mlp_pack import pack_conv2d_k3_c32
+            from .mlp_pack import pack_conv2d_k3_c32, pack_conv2d_k3_c8
             self._packed = (pack_conv2d_k3_c32(self.fpn.smooth1.weight).to(device),
-                            pack_conv2d_k3_c32(self.fpn.smooth0.weight).to(device))
+                            pack_conv2d_k3_c32(self.fpn.smooth0.weight).to(device),
+                            pack_conv2d_k3_c8(self.fpn.conv0[1].conv.weight).to(device))
         return self._packed
 
     def forward(self, x):
         from . import ops
         f = self.fpn
-        c0 = f.conv0(x)
+        fused = self.fused_smooth and torch.backends.cudnn.allow_tf32
+        if fused and isinstance(f.conv0[0].bn, nn.Identity):
+            a, b = f.conv0[0].conv, f.conv0[1].conv
+            c0 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias)
+        else:
+            c0 = f.conv0(x)
         c1 = f.conv1(c0)
         c2 = f.conv2(c1)
         quarter = f.toplayer(c2)
-        if self.fused_smooth and torch.backends.cudnn.allow_tf32:
-            w1, w0 = self._smooth_weights(x.device)
+        if fused:
+            w1, w0, _ = self._smooth_weights(x.device)
             half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
             _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)
             return quarter, feat1, feat0

@@ -242,3 +242,23 @@ def pack_conv2d_k3_c32(weight):
                 for e in range(2):
                     out[:, j, nt, :, r, e] = w[nt * 8 + g, half * 16 + 2 * t + 8 * r + e, :, dx].T
     return out.reshape(-1).view(torch.int32).to(weight.device)
+
+
+def pack_conv2d_k3_c8(weight):
+    """Conv2d weight (8, 8, 3, 3) -> int32 tensor (384,) in the order bmv_fpn_stem reads: [dy][k-step j][lane] x {b0, b1};
+    k-step 0 holds taps dx = 0 (K 0..7) and dx = 1 (K 8..15), k-step 1 holds dx = 2 and zeros."""
+    if tuple(weight.shape) != (8, 8, 3, 3):
+        raise ValueError(f"conv2d_k3_c8 needs an (8,8,3,3) weight, got {tuple(weight.shape)}")
+    w = weight.detach().float().cpu()
+    B = torch.zeros(3, 2, 16, 8)                              # [dy][j][k][n]
+    for dx in range(3):
+        j, k0 = dx // 2, (dx % 2) * 8
+        B[:, j, k0:k0 + 8, :] = w[:, :, :, dx].permute(2, 1, 0)
+    B = B.half()
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((3, 2, 32, 2, 2), dtype=torch.float16)
+    for r in range(2):
+        for e in range(2):
+            out[:, :, :, r, e] = B[:, :, 2 * t + 8 * r + e, g]
+    return out.reshape(-1).view(torch.int32).to(weight.device)

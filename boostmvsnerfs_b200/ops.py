@@ -695,3 +695,25 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     p.out = out.data_ptr()
     _lib.call("bmv_fpn_topdown_smooth", p, _stream())
     return mid, out
+
+
+def fpn_stem(x, w0, b0, wfrag1, b1):
+    """relu(conv3x3_{8->8}(relu(conv3x3_{3->8}(x) + b0)) + b1) in one launch (reference
+    lib/networks/enerf/feature_net.py:7-9; BN already folded into w/b).  x (N,3,H,W) fp32, any strides;
+    returns (N,8,H,W) channels_last."""
+    _f32(x, "x")
+    N, C, H, W = x.shape
+    if C != 3:
+        raise BmvError("fpn_stem: x must have 3 channels")
+    if wfrag1.dtype != torch.int32 or wfrag1.numel() != 384:
+        raise BmvError("fpn_stem: wfrag1 must come from mlp_pack.pack_conv2d_k3_c8")
+    w0c, b0c, b1c = _cf32(w0.reshape(8, 27), "w0"), _cf32(b0, "b0"), _cf32(b1, "b1")
+    out = torch.empty((N, 8, H, W), device=x.device, memory_format=torch.channels_last)
+    p = _lib.FpnStemParams()
+    p.x = x.data_ptr()
+    p.x_n_stride, p.x_c_stride, p.x_y_stride, p.x_x_stride = x.stride()
+    p.w0, p.b0, p.wfrag1, p.b1 = w0c.data_ptr(), b0c.data_ptr(), wfrag1.data_ptr(), b1c.data_ptr()
+    p.N, p.H, p.W = N, H, W
+    p.out = out.data_ptr()
+    _lib.call("bmv_fpn_stem", p, _stream())
+    return out

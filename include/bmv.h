@@ -381,6 +381,22 @@ typedef struct bmv_fpn_fused_params {
 BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream);
 BMV_API int bmv_fpn_topdown_smooth_weight_words(int Cout);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused stem of the feature pyramid: ConvBnReLU(3,8,3) -> ConvBnReLU(8,8,3) at full resolution
+ * (reference lib/networks/enerf/feature_net.py:7-9,29; BN folded).  x: (N,3,H,W) fp32 via strides (any
+ * layout); w0 (8,3,3,3) fp32 row-major + b0 (8); wfrag1: 384 words = the 8->8 weights in B-fragment
+ * order [dy][k-step][lane][2] (mlp_pack.pack_conv2d_k3_c8) + b1 (8); out (N,H,W,8) channels-last fp32.
+ * First layer fp32 on CUDA cores, second on tensor cores with fp16 operands (TF32-class gating).
+ */
+typedef struct bmv_fpn_stem_params {
+  const float* x; int64_t x_n_stride, x_c_stride, x_y_stride, x_x_stride;
+  const float* w0; const float* b0;
+  const uint32_t* wfrag1; const float* b1;
+  int32_t N, H, W;
+  float* out;
+} bmv_fpn_stem_params;
+BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

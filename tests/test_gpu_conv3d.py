@@ -186,3 +186,27 @@ def test_fpn_plan_fused_smooth_matches_unfused():
     for a, b in zip(got, ref):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("hw", [(64, 96), (9, 70), (33, 17)])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_fpn_stem_vs_torch(hw, layout):
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3_c8
+    H, W = hw
+    torch.manual_seed(H)
+    x = torch.randn(2, 3, H, W, device="cuda")
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    c0 = torch.nn.Conv2d(3, 8, 3, padding=1).cuda()
+    c1 = torch.nn.Conv2d(8, 8, 3, padding=1).cuda()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = torch.relu(c1(torch.relu(c0(x))))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    out = ops.fpn_stem(x, c0.weight, c0.bias, pack_conv2d_k3_c8(c1.weight), c1.bias)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()

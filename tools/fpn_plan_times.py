@@ -36,6 +36,9 @@ with torch.no_grad():
     steps.append(("smooth0 32->8 k3 full", lambda: f.smooth0(full)))
     from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3_c32
     w1, w0 = pack_conv2d_k3_c32(f.smooth1.weight), pack_conv2d_k3_c32(f.smooth0.weight)
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3_c8
+    wst = pack_conv2d_k3_c8(f.conv0[1].conv.weight)
+    steps.append(("fused stem conv0.0+conv0.1", lambda: ops.fpn_stem(x, f.conv0[0].conv.weight, f.conv0[0].conv.bias, wst, f.conv0[1].conv.bias)))
     steps.append(("fused topdown+smooth1 half", lambda: ops.fpn_topdown_smooth(q, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)))
     steps.append(("fused topdown+smooth0 full", lambda: ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)))
     steps.append(("TOTAL plan forward", lambda: plan(x)))
