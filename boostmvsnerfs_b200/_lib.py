@@ -64,7 +64,8 @@ class RaygenFetchParams(C.Structure):
                 ("tar_center", C.c_void_p), ("render_scale", f32),
                 ("rays12", C.c_void_p), ("z_vals", C.c_void_p), ("xyz", C.c_void_p), ("uvd", C.c_void_p),
                 ("vox_feat", C.c_void_p), ("img_feat", C.c_void_p),
-                ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
+                ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p),
+                ("rgb_c_stride", i64), ("rgb_y_stride", i64), ("rgb_x_stride", i64)]
 
 
 class VisibilityParams(C.Structure):

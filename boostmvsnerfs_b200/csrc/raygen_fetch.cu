@@ -85,9 +85,10 @@ __device__ __forceinline__ void fetch_sample(const bmv_raygen_fetch_params& p, c
       for (int c = 0; c < Cf; ++c) o[c] = tap2_fetch(f + (int64_t)c * p.imf_c_stride, tp);
     }
     {
-      const Tap2 tp = border_taps(gx, gy, p.Hf, p.Wf, p.Wf, 1);
+      const RgbStrides rs3 = rgb_strides(p);
+      const Tap2 tp = border_taps(gx, gy, p.Hf, p.Wf, rs3.y, rs3.x);
       const float* f = p.rgb + (int64_t)view * p.rgb_view_stride;
-      const int64_t plane = (int64_t)p.Hf * p.Wf;
+      const int64_t plane = rs3.c;
       // colour = bilinear(img*scale+shift); img*0.5+0.5 is exact as an FMA (0.5 is a power of two)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {

@@ -84,6 +84,7 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v;
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_render_rays_params rp) {
   constexpr int V = 3, CF = 8;
   const bmv_raygen_fetch_params& p = rp.g;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
         const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
         const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
         const SamplePoint q = sample_point(p, r, s);
-        const int cnt = gather_sample_regs<CF, V>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
+        const int cnt = gather_sample_regs<CF, V, VEC>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
         if (p.z_vals) p.z_vals[si] = q.z;
         if (p.vis_mask) p.vis_mask[si] = div_rn((float)cnt, (float)V);
         if (p.vis_count) p.vis_count[si] = cnt;
@@ -424,7 +425,9 @@ extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv
   const size_t smem = (size_t)(MMA_PACK_WORDS + kMmaWarps * 32 * kStageStride) * 4;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(render_rays_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(render_rays_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(render_rays_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("bmv_render_rays_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -433,6 +436,7 @@ extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv
   }
   const int64_t rounds = ceil_div64(p->n_rays * p->S, kMmaWarps * 32);
   const unsigned blocks = (unsigned)(rounds < kNumSMs ? rounds : kNumSMs);   // persistent: one CTA per SM
-  render_rays_mma_kernel<<<blocks, kMmaWarps * 32, smem, (cudaStream_t)stream>>>(*rp);
+  if (gather_vec_ok(*p)) render_rays_mma_kernel<true><<<blocks, kMmaWarps * 32, smem, (cudaStream_t)stream>>>(*rp);
+  else render_rays_mma_kernel<false><<<blocks, kMmaWarps * 32, smem, (cudaStream_t)stream>>>(*rp);
   return check_launch("bmv_render_rays_mma");
 }

@@ -281,6 +281,11 @@ class EnerfNetwork(nn.Module):
                 align_corners=True, mode='bilinear')
         if rs == 1.:
             rgb, affine = inps, (0.5, 0.5)          # unpreprocess folded into the fetch
+            if self.channels_last and inps.is_cuda:
+                # (N,H,W,4) channels-last copy: one 16-byte load per bilinear tap in the fused render kernel
+                rgb4 = inps.new_zeros((inps.shape[0], inps.shape[2], inps.shape[3], 4))
+                rgb4[..., :3] = inps.permute(0, 2, 3, 1)
+                rgb = rgb4.permute(0, 3, 1, 2)[:, :3]
         else:          # level-0 rendering of the pre-train configs: resized colours (enerf/utils.py:669-676)
             rgb = torch.nn.functional.interpolate(inps * 0.5 + 0.5, size=(H, W), align_corners=True, mode='bilinear')
             affine = (1.0, 0.0)

@@ -282,12 +282,13 @@ def _fill_fetch_inputs(p, volume, im_feat, rgb, cams, views, render_scale, rgb_a
             p.hv, p.wv = volume.shape[2], volume.shape[3]
     if im_feat is not None:
         _f32(im_feat, "im_feat")
-        rgb = _cf32(rgb, "rgb")
+        _f32(rgb, "rgb")
         p.im_feat = im_feat.data_ptr()
         p.Cf, p.Hf, p.Wf = im_feat.shape[1], im_feat.shape[2], im_feat.shape[3]
         p.imf_view_stride, p.imf_c_stride, p.imf_y_stride, p.imf_x_stride = im_feat.stride()
         assert rgb.shape[1:] == (3, p.Hf, p.Wf), (rgb.shape, p.Hf, p.Wf)
         p.rgb, p.rgb_view_stride = rgb.data_ptr(), rgb.stride(0)
+        p.rgb_c_stride, p.rgb_y_stride, p.rgb_x_stride = rgb.stride(1), rgb.stride(2), rgb.stride(3)
         p.rgb_scale, p.rgb_shift = rgb_affine
         p._keep = (rgb,)
     p.src_exts, p.src_ixts = cams.exts.data_ptr(), cams.ixts.data_ptr()

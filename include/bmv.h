@@ -160,7 +160,7 @@ typedef struct bmv_raygen_fetch_params {
   int32_t V; int32_t view[BMV_MAX_VIEWS];
   const float* im_feat; int32_t Cf; int32_t Hf, Wf;    /* (N,Cf,Hf,Wf)-like with strides below */
   int64_t imf_view_stride, imf_c_stride, imf_y_stride, imf_x_stride;
-  const float* rgb;             /* (N,3,Hf,Wf) planar */
+  const float* rgb;             /* (N,3,Hf,Wf); strides: rgb_view_stride + rgb_{c,y,x}_stride at the end of the struct */
   int64_t rgb_view_stride;
   float rgb_scale, rgb_shift;   /* colour = rgb*scale+shift (0.5,0.5 folds unpreprocess; 1,0 if pre-resized) */
   /* cameras, DEVICE memory */
@@ -178,6 +178,9 @@ typedef struct bmv_raygen_fetch_params {
   float* img_feat;              /* (n_rays*S,V,Cf+3+4) */
   float* vis_mask;              /* (n_rays,S) fp32 count/V */
   int32_t* vis_count;           /* (n_rays,S) integer count */
+  /* rgb element strides (floats).  All zero = planar contiguous (c: Hf*Wf, y: Wf, x: 1).  A channels-last
+   * (N,H,W,4) image (c: 1, x: 4) lets the fused render kernels fetch a tap with one 16-byte load. */
+  int64_t rgb_c_stride, rgb_y_stride, rgb_x_stride;
 } bmv_raygen_fetch_params;
 BMV_API int bmv_raygen_sample_fetch(const bmv_raygen_fetch_params* p, bmv_stream_t stream);
 

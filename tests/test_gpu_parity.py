@@ -354,6 +354,21 @@ def test_tensor_core_render_matches_fp32_paths(ops, g, seed):
     exact(part["raw"], mma["raw"][1003:1780], "ray sub-range (ragged tiles)")
     one = ops.render_rays(*args, mlp_pack.pack_nerf_weights_mma(net), engine="mma", ray_begin=5, n_rays=1)
     exact(one["raw"], mma["raw"][5:6], "single ray")
+    # channels-last volume / features and a 4-float-per-pixel image select the 16-byte-load gather: same bits
+    vol, imf, img = args[8], args[9], args[10]
+    vol_cl = vol.permute(1, 2, 3, 0).contiguous().permute(3, 0, 1, 2)
+    imf_cl = imf.contiguous(memory_format=torch.channels_last)
+    img4 = img.new_zeros((img.shape[0], img.shape[2], img.shape[3], 4))
+    img4[..., :3] = img.permute(0, 2, 3, 1)
+    args_cl = args[:8] + (vol_cl, imf_cl, img4.permute(0, 3, 1, 2)[:, :3]) + args[11:]
+    vec = ops.render_rays(*args_cl, mlp_pack.pack_nerf_weights_mma(net), engine="mma", want_count=True)
+    exact(vec["raw"], mma["raw"], "vectorised gather vs scalar gather")
+    exact(vec["vis_mask"], mma["vis_mask"], "visibility (vectorised gather)")
+    # strided (non-planar) rgb through the fp32 kernel and the stand-alone fetch
+    fma_cl = ops.render_rays(*args_cl, mlp_pack.pack_nerf_weights(net))
+    exact(fma_cl["raw"], fma["raw"], "fp32-FMA kernel with channels-last inputs")
+    o_cl = ops.raygen_sample_fetch(*args_cl, want=("img_feat",))
+    exact(o_cl["img_feat"], o["img_feat"], "stand-alone fetch with channels-last rgb")
 
 
 def test_fused_render_matches_unfused_path(ops, g):
