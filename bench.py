@@ -457,8 +457,9 @@ def main_ours(args):
                              "share_of_step": per_launch_ms * launches_per_stage[name] / ms}
     for name, k in kernels.items():
         if name.startswith("render_fused"):
-            # the fused gather+MLP kernel is FP32-FMA bound, not HBM bound: 14.6 kFMA per sample
-            # (csrc/nerf_mlp.cuh) against 148 SMs x 128 FMA/clk x clocks.max.sm
+            # the fused gather+MLP kernel is compute bound, not HBM bound: 14.6 kFMA per sample (csrc/nerf_mlp.cuh).
+            # Reported as fp32-equivalent FLOP/s against the fp32 FMA peak (148 SMs x 128 FMA/clk x clocks.max.sm);
+            # the tensor-core engine spends 3 fp16 MMAs per fp32 product (csrc/render_mma.cu).
             lvl = int(name[-1])
             samples = int(wl["H"] * rc.render_scale[lvl]) * int(wl["W"] * rc.render_scale[lvl]) * rc.num_samples[lvl]
             flops = samples * 2 * 14600.0
@@ -494,7 +495,11 @@ def main_ours(args):
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels, "frame_sharded": sharded,
         "stage_ms_per_step": step_ms_stage, "hand_written_ms_per_step": hand_ms,
         "host_enqueue_ms_per_step": t_host, "instrumented_ms_per_step": ms_instrumented,
-        "kept_library_ms_per_step": {k: v for k, v in step_ms_stage.items() if k.startswith(("cost_reg", "nerf", "feature"))},
+        # stages that mix libbmv tensor-core convolution kernels with kept cuDNN layers
+        "mixed_library_stage_ms_per_step": {k: v for k, v in step_ms_stage.items() if k.startswith(("cost_reg", "nerf", "feature"))},
+        # device time of every libbmv entry point per frame (CUDA events around each launch, instrumented pass)
+        "libbmv_kernel_ms_per_step": {e: sum(ts) / args.steps for e, ts in sorted(ksum.items())},
+        "libbmv_launches_per_step": {e: len(ts) / args.steps for e, ts in sorted(ksum.items())},
     }
     if world == 1 and args.torch_gpu_baseline:
         # the reference's own eager-PyTorch op sequence on the same GPU, batch and weights: the
