@@ -34,25 +34,25 @@ namespace bmv {
 constexpr int kConvThreads = 256;
 constexpr int kConvWarps = kConvThreads / 32;
 
-template <int CIN> struct ConvCfg;
+template <int CIN, int NTILES> struct ConvCfg;
 // Shared-memory voxel v (index in its staged row) holds its 16-byte chunk c at chunk c ^ swz(v): with
 // 32- and 64-byte voxels this makes the 8 rows of every ldmatrix 8x8 block hit 8 distinct 16-byte bank groups.
-template <> struct ConvCfg<16> {
-  static constexpr int VS = 32, KS = 3, NT = 1, TH = 4, WD = 2, EXTRA = 0;
-  static constexpr bool BREG = true;
+template <int NTILES> struct ConvCfg<16, NTILES> {
+  static constexpr int VS = 32, KS = 3, NT = NTILES, TH = 4, WD = NTILES == 1 ? 2 : 1, EXTRA = 0;
+  static constexpr bool BREG = NTILES == 1;
   __device__ static __forceinline__ int swz(int v) { return (v >> 2) & 1; }
   // k-step j: voxel offset and first 16-byte chunk of the lane's row segment (hi = lane / 16)
   __device__ static __forceinline__ int step_voxel(int j, int hi) { return j; }
   __device__ static __forceinline__ int step_chunk(int j, int hi) { return hi; }
 };
-template <> struct ConvCfg<32> {
+template <> struct ConvCfg<32, 1> {
   static constexpr int VS = 64, KS = 6, NT = 1, TH = 2, WD = 2, EXTRA = 0;
   static constexpr bool BREG = false;
   __device__ static __forceinline__ int swz(int v) { return (v >> 1) & 3; }
   __device__ static __forceinline__ int step_voxel(int j, int hi) { return j >> 1; }
   __device__ static __forceinline__ int step_chunk(int j, int hi) { return (j & 1) * 2 + hi; }
 };
-template <> struct ConvCfg<8> {
+template <> struct ConvCfg<8, 2> {
   static constexpr int VS = 16, KS = 2, NT = 2, TH = 4, WD = 1, EXTRA = 1;   // +1 voxel: the unpaired tap reads x+3
   static constexpr bool BREG = false;
   __device__ static __forceinline__ int swz(int v) { return 0; }
@@ -60,9 +60,9 @@ template <> struct ConvCfg<8> {
   __device__ static __forceinline__ int step_chunk(int j, int hi) { return 0; }
 };
 
-template <int CIN>
+template <int CIN, int NTILES>
 struct ConvTile {
-  using Cfg = ConvCfg<CIN>;
+  using Cfg = ConvCfg<CIN, NTILES>;
   static constexpr int TD = 8, TW = 32, TH = Cfg::TH;
   static constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
   static constexpr int ROWV = HW + Cfg::EXTRA;                          // staged voxels per row
@@ -72,10 +72,10 @@ struct ConvTile {
   static constexpr int JOBS = (TD / Cfg::WD) * (TW / 16);
 };
 
-template <int CIN>
+template <int CIN, int NTILES>
 __global__ void __launch_bounds__(kConvThreads, CIN == 8 ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
-  using T = ConvTile<CIN>;
-  using Cfg = ConvCfg<CIN>;
+  using T = ConvTile<CIN, NTILES>;
+  using Cfg = ConvCfg<CIN, NTILES>;
   constexpr int NT = Cfg::NT, KS = Cfg::KS, WD = Cfg::WD, TH = T::TH;
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* tile = smem;
@@ -253,15 +253,164 @@ __global__ void __launch_bounds__(kConvThreads, CIN == 8 ? 3 : 2) conv3d_k3_mma_
   }
 }
 
-template <int CIN>
-static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
-  using T = ConvTile<CIN>;
+// ------------------------------------------------------------------ stride 2 (8 -> 16 channels: conv1 of the U-Nets)
+// out[o] = sum_k x[2o - 1 + k] w[k].  Same implicit GEMM; the A rows of an M-tile are every second staged
+// voxel (ldmatrix takes one address per row), taps kx = 0,1 are the contiguous voxel pair (2o, 2o+1) of the
+// staged row, kx = 2 is paired with zero weights.  CTA: 4 x 4 x 32 outputs from a 9 x 9 x 66 input tile.
+struct ConvS2 {
+  static constexpr int TD = 4, TH = 4, TW = 32, NT = 2, KS = 2;
+  static constexpr int HD = 2 * TD + 1, HH = 2 * TH + 1, ROWV = 2 * TW + 2;
+  static constexpr int ROWB = ROWV * 16;
+  static constexpr int TILE_BYTES = HD * HH * ROWB;
+  static constexpr int W_WORDS = 9 * KS * NT * 32 * 2;
+};
+
+__global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3s2_c8_mma_kernel(bmv_conv3d_params p, int Do, int Ho, int Wo) {
+  using T = ConvS2;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* tile = smem;
+  const uint2* wfrag = reinterpret_cast<const uint2*>(smem + T::TILE_BYTES);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
+    uint4* dst = reinterpret_cast<uint4*>(smem + T::TILE_BYTES);
+    for (int i = threadIdx.x; i < T::W_WORDS / 4; i += kConvThreads) dst[i] = __ldg(src + i);
+  }
+  const int tiles_w = (Wo + T::TW - 1) / T::TW, tiles_h = (Ho + T::TH - 1) / T::TH, tiles_d = (Do + T::TD - 1) / T::TD;
+  int b = blockIdx.x;
+  const int tw = b % tiles_w; b /= tiles_w;
+  const int th = b % tiles_h; b /= tiles_h;
+  const int td = b % tiles_d; b /= tiles_d;
+  const int n = b;
+  const int x0 = tw * T::TW, y0 = th * T::TH, d0 = td * T::TD;          // output coordinates
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const float* xin = p.x + (int64_t)n * p.x_n_stride;
+    constexpr int PER_ROW = T::ROWV * 2, ROWS = T::HD * T::HH, P = (PER_ROW + 31) / 32, VPP = 16;
+    const int c4 = lane & 1, hx0 = lane >> 1;
+    const int64_t lane_off = (int64_t)(2 * x0 - 1 + hx0) * p.x_x_stride + c4 * 4, pass_off = (int64_t)VPP * p.x_x_stride;
+    for (int row = warp; row < ROWS; row += 2 * kConvWarps) {
+      float4 val[2][P];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = row + rr * kConvWarps;
+        const int hd = r / T::HH, hy = r - hd * T::HH;
+        const int gy = 2 * y0 - 1 + hy, gd = 2 * d0 - 1 + hd;
+        const bool row_ok = r < ROWS && gy >= 0 && gy < p.H && gd >= 0 && gd < p.D;
+        const float* src = xin + (int64_t)gd * p.x_d_stride + (int64_t)gy * p.x_y_stride + lane_off;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int hx = hx0 + VPP * k, gx = 2 * x0 - 1 + hx;
+          val[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && hx < T::ROWV && gx >= 0 && gx < p.W) val[rr][k] = __ldg(reinterpret_cast<const float4*>(src + k * pass_off));
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = row + rr * kConvWarps;
+        if (r < ROWS) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            const int hx = hx0 + VPP * k;
+            if (hx < T::ROWV) *reinterpret_cast<uint2*>(tile + r * T::ROWB + hx * 16 + c4 * 8) = pack_half4(val[rr][k]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhi = lane >> 4;
+  float bias0[T::NT], bias1[T::NT];
+#pragma unroll
+  for (int nt = 0; nt < T::NT; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    bias0[nt] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+    bias1[nt] = (p.bias && c + 1 < p.Cout) ? __ldg(p.bias + c + 1) : 0.f;
+  }
+  float* out = p.out + (int64_t)n * p.o_n_stride;
+  // one job per warp: output plane od, x half mx, all TH rows
+  {
+    const int mx = warp & 1, od = warp >> 1;
+    if (d0 + od < Do && x0 + mx * 16 < Wo) {
+      float acc[T::TH][T::NT][4];
+#pragma unroll
+      for (int oy = 0; oy < T::TH; ++oy)
+#pragma unroll
+        for (int nt = 0; nt < T::NT; ++nt) {
+          acc[oy][nt][0] = bias0[nt]; acc[oy][nt][1] = bias1[nt]; acc[oy][nt][2] = bias0[nt]; acc[oy][nt][3] = bias1[nt];
+        }
+      const uint32_t lane_base = tile_s + (2 * (mx * 16 + lrow) + lhi) * 16;
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+        for (int py = 0; py < 2 * T::TH + 1; ++py) {
+#pragma unroll
+          for (int j = 0; j < T::KS; ++j) {
+            uint32_t a[4];
+            ldmatrix_x4(a, lane_base + ((2 * od + dz) * T::HH + py) * T::ROWB + j * 32);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              if ((py - dy) < 0 || ((py - dy) & 1) || (py - dy) / 2 >= T::TH) continue;
+              const int oy = (py - dy) / 2;
+#pragma unroll
+              for (int nt = 0; nt < T::NT; ++nt) {
+                const uint2 bw = wfrag[((((dz * 3 + dy) * T::KS + j) * T::NT + nt) << 5) + lane];
+                hmma16816(acc[oy][nt], a, bw.x, bw.y);
+              }
+            }
+          }
+        }
+      }
+      const int gx0 = x0 + mx * 16 + g, gx1 = gx0 + 8;
+#pragma unroll
+      for (int oy = 0; oy < T::TH; ++oy) {
+        const int gy = y0 + oy;
+        if (gy >= Ho) continue;
+        float* orow = out + (int64_t)(d0 + od) * p.o_d_stride + (int64_t)gy * p.o_y_stride;
+#pragma unroll
+        for (int nt = 0; nt < T::NT; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          if (c + 1 >= p.Cout + 1 || c >= p.Cout) continue;
+          float v0 = acc[oy][nt][0], v1 = acc[oy][nt][1], v2 = acc[oy][nt][2], v3 = acc[oy][nt][3];
+          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+          if (gx0 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
+          if (gx1 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
+        }
+      }
+    }
+  }
+}
+
+static int launch_conv_s2(const bmv_conv3d_params& p, cudaStream_t st) {
+  using T = ConvS2;
   const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) {
+      set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+      return BMV_ERR_CUDA_LAUNCH;
+    }
+    configured = true;
+  }
+  const int Do = (p.D - 1) / 2 + 1, Ho = (p.H - 1) / 2 + 1, Wo = (p.W - 1) / 2 + 1;
+  const int64_t blocks = (int64_t)p.N * ((Do + T::TD - 1) / T::TD) * ((Ho + T::TH - 1) / T::TH) * ((Wo + T::TW - 1) / T::TW);
+  conv3d_k3s2_c8_mma_kernel<<<(unsigned)blocks, kConvThreads, smem, st>>>(p, Do, Ho, Wo);
+  return check_launch("bmv_conv3d_k3");
+}
+
+template <int CIN, int NTILES>
+static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
+  using T = ConvTile<CIN, NTILES>;
+  const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -269,7 +418,7 @@ static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
     configured = true;
   }
   const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
-  conv3d_k3_mma_kernel<CIN><<<(unsigned)blocks, kConvThreads, smem, st>>>(p);
+  conv3d_k3_mma_kernel<CIN, NTILES><<<(unsigned)blocks, kConvThreads, smem, st>>>(p);
   return check_launch("bmv_conv3d_k3");
 }
 
@@ -284,17 +433,27 @@ extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t st
               BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: input must be channels-last with 16-byte aligned voxels");
   BMV_REQUIRE(!p->out2 || (p->split >= 1 && p->split < p->Cout), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad split");
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->Cin == 16 && p->Cout <= 8) return launch_conv<16>(*p, st);
-  if (p->Cin == 32 && p->Cout <= 8) return launch_conv<32>(*p, st);
-  if (p->Cin == 8 && p->Cout <= 16) return launch_conv<8>(*p, st);
-  set_error("bmv_conv3d_k3: (Cin=%d, Cout=%d) not instantiated (16->8, 32->8, 8->16)", p->Cin, p->Cout);
+  BMV_REQUIRE(p->stride == 0 || p->stride == 1 || p->stride == 2, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride must be 1 or 2");
+  if (p->stride == 2) {
+    BMV_REQUIRE(p->Cin == 8 && p->Cout % 2 == 0 && p->Cout <= 16 && !p->out2, BMV_ERR_UNSUPPORTED_SHAPE,
+                "bmv_conv3d_k3: stride 2 is instantiated for Cin=8, even Cout<=16, single output (got Cin=%d, Cout=%d)", p->Cin, p->Cout);
+    BMV_REQUIRE(p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 && p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 &&
+                    ((uintptr_t)p->out & 7) == 0, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride-2 output must be 8-byte aligned");
+    return launch_conv_s2(*p, st);
+  }
+  if (p->Cin == 16 && p->Cout <= 8) return launch_conv<16, 1>(*p, st);
+  if (p->Cin == 16 && p->Cout <= 16) return launch_conv<16, 2>(*p, st);
+  if (p->Cin == 32 && p->Cout <= 8) return launch_conv<32, 1>(*p, st);
+  if (p->Cin == 8 && p->Cout <= 16) return launch_conv<8, 2>(*p, st);
+  set_error("bmv_conv3d_k3: (Cin=%d, Cout=%d) not instantiated (16->16, 32->8, 8->16)", p->Cin, p->Cout);
   return BMV_ERR_UNSUPPORTED_SHAPE;
 }
 
 // words (uint32) of the fragment-ordered weight buffer for a (Cin, Cout) pair, -1 if not instantiated
 extern "C" BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout) {
-  if (Cin == 16 && Cout <= 8) return bmv::ConvTile<16>::W_WORDS;
-  if (Cin == 32 && Cout <= 8) return bmv::ConvTile<32>::W_WORDS;
-  if (Cin == 8 && Cout <= 16) return bmv::ConvTile<8>::W_WORDS;
+  if (Cin == 16 && Cout <= 8) return bmv::ConvTile<16, 1>::W_WORDS;
+  if (Cin == 16 && Cout <= 16) return bmv::ConvTile<16, 2>::W_WORDS;
+  if (Cin == 32 && Cout <= 8) return bmv::ConvTile<32, 1>::W_WORDS;
+  if (Cin == 8 && Cout <= 16) return bmv::ConvTile<8, 2>::W_WORDS;
   return -1;
 }

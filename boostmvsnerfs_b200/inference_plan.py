@@ -118,13 +118,19 @@ class MergedHeadsCostReg(nn.Module):
                 and isinstance(self.net.conv0.bn, nn.Identity))
 
     def _packed_weights(self, device):
-        if self._packed is None or self._packed[0].device != device:
+        if self._packed is None or self._packed['device'] != device:
             from .mlp_pack import pack_conv3d_k3, pack_convT3d_k3s2
-            c0, t9, t11 = self.net.conv0.conv, self.net.conv9[0], self.net.conv11[0]
-            self._packed = (pack_conv3d_k3(c0.weight).to(device), c0.bias.detach().float().contiguous().to(device),
-                            pack_conv3d_k3(self.heads.weight).to(device),
-                            pack_convT3d_k3s2(t9.weight).to(device), t9.bias.detach().float().contiguous().to(device),
-                            pack_convT3d_k3s2(t11.weight).to(device), t11.bias.detach().float().contiguous().to(device))
+            n = self.net
+            bias = lambda m: m.bias.detach().float().contiguous().to(device)
+            self._packed = {
+                'device': device,
+                'conv0': (pack_conv3d_k3(n.conv0.conv.weight).to(device), bias(n.conv0.conv)),
+                'conv1': (pack_conv3d_k3(n.conv1.conv.weight).to(device), bias(n.conv1.conv)),
+                'conv2': (pack_conv3d_k3(n.conv2.conv.weight).to(device), bias(n.conv2.conv)),
+                'conv9': (pack_convT3d_k3s2(n.conv9[0].weight).to(device), bias(n.conv9[0])),
+                'conv11': (pack_convT3d_k3s2(n.conv11[0].weight).to(device), bias(n.conv11[0])),
+                'heads': pack_conv3d_k3(self.heads.weight).to(device),
+            }
         return self._packed
 
     def forward(self, x):
@@ -132,25 +138,27 @@ class MergedHeadsCostReg(nn.Module):
         fast = self._use_tensor_core_convs(x)
         if fast:
             from . import ops
-            w0, b0, wh, w9, b9, w11, b11 = self._packed_weights(x.device)
-            s0 = ops.conv3d_k3(x, w0, b0, 8, relu=True)
+            pk = self._packed_weights(x.device)
+            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True)                       # ConvBnReLU3D(C, 8)
+            s1 = ops.conv3d_k3(s0, *pk['conv1'], 16, relu=True, stride=2)           # ConvBnReLU3D(8, 16, stride=2)
+            s1 = ops.conv3d_k3(s1, *pk['conv2'], 16, relu=True)                     # ConvBnReLU3D(16, 16)
         else:
             s0 = n.conv0(x)
-        s1 = n.conv2(n.conv1(s0))
+            s1 = n.conv2(n.conv1(s0))
         s2 = n.conv4(n.conv3(s1))
         y = s2
         if n.depth_levels == 3:
             y = s2 + n.conv7(n.conv6(n.conv5(s2)))
         if fast and y.stride(1) == 1 and s1.stride(1) == 1:
-            y = ops.convT3d_k3s2_add(y, w9, b9, 16, skip=s1)
-            y = ops.convT3d_k3s2_add(y, w11, b11, 8, skip=s0)
+            y = ops.convT3d_k3s2_add(y, *pk['conv9'], 16, skip=s1)
+            y = ops.convT3d_k3s2_add(y, *pk['conv11'], 8, skip=s0)
         else:
             y = s1 + n.conv9(y)
             y = s0 + n.conv11(y)
         if fast and y.stride(1) == 1:
             # feature volume and depth logits as two dense tensors (32-byte voxels for the trilinear fetch)
             logits = torch.empty((y.shape[0], 1) + tuple(y.shape[2:]), device=y.device)
-            feat = ops.conv3d_k3(y, wh, None, 9, relu=False, out2=logits, split=8)
+            feat = ops.conv3d_k3(y, pk['heads'], None, 9, relu=False, out2=logits, split=8)
             return feat, logits[:, 0]
         out = self.heads(y)
         return out[:, :8], out[:, 8]

@@ -156,7 +156,12 @@ def pack_nerf_weights_mma(nerf):
 
 
 # ------------------------------------------------------------------------------------------ conv3d (csrc/conv3d_mma.cu)
-CONV3D_K3_SHAPES = {16: 8, 32: 8, 8: 16}     # Cin -> largest Cout instantiated
+CONV3D_K3_SHAPES = {16: 16, 32: 8, 8: 16}    # Cin -> largest Cout instantiated
+
+
+def _conv3d_ntiles(cin, cout):
+    """n-tiles (of 8 output channels) of the kernel instantiation that serves (cin, cout)."""
+    return 2 if cin == 8 else (cout + 7) // 8
 
 
 def _conv3d_ksteps(cin):
@@ -179,7 +184,7 @@ def pack_conv3d_k3(weight):
     if Cin not in CONV3D_K3_SHAPES or Cout > CONV3D_K3_SHAPES[Cin] or tuple(weight.shape[2:]) != (3, 3, 3):
         raise ValueError(f"conv3d_k3 is not instantiated for weight {tuple(weight.shape)}")
     steps = _conv3d_ksteps(Cin)
-    NT = (CONV3D_K3_SHAPES[Cin] + 7) // 8
+    NT = _conv3d_ntiles(Cin, Cout)
     w = torch.zeros(NT * 8, Cin, 3, 3, 3)
     w[:Cout] = weight.detach().float().cpu()
     # B[dz][dy][j][k][n]

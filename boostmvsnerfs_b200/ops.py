@@ -604,7 +604,7 @@ def fpn_topdown(prev, lateral_in, weight, bias):
 
 
 # ------------------------------------------------------------------------------------------ tensor-core 3-D convolution
-def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0):
+def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1):
     """3x3x3 / stride 1 / pad 1 convolution (+bias, optional ReLU) of a channels_last_3d fp32 volume
     on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
     lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
@@ -615,7 +615,8 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0):
     if x.stride(1) != 1:
         raise BmvError("conv3d_k3: x must be channels_last_3d")
     if out is None:
-        out = torch.empty((N, split if out2 is not None else cout, D, H, W), device=x.device,
+        Do, Ho, Wo = (((D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1) if stride == 2 else (D, H, W))
+        out = torch.empty((N, split if out2 is not None else cout, Do, Ho, Wo), device=x.device,
                           memory_format=torch.channels_last_3d)
     if out.stride(1) != 1 or (out2 is not None and out2.shape[1] > 1 and out2.stride(1) != 1):
         raise BmvError("conv3d_k3: out must be channels_last_3d")
@@ -628,6 +629,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0):
     p.wfrag = wfrag.data_ptr()
     p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
     p.N, p.D, p.H, p.W, p.Cin, p.Cout, p.relu = N, D, H, W, Cin, cout, int(bool(relu))
+    p.stride = stride
     p.out = out.data_ptr()
     p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
     if out2 is not None:

@@ -331,7 +331,7 @@ BMV_API int bmv_fpn_topdown(const bmv_fpn_topdown_params* p, bmv_stream_t stream
  * strides, Cout channels written at out + ... + c).  wfrag: bmv_conv3d_k3_weight_words(Cin,Cout)
  * uint32 words in mma B-fragment order [dz][dy][k-step][n-tile][lane][2] (mlp_pack.pack_conv3d_k3; the
  * k-steps of each Cin are described in csrc/conv3d_mma.cu).
- * Instantiated (Cin,Cout<=): (16,8) (32,8) (8,16).
+ * Instantiated (Cin,Cout<=): (16,8) (16,16) (32,8) (8,16).
  */
 typedef struct bmv_conv3d_params {
   const float* x; int64_t x_n_stride, x_d_stride, x_y_stride, x_x_stride;
@@ -340,6 +340,8 @@ typedef struct bmv_conv3d_params {
   float* out; int64_t o_n_stride, o_d_stride, o_y_stride, o_x_stride;
   float* out2; int64_t o2_n_stride, o2_d_stride, o2_y_stride, o2_x_stride;   /* optional: channels >= split */
   int32_t split;                /* with out2: channel c >= split is written to out2 at channel c - split */
+  int32_t stride;               /* 0/1: stride 1.  2: stride-2 convolution (Cin=8, Cout<=16; ConvBnReLU3D(8,16,stride=2),
+                                   cost_reg_net.py:14,53), out is (N, (D-1)/2+1, (H-1)/2+1, (W-1)/2+1, Cout) */
 } bmv_conv3d_params;
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);

@@ -17,6 +17,8 @@ SHAPES = [  # (N, Cin, Cout, D, H, W, bias, relu)
     (2, 8, 9, 8, 8, 64, False, False),       # merged output heads
     (1, 8, 9, 3, 9, 17, True, True),
     (1, 8, 16, 8, 4, 32, True, False),
+    (2, 16, 16, 4, 8, 40, True, True),       # conv2 of the U-Nets
+    (1, 16, 12, 3, 5, 19, False, False),
 ]
 
 
@@ -51,6 +53,32 @@ def test_conv3d_k3_matches_cudnn(shape, exact_operands):
     scale = ref.abs().max().item()
     tol = (1e-5 if exact_operands else 2e-3) * scale
     assert (y - ref).abs().max().item() <= tol, ((y - ref).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 8, 8, 64), (1, 16, 6, 10, 38), (1, 12, 5, 7, 33), (2, 16, 2, 2, 2)])
+@pytest.mark.parametrize("exact_operands", [True, False])
+def test_conv3d_k3_stride2_matches_cudnn(shape, exact_operands):
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3
+    N, Cout, D, H, W = shape
+    g = torch.Generator().manual_seed(D * 10 + W)
+    x = torch.randn((N, 8, D, H, W), generator=g)
+    w = torch.randn((Cout, 8, 3, 3, 3), generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    if exact_operands:
+        x, w = x.half().float(), w.half().float()
+    x = x.cuda().contiguous(memory_format=torch.channels_last_3d)
+    w, b = w.cuda(), b.cuda()
+    y = ops.conv3d_k3(x, pack_conv3d_k3(w), b, Cout, True, stride=2)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.relu(torch.nn.functional.conv3d(x, w, b, stride=2, padding=1))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    scale = ref.abs().max().item()
+    assert (y - ref).abs().max().item() <= (1e-5 if exact_operands else 2e-3) * scale
 
 
 def test_conv3d_k3_strided_output_and_errors():

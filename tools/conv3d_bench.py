@@ -5,7 +5,8 @@ import torch
 from boostmvsnerfs_b200 import ops
 from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3
 
-SHAPES = [("cost_reg_1.conv0", 4, 16, 8, 8, 272, 480, True), ("cost_reg_1.heads", 4, 8, 9, 8, 272, 480, False),
+SHAPES = [("cost_reg_1.conv2", 4, 16, 16, 4, 136, 240, True), ("cost_reg_0.conv2", 4, 16, 16, 32, 34, 60, True),
+          ("cost_reg_1.conv0", 4, 16, 8, 8, 272, 480, True), ("cost_reg_1.heads", 4, 8, 9, 8, 272, 480, False),
           ("cost_reg_0.conv0", 4, 32, 8, 64, 68, 120, True), ("cost_reg_0.heads", 4, 8, 9, 64, 68, 120, False)]
 
 
@@ -40,6 +41,17 @@ for name, N, Cin, Cout, D, H, W, relu in SHAPES:
     torch.backends.cudnn.allow_tf32 = True
     mb = (x.numel() + N * Cout * D * H * W) * 4 / 1e6
     print(f"{name:18s} ours {t_ours:8.1f} us ({mb / t_ours * 1e3:7.0f} GB/s algorithmic)   cudnn tf32 {t_tf32:8.1f} us   cudnn fp32 {t_fp32:8.1f} us")
+
+for name, N, Cout, D, H, W in [("cost_reg_1.conv1 s2", 4, 16, 8, 272, 480), ("cost_reg_0.conv1 s2", 4, 16, 64, 68, 120)]:
+    x = torch.randn((N, 8, D, H, W), device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    w = torch.randn((Cout, 8, 3, 3, 3), device="cuda") * 0.1
+    wcl = w.contiguous(memory_format=torch.channels_last_3d)
+    b = torch.randn(Cout, device="cuda")
+    wf = pack_conv3d_k3(w)
+    t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, True, stride=2))
+    t_lib = timeit(lambda: torch.relu_(torch.nn.functional.conv3d(x, wcl, b, stride=2, padding=1)))
+    mb = (x.numel() + x.numel() // 8 * 2) * 4 / 1e6
+    print(f"{name:24s} ours {t_ours:8.1f} us ({mb / t_ours * 1e3:7.0f} GB/s algorithmic)   cudnn tf32 + relu {t_lib:8.1f} us")
 
 from boostmvsnerfs_b200.mlp_pack import pack_convT3d_k3s2
 for name, N, Cin, Cout, D, H, W in [("cost_reg_1.conv11T+add", 4, 16, 8, 4, 136, 240), ("cost_reg_1.conv9T+add", 4, 32, 16, 2, 68, 120),
