@@ -494,6 +494,9 @@ def main_ours(args):
         "eager": eager, "cuda_graph": graph_res,
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels, "frame_sharded": sharded,
         "stage_ms_per_step": step_ms_stage, "hand_written_ms_per_step": hand_ms,
+        "stage_ms_note": "eager instrumented pass: when the GPU outruns the Python enqueue (host_enqueue_ms_per_step >= "
+                         "eager ms_per_step) the stage where the stream runs dry is inflated by the host gap; "
+                         "libbmv_kernel_ms_per_step (events right around each launch) and the graph replay are not",
         "host_enqueue_ms_per_step": t_host, "instrumented_ms_per_step": ms_instrumented,
         # stages that mix libbmv tensor-core convolution kernels with kept cuDNN layers
         "mixed_library_stage_ms_per_step": {k: v for k, v in step_ms_stage.items() if k.startswith(("cost_reg", "nerf", "feature"))},
