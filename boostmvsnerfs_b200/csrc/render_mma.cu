@@ -20,7 +20,7 @@
 
 namespace bmv {
 
-constexpr int kMmaWarps = 12;
+constexpr int kMmaWarps = 16;      // 128 registers per thread (76 B of spills) beat 12 warps at 166: 1.88 -> 1.74 ms per C2 frame
 constexpr int kStageStride = 72;        // floats per staged sample: vox 8 | 3 x (f_v 15 + pad) ; 72 = 8 mod 32
 
 // fragment-ordered weight blocks (128 words each), in this order
