@@ -479,10 +479,15 @@ def main_ours(args):
     hand_ms = sum(step_ms_stage.get(k, 0.0) for k in alg)
     eager = {"ms_per_step": ms, "value": world * rays_per_frame / (ms * 1e-3), "e2e_ms_per_step": ms_e2e,
              "e2e_value": world * rays_per_frame / (ms_e2e * 1e-3)}
-    execution = "eager (stream launches)"
+    # headline = the faster of the two public entry points (Network.forward / FrameGraph.__call__), chosen
+    # separately for the device-resident number and for the end-to-end number; both modes are listed in full
+    execution = "value: eager (stream launches)"
     if graph_res and "error" not in graph_res and graph_res["ms_per_step"] < ms:
-        # headline = the faster of the two public entry points (Network.forward / FrameGraph.__call__)
-        ms, ms_e2e, execution = graph_res["ms_per_step"], graph_res["e2e_ms_per_step"], "cuda_graph replay (FrameGraph)"
+        ms, execution = graph_res["ms_per_step"], "value: cuda_graph replay (FrameGraph)"
+    if graph_res and "error" not in graph_res and graph_res["e2e_ms_per_step"] < ms_e2e:
+        ms_e2e, execution = graph_res["e2e_ms_per_step"], execution + "; e2e: cuda_graph replay (FrameGraph)"
+    else:
+        execution += "; e2e: eager (stream launches)"
     line = {
         "metric": "rays_per_sec", "value": world * rays_per_frame / (ms * 1e-3), "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "ms_per_frame": ms,

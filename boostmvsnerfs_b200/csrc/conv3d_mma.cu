@@ -39,7 +39,7 @@ template <int CIN, int NTILES> struct ConvCfg;
 // 32- and 64-byte voxels this makes the 8 rows of every ldmatrix 8x8 block hit 8 distinct 16-byte bank groups.
 template <int NTILES> struct ConvCfg<16, NTILES> {
   static constexpr int VS = 32, KS = 3, NT = NTILES, TH = 4, WD = NTILES == 1 ? 2 : 1, EXTRA = 0;
-  static constexpr bool BREG = NTILES == 1;
+  static constexpr bool BREG = false;
   __device__ static __forceinline__ int swz(int v) { return (v >> 2) & 1; }
   // k-step j: voxel offset and first 16-byte chunk of the lane's row segment (hi = lane / 16)
   __device__ static __forceinline__ int step_voxel(int j, int hi) { return j; }
@@ -73,7 +73,7 @@ struct ConvTile {
 };
 
 template <int CIN, int NTILES>
-__global__ void __launch_bounds__(kConvThreads, CIN == 8 ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
+__global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILES == 1)) ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
   using T = ConvTile<CIN, NTILES>;
   using Cfg = ConvCfg<CIN, NTILES>;
   constexpr int NT = Cfg::NT, KS = Cfg::KS, WD = Cfg::WD, TH = T::TH;

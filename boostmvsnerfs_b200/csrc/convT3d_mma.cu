@@ -31,13 +31,13 @@ struct CtCfg {
   static constexpr int ROWB = HW * VS;
   static constexpr int TILE_BYTES = HD * HH * ROWB;
   static constexpr int W_WORDS = 27 * KT * NT * 32 * 2;
-  static constexpr bool BREG = (27 * KT * NT <= 27);
+  static constexpr bool BREG = false;
   static constexpr int JOBS = TD * TH * (TW / 16);
   __device__ static __forceinline__ int swz(int v) { return CIN == 16 ? (v >> 2) & 1 : (v >> 1) & 3; }
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kCtThreads, 2) convT3d_k3s2_mma_kernel(bmv_convT3d_params p) {
+__global__ void __launch_bounds__(kCtThreads, (CIN == 16 ? 4 : 2)) convT3d_k3s2_mma_kernel(bmv_convT3d_params p) {
   using C = CtCfg<CIN, COUT>;
   constexpr int KT = C::KT, NT = C::NT;
   extern __shared__ __align__(16) unsigned char smem[];
