@@ -1,0 +1,167 @@
+"""CPU checks of the MMA weight packers (mlp_pack.pack_conv*): the packed words are unpacked with the
+mma.sync.m16n8k16 B-fragment rule (lane = 4g+t holds b0 = B[2t, 2t+1][g], b1 = B[2t+8, 2t+9][g]) and fed
+through a plain restatement of each kernel's implicit-GEMM addressing (the k-step -> (voxel offset, channel)
+maps of csrc/conv3d_mma.cu, convT3d_mma.cu, fpn_fused.cu, fpn_stem.cu); the result must equal torch's
+convolution on fp16-representable operands.  Runs without a GPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from boostmvsnerfs_b200 import mlp_pack
+
+
+def unpack_b(words, lead):
+    """words: int32 tensor [*lead][lane 32][2 regs] -> float B[*lead][k 16][n 8]."""
+    h = words.view(torch.float16).float().view(*lead, 32, 2, 2)          # [.., lane, reg, elem]
+    B = torch.zeros(*lead, 16, 8)
+    for lane in range(32):
+        g, t = lane // 4, lane % 4
+        for r in range(2):
+            for e in range(2):
+                B[..., 2 * t + 8 * r + e, g] = h[..., lane, r, e]
+    return B
+
+
+def conv3d_step_sources(cin):
+    """(voxel offset dx, channel) read by K index k of k-step j — restates ConvCfg::step_voxel/step_chunk."""
+    if cin == 16:
+        return [[(j, k) for k in range(16)] for j in range(3)]
+    if cin == 32:
+        return [[(j >> 1, (j & 1) * 16 + k) for k in range(16)] for j in range(6)]
+    return [[(2 * j + (k >= 8), k % 8) for k in range(16)] for j in range(2)]      # cin == 8: voxel pairs
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 8), (16, 16), (16, 5), (32, 8), (8, 9), (8, 16)])
+def test_pack_conv3d_k3_reproduces_conv3d(cin, cout):
+    g = torch.Generator().manual_seed(cin * 31 + cout)
+    w = (torch.randn((cout, cin, 3, 3, 3), generator=g) * 0.2).half().float()
+    x = torch.randn((1, cin, 4, 5, 9), generator=g).half().float()
+    steps = conv3d_step_sources(cin)
+    nt = mlp_pack._conv3d_ntiles(cin, cout)
+    B = unpack_b(mlp_pack.pack_conv3d_k3(w), (3, 3, len(steps), nt))     # [dz][dy][j][nt][k][n]
+    xp = F.pad(x, (1, 3, 1, 1, 1, 1))[0]                                 # +2 extra on the right: Cin=8 reads x+3
+    D, H, W = x.shape[2:]
+    out = torch.zeros(nt * 8, D, H, W)
+    for dz in range(3):
+        for dy in range(3):
+            for j, step in enumerate(steps):
+                for k, (dx, c) in enumerate(step):
+                    a = xp[c, dz:dz + D, dy:dy + H, dx:dx + W]           # A[voxel, k]
+                    for t in range(nt):
+                        out[t * 8:(t + 1) * 8] += B[dz, dy, j, t, k][:, None, None, None] * a
+    ref = F.conv3d(x, w, padding=1)[0]
+    assert torch.allclose(out[:cout], ref, atol=1e-4), (out[:cout] - ref).abs().max()
+    assert out[cout:].abs().max() == 0 if cout < nt * 8 else True
+
+
+def test_pack_conv3d_k3_stride2_addressing():
+    """Stride 2 uses the Cin=8 packing with A rows at every second voxel (conv3d_k3s2_c8_mma_kernel)."""
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn((16, 8, 3, 3, 3), generator=g) * 0.2).half().float()
+    x = torch.randn((1, 8, 6, 4, 10), generator=g).half().float()
+    B = unpack_b(mlp_pack.pack_conv3d_k3(w), (3, 3, 2, 2))
+    xp = F.pad(x, (1, 3, 1, 1, 1, 1))[0]
+    Do, Ho, Wo = 3, 2, 5
+    out = torch.zeros(16, Do, Ho, Wo)
+    for dz in range(3):
+        for dy in range(3):
+            for j in range(2):
+                for k in range(16):
+                    dx, c = 2 * j + (k >= 8), k % 8
+                    a = xp[c, dz:dz + 2 * Do:2, dy:dy + 2 * Ho:2, dx:dx + 2 * Wo:2]
+                    for t in range(2):
+                        out[t * 8:(t + 1) * 8] += B[dz, dy, j, t, k][:, None, None, None] * a
+    ref = F.conv3d(x, w, stride=2, padding=1)[0]
+    assert torch.allclose(out, ref, atol=1e-4)
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 8), (32, 16)])
+def test_pack_convT3d_k3s2_reproduces_conv_transpose(cin, cout):
+    g = torch.Generator().manual_seed(cin)
+    w = (torch.randn((cin, cout, 3, 3, 3), generator=g) * 0.2).half().float()
+    x = torch.randn((1, cin, 2, 3, 4), generator=g).half().float()
+    kt, nt = cin // 16, cout // 8
+    B = unpack_b(mlp_pack.pack_convT3d_k3s2(w), (27, kt, nt))            # [tap][kt][nt][k][n]
+    D, H, W = x.shape[2:]
+    xp = F.pad(x, (0, 1, 0, 1, 0, 1))[0]                                 # +1 halo on the high side
+    out = torch.zeros(cout, 2 * D, 2 * H, 2 * W)
+    # shift s in a dimension serves (parity 0, tap 1) and (parity 1, tap 2) when s = 0, (parity 1, tap 0) when s = 1
+    opts = {0: [(0, 1), (1, 2)], 1: [(1, 0)]}
+    for sz in range(2):
+        for sy in range(2):
+            for sx in range(2):
+                a = xp[:, sz:sz + D, sy:sy + H, sx:sx + W]               # (cin, D, H, W)
+                for pz, kz in opts[sz]:
+                    for py, ky in opts[sy]:
+                        for px, kx in opts[sx]:
+                            tap = (kz * 3 + ky) * 3 + kx
+                            Bt = torch.cat([torch.cat([B[tap, k, t] for t in range(nt)], dim=1) for k in range(kt)], dim=0)  # (cin, cout)
+                            out[:, pz::2, py::2, px::2] += torch.einsum("cdhw,co->odhw", a, Bt)
+    ref = F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1)[0]
+    assert torch.allclose(out, ref, atol=1e-4), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("cout", [8, 16])
+def test_pack_conv2d_k3_c32_reproduces_conv2d(cout):
+    g = torch.Generator().manual_seed(cout)
+    w = (torch.randn((cout, 32, 3, 3), generator=g) * 0.2).half().float()
+    x = torch.randn((1, 32, 5, 7), generator=g).half().float()
+    nt = cout // 8
+    B = unpack_b(mlp_pack.pack_conv2d_k3_c32(w), (3, 6, nt))             # [dy][j = dx*2+half][nt][k][n]
+    xp = F.pad(x, (1, 1, 1, 1))[0]
+    H, W = x.shape[2:]
+    out = torch.zeros(cout, H, W)
+    for dy in range(3):
+        for j in range(6):
+            dx, half = j >> 1, j & 1
+            for k in range(16):
+                a = xp[half * 16 + k, dy:dy + H, dx:dx + W]
+                for t in range(nt):
+                    out[t * 8:(t + 1) * 8] += B[dy, j, t, k][:, None, None] * a
+    assert torch.allclose(out, F.conv2d(x, w, padding=1)[0], atol=1e-4)
+
+
+def test_pack_conv2d_k3_c8_reproduces_conv2d():
+    g = torch.Generator().manual_seed(1)
+    w = (torch.randn((8, 8, 3, 3), generator=g) * 0.2).half().float()
+    x = torch.randn((1, 8, 4, 6), generator=g).half().float()
+    B = unpack_b(mlp_pack.pack_conv2d_k3_c8(w), (3, 2))                  # [dy][j][k][n]
+    xp = F.pad(x, (1, 3, 1, 1))[0]
+    H, W = x.shape[2:]
+    out = torch.zeros(8, H, W)
+    for dy in range(3):
+        for j in range(2):
+            for k in range(16):
+                dx, c = 2 * j + (k >= 8), k % 8
+                out += B[dy, j, k][:, None, None] * xp[c, dy:dy + H, dx:dx + W]
+    assert torch.allclose(out, F.conv2d(x, w, padding=1)[0], atol=1e-4)
+
+
+def test_packers_reject_uninstantiated_shapes():
+    with pytest.raises(ValueError):
+        mlp_pack.pack_conv3d_k3(torch.zeros(8, 24, 3, 3, 3))
+    with pytest.raises(ValueError):
+        mlp_pack.pack_conv3d_k3(torch.zeros(24, 16, 3, 3, 3))
+    with pytest.raises(ValueError):
+        mlp_pack.pack_convT3d_k3s2(torch.zeros(16, 16, 3, 3, 3))
+    with pytest.raises(ValueError):
+        mlp_pack.pack_conv2d_k3_c32(torch.zeros(8, 16, 3, 3))
+    with pytest.raises(ValueError):
+        mlp_pack.pack_conv2d_k3_c8(torch.zeros(8, 8, 5, 5))
+
+
+def test_cost_reg_plan_uses_cudnn_on_cpu_and_when_tf32_is_off():
+    """The tensor-core convolutions are a CUDA + allow_tf32 fast path; everywhere else the plan is the folded
+    cuDNN/ATen module (and therefore runs on CPU for the host-logic tests)."""
+    from boostmvsnerfs_b200.inference_plan import MergedHeadsCostReg, PlanCache
+    from boostmvsnerfs_b200.modules import MinCostRegNet
+    torch.manual_seed(0)
+    net = MinCostRegNet(16).eval()
+    plan = PlanCache().get("cr", net, None)
+    assert isinstance(plan, MergedHeadsCostReg)
+    x = torch.rand(1, 16, 8, 16, 16)
+    assert not plan._use_tensor_core_convs(x)
+    with torch.no_grad():
+        feat, logits = plan(x)
+        ref_feat, ref_logits = net(x)
+    assert torch.allclose(feat, ref_feat, atol=1e-5) and torch.allclose(logits, ref_logits, atol=1e-5)
