@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(kStThreads, 3) fpn_stem_kernel(bmv_fpn_stem_pa
         r = __ldg(px); g = __ldg(px + p.x_c_stride); b = __ldg(px + 2 * p.x_c_stride);
       }
       s_img[i * 3] = r; s_img[i * 3 + 1] = g; s_img[i * 3 + 2] = b;
+      // optional by-product: the image as (N,H,W,4) channels-last for the colour fetch of the render kernels
+      if (p.rgb4 && iy >= 2 && iy < 2 + kStTY && ix >= 2 && ix < 2 + kStTX && y < p.H && x < p.W)
+        *reinterpret_cast<float4*>(p.rgb4 + (((int64_t)n * p.H + y) * p.W + x) * 4) = make_float4(r, g, b, 0.f);
     }
   }
   __syncthreads();
@@ -131,8 +134,8 @@ extern "C" BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t s
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->w0 && p->wfrag1 && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: bad size");
-  BMV_REQUIRE(((uintptr_t)p->out & 7) == 0 && ((uintptr_t)p->wfrag1 & 7) == 0, BMV_ERR_INVALID_ARGUMENT,
-              "bmv_fpn_stem: out / wfrag1 must be 8-byte aligned");
+  BMV_REQUIRE(((uintptr_t)p->out & 7) == 0 && ((uintptr_t)p->wfrag1 & 7) == 0 && ((uintptr_t)p->rgb4 & 15) == 0,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: out / wfrag1 must be 8-byte, rgb4 16-byte aligned");
   const dim3 grid((unsigned)(((p->W + kStTX - 1) / kStTX) * ((p->H + kStTY - 1) / kStTY)), (unsigned)p->N);
   fpn_stem_kernel<<<grid, kStThreads, 0, (cudaStream_t)stream>>>(*p);
   return check_launch("bmv_fpn_stem");

@@ -190,11 +190,13 @@ class FusedTopDownFPN(nn.Module):
         from . import ops
         f = self.fpn
         fused = self.fused_smooth and torch.backends.cudnn.allow_tf32
+        self.rgb_nhwc4 = None
         if fused and isinstance(f.conv0[0].bn, nn.Identity):
-            a, b = f.conv0[0].conv, f.conv0[1].conv
-            c0 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias)
+            a, b = f.conv0[0].conv, f.conv0[1].conv      # the stem reads x with any strides: no layout copy
+            c0, self.rgb_nhwc4 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias,
+                                              want_rgb4=True)
         else:
-            c0 = f.conv0(x)
+            c0 = f.conv0(x.contiguous(memory_format=torch.channels_last))
         c1 = f.conv1(c0)
         c2 = f.conv2(c1)
         quarter = f.toplayer(c2)

@@ -101,10 +101,15 @@ class EnerfNetwork(nn.Module):
     def forward_feat(self, x):
         """x (N,3,H,W) -> dict level_{0,1,2} of (N,C,h,w)
         (reference lib/networks/enerf/network.py:58-67, batch dim squeezed)."""
-        if self.channels_last:
+        plan = self._kept('feature_net')
+        fused_plan = type(plan).__name__ == 'FusedTopDownFPN'
+        if self.channels_last and not fused_plan:
             x = x.contiguous(memory_format=torch.channels_last)
-        quarter, half, full = self._kept('feature_net')(x)
-        return {'level_0': quarter, 'level_1': half, 'level_2': full}
+        quarter, half, full = plan(x)
+        feats = {'level_0': quarter, 'level_1': half, 'level_2': full}
+        if fused_plan and plan.rgb_nhwc4 is not None:
+            feats['rgb_nhwc4'] = plan.rgb_nhwc4             # by-product of the stem kernel (see _render_level)
+        return feats
 
     @staticmethod
     def _proj_all(exts, ixts, tar_ext, tar_ixt, src_scale, tar_scale):
@@ -283,8 +288,10 @@ class EnerfNetwork(nn.Module):
             rgb, affine = inps, (0.5, 0.5)          # unpreprocess folded into the fetch
             if self.channels_last and inps.is_cuda:
                 # (N,H,W,4) channels-last copy: one 16-byte load per bilinear tap in the fused render kernel
-                rgb4 = inps.new_zeros((inps.shape[0], inps.shape[2], inps.shape[3], 4))
-                rgb4[..., :3] = inps.permute(0, 2, 3, 1)
+                rgb4 = feats.get('rgb_nhwc4')
+                if rgb4 is None or rgb4.shape[:3] != (inps.shape[0], inps.shape[2], inps.shape[3]):
+                    rgb4 = inps.new_zeros((inps.shape[0], inps.shape[2], inps.shape[3], 4))
+                    rgb4[..., :3] = inps.permute(0, 2, 3, 1)
                 rgb = rgb4.permute(0, 3, 1, 2)[:, :3]
         else:          # level-0 rendering of the pre-train configs: resized colours (enerf/utils.py:669-676)
             rgb = torch.nn.functional.interpolate(inps * 0.5 + 0.5, size=(H, W), align_corners=True, mode='bilinear')

@@ -700,10 +700,11 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     return mid, out
 
 
-def fpn_stem(x, w0, b0, wfrag1, b1):
+def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False):
     """relu(conv3x3_{8->8}(relu(conv3x3_{3->8}(x) + b0)) + b1) in one launch (reference
     lib/networks/enerf/feature_net.py:7-9; BN already folded into w/b).  x (N,3,H,W) fp32, any strides;
-    returns (N,8,H,W) channels_last."""
+    returns (N,8,H,W) channels_last — and, with want_rgb4, also x as an (N,H,W,4) [r,g,b,0] tensor (the layout
+    the render kernels fetch colours from with one 16-byte load per tap)."""
     _f32(x, "x")
     N, C, H, W = x.shape
     if C != 3:
@@ -718,5 +719,7 @@ def fpn_stem(x, w0, b0, wfrag1, b1):
     p.w0, p.b0, p.wfrag1, p.b1 = w0c.data_ptr(), b0c.data_ptr(), wfrag1.data_ptr(), b1c.data_ptr()
     p.N, p.H, p.W = N, H, W
     p.out = out.data_ptr()
+    rgb4 = torch.empty((N, H, W, 4), device=x.device) if want_rgb4 else None
+    p.rgb4 = rgb4.data_ptr() if want_rgb4 else 0
     _lib.call("bmv_fpn_stem", p, _stream())
-    return out
+    return (out, rgb4) if want_rgb4 else out

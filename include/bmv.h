@@ -399,6 +399,8 @@ typedef struct bmv_fpn_stem_params {
   const uint32_t* wfrag1; const float* b1;
   int32_t N, H, W;
   float* out;
+  float* rgb4;                  /* optional by-product: x as (N,H,W,4) channels-last [r,g,b,0] (see rgb_*_stride of
+                                   bmv_raygen_fetch_params), or NULL */
 } bmv_fpn_stem_params;
 BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream);
 

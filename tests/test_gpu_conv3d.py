@@ -238,3 +238,6 @@ def test_fpn_stem_vs_torch(hw, layout):
     out = ops.fpn_stem(x, c0.weight, c0.bias, pack_conv2d_k3_c8(c1.weight), c1.bias)
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
     assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    out2, rgb4 = ops.fpn_stem(x, c0.weight, c0.bias, pack_conv2d_k3_c8(c1.weight), c1.bias, want_rgb4=True)
+    assert torch.equal(out2, out)
+    assert torch.equal(rgb4[..., :3], x.permute(0, 2, 3, 1)) and rgb4[..., 3].abs().max().item() == 0
