@@ -160,6 +160,12 @@ inline bool gather_vec_ok(const bmv_raygen_fetch_params& p) {
 
 __device__ __forceinline__ float4 ldg4(const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); }
 
+// Division for quantities that only steer interpolation / direction features (tolerance 1e-4): the VEC (fast
+// path) instantiation uses MUFU.RCP + multiply (<= 2 ulp) instead of the ~15-instruction IEEE sequence — 33
+// divisions per sample.  Everything that decides a visibility count or a sample depth stays IEEE (div_rn).
+template <bool FAST>
+__device__ __forceinline__ float gdiv(float a, float b) { return FAST ? __fdividef(a, b) : div_rn(a, b); }
+
 // VEC = true: the layouts of gather_vec_ok(); every tap is fetched with 16-byte loads (52 loads per sample
 // instead of 196 scalar ones).  The arithmetic — order of the fmaf chains per channel — is identical.
 template <int CF, int V, bool VEC = false>
@@ -202,7 +208,7 @@ __device__ __forceinline__ int gather_sample_regs(const bmv_raygen_fetch_params&
   float ttx = sub_rn(x, tar_c[0]), tty = sub_rn(y, tar_c[1]), ttz = sub_rn(zz, tar_c[2]);
   {
     const float n = sqrtf(ttx * ttx + tty * tty + ttz * ttz) + 1e-6f;
-    ttx = div_rn(ttx, n); tty = div_rn(tty, n); ttz = div_rn(ttz, n);
+    ttx = gdiv<VEC>(ttx, n); tty = gdiv<VEC>(tty, n); ttz = gdiv<VEC>(ttz, n);
   }
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -216,8 +222,8 @@ __device__ __forceinline__ int gather_sample_regs(const bmv_raygen_fetch_params&
     const float qy = dot3_gemm(cx, cy, cz, mul_rn(cam.K[3], rs), mul_rn(cam.K[4], rs), mul_rn(cam.K[5], rs));
     const float qz = dot3_gemm(cx, cy, cz, cam.K[6], cam.K[7], cam.K[8]);
     const float qzc = (qz != qz) ? qz : fmaxf(qz, 1e-6f);
-    float gx = div_rn(div_rn(qx, qzc), (float)(p.Wf - 1));
-    float gy = div_rn(div_rn(qy, qzc), (float)(p.Hf - 1));
+    float gx = gdiv<VEC>(gdiv<VEC>(qx, qzc), (float)(p.Wf - 1));
+    float gy = gdiv<VEC>(gdiv<VEC>(qy, qzc), (float)(p.Hf - 1));
     gx = sub_rn(mul_rn(gx, 2.f), 1.f);
     gy = sub_rn(mul_rn(gy, 2.f), 1.f);
     const int view = views[v];
@@ -264,12 +270,12 @@ __device__ __forceinline__ int gather_sample_regs(const bmv_raygen_fetch_params&
     }
     float sx = sub_rn(x, cam.c[0]), sy = sub_rn(y, cam.c[1]), sz = sub_rn(zz, cam.c[2]);
     const float n = sqrtf(sx * sx + sy * sy + sz * sz) + 1e-6f;
-    sx = div_rn(sx, n); sy = div_rn(sy, n); sz = div_rn(sz, n);
+    sx = gdiv<VEC>(sx, n); sy = gdiv<VEC>(sy, n); sz = gdiv<VEC>(sz, n);
     const float ex = sub_rn(ttx, sx), ey = sub_rn(tty, sy), ez = sub_rn(ttz, sz);
     const float en = fmaxf(sqrtf(ex * ex + ey * ey + ez * ez), 1e-6f);
-    f[v][CF + 3] = div_rn(ex, en);
-    f[v][CF + 4] = div_rn(ey, en);
-    f[v][CF + 5] = div_rn(ez, en);
+    f[v][CF + 3] = gdiv<VEC>(ex, en);
+    f[v][CF + 4] = gdiv<VEC>(ey, en);
+    f[v][CF + 5] = gdiv<VEC>(ez, en);
     f[v][CF + 6] = ttx * sx + tty * sy + ttz * sz;
   }
   return cnt;

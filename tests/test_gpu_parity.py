@@ -362,7 +362,10 @@ def test_tensor_core_render_matches_fp32_paths(ops, g, seed):
     img4[..., :3] = img.permute(0, 2, 3, 1)
     args_cl = args[:8] + (vol_cl, imf_cl, img4.permute(0, 3, 1, 2)[:, :3]) + args[11:]
     vec = ops.render_rays(*args_cl, mlp_pack.pack_nerf_weights_mma(net), engine="mma", want_count=True)
-    exact(vec["raw"], mma["raw"], "vectorised gather vs scalar gather")
+    # (the fast-path instantiation also replaces 33 IEEE divisions per sample by reciprocal-multiply: <= 2 ulp
+    # on interpolation coordinates and direction features, never on visibility or depths)
+    close(vec["raw"], mma["raw"], "vectorised gather vs scalar gather", rtol=2e-5)
+    exact(vec["z_vals"], mma["z_vals"], "z_vals (vectorised gather)")
     exact(vec["vis_mask"], mma["vis_mask"], "visibility (vectorised gather)")
     # strided (non-planar) rgb through the fp32 kernel and the stand-alone fetch
     fma_cl = ops.render_rays(*args_cl, mlp_pack.pack_nerf_weights(net))
