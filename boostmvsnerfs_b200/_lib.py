@@ -147,7 +147,8 @@ class FpnFusedParams(C.Structure):
 class FpnStemParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_n_stride", i64), ("x_c_stride", i64), ("x_y_stride", i64), ("x_x_stride", i64),
                 ("w0", C.c_void_p), ("b0", C.c_void_p), ("wfrag1", C.c_void_p), ("b1", C.c_void_p),
-                ("N", i32), ("H", i32), ("W", i32), ("out", C.c_void_p), ("rgb4", C.c_void_p)]
+                ("N", i32), ("H", i32), ("W", i32), ("out", C.c_void_p), ("rgb4", C.c_void_p),
+                ("out_s2d", C.c_void_p)]
 
 
 ENTRY_POINTS = {

@@ -120,10 +120,15 @@ __global__ void __launch_bounds__(kStThreads, 3) fpn_stem_kernel(bmv_fpn_stem_pa
     for (int oy = 0; oy < kStWY; ++oy) {
       const int gy = y0 + yb + oy;
       if (gy >= p.H) continue;
-      if (gx0 < p.W)
-        *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * 8 + 2 * t) = make_float2(fmaxf(acc[oy][0], 0.f), fmaxf(acc[oy][1], 0.f));
-      if (gx1 < p.W)
-        *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * 8 + 2 * t) = make_float2(fmaxf(acc[oy][2], 0.f), fmaxf(acc[oy][3], 0.f));
+      const float2 r0 = make_float2(fmaxf(acc[oy][0], 0.f), fmaxf(acc[oy][1], 0.f));
+      const float2 r1 = make_float2(fmaxf(acc[oy][2], 0.f), fmaxf(acc[oy][3], 0.f));
+      if (gx0 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * 8 + 2 * t) = r0;
+      if (gx1 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * 8 + 2 * t) = r1;
+      if (p.out_s2d) {                                                  // (N, H/2, W/2, [py][px][8])
+        float* zrow = p.out_s2d + (((int64_t)n * (p.H >> 1) + (gy >> 1)) * (p.W >> 1)) * 32 + (gy & 1) * 16 + 2 * t;
+        if (gx0 < p.W) *reinterpret_cast<float2*>(zrow + (int64_t)(gx0 >> 1) * 32 + (gx0 & 1) * 8) = r0;
+        if (gx1 < p.W) *reinterpret_cast<float2*>(zrow + (int64_t)(gx1 >> 1) * 32 + (gx1 & 1) * 8) = r1;
+      }
     }
   }
 }
@@ -134,8 +139,11 @@ extern "C" BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t s
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->w0 && p->wfrag1 && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: bad size");
-  BMV_REQUIRE(((uintptr_t)p->out & 7) == 0 && ((uintptr_t)p->wfrag1 & 7) == 0 && ((uintptr_t)p->rgb4 & 15) == 0,
-              BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: out / wfrag1 must be 8-byte, rgb4 16-byte aligned");
+  BMV_REQUIRE(((uintptr_t)p->out & 7) == 0 && ((uintptr_t)p->wfrag1 & 7) == 0 && ((uintptr_t)p->rgb4 & 15) == 0 &&
+                  ((uintptr_t)p->out_s2d & 7) == 0,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: out / out_s2d / wfrag1 must be 8-byte, rgb4 16-byte aligned");
+  BMV_REQUIRE(!p->out_s2d || (p->H % 2 == 0 && p->W % 2 == 0), BMV_ERR_INVALID_ARGUMENT,
+              "bmv_fpn_stem: the space-to-depth output needs even H and W");
   const dim3 grid((unsigned)(((p->W + kStTX - 1) / kStTX) * ((p->H + kStTY - 1) / kStTY)), (unsigned)p->N);
   fpn_stem_kernel<<<grid, kStThreads, 0, (cudaStream_t)stream>>>(*p);
   return check_launch("bmv_fpn_stem");

@@ -60,6 +60,12 @@ class S2DConv5x5(nn.Module):
             raise ValueError("space-to-depth needs even H and W")
         z = x.permute(0, 2, 3, 1).reshape(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5)
         z = z.reshape(N, H // 2, W // 2, 4 * C).permute(0, 3, 1, 2)          # NCHW view, channels-last memory
+        return self.forward_s2d(z)
+
+    def forward_s2d(self, z):
+        """z: the space-to-depth tensor (N, 4C, H/2, W/2), channel order (py, px, c), channels-last memory."""
+        if self.relu and self.bias is not None and z.is_cuda and not torch.is_grad_enabled():
+            return torch.cudnn_convolution_relu(z, self.weight, self.bias, (1, 1), (1, 1), (1, 1), 1)
         y = torch.nn.functional.conv2d(z, self.weight, self.bias, stride=1, padding=1)
         return torch.relu_(y) if self.relu else y
 
@@ -193,11 +199,13 @@ class FusedTopDownFPN(nn.Module):
         self.rgb_nhwc4 = None
         if fused and isinstance(f.conv0[0].bn, nn.Identity):
             a, b = f.conv0[0].conv, f.conv0[1].conv      # the stem reads x with any strides: no layout copy
-            c0, self.rgb_nhwc4 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias,
-                                              want_rgb4=True)
+            want_s2d = isinstance(f.conv1[0], S2DConv5x5) and x.shape[-1] % 2 == 0 and x.shape[-2] % 2 == 0
+            c0, self.rgb_nhwc4, z0 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias,
+                                                  want_rgb4=True, want_s2d=want_s2d)
+            c1 = f.conv1[1](f.conv1[0].forward_s2d(z0)) if want_s2d else f.conv1(c0)
         else:
             c0 = f.conv0(x.contiguous(memory_format=torch.channels_last))
-        c1 = f.conv1(c0)
+            c1 = f.conv1(c0)
         c2 = f.conv2(c1)
         quarter = f.toplayer(c2)
         if fused:

@@ -36,6 +36,11 @@ class _CBR(nn.Module):
         self.bn = bn_cls(cout)
 
     def forward(self, x):
+        if isinstance(self.bn, nn.Identity) and x.is_cuda and self.conv.bias is not None and not torch.is_grad_enabled():
+            # BN already folded (inference_plan.py): one fused cuDNN call instead of conv + bias-add + ReLU kernels
+            # (identical results; ~2x faster on the channels-last layers that stay on cuDNN, tools/cudnn_fused_bias_relu.py)
+            c = self.conv
+            return torch.cudnn_convolution_relu(x, c.weight, c.bias, c.stride, c.padding, c.dilation, c.groups)
         return F.relu(self.bn(self.conv(x)), inplace=True)
 
 

@@ -700,11 +700,13 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     return mid, out
 
 
-def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False):
+def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False):
     """relu(conv3x3_{8->8}(relu(conv3x3_{3->8}(x) + b0)) + b1) in one launch (reference
     lib/networks/enerf/feature_net.py:7-9; BN already folded into w/b).  x (N,3,H,W) fp32, any strides;
     returns (N,8,H,W) channels_last — and, with want_rgb4, also x as an (N,H,W,4) [r,g,b,0] tensor (the layout
-    the render kernels fetch colours from with one 16-byte load per tap)."""
+    the render kernels fetch colours from with one 16-byte load per tap); with want_s2d (implies the 3-tuple
+    return) also the space-to-depth(2) copy of the output, (N,32,H/2,W/2) channels_last with channel order
+    (py, px, c) — the input layout of the regrouped 5x5/stride-2 layer (inference_plan.S2DConv5x5)."""
     _f32(x, "x")
     N, C, H, W = x.shape
     if C != 3:
@@ -721,5 +723,13 @@ def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False):
     p.out = out.data_ptr()
     rgb4 = torch.empty((N, H, W, 4), device=x.device) if want_rgb4 else None
     p.rgb4 = rgb4.data_ptr() if want_rgb4 else 0
+    s2d = None
+    if want_s2d:
+        if H % 2 or W % 2:
+            raise BmvError("fpn_stem: space-to-depth output needs even H and W")
+        s2d = torch.empty((N, 32, H // 2, W // 2), device=x.device, memory_format=torch.channels_last)
+        p.out_s2d = s2d.data_ptr()
     _lib.call("bmv_fpn_stem", p, _stream())
+    if want_s2d:
+        return out, rgb4, s2d
     return (out, rgb4) if want_rgb4 else out

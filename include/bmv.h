@@ -401,6 +401,8 @@ typedef struct bmv_fpn_stem_params {
   float* out;
   float* rgb4;                  /* optional by-product: x as (N,H,W,4) channels-last [r,g,b,0] (see rgb_*_stride of
                                    bmv_raygen_fetch_params), or NULL */
+  float* out_s2d;               /* optional second copy of the output in space-to-depth(2) layout (N,H/2,W/2,32), channel
+                                   (y&1)*16 + (x&1)*8 + c: the input of the regrouped 5x5/stride-2 conv1.0; H, W even; or NULL */
 } bmv_fpn_stem_params;
 BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream);
 

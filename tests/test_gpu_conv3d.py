@@ -241,3 +241,7 @@ def test_fpn_stem_vs_torch(hw, layout):
     out2, rgb4 = ops.fpn_stem(x, c0.weight, c0.bias, pack_conv2d_k3_c8(c1.weight), c1.bias, want_rgb4=True)
     assert torch.equal(out2, out)
     assert torch.equal(rgb4[..., :3], x.permute(0, 2, 3, 1)) and rgb4[..., 3].abs().max().item() == 0
+    if H % 2 == 0 and W % 2 == 0:
+        out3, _, z = ops.fpn_stem(x, c0.weight, c0.bias, pack_conv2d_k3_c8(c1.weight), c1.bias, want_rgb4=True, want_s2d=True)
+        zr = out.permute(0, 2, 3, 1).reshape(2, H // 2, 2, W // 2, 2, 8).permute(0, 1, 3, 2, 4, 5).reshape(2, H // 2, W // 2, 32)
+        assert torch.equal(out3, out) and torch.equal(z.permute(0, 2, 3, 1), zr)
