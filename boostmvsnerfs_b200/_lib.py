@@ -126,7 +126,7 @@ class Conv3dParams(C.Structure):
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("relu", i32),
                 ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64),
                 ("out2", C.c_void_p), ("o2_n_stride", i64), ("o2_d_stride", i64), ("o2_y_stride", i64),
-                ("o2_x_stride", i64), ("split", i32), ("stride", i32)]
+                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32)]
 
 
 class ConvT3dParams(C.Structure):

@@ -72,7 +72,7 @@ struct ConvTile {
   static constexpr int JOBS = (TD / Cfg::WD) * (TW / 16);
 };
 
-template <int CIN, int NTILES>
+template <int CIN, int NTILES, bool IN_HALF>
 __global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILES == 1)) ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
   using T = ConvTile<CIN, NTILES>;
   using Cfg = ConvCfg<CIN, NTILES>;
@@ -94,6 +94,47 @@ __global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILE
   const int td = b % tiles_d; b /= tiles_d;
   const int n = b;
   const int x0 = tw * T::TW, y0 = th * TH, d0 = td * T::TD;
+  if (IN_HALF) {
+    // ---- fp16 input: the staged tile is a straight copy, 16 bytes (8 channels) per lane per pass
+    const __half* xin = reinterpret_cast<const __half*>(p.x) + (int64_t)n * p.x_n_stride;
+    constexpr int CH8 = CIN / 8;                                        // 16-byte chunks per voxel
+    constexpr int PER_ROW = T::ROWV * CH8;
+    constexpr int ROWS = T::HD * T::HH;
+    constexpr int P = (PER_ROW + 31) / 32;
+    constexpr int VPP = 32 / CH8;
+    constexpr int RB = 4;                                               // rows in flight per warp
+    const int sl = threadIdx.x & 31, sw = threadIdx.x >> 5;
+    const int c8 = sl % CH8, hx0 = sl / CH8;
+    const int64_t lane_off = (int64_t)(x0 - 1 + hx0) * p.x_x_stride + c8 * 8, pass_off = (int64_t)VPP * p.x_x_stride;
+    for (int row = sw; row < ROWS; row += RB * kConvWarps) {
+      uint4 val[RB][P];
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+        const int r = row + rr * kConvWarps;
+        const int hd = r / T::HH, hy = r - hd * T::HH;
+        const int gy = y0 + hy - 1, gd = d0 + hd - 1;
+        const bool row_ok = r < ROWS && gy >= 0 && gy < p.H && gd >= 0 && gd < p.D;
+        const __half* src = xin + (int64_t)gd * p.x_d_stride + (int64_t)gy * p.x_y_stride + lane_off;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int hx = hx0 + VPP * k, gx = x0 - 1 + hx;
+          val[rr][k] = make_uint4(0u, 0u, 0u, 0u);
+          if (row_ok && hx < T::HW && gx >= 0 && gx < p.W) val[rr][k] = __ldg(reinterpret_cast<const uint4*>(src + k * pass_off));
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+        const int r = row + rr * kConvWarps;
+        if (r < ROWS) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            const int hx = hx0 + VPP * k;
+            if (hx < T::ROWV) *reinterpret_cast<uint4*>(tile + r * T::ROWB + hx * Cfg::VS + ((c8 ^ Cfg::swz(hx)) << 4)) = val[rr][k];
+          }
+        }
+      }
+    }
+  } else
   // ---- stage the input tile with halo as fp16.  One warp per staged row (a contiguous run of float4 in
   // channels-last memory): lane l covers float4 l, l+32, ... of the row, so its channel chunk c4 is fixed,
   // its voxel advances by 32/CH4 per pass, and everything row-dependent is warp-uniform.
@@ -402,15 +443,15 @@ static int launch_conv_s2(const bmv_conv3d_params& p, cudaStream_t st) {
   return check_launch("bmv_conv3d_k3");
 }
 
-template <int CIN, int NTILES>
-static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
+template <int CIN, int NTILES, bool IN_HALF>
+static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st) {
   using T = ConvTile<CIN, NTILES>;
   const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -418,8 +459,13 @@ static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
     configured = true;
   }
   const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
-  conv3d_k3_mma_kernel<CIN, NTILES><<<(unsigned)blocks, kConvThreads, smem, st>>>(p);
+  conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF><<<(unsigned)blocks, kConvThreads, smem, st>>>(p);
   return check_launch("bmv_conv3d_k3");
+}
+
+template <int CIN, int NTILES>
+static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
+  return p.in_half ? launch_conv_t<CIN, NTILES, true>(p, st) : launch_conv_t<CIN, NTILES, false>(p, st);
 }
 
 }  // namespace bmv
@@ -428,9 +474,13 @@ extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t st
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad size");
-  BMV_REQUIRE(p->x_x_stride % 4 == 0 && p->x_y_stride % 4 == 0 && p->x_d_stride % 4 == 0 && p->x_n_stride % 4 == 0 &&
-                  ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->wfrag & 15) == 0,
-              BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: input must be channels-last with 16-byte aligned voxels");
+  {
+    const int m = p->in_half ? 8 : 4;                                   // elements per 16 bytes
+    BMV_REQUIRE(p->x_x_stride % m == 0 && p->x_y_stride % m == 0 && p->x_d_stride % m == 0 && p->x_n_stride % m == 0 &&
+                    ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->wfrag & 15) == 0,
+                BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: input must be channels-last with 16-byte aligned voxels");
+    BMV_REQUIRE(!p->in_half || p->stride != 2, BMV_ERR_UNSUPPORTED_SHAPE, "bmv_conv3d_k3: fp16 input is stride-1 only");
+  }
   BMV_REQUIRE(!p->out2 || (p->split >= 1 && p->split < p->Cout), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad split");
   cudaStream_t st = (cudaStream_t)stream;
   BMV_REQUIRE(p->stride == 0 || p->stride == 1 || p->stride == 2, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride must be 1 or 2");

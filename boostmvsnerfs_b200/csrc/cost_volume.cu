@@ -49,6 +49,24 @@ template <>
 __device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// two fp32 values -> one 32-bit word of 16-bit outputs
+template <typename OutT>
+__device__ __forceinline__ uint32_t pack_out2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack_out2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack_out2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack_out2<float>(float a, float b) { return 0u; }   // never used (4-byte branch)
 
 // v1: one thread per voxel (flat index over D*h*w, x fastest -> coalesced planar stores),
 // S views x 4 taps gathered per channel straight from L2/L1.
@@ -152,10 +170,9 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume
   } else {
 #pragma unroll
     for (int q = 0; q < CPT; q += 4) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(var[q], var[q + 1]), hi = __floats2bfloat162_rn(var[q + 2], var[q + 3]);
       uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      pk.x = pack_out2<OutT>(var[q], var[q + 1]);
+      pk.y = pack_out2<OutT>(var[q + 2], var[q + 3]);
       *reinterpret_cast<uint2*>(out + q) = pk;
     }
   }
@@ -262,10 +279,9 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volum
     } else {
 #pragma unroll
       for (int q = 0; q < CPT; q += 4) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(var[q], var[q + 1]), hi = __floats2bfloat162_rn(var[q + 2], var[q + 3]);
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        pk.x = pack_out2<OutT>(var[q], var[q + 1]);
+        pk.y = pack_out2<OutT>(var[q + 2], var[q + 3]);
         *reinterpret_cast<uint2*>(out + q) = pk;
       }
     }
@@ -357,10 +373,9 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
         if constexpr (sizeof(OutT) == 4) {
           *reinterpret_cast<float4*>(out) = var;
         } else {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(var.x, var.y), hi = __floats2bfloat162_rn(var.z, var.w);
           uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          pk.x = pack_out2<OutT>(var.x, var.y);
+          pk.y = pack_out2<OutT>(var.z, var.w);
           *reinterpret_cast<uint2*>(out) = pk;
         }
       }
@@ -496,7 +511,10 @@ extern "C" BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_
   BMV_REQUIRE((int64_t)p->Hs * llabs(p->feat_y_stride) + (int64_t)p->Ws * llabs(p->feat_x_stride) < (1ll << 31),
               BMV_ERR_UNSUPPORTED_SHAPE, "bmv_cost_volume_var: source map too large for 32-bit tap offsets");
   cudaStream_t st = (cudaStream_t)stream;
-  return p->out_bf16 ? launch_cost_volume<__nv_bfloat16>(*p, st) : launch_cost_volume<float>(*p, st);
+  BMV_REQUIRE(p->out_bf16 >= 0 && p->out_bf16 <= 2, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var: out_bf16 must be 0, 1 or 2");
+  if (p->out_bf16 == 1) return launch_cost_volume<__nv_bfloat16>(*p, st);
+  if (p->out_bf16 == 2) return launch_cost_volume<__half>(*p, st);
+  return launch_cost_volume<float>(*p, st);
 }
 
 extern "C" BMV_API int bmv_depth_planes_first(const bmv_depth_planes_first_params* p, bmv_stream_t stream) {

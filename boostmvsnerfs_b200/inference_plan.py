@@ -119,7 +119,7 @@ class MergedHeadsCostReg(nn.Module):
 
     def _use_tensor_core_convs(self, x):
         from .mlp_pack import CONV3D_K3_SHAPES
-        return (self.tensor_core_convs and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+        return (self.tensor_core_convs and x.is_cuda and x.dtype in (torch.float32, torch.float16) and x.stride(1) == 1
                 and torch.backends.cudnn.allow_tf32 and x.shape[1] in CONV3D_K3_SHAPES
                 and isinstance(self.net.conv0.bn, nn.Identity))
 

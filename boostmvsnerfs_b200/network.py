@@ -238,10 +238,17 @@ class EnerfNetwork(nn.Module):
             f = feats[f'level_{i}']
             C = f.shape[1]
             with self._stage(f'cost_volume_l{i}'):
+                # When conv0 of the regulariser runs on libbmv's tensor-core kernel its operands are rounded to
+                # fp16 anyway: K1 then emits the volume in fp16 (same result, half the write + read traffic).
+                plan = self._kept(f'cost_reg_{i}')
+                vdt = torch.float32
+                if self.channels_last and dev.type == 'cuda' and getattr(plan, 'tensor_core_convs', False) \
+                        and torch.backends.cudnn.allow_tf32 and C in (16, 32):
+                    vdt = torch.float16
                 if self.channels_last:
-                    vols = torch.empty((K, D, h, w, C), device=dev).permute(0, 4, 1, 2, 3)
+                    vols = torch.empty((K, D, h, w, C), device=dev, dtype=vdt).permute(0, 4, 1, 2, 3)
                 else:
-                    vols = torch.empty((K, C, D, h, w), device=dev)
+                    vols = torch.empty((K, C, D, h, w), device=dev, dtype=vdt)
                 if depth is None:
                     planes0, nf0 = ops.depth_planes_first(near_far, D, h, w, rc.depth_inv[i])
                     planes = [planes0] * K

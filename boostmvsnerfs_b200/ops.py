@@ -110,10 +110,10 @@ def _cost_volume_launch(p, Cc, D, h, w, device, out, out_dtype, channels_last):
             out = torch.empty((D, h, w, Cc), device=device, dtype=out_dtype).permute(3, 0, 1, 2)
         else:
             out = torch.empty((Cc, D, h, w), device=device, dtype=out_dtype)
-    assert out.shape == (Cc, D, h, w) and out.dtype in (torch.float32, torch.bfloat16)
+    assert out.shape == (Cc, D, h, w) and out.dtype in (torch.float32, torch.bfloat16, torch.float16)
     p.out = out.data_ptr()
     p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride()
-    p.out_bf16 = 1 if out.dtype == torch.bfloat16 else 0
+    p.out_bf16 = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out.dtype]
     _lib.call("bmv_cost_volume_var", p, _stream())
     return out
 
@@ -609,8 +609,10 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
     on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
     lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
     returns (N,cout,D,H,W) channels_last_3d (or writes `out`, any voxel-major strides).  With `out2`
-    (N,cout-split,D,H,W) channels >= split go there instead (`out` then holds `split` channels)."""
-    _f32(x, "x")
+    (N,cout-split,D,H,W) channels >= split go there instead (`out` then holds `split` channels).
+    x may also be float16 (the operands are rounded to fp16 anyway: same result, half the read traffic)."""
+    if not (x.is_cuda and x.dtype in (torch.float32, torch.float16)):
+        raise BmvError(f"conv3d_k3: x must be a CUDA float32/float16 tensor, got {x.dtype} on {x.device}")
     N, Cin, D, H, W = x.shape
     if x.stride(1) != 1:
         raise BmvError("conv3d_k3: x must be channels_last_3d")
@@ -630,6 +632,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
     p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
     p.N, p.D, p.H, p.W, p.Cin, p.Cout, p.relu = N, D, H, W, Cin, cout, int(bool(relu))
     p.stride = stride
+    p.in_half = int(x.dtype == torch.float16)
     p.out = out.data_ptr()
     p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
     if out2 is not None:

@@ -80,7 +80,7 @@ typedef struct bmv_cost_volume_params {
   int32_t D, h, w;              /* volume size */
   float* out;                   /* (C,D,h,w) with the strides below */
   int64_t out_c_stride, out_d_stride, out_y_stride, out_x_stride;
-  int32_t out_bf16;             /* 0: fp32 out, 1: out points to bf16 storage (round-to-nearest-even) */
+  int32_t out_bf16;             /* 0: fp32 out, 1: out points to bf16 storage, 2: fp16 storage (round-to-nearest-even) */
   int32_t exact_coords;         /* 1: reproduce the reference's coordinate arithmetic op for op (IEEE divisions,
                                    slower); 0: reciprocal-multiply form, coordinates within 2 ulp (default) */
 } bmv_cost_volume_params;
@@ -342,6 +342,8 @@ typedef struct bmv_conv3d_params {
   int32_t split;                /* with out2: channel c >= split is written to out2 at channel c - split */
   int32_t stride;               /* 0/1: stride 1.  2: stride-2 convolution (Cin=8, Cout<=16; ConvBnReLU3D(8,16,stride=2),
                                    cost_reg_net.py:14,53), out is (N, (D-1)/2+1, (H-1)/2+1, (W-1)/2+1, Cout) */
+  int32_t in_half;              /* 1: x points to fp16 storage (strides in fp16 elements, multiples of 8); stride 1 only.
+                                   The operands are rounded to fp16 in any case, so results are identical. */
 } bmv_conv3d_params;
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);
