@@ -442,6 +442,8 @@ def main_ours(args):
         if not ts or per_frame % len(names):
             continue
         per_name = per_frame // len(names)
+        for nm in names:
+            launches_per_stage[nm] = per_name              # chain-batched kernels launch once per level
         for f in range(args.steps):
             for j, nm in enumerate(names):
                 per_kernel.setdefault(nm, []).extend(ts[f * per_frame + j * per_name:f * per_frame + (j + 1) * per_name])

@@ -38,14 +38,16 @@ class DepthPlanesFirstParams(C.Structure):
 class DepthPlanesNextParams(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("std", C.c_void_p), ("near_far", C.c_void_p), ("t", C.c_void_p),
                 ("h0", i32), ("w0", i32), ("h", i32), ("w", i32), ("D", i32), ("cur_inv", i32),
-                ("planes", C.c_void_p), ("near_far_out", C.c_void_p)]
+                ("planes", C.c_void_p), ("near_far_out", C.c_void_p),
+                ("batch", i32), ("depth_b_stride", i64), ("std_b_stride", i64), ("nf_b_stride", i64)]
 
 
 class DepthRegressionParams(C.Structure):
     _fields_ = [("logits", C.c_void_p), ("planes", C.c_void_p),
                 ("planes_d_stride", i64), ("planes_pix_stride", i64),
                 ("D", i32), ("h", i32), ("w", i32), ("depth_inv", i32),
-                ("depth", C.c_void_p), ("std", C.c_void_p)]
+                ("depth", C.c_void_p), ("std", C.c_void_p),
+                ("batch", i32), ("logits_b_stride", i64), ("planes_b_stride", i64)]
 
 
 class RaygenFetchParams(C.Structure):

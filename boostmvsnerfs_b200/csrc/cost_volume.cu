@@ -413,6 +413,11 @@ __global__ void depth_planes_next_kernel(bmv_depth_planes_next_params p) {
   const int x = i % p.w, y = i / p.w;
   UpCoord uy = up_coord(y, p.h0, p.h), ux = up_coord(x, p.w0, p.w);
   const int hw0 = p.h0 * p.w0;
+  {
+    const int b = blockIdx.y;                                           // chain
+    p.depth += b * p.depth_b_stride; p.std += b * p.std_b_stride; p.near_far += b * p.nf_b_stride;
+    p.planes += (int64_t)b * p.D * hw; p.near_far_out += (int64_t)b * 2 * hw;
+  }
   float dep = up_sample(p.depth, p.w0, uy, ux);
   float sd = up_sample(p.std, p.w0, uy, ux);
   float nf0 = up_sample(p.near_far, p.w0, uy, ux);
@@ -533,7 +538,8 @@ extern "C" BMV_API int bmv_depth_planes_next(const bmv_depth_planes_next_params*
               BMV_ERR_INVALID_ARGUMENT, "bmv_depth_planes_next: null pointer");
   BMV_REQUIRE(p->D >= 1 && p->h >= 1 && p->w >= 1 && p->h0 >= 1 && p->w0 >= 1, BMV_ERR_INVALID_ARGUMENT,
               "bmv_depth_planes_next: bad size");
+  BMV_REQUIRE(p->batch >= 0 && p->batch <= 65535, BMV_ERR_INVALID_ARGUMENT, "bmv_depth_planes_next: bad batch");
   int n = p->h * p->w;
-  depth_planes_next_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p);
+  depth_planes_next_kernel<<<dim3((n + 255) / 256, p->batch > 1 ? p->batch : 1), 256, 0, (cudaStream_t)stream>>>(*p);
   return check_launch("bmv_depth_planes_next");
 }

@@ -11,8 +11,10 @@ __global__ void __launch_bounds__(256) depth_regression_kernel(bmv_depth_regress
   const int hw = p.h * p.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw) return;
-  const float* lg = p.logits + i;
-  const float* pl = p.planes + (int64_t)i * p.planes_pix_stride;
+  const int b = blockIdx.y;                                             // chain
+  const float* lg = p.logits + b * p.logits_b_stride + i;
+  const float* pl = p.planes + b * p.planes_b_stride + (int64_t)i * p.planes_pix_stride;
+  p.depth += (int64_t)b * hw; p.std += (int64_t)b * hw;
   float m = -INFINITY;
   for (int d = 0; d < p.D; ++d) m = fmaxf(m, __ldg(lg + (int64_t)d * hw));
   float den = 0.f;
@@ -44,8 +46,10 @@ __global__ void __launch_bounds__(128) depth_regression_reg_kernel(bmv_depth_reg
   const int hw = p.h * p.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw) return;
-  const float* lg = p.logits + i;
-  const float* pl = p.planes + (int64_t)i * p.planes_pix_stride;
+  const int b = blockIdx.y;                                             // chain
+  const float* lg = p.logits + b * p.logits_b_stride + i;
+  const float* pl = p.planes + b * p.planes_b_stride + (int64_t)i * p.planes_pix_stride;
+  p.depth += (int64_t)b * hw; p.std += (int64_t)b * hw;
   float e[D], v[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) e[d] = __ldg(lg + (int64_t)d * hw);
@@ -81,14 +85,17 @@ extern "C" BMV_API int bmv_depth_regression(const bmv_depth_regression_params* p
   BMV_REQUIRE(p && p->logits && p->planes && p->depth && p->std, BMV_ERR_INVALID_ARGUMENT,
               "bmv_depth_regression: null pointer");
   BMV_REQUIRE(p->D >= 1 && p->h >= 1 && p->w >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_depth_regression: bad size");
+  BMV_REQUIRE(p->batch >= 0 && p->batch <= 65535, BMV_ERR_INVALID_ARGUMENT, "bmv_depth_regression: bad batch");
   const int hw = p->h * p->w;
+  const unsigned nb = p->batch > 1 ? (unsigned)p->batch : 1u;
   cudaStream_t st = (cudaStream_t)stream;
+  const dim3 g128((hw + 127) / 128, nb), g256((hw + 255) / 256, nb);
   switch (p->D) {
-    case 8: depth_regression_reg_kernel<8><<<(hw + 127) / 128, 128, 0, st>>>(*p); break;
-    case 16: depth_regression_reg_kernel<16><<<(hw + 127) / 128, 128, 0, st>>>(*p); break;
-    case 32: depth_regression_reg_kernel<32><<<(hw + 127) / 128, 128, 0, st>>>(*p); break;
-    case 64: depth_regression_reg_kernel<64><<<(hw + 127) / 128, 128, 0, st>>>(*p); break;
-    default: depth_regression_kernel<<<(hw + 255) / 256, 256, 0, st>>>(*p);
+    case 8: depth_regression_reg_kernel<8><<<g128, 128, 0, st>>>(*p); break;
+    case 16: depth_regression_reg_kernel<16><<<g128, 128, 0, st>>>(*p); break;
+    case 32: depth_regression_reg_kernel<32><<<g128, 128, 0, st>>>(*p); break;
+    case 64: depth_regression_reg_kernel<64><<<g128, 128, 0, st>>>(*p); break;
+    default: depth_regression_kernel<<<g256, 256, 0, st>>>(*p);
   }
   return check_launch("bmv_depth_regression");
 }

@@ -251,29 +251,28 @@ class EnerfNetwork(nn.Module):
                     vols = torch.empty((K, C, D, h, w), device=dev, dtype=vdt)
                 if depth is None:
                     planes0, nf0 = ops.depth_planes_first(near_far, D, h, w, rc.depth_inv[i])
-                    planes = [planes0] * K
-                    nf = [nf0] * K
+                    planes = planes0                       # shared (D,)
+                    nf = nf0                               # shared (2,h,w)
                     for k in range(K):
                         ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
-                else:
-                    planes, nf_new = [], []
+                else:                                      # all K chains' hypotheses in one launch
+                    planes, nf = ops.depth_planes_next_batched(depth, std, nf, D, h, w, rc.depth_inv[i])
                     for k in range(K):
-                        pl, nfk = ops.depth_planes_next(depth[k], std[k], nf[k], D, h, w, rc.depth_inv[i])
-                        planes.append(pl)
-                        nf_new.append(nfk)
-                        ops.cost_volume_var(f, triples[k], projs[i], pl, out=vols[k])
-                    nf = nf_new
+                        ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k])
             with self._stage(f'cost_reg_{i}'):
                 feat_vol, logits = self._kept(f'cost_reg_{i}')(vols)
                 del vols
             with self._stage(f'depth_regression_l{i}'):
-                depth, std = [], []
-                for k in range(K):
-                    d, s = ops.depth_regression(logits[k], planes[k], rc.depth_inv[i])
-                    depth.append(d)
-                    std.append(s)
+                if logits.stride(-1) == 1 and logits.stride(-2) == w and logits.stride(-3) == h * w:
+                    depth, std = ops.depth_regression_batched(logits, planes, rc.depth_inv[i])   # (K,h,w) each
+                else:
+                    dl, sl = zip(*[ops.depth_regression(logits[k], planes if planes.dim() == 1 else planes[k],
+                                                        rc.depth_inv[i]) for k in range(K)])
+                    depth, std = torch.stack(dl), torch.stack(sl)
             if rc.render_if[i]:
-                states[i] = {'feat_vol': feat_vol, 'depth': depth, 'std': std, 'nf': nf}
+                nf_k = [nf[k] for k in range(K)] if nf.dim() == 4 else [nf] * K
+                states[i] = {'feat_vol': feat_vol, 'depth': [depth[k] for k in range(K)],
+                             'std': [std[k] for k in range(K)], 'nf': nf_k}
         return states
 
     def _render_level(self, i, feats, inps, state, rays, cams, triples, Hh, Ww, ray_begin=0, n_rays=None):

@@ -152,6 +152,51 @@ def depth_planes_next(depth, std, near_far, D, h, w, cur_inv):
     return planes, nf
 
 
+def depth_planes_next_batched(depth, std, near_far, D, h, w, cur_inv):
+    """All K chains in one launch: depth/std (K,h0,w0), near_far (K,2,h0,w0) or shared (2,h0,w0)
+    -> planes (K,D,h,w), near_far_out (K,2,h,w)."""
+    depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
+    dev = depth.device
+    K, h0, w0 = depth.shape
+    t = _linspace(D, dev)
+    planes = torch.empty((K, D, h, w), device=dev)
+    nf = torch.empty((K, 2, h, w), device=dev)
+    p = _lib.DepthPlanesNextParams()
+    p.depth, p.std, p.near_far, p.t = depth.data_ptr(), std.data_ptr(), near_far.data_ptr(), t.data_ptr()
+    p.h0, p.w0, p.h, p.w, p.D, p.cur_inv = h0, w0, h, w, D, int(cur_inv)
+    p.planes, p.near_far_out = planes.data_ptr(), nf.data_ptr()
+    p.batch, p.depth_b_stride, p.std_b_stride = K, h0 * w0, h0 * w0
+    p.nf_b_stride = 2 * h0 * w0 if near_far.dim() == 4 else 0
+    _lib.call("bmv_depth_planes_next", p, _stream())
+    return planes, nf
+
+
+def depth_regression_batched(logits, planes, depth_inv):
+    """All K chains in one launch: logits (K,D,h,w) (any chain stride, planar within a chain); planes (K,D,h,w),
+    or shared (D,) -> depth (K,h,w), std (K,h,w)."""
+    _f32(logits, "logits")
+    planes = _cf32(planes, "planes")
+    K, D, h, w = logits.shape
+    if tuple(logits.stride()[1:]) != (h * w, w, 1):
+        raise BmvError("depth_regression_batched: each chain's logits must be planar-contiguous")
+    dev = logits.device
+    depth = torch.empty((K, h, w), device=dev)
+    std = torch.empty((K, h, w), device=dev)
+    p = _lib.DepthRegressionParams()
+    p.logits, p.planes = logits.data_ptr(), planes.data_ptr()
+    if planes.dim() == 1:
+        assert planes.numel() == D
+        p.planes_d_stride, p.planes_pix_stride, p.planes_b_stride = 1, 0, 0
+    else:
+        assert planes.shape == (K, D, h, w)
+        p.planes_d_stride, p.planes_pix_stride, p.planes_b_stride = h * w, 1, D * h * w
+    p.D, p.h, p.w, p.depth_inv = D, h, w, int(depth_inv)
+    p.batch, p.logits_b_stride = K, logits.stride(0)
+    p.depth, p.std = depth.data_ptr(), std.data_ptr()
+    _lib.call("bmv_depth_regression", p, _stream())
+    return depth, std
+
+
 # ------------------------------------------------------------------------------------------ K2
 def depth_regression(logits, planes, depth_inv):
     """logits (D,h,w); planes (D,h,w) or (D,) -> depth (h,w), std (h,w)

@@ -111,6 +111,10 @@ typedef struct bmv_depth_planes_next_params {
   int32_t h0, w0, h, w, D, cur_inv;
   float* planes;                /* (D,h,w) */
   float* near_far_out;          /* (2,h,w) */
+  /* batch > 1: `batch` chains in one launch; chain b reads depth + b*depth_b_stride, std + b*std_b_stride,
+   * near_far + b*nf_b_stride (0 = shared) and writes planes + b*D*h*w, near_far_out + b*2*h*w.  0/1 = single. */
+  int32_t batch;
+  int64_t depth_b_stride, std_b_stride, nf_b_stride;
 } bmv_depth_planes_next_params;
 BMV_API int bmv_depth_planes_next(const bmv_depth_planes_next_params* p, bmv_stream_t stream);
 
@@ -125,6 +129,10 @@ typedef struct bmv_depth_regression_params {
   int32_t D, h, w, depth_inv;
   float* depth;                 /* (h,w) */
   float* std;                   /* (h,w) */
+  /* batch > 1: `batch` chains in one launch; chain b reads logits + b*logits_b_stride and planes +
+   * b*planes_b_stride (0 = shared) and writes depth + b*h*w, std + b*h*w.  0/1 = single. */
+  int32_t batch;
+  int64_t logits_b_stride, planes_b_stride;
 } bmv_depth_regression_params;
 BMV_API int bmv_depth_regression(const bmv_depth_regression_params* p, bmv_stream_t stream);
 

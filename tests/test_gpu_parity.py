@@ -397,6 +397,33 @@ def test_fused_render_matches_unfused_path(ops, g):
     exact(part["raw"], f["raw"][1000:1777], "ray sub-range")
 
 
+def test_chain_batched_planes_and_depth_regression_equal_per_chain_launches(ops):
+    """bmv_depth_planes_next / bmv_depth_regression with batch = K: bit-identical to K single launches."""
+    torch.manual_seed(9)
+    K, D, h0, w0, h, w = 3, 8, 17, 30, 34, 60
+    depth = torch.rand(K, h0, w0, device="cuda") * 0.5 + 0.5
+    std = torch.rand(K, h0, w0, device="cuda") * 0.05
+    nf_shared = torch.stack([torch.full((h0, w0), 1.2, device="cuda"), torch.full((h0, w0), 0.3, device="cuda")])
+    nf_each = nf_shared[None].repeat(K, 1, 1, 1) * (1 + 0.1 * torch.rand(K, 1, 1, 1, device="cuda"))
+    for nf in (nf_shared, nf_each):
+        planes, nfo = ops.depth_planes_next_batched(depth, std, nf, D, h, w, False)
+        for k in range(K):
+            pk, nk = ops.depth_planes_next(depth[k], std[k], nf if nf.dim() == 3 else nf[k], D, h, w, False)
+            exact(planes[k], pk, "batched planes")
+            exact(nfo[k], nk, "batched near/far")
+    logits = torch.randn(K, D, h, w, device="cuda")
+    for pl in (planes, torch.linspace(0.5, 2.0, D, device="cuda")):
+        d, s_ = ops.depth_regression_batched(logits, pl, False)
+        for k in range(K):
+            dk, sk = ops.depth_regression(logits[k], pl if pl.dim() == 1 else pl[k], False)
+            exact(d[k], dk, "batched depth")
+            exact(s_[k], sk, "batched std")
+    # chain stride larger than D*h*w (a channel slice of a wider tensor)
+    wide = torch.randn(K, 2, D, h, w, device="cuda")
+    d2, _ = ops.depth_regression_batched(wide[:, 1], planes, False)
+    exact(d2[1], ops.depth_regression(wide[1, 1], planes[1], False)[0], "strided chains")
+
+
 # ------------------------------------------------------------------------------------------ FPN fusion
 @pytest.mark.parametrize("cin,hw", [(8, (64, 96)), (16, (34, 50))])
 def test_fpn_topdown_vs_torch(ops, cin, hw):
