@@ -71,8 +71,15 @@ __device__ __forceinline__ bool coord_ok(float v) { return fabsf(v) < 1.0e9f; } 
 // align_corners=True bilinear upsample source position (ATen upsample_bilinear2d):
 // scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, i1 = i0 + (i0 < in-1), lambda = src-i0.
 struct UpCoord { int i0, i1; float l0, l1; };
+__device__ __forceinline__ float up_scale(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+__device__ __forceinline__ UpCoord up_coord_scaled(int dst, int in_size, float scale);
 __device__ __forceinline__ UpCoord up_coord(int dst, int in_size, int out_size) {
-  float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  return up_coord_scaled(dst, in_size, up_scale(in_size, out_size));
+}
+// same with the (loop-invariant) scale hoisted by the caller
+__device__ __forceinline__ UpCoord up_coord_scaled(int dst, int in_size, float scale) {
   float src = mul_rn(scale, (float)dst);
   UpCoord u;
   u.i0 = (int)src;

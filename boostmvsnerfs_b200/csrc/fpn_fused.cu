@@ -50,6 +50,12 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
     float* mid = p.mid ? p.mid + (int64_t)n * p.H * p.W * 32 : nullptr;
     const int cg = threadIdx.x & 7;
     const float4 bb = *reinterpret_cast<const float4*>(sW + 32 * CIN + cg * 4);
+    // the lane's 4 x CIN lateral weights live in registers: as shared-memory operands (one LDS.128 per input
+    // channel per item, 4 wavefronts each) they were 47 % of the L1 data-pipe wavefronts of this kernel (ncu)
+    float4 wreg[CIN];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) wreg[i] = *reinterpret_cast<const float4*>(sW + i * 32 + cg * 4);
+    const float sy = up_scale(Hp, p.H), sx = up_scale(Wp, p.W);
     for (int pi = threadIdx.x >> 3; pi < kFfHY * kFfHX; pi += kFfThreads / 8) {
       const int hy = pi / kFfHX, hx = pi - hy * kFfHX;
       const int y = y0 + hy - 1, x = x0 + hx - 1;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
           const float4 tt = __ldg(reinterpret_cast<const float4*>(in + i));
           v[i] = tt.x; v[i + 1] = tt.y; v[i + 2] = tt.z; v[i + 3] = tt.w;
         }
-        const UpCoord uy = up_coord(y, Hp, p.H), ux = up_coord(x, Wp, p.W);
+        const UpCoord uy = up_coord_scaled(y, Hp, sy), ux = up_coord_scaled(x, Wp, sx);
         const float* pb = prev + cg * 4;
         const float4 a = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)uy.i0 * Wp + ux.i0) * 32));
         const float4 b = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)uy.i0 * Wp + ux.i1) * 32));
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
         float acc[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
         for (int i = 0; i < CIN; ++i) {
-          const float4 w = *reinterpret_cast<const float4*>(sW + i * 32 + cg * 4);
+          const float4 w = wreg[i];
           acc[0] = fmaf(w.x, v[i], acc[0]); acc[1] = fmaf(w.y, v[i], acc[1]);
           acc[2] = fmaf(w.z, v[i], acc[2]); acc[3] = fmaf(w.w, v[i], acc[3]);
         }
