@@ -245,6 +245,7 @@ class EnerfNetwork(nn.Module):
                 if self.channels_last and dev.type == 'cuda' and getattr(plan, 'tensor_core_convs', False) \
                         and torch.backends.cudnn.allow_tf32 and C in (16, 32):
                     vdt = torch.float16
+                self.last_volume_dtype = vdt
                 if self.channels_last:
                     vols = torch.empty((K, D, h, w, C), device=dev, dtype=vdt).permute(0, 4, 1, 2, 3)
                 else:
