@@ -21,9 +21,12 @@
 // A CTA stages an (8+2)x(TH+2)x(32+2) input tile as fp16 in shared memory (zero outside the volume = the
 // convolution's padding).  A warp owns WD x TH x 16 output voxels and walks the INPUT rows: each A
 // fragment (one ldmatrix.x4) is used for every (dz,dy) whose output row the warp owns, so shared-memory
-// traffic per MMA drops ~3x against a per-output-tile loop; weights (host-arranged B fragments) stay in
-// registers when they fit.  Bias + ReLU are fused in the epilogue; channels >= `split` can go to a
-// second tensor (the depth logits of the merged heads).
+// traffic per MMA drops ~3x against a per-output-tile loop; weights are host-arranged B fragments read from
+// shared memory (register-resident weights cost a CTA of occupancy: 151 vs 145 us on conv0 of level 1, so the
+// BREG switch of ConvCfg is off everywhere).  The input may be fp32 (converted while staging, one warp per
+// staged row) or fp16 (K1 emits the cost volume in fp16 for this kernel: the staged tile is a straight copy).
+// Bias + ReLU are fused in the epilogue; channels >= `split` can go to a second tensor (the depth logits of
+// the merged heads).
 #include <cuda_fp16.h>
 
 #include "bmv_internal.cuh"
