@@ -73,21 +73,60 @@ class FrameGraph:
         entry["graph"] = g
         return entry
 
+    def prefetch(self, batch):
+        """Start uploading the NEXT frame's host batch on a copy stream while the current frame renders.
+        The following __call__ with the same batch object only does a device-to-device copy of the staged
+        tensors before the replay.  No-op until the graph for this batch signature exists."""
+        triples = self._triples(batch)
+        entry = self._cache.get(self._key(batch, triples))
+        if entry is None:
+            return
+        if "stage" not in entry:
+            entry["stage"] = {k: torch.empty_like(t) for k, t in entry["static"].items()}
+            entry["copy_stream"] = torch.cuda.Stream(device=entry["cam_dev"].device)
+            entry["ev_staged"], entry["ev_consumed"] = torch.cuda.Event(), torch.cuda.Event()
+            entry["ev_consumed"].record()
+        cs = entry["copy_stream"]
+        cs.wait_event(entry["ev_consumed"])                 # the previous staged frame has been copied out
+        with torch.cuda.stream(cs):
+            for k, t in entry["stage"].items():
+                t.copy_(batch[k], non_blocking=True)
+            entry["ev_staged"].record(cs)
+        entry["staged_for"] = batch
+
     def _load(self, entry, batch):
         net = self.net
         st = entry["static"]
-        for k, t in st.items():
-            t.copy_(batch[k], non_blocking=True)
+        if entry.get("staged_for") is batch:                # uploaded by prefetch(): device-to-device only
+            torch.cuda.current_stream().wait_event(entry["ev_staged"])
+            for k, t in st.items():
+                t.copy_(entry["stage"][k], non_blocking=True)
+            entry["ev_consumed"].record()
+            entry["staged_for"] = None
+        else:
+            for k, t in st.items():
+                t.copy_(batch[k], non_blocking=True)
         N = st["all_src_inps"].shape[1]
         cams = [batch[k] for k in ("all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt")]
         if all(c.device.type == "cpu" for c in cams):
             flat = torch.cat([c.reshape(-1) for c in cams])
         else:
+            # device-resident cameras: reading them back costs a host sync per frame; the same (unmodified)
+            # tensors as last time mean the camera block already on the device is still valid
+            sig = tuple((c.data_ptr(), c._version, c.device) for c in cams)
+            if entry.get("cam_sig") == sig:
+                return
+            entry["cam_sig"] = sig
             flat = torch.cat([c.reshape(-1).to(st["near_far"].device) for c in cams]).cpu()
+        # the pinned camera buffers are re-used every frame: wait until the previous frame's upload has executed
+        # before overwriting them (the host may run a frame ahead of the GPU)
+        if "cam_ev" in entry:
+            entry["cam_ev"].synchronize()
         entry["cam_host"].copy_(net._camera_host(flat, N))
         entry["cam_dev"].copy_(entry["cam_host"], non_blocking=True)
         entry["gen_host"].copy_(net._raygen_host(flat, N))
         entry["gen_dev"].copy_(entry["gen_host"], non_blocking=True)
+        entry.setdefault("cam_ev", torch.cuda.Event()).record()
 
     def __call__(self, batch):
         """batch: tensors on the GPU or in (pinned) host memory; B must be 1.  Returns the output dict;
