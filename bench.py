@@ -268,7 +268,9 @@ def workload_config(name, wl):
     return {"workload": f"{name}: ENeRF + BoostMVSNeRFs K={wl['K']} cost volumes, {wl['W']}x{wl['H']} "
                         f"(960x540 padded to /32 for C2), N={wl['n_views']} source views, 3 views per volume, "
                         "levels (64 planes @1/8, 8 planes @1/2), 2 samples/ray, random-init weights",
-            "e2e_inputs": "pinned host: N source images + cameras + near/far; rays generated on device",
+            "e2e_inputs": "pinned host: N source images + cameras + near/far, uploaded every step (graph mode: on a copy "
+                          "stream while the previous frame renders, FrameGraph.prefetch); rays generated on device; "
+                          "rgb + depth read back to pinned host memory every step",
             "l2": "no explicit flush: one frame streams ~3 GB through HBM (volumes 4x67 MB per level, fetched "
                   "features 4x221 MB), far above the 126 MB L2",
             "timing": "CUDA events on the launch stream around exactly `steps` frames, max over ranks"}
