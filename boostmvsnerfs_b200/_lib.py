@@ -128,7 +128,7 @@ class Conv3dParams(C.Structure):
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("relu", i32),
                 ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64),
                 ("out2", C.c_void_p), ("o2_n_stride", i64), ("o2_d_stride", i64), ("o2_y_stride", i64),
-                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32)]
+                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32), ("no_tma", i32)]
 
 
 class ConvT3dParams(C.Structure):
@@ -175,7 +175,7 @@ ENTRY_POINTS = {
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",
-                 "bmv_conv3d_k3_weight_words", "bmv_convT3d_k3s2_weight_words",
+                 "bmv_conv3d_k3_weight_words", "bmv_conv3d_k3_last_used_tma", "bmv_convT3d_k3s2_weight_words",
                  "bmv_fpn_topdown_smooth_weight_words")
 
 _lib = None
@@ -204,6 +204,7 @@ def load():
     lib.bmv_render_rays_supported.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.bmv_conv3d_k3_weight_words.restype = C.c_int
     lib.bmv_conv3d_k3_weight_words.argtypes = [C.c_int, C.c_int]
+    lib.bmv_conv3d_k3_last_used_tma.restype = C.c_int
     lib.bmv_convT3d_k3s2_weight_words.restype = C.c_int
     lib.bmv_convT3d_k3s2_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_fpn_topdown_smooth_weight_words.restype = C.c_int

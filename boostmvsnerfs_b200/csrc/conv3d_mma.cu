@@ -27,6 +27,9 @@
 // staged row) or fp16 (K1 emits the cost volume in fp16 for this kernel: the staged tile is a straight copy).
 // Bias + ReLU are fused in the epilogue; channels >= `split` can go to a second tensor (the depth logits of
 // the merged heads).
+#include <cuda.h>
+
+#include <cstring>
 #include <cuda_fp16.h>
 
 #include "bmv_internal.cuh"
@@ -75,20 +78,42 @@ struct ConvTile {
   static constexpr int JOBS = (TD / Cfg::WD) * (TW / 16);
 };
 
-template <int CIN, int NTILES, bool IN_HALF>
-__global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILES == 1)) ? 3 : 2) conv3d_k3_mma_kernel(bmv_conv3d_params p) {
+// ---- TMA staging (fp16 input, Cin 16 / 32): ONE elected thread issues a 5-D tiled bulk-tensor copy of the whole
+// (10 x (TH+2) x 34 x Cin) halo tile; out-of-bounds coordinates (negative or past the volume) are zero-filled by the
+// TMA unit — that IS the convolution's padding — and the hardware 32B / 64B swizzle gives the same conflict-free
+// ldmatrix pattern as the manual swizzle of the register-staged path.  All threads wait on an mbarrier.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    if (spins > (1u << 24)) __trap();                                   // a faulted copy must not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t mbar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <int CIN, int NTILES, bool IN_HALF, bool TMA>
+__global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILES == 1)) ? 3 : 2)
+conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tmap) {
   using T = ConvTile<CIN, NTILES>;
   using Cfg = ConvCfg<CIN, NTILES>;
   constexpr int NT = Cfg::NT, KS = Cfg::KS, WD = Cfg::WD, TH = T::TH;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // the TMA destination must be 128-byte aligned: round the dynamic window up (the launcher allocates 128 B extra)
+  unsigned char* smem = smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
   unsigned char* tile = smem;
   const uint2* wfrag = reinterpret_cast<const uint2*>(smem + T::TILE_BYTES);
-  // ---- weights -> shared memory
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
-    uint4* dst = reinterpret_cast<uint4*>(smem + T::TILE_BYTES);
-    for (int i = threadIdx.x; i < T::W_WORDS / 4; i += kConvThreads) dst[i] = __ldg(src + i);
-  }
+  __shared__ __align__(8) uint64_t s_mbar;
   // ---- which output tile
   const int tiles_w = (p.W + T::TW - 1) / T::TW, tiles_h = (p.H + TH - 1) / TH, tiles_d = (p.D + T::TD - 1) / T::TD;
   int b = blockIdx.x;
@@ -97,7 +122,24 @@ __global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILE
   const int td = b % tiles_d; b /= tiles_d;
   const int n = b;
   const int x0 = tw * T::TW, y0 = th * TH, d0 = td * T::TD;
-  if (IN_HALF) {
+  if (TMA) {
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(mbar, (uint32_t)T::TILE_BYTES);
+      tma_load_5d((uint32_t)__cvta_generic_to_shared(tile), &tmap, mbar, 0, x0 - 1, y0 - 1, d0 - 1, n);
+    }
+  }
+  // ---- weights -> shared memory (overlaps the bulk copy on the TMA path)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
+    uint4* dst = reinterpret_cast<uint4*>(smem + T::TILE_BYTES);
+    for (int i = threadIdx.x; i < T::W_WORDS / 4; i += kConvThreads) dst[i] = __ldg(src + i);
+  }
+  if (TMA) {
+    mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0);
+  } else if (IN_HALF) {
     // ---- fp16 input: the staged tile is a straight copy, 16 bytes (8 channels) per lane per pass
     const __half* xin = reinterpret_cast<const __half*>(p.x) + (int64_t)n * p.x_n_stride;
     constexpr int CH8 = CIN / 8;                                        // 16-byte chunks per voxel
@@ -239,7 +281,15 @@ __global__ void __launch_bounds__(kConvThreads, (CIN == 8 || (CIN == 16 && NTILE
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
           uint32_t a[4];
-          ldmatrix_x4(a, aoff[j] + ((db + pd) * T::HH + py) * T::ROWB);
+          if (TMA) {
+            // dense [d][y][x][c] box written by the TMA unit with its 32B / 64B swizzle: 16-byte chunk index XOR
+            // address bits [7] (32B voxels) / [8:7] (64B voxels); the tile base is 1024-byte aligned
+            const uint32_t lin = tile_s + ((((db + pd) * T::HH + py) * T::HW) + mx * 16 + lrow + Cfg::step_voxel(j, lhi)) * Cfg::VS +
+                                 (Cfg::step_chunk(j, lhi) << 4);
+            ldmatrix_x4(a, lin ^ (((lin >> 7) & (Cfg::VS == 32 ? 1u : 3u)) << 4));
+          } else {
+            ldmatrix_x4(a, aoff[j] + ((db + pd) * T::HH + py) * T::ROWB);
+          }
 #pragma unroll
           for (int dz = 0; dz < 3; ++dz) {
             const int od = pd - dz;
@@ -446,15 +496,51 @@ static int launch_conv_s2(const bmv_conv3d_params& p, cudaStream_t st) {
   return check_launch("bmv_conv3d_k3");
 }
 
-template <int CIN, int NTILES, bool IN_HALF>
-static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st) {
+static thread_local int g_last_conv3d_tma = 0;      // which staging path the last stride-1 launch of this thread used (tests)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// 5-D map (C, W, H, D, N) of the fp16 channels-last input, box = one halo tile; false if the layout does not qualify
+template <int CIN, int NTILES>
+static bool make_input_map(const bmv_conv3d_params& p, CUtensorMap* map) {
   using T = ConvTile<CIN, NTILES>;
-  const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || !p.in_half || T::ROWV != T::HW) return false;
+  if (p.x_x_stride != CIN) return false;                                // voxels contiguous along x
+  const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+  const cuuint64_t strides[4] = {(cuuint64_t)p.x_x_stride * 2, (cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2,
+                                 (cuuint64_t)p.x_n_stride * 2};         // bytes, dims 1..4
+  const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)T::HW, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(p.x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int CIN, int NTILES, bool IN_HALF, bool TMA>
+static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st, const CUtensorMap& map) {
+  using T = ConvTile<CIN, NTILES>;
+  const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4 + 128;
+  g_last_conv3d_tma = TMA ? 1 : 0;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -462,13 +548,18 @@ static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st) {
     configured = true;
   }
   const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
-  conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF><<<(unsigned)blocks, kConvThreads, smem, st>>>(p);
+  conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF, TMA><<<(unsigned)blocks, kConvThreads, smem, st>>>(p, map);
   return check_launch("bmv_conv3d_k3");
 }
 
 template <int CIN, int NTILES>
 static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
-  return p.in_half ? launch_conv_t<CIN, NTILES, true>(p, st) : launch_conv_t<CIN, NTILES, false>(p, st);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if constexpr ((CIN == 16 || CIN == 32) && NTILES == 1) {
+    if (p.in_half && !p.no_tma && make_input_map<CIN, NTILES>(p, &map)) return launch_conv_t<CIN, NTILES, true, true>(p, st, map);
+  }
+  return p.in_half ? launch_conv_t<CIN, NTILES, true, false>(p, st, map) : launch_conv_t<CIN, NTILES, false, false>(p, st, map);
 }
 
 }  // namespace bmv
@@ -501,6 +592,9 @@ extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t st
   set_error("bmv_conv3d_k3: (Cin=%d, Cout=%d) not instantiated (16->16, 32->8, 8->16)", p->Cin, p->Cout);
   return BMV_ERR_UNSUPPORTED_SHAPE;
 }
+
+// 1 if the calling thread's last stride-1 bmv_conv3d_k3 launch staged its input tile with TMA, else 0
+extern "C" BMV_API int bmv_conv3d_k3_last_used_tma(void) { return bmv::g_last_conv3d_tma; }
 
 // words (uint32) of the fragment-ordered weight buffer for a (Cin, Cout) pair, -1 if not instantiated
 extern "C" BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout) {

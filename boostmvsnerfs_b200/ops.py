@@ -649,7 +649,7 @@ def fpn_topdown(prev, lateral_in, weight, bias):
 
 
 # ------------------------------------------------------------------------------------------ tensor-core 3-D convolution
-def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1):
+def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1, no_tma=False):
     """3x3x3 / stride 1 / pad 1 convolution (+bias, optional ReLU) of a channels_last_3d fp32 volume
     on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
     lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
@@ -678,6 +678,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
     p.N, p.D, p.H, p.W, p.Cin, p.Cout, p.relu = N, D, H, W, Cin, cout, int(bool(relu))
     p.stride = stride
     p.in_half = int(x.dtype == torch.float16)
+    p.no_tma = int(bool(no_tma))
     p.out = out.data_ptr()
     p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
     if out2 is not None:

@@ -351,10 +351,14 @@ typedef struct bmv_conv3d_params {
   int32_t stride;               /* 0/1: stride 1.  2: stride-2 convolution (Cin=8, Cout<=16; ConvBnReLU3D(8,16,stride=2),
                                    cost_reg_net.py:14,53), out is (N, (D-1)/2+1, (H-1)/2+1, (W-1)/2+1, Cout) */
   int32_t in_half;              /* 1: x points to fp16 storage (strides in fp16 elements, multiples of 8); stride 1 only.
-                                   The operands are rounded to fp16 in any case, so results are identical. */
+                                   The operands are rounded to fp16 in any case, so results are identical.  With
+                                   Cin 16 / 32, Cout <= 8 and voxels contiguous along x the input tile is staged by TMA
+                                   (one 5-D bulk-tensor copy per CTA, hardware zero fill = the padding). */
+  int32_t no_tma;               /* 1: force the register-staged path (A/B testing) */
 } bmv_conv3d_params;
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);
+BMV_API int bmv_conv3d_k3_last_used_tma(void);   /* 1 if this thread's last stride-1 launch staged its tile with TMA */
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) + bias + skip add:

@@ -34,6 +34,11 @@ for name, N, Cin, Cout, D, H, W, relu in SHAPES:
         t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, relu, out2=logits, split=8))
     else:
         t_ours = timeit(lambda: ops.conv3d_k3(x, wf, b, Cout, relu))
+    if Cin in (16, 32) and Cout <= 8:
+        xh = x.half()
+        t_h = timeit(lambda: ops.conv3d_k3(xh, wf, b, Cout, relu, no_tma=True))
+        t_t = timeit(lambda: ops.conv3d_k3(xh, wf, b, Cout, relu))
+        print(f"{name:18s} fp16 input: register-staged {t_h:8.1f} us   TMA-staged {t_t:8.1f} us")
     torch.backends.cudnn.allow_tf32 = True
     t_tf32 = timeit(lambda: torch.nn.functional.conv3d(x, wcl, b, padding=1))
     torch.backends.cudnn.allow_tf32 = False
