@@ -136,7 +136,8 @@ class ConvT3dParams(C.Structure):
                 ("wfrag", C.c_void_p), ("bias", C.c_void_p),
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
                 ("skip", C.c_void_p), ("s_n_stride", i64), ("s_d_stride", i64), ("s_y_stride", i64), ("s_x_stride", i64),
-                ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64)]
+                ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64),
+                ("out_half", i32)]
 
 
 class FpnFusedParams(C.Structure):

@@ -284,9 +284,9 @@ conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tm
           if (TMA) {
             // dense [d][y][x][c] box written by the TMA unit with its 32B / 64B swizzle: 16-byte chunk index XOR
             // address bits [7] (32B voxels) / [8:7] (64B voxels); the tile base is 1024-byte aligned
-            const uint32_t lin = tile_s + ((((db + pd) * T::HH + py) * T::HW) + mx * 16 + lrow + Cfg::step_voxel(j, lhi)) * Cfg::VS +
+            const uint32_t lin = tile_s + ((((db + pd) * T::HH + py) * T::ROWV) + mx * 16 + lrow + Cfg::step_voxel(j, lhi)) * Cfg::VS +
                                  (Cfg::step_chunk(j, lhi) << 4);
-            ldmatrix_x4(a, lin ^ (((lin >> 7) & (Cfg::VS == 32 ? 1u : 3u)) << 4));
+            ldmatrix_x4(a, lin ^ (((lin >> 7) & (Cfg::VS == 32 ? 1u : (Cfg::VS == 64 ? 3u : 0u))) << 4));
           } else {
             ldmatrix_x4(a, aoff[j] + ((db + pd) * T::HH + py) * T::ROWB);
           }
@@ -518,15 +518,16 @@ template <int CIN, int NTILES>
 static bool make_input_map(const bmv_conv3d_params& p, CUtensorMap* map) {
   using T = ConvTile<CIN, NTILES>;
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || !p.in_half || T::ROWV != T::HW) return false;
+  if (!enc || !p.in_half) return false;
   if (p.x_x_stride != CIN) return false;                                // voxels contiguous along x
   const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
   const cuuint64_t strides[4] = {(cuuint64_t)p.x_x_stride * 2, (cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2,
                                  (cuuint64_t)p.x_n_stride * 2};         // bytes, dims 1..4
-  const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)T::HW, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
+  const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)T::ROWV, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};   // ROWV = HW (+1 for Cin 8)
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(p.x), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -556,7 +557,7 @@ template <int CIN, int NTILES>
 static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  if constexpr ((CIN == 16 || CIN == 32) && NTILES == 1) {
+  if constexpr (((CIN == 16 || CIN == 32) && NTILES == 1) || (CIN == 8 && NTILES == 2)) {
     if (p.in_half && !p.no_tma && make_input_map<CIN, NTILES>(p, &map)) return launch_conv_t<CIN, NTILES, true, true>(p, st, map);
   }
   return p.in_half ? launch_conv_t<CIN, NTILES, true, false>(p, st, map) : launch_conv_t<CIN, NTILES, false, false>(p, st, map);

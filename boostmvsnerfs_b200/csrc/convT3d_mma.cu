@@ -167,7 +167,12 @@ __global__ void __launch_bounds__(kCtThreads, (CIN == 16 ? 4 : 2)) convT3d_k3s2_
             const float2 s = __ldg(reinterpret_cast<const float2*>(skip + rows + (int64_t)ox * p.s_x_stride + c));
             v.x += s.x; v.y += s.y;
           }
-          *reinterpret_cast<float2*>(out + rowo + (int64_t)ox * p.o_x_stride + c) = v;
+          if (p.out_half) {
+            __half2 hv = __floats2half2_rn(v.x, v.y);
+            *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + rowo + (int64_t)ox * p.o_x_stride + c) = hv;
+          } else {
+            *reinterpret_cast<float2*>(out + rowo + (int64_t)ox * p.o_x_stride + c) = v;
+          }
         }
       }
     }
@@ -204,7 +209,7 @@ extern "C" BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_
                   ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->wfrag & 15) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: input must be channels-last with 16-byte aligned voxels");
   BMV_REQUIRE(p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 && p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 &&
-                  ((uintptr_t)p->out & 7) == 0,
+                  ((uintptr_t)p->out & (p->out_half ? 3 : 7)) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: output must be channels-last with 8-byte aligned voxels");
   BMV_REQUIRE(!p->skip || (p->s_x_stride % 2 == 0 && p->s_y_stride % 2 == 0 && p->s_d_stride % 2 == 0 &&
                            p->s_n_stride % 2 == 0 && ((uintptr_t)p->skip & 7) == 0),

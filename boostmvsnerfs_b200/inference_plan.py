@@ -157,7 +157,8 @@ class MergedHeadsCostReg(nn.Module):
             y = s2 + n.conv7(n.conv6(n.conv5(s2)))
         if fast and y.stride(1) == 1 and s1.stride(1) == 1:
             y = ops.convT3d_k3s2_add(y, *pk['conv9'], 16, skip=s1)
-            y = ops.convT3d_k3s2_add(y, *pk['conv11'], 8, skip=s0)
+            # the full-resolution result only feeds the fp16-operand heads convolution: store it as fp16 (TMA-staged there)
+            y = ops.convT3d_k3s2_add(y, *pk['conv11'], 8, skip=s0, out_dtype=torch.float16)
         else:
             y = s1 + n.conv9(y)
             y = s0 + n.conv11(y)

@@ -690,7 +690,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
     return out
 
 
-def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None):
+def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None, out_dtype=torch.float32):
     """out = skip + ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1)(x) + bias on tensor cores
     (fp16 operands, fp32 accumulation; reference `x = conv0 + self.conv11(x)`,
     lib/networks/enerf/cost_reg_net.py:40-44,80-82).  x (N,Cin,D,H,W) and skip (N,cout,2D,2H,2W)
@@ -702,8 +702,11 @@ def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None):
     need = _lib.load().bmv_convT3d_k3s2_weight_words(Cin, cout)
     if need < 0 or wfrag.numel() != need or wfrag.dtype != torch.int32:
         raise BmvError(f"convT3d_k3s2_add: weight buffer does not match (Cin={Cin}, Cout={cout})")
-    out = torch.empty((N, cout, 2 * D, 2 * H, 2 * W), device=x.device, memory_format=torch.channels_last_3d)
+    if out_dtype not in (torch.float32, torch.float16):
+        raise BmvError("convT3d_k3s2_add: out_dtype must be float32 or float16")
+    out = torch.empty((N, cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=out_dtype, memory_format=torch.channels_last_3d)
     p = _lib.ConvT3dParams()
+    p.out_half = int(out_dtype == torch.float16)
     p.x = x.data_ptr()
     p.x_n_stride, p.x_d_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3), x.stride(4)
     p.wfrag = wfrag.data_ptr()

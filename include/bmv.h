@@ -376,6 +376,8 @@ typedef struct bmv_convT3d_params {
   int32_t N, D, H, W, Cin, Cout;              /* D,H,W: INPUT size */
   const float* skip; int64_t s_n_stride, s_d_stride, s_y_stride, s_x_stride;   /* or NULL */
   float* out; int64_t o_n_stride, o_d_stride, o_y_stride, o_x_stride;
+  int32_t out_half;             /* 1: out points to fp16 storage (strides in fp16 elements): the result only feeds another
+                                   fp16-operand convolution (the merged heads), so nothing is lost */
 } bmv_convT3d_params;
 BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_convT3d_k3s2_weight_words(int Cin, int Cout);

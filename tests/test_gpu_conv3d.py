@@ -137,6 +137,9 @@ def test_convT3d_k3s2_add_matches_cudnn(shape, exact_operands, with_skip):
     scale = ref.abs().max().item()
     tol = (1e-5 if exact_operands else 2e-3) * scale
     assert (y - ref).abs().max().item() <= tol, ((y - ref).abs().max().item(), scale)
+    # fp16 output storage = the fp32 result rounded to fp16
+    yh = ops.convT3d_k3s2_add(x, pack_convT3d_k3s2(w), b, Cout, skip=skip if with_skip else None, out_dtype=torch.float16)
+    assert yh.dtype == torch.float16 and torch.equal(yh, y.half())
 
 
 @pytest.mark.parametrize("minimal", [True, False])
