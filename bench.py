@@ -198,10 +198,11 @@ def conv_kernel_bytes(wl, rc, volume_bytes=4):
     for i in range(rc.num):
         C = int(32 * 2 ** (-i))
         vox = K * rc.volume_planes[i] * int(H * rc.volume_scale[i]) * int(W * rc.volume_scale[i])
-        out["bmv_conv3d_k3"] += [(f"conv0_l{i}", vox * (C * volume_bytes + 8 * 4)), (f"conv1_l{i}", vox * 8 * 4 + vox // 8 * 16 * 4),
-                                 (f"conv2_l{i}", vox // 8 * 16 * 4 * 2), (f"heads_l{i}", vox * (8 + 9) * 4)]
-        out["bmv_convT3d_k3s2"] += [(f"conv9T_l{i}", vox // 64 * 32 * 4 + vox // 8 * 16 * 4 * 2),
-                                    (f"conv11T_l{i}", vox // 8 * 16 * 4 + vox * 8 * 4 * 2)]
+        a = volume_bytes      # activations between libbmv kernels are fp16 exactly when the cost volume is
+        out["bmv_conv3d_k3"] += [(f"conv0_l{i}", vox * (C * volume_bytes + 8 * a)), (f"conv1_l{i}", vox * 8 * a + vox // 8 * 16 * a),
+                                 (f"conv2_l{i}", vox // 8 * 16 * (a + 4)), (f"heads_l{i}", vox * (8 * a + 9 * 4))]
+        out["bmv_convT3d_k3s2"] += [(f"conv9T_l{i}", vox // 64 * 32 * 4 + vox // 8 * 16 * (4 + a)),
+                                    (f"conv11T_l{i}", vox // 8 * 16 * a + vox * 8 * a * 2)]
     return out
 
 

@@ -128,7 +128,7 @@ class Conv3dParams(C.Structure):
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("relu", i32),
                 ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64),
                 ("out2", C.c_void_p), ("o2_n_stride", i64), ("o2_d_stride", i64), ("o2_y_stride", i64),
-                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32), ("no_tma", i32)]
+                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32), ("no_tma", i32), ("out_half", i32)]
 
 
 class ConvT3dParams(C.Structure):
@@ -137,7 +137,7 @@ class ConvT3dParams(C.Structure):
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
                 ("skip", C.c_void_p), ("s_n_stride", i64), ("s_d_stride", i64), ("s_y_stride", i64), ("s_x_stride", i64),
                 ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64),
-                ("out_half", i32)]
+                ("out_half", i32), ("skip_half", i32), ("in_half", i32)]
 
 
 class FpnFusedParams(C.Structure):

@@ -326,7 +326,14 @@ conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tm
           const int c = nt * 8 + 2 * t;
           float v0 = acc[od][oy][nt][0], v1 = acc[od][oy][nt][1], v2 = acc[od][oy][nt][2], v3 = acc[od][oy][nt][3];
           if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-          if (vec_ok && nt * 8 + 8 <= split) {                          // whole n-tile lands in `out`: 8-byte stores
+          if (p.out_half) {                                             // fp16 storage (launcher: even Cout, no split)
+            __half* hrow = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + (int64_t)gd * p.o_d_stride +
+                           (int64_t)gy * p.o_y_stride;
+            if (c < p.Cout) {
+              if (gx0 < p.W) *reinterpret_cast<__half2*>(hrow + (int64_t)gx0 * p.o_x_stride + c) = __floats2half2_rn(v0, v1);
+              if (gx1 < p.W) *reinterpret_cast<__half2*>(hrow + (int64_t)gx1 * p.o_x_stride + c) = __floats2half2_rn(v2, v3);
+            }
+          } else if (vec_ok && nt * 8 + 8 <= split) {                   // whole n-tile lands in `out`: 8-byte stores
             if (gx0 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
             if (gx1 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
           } else {
@@ -359,16 +366,15 @@ struct ConvS2 {
   static constexpr int W_WORDS = 9 * KS * NT * 32 * 2;
 };
 
-__global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3s2_c8_mma_kernel(bmv_conv3d_params p, int Do, int Ho, int Wo) {
+template <bool TMA>
+__global__ void __launch_bounds__(kConvThreads, 2)
+conv3d_k3s2_c8_mma_kernel(bmv_conv3d_params p, int Do, int Ho, int Wo, const __grid_constant__ CUtensorMap tmap) {
   using T = ConvS2;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
   unsigned char* tile = smem;
   const uint2* wfrag = reinterpret_cast<const uint2*>(smem + T::TILE_BYTES);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
-    uint4* dst = reinterpret_cast<uint4*>(smem + T::TILE_BYTES);
-    for (int i = threadIdx.x; i < T::W_WORDS / 4; i += kConvThreads) dst[i] = __ldg(src + i);
-  }
+  __shared__ __align__(8) uint64_t s_mbar;
   const int tiles_w = (Wo + T::TW - 1) / T::TW, tiles_h = (Ho + T::TH - 1) / T::TH, tiles_d = (Do + T::TD - 1) / T::TD;
   int b = blockIdx.x;
   const int tw = b % tiles_w; b /= tiles_w;
@@ -377,7 +383,23 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3s2_c8_mma_kernel(bmv
   const int n = b;
   const int x0 = tw * T::TW, y0 = th * T::TH, d0 = td * T::TD;          // output coordinates
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (TMA) {                                                            // fp16 input: one bulk-tensor copy of the 9 x 9 x 66 tile
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(mbar, (uint32_t)T::TILE_BYTES);
+      tma_load_5d((uint32_t)__cvta_generic_to_shared(tile), &tmap, mbar, 0, 2 * x0 - 1, 2 * y0 - 1, 2 * d0 - 1, n);
+    }
+  }
   {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
+    uint4* dst = reinterpret_cast<uint4*>(smem + T::TILE_BYTES);
+    for (int i = threadIdx.x; i < T::W_WORDS / 4; i += kConvThreads) dst[i] = __ldg(src + i);
+  }
+  if (TMA) {
+    mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0);
+  } else {
     const float* xin = p.x + (int64_t)n * p.x_n_stride;
     constexpr int PER_ROW = T::ROWV * 2, ROWS = T::HD * T::HH, P = (PER_ROW + 31) / 32, VPP = 16;
     const int c4 = lane & 1, hx0 = lane >> 1;
@@ -468,32 +490,19 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_k3s2_c8_mma_kernel(bmv
           if (c + 1 >= p.Cout + 1 || c >= p.Cout) continue;
           float v0 = acc[oy][nt][0], v1 = acc[oy][nt][1], v2 = acc[oy][nt][2], v3 = acc[oy][nt][3];
           if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-          if (gx0 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
-          if (gx1 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
+          if (p.out_half) {
+            __half* hrow = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + (int64_t)(d0 + od) * p.o_d_stride +
+                           (int64_t)gy * p.o_y_stride;
+            if (gx0 < Wo) *reinterpret_cast<__half2*>(hrow + (int64_t)gx0 * p.o_x_stride + c) = __floats2half2_rn(v0, v1);
+            if (gx1 < Wo) *reinterpret_cast<__half2*>(hrow + (int64_t)gx1 * p.o_x_stride + c) = __floats2half2_rn(v2, v3);
+          } else {
+            if (gx0 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
+            if (gx1 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
+          }
         }
       }
     }
   }
-}
-
-static int launch_conv_s2(const bmv_conv3d_params& p, cudaStream_t st) {
-  using T = ConvS2;
-  const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) {
-      set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
-      return BMV_ERR_CUDA_LAUNCH;
-    }
-    configured = true;
-  }
-  const int Do = (p.D - 1) / 2 + 1, Ho = (p.H - 1) / 2 + 1, Wo = (p.W - 1) / 2 + 1;
-  const int64_t blocks = (int64_t)p.N * ((Do + T::TD - 1) / T::TD) * ((Ho + T::TH - 1) / T::TH) * ((Wo + T::TW - 1) / T::TW);
-  conv3d_k3s2_c8_mma_kernel<<<(unsigned)blocks, kConvThreads, smem, st>>>(p, Do, Ho, Wo);
-  return check_launch("bmv_conv3d_k3");
 }
 
 static thread_local int g_last_conv3d_tma = 0;      // which staging path the last stride-1 launch of this thread used (tests)
@@ -532,6 +541,50 @@ static bool make_input_map(const bmv_conv3d_params& p, CUtensorMap* map) {
   return r == CUDA_SUCCESS;
 }
 
+template <bool TMA>
+static int launch_conv_s2_t(const bmv_conv3d_params& p, cudaStream_t st, const CUtensorMap& map) {
+  using T = ConvS2;
+  const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4 + 128;
+  g_last_conv3d_tma = TMA ? 1 : 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel<TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel<TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) {
+      set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+      return BMV_ERR_CUDA_LAUNCH;
+    }
+    configured = true;
+  }
+  const int Do = (p.D - 1) / 2 + 1, Ho = (p.H - 1) / 2 + 1, Wo = (p.W - 1) / 2 + 1;
+  const int64_t blocks = (int64_t)p.N * ((Do + T::TD - 1) / T::TD) * ((Ho + T::TH - 1) / T::TH) * ((Wo + T::TW - 1) / T::TW);
+  conv3d_k3s2_c8_mma_kernel<TMA><<<(unsigned)blocks, kConvThreads, smem, st>>>(p, Do, Ho, Wo, map);
+  return check_launch("bmv_conv3d_k3");
+}
+
+static int launch_conv_s2(const bmv_conv3d_params& p, cudaStream_t st) {
+  using T = ConvS2;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (p.in_half && !p.no_tma && enc && p.x_x_stride == 8) {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+    const cuuint64_t strides[4] = {(cuuint64_t)p.x_x_stride * 2, (cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2,
+                                   (cuuint64_t)p.x_n_stride * 2};
+    const cuuint32_t box[5] = {8, (cuuint32_t)T::ROWV, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      return launch_conv_s2_t<true>(p, st, map);
+  }
+  if (p.in_half) {
+    set_error("bmv_conv3d_k3: fp16 input with stride 2 needs the TMA path (voxels contiguous along x, driver support)");
+    return BMV_ERR_UNSUPPORTED_SHAPE;
+  }
+  return launch_conv_s2_t<false>(p, st, map);
+}
+
 template <int CIN, int NTILES, bool IN_HALF, bool TMA>
 static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st, const CUtensorMap& map) {
   using T = ConvTile<CIN, NTILES>;
@@ -557,7 +610,7 @@ template <int CIN, int NTILES>
 static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  if constexpr (((CIN == 16 || CIN == 32) && NTILES == 1) || (CIN == 8 && NTILES == 2)) {
+  if constexpr (CIN == 16 || (CIN == 32 && NTILES == 1) || (CIN == 8 && NTILES == 2)) {
     if (p.in_half && !p.no_tma && make_input_map<CIN, NTILES>(p, &map)) return launch_conv_t<CIN, NTILES, true, true>(p, st, map);
   }
   return p.in_half ? launch_conv_t<CIN, NTILES, true, false>(p, st, map) : launch_conv_t<CIN, NTILES, false, false>(p, st, map);
@@ -574,8 +627,10 @@ extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t st
     BMV_REQUIRE(p->x_x_stride % m == 0 && p->x_y_stride % m == 0 && p->x_d_stride % m == 0 && p->x_n_stride % m == 0 &&
                     ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->wfrag & 15) == 0,
                 BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: input must be channels-last with 16-byte aligned voxels");
-    BMV_REQUIRE(!p->in_half || p->stride != 2, BMV_ERR_UNSUPPORTED_SHAPE, "bmv_conv3d_k3: fp16 input is stride-1 only");
   }
+  BMV_REQUIRE(!p->out_half || (!p->out2 && p->Cout % 2 == 0 && p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 &&
+                               p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 && ((uintptr_t)p->out & 3) == 0),
+              BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: fp16 output needs even Cout, a single output tensor and 4-byte aligned voxels");
   BMV_REQUIRE(!p->out2 || (p->split >= 1 && p->split < p->Cout), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad split");
   cudaStream_t st = (cudaStream_t)stream;
   BMV_REQUIRE(p->stride == 0 || p->stride == 1 || p->stride == 2, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride must be 1 or 2");
@@ -583,7 +638,7 @@ extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t st
     BMV_REQUIRE(p->Cin == 8 && p->Cout % 2 == 0 && p->Cout <= 16 && !p->out2, BMV_ERR_UNSUPPORTED_SHAPE,
                 "bmv_conv3d_k3: stride 2 is instantiated for Cin=8, even Cout<=16, single output (got Cin=%d, Cout=%d)", p->Cin, p->Cout);
     BMV_REQUIRE(p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 && p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 &&
-                    ((uintptr_t)p->out & 7) == 0, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride-2 output must be 8-byte aligned");
+                    ((uintptr_t)p->out & (p->out_half ? 3 : 7)) == 0, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride-2 output alignment");
     return launch_conv_s2(*p, st);
   }
   if (p->Cin == 16 && p->Cout <= 8) return launch_conv<16, 1>(*p, st);

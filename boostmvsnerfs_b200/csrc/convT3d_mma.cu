@@ -57,6 +57,34 @@ __global__ void __launch_bounds__(kCtThreads, (CIN == 16 ? 4 : 2)) convT3d_k3s2_
   const int x0 = tw * C::TW, y0 = th * C::TH, d0 = td * C::TD;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // ---- stage the input tile (+1 halo on the high side) as fp16, one warp per row (see conv3d_mma.cu)
+  if (p.in_half) {                                                      // fp16 input: straight 16-byte copies
+    const __half* xin = reinterpret_cast<const __half*>(p.x) + (int64_t)n * p.x_n_stride;
+    constexpr int CH8 = CIN / 8;
+    constexpr int PER_ROW = C::HW * CH8;
+    constexpr int ROWS = C::HD * C::HH;
+    constexpr int P = (PER_ROW + 31) / 32;
+    constexpr int VPP = 32 / CH8;
+    const int c8 = lane % CH8, hx0 = lane / CH8;
+    const int64_t lane_off = (int64_t)(x0 + hx0) * p.x_x_stride + c8 * 8, pass_off = (int64_t)VPP * p.x_x_stride;
+    for (int r = warp; r < ROWS; r += kCtWarps) {
+      const int hd = r / C::HH, hy = r - hd * C::HH;
+      const int gy = y0 + hy, gd = d0 + hd;
+      const bool row_ok = gy < p.H && gd < p.D;
+      const __half* src = xin + (int64_t)gd * p.x_d_stride + (int64_t)gy * p.x_y_stride + lane_off;
+      uint4 val[P];
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int hx = hx0 + VPP * k;
+        val[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok && hx < C::HW && x0 + hx < p.W) val[k] = __ldg(reinterpret_cast<const uint4*>(src + k * pass_off));
+      }
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int hx = hx0 + VPP * k;
+        if (hx < C::HW) *reinterpret_cast<uint4*>(tile + r * C::ROWB + hx * C::VS + ((c8 ^ C::swz(hx)) << 4)) = val[k];
+      }
+    }
+  } else
   {
     const float* xin = p.x + (int64_t)n * p.x_n_stride;
     constexpr int CH4 = CIN / 4;
@@ -164,8 +192,15 @@ __global__ void __launch_bounds__(kCtThreads, (CIN == 16 ? 4 : 2)) convT3d_k3s2_
           const int ox = 2 * m + px;
           float2 v = make_float2(acc[cls][nt][2 * h], acc[cls][nt][2 * h + 1]);
           if (skip) {
-            const float2 s = __ldg(reinterpret_cast<const float2*>(skip + rows + (int64_t)ox * p.s_x_stride + c));
-            v.x += s.x; v.y += s.y;
+            if (p.skip_half) {
+              const __half2 hs = *reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p.skip) + (int64_t)n * p.s_n_stride + rows +
+                                                                   (int64_t)ox * p.s_x_stride + c);
+              const float2 s = __half22float2(hs);
+              v.x += s.x; v.y += s.y;
+            } else {
+              const float2 s = __ldg(reinterpret_cast<const float2*>(skip + rows + (int64_t)ox * p.s_x_stride + c));
+              v.x += s.x; v.y += s.y;
+            }
           }
           if (p.out_half) {
             __half2 hv = __floats2half2_rn(v.x, v.y);
@@ -205,14 +240,15 @@ extern "C" BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: bad size");
-  BMV_REQUIRE(p->x_x_stride % 4 == 0 && p->x_y_stride % 4 == 0 && p->x_d_stride % 4 == 0 && p->x_n_stride % 4 == 0 &&
+  const int xm = p->in_half ? 8 : 4;
+  BMV_REQUIRE(p->x_x_stride % xm == 0 && p->x_y_stride % xm == 0 && p->x_d_stride % xm == 0 && p->x_n_stride % xm == 0 &&
                   ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->wfrag & 15) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: input must be channels-last with 16-byte aligned voxels");
   BMV_REQUIRE(p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 && p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 &&
                   ((uintptr_t)p->out & (p->out_half ? 3 : 7)) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: output must be channels-last with 8-byte aligned voxels");
   BMV_REQUIRE(!p->skip || (p->s_x_stride % 2 == 0 && p->s_y_stride % 2 == 0 && p->s_d_stride % 2 == 0 &&
-                           p->s_n_stride % 2 == 0 && ((uintptr_t)p->skip & 7) == 0),
+                           p->s_n_stride % 2 == 0 && ((uintptr_t)p->skip & (p->skip_half ? 3 : 7)) == 0),
               BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: skip must be channels-last with 8-byte aligned voxels");
   cudaStream_t st = (cudaStream_t)stream;
   if (p->Cin == 16 && p->Cout == 8) return launch_convT<16, 8>(*p, st);

@@ -145,9 +145,11 @@ class MergedHeadsCostReg(nn.Module):
         if fast:
             from . import ops
             pk = self._packed_weights(x.device)
-            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True)                       # ConvBnReLU3D(C, 8)
-            s1 = ops.conv3d_k3(s0, *pk['conv1'], 16, relu=True, stride=2)           # ConvBnReLU3D(8, 16, stride=2)
-            s1 = ops.conv3d_k3(s1, *pk['conv2'], 16, relu=True)                     # ConvBnReLU3D(16, 16)
+            # activations that only feed other fp16-operand libbmv kernels are stored as fp16 and staged by TMA
+            h = torch.float16
+            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True, out_dtype=h)          # ConvBnReLU3D(C, 8)
+            s1 = ops.conv3d_k3(s0, *pk['conv1'], 16, relu=True, stride=2, out_dtype=h)   # ConvBnReLU3D(8, 16, stride=2)
+            s1 = ops.conv3d_k3(s1, *pk['conv2'], 16, relu=True)                     # ConvBnReLU3D(16, 16); fp32: cuDNN reads it
         else:
             s0 = n.conv0(x)
             s1 = n.conv2(n.conv1(s0))
@@ -156,7 +158,7 @@ class MergedHeadsCostReg(nn.Module):
         if n.depth_levels == 3:
             y = s2 + n.conv7(n.conv6(n.conv5(s2)))
         if fast and y.stride(1) == 1 and s1.stride(1) == 1:
-            y = ops.convT3d_k3s2_add(y, *pk['conv9'], 16, skip=s1)
+            y = ops.convT3d_k3s2_add(y, *pk['conv9'], 16, skip=s1, out_dtype=torch.float16)
             # the full-resolution result only feeds the fp16-operand heads convolution: store it as fp16 (TMA-staged there)
             y = ops.convT3d_k3s2_add(y, *pk['conv11'], 8, skip=s0, out_dtype=torch.float16)
         else:

@@ -649,7 +649,7 @@ def fpn_topdown(prev, lateral_in, weight, bias):
 
 
 # ------------------------------------------------------------------------------------------ tensor-core 3-D convolution
-def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1, no_tma=False):
+def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1, no_tma=False, out_dtype=torch.float32):
     """3x3x3 / stride 1 / pad 1 convolution (+bias, optional ReLU) of a channels_last_3d fp32 volume
     on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
     lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
@@ -663,7 +663,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
         raise BmvError("conv3d_k3: x must be channels_last_3d")
     if out is None:
         Do, Ho, Wo = (((D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1) if stride == 2 else (D, H, W))
-        out = torch.empty((N, split if out2 is not None else cout, Do, Ho, Wo), device=x.device,
+        out = torch.empty((N, split if out2 is not None else cout, Do, Ho, Wo), device=x.device, dtype=out_dtype,
                           memory_format=torch.channels_last_3d)
     if out.stride(1) != 1 or (out2 is not None and out2.shape[1] > 1 and out2.stride(1) != 1):
         raise BmvError("conv3d_k3: out must be channels_last_3d")
@@ -679,6 +679,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
     p.stride = stride
     p.in_half = int(x.dtype == torch.float16)
     p.no_tma = int(bool(no_tma))
+    p.out_half = int(out.dtype == torch.float16)
     p.out = out.data_ptr()
     p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
     if out2 is not None:
@@ -695,7 +696,8 @@ def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None, out_dtype=torch.float32):
     (fp16 operands, fp32 accumulation; reference `x = conv0 + self.conv11(x)`,
     lib/networks/enerf/cost_reg_net.py:40-44,80-82).  x (N,Cin,D,H,W) and skip (N,cout,2D,2H,2W)
     channels_last_3d; wfrag from mlp_pack.pack_convT3d_k3s2."""
-    _f32(x, "x")
+    if not (x.is_cuda and x.dtype in (torch.float32, torch.float16)):
+        raise BmvError(f"convT3d_k3s2_add: x must be a CUDA float32/float16 tensor, got {x.dtype}")
     N, Cin, D, H, W = x.shape
     if x.stride(1) != 1:
         raise BmvError("convT3d_k3s2_add: x must be channels_last_3d")
@@ -707,13 +709,16 @@ def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None, out_dtype=torch.float32):
     out = torch.empty((N, cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=out_dtype, memory_format=torch.channels_last_3d)
     p = _lib.ConvT3dParams()
     p.out_half = int(out_dtype == torch.float16)
+    p.in_half = int(x.dtype == torch.float16)
     p.x = x.data_ptr()
     p.x_n_stride, p.x_d_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3), x.stride(4)
     p.wfrag = wfrag.data_ptr()
     p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
     p.N, p.D, p.H, p.W, p.Cin, p.Cout = N, D, H, W, Cin, cout
     if skip is not None:
-        _f32(skip, "skip")
+        if not (skip.is_cuda and skip.dtype in (torch.float32, torch.float16)):
+            raise BmvError("convT3d_k3s2_add: skip must be a CUDA float32/float16 tensor")
+        p.skip_half = int(skip.dtype == torch.float16)
         if tuple(skip.shape) != tuple(out.shape) or skip.stride(1) != 1:
             raise BmvError(f"convT3d_k3s2_add: skip must be channels_last_3d of shape {tuple(out.shape)}")
         p.skip = skip.data_ptr()

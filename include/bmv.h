@@ -350,11 +350,13 @@ typedef struct bmv_conv3d_params {
   int32_t split;                /* with out2: channel c >= split is written to out2 at channel c - split */
   int32_t stride;               /* 0/1: stride 1.  2: stride-2 convolution (Cin=8, Cout<=16; ConvBnReLU3D(8,16,stride=2),
                                    cost_reg_net.py:14,53), out is (N, (D-1)/2+1, (H-1)/2+1, (W-1)/2+1, Cout) */
-  int32_t in_half;              /* 1: x points to fp16 storage (strides in fp16 elements, multiples of 8); stride 1 only.
+  int32_t in_half;              /* 1: x points to fp16 storage (strides in fp16 elements, multiples of 8).
                                    The operands are rounded to fp16 in any case, so results are identical.  With
                                    Cin 16 / 32, Cout <= 8 and voxels contiguous along x the input tile is staged by TMA
                                    (one 5-D bulk-tensor copy per CTA, hardware zero fill = the padding). */
   int32_t no_tma;               /* 1: force the register-staged path (A/B testing) */
+  int32_t out_half;             /* 1: out points to fp16 storage (strides in fp16 elements; even Cout, no out2): for results
+                                   that only feed other fp16-operand libbmv convolutions */
 } bmv_conv3d_params;
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);
@@ -378,6 +380,8 @@ typedef struct bmv_convT3d_params {
   float* out; int64_t o_n_stride, o_d_stride, o_y_stride, o_x_stride;
   int32_t out_half;             /* 1: out points to fp16 storage (strides in fp16 elements): the result only feeds another
                                    fp16-operand convolution (the merged heads), so nothing is lost */
+  int32_t skip_half;            /* 1: skip points to fp16 storage (strides in fp16 elements) */
+  int32_t in_half;              /* 1: x points to fp16 storage (strides in fp16 elements, multiples of 8) */
 } bmv_convT3d_params;
 BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_convT3d_k3s2_weight_words(int Cin, int Cout);

@@ -79,6 +79,14 @@ def test_conv3d_k3_stride2_matches_cudnn(shape, exact_operands):
     assert y.shape == ref.shape, (y.shape, ref.shape)
     scale = ref.abs().max().item()
     assert (y - ref).abs().max().item() <= (1e-5 if exact_operands else 2e-3) * scale
+    # fp16 input (staged by TMA: one 9x9x66-voxel bulk copy per CTA) and fp16 output
+    from boostmvsnerfs_b200 import _lib
+    xh = x.half()
+    yh = ops.conv3d_k3(xh, pack_conv3d_k3(w), b, Cout, True, stride=2)
+    assert _lib.load().bmv_conv3d_k3_last_used_tma() == 1
+    assert torch.equal(yh, ops.conv3d_k3(xh.float(), pack_conv3d_k3(w), b, Cout, True, stride=2))
+    y16 = ops.conv3d_k3(xh, pack_conv3d_k3(w), b, Cout, True, stride=2, out_dtype=torch.float16)
+    assert torch.equal(y16, yh.half())
 
 
 def test_conv3d_k3_strided_output_and_errors():
@@ -140,6 +148,11 @@ def test_convT3d_k3s2_add_matches_cudnn(shape, exact_operands, with_skip):
     # fp16 output storage = the fp32 result rounded to fp16
     yh = ops.convT3d_k3s2_add(x, pack_convT3d_k3s2(w), b, Cout, skip=skip if with_skip else None, out_dtype=torch.float16)
     assert yh.dtype == torch.float16 and torch.equal(yh, y.half())
+    # fp16 input / skip storage: same as the fp32 tensors holding the rounded values
+    xh, sh = x.half(), skip.half()
+    a = ops.convT3d_k3s2_add(xh, pack_convT3d_k3s2(w), b, Cout, skip=sh if with_skip else None)
+    b_ = ops.convT3d_k3s2_add(xh.float(), pack_convT3d_k3s2(w), b, Cout, skip=sh.float() if with_skip else None)
+    assert torch.equal(a, b_)
 
 
 @pytest.mark.parametrize("minimal", [True, False])
