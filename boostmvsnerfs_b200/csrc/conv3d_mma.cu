@@ -359,7 +359,7 @@ conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tm
 // voxel (ldmatrix takes one address per row), taps kx = 0,1 are the contiguous voxel pair (2o, 2o+1) of the
 // staged row, kx = 2 is paired with zero weights.  CTA: 4 x 4 x 32 outputs from a 9 x 9 x 66 input tile.
 struct ConvS2 {
-  static constexpr int TD = 4, TH = 4, TW = 32, NT = 2, KS = 2;
+  static constexpr int TD = 4, TH = 2, TW = 32, NT = 2, KS = 2;
   static constexpr int HD = 2 * TD + 1, HH = 2 * TH + 1, ROWV = 2 * TW + 2;
   static constexpr int ROWB = ROWV * 16;
   static constexpr int TILE_BYTES = HD * HH * ROWB;
@@ -367,7 +367,7 @@ struct ConvS2 {
 };
 
 template <bool TMA>
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 4)
 conv3d_k3s2_c8_mma_kernel(bmv_conv3d_params p, int Do, int Ho, int Wo, const __grid_constant__ CUtensorMap tmap) {
   using T = ConvS2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
