@@ -26,7 +26,7 @@ template <int CIN, int COUT>
 struct CtCfg {
   static constexpr int KT = CIN / 16, NT = COUT / 8;
   static constexpr int VS = CIN * 2;                                    // bytes per staged voxel
-  static constexpr int TD = 4, TH = 4, TW = 32;                         // input positions per CTA
+  static constexpr int TD = CIN == 32 ? 2 : 4, TH = CIN == 32 ? 2 : 4, TW = 32;   // input positions per CTA (32->16 runs at 1/4 res: small tiles = enough CTAs)
   static constexpr int HD = TD + 1, HH = TH + 1, HW = TW + 1;           // +1: odd outputs read input m+1
   static constexpr int ROWB = HW * VS;
   static constexpr int TILE_BYTES = HD * HH * ROWB;
