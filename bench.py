@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--stage-report", action="store_true", help="print the per-stage table to stderr")
-    ap.add_argument("--mlp-engine", default=None, choices=["mma", "fma"], help="override Network.mlp_engine")
+    ap.add_argument("--mlp-engine", default=None, choices=["mma", "fma", "umma"], help="override Network.mlp_engine")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
                     help="also time the reference's op sequence (oracle restatement) as eager PyTorch on this GPU")
     return ap.parse_args()

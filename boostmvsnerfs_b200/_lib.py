@@ -166,6 +166,7 @@ ENTRY_POINTS = {
     "bmv_nerf_mlp": NerfMlpParams,
     "bmv_render_rays": RenderRaysParams,
     "bmv_render_rays_mma": RenderRaysParams,
+    "bmv_render_rays_umma": RenderRaysParams,
     "bmv_cost_volume_var_img": CostVolumeImgParams,
     "bmv_mvs_march_fetch": MvsMarchParams,
     "bmv_fpn_topdown": FpnTopdownParams,
@@ -176,6 +177,7 @@ ENTRY_POINTS = {
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",
+                 "bmv_render_rays_umma_weight_words", "bmv_umma_selftest",
                  "bmv_conv3d_k3_weight_words", "bmv_conv3d_k3_last_used_tma", "bmv_convT3d_k3s2_weight_words",
                  "bmv_fpn_topdown_smooth_weight_words")
 
@@ -201,6 +203,9 @@ def load():
     lib.bmv_nerf_mlp_weight_count.restype = C.c_int
     lib.bmv_nerf_mlp_weight_count.argtypes = [C.c_int]
     lib.bmv_render_rays_mma_weight_words.restype = C.c_int
+    lib.bmv_render_rays_umma_weight_words.restype = C.c_int
+    lib.bmv_umma_selftest.restype = C.c_int
+    lib.bmv_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.bmv_render_rays_supported.restype = C.c_int
     lib.bmv_render_rays_supported.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.bmv_conv3d_k3_weight_words.restype = C.c_int

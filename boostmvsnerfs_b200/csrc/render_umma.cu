@@ -1,0 +1,502 @@
+// K3+K5 on the 5th-generation tensor cores: the fused gather + per-sample MLP of render_mma.cu with every
+// Linear layer issued as tcgen05.mma (UMMA) — operands in shared memory, accumulators in tensor memory (TMEM).
+//
+// Why: ncu on render_mma.cu (profiles/round1g) shows the legacy mma.sync path at HMMA pipe 38 % / issue 49 %
+// with 221 M warp instructions per launch — a warp-level MMA needs its A fragments rebuilt in registers for
+// every layer and 3 x 112 mma.sync per 16 samples.  Here one thread owns one SAMPLE ROW of a 128-sample tile:
+// it gathers the sample, writes the row of each layer's A operand (fp16 hi + lo, 22 significant bits) into
+// shared memory in the UMMA canonical K-major layout, ONE thread of the tile's 4 warps issues the layer's
+// MMAs (M = 128, N = 16..64, K = 16 per instruction, three per product: lo*hi + hi*lo + hi*hi, fp32
+// accumulate in TMEM), and the row comes back with tcgen05.ld (lane = row) for bias / ReLU / soft-max.
+// Two tiles (2 x 4 warps) share a CTA and ping-pong: while one waits for its MMAs the other runs its
+// CUDA-core phase.  The shared [hid | pooled | vox] part of color.0 and the [var | mean] part of global_fc
+// are computed once per sample and added to the per-view parts in the epilogue.
+//
+// Shared-memory operand layout (SWIZZLE_NONE, K-major; reference for the descriptor fields:
+// cute/arch/mma_sm100_desc.hpp): an operand is a sequence of K-chunks of 8 fp16; chunk c is a slab of
+// ROWS x 16 bytes (row r at byte r*16), i.e. 8-row core matrices 128 B apart (SBO = 128) and the two
+// K-chunks of one K=16 instruction LBO bytes apart (A: 4096, the hi and lo slabs of a chunk are adjacent;
+// B: N*16).  A thread writing its row's chunk stores 16 contiguous bytes next to its neighbours' (no bank
+// conflicts).  TMEM: 512 columns, tile w uses columns [256 w, 256 w + 256); accumulator row i = lane i.
+//
+// Accuracy: identical split to render_mma.cu (dropped lo*lo term 2^-22), agrees with the fp32 kernels to
+// ~1e-5 (tests/test_gpu_umma.py); the gather is the same code (gather_sample_regs).
+#include "raygen_common.cuh"
+
+namespace bmv {
+
+// ----------------------------------------------------------------------------------------- packed weights
+// [hi block][lo block][fp32 vectors]; inside a block the matrices below, each as [K/8][N][8] fp16.
+constexpr int UW_GS = 0;                       // global_fc [var16 | mean16] : N=32, K=32
+constexpr int UW_GV = UW_GS + 32 * 32 * 2;     // global_fc per-view x       : N=32, K=16
+constexpr int UW_FC = UW_GV + 32 * 16 * 2;     // agg.fc                     : N=16, K=32
+constexpr int UW_L0 = UW_FC + 16 * 32 * 2;     // lr0 [pooled16 | vox8 | 0]  : N=64, K=32
+constexpr int UW_CS = UW_L0 + 64 * 32 * 2;     // color.0 [hid64 | pooled16 | vox8 | 0] : N=64, K=96
+constexpr int UW_CV = UW_CS + 64 * 96 * 2;     // color.0 per-view f_v       : N=64, K=16
+constexpr int UW_BLOCK = UW_CV + 64 * 16 * 2;  // bytes per hi (or lo) block = 22528
+// fp32 vectors (float offsets from the start of the vector area) — same order as the mma.sync packing
+constexpr int UV_BG = 0, UV_WA = 32, UV_BFC = 64, UV_BL = 80, UV_WS = 144, UV_BC = 208, UV_W2 = 272, UV_WV = 336,
+              UV_BV = 384, UV_SC = 396, UV_COUNT = 400;
+constexpr int UMMA_PACK_BYTES = 2 * UW_BLOCK + UV_COUNT * 4;
+constexpr int UMMA_PACK_WORDS = UMMA_PACK_BYTES / 4;
+
+// ----------------------------------------------------------------------------------------- A-operand chunks of a tile
+constexpr int CH_VAR = 0, CH_MEAN = 2, CH_X = 4;          // phase A (x_v at CH_X + 2v)
+constexpr int CH_IM = 0;                                  // phase B (aliases var/mean)
+constexpr int CH_HID = 0;                                 // phase D (aliases 0..7)
+constexpr int CH_F = 10;                                  // f_v at CH_F + 2v, live from phase A to E
+constexpr int CH_POOLED = 16, CH_VOX = 18, CH_ZERO = 19;
+constexpr int kTileChunks = 20;
+constexpr int kChunkBytes = 4096;                         // hi slab (128 rows x 16 B) + lo slab
+constexpr int kTileBytes = kTileChunks * kChunkBytes;     // 81920
+constexpr int kUmmaTiles = 2;                             // 128-sample tiles in flight per CTA
+constexpr int kUmmaThreads = kUmmaTiles * 128;
+constexpr int kTmemColsPerTile = 256;
+constexpr int kPackPadded = (UMMA_PACK_BYTES + 127) / 128 * 128;   // operand tiles start 128-byte aligned
+constexpr size_t kUmmaSmem = (size_t)kPackPadded + (size_t)kUmmaTiles * kTileBytes + 128;
+
+// ----------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: start address, leading (K-chunk) and stride (8-row group) byte offsets in
+// 16-byte units, descriptor version 1 (Blackwell), SWIZZLE_NONE
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D fp32, A/B fp16, both K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// one K = 16 step of a split product: D (+)= A_lo B_hi + A_hi B_lo + A_hi B_hi
+__device__ __forceinline__ void umma_kstep(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lbo, uint32_t a_lo_off, uint32_t b_hi,
+                                           uint32_t b_lbo, uint32_t b_lo_off, uint32_t idesc, uint32_t acc) {
+  const uint64_t ah = umma_desc(a_hi, a_lbo, 128), al = umma_desc(a_hi + a_lo_off, a_lbo, 128);
+  const uint64_t bh = umma_desc(b_hi, b_lbo, 128), bl = umma_desc(b_hi + b_lo_off, b_lbo, 128);
+  umma_f16(d_tmem, al, bh, idesc, acc);
+  umma_f16(d_tmem, ah, bl, idesc, 1u);
+  umma_f16(d_tmem, ah, bh, idesc, 1u);
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane (32 lanes x 32 bit, repeated 16 times)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  // load and wait in ONE asm statement: the registers are not defined for the compiler before the wait
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_alloc_512(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(512u) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(512u) : "memory");
+}
+
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi), two values per 32-bit word
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  __half2 hh = __floats2half2_rn(v0, v1);
+  const float2 back = __half22float2(hh);
+  __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
+  hi = *reinterpret_cast<uint32_t*>(&hh);
+  lo = *reinterpret_cast<uint32_t*>(&ll);
+}
+// this row's 8 values of K-chunk `chunk`: 16 B into the hi slab, 16 B into the lo slab
+__device__ __forceinline__ void put_chunk(unsigned char* tile, int chunk, int row, float v0, float v1, float v2, float v3,
+                                          float v4, float v5, float v6, float v7) {
+  uint4 hi, lo;
+  split2(v0, v1, hi.x, lo.x); split2(v2, v3, hi.y, lo.y); split2(v4, v5, hi.z, lo.z); split2(v6, v7, hi.w, lo.w);
+  unsigned char* q = tile + chunk * kChunkBytes + row * 16;
+  *reinterpret_cast<uint4*>(q) = hi;
+  *reinterpret_cast<uint4*>(q + 2048) = lo;
+}
+
+// All 128 threads of a tile: publish the operand rows just written, then ONE thread issues `issue()`'s MMAs
+// and commits them to the tile's mbarrier; everybody waits for the accumulators.
+template <class Issue>
+__device__ __forceinline__ void tile_mma_phase(int wg, bool leader, uint32_t mbar, uint32_t& parity, Issue issue) {
+  proxy_fence_async();                 // generic-proxy st.shared -> visible to the tensor core (async proxy)
+  tc_fence_before();                   // earlier tcgen05.ld of the columns about to be overwritten
+  bar_sync_named(1 + wg, 128);
+  if (leader) {
+    tc_fence_after();
+    issue();
+    umma_commit(mbar);
+  }
+  mbar_wait(mbar, parity);
+  parity ^= 1u;
+  __syncwarp();
+  tc_fence_after();
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_render_rays_params rp) {
+  constexpr int V = 3, CF = 8;
+  const bmv_raygen_fetch_params& p = rp.g;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  unsigned char* sW = smem;                                             // hi block, lo block
+  const float* sV = reinterpret_cast<const float*>(smem + 2 * UW_BLOCK);  // fp32 vectors
+  unsigned char* sA = smem + kPackPadded;                               // operand tiles
+  __shared__ ViewCam cams[V];
+  __shared__ float s_tar_c[3];
+  __shared__ int s_view[V];
+  __shared__ __align__(8) uint64_t s_mbar[kUmmaTiles];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wg = warp >> 2, row = tid & 127;
+  for (int i = tid * 16; i < UMMA_PACK_BYTES; i += kUmmaThreads * 16)
+    *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(rp.mlp_weights) + i));
+  if (tid < V) s_view[tid] = p.view[tid];
+  if (tid == 0) {
+    for (int w = 0; w < kUmmaTiles; ++w) mbar_init(smem_u32(&s_mbar[w]), 1);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc_512(smem_u32(&s_tmem));
+  unsigned char* tile = sA + wg * kTileBytes;
+  // the zero K-chunk next to vox never changes
+  *reinterpret_cast<uint4*>(tile + CH_ZERO * kChunkBytes + row * 16) = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<uint4*>(tile + CH_ZERO * kChunkBytes + 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  for (int v = 0; v < V; ++v) load_cam(&cams[v], p.src_exts, p.src_ixts, p.src_centers, s_view[v], tid);
+  if (tid < 3) s_tar_c[tid] = p.tar_center[tid];
+  __syncthreads();
+
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t tcol0 = tmem_base + (uint32_t)(wg * kTmemColsPerTile);            // columns of this tile (issuer)
+  const uint32_t trow = tcol0 + ((uint32_t)((warp & 3) * 32) << 16);               // + this warp's lane quarter (loads)
+  const uint32_t mbar = smem_u32(&s_mbar[wg]);
+  const uint32_t aT = smem_u32(tile), wB = smem_u32(sW);
+  const bool leader = (row == 0);
+  uint32_t parity = 0;
+  const int S = p.S;
+  const int64_t n_samples = p.n_rays * S;
+  const int64_t n_tiles = (n_samples + 127) / 128;
+  const float ba = sV[UV_SC], bs = sV[UV_SC + 1], b2 = sV[UV_SC + 2];
+
+  for (int64_t tix = (int64_t)blockIdx.x * kUmmaTiles + wg; tix < n_tiles; tix += (int64_t)gridDim.x * kUmmaTiles) {
+    const int64_t si = tix * 128 + row;
+    const bool live = si < n_samples;
+    float rgbv[V][3];
+    // ------------------------------------------------------------ phase A: gather, view_fc, mean / variance
+    {
+      float vox[8];
+      float f[V][CF + 7];
+      if (live) {
+        const int64_t li = si / S;
+        const int s = (int)(si % S);
+        const RaySetup r = ray_setup(p, li);
+        const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
+        const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
+        const SamplePoint q = sample_point(p, r, s);
+        const int cnt = gather_sample_regs<CF, V, VEC>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
+        if (p.z_vals) p.z_vals[si] = q.z;
+        if (p.vis_mask) p.vis_mask[si] = div_rn((float)cnt, (float)V);
+        if (p.vis_count) p.vis_count[si] = cnt;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vox[c] = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int c = 0; c < CF + 7; ++c) f[v][c] = 0.f;
+      }
+      put_chunk(tile, CH_VOX, row, vox[0], vox[1], vox[2], vox[3], vox[4], vox[5], vox[6], vox[7]);
+      float x[V][11];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        put_chunk(tile, CH_F + 2 * v, row, f[v][0], f[v][1], f[v][2], f[v][3], f[v][4], f[v][5], f[v][6], f[v][7]);
+        put_chunk(tile, CH_F + 2 * v + 1, row, f[v][8], f[v][9], f[v][10], f[v][11], f[v][12], f[v][13], f[v][14], 0.f);
+        rgbv[v][0] = f[v][8]; rgbv[v][1] = f[v][9]; rgbv[v][2] = f[v][10];
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {
+          const float4 w = *reinterpret_cast<const float4*>(sV + UV_WV + c * 4);
+          const float e = fmaf(w.w, f[v][14], fmaf(w.z, f[v][13], fmaf(w.y, f[v][12], fmaf(w.x, f[v][11], sV[UV_BV + c]))));
+          x[v][c] = f[v][c] + fmaxf(e, 0.f);
+        }
+        put_chunk(tile, CH_X + 2 * v, row, x[v][0], x[v][1], x[v][2], x[v][3], x[v][4], x[v][5], x[v][6], x[v][7]);
+        put_chunk(tile, CH_X + 2 * v + 1, row, x[v][8], x[v][9], x[v][10], 0.f, 0.f, 0.f, 0.f, 0.f);
+      }
+      float var[11], mean[11];
+#pragma unroll
+      for (int c = 0; c < 11; ++c) {
+        const float m = (x[0][c] + x[1][c] + x[2][c]) * (1.f / 3.f);
+        const float e0 = x[0][c] - m, e1 = x[1][c] - m, e2 = x[2][c] - m;
+        mean[c] = m;
+        var[c] = fmaf(e2, e2, fmaf(e1, e1, e0 * e0)) * 0.5f;
+      }
+      put_chunk(tile, CH_VAR, row, var[0], var[1], var[2], var[3], var[4], var[5], var[6], var[7]);
+      put_chunk(tile, CH_VAR + 1, row, var[8], var[9], var[10], 0.f, 0.f, 0.f, 0.f, 0.f);
+      put_chunk(tile, CH_MEAN, row, mean[0], mean[1], mean[2], mean[3], mean[4], mean[5], mean[6], mean[7]);
+      put_chunk(tile, CH_MEAN + 1, row, mean[8], mean[9], mean[10], 0.f, 0.f, 0.f, 0.f, 0.f);
+    }
+    // global_fc: S = [var | mean] Wgs -> cols 0..31 ; P_v = x_v Wgv -> cols 32 + 32 v
+    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+      const uint32_t id = umma_idesc(32);
+      umma_kstep(tcol0, aT + CH_VAR * kChunkBytes, kChunkBytes, 2048, wB + UW_GS, 32 * 16, UW_BLOCK, id, 0u);
+      umma_kstep(tcol0, aT + CH_MEAN * kChunkBytes, kChunkBytes, 2048, wB + UW_GS + 2 * 32 * 16, 32 * 16, UW_BLOCK, id, 1u);
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        umma_kstep(tcol0 + 32 + 32 * v, aT + (CH_X + 2 * v) * kChunkBytes, kChunkBytes, 2048, wB + UW_GV, 32 * 16, UW_BLOCK, id, 0u);
+    });
+    // ------------------------------------------------------------ phase B: ReLU, view soft-max, pooled input of fc
+    {
+      float G[V][32];
+      {
+        float Sh[32];
+        tmem_ld16(trow, *reinterpret_cast<float(*)[16]>(&Sh[0]));
+        tmem_ld16(trow + 16, *reinterpret_cast<float(*)[16]>(&Sh[16]));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) Sh[j] += sV[UV_BG + j];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          tmem_ld16(trow + 32 + 32 * v, *reinterpret_cast<float(*)[16]>(&G[v][0]));
+          tmem_ld16(trow + 32 + 32 * v + 16, *reinterpret_cast<float(*)[16]>(&G[v][16]));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) G[v][j] = fmaxf(G[v][j] + Sh[j], 0.f);
+        }
+      }
+      float lg[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          a0 = fmaf(sV[UV_WA + j], G[v][j], a0);
+          a1 = fmaf(sV[UV_WA + j + 1], G[v][j + 1], a1);
+        }
+        lg[v] = fmaxf(a0 + a1 + ba, 0.f);
+      }
+      const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
+      const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
+      const float inv = 1.f / (e0 + e1 + e2);
+      const float w0 = e0 * inv, w1 = e1 * inv, w2 = e2 * inv;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float im[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) im[j] = fmaf(w2, G[2][8 * c + j], fmaf(w1, G[1][8 * c + j], w0 * G[0][8 * c + j]));
+        put_chunk(tile, CH_IM + c, row, im[0], im[1], im[2], im[3], im[4], im[5], im[6], im[7]);
+      }
+    }
+    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+      const uint32_t id = umma_idesc(16);
+      umma_kstep(tcol0, aT + CH_IM * kChunkBytes, kChunkBytes, 2048, wB + UW_FC, 16 * 16, UW_BLOCK, id, 0u);
+      umma_kstep(tcol0, aT + (CH_IM + 2) * kChunkBytes, kChunkBytes, 2048, wB + UW_FC + 2 * 16 * 16, 16 * 16, UW_BLOCK, id, 1u);
+    });
+    // ------------------------------------------------------------ phase C: pooled = relu(fc) -> lr0
+    {
+      float pc[16];
+      tmem_ld16(trow, pc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pc[j] = fmaxf(pc[j] + sV[UV_BFC + j], 0.f);
+      put_chunk(tile, CH_POOLED, row, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
+      put_chunk(tile, CH_POOLED + 1, row, pc[8], pc[9], pc[10], pc[11], pc[12], pc[13], pc[14], pc[15]);
+    }
+    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+      const uint32_t id = umma_idesc(64);
+      umma_kstep(tcol0, aT + CH_POOLED * kChunkBytes, kChunkBytes, 2048, wB + UW_L0, 64 * 16, UW_BLOCK, id, 0u);
+      umma_kstep(tcol0, aT + CH_VOX * kChunkBytes, kChunkBytes, 2048, wB + UW_L0 + 2 * 64 * 16, 64 * 16, UW_BLOCK, id, 1u);
+    });
+    // ------------------------------------------------------------ phase D: hid = relu(lr0), sigma
+    float sig;
+    {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float h[16];
+        tmem_ld16(trow + 16 * c, h);
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          h[j] = fmaxf(h[j] + sV[UV_BL + 16 * c + j], 0.f);
+          h[j + 1] = fmaxf(h[j + 1] + sV[UV_BL + 16 * c + j + 1], 0.f);
+          a0 = fmaf(sV[UV_WS + 16 * c + j], h[j], a0);
+          a1 = fmaf(sV[UV_WS + 16 * c + j + 1], h[j + 1], a1);
+        }
+        put_chunk(tile, CH_HID + 2 * c, row, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        put_chunk(tile, CH_HID + 2 * c + 1, row, h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+      }
+      sig = a0 + a1 + bs;
+      sig = sig > 20.f ? sig : log1pf(expf(sig));
+    }
+    // color.0: S = [hid | pooled | vox] Wcs -> cols 0..63 ; P_v = f_v Wcv -> cols 64 + 64 v
+    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+      const uint32_t id = umma_idesc(64);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_kstep(tcol0, aT + (CH_HID + 2 * ks) * kChunkBytes, kChunkBytes, 2048, wB + UW_CS + ks * 2 * 64 * 16, 64 * 16, UW_BLOCK, id, ks ? 1u : 0u);
+      umma_kstep(tcol0, aT + CH_POOLED * kChunkBytes, kChunkBytes, 2048, wB + UW_CS + 4 * 2 * 64 * 16, 64 * 16, UW_BLOCK, id, 1u);
+      umma_kstep(tcol0, aT + CH_VOX * kChunkBytes, kChunkBytes, 2048, wB + UW_CS + 5 * 2 * 64 * 16, 64 * 16, UW_BLOCK, id, 1u);
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        umma_kstep(tcol0 + 64 + 64 * v, aT + (CH_F + 2 * v) * kChunkBytes, kChunkBytes, 2048, wB + UW_CV, 64 * 16, UW_BLOCK, id, 0u);
+    });
+    // ------------------------------------------------------------ phase E: color.2, view soft-max, rgb
+    {
+      float cl[V] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float sh[16];
+        tmem_ld16(trow + 16 * c, sh);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sh[j] += sV[UV_BC + 16 * c + j];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float pv[16];
+          tmem_ld16(trow + 64 + 64 * v + 16 * c, pv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cl[v] = fmaf(sV[UV_W2 + 16 * c + j], fmaxf(pv[j] + sh[j], 0.f), cl[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) cl[v] = fmaxf(cl[v] + b2, 0.f);
+      const float mx = fmaxf(cl[0], fmaxf(cl[1], cl[2]));
+      const float e0 = expf(cl[0] - mx), e1 = expf(cl[1] - mx), e2 = expf(cl[2] - mx);
+      const float inv = 1.f / (e0 + e1 + e2);
+      float4 o;
+      o.x = (e0 * rgbv[0][0] + e1 * rgbv[1][0] + e2 * rgbv[2][0]) * inv;
+      o.y = (e0 * rgbv[0][1] + e1 * rgbv[1][1] + e2 * rgbv[2][1]) * inv;
+      o.z = (e0 * rgbv[0][2] + e1 * rgbv[1][2] + e2 * rgbv[2][2]) * inv;
+      o.w = sig;
+      if (live) reinterpret_cast<float4*>(rp.raw)[si] = o;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
+// ----------------------------------------------------------------------------------------- self test
+// D (128 x N, fp32) = A (128 x K, fp32, row-major) . B^T with B given in the packed [hi block][lo block]
+// layout ([K/8][N][8] fp16 each): one CTA, the same descriptor / issue / load helpers as the render kernel.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const uint4* __restrict__ Bp,
+                                                               float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int chunks = K / 8;
+  unsigned char* sAop = smem;                               // chunks x 4096
+  unsigned char* sB = smem + chunks * kChunkBytes;          // hi block, lo block of chunks x N x 16
+  const int bblock = chunks * N * 16;
+  for (int i = tid; i < 2 * bblock / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = Bp[i];
+  for (int c = 0; c < chunks; ++c) {
+    const float* a = A + (int64_t)tid * K + 8 * c;
+    put_chunk(sAop, c, tid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+  }
+  if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+  __syncwarp();
+  if (warp == 0) tmem_alloc_512(smem_u32(&s_tmem));
+  proxy_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  if (tid == 0) {
+    const uint32_t id = umma_idesc(N);
+    for (int ks = 0; ks < K / 16; ++ks)
+      umma_kstep(tmem_base, smem_u32(sAop) + ks * 2 * kChunkBytes, kChunkBytes, 2048, smem_u32(sB) + ks * 2 * N * 16, N * 16, bblock, id, ks ? 1u : 0u);
+    umma_commit(smem_u32(&s_mbar));
+  }
+  mbar_wait(smem_u32(&s_mbar), 0);
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int c = 0; c < N / 16; ++c) {
+    float v[16];
+    tmem_ld16(trow + 16 * c, v);
+    for (int j = 0; j < 16; ++j) D[(int64_t)tid * N + 16 * c + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
+}  // namespace bmv
+
+extern "C" BMV_API int bmv_render_rays_umma_weight_words(void) { return bmv::UMMA_PACK_WORDS; }
+
+extern "C" BMV_API int bmv_umma_selftest(const float* A, const void* B_packed, float* D, int N, int K, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(A && B_packed && D, BMV_ERR_INVALID_ARGUMENT, "bmv_umma_selftest: null pointer");
+  BMV_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K <= 96 && K % 16 == 0, BMV_ERR_UNSUPPORTED_SHAPE,
+              "bmv_umma_selftest: N=%d K=%d unsupported", N, K);
+  const size_t smem = (size_t)(K / 8) * kChunkBytes + (size_t)2 * (K / 8) * N * 16 + 128;
+  cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("bmv_umma_selftest: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    return BMV_ERR_CUDA_LAUNCH;
+  }
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, reinterpret_cast<const uint4*>(B_packed), D, N, K);
+  return check_launch("bmv_umma_selftest");
+}
+
+extern "C" BMV_API int bmv_render_rays_umma(const bmv_render_rays_params* rp, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(rp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: null params");
+  const bmv_raygen_fetch_params* p = &rp->g;
+  BMV_REQUIRE(p->n_rays >= 0 && p->ray_begin >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: bad ray range");
+  if (p->n_rays == 0) return BMV_OK;
+  BMV_REQUIRE(!p->xyz_in, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: pointwise mode is not supported here");
+  BMV_REQUIRE(p->rays12_in || (p->depth && p->std && p->near_far && (p->rays || p->ray_gen)), BMV_ERR_INVALID_ARGUMENT,
+              "bmv_render_rays_umma: null ray inputs");
+  BMV_REQUIRE(p->volume && p->im_feat && p->rgb && p->src_exts && p->src_ixts && p->src_centers && p->tar_center &&
+                  rp->mlp_weights && rp->raw,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: null device pointer");
+  BMV_REQUIRE(((uintptr_t)rp->mlp_weights & 15) == 0 && ((uintptr_t)rp->raw & 15) == 0, BMV_ERR_INVALID_ARGUMENT,
+              "bmv_render_rays_umma: weights/raw must be 16-byte aligned");
+  BMV_REQUIRE(p->S >= 1 && (p->S == 1 || p->t), BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: bad S / t");
+  BMV_REQUIRE(p->H >= 2 && p->W >= 2 && p->hv >= 1 && p->wv >= 1 && p->Hf >= 2 && p->Wf >= 2 && p->Dv >= 1,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: bad grid size");
+  BMV_REQUIRE(p->Cv == 8 && p->Cf == 8 && p->V == 3, BMV_ERR_UNSUPPORTED_SHAPE,
+              "bmv_render_rays_umma: (Cv=%d, Cf=%d, V=%d) not instantiated (8, 8, 3)", p->Cv, p->Cf, p->V);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(render_rays_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(render_rays_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+    if (e != cudaSuccess) {
+      set_error("bmv_render_rays_umma: cannot reserve %zu B shared memory: %s", kUmmaSmem, cudaGetErrorString(e));
+      return BMV_ERR_CUDA_LAUNCH;
+    }
+    configured = true;
+  }
+  // persistent: one CTA per SM owns all 512 TMEM columns (the shared-memory footprint keeps it alone on the SM)
+  const int64_t tiles = ceil_div64(p->n_rays * p->S, 128);
+  const int64_t want = ceil_div64(tiles, kUmmaTiles);
+  const unsigned blocks = (unsigned)(want < kNumSMs ? want : kNumSMs);
+  if (gather_vec_ok(*p)) render_rays_umma_kernel<true><<<blocks, kUmmaThreads, kUmmaSmem, (cudaStream_t)stream>>>(*rp);
+  else render_rays_umma_kernel<false><<<blocks, kUmmaThreads, kUmmaSmem, (cudaStream_t)stream>>>(*rp);
+  return check_launch("bmv_render_rays_umma");
+}

@@ -128,10 +128,9 @@ def _fragment_blocks(w_pad):
     return out.reshape(-1).view(torch.int32)
 
 
-def pack_nerf_weights_mma(nerf):
-    """Weights of the level-1 NeRF MLP (feat_ch = 11, 3 views) for the tensor-core kernel
-    (csrc/render_mma.cu): fragment-ordered split-fp16 blocks followed by the fp32 bias / 1-output
-    vectors.  Returns an int32 tensor (MMA_PACK_WORDS,) on the module's device."""
+def _tensor_core_matrices(nerf):
+    """The level-1 NeRF MLP (feat_ch = 11, 3 views) as the six padded (N, K) weight matrices both tensor-core
+    kernels multiply by, plus the fp32 bias / 1-output vectors (400 floats) they read in the epilogues."""
     sd = {k: v.detach().float().cpu() for k, v in nerf.state_dict().items()}
     if "agg.view_fc.0.weight" not in sd:
         raise ValueError("fused MLP requires cfg.enerf.viewdir_agg=True (the shipped configs)")
@@ -144,14 +143,51 @@ def pack_nerf_weights_mma(nerf):
     l0 = torch.zeros(64, 32); l0[:, 0:16] = wl[:, 8:24]; l0[:, 16:24] = wl[:, 0:8]                  # [pooled | vox]
     cs = torch.zeros(64, 96); cs[:, 0:64] = wc[:, 0:64]; cs[:, 64:80] = wc[:, 72:88]; cs[:, 80:88] = wc[:, 64:72]
     cv = torch.zeros(64, 16); cv[:, 0:15] = wc[:, 88:103]
-    blocks = torch.cat([_fragment_blocks(m) for m in (gs, gv, wfc.clone(), l0, cs, cv)])
     wv = torch.zeros(12, 4); wv[:F] = sd["agg.view_fc.0.weight"]
     bv = torch.zeros(12); bv[:F] = sd["agg.view_fc.0.bias"]
     vec = torch.cat([sd["agg.global_fc.0.bias"], sd["agg.agg_w_fc.0.weight"][0], sd["agg.fc.0.bias"], sd["lr0.0.bias"],
                      sd["sigma.0.weight"][0], sd["color.0.bias"], sd["color.2.weight"][0], wv.reshape(-1), bv,
                      torch.stack([sd["agg.agg_w_fc.0.bias"][0], sd["sigma.0.bias"][0], sd["color.2.bias"][0],
                                   torch.tensor(0.)])])
-    packed = torch.cat([blocks, vec.contiguous().view(torch.int32)])
+    return (gs, gv, wfc.clone(), l0, cs, cv), vec.contiguous()
+
+
+def pack_nerf_weights_mma(nerf):
+    """Weights of the level-1 NeRF MLP (feat_ch = 11, 3 views) for the tensor-core kernel
+    (csrc/render_mma.cu): fragment-ordered split-fp16 blocks followed by the fp32 bias / 1-output
+    vectors.  Returns an int32 tensor (MMA_PACK_WORDS,) on the module's device."""
+    mats, vec = _tensor_core_matrices(nerf)
+    blocks = torch.cat([_fragment_blocks(m) for m in mats])
+    packed = torch.cat([blocks, vec.view(torch.int32)])
+    return packed.to(next(nerf.parameters()).device)
+
+
+def umma_operand(w_pad):
+    """(N, K) fp32 -> (hi, lo) fp16 tensors of shape (K/8, N, 8): the SWIZZLE_NONE K-major shared-memory layout a
+    tcgen05.mma descriptor with SBO = 128 B, LBO = N*16 B addresses (K-chunk c is a slab of N rows x 16 bytes)."""
+    N, K = w_pad.shape
+    assert K % 16 == 0 and N % 8 == 0
+    hi = w_pad.half()
+    lo = (w_pad - hi.float()).half()
+    lay = lambda m: m.reshape(N, K // 8, 8).permute(1, 0, 2).contiguous()
+    return lay(hi), lay(lo)
+
+
+def pack_umma_matrix(w_pad):
+    """[hi block][lo block] of one matrix as int32 words (bmv_umma_selftest's B operand)."""
+    hi, lo = umma_operand(w_pad)
+    return torch.cat([hi.reshape(-1), lo.reshape(-1)]).view(torch.int32)
+
+
+def pack_nerf_weights_umma(nerf):
+    """Weights of the level-1 NeRF MLP for the tcgen05 kernel (csrc/render_umma.cu): [hi block][lo block] with the
+    six matrices in kernel order (UW_GS .. UW_CV), each in the layout of umma_operand, then the fp32 vectors.
+    Returns an int32 tensor (UMMA_PACK_WORDS,) on the module's device."""
+    mats, vec = _tensor_core_matrices(nerf)
+    ops = [umma_operand(m) for m in mats]
+    hi = torch.cat([h.reshape(-1) for h, _ in ops])
+    lo = torch.cat([l.reshape(-1) for _, l in ops])
+    packed = torch.cat([hi.view(torch.int32), lo.view(torch.int32), vec.view(torch.int32)])
     return packed.to(next(nerf.parameters()).device)
 
 

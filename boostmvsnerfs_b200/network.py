@@ -84,8 +84,9 @@ class EnerfNetwork(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in nerf.parameters())
         hit = self._packed.get((i, engine))
         if hit is None or hit[0] != key:
-            from .mlp_pack import pack_nerf_weights, pack_nerf_weights_mma
-            self._packed[(i, engine)] = (key, pack_nerf_weights_mma(nerf) if engine == 'mma' else pack_nerf_weights(nerf))
+            from . import mlp_pack
+            pack = {'mma': mlp_pack.pack_nerf_weights_mma, 'umma': mlp_pack.pack_nerf_weights_umma}.get(engine, mlp_pack.pack_nerf_weights)
+            self._packed[(i, engine)] = (key, pack(nerf))
         return self._packed[(i, engine)][1]
 
     def _kept(self, name):

@@ -512,13 +512,14 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
     Returns dict(raw (n,S,4), z_vals (n,S), vis_mask (n,S) [, vis_count (n,S) int32]); `out` may
     supply preallocated contiguous tensors for any of them."""
     depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
-    if engine not in ("fma", "mma"):
+    if engine not in ("fma", "mma", "umma"):
         raise BmvError(f"render_rays: unknown engine {engine!r}")
     w = packed_weights
-    if engine == "mma":
+    if engine in ("mma", "umma"):
+        words = getattr(_lib.load(), f"bmv_render_rays_{engine}_weight_words")()
         if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()
-                and w.numel() == _lib.load().bmv_render_rays_mma_weight_words()):
-            raise BmvError("render_rays(engine='mma'): weights must come from mlp_pack.pack_nerf_weights_mma")
+                and w.numel() == words):
+            raise BmvError(f"render_rays(engine='{engine}'): weights must come from mlp_pack.pack_nerf_weights_{engine}")
     else:
         w = _cf32(w, "packed_weights")
     dev = depth.device
@@ -546,8 +547,24 @@ def render_rays(depth, std, near_far, rays, H, W, depth_inv, S, volume, im_feat,
     else:
         raw = res["raw"] = torch.empty((n, S, 4), device=dev)
     rp.mlp_weights, rp.raw = w.data_ptr(), raw.data_ptr()
-    _lib.call("bmv_render_rays_mma" if engine == "mma" else "bmv_render_rays", rp, _stream())
+    _lib.call({"mma": "bmv_render_rays_mma", "umma": "bmv_render_rays_umma"}.get(engine, "bmv_render_rays"), rp, _stream())
     return res
+
+
+def umma_selftest(a, w):
+    """a (128,K) fp32 CUDA, w (N,K) fp32 -> a @ w.T through bmv_umma_selftest (one tcgen05 tile, split-fp16 operands)."""
+    from .mlp_pack import pack_umma_matrix
+    a = _cf32(a, "a")
+    N, K = w.shape
+    if a.shape != (128, K):
+        raise BmvError(f"umma_selftest: a must be (128, {K})")
+    b = pack_umma_matrix(w.detach().float().cpu()).to(a.device)
+    d = torch.empty((128, N), device=a.device)
+    lib = _lib.load()
+    rc = lib.bmv_umma_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), int(N), int(K), _stream())
+    if rc != 0:
+        raise BmvError(f"bmv_umma_selftest failed with status {rc}: {lib.bmv_last_error_string().decode()}")
+    return d
 
 
 # ------------------------------------------------------------------------------------------ K1b / K3b (MVSNeRF)

@@ -267,6 +267,16 @@ BMV_API int bmv_render_rays_supported(int Cv, int Cf, int V);
  * Instantiated for Cv=8, Cf=8, V=3 (the ENeRF level-1 MLP). */
 BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* p, bmv_stream_t stream);
 BMV_API int bmv_render_rays_mma_weight_words(void);
+/* 5th-generation tensor-core variant (csrc/render_umma.cu): same contract and the same split-fp16 arithmetic,
+ * every Linear layer issued as tcgen05.mma on 128-sample tiles (operands in shared memory in the UMMA
+ * K-major layout, accumulators in tensor memory, read back with tcgen05.ld); two tiles ping-pong per CTA.
+ * mlp_weights must come from the UMMA packing (bmv_render_rays_umma_weight_words 32-bit words). */
+BMV_API int bmv_render_rays_umma(const bmv_render_rays_params* p, bmv_stream_t stream);
+BMV_API int bmv_render_rays_umma_weight_words(void);
+/* Unit test hook for the tcgen05 plumbing (descriptors, TMEM allocation, commit, tcgen05.ld):
+ * D (128,N) fp32 = A (128,K) fp32 . B^T, B (N,K) given as [hi block][lo block] of (K/8,N,8) fp16
+ * (mlp_pack.pack_umma_matrix); N % 16 == 0, 16 <= N <= 256, K % 16 == 0, K <= 96.  Device pointers. */
+BMV_API int bmv_umma_selftest(const float* A, const void* B_packed, float* D, int N, int K, bmv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1b  MVSNeRF cost volume with colour channels.
