@@ -36,7 +36,7 @@ constexpr int UW_CV = UW_CS + 64 * 96 * 2;     // color.0 per-view f_v       : N
 constexpr int UW_BLOCK = UW_CV + 64 * 16 * 2;  // bytes per hi (or lo) block = 22528
 // fp32 vectors (float offsets from the start of the vector area) — same order as the mma.sync packing
 constexpr int UV_BG = 0, UV_WA = 32, UV_BFC = 64, UV_BL = 80, UV_WS = 144, UV_BC = 208, UV_W2 = 272, UV_WV = 336,
-              UV_BV = 384, UV_SC = 396, UV_COUNT = 400;
+              UV_BV = 384, UV_SC = 396, UV_TAG = 400, UV_COUNT = 404;   // UV_TAG: 'UMMA' + 3 zero words (packing id)
 constexpr int UMMA_PACK_BYTES = 2 * UW_BLOCK + UV_COUNT * 4;
 constexpr int UMMA_PACK_WORDS = UMMA_PACK_BYTES / 4;
 
@@ -45,7 +45,7 @@ constexpr int CH_VAR = 0, CH_MEAN = 2, CH_X = 4;          // phase A (x_v at CH_
 constexpr int CH_IM = 0;                                  // phase B (aliases var/mean)
 constexpr int CH_HID = 0;                                 // phase D (aliases 0..7)
 constexpr int CH_F = 10;                                  // f_v at CH_F + 2v, live from phase A to E
-constexpr int CH_POOLED = 16, CH_VOX = 18, CH_ZERO = 19;
+constexpr int CH_POOLED = 16, CH_VOX = 18, CH_ONE = 19;    // CH_ONE: (1, 0, ..., 0), the bias column of lr0 / color.0
 constexpr int kTileChunks = 20;
 constexpr int kChunkBytes = 4096;                         // hi slab (128 rows x 16 B) + lo slab
 constexpr int kTileBytes = kTileChunks * kChunkBytes;     // 81920
@@ -138,22 +138,159 @@ __device__ __forceinline__ void put_chunk(unsigned char* tile, int chunk, int ro
   *reinterpret_cast<uint4*>(q + 2048) = lo;
 }
 
-// All 128 threads of a tile: publish the operand rows just written, then ONE thread issues `issue()`'s MMAs
-// and commits them to the tile's mbarrier; everybody waits for the accumulators.
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float4 lds4f(const float* q) { return *reinterpret_cast<const float4*>(q); }
+
+// All 128 threads of a tile: publish the operand rows just written; ONE thread (`leader`) issues the MMAs.
 template <class Issue>
-__device__ __forceinline__ void tile_mma_phase(int wg, bool leader, uint32_t mbar, uint32_t& parity, Issue issue) {
+__device__ __forceinline__ void tile_publish_and_issue(int wg, bool leader, Issue issue) {
   proxy_fence_async();                 // generic-proxy st.shared -> visible to the tensor core (async proxy)
   tc_fence_before();                   // earlier tcgen05.ld of the columns about to be overwritten
   bar_sync_named(1 + wg, 128);
   if (leader) {
     tc_fence_after();
     issue();
-    umma_commit(mbar);
   }
+}
+// ... and everybody waits for the accumulators of that commit
+__device__ __forceinline__ void tile_wait(uint32_t mbar, uint32_t parity) {
   mbar_wait(mbar, parity);
-  parity ^= 1u;
   __syncwarp();
   tc_fence_after();
+}
+
+// ----------------------------------------------------------------------------------------- pipelined gather
+// The gather of tile i+1 is split into four parts whose global loads are ISSUED right after the MMAs of a phase
+// of tile i were handed to the tensor core and CONSUMED after that phase's epilogue, so their latency (and
+// the MMA latency) is covered by the thread's own work instead of by other warps (there are only 8 per SM).
+// Arithmetic and operation order are those of gather_sample_regs<8, 3, true>.
+struct NextSample {
+  float x, y, zz, gxv, gyv, dn, ttx, tty, ttz;
+  int cnt;
+};
+struct VoxTaps { float4 a[8], b[8]; float w[8]; };
+struct ViewTaps { float4 fa[4], fb[4], c[4]; float w[4]; };
+
+__device__ __forceinline__ void next_setup(const bmv_raygen_fetch_params& p, const float* tar_c, int64_t si, bool live,
+                                           NextSample& ns) {
+  const int S = p.S;
+  const int64_t li = si / S;
+  const int s = (int)(si % S);
+  const RaySetup r = ray_setup(p, li);
+  const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
+  ns.gxv = sub_rn(mul_rn(un, 2.f), 1.f);
+  ns.gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
+  const SamplePoint q = sample_point(p, r, s);
+  ns.x = q.x; ns.y = q.y; ns.zz = q.zz; ns.dn = q.dn;
+  if (live && p.z_vals) p.z_vals[si] = q.z;
+  float ttx = sub_rn(q.x, tar_c[0]), tty = sub_rn(q.y, tar_c[1]), ttz = sub_rn(q.zz, tar_c[2]);
+  const float n = sqrtf(ttx * ttx + tty * tty + ttz * ttz) + 1e-6f;
+  ns.ttx = __fdividef(ttx, n); ns.tty = __fdividef(tty, n); ns.ttz = __fdividef(ttz, n);
+  ns.cnt = 0;
+}
+
+__device__ __forceinline__ void vox_issue(const bmv_raygen_fetch_params& p, const NextSample& ns, VoxTaps& t) {
+  const float gz = sub_rn(mul_rn(ns.dn, 2.f), 1.f);
+  const float ix = unnormalize_ac(ns.gxv, p.wv), iy = unnormalize_ac(ns.gyv, p.hv), iz = unnormalize_ac(gz, p.Dv);
+  const bool fin = coord_ok(ix) && coord_ok(iy) && coord_ok(iz);
+  const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+  const float fx1 = ix - x0, fy1 = iy - y0, fz1 = iz - z0;
+  const float fx0 = (x0 + 1.f) - ix, fy0 = (y0 + 1.f) - iy, fz0 = (z0 + 1.f) - iz;
+#pragma unroll
+  for (int corner = 0; corner < 8; ++corner) {
+    const int bx = corner & 1, by = (corner >> 1) & 1, bz = corner >> 2;
+    const float cxf = x0 + bx, cyf = y0 + by, czf = z0 + bz;
+    const bool ok = fin && cxf >= 0.f && cxf <= (float)(p.wv - 1) && cyf >= 0.f && cyf <= (float)(p.hv - 1) &&
+                    czf >= 0.f && czf <= (float)(p.Dv - 1);
+    t.w[corner] = (bx ? fx1 : fx0) * (by ? fy1 : fy0) * (bz ? fz1 : fz0);
+    if (ok) {
+      const float* src = p.volume + (int64_t)czf * p.vol_d_stride + (int64_t)cyf * p.vol_y_stride + (int64_t)cxf * p.vol_x_stride;
+      t.a[corner] = ldg4(src);
+      t.b[corner] = ldg4(src + 4);
+    } else {                                              // the reference skips the corner: contributes exactly 0
+      t.a[corner] = make_float4(0.f, 0.f, 0.f, 0.f);
+      t.b[corner] = make_float4(0.f, 0.f, 0.f, 0.f);
+      t.w[corner] = 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void vox_consume(const VoxTaps& t, float (&vox)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) vox[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = t.w[k];
+    const float4 a = t.a[k], b = t.b[k];
+    vox[0] = fmaf(w, a.x, vox[0]); vox[1] = fmaf(w, a.y, vox[1]); vox[2] = fmaf(w, a.z, vox[2]); vox[3] = fmaf(w, a.w, vox[3]);
+    vox[4] = fmaf(w, b.x, vox[4]); vox[5] = fmaf(w, b.y, vox[5]); vox[6] = fmaf(w, b.z, vox[6]); vox[7] = fmaf(w, b.w, vox[7]);
+  }
+}
+
+// view v: visibility, projection, taps (loads in flight in `t`), direction features -> f[11..14]
+__device__ __forceinline__ void view_issue(const bmv_raygen_fetch_params& p, const ViewCam& cam, int view, NextSample& ns,
+                                           ViewTaps& t, float (&f)[15]) {
+  const float isx = (float)(p.W - 1), isy = (float)(p.H - 1);
+  const float x = ns.x, y = ns.y, zz = ns.zz;
+  ns.cnt += point_visible(cam, x, y, zz, isx, isy) ? 1 : 0;
+  const float cx = dot4_gemm(x, y, zz, 1.f, cam.E[0], cam.E[1], cam.E[2], cam.E[3]);
+  const float cy = dot4_gemm(x, y, zz, 1.f, cam.E[4], cam.E[5], cam.E[6], cam.E[7]);
+  const float cz = dot4_gemm(x, y, zz, 1.f, cam.E[8], cam.E[9], cam.E[10], cam.E[11]);
+  const float rs = p.render_scale;
+  const float qx = dot3_gemm(cx, cy, cz, mul_rn(cam.K[0], rs), mul_rn(cam.K[1], rs), mul_rn(cam.K[2], rs));
+  const float qy = dot3_gemm(cx, cy, cz, mul_rn(cam.K[3], rs), mul_rn(cam.K[4], rs), mul_rn(cam.K[5], rs));
+  const float qz = dot3_gemm(cx, cy, cz, cam.K[6], cam.K[7], cam.K[8]);
+  const float qzc = (qz != qz) ? qz : fmaxf(qz, 1e-6f);
+  float gx = __fdividef(__fdividef(qx, qzc), (float)(p.Wf - 1));
+  float gy = __fdividef(__fdividef(qy, qzc), (float)(p.Hf - 1));
+  gx = sub_rn(mul_rn(gx, 2.f), 1.f);
+  gy = sub_rn(mul_rn(gy, 2.f), 1.f);
+  const Tap2 tp = border_taps(gx, gy, p.Hf, p.Wf, p.imf_y_stride, p.imf_x_stride);
+  const float* fm = p.im_feat + (int64_t)view * p.imf_view_stride;
+  t.fa[0] = ldg4(fm + tp.o00); t.fb[0] = ldg4(fm + tp.o00 + 4);
+  t.fa[1] = ldg4(fm + tp.o01); t.fb[1] = ldg4(fm + tp.o01 + 4);
+  t.fa[2] = ldg4(fm + tp.o10); t.fb[2] = ldg4(fm + tp.o10 + 4);
+  t.fa[3] = ldg4(fm + tp.o11); t.fb[3] = ldg4(fm + tp.o11 + 4);
+  const Tap2 tr = border_taps(gx, gy, p.Hf, p.Wf, p.rgb_y_stride, 4);
+  const float* fr = p.rgb + (int64_t)view * p.rgb_view_stride;
+  t.c[0] = ldg4(fr + tr.o00); t.c[1] = ldg4(fr + tr.o01); t.c[2] = ldg4(fr + tr.o10); t.c[3] = ldg4(fr + tr.o11);
+  t.w[0] = tp.w00; t.w[1] = tp.w01; t.w[2] = tp.w10; t.w[3] = tp.w11;
+  float sx = sub_rn(x, cam.c[0]), sy = sub_rn(y, cam.c[1]), sz = sub_rn(zz, cam.c[2]);
+  const float n = sqrtf(sx * sx + sy * sy + sz * sz) + 1e-6f;
+  sx = __fdividef(sx, n); sy = __fdividef(sy, n); sz = __fdividef(sz, n);
+  const float ex = sub_rn(ns.ttx, sx), ey = sub_rn(ns.tty, sy), ez = sub_rn(ns.ttz, sz);
+  const float en = fmaxf(sqrtf(ex * ex + ey * ey + ez * ez), 1e-6f);
+  f[11] = __fdividef(ex, en);
+  f[12] = __fdividef(ey, en);
+  f[13] = __fdividef(ez, en);
+  f[14] = ns.ttx * sx + ns.tty * sy + ns.ttz * sz;
+}
+__device__ __forceinline__ void view_consume(const bmv_raygen_fetch_params& p, const ViewTaps& t, float (&f)[15]) {
+  const float w00 = t.w[0], w01 = t.w[1], w10 = t.w[2], w11 = t.w[3];
+  f[0] = fmaf(w11, t.fa[3].x, fmaf(w10, t.fa[2].x, fmaf(w01, t.fa[1].x, w00 * t.fa[0].x)));
+  f[1] = fmaf(w11, t.fa[3].y, fmaf(w10, t.fa[2].y, fmaf(w01, t.fa[1].y, w00 * t.fa[0].y)));
+  f[2] = fmaf(w11, t.fa[3].z, fmaf(w10, t.fa[2].z, fmaf(w01, t.fa[1].z, w00 * t.fa[0].z)));
+  f[3] = fmaf(w11, t.fa[3].w, fmaf(w10, t.fa[2].w, fmaf(w01, t.fa[1].w, w00 * t.fa[0].w)));
+  f[4] = fmaf(w11, t.fb[3].x, fmaf(w10, t.fb[2].x, fmaf(w01, t.fb[1].x, w00 * t.fb[0].x)));
+  f[5] = fmaf(w11, t.fb[3].y, fmaf(w10, t.fb[2].y, fmaf(w01, t.fb[1].y, w00 * t.fb[0].y)));
+  f[6] = fmaf(w11, t.fb[3].z, fmaf(w10, t.fb[2].z, fmaf(w01, t.fb[1].z, w00 * t.fb[0].z)));
+  f[7] = fmaf(w11, t.fb[3].w, fmaf(w10, t.fb[2].w, fmaf(w01, t.fb[1].w, w00 * t.fb[0].w)));
+  const float sc = p.rgb_scale, sf = p.rgb_shift;
+  f[8] = fmaf(w11, fmaf(t.c[3].x, sc, sf), fmaf(w10, fmaf(t.c[2].x, sc, sf), fmaf(w01, fmaf(t.c[1].x, sc, sf), w00 * fmaf(t.c[0].x, sc, sf))));
+  f[9] = fmaf(w11, fmaf(t.c[3].y, sc, sf), fmaf(w10, fmaf(t.c[2].y, sc, sf), fmaf(w01, fmaf(t.c[1].y, sc, sf), w00 * fmaf(t.c[0].y, sc, sf))));
+  f[10] = fmaf(w11, fmaf(t.c[3].z, sc, sf), fmaf(w10, fmaf(t.c[2].z, sc, sf), fmaf(w01, fmaf(t.c[1].z, sc, sf), w00 * fmaf(t.c[0].z, sc, sf))));
 }
 
 template <bool VEC>
@@ -163,28 +300,29 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   unsigned char* sW = smem;                                             // hi block, lo block
-  const float* sV = reinterpret_cast<const float*>(smem + 2 * UW_BLOCK);  // fp32 vectors
+  const float* sV = reinterpret_cast<const float*>(smem + 2 * UW_BLOCK);  // fp32 vectors (16-byte aligned)
   unsigned char* sA = smem + kPackPadded;                               // operand tiles
   __shared__ ViewCam cams[V];
   __shared__ float s_tar_c[3];
   __shared__ int s_view[V];
-  __shared__ __align__(8) uint64_t s_mbar[kUmmaTiles];
+  __shared__ __align__(8) uint64_t s_mbar[kUmmaTiles][4];               // [tile][0: phases A-C, 1..3: color.0 of view v]
   __shared__ uint32_t s_tmem;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int wg = warp >> 2, row = tid & 127;
   for (int i = tid * 16; i < UMMA_PACK_BYTES; i += kUmmaThreads * 16)
     *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(rp.mlp_weights) + i));
   if (tid < V) s_view[tid] = p.view[tid];
   if (tid == 0) {
-    for (int w = 0; w < kUmmaTiles; ++w) mbar_init(smem_u32(&s_mbar[w]), 1);
+    for (int w = 0; w < kUmmaTiles; ++w)
+      for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&s_mbar[w][k]), 1);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc_512(smem_u32(&s_tmem));
   unsigned char* tile = sA + wg * kTileBytes;
-  // the zero K-chunk next to vox never changes
-  *reinterpret_cast<uint4*>(tile + CH_ZERO * kChunkBytes + row * 16) = make_uint4(0, 0, 0, 0);
-  *reinterpret_cast<uint4*>(tile + CH_ZERO * kChunkBytes + 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+  // the constant K-chunk after vox, (1, 0, ..., 0): its 1 multiplies the bias column folded into lr0 / color.0
+  *reinterpret_cast<uint4*>(tile + CH_ONE * kChunkBytes + row * 16) = make_uint4(0x00003C00u, 0, 0, 0);
+  *reinterpret_cast<uint4*>(tile + CH_ONE * kChunkBytes + 2048 + row * 16) = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -195,42 +333,48 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
   const uint32_t tmem_base = s_tmem;
   const uint32_t tcol0 = tmem_base + (uint32_t)(wg * kTmemColsPerTile);            // columns of this tile (issuer)
   const uint32_t trow = tcol0 + ((uint32_t)((warp & 3) * 32) << 16);               // + this warp's lane quarter (loads)
-  const uint32_t mbar = smem_u32(&s_mbar[wg]);
+  const uint32_t mbar0 = smem_u32(&s_mbar[wg][0]);
   const uint32_t aT = smem_u32(tile), wB = smem_u32(sW);
-  const bool leader = (row == 0);
-  uint32_t parity = 0;
+  uint32_t par0 = 0, parE = 0;
   const int S = p.S;
   const int64_t n_samples = p.n_rays * S;
   const int64_t n_tiles = (n_samples + 127) / 128;
+  const int64_t tstride = (int64_t)gridDim.x * kUmmaTiles;
   const float ba = sV[UV_SC], bs = sV[UV_SC + 1], b2 = sV[UV_SC + 2];
+  constexpr uint32_t LBO_A = kChunkBytes, LO_A = 2048, LO_B = UW_BLOCK;
 
-  for (int64_t tix = (int64_t)blockIdx.x * kUmmaTiles + wg; tix < n_tiles; tix += (int64_t)gridDim.x * kUmmaTiles) {
-    const int64_t si = tix * 128 + row;
-    const bool live = si < n_samples;
+  // gathered sample of the tile about to be processed (filled by the prologue / by the previous iteration)
+  float vox[8];
+  float f[V][CF + 7];
+  int64_t tix = (int64_t)blockIdx.x * kUmmaTiles + wg;
+  if (tix < n_tiles) {
+    const int64_t si_raw = tix * 128 + row;
+    const bool live = si_raw < n_samples;
+    const int64_t si = live ? si_raw : n_samples - 1;
+    const int64_t li = si / S;
+    const int s = (int)(si % S);
+    const RaySetup r = ray_setup(p, li);
+    const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
+    const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
+    const SamplePoint q = sample_point(p, r, s);
+    const int cnt = gather_sample_regs<CF, V, VEC>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
+    if (live) {
+      if (p.z_vals) p.z_vals[si] = q.z;
+      if (p.vis_mask) p.vis_mask[si] = div_rn((float)cnt, (float)V);
+      if (p.vis_count) p.vis_count[si] = cnt;
+    }
+  }
+
+  for (; tix < n_tiles; tix += tstride) {
+    const int64_t si_out = tix * 128 + row;
+    const bool live_out = si_out < n_samples;
+    const bool has_next = tix + tstride < n_tiles;               // uniform over the tile's 4 warps
+    const int64_t nsi_raw = (tix + tstride) * 128 + row;
+    const bool nlive = has_next && nsi_raw < n_samples;
+    const int64_t nsi = nsi_raw < n_samples ? nsi_raw : n_samples - 1;
     float rgbv[V][3];
-    // ------------------------------------------------------------ phase A: gather, view_fc, mean / variance
+    // ------------------------------------------------------------ phase A: view_fc, mean / variance, operand rows
     {
-      float vox[8];
-      float f[V][CF + 7];
-      if (live) {
-        const int64_t li = si / S;
-        const int s = (int)(si % S);
-        const RaySetup r = ray_setup(p, li);
-        const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
-        const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
-        const SamplePoint q = sample_point(p, r, s);
-        const int cnt = gather_sample_regs<CF, V, VEC>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
-        if (p.z_vals) p.z_vals[si] = q.z;
-        if (p.vis_mask) p.vis_mask[si] = div_rn((float)cnt, (float)V);
-        if (p.vis_count) p.vis_count[si] = cnt;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) vox[c] = 0.f;
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-#pragma unroll
-          for (int c = 0; c < CF + 7; ++c) f[v][c] = 0.f;
-      }
       put_chunk(tile, CH_VOX, row, vox[0], vox[1], vox[2], vox[3], vox[4], vox[5], vox[6], vox[7]);
       float x[V][11];
 #pragma unroll
@@ -240,7 +384,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
         rgbv[v][0] = f[v][8]; rgbv[v][1] = f[v][9]; rgbv[v][2] = f[v][10];
 #pragma unroll
         for (int c = 0; c < 11; ++c) {
-          const float4 w = *reinterpret_cast<const float4*>(sV + UV_WV + c * 4);
+          const float4 w = lds4f(sV + UV_WV + c * 4);
           const float e = fmaf(w.w, f[v][14], fmaf(w.z, f[v][13], fmaf(w.y, f[v][12], fmaf(w.x, f[v][11], sV[UV_BV + c]))));
           x[v][c] = f[v][c] + fmaxf(e, 0.f);
         }
@@ -256,130 +400,151 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
         var[c] = fmaf(e2, e2, fmaf(e1, e1, e0 * e0)) * 0.5f;
       }
       put_chunk(tile, CH_VAR, row, var[0], var[1], var[2], var[3], var[4], var[5], var[6], var[7]);
-      put_chunk(tile, CH_VAR + 1, row, var[8], var[9], var[10], 0.f, 0.f, 0.f, 0.f, 0.f);
+      put_chunk(tile, CH_VAR + 1, row, var[8], var[9], var[10], 0.f, 0.f, 0.f, 0.f, 1.f);     // K index 15: global_fc bias column
       put_chunk(tile, CH_MEAN, row, mean[0], mean[1], mean[2], mean[3], mean[4], mean[5], mean[6], mean[7]);
       put_chunk(tile, CH_MEAN + 1, row, mean[8], mean[9], mean[10], 0.f, 0.f, 0.f, 0.f, 0.f);
     }
-    // global_fc: S = [var | mean] Wgs -> cols 0..31 ; P_v = x_v Wgv -> cols 32 + 32 v
-    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+    // global_fc (+bias, folded): G_v = [var | mean] Wgs + x_v Wgv -> cols 32 v
+    tile_publish_and_issue(wg, row == 0, [&]() {
       const uint32_t id = umma_idesc(32);
-      umma_kstep(tcol0, aT + CH_VAR * kChunkBytes, kChunkBytes, 2048, wB + UW_GS, 32 * 16, UW_BLOCK, id, 0u);
-      umma_kstep(tcol0, aT + CH_MEAN * kChunkBytes, kChunkBytes, 2048, wB + UW_GS + 2 * 32 * 16, 32 * 16, UW_BLOCK, id, 1u);
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        umma_kstep(tcol0 + 32 + 32 * v, aT + (CH_X + 2 * v) * kChunkBytes, kChunkBytes, 2048, wB + UW_GV, 32 * 16, UW_BLOCK, id, 0u);
-    });
-    // ------------------------------------------------------------ phase B: ReLU, view soft-max, pooled input of fc
-    {
-      float G[V][32];
-      {
-        float Sh[32];
-        tmem_ld16(trow, *reinterpret_cast<float(*)[16]>(&Sh[0]));
-        tmem_ld16(trow + 16, *reinterpret_cast<float(*)[16]>(&Sh[16]));
-#pragma unroll
-        for (int j = 0; j < 32; ++j) Sh[j] += sV[UV_BG + j];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          tmem_ld16(trow + 32 + 32 * v, *reinterpret_cast<float(*)[16]>(&G[v][0]));
-          tmem_ld16(trow + 32 + 32 * v + 16, *reinterpret_cast<float(*)[16]>(&G[v][16]));
-#pragma unroll
-          for (int j = 0; j < 32; ++j) G[v][j] = fmaxf(G[v][j] + Sh[j], 0.f);
-        }
+      for (int v = 0; v < V; ++v) {
+        umma_kstep(tcol0 + 32 * v, aT + CH_VAR * kChunkBytes, LBO_A, LO_A, wB + UW_GS, 32 * 16, LO_B, id, 0u);
+        umma_kstep(tcol0 + 32 * v, aT + CH_MEAN * kChunkBytes, LBO_A, LO_A, wB + UW_GS + 2 * 32 * 16, 32 * 16, LO_B, id, 1u);
+        umma_kstep(tcol0 + 32 * v, aT + (CH_X + 2 * v) * kChunkBytes, LBO_A, LO_A, wB + UW_GV, 32 * 16, LO_B, id, 1u);
       }
+      umma_commit(mbar0);
+    });
+    NextSample ns;
+    VoxTaps vt;
+    if (VEC && has_next) {
+      next_setup(p, s_tar_c, nsi, nlive, ns);
+      vox_issue(p, ns, vt);
+    }
+    tile_wait(mbar0, par0); par0 ^= 1u;
+    // ------------------------------------------------------------ phase B: ReLU, view soft-max, input of fc
+    {
       float lg[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        float a0 = 0.f, a1 = 0.f;
+        float G[32];
+        tmem_ld32(trow + 32 * v, G);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          a0 = fmaf(sV[UV_WA + j], G[v][j], a0);
-          a1 = fmaf(sV[UV_WA + j + 1], G[v][j + 1], a1);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 w = lds4f(sV + UV_WA + j);
+          a0 = fmaf(w.x, fmaxf(G[j], 0.f), a0); a1 = fmaf(w.y, fmaxf(G[j + 1], 0.f), a1);
+          a2 = fmaf(w.z, fmaxf(G[j + 2], 0.f), a2); a3 = fmaf(w.w, fmaxf(G[j + 3], 0.f), a3);
         }
-        lg[v] = fmaxf(a0 + a1 + ba, 0.f);
+        lg[v] = fmaxf((a0 + a1) + (a2 + a3) + ba, 0.f);
       }
       const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
       const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
       const float inv = 1.f / (e0 + e1 + e2);
       const float w0 = e0 * inv, w1 = e1 * inv, w2 = e2 * inv;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float im[8];
+      for (int h = 0; h < 2; ++h) {
+        float g0[16], g1[16], g2[16];
+        tmem_ld16(trow + 16 * h, g0);
+        tmem_ld16(trow + 32 + 16 * h, g1);
+        tmem_ld16(trow + 64 + 16 * h, g2);
+        float im[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) im[j] = fmaf(w2, G[2][8 * c + j], fmaf(w1, G[1][8 * c + j], w0 * G[0][8 * c + j]));
-        put_chunk(tile, CH_IM + c, row, im[0], im[1], im[2], im[3], im[4], im[5], im[6], im[7]);
+        for (int j = 0; j < 16; ++j) im[j] = fmaf(w2, fmaxf(g2[j], 0.f), fmaf(w1, fmaxf(g1[j], 0.f), w0 * fmaxf(g0[j], 0.f)));
+        put_chunk(tile, CH_IM + 2 * h, row, im[0], im[1], im[2], im[3], im[4], im[5], im[6], im[7]);
+        put_chunk(tile, CH_IM + 2 * h + 1, row, im[8], im[9], im[10], im[11], im[12], im[13], im[14], im[15]);
       }
     }
-    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+    if (VEC && has_next) vox_consume(vt, vox);
+    tile_publish_and_issue(wg, row == 32, [&]() {
       const uint32_t id = umma_idesc(16);
-      umma_kstep(tcol0, aT + CH_IM * kChunkBytes, kChunkBytes, 2048, wB + UW_FC, 16 * 16, UW_BLOCK, id, 0u);
-      umma_kstep(tcol0, aT + (CH_IM + 2) * kChunkBytes, kChunkBytes, 2048, wB + UW_FC + 2 * 16 * 16, 16 * 16, UW_BLOCK, id, 1u);
+      umma_kstep(tcol0 + 96, aT + CH_IM * kChunkBytes, LBO_A, LO_A, wB + UW_FC, 16 * 16, LO_B, id, 0u);
+      umma_kstep(tcol0 + 96, aT + (CH_IM + 2) * kChunkBytes, LBO_A, LO_A, wB + UW_FC + 2 * 16 * 16, 16 * 16, LO_B, id, 1u);
+      umma_commit(mbar0);
     });
+    ViewTaps wt;
+    if (VEC && has_next) view_issue(p, cams[0], s_view[0], ns, wt, f[0]);
+    tile_wait(mbar0, par0); par0 ^= 1u;
     // ------------------------------------------------------------ phase C: pooled = relu(fc) -> lr0
     {
       float pc[16];
-      tmem_ld16(trow, pc);
+      tmem_ld16(trow + 96, pc);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pc[j] = fmaxf(pc[j] + sV[UV_BFC + j], 0.f);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = lds4f(sV + UV_BFC + j);
+        pc[j] = fmaxf(pc[j] + b.x, 0.f); pc[j + 1] = fmaxf(pc[j + 1] + b.y, 0.f);
+        pc[j + 2] = fmaxf(pc[j + 2] + b.z, 0.f); pc[j + 3] = fmaxf(pc[j + 3] + b.w, 0.f);
+      }
       put_chunk(tile, CH_POOLED, row, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
       put_chunk(tile, CH_POOLED + 1, row, pc[8], pc[9], pc[10], pc[11], pc[12], pc[13], pc[14], pc[15]);
     }
-    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+    if (VEC && has_next) view_consume(p, wt, f[0]);
+    tile_publish_and_issue(wg, row == 64, [&]() {
       const uint32_t id = umma_idesc(64);
-      umma_kstep(tcol0, aT + CH_POOLED * kChunkBytes, kChunkBytes, 2048, wB + UW_L0, 64 * 16, UW_BLOCK, id, 0u);
-      umma_kstep(tcol0, aT + CH_VOX * kChunkBytes, kChunkBytes, 2048, wB + UW_L0 + 2 * 64 * 16, 64 * 16, UW_BLOCK, id, 1u);
+      umma_kstep(tcol0 + 112, aT + CH_POOLED * kChunkBytes, LBO_A, LO_A, wB + UW_L0, 64 * 16, LO_B, id, 0u);
+      umma_kstep(tcol0 + 112, aT + CH_VOX * kChunkBytes, LBO_A, LO_A, wB + UW_L0 + 2 * 64 * 16, 64 * 16, LO_B, id, 1u);
+      umma_commit(mbar0);
     });
-    // ------------------------------------------------------------ phase D: hid = relu(lr0), sigma
+    if (VEC && has_next) view_issue(p, cams[1], s_view[1], ns, wt, f[1]);
+    tile_wait(mbar0, par0); par0 ^= 1u;
+    // ------------------------------------------------------------ phase D: hid = relu(lr0 + bias (folded)), sigma
     float sig;
     {
-      float a0 = 0.f, a1 = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float h[16];
-        tmem_ld16(trow + 16 * c, h);
+        tmem_ld16(trow + 112 + 16 * c, h);
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          h[j] = fmaxf(h[j] + sV[UV_BL + 16 * c + j], 0.f);
-          h[j + 1] = fmaxf(h[j + 1] + sV[UV_BL + 16 * c + j + 1], 0.f);
-          a0 = fmaf(sV[UV_WS + 16 * c + j], h[j], a0);
-          a1 = fmaf(sV[UV_WS + 16 * c + j + 1], h[j + 1], a1);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 w = lds4f(sV + UV_WS + 16 * c + j);
+          h[j] = fmaxf(h[j], 0.f); h[j + 1] = fmaxf(h[j + 1], 0.f); h[j + 2] = fmaxf(h[j + 2], 0.f); h[j + 3] = fmaxf(h[j + 3], 0.f);
+          a0 = fmaf(w.x, h[j], a0); a1 = fmaf(w.y, h[j + 1], a1); a2 = fmaf(w.z, h[j + 2], a2); a3 = fmaf(w.w, h[j + 3], a3);
         }
         put_chunk(tile, CH_HID + 2 * c, row, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
         put_chunk(tile, CH_HID + 2 * c + 1, row, h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
       }
-      sig = a0 + a1 + bs;
+      sig = (a0 + a1) + (a2 + a3) + bs;
       sig = sig > 20.f ? sig : log1pf(expf(sig));
     }
-    // color.0: S = [hid | pooled | vox] Wcs -> cols 0..63 ; P_v = f_v Wcv -> cols 64 + 64 v
-    tile_mma_phase(wg, leader, mbar, parity, [&]() {
+    if (VEC && has_next) view_consume(p, wt, f[1]);
+    // color.0 (+bias, folded) per view: C_v = [hid | pooled | vox | 1] Wcs + f_v Wcv -> cols 64 v, one commit per view
+    tile_publish_and_issue(wg, row == 96, [&]() {
       const uint32_t id = umma_idesc(64);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_kstep(tcol0, aT + (CH_HID + 2 * ks) * kChunkBytes, kChunkBytes, 2048, wB + UW_CS + ks * 2 * 64 * 16, 64 * 16, UW_BLOCK, id, ks ? 1u : 0u);
-      umma_kstep(tcol0, aT + CH_POOLED * kChunkBytes, kChunkBytes, 2048, wB + UW_CS + 4 * 2 * 64 * 16, 64 * 16, UW_BLOCK, id, 1u);
-      umma_kstep(tcol0, aT + CH_VOX * kChunkBytes, kChunkBytes, 2048, wB + UW_CS + 5 * 2 * 64 * 16, 64 * 16, UW_BLOCK, id, 1u);
+      for (int v = 0; v < V; ++v) {
+        const uint32_t d = tcol0 + 64 * v;
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        umma_kstep(tcol0 + 64 + 64 * v, aT + (CH_F + 2 * v) * kChunkBytes, kChunkBytes, 2048, wB + UW_CV, 64 * 16, UW_BLOCK, id, 0u);
+        for (int ks = 0; ks < 4; ++ks)
+          umma_kstep(d, aT + (CH_HID + 2 * ks) * kChunkBytes, LBO_A, LO_A, wB + UW_CS + ks * 2 * 64 * 16, 64 * 16, LO_B, id, ks ? 1u : 0u);
+        umma_kstep(d, aT + CH_POOLED * kChunkBytes, LBO_A, LO_A, wB + UW_CS + 4 * 2 * 64 * 16, 64 * 16, LO_B, id, 1u);
+        umma_kstep(d, aT + CH_VOX * kChunkBytes, LBO_A, LO_A, wB + UW_CS + 5 * 2 * 64 * 16, 64 * 16, LO_B, id, 1u);
+        umma_kstep(d, aT + (CH_F + 2 * v) * kChunkBytes, LBO_A, LO_A, wB + UW_CV, 64 * 16, LO_B, id, 1u);
+        umma_commit(mbar0 + 8 * (1 + v));
+      }
     });
+    if (VEC && has_next) view_issue(p, cams[2], s_view[2], ns, wt, f[2]);
     // ------------------------------------------------------------ phase E: color.2, view soft-max, rgb
     {
-      float cl[V] = {0.f, 0.f, 0.f};
+      float cl[V];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float sh[16];
-        tmem_ld16(trow + 16 * c, sh);
+      for (int v = 0; v < V; ++v) {
+        tile_wait(mbar0 + 8 * (1 + v), parE);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sh[j] += sV[UV_BC + 16 * c + j];
+        for (int h = 0; h < 2; ++h) {
+          float c[32];
+          tmem_ld32(trow + 64 * v + 32 * h, c);
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          float pv[16];
-          tmem_ld16(trow + 64 + 64 * v + 16 * c, pv);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) cl[v] = fmaf(sV[UV_W2 + 16 * c + j], fmaxf(pv[j] + sh[j], 0.f), cl[v]);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 w = lds4f(sV + UV_W2 + 32 * h + j);
+            a0 = fmaf(w.x, fmaxf(c[j], 0.f), a0); a1 = fmaf(w.y, fmaxf(c[j + 1], 0.f), a1);
+            a2 = fmaf(w.z, fmaxf(c[j + 2], 0.f), a2); a3 = fmaf(w.w, fmaxf(c[j + 3], 0.f), a3);
+          }
         }
+        cl[v] = fmaxf((a0 + a1) + (a2 + a3) + b2, 0.f);
       }
-#pragma unroll
-      for (int v = 0; v < V; ++v) cl[v] = fmaxf(cl[v] + b2, 0.f);
+      parE ^= 1u;
       const float mx = fmaxf(cl[0], fmaxf(cl[1], cl[2]));
       const float e0 = expf(cl[0] - mx), e1 = expf(cl[1] - mx), e2 = expf(cl[2] - mx);
       const float inv = 1.f / (e0 + e1 + e2);
@@ -388,7 +553,29 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
       o.y = (e0 * rgbv[0][1] + e1 * rgbv[1][1] + e2 * rgbv[2][1]) * inv;
       o.z = (e0 * rgbv[0][2] + e1 * rgbv[1][2] + e2 * rgbv[2][2]) * inv;
       o.w = sig;
-      if (live) reinterpret_cast<float4*>(rp.raw)[si] = o;
+      if (live_out) reinterpret_cast<float4*>(rp.raw)[si_out] = o;
+    }
+    if (has_next) {
+      if (VEC) {
+        view_consume(p, wt, f[2]);
+        if (nlive) {
+          if (p.vis_mask) p.vis_mask[nsi] = div_rn((float)ns.cnt, (float)V);
+          if (p.vis_count) p.vis_count[nsi] = ns.cnt;
+        }
+      } else {                                              // general strides: plain (unpipelined) gather
+        const int64_t li = nsi / S;
+        const int s = (int)(nsi % S);
+        const RaySetup r = ray_setup(p, li);
+        const float un = div_rn(r.fx, (float)(p.W - 1)), vn = div_rn(r.fy, (float)(p.H - 1));
+        const float gxv = sub_rn(mul_rn(un, 2.f), 1.f), gyv = sub_rn(mul_rn(vn, 2.f), 1.f);
+        const SamplePoint q = sample_point(p, r, s);
+        const int cnt = gather_sample_regs<CF, V, false>(p, cams, s_view, s_tar_c, q.x, q.y, q.zz, gxv, gyv, q.dn, vox, f);
+        if (nlive) {
+          if (p.z_vals) p.z_vals[nsi] = q.z;
+          if (p.vis_mask) p.vis_mask[nsi] = div_rn((float)cnt, (float)V);
+          if (p.vis_count) p.vis_count[nsi] = cnt;
+        }
+      }
     }
   }
   tc_fence_before();

@@ -162,6 +162,9 @@ def pack_nerf_weights_mma(nerf):
     return packed.to(next(nerf.parameters()).device)
 
 
+UMMA_PACK_TAG = 0x414D4D55      # "UMMA"
+
+
 def umma_operand(w_pad):
     """(N, K) fp32 -> (hi, lo) fp16 tensors of shape (K/8, N, 8): the SWIZZLE_NONE K-major shared-memory layout a
     tcgen05.mma descriptor with SBO = 128 B, LBO = N*16 B addresses (K-chunk c is a slab of N rows x 16 bytes)."""
@@ -183,11 +186,17 @@ def pack_nerf_weights_umma(nerf):
     """Weights of the level-1 NeRF MLP for the tcgen05 kernel (csrc/render_umma.cu): [hi block][lo block] with the
     six matrices in kernel order (UW_GS .. UW_CV), each in the layout of umma_operand, then the fp32 vectors.
     Returns an int32 tensor (UMMA_PACK_WORDS,) on the module's device."""
-    mats, vec = _tensor_core_matrices(nerf)
-    ops = [umma_operand(m) for m in mats]
+    (gs, gv, wfc, l0, cs, cv), vec = _tensor_core_matrices(nerf)
+    # biases ride in the MMAs: the kernel puts a 1 in a padding column of the A operand (K index 15 of
+    # [var | mean], K index 24 of [pooled | vox | 1 0..], i.e. 88 of [hid | pooled | vox | 1 0..])
+    gs[:, 15] = vec[0:32]            # global_fc.bias
+    l0[:, 24] = vec[80:144]          # lr0.bias
+    cs[:, 88] = vec[208:272]         # color.0.bias
+    ops = [umma_operand(m) for m in (gs, gv, wfc, l0, cs, cv)]
     hi = torch.cat([h.reshape(-1) for h, _ in ops])
     lo = torch.cat([l.reshape(-1) for _, l in ops])
-    packed = torch.cat([hi.view(torch.int32), lo.view(torch.int32), vec.view(torch.int32)])
+    tag = torch.tensor([UMMA_PACK_TAG, 0, 0, 0], dtype=torch.int32)    # tells this packing from the mma.sync one (same length otherwise)
+    packed = torch.cat([hi.view(torch.int32), lo.view(torch.int32), vec.view(torch.int32), tag])
     return packed.to(next(nerf.parameters()).device)
 
 

@@ -11,7 +11,7 @@ from boostmvsnerfs_b200.modules import NeRF
 # kernel constants (csrc/render_umma.cu)
 MATS = [("GS", 32, 32), ("GV", 32, 16), ("FC", 16, 32), ("L0", 64, 32), ("CS", 64, 96), ("CV", 64, 16)]
 UW_BLOCK = sum(n * k * 2 for _, n, k in MATS)
-UV = dict(BG=0, WA=32, BFC=64, BL=80, WS=144, BC=208, W2=272, WV=336, BV=384, SC=396, COUNT=400)
+UV = dict(BG=0, WA=32, BFC=64, BL=80, WS=144, BC=208, W2=272, WV=336, BV=384, SC=396, TAG=400, COUNT=404)
 
 
 def _net(seed=0):
@@ -48,7 +48,7 @@ def _unpack(packed):
 
 def test_umma_block_size_matches_kernel_constants():
     assert UW_BLOCK == 22528
-    assert mlp_pack.pack_nerf_weights_umma(_net()).numel() * 4 == 2 * UW_BLOCK + 1600
+    assert mlp_pack.pack_nerf_weights_umma(_net()).numel() * 4 == 2 * UW_BLOCK + 1616
 
 
 def test_umma_operand_round_trip():
@@ -80,21 +80,23 @@ def test_umma_dataflow_reproduces_the_module():
     mean = x.mean(1)
     var = ((x - mean[:, None]) ** 2).sum(1) / 2
     pad = lambda a, n: np.concatenate([a, np.zeros(a.shape[:-1] + (n - a.shape[-1],))], -1)
-    a_gs = np.concatenate([pad(var, 16), pad(mean, 16)], -1)     # K = 32
+    var16 = pad(var, 16); var16[:, 15] = 1.0                     # bias column of global_fc
+    a_gs = np.concatenate([var16, pad(mean, 16)], -1)            # K = 32
     S = a_gs @ M["GS"].T
-    G = relu(S[:, None] + pad(x, 16) @ M["GV"].T + v("BG", 32))  # (P,3,32)
+    G = relu(S[:, None] + pad(x, 16) @ M["GV"].T)                # (P,3,32)
     # phase B
     lg = relu(G @ v("WA", 32) + vec[UV["SC"]])
     wts = np.exp(lg - lg.max(1, keepdims=True)); wts /= wts.sum(1, keepdims=True)
     im = (G * wts[..., None]).sum(1)
     pooled = relu(im @ M["FC"].T + v("BFC", 16))
     # phase C/D
-    a_pv = np.concatenate([pooled, vx, np.zeros((P, 8))], -1)    # K = 32
-    hid = relu(a_pv @ M["L0"].T + v("BL", 64))
+    one = np.zeros((P, 8)); one[:, 0] = 1.0                      # bias column of lr0 / color.0
+    a_pv = np.concatenate([pooled, vx, one], -1)                 # K = 32
+    hid = relu(a_pv @ M["L0"].T)
     sig = hid @ v("WS", 64) + vec[UV["SC"] + 1]
     sig = np.where(sig > 20, sig, np.log1p(np.exp(sig)))
     # phase E
-    Sc = np.concatenate([hid, a_pv], -1) @ M["CS"].T + v("BC", 64)
+    Sc = np.concatenate([hid, a_pv], -1) @ M["CS"].T
     Pc = pad(f, 16) @ M["CV"].T                                  # (P,3,64)
     cl = relu(relu(Sc[:, None] + Pc) @ v("W2", 64) + vec[UV["SC"] + 2])
     beta = np.exp(cl - cl.max(1, keepdims=True)); beta /= beta.sum(1, keepdims=True)
