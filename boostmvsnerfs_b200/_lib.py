@@ -171,6 +171,7 @@ ENTRY_POINTS = {
     "bmv_mvs_march_fetch": MvsMarchParams,
     "bmv_fpn_topdown": FpnTopdownParams,
     "bmv_conv3d_k3": Conv3dParams,
+    "bmv_conv3d_k3_umma": Conv3dParams,
     "bmv_convT3d_k3s2": ConvT3dParams,
     "bmv_fpn_topdown_smooth": FpnFusedParams,
     "bmv_fpn_stem": FpnStemParams,
@@ -178,7 +179,7 @@ ENTRY_POINTS = {
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",
                  "bmv_render_rays_umma_weight_words", "bmv_umma_selftest",
-                 "bmv_conv3d_k3_weight_words", "bmv_conv3d_k3_last_used_tma", "bmv_convT3d_k3s2_weight_words",
+                 "bmv_conv3d_k3_weight_words", "bmv_conv3d_k3_umma_weight_words", "bmv_conv3d_k3_last_used_tma", "bmv_convT3d_k3s2_weight_words",
                  "bmv_fpn_topdown_smooth_weight_words")
 
 _lib = None
@@ -211,6 +212,8 @@ def load():
     lib.bmv_conv3d_k3_weight_words.restype = C.c_int
     lib.bmv_conv3d_k3_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_conv3d_k3_last_used_tma.restype = C.c_int
+    lib.bmv_conv3d_k3_umma_weight_words.restype = C.c_int
+    lib.bmv_conv3d_k3_umma_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_convT3d_k3s2_weight_words.restype = C.c_int
     lib.bmv_convT3d_k3s2_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_fpn_topdown_smooth_weight_words.restype = C.c_int

@@ -39,6 +39,7 @@ extern "C" BMV_API int bmv_sizeof_params(const char* entry) {
   if (!strcmp(entry, "bmv_mvs_march_fetch")) return (int)sizeof(bmv_mvs_march_params);
   if (!strcmp(entry, "bmv_fpn_topdown")) return (int)sizeof(bmv_fpn_topdown_params);
   if (!strcmp(entry, "bmv_conv3d_k3")) return (int)sizeof(bmv_conv3d_params);
+  if (!strcmp(entry, "bmv_conv3d_k3_umma")) return (int)sizeof(bmv_conv3d_params);
   if (!strcmp(entry, "bmv_convT3d_k3s2")) return (int)sizeof(bmv_convT3d_params);
   if (!strcmp(entry, "bmv_fpn_topdown_smooth")) return (int)sizeof(bmv_fpn_fused_params);
   if (!strcmp(entry, "bmv_fpn_stem")) return (int)sizeof(bmv_fpn_stem_params);

@@ -1,0 +1,272 @@
+// 3x3x3 / stride-1 / pad-1 convolution (+bias, ReLU, split outputs) on the 5th-generation tensor cores:
+// TMA -> shared memory -> tcgen05.mma -> tensor memory -> registers -> HBM.  Same contract and the same
+// fp16-operand / fp32-accumulate arithmetic as conv3d_mma.cu (TF32-class, gated by the host the same way).
+//
+// Why: ncu on the TMA-staged mma.sync kernels (profiles/round1j) shows them bound by the legacy HMMA path
+// (pipe 52-59 % busy, math-pipe-throttle stalls) at 0.25-0.4 of the HBM roofline.  With tcgen05 the implicit
+// GEMM needs no fragments in registers at all: M = 128 consecutive x voxels of one output row, N = 16 output
+// channels (Cout padded), K = 16 input values per instruction, and the A operand of tap (dz,dy,dx) is the
+// staged halo tile itself, addressed by a shared-memory descriptor whose start is shifted by the tap:
+//     Cin  8: voxels are 16 bytes = one K-chunk; rows (voxels) 16 B apart = the SWIZZLE_NONE core-matrix pitch,
+//             the second K-chunk is the NEXT voxel (LBO = 16): taps dx, dx+1 in one MMA, 2 MMAs per (dz,dy)
+//             (the partner of dx = 2 has zero weights), 18 MMAs per output row;
+//     Cin 16: voxels are 32 bytes = the SWIZZLE_32B row the TMA unit writes (absolute-address XOR, the same on
+//             the tensor-core side), one MMA per tap, 27 per output row.
+// An output row's accumulator is 16 TMEM columns (lane = voxel); the epilogue thread of voxel x reads them
+// with one tcgen05.ld, adds the bias, applies ReLU and writes its voxel's channels as 16/32-byte stores.
+// One thread issues everything; a commit per output plane lets the epilogue of plane z run under the MMAs of
+// plane z+1, and two CTAs per SM overlap one tile's TMA load with the other's MMAs.
+#include <cuda.h>
+
+#include <cstring>
+#include <cuda_fp16.h>
+
+#include "bmv_internal.cuh"
+#include "umma.cuh"
+
+namespace bmv {
+
+template <int CIN> struct UConv;
+template <> struct UConv<8> {
+  static constexpr int VS = 16, KS = 2, TH = 4, TD = 4, EXTRA = 1;
+  static constexpr uint32_t LAYOUT = 0, A_LBO = 16, A_SBO = 128;
+  __device__ static __forceinline__ uint32_t step_off(int j) { return (uint32_t)j * 32u; }      // voxels 2j, 2j+1
+};
+template <> struct UConv<16> {
+  static constexpr int VS = 32, KS = 3, TH = 3, TD = 2, EXTRA = 0;
+  static constexpr uint32_t LAYOUT = 6, A_LBO = 16, A_SBO = 256;                                 // SWIZZLE_32B: 8 rows x 32 B
+  __device__ static __forceinline__ uint32_t step_off(int j) { return (uint32_t)j * 32u; }      // voxel j
+};
+template <int CIN> struct UTile {
+  using C = UConv<CIN>;
+  static constexpr int TW = 128, TH = C::TH, TD = C::TD, HH = TH + 2, HD = TD + 2;
+  static constexpr int ROWV = TW + 2 + C::EXTRA, ROWB = ROWV * C::VS;
+  static constexpr int TILE_BYTES = HD * HH * ROWB;
+  static constexpr int N_MMA = 9 * C::KS;                   // MMAs per output row
+  static constexpr int W_BYTES = N_MMA * 512;               // one (N=16, K=16) fp16 operand per MMA
+  static constexpr int ROWS = TD * TH;
+  static constexpr uint32_t TMEM_COLS = ROWS * 16 <= 32 ? 32 : (ROWS * 16 <= 64 ? 64 : (ROWS * 16 <= 128 ? 128 : 256));
+  static constexpr size_t SMEM = (size_t)TILE_BYTES + W_BYTES + 1024;
+};
+
+__device__ __forceinline__ void umma_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t mbar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(128, 2) conv3d_k3_umma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tmap) {
+  using T = UTile<CIN>;
+  using C = UConv<CIN>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // swizzled TMA boxes and the tensor core XOR absolute address bits: keep the tile 1024-byte aligned
+  unsigned char* tile = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+  unsigned char* wsm = tile + T::TILE_BYTES;
+  __shared__ __align__(8) uint64_t s_mbar_tma;
+  __shared__ __align__(8) uint64_t s_mbar_mma[T::TD];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tiles_w = (p.W + T::TW - 1) / T::TW, tiles_h = (p.H + T::TH - 1) / T::TH, tiles_d = (p.D + T::TD - 1) / T::TD;
+  int b = blockIdx.x;
+  const int tw = b % tiles_w; b /= tiles_w;
+  const int th = b % tiles_h; b /= tiles_h;
+  const int td = b % tiles_d; b /= tiles_d;
+  const int n = b;
+  const int x0 = tw * T::TW, y0 = th * T::TH, d0 = td * T::TD;
+  const uint32_t mbar_tma = smem_u32(&s_mbar_tma);
+  if (tid == 0) {
+    mbar_init(mbar_tma, 1);
+    for (int i = 0; i < T::TD; ++i) mbar_init(smem_u32(&s_mbar_mma[i]), 1);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), T::TMEM_COLS);
+  __syncthreads();
+  if (tid == 0) {
+    umma_mbar_expect_tx(mbar_tma, (uint32_t)T::TILE_BYTES);
+    umma_tma_load_5d(smem_u32(tile), &tmap, mbar_tma, 0, x0 - 1, y0 - 1, d0 - 1, n);
+  }
+  {                                                         // weights (already in operand order) under the bulk copy
+    const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
+    uint4* dst = reinterpret_cast<uint4*>(wsm);
+    for (int i = tid; i < T::W_BYTES / 16; i += 128) dst[i] = __ldg(src + i);
+  }
+  proxy_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  if (tid == 0) {
+    mbar_wait(mbar_tma, 0);
+    tc_fence_after();
+    const uint32_t id = umma_idesc(16);
+    const uint32_t a0 = smem_u32(tile), w0 = smem_u32(wsm);
+    for (int od = 0; od < T::TD; ++od) {
+      if (d0 + od < p.D) {
+        for (int oy = 0; oy < T::TH; ++oy) {
+          if (y0 + oy >= p.H) break;
+          const uint32_t dcol = tmem_base + (uint32_t)((od * T::TH + oy) * 16);
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t arow = a0 + (uint32_t)(((od + dz) * T::HH + (oy + dy)) * T::ROWB);
+#pragma unroll
+              for (int j = 0; j < C::KS; ++j) {
+                const uint64_t ad = umma_desc(arow + C::step_off(j), C::A_LBO, C::A_SBO, C::LAYOUT);
+                const uint64_t bd = umma_desc(w0 + (uint32_t)(((dz * 3 + dy) * C::KS + j) * 512), 256, 128, 0);
+                umma_f16(dcol, ad, bd, id, (dz | dy | j) ? 1u : 0u);
+              }
+            }
+        }
+      }
+      umma_commit(smem_u32(&s_mbar_mma[od]));
+    }
+  }
+  // ---- epilogue: thread = voxel x0 + tid, one output row at a time
+  const int gx = x0 + tid;
+  const int split = p.out2 ? p.split : p.Cout;
+  float bias[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) bias[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int od = 0; od < T::TD; ++od) {
+    mbar_wait(smem_u32(&s_mbar_mma[od]), 0);
+    __syncwarp();
+    tc_fence_after();
+    if (d0 + od >= p.D) continue;                           // uniform
+    for (int oy = 0; oy < T::TH; ++oy) {
+      if (y0 + oy >= p.H) break;                            // uniform
+      float v[16];
+      tmem_ld16(trow + (uint32_t)((od * T::TH + oy) * 16), v);
+      if (gx >= p.W) continue;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        v[c] += bias[c];
+        if (p.relu) v[c] = fmaxf(v[c], 0.f);
+      }
+      const int64_t vo = (int64_t)(d0 + od) * p.o_d_stride + (int64_t)(y0 + oy) * p.o_y_stride + (int64_t)gx * p.o_x_stride;
+      if (p.out_half) {
+        __half* o = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + vo;
+        uint32_t h[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          __half2 t2 = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+          h[c] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        if (p.Cout == 8 && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+        else if (p.Cout == 16 && (((uintptr_t)o) & 15) == 0) {
+          *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (2 * c < p.Cout) *reinterpret_cast<uint32_t*>(o + 2 * c) = h[c];
+        }
+      } else {
+        float* o = p.out + (int64_t)n * p.o_n_stride + vo;
+        if ((split == 8 || split == 16) && (((uintptr_t)o) & 15) == 0) {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          if (split == 16) {
+            *reinterpret_cast<float4*>(o + 8) = make_float4(v[8], v[9], v[10], v[11]);
+            *reinterpret_cast<float4*>(o + 12) = make_float4(v[12], v[13], v[14], v[15]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < split) o[c] = v[c];
+        }
+        if (p.out2) {
+          float* o2 = p.out2 + (int64_t)n * p.o2_n_stride + (int64_t)(d0 + od) * p.o2_d_stride + (int64_t)(y0 + oy) * p.o2_y_stride +
+                      (int64_t)gx * p.o2_x_stride;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c >= split && c < p.Cout) o2[c - split] = v[c];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, T::TMEM_COLS);
+}
+
+typedef CUresult (*UEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static UEncodeTiledFn u_encode_tiled_fn() {
+  static UEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<UEncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+template <int CIN>
+static int launch_uconv(const bmv_conv3d_params& p, cudaStream_t st) {
+  using T = UTile<CIN>;
+  UEncodeTiledFn enc = u_encode_tiled_fn();
+  BMV_REQUIRE(enc != nullptr, BMV_ERR_CUDA_LAUNCH, "bmv_conv3d_k3_umma: cuTensorMapEncodeTiled is not available");
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+  const cuuint64_t strides[4] = {(cuuint64_t)p.x_x_stride * 2, (cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2,
+                                 (cuuint64_t)p.x_n_stride * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)T::ROWV, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(p.x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BMV_REQUIRE(r == CUDA_SUCCESS, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_k3_umma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3d_k3_umma_kernel<CIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) {
+      set_error("bmv_conv3d_k3_umma: cannot reserve %zu B shared memory: %s", (size_t)T::SMEM, cudaGetErrorString(e));
+      return BMV_ERR_CUDA_LAUNCH;
+    }
+    configured = true;
+  }
+  const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
+  conv3d_k3_umma_kernel<CIN><<<(unsigned)blocks, 128, T::SMEM, st>>>(p, map);
+  return check_launch("bmv_conv3d_k3_umma");
+}
+
+}  // namespace bmv
+
+extern "C" BMV_API int bmv_conv3d_k3_umma(const bmv_conv3d_params* p, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: null pointer");
+  BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: bad size");
+  BMV_REQUIRE(p->in_half && (p->stride == 0 || p->stride == 1) && p->x_x_stride == p->Cin, BMV_ERR_UNSUPPORTED_SHAPE,
+              "bmv_conv3d_k3_umma: needs an fp16 channels-last input with contiguous voxels along x and stride 1");
+  BMV_REQUIRE(p->x_y_stride % 8 == 0 && p->x_d_stride % 8 == 0 && p->x_n_stride % 8 == 0 && ((uintptr_t)p->x & 15) == 0 &&
+                  ((uintptr_t)p->wfrag & 15) == 0,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: input rows / weights must be 16-byte aligned");
+  BMV_REQUIRE(p->Cout >= 1 && p->Cout <= 16, BMV_ERR_UNSUPPORTED_SHAPE, "bmv_conv3d_k3_umma: Cout must be <= 16 (got %d)", p->Cout);
+  BMV_REQUIRE(!p->out_half || (!p->out2 && p->Cout % 2 == 0 && p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 &&
+                               p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 && ((uintptr_t)p->out & 3) == 0),
+              BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: fp16 output needs even Cout, a single output tensor and 4-byte aligned voxels");
+  BMV_REQUIRE(!p->out2 || (p->split >= 1 && p->split < p->Cout), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: bad split");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->Cin == 8) return launch_uconv<8>(*p, st);
+  if (p->Cin == 16) return launch_uconv<16>(*p, st);
+  set_error("bmv_conv3d_k3_umma: Cin=%d not instantiated (8, 16)", p->Cin);
+  return BMV_ERR_UNSUPPORTED_SHAPE;
+}
+
+// bytes/4 of the operand-ordered weight buffer (mlp_pack.pack_conv3d_k3_umma), -1 if not instantiated
+extern "C" BMV_API int bmv_conv3d_k3_umma_weight_words(int Cin, int Cout) {
+  if (Cout < 1 || Cout > 16) return -1;
+  if (Cin == 8) return bmv::UTile<8>::W_BYTES / 4;
+  if (Cin == 16) return bmv::UTile<16>::W_BYTES / 4;
+  return -1;
+}

@@ -666,13 +666,20 @@ def fpn_topdown(prev, lateral_in, weight, bias):
 
 
 # ------------------------------------------------------------------------------------------ tensor-core 3-D convolution
-def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1, no_tma=False, out_dtype=torch.float32):
+def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1, no_tma=False, out_dtype=torch.float32,
+              engine="mma"):
     """3x3x3 / stride 1 / pad 1 convolution (+bias, optional ReLU) of a channels_last_3d fp32 volume
     on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
     lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
     returns (N,cout,D,H,W) channels_last_3d (or writes `out`, any voxel-major strides).  With `out2`
     (N,cout-split,D,H,W) channels >= split go there instead (`out` then holds `split` channels).
-    x may also be float16 (the operands are rounded to fp16 anyway: same result, half the read traffic)."""
+    x may also be float16 (the operands are rounded to fp16 anyway: same result, half the read traffic).
+    engine='umma': bmv_conv3d_k3_umma (TMA + tcgen05 + tensor memory; fp16 x, stride 1, Cin 8/16, wfrag from
+    mlp_pack.pack_conv3d_k3_umma)."""
+    if engine not in ("mma", "umma"):
+        raise BmvError(f"conv3d_k3: unknown engine {engine!r}")
+    if engine == "umma" and (x.dtype != torch.float16 or stride != 1):
+        raise BmvError("conv3d_k3(engine='umma'): needs a float16 input and stride 1")
     if not (x.is_cuda and x.dtype in (torch.float32, torch.float16)):
         raise BmvError(f"conv3d_k3: x must be a CUDA float32/float16 tensor, got {x.dtype} on {x.device}")
     N, Cin, D, H, W = x.shape
@@ -684,9 +691,9 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
                           memory_format=torch.channels_last_3d)
     if out.stride(1) != 1 or (out2 is not None and out2.shape[1] > 1 and out2.stride(1) != 1):
         raise BmvError("conv3d_k3: out must be channels_last_3d")
-    need = _lib.load().bmv_conv3d_k3_weight_words(Cin, cout)
+    need = (_lib.load().bmv_conv3d_k3_umma_weight_words if engine == "umma" else _lib.load().bmv_conv3d_k3_weight_words)(Cin, cout)
     if need < 0 or wfrag.numel() != need or wfrag.dtype != torch.int32:
-        raise BmvError(f"conv3d_k3: weight buffer does not match (Cin={Cin}, Cout={cout}): {wfrag.numel()} vs {need}")
+        raise BmvError(f"conv3d_k3: weight buffer does not match (Cin={Cin}, Cout={cout}, engine={engine}): {wfrag.numel()} vs {need}")
     p = _lib.Conv3dParams()
     p.x = x.data_ptr()
     p.x_n_stride, p.x_d_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3), x.stride(4)
@@ -704,7 +711,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
         p.out2, p.split = out2.data_ptr(), split
         p.o2_n_stride, p.o2_d_stride, p.o2_y_stride, p.o2_x_stride = (out2.stride(0), out2.stride(2), out2.stride(3),
                                                                       out2.stride(4))
-    _lib.call("bmv_conv3d_k3", p, _stream())
+    _lib.call("bmv_conv3d_k3_umma" if engine == "umma" else "bmv_conv3d_k3", p, _stream())
     return out
 
 

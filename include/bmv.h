@@ -371,6 +371,13 @@ typedef struct bmv_conv3d_params {
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);
 BMV_API int bmv_conv3d_k3_last_used_tma(void);   /* 1 if this thread's last stride-1 launch staged its tile with TMA */
+/* The same convolution on the 5th-generation tensor cores (csrc/conv3d_umma.cu): the halo tile is staged by one
+ * 5-D TMA copy, every tap is a tcgen05.mma whose A operand is that tile addressed through a shifted shared-memory
+ * descriptor (M = 128 x voxels, N = 16, K = 16), accumulators live in tensor memory.  Same params struct and
+ * arithmetic class; requires in_half = 1, stride 1, x_x_stride == Cin, Cin in {8, 16}, Cout <= 16.
+ * wfrag: bmv_conv3d_k3_umma_weight_words(Cin,Cout) words in operand order (mlp_pack.pack_conv3d_k3_umma). */
+BMV_API int bmv_conv3d_k3_umma(const bmv_conv3d_params* p, bmv_stream_t stream);
+BMV_API int bmv_conv3d_k3_umma_weight_words(int Cin, int Cout);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) + bias + skip add:

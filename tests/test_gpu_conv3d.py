@@ -261,3 +261,51 @@ def test_fpn_stem_vs_torch(hw, layout):
         out3, _, z = ops.fpn_stem(x, c0.weight, c0.bias, pack_conv2d_k3_c8(c1.weight), c1.bias, want_rgb4=True, want_s2d=True)
         zr = out.permute(0, 2, 3, 1).reshape(2, H // 2, 2, W // 2, 2, 8).permute(0, 1, 3, 2, 4, 5).reshape(2, H // 2, W // 2, 32)
         assert torch.equal(out3, out) and torch.equal(z.permute(0, 2, 3, 1), zr)
+
+
+UMMA_SHAPES = [  # (N, Cin, Cout, D, H, W, bias, relu, out_half, split)
+    (2, 8, 9, 8, 8, 64, False, False, False, 8),        # merged output heads: features + logits
+    (1, 8, 9, 3, 9, 17, True, True, False, 8),          # ragged in every dimension
+    (1, 8, 9, 5, 6, 300, True, False, False, 8),        # three x tiles
+    (1, 8, 16, 8, 4, 140, True, False, True, 0),
+    (2, 16, 8, 8, 12, 64, True, True, True, 0),         # conv0 of the level-1 U-Net
+    (1, 16, 8, 5, 7, 45, True, True, False, 0),
+    (2, 16, 16, 4, 8, 240, True, True, False, 0),       # conv2
+    (1, 16, 12, 3, 5, 19, False, False, False, 0),
+]
+
+
+@pytest.mark.parametrize("shape", UMMA_SHAPES)
+@pytest.mark.parametrize("exact_operands", [True, False])
+def test_conv3d_k3_umma_matches_cudnn(shape, exact_operands):
+    """bmv_conv3d_k3_umma (TMA + tcgen05 + TMEM) against cuDNN fp32 and against the mma.sync kernel."""
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3, pack_conv3d_k3_umma
+    N, Cin, Cout, D, H, W, bias, relu, out_half, split = shape
+    g = torch.Generator().manual_seed(Cin * 100 + W + Cout)
+    x = torch.randn((N, Cin, D, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3, 3), generator=g) * 0.1
+    b = torch.randn(Cout, generator=g) if bias else None
+    if exact_operands:
+        x, w = x.half().float(), w.half().float()
+    x = x.cuda().contiguous(memory_format=torch.channels_last_3d)
+    w = w.cuda()
+    b = b.cuda() if bias else None
+    xh = x.half()
+    ref = _reference(xh.float(), w, b, relu)
+    scale = ref.abs().max().item()
+    tol = (1e-5 if exact_operands else 2e-3) * scale
+    kw = dict(out_dtype=torch.float16) if out_half else {}
+    if split:
+        out2 = torch.empty((N, Cout - split, D, H, W), device="cuda")
+        y = ops.conv3d_k3(xh, pack_conv3d_k3_umma(w), b, Cout, relu, out2=out2, split=split, engine="umma")
+        got = torch.cat([y, out2], dim=1)
+    else:
+        got = ops.conv3d_k3(xh, pack_conv3d_k3_umma(w), b, Cout, relu, engine="umma", **kw)
+        assert got.stride(1) == 1
+    if out_half:
+        tol = max(tol, 1e-3 * scale)                            # fp16 storage of the result
+    assert got.shape == ref.shape
+    assert (got.float() - ref).abs().max().item() <= tol, ((got.float() - ref).abs().max().item(), scale)
+    old = ops.conv3d_k3(xh, pack_conv3d_k3(w), b, Cout, relu)
+    assert (got.float() - old).abs().max().item() <= max(tol, 2e-5 * scale)
