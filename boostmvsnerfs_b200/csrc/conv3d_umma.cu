@@ -12,10 +12,16 @@
 //             (the partner of dx = 2 has zero weights), 18 MMAs per output row;
 //     Cin 16: voxels are 32 bytes = the SWIZZLE_32B row the TMA unit writes (absolute-address XOR, the same on
 //             the tensor-core side), one MMA per tap, 27 per output row.
-// An output row's accumulator is 16 TMEM columns (lane = voxel); the epilogue thread of voxel x reads them
-// with one tcgen05.ld, adds the bias, applies ReLU and writes its voxel's channels as 16/32-byte stores.
-// One thread issues everything; a commit per output plane lets the epilogue of plane z run under the MMAs of
-// plane z+1, and two CTAs per SM overlap one tile's TMA load with the other's MMAs.
+// An output row's accumulator is 16 TMEM columns (lane = voxel), the rows of an output plane are adjacent column
+// groups.  With N = 16 an MMA is bound by reading its 4 KB A operand from shared memory (128 B/clk: 32 clk against
+// 8 clk of math), so ONE MMA serves every output row an input row contributes to: input row hy of plane z' feeds
+// output rows oy = hy-2 .. hy (dy = hy - oy) of plane z'-dz, whose accumulators are adjacent -> N = 16..48 with
+// B = a row range of the stacked weights [W(dz,2); W(dz,1); W(dz,0)].  That is 3 (TH+2) KS / TH MMAs per output
+// row instead of 9 KS.  Accumulators are zeroed by one MMA against a zero B operand (an MMA spans rows that were
+// and were not written before, so the accumulate flag cannot do it).  The epilogue thread of voxel x reads its
+// 16 columns with one tcgen05.ld, adds the bias, applies ReLU and writes the voxel's channels as 16/32-byte stores.
+// Two threads (different warps) issue half of the output planes each; a commit per plane lets the epilogue of
+// plane z run under the MMAs of plane z+1, and two CTAs per SM overlap one tile's TMA load with the other's MMAs.
 #include <cuda.h>
 
 #include <cstring>
@@ -42,11 +48,12 @@ template <int CIN> struct UTile {
   static constexpr int TW = 128, TH = C::TH, TD = C::TD, HH = TH + 2, HD = TD + 2;
   static constexpr int ROWV = TW + 2 + C::EXTRA, ROWB = ROWV * C::VS;
   static constexpr int TILE_BYTES = HD * HH * ROWB;
-  static constexpr int N_MMA = 9 * C::KS;                   // MMAs per output row
-  static constexpr int W_BYTES = N_MMA * 512;               // one (N=16, K=16) fp16 operand per MMA
+  static constexpr int WS_BYTES = 2 * 48 * 16;               // stacked [W(dz,2); W(dz,1); W(dz,0)] of one (dz, k-step): (K/8, 48, 8) fp16
+  static constexpr int W_BYTES = 3 * C::KS * WS_BYTES;
+  static constexpr int Z_BYTES = 2 * 16 * TH * 16;           // zero B operand (N = 16 TH) that clears a plane's accumulators
   static constexpr int ROWS = TD * TH;
   static constexpr uint32_t TMEM_COLS = ROWS * 16 <= 32 ? 32 : (ROWS * 16 <= 64 ? 64 : (ROWS * 16 <= 128 ? 128 : 256));
-  static constexpr size_t SMEM = (size_t)TILE_BYTES + W_BYTES + 1024;
+  static constexpr size_t SMEM = (size_t)TILE_BYTES + W_BYTES + Z_BYTES + 1024;
 };
 
 __device__ __forceinline__ void umma_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
@@ -92,37 +99,45 @@ __global__ void __launch_bounds__(128, 2) conv3d_k3_umma_kernel(bmv_conv3d_param
     const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
     uint4* dst = reinterpret_cast<uint4*>(wsm);
     for (int i = tid; i < T::W_BYTES / 16; i += 128) dst[i] = __ldg(src + i);
+    for (int i = tid; i < T::Z_BYTES / 16; i += 128) dst[T::W_BYTES / 16 + i] = make_uint4(0u, 0u, 0u, 0u);
   }
   proxy_fence_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-  if (tid == 0) {
+  // ---- issue: lane 0 of warps 0 and 1, half of the output planes each (their accumulators are disjoint)
+  if ((tid & 31) == 0 && warp < 2) {
     mbar_wait(mbar_tma, 0);
     tc_fence_after();
-    const uint32_t id = umma_idesc(16);
-    const uint32_t a0 = smem_u32(tile), w0 = smem_u32(wsm);
-    for (int od = 0; od < T::TD; ++od) {
-      if (d0 + od < p.D) {
-        for (int oy = 0; oy < T::TH; ++oy) {
-          if (y0 + oy >= p.H) break;
-          const uint32_t dcol = tmem_base + (uint32_t)((od * T::TH + oy) * 16);
+    // descriptors: high word constant, low word = (address >> 4) | (LBO >> 4) << 16 advanced by compile-time offsets
+    constexpr uint32_t A_HI = (C::A_SBO >> 4) | (1u << 14) | (C::LAYOUT << 29);
+    constexpr uint32_t B_HI = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo = ((smem_u32(tile) & 0x3FFFFu) >> 4) | ((C::A_LBO >> 4) << 16);
+    const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | ((768u >> 4) << 16);                  // stacked weights: LBO = 48 rows x 16 B
+    const uint32_t z_lo = (((smem_u32(wsm) + T::W_BYTES) & 0x3FFFFu) >> 4) | (((16u * T::TH * 16u) >> 4) << 16);
 #pragma unroll
-          for (int dz = 0; dz < 3; ++dz)
+    for (int oi = 0; oi < (T::TD + 1) / 2; ++oi) {
+      const int od = warp * ((T::TD + 1) / 2) + oi;
+      if (od < T::TD) {
+        const uint32_t dplane = tmem_base + (uint32_t)(od * T::TH * 16);
+        umma_f16_lohi<false>(dplane, a_lo + (uint32_t)((((od + 1) * T::HH + 1) * T::ROWB) >> 4), A_HI, z_lo, B_HI, umma_idesc(16 * T::TH));
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const uint32_t arow = a0 + (uint32_t)(((od + dz) * T::HH + (oy + dy)) * T::ROWB);
+        for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
-              for (int j = 0; j < C::KS; ++j) {
-                const uint64_t ad = umma_desc(arow + C::step_off(j), C::A_LBO, C::A_SBO, C::LAYOUT);
-                const uint64_t bd = umma_desc(w0 + (uint32_t)(((dz * 3 + dy) * C::KS + j) * 512), 256, 128, 0);
-                umma_f16(dcol, ad, bd, id, (dz | dy | j) ? 1u : 0u);
-              }
+          for (int hy = 0; hy < T::HH; ++hy) {
+            constexpr int TH = T::TH;
+            const int oy_min = hy - 2 > 0 ? hy - 2 : 0, oy_max = hy < TH - 1 ? hy : TH - 1;
+            const int cnt = oy_max - oy_min + 1, b0 = 2 - (hy - oy_min);
+#pragma unroll
+            for (int j = 0; j < C::KS; ++j) {
+              const uint32_t al = a_lo + (uint32_t)(((((od + dz) * T::HH + hy) * T::ROWB) + (int)C::step_off(j)) >> 4);
+              const uint32_t bl = w_lo + (uint32_t)((((dz * C::KS + j) * T::WS_BYTES) + b0 * 256) >> 4);
+              umma_f16_lohi<true>(dplane + (uint32_t)(oy_min * 16), al, A_HI, bl, B_HI, umma_idesc(16 * cnt));
             }
-        }
+          }
+        umma_commit(smem_u32(&s_mbar_mma[od]));
       }
-      umma_commit(smem_u32(&s_mbar_mma[od]));
     }
   }
   // ---- epilogue: thread = voxel x0 + tid, one output row at a time

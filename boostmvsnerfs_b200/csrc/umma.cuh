@@ -23,6 +23,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// same with the descriptors given as (low, high) 32-bit halves and a compile-time accumulate flag: an issue loop
+// that only advances the low words by constants costs two integer adds per MMA
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+  asm volatile("{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %6, 0;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n"
+               " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n"
+               ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
 // one K = 16 step of a split product: D (+)= A_lo B_hi + A_hi B_lo + A_hi B_hi
 __device__ __forceinline__ void umma_kstep(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lbo, uint32_t a_lo_off, uint32_t b_hi,
                                            uint32_t b_lbo, uint32_t b_lo_off, uint32_t idesc, uint32_t acc) {

@@ -108,6 +108,9 @@ class MergedHeadsCostReg(nn.Module):
     # would run the convolution in TF32 (torch.backends.cudnn.allow_tf32, the default); strict-fp32
     # runs keep cuDNN's fp32 kernels.
     tensor_core_convs = True
+    # Layers (by name) whose stride-1 convolution runs on the tcgen05 kernel (csrc/conv3d_umma.cu) when its input is
+    # fp16: the merged heads (Cin 8) are ~1.7x faster there; the Cin-16 layers are not (profiles/round1l_tcgen05.md).
+    umma_layers = ('heads',)
 
     def __init__(self, net):
         super().__init__()
@@ -125,7 +128,7 @@ class MergedHeadsCostReg(nn.Module):
 
     def _packed_weights(self, device):
         if self._packed is None or self._packed['device'] != device:
-            from .mlp_pack import pack_conv3d_k3, pack_convT3d_k3s2
+            from .mlp_pack import pack_conv3d_k3, pack_conv3d_k3_umma, pack_convT3d_k3s2
             n = self.net
             bias = lambda m: m.bias.detach().float().contiguous().to(device)
             self._packed = {
@@ -136,6 +139,7 @@ class MergedHeadsCostReg(nn.Module):
                 'conv9': (pack_convT3d_k3s2(n.conv9[0].weight).to(device), bias(n.conv9[0])),
                 'conv11': (pack_convT3d_k3s2(n.conv11[0].weight).to(device), bias(n.conv11[0])),
                 'heads': pack_conv3d_k3(self.heads.weight).to(device),
+                'heads_umma': pack_conv3d_k3_umma(self.heads.weight).to(device),
             }
         return self._packed
 
@@ -167,7 +171,10 @@ class MergedHeadsCostReg(nn.Module):
         if fast and y.stride(1) == 1:
             # feature volume and depth logits as two dense tensors (32-byte voxels for the trilinear fetch)
             logits = torch.empty((y.shape[0], 1) + tuple(y.shape[2:]), device=y.device)
-            feat = ops.conv3d_k3(y, pk['heads'], None, 9, relu=False, out2=logits, split=8)
+            if 'heads' in self.umma_layers and y.dtype == torch.float16 and y.stride(4) == y.shape[1]:
+                feat = ops.conv3d_k3(y, pk['heads_umma'], None, 9, relu=False, out2=logits, split=8, engine='umma')
+            else:
+                feat = ops.conv3d_k3(y, pk['heads'], None, 9, relu=False, out2=logits, split=8)
             return feat, logits[:, 0]
         out = self.heads(y)
         return out[:, :8], out[:, 8]

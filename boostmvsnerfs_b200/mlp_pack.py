@@ -255,26 +255,30 @@ CONV3D_K3_UMMA_CIN = (8, 16)            # input channels bmv_conv3d_k3_umma is i
 
 
 def pack_conv3d_k3_umma(weight):
-    """weight (Cout <= 16, Cin in {8, 16}, 3, 3, 3) fp32 -> int32 tensor in the order bmv_conv3d_k3_umma issues its
-    MMAs: [dz][dy][k-step j] x one (N=16, K=16) fp16 B operand in the tcgen05 K-major SWIZZLE_NONE layout
-    ((K/8, N, 8): SBO = 128 B, LBO = 256 B).  Cin 16: k-step j = tap dx = j, K = the 16 channels.  Cin 8: k-step j
-    holds taps dx = 2j (K 0..7) and dx = 2j+1 (K 8..15; dx = 3 does not exist: zeros).  Output channels >= Cout are 0."""
+    """weight (Cout <= 16, Cin in {8, 16}, 3, 3, 3) fp32 -> int32 tensor in the order bmv_conv3d_k3_umma reads:
+    [dz][k-step j] x one STACKED (N=48, K=16) fp16 B operand [W(dz,dy=2); W(dz,1); W(dz,0)] (16 output channels each,
+    channels >= Cout zero) in the tcgen05 K-major SWIZZLE_NONE layout ((K/8, 48, 8): SBO = 128 B, LBO = 768 B) — the
+    kernel multiplies an input row by a row range of it (the output rows that input row contributes to).
+    Cin 16: k-step j = tap dx = j, K = the 16 channels.  Cin 8: k-step j holds taps dx = 2j (K 0..7) and dx = 2j+1
+    (K 8..15; dx = 3 does not exist: zeros)."""
     Cout, Cin = weight.shape[:2]
     if Cin not in CONV3D_K3_UMMA_CIN or Cout > 16 or tuple(weight.shape[2:]) != (3, 3, 3):
         raise ValueError(f"conv3d_k3_umma is not instantiated for weight {tuple(weight.shape)}")
     w = torch.zeros(16, Cin, 3, 3, 3)
     w[:Cout] = weight.detach().float().cpu()
     KS = 3 if Cin == 16 else 2
-    B = torch.zeros(3, 3, KS, 16, 16)                          # [dz][dy][j][n][k]
+    B = torch.zeros(3, KS, 3, 16, 16)                          # [dz][j][block b <-> dy = 2-b][n][k]
     for j in range(KS):
-        if Cin == 16:
-            B[:, :, j] = w[:, :, :, :, j].permute(2, 3, 0, 1)
-        else:
-            for half in range(2):
-                dx = 2 * j + half
-                if dx < 3:
-                    B[:, :, j, :, 8 * half:8 * half + 8] = w[:, :, :, :, dx].permute(2, 3, 0, 1)
-    B = B.half().reshape(9 * KS, 16, 2, 8).permute(0, 2, 1, 3).contiguous()      # per MMA: (K/8, N, 8)
+        for b in range(3):
+            dy = 2 - b
+            if Cin == 16:
+                B[:, j, b] = w[:, :, :, dy, j].permute(2, 0, 1)
+            else:
+                for half in range(2):
+                    dx = 2 * j + half
+                    if dx < 3:
+                        B[:, j, b, :, 8 * half:8 * half + 8] = w[:, :, :, dy, dx].permute(2, 0, 1)
+    B = B.half().reshape(3 * KS, 48, 2, 8).permute(0, 2, 1, 3).contiguous()      # per (dz, j): (K/8, 48, 8)
     return B.reshape(-1).view(torch.int32).to(weight.device)
 
 
