@@ -34,26 +34,31 @@ namespace bmv {
 
 template <int CIN> struct UConv;
 template <> struct UConv<8> {
-  static constexpr int VS = 16, KS = 2, TH = 4, TD = 4, EXTRA = 1;
+  // TMA moves one box ROW per ~2.5 clk whatever its size (measured: 16-byte rows made the copy the bottleneck), so the
+  // (C, W) dimensions are merged into rows of 128 voxels = 256 8-byte elements (the box limit): 36 rows per tile instead
+  // of 4716.  An MMA still spans 128 voxels, of which the last two read past the row: 126 valid outputs per x tile.
+  static constexpr int VS = 16, KS = 2, TH = 4, TD = 4, ROWV = 128, TWV = 126;
   static constexpr uint32_t LAYOUT = 0, A_LBO = 16, A_SBO = 128;
   __device__ static __forceinline__ uint32_t step_off(int j) { return (uint32_t)j * 32u; }      // voxels 2j, 2j+1
 };
 template <> struct UConv<16> {
-  static constexpr int VS = 32, KS = 3, TH = 3, TD = 2, EXTRA = 0;
+  static constexpr int VS = 32, KS = 3, TH = 4, TD = 2, ROWV = 130, TWV = 128;
   static constexpr uint32_t LAYOUT = 6, A_LBO = 16, A_SBO = 256;                                 // SWIZZLE_32B: 8 rows x 32 B
   __device__ static __forceinline__ uint32_t step_off(int j) { return (uint32_t)j * 32u; }      // voxel j
 };
 template <int CIN> struct UTile {
   using C = UConv<CIN>;
-  static constexpr int TW = 128, TH = C::TH, TD = C::TD, HH = TH + 2, HD = TD + 2;
-  static constexpr int ROWV = TW + 2 + C::EXTRA, ROWB = ROWV * C::VS;
+  static constexpr int TW = C::TWV, TH = C::TH, TD = C::TD, HH = TH + 2, HD = TD + 2;   // TW: valid outputs per x tile
+  static constexpr int ROWV = C::ROWV, ROWB = ROWV * C::VS;
   static constexpr int TILE_BYTES = HD * HH * ROWB;
   static constexpr int WS_BYTES = 2 * 48 * 16;               // stacked [W(dz,2); W(dz,1); W(dz,0)] of one (dz, k-step): (K/8, 48, 8) fp16
   static constexpr int W_BYTES = 3 * C::KS * WS_BYTES;
   static constexpr int Z_BYTES = 2 * 16 * TH * 16;           // zero B operand (N = 16 TH) that clears a plane's accumulators
   static constexpr int ROWS = TD * TH;
   static constexpr uint32_t TMEM_COLS = ROWS * 16 <= 32 ? 32 : (ROWS * 16 <= 64 ? 64 : (ROWS * 16 <= 128 ? 128 : 256));
-  static constexpr size_t SMEM = (size_t)TILE_BYTES + W_BYTES + Z_BYTES + 1024;
+  static constexpr int TILE_PAD = 64;                                          // zeros behind the last row (read by the MMA rows past it)
+  static constexpr int TILE_STRIDE = (TILE_BYTES + TILE_PAD + 1023) / 1024 * 1024;   // two staged tiles, each 1024-byte aligned
+  static constexpr size_t SMEM = (size_t)2 * TILE_STRIDE + W_BYTES + Z_BYTES + 1024;
 };
 
 __device__ __forceinline__ void umma_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
@@ -64,64 +69,105 @@ __device__ __forceinline__ void umma_tma_load_5d(uint32_t dst, const CUtensorMap
                ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+__device__ __forceinline__ void umma_tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t mbar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
+constexpr int kUcThreads = 224;     // warp 0: TMA producer, warps 1-2: MMA issuers (half of the planes each), warps 3-6: epilogue
+
+// Persistent, warp-specialised: every CTA (one per SM) walks tiles blockIdx.x, +gridDim.x, ... through a two-slot
+// pipeline.  A slot = one staged halo tile + one set of accumulators (half of the CTA's TMEM columns):
+//   producer : wait empty[slot] -> one 5-D TMA copy of the next tile -> full[slot]
+//   issuers  : wait full[slot] and acc_empty[slot] -> MMAs -> commit acc_full[slot][plane] per plane, empty[slot] at the end
+//   epilogue : wait acc_full[slot][plane] -> tcgen05.ld, bias, ReLU, stores -> arrive acc_empty[slot]
+// so the copy of tile i+1 and the epilogue of tile i-1 run under the MMAs of tile i; TMEM allocation, barrier set-up
+// and the weight copy happen once per CTA.
 template <int CIN>
-__global__ void __launch_bounds__(128, 2) conv3d_k3_umma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kUcThreads, 1) conv3d_k3_umma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tmap,
+                                                                     int n_tiles) {
   using T = UTile<CIN>;
   using C = UConv<CIN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // swizzled TMA boxes and the tensor core XOR absolute address bits: keep the tile 1024-byte aligned
-  unsigned char* tile = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-  unsigned char* wsm = tile + T::TILE_BYTES;
-  __shared__ __align__(8) uint64_t s_mbar_tma;
-  __shared__ __align__(8) uint64_t s_mbar_mma[T::TD];
+  // swizzled TMA boxes and the tensor core XOR absolute address bits: keep the tiles 1024-byte aligned
+  unsigned char* tile0 = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+  unsigned char* wsm = tile0 + 2 * T::TILE_STRIDE;
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_acc_empty[2], s_acc_full[2][T::TD];
   __shared__ uint32_t s_tmem;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_w = (p.W + T::TW - 1) / T::TW, tiles_h = (p.H + T::TH - 1) / T::TH, tiles_d = (p.D + T::TD - 1) / T::TD;
-  int b = blockIdx.x;
-  const int tw = b % tiles_w; b /= tiles_w;
-  const int th = b % tiles_h; b /= tiles_h;
-  const int td = b % tiles_d; b /= tiles_d;
-  const int n = b;
-  const int x0 = tw * T::TW, y0 = th * T::TH, d0 = td * T::TD;
-  const uint32_t mbar_tma = smem_u32(&s_mbar_tma);
   if (tid == 0) {
-    mbar_init(mbar_tma, 1);
-    for (int i = 0; i < T::TD; ++i) mbar_init(smem_u32(&s_mbar_mma[i]), 1);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      mbar_init(smem_u32(&s_full[s2]), 1);
+      mbar_init(smem_u32(&s_empty[s2]), 2);                 // both issuer warps commit
+      mbar_init(smem_u32(&s_acc_empty[s2]), 128);           // every epilogue thread arrives
+      for (int i = 0; i < T::TD; ++i) mbar_init(smem_u32(&s_acc_full[s2][i]), 1);
+    }
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), T::TMEM_COLS);
-  __syncthreads();
-  if (tid == 0) {
-    umma_mbar_expect_tx(mbar_tma, (uint32_t)T::TILE_BYTES);
-    umma_tma_load_5d(smem_u32(tile), &tmap, mbar_tma, 0, x0 - 1, y0 - 1, d0 - 1, n);
-  }
-  {                                                         // weights (already in operand order) under the bulk copy
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 2 * T::TMEM_COLS);
+  {                                                         // weights (already in operand order) + the zero operand, once per CTA
     const uint4* src = reinterpret_cast<const uint4*>(p.wfrag);
     uint4* dst = reinterpret_cast<uint4*>(wsm);
-    for (int i = tid; i < T::W_BYTES / 16; i += 128) dst[i] = __ldg(src + i);
-    for (int i = tid; i < T::Z_BYTES / 16; i += 128) dst[T::W_BYTES / 16 + i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < T::W_BYTES / 16; i += kUcThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < T::Z_BYTES / 16; i += kUcThreads) dst[T::W_BYTES / 16 + i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 2 * T::TILE_PAD / 16)
+      *reinterpret_cast<uint4*>(tile0 + (tid / (T::TILE_PAD / 16)) * T::TILE_STRIDE + T::TILE_BYTES + (tid % (T::TILE_PAD / 16)) * 16) =
+          make_uint4(0u, 0u, 0u, 0u);
   }
   proxy_fence_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-  // ---- issue: lane 0 of warps 0 and 1, half of the output planes each (their accumulators are disjoint)
-  if ((tid & 31) == 0 && warp < 2) {
-    mbar_wait(mbar_tma, 0);
-    tc_fence_after();
-    // descriptors: high word constant, low word = (address >> 4) | (LBO >> 4) << 16 advanced by compile-time offsets
-    constexpr uint32_t A_HI = (C::A_SBO >> 4) | (1u << 14) | (C::LAYOUT << 29);
-    constexpr uint32_t B_HI = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo = ((smem_u32(tile) & 0x3FFFFu) >> 4) | ((C::A_LBO >> 4) << 16);
-    const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | ((768u >> 4) << 16);                  // stacked weights: LBO = 48 rows x 16 B
-    const uint32_t z_lo = (((smem_u32(wsm) + T::W_BYTES) & 0x3FFFFu) >> 4) | (((16u * T::TH * 16u) >> 4) << 16);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int slot = it & 1, ph = (it >> 1) & 1;
+        int b = t;
+        const int tw = b % tiles_w; b /= tiles_w;
+        const int th = b % tiles_h; b /= tiles_h;
+        const int td = b % tiles_d; b /= tiles_d;
+        mbar_wait(smem_u32(&s_empty[slot]), ph ^ 1);        // the MMAs that read this slot two tiles ago are done
+        umma_mbar_expect_tx(smem_u32(&s_full[slot]), (uint32_t)T::TILE_BYTES);
+        if (CIN == 8)                                       // merged (C, W) rows of 8-byte elements: 2 per voxel
+          umma_tma_load_4d(smem_u32(tile0 + slot * T::TILE_STRIDE), &tmap, smem_u32(&s_full[slot]), (tw * T::TW - 1) * 2, th * T::TH - 1,
+                           td * T::TD - 1, b);
+        else
+          umma_tma_load_5d(smem_u32(tile0 + slot * T::TILE_STRIDE), &tmap, smem_u32(&s_full[slot]), 0, tw * T::TW - 1, th * T::TH - 1,
+                           td * T::TD - 1, b);
+      }
+    }
+  } else if (warp <= 2) {
+    // ------------------------------------------------------------------ MMA issuers: lane 0 of warps 1, 2
+    if (lane == 0) {
+      constexpr uint32_t A_HI = (C::A_SBO >> 4) | (1u << 14) | (C::LAYOUT << 29);
+      constexpr uint32_t B_HI = (128u >> 4) | (1u << 14);
+      const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | ((768u >> 4) << 16);                // stacked weights: LBO = 48 rows x 16 B
+      const uint32_t z_lo = (((smem_u32(wsm) + T::W_BYTES) & 0x3FFFFu) >> 4) | (((16u * T::TH * 16u) >> 4) << 16);
+      constexpr int PL = (T::TD + 1) / 2;                   // planes per issuer
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int slot = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(smem_u32(&s_full[slot]), ph);
+        mbar_wait(smem_u32(&s_acc_empty[slot]), ph ^ 1);
+        tc_fence_after();
+        const uint32_t a_lo = ((smem_u32(tile0 + slot * T::TILE_STRIDE) & 0x3FFFFu) >> 4) | ((C::A_LBO >> 4) << 16);
+        const uint32_t dslot = tmem_base + (uint32_t)(slot * T::TMEM_COLS);
+        // Consecutive MMAs into the same accumulator columns serialise on the tensor pipe's latency (measured: ~66 clk
+        // per MMA with one chain per issuer), so the planes of this issuer are interleaved innermost: independent chains.
+        const int odb = (warp - 1) * PL;
 #pragma unroll
-    for (int oi = 0; oi < (T::TD + 1) / 2; ++oi) {
-      const int od = warp * ((T::TD + 1) / 2) + oi;
-      if (od < T::TD) {
-        const uint32_t dplane = tmem_base + (uint32_t)(od * T::TH * 16);
-        umma_f16_lohi<false>(dplane, a_lo + (uint32_t)((((od + 1) * T::HH + 1) * T::ROWB) >> 4), A_HI, z_lo, B_HI, umma_idesc(16 * T::TH));
+        for (int oi = 0; oi < PL; ++oi)
+          if (odb + oi < T::TD)
+            umma_f16_lohi<false>(dslot + (uint32_t)((odb + oi) * T::TH * 16), a_lo + (uint32_t)((((odb + oi + 1) * T::HH + 1) * T::ROWB) >> 4),
+                                 A_HI, z_lo, B_HI, umma_idesc(16 * T::TH));
 #pragma unroll
         for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
@@ -131,82 +177,104 @@ __global__ void __launch_bounds__(128, 2) conv3d_k3_umma_kernel(bmv_conv3d_param
             const int cnt = oy_max - oy_min + 1, b0 = 2 - (hy - oy_min);
 #pragma unroll
             for (int j = 0; j < C::KS; ++j) {
-              const uint32_t al = a_lo + (uint32_t)(((((od + dz) * T::HH + hy) * T::ROWB) + (int)C::step_off(j)) >> 4);
               const uint32_t bl = w_lo + (uint32_t)((((dz * C::KS + j) * T::WS_BYTES) + b0 * 256) >> 4);
-              umma_f16_lohi<true>(dplane + (uint32_t)(oy_min * 16), al, A_HI, bl, B_HI, umma_idesc(16 * cnt));
+#pragma unroll
+              for (int oi = 0; oi < PL; ++oi) {
+                const int od = odb + oi;
+                if (od < T::TD) {
+                  const uint32_t al = a_lo + (uint32_t)(((((od + dz) * T::HH + hy) * T::ROWB) + (int)C::step_off(j)) >> 4);
+                  umma_f16_lohi<true>(dslot + (uint32_t)((od * T::TH + oy_min) * 16), al, A_HI, bl, B_HI, umma_idesc(16 * cnt));
+                }
+              }
             }
           }
-        umma_commit(smem_u32(&s_mbar_mma[od]));
+#pragma unroll
+        for (int oi = 0; oi < PL; ++oi)
+          if (odb + oi < T::TD) umma_commit(smem_u32(&s_acc_full[slot][odb + oi]));
+        umma_commit(smem_u32(&s_empty[slot]));              // this issuer's reads of the staged tile are complete
       }
     }
-  }
-  // ---- epilogue: thread = voxel x0 + tid, one output row at a time
-  const int gx = x0 + tid;
-  const int split = p.out2 ? p.split : p.Cout;
-  float bias[16];
+  } else {
+    // ------------------------------------------------------------------ epilogue: thread = voxel x0 + 32 (warp % 4) + lane
+    const int q = warp & 3, vx = q * 32 + lane;
+    const int split = p.out2 ? p.split : p.Cout;
+    float bias[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) bias[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-  for (int od = 0; od < T::TD; ++od) {
-    mbar_wait(smem_u32(&s_mbar_mma[od]), 0);
-    __syncwarp();
-    tc_fence_after();
-    if (d0 + od >= p.D) continue;                           // uniform
-    for (int oy = 0; oy < T::TH; ++oy) {
-      if (y0 + oy >= p.H) break;                            // uniform
-      float v[16];
-      tmem_ld16(trow + (uint32_t)((od * T::TH + oy) * 16), v);
-      if (gx >= p.W) continue;
+    for (int c = 0; c < 16; ++c) bias[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int slot = it & 1, ph = (it >> 1) & 1;
+      int b = t;
+      const int tw = b % tiles_w; b /= tiles_w;
+      const int th = b % tiles_h; b /= tiles_h;
+      const int td = b % tiles_d; b /= tiles_d;
+      const int n = b, x0 = tw * T::TW, y0 = th * T::TH, d0 = td * T::TD;
+      const int gx = x0 + vx;
+      const uint32_t trow = tmem_base + (uint32_t)(slot * T::TMEM_COLS) + ((uint32_t)(q * 32) << 16);
+      for (int od = 0; od < T::TD; ++od) {
+        mbar_wait(smem_u32(&s_acc_full[slot][od]), ph);
+        __syncwarp();
+        tc_fence_after();
+        if (d0 + od >= p.D) continue;                       // uniform
+        for (int oy = 0; oy < T::TH; ++oy) {
+          if (y0 + oy >= p.H) break;                        // uniform
+          float v[16];
+          tmem_ld16(trow + (uint32_t)((od * T::TH + oy) * 16), v);
+          if (gx >= p.W || vx >= T::TW) continue;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        v[c] += bias[c];
-        if (p.relu) v[c] = fmaxf(v[c], 0.f);
-      }
-      const int64_t vo = (int64_t)(d0 + od) * p.o_d_stride + (int64_t)(y0 + oy) * p.o_y_stride + (int64_t)gx * p.o_x_stride;
-      if (p.out_half) {
-        __half* o = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + vo;
-        uint32_t h[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          __half2 t2 = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
-          h[c] = *reinterpret_cast<uint32_t*>(&t2);
-        }
-        if (p.Cout == 8 && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-        else if (p.Cout == 16 && (((uintptr_t)o) & 15) == 0) {
-          *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (2 * c < p.Cout) *reinterpret_cast<uint32_t*>(o + 2 * c) = h[c];
-        }
-      } else {
-        float* o = p.out + (int64_t)n * p.o_n_stride + vo;
-        if ((split == 8 || split == 16) && (((uintptr_t)o) & 15) == 0) {
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          if (split == 16) {
-            *reinterpret_cast<float4*>(o + 8) = make_float4(v[8], v[9], v[10], v[11]);
-            *reinterpret_cast<float4*>(o + 12) = make_float4(v[12], v[13], v[14], v[15]);
+          for (int c = 0; c < 16; ++c) {
+            v[c] += bias[c];
+            if (p.relu) v[c] = fmaxf(v[c], 0.f);
           }
-        } else {
+          const int64_t vo = (int64_t)(d0 + od) * p.o_d_stride + (int64_t)(y0 + oy) * p.o_y_stride + (int64_t)gx * p.o_x_stride;
+          if (p.out_half) {
+            __half* o = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + vo;
+            uint32_t h[8];
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < split) o[c] = v[c];
-        }
-        if (p.out2) {
-          float* o2 = p.out2 + (int64_t)n * p.o2_n_stride + (int64_t)(d0 + od) * p.o2_d_stride + (int64_t)(y0 + oy) * p.o2_y_stride +
-                      (int64_t)gx * p.o2_x_stride;
+            for (int c = 0; c < 8; ++c) {
+              __half2 t2 = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+              h[c] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            if (p.Cout == 8 && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+            else if (p.Cout == 16 && (((uintptr_t)o) & 15) == 0) {
+              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c >= split && c < p.Cout) o2[c - split] = v[c];
+              for (int c = 0; c < 8; ++c)
+                if (2 * c < p.Cout) *reinterpret_cast<uint32_t*>(o + 2 * c) = h[c];
+            }
+          } else {
+            float* o = p.out + (int64_t)n * p.o_n_stride + vo;
+            if ((split == 8 || split == 16) && (((uintptr_t)o) & 15) == 0) {
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              if (split == 16) {
+                *reinterpret_cast<float4*>(o + 8) = make_float4(v[8], v[9], v[10], v[11]);
+                *reinterpret_cast<float4*>(o + 12) = make_float4(v[12], v[13], v[14], v[15]);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c < split) o[c] = v[c];
+            }
+            if (p.out2) {
+              float* o2 = p.out2 + (int64_t)n * p.o2_n_stride + (int64_t)(d0 + od) * p.o2_d_stride + (int64_t)(y0 + oy) * p.o2_y_stride +
+                          (int64_t)gx * p.o2_x_stride;
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c >= split && c < p.Cout) o2[c - split] = v[c];
+            }
+          }
         }
       }
+      tc_fence_before();                                    // this thread's tcgen05.ld of the slot are complete (wait::ld inside tmem_ld16)
+      umma_mbar_arrive(smem_u32(&s_acc_empty[slot]));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, T::TMEM_COLS);
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * T::TMEM_COLS);
 }
 
 typedef CUresult (*UEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -230,14 +298,23 @@ static int launch_uconv(const bmv_conv3d_params& p, cudaStream_t st) {
   BMV_REQUIRE(enc != nullptr, BMV_ERR_CUDA_LAUNCH, "bmv_conv3d_k3_umma: cuTensorMapEncodeTiled is not available");
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
-  const cuuint64_t strides[4] = {(cuuint64_t)p.x_x_stride * 2, (cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2,
-                                 (cuuint64_t)p.x_n_stride * 2};
-  const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)T::ROWV, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(p.x), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (CIN == 8) {
+    // (2W, H, D, N) of 8-byte elements (a voxel = 16 bytes = 2 elements), box = 128 voxels x HH x HD
+    const cuuint64_t dims[4] = {(cuuint64_t)p.W * 2, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2, (cuuint64_t)p.x_n_stride * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)T::ROWV * 2, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<float*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+    const cuuint64_t strides[4] = {(cuuint64_t)p.x_x_stride * 2, (cuuint64_t)p.x_y_stride * 2, (cuuint64_t)p.x_d_stride * 2,
+                                   (cuuint64_t)p.x_n_stride * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)T::ROWV, (cuuint32_t)T::HH, (cuuint32_t)T::HD, 1u};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   BMV_REQUIRE(r == CUDA_SUCCESS, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
   static bool configured = false;
   if (!configured) {
@@ -250,8 +327,10 @@ static int launch_uconv(const bmv_conv3d_params& p, cudaStream_t st) {
     }
     configured = true;
   }
-  const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
-  conv3d_k3_umma_kernel<CIN><<<(unsigned)blocks, 128, T::SMEM, st>>>(p, map);
+  const int64_t tiles = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
+  BMV_REQUIRE(tiles < (1ll << 31), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: too many tiles");
+  const unsigned blocks = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);    // persistent: one CTA per SM (it owns all TMEM it needs)
+  conv3d_k3_umma_kernel<CIN><<<blocks, kUcThreads, T::SMEM, st>>>(p, map, (int)tiles);
   return check_launch("bmv_conv3d_k3_umma");
 }
 

@@ -56,9 +56,10 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
-  while (!done) {
+  for (uint32_t spins = 0; !done; ++spins) {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();                                   // a broken pipeline must fault, not hang the GPU
   }
 }
 // 16 consecutive fp32 columns of this thread's TMEM lane (32 lanes x 32 bit, repeated 16 times)
