@@ -185,22 +185,33 @@ def algorithmic_bytes(wl, rc, volume_bytes=4):
     return out
 
 
-def conv_kernel_bytes(wl, rc, volume_bytes=4):
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, MB per launch) of the kernels `roofline` can name, from the
+# committed `ncu --set full` captures (profiles/round1g_ncu_full_kernels.csv, round1j_ncu_full_conv_tma.csv,
+# round1l_ncu_tcgen05.csv).  Traffic
+# below the algorithmic bytes = part of the input / output was served by the 126 MB L2 (producer and consumer adjacent).
+NCU_TRAFFIC_MB = {"render_fused_l1": 124.2, "fpn_topdown_smooth_full": 275.6, "fpn_topdown_smooth_half": 174.6, "fpn_stem": 81.2,
+                  "cost_volume_l0": 24.3, "cost_volume_l1": 46.1, "heads_l1": 159.8, "conv0_l1": 176.0, "conv0_l0": 156.0}
+
+
+def conv_kernel_bytes(wl, rc, volume_bytes=4, heads_entry="bmv_conv3d_k3"):
     """Compulsory HBM bytes of each libbmv convolution launch of one frame, keyed by entry point, in launch
     order (FPN: stem, half-resolution step, full-resolution step; per cascade level: conv0, conv1, conv2, heads /
-    conv9T, conv11T).  All K chains (N views) are batched in one launch."""
+    conv9T, conv11T).  All K chains (N views) are batched in one launch.  heads_entry: the entry point the merged
+    heads run on (bmv_conv3d_k3_umma when the inference plan routes them to the tcgen05 kernel)."""
     H, W, K, N = wl["H"], wl["W"], wl["K"], wl["n_views"]
     px = N * H * W
     out = {"bmv_fpn_stem": [("fpn_stem", px * 4 * (3 + 8 + 4 + 8))],
            "bmv_fpn_topdown_smooth": [("fpn_topdown_smooth_half", px // 4 * 4 * (32 // 4 + 16 + 32 + 16)),
                                       ("fpn_topdown_smooth_full", px * 4 * (32 // 4 + 8 + 8))],
            "bmv_conv3d_k3": [], "bmv_convT3d_k3s2": []}
+    out.setdefault(heads_entry, [])
     for i in range(rc.num):
         C = int(32 * 2 ** (-i))
         vox = K * rc.volume_planes[i] * int(H * rc.volume_scale[i]) * int(W * rc.volume_scale[i])
         a = volume_bytes      # activations between libbmv kernels are fp16 exactly when the cost volume is
         out["bmv_conv3d_k3"] += [(f"conv0_l{i}", vox * (C * volume_bytes + 8 * a)), (f"conv1_l{i}", vox * 8 * a + vox // 8 * 16 * a),
-                                 (f"conv2_l{i}", vox // 8 * 16 * (a + 4)), (f"heads_l{i}", vox * (8 * a + 9 * 4))]
+                                 (f"conv2_l{i}", vox // 8 * 16 * (a + 4))]
+        out[heads_entry] += [(f"heads_l{i}", vox * (8 * a + 9 * 4))]
         out["bmv_convT3d_k3s2"] += [(f"conv9T_l{i}", vox // 64 * 32 * 4 + vox // 8 * 16 * (4 + a)),
                                     (f"conv11T_l{i}", vox // 8 * 16 * a + vox * 8 * a * 2)]
     return out
@@ -462,6 +473,7 @@ def main_ours(args):
              "bmv_depth_regression": ["depth_regression_l0", "depth_regression_l1"],
              "bmv_render_rays": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_render_rays_mma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
+             "bmv_render_rays_umma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_raygen_sample_fetch": [f"raygen_fetch_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_composite_blend": [f"composite_blend_l{i}" for i in range(rc.num) if rc.render_if[i]]}
     for entry, names in order.items():
@@ -489,7 +501,8 @@ def main_ours(args):
                              "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peak_gbs,
                              "share_of_step": per_launch_ms * launches_per_stage[name] / ms}
     # libbmv convolution kernels (one launch each per frame), same accounting
-    for entry, layers in conv_kernel_bytes(wl, rc, 2 if vol_dtype == "float16" else 4).items():
+    heads_entry = "bmv_conv3d_k3_umma" if ksum.get("bmv_conv3d_k3_umma") else "bmv_conv3d_k3"
+    for entry, layers in conv_kernel_bytes(wl, rc, 2 if vol_dtype == "float16" else 4, heads_entry).items():
         ts = ksum.get(entry, [])
         if len(ts) != len(layers) * args.steps:
             continue
@@ -512,13 +525,37 @@ def main_ours(args):
             k["frac_fp32_peak"] = k["tflops"] / peak_tf
         else:
             k["bound"] = "hbm"
+    # `roofline`: the DOMINANT kernel of the step (largest share of the frame).  That is the fused gather+MLP kernel: its
+    # Linear layers run on the tensor cores, so it is reported against the measured dense tensor peak with its ALGORITHMIC
+    # flops (2 x 14.6 kMAC per sample; the kernel spends 3 fp16 MMAs per fp32 product and ~6 k CUDA-core
+    # instructions per sample on the gather / splits / activations, which is what actually bounds it).
+    # `roofline_hbm`: the dominant HBM-bound hand-written kernel, against the measured copy bandwidth.
+    def _share(n):
+        return kernels[n]["ms_per_launch"] * kernels[n]["launches_per_step"]
     hbm_kernels = {n: k for n, k in kernels.items() if k["bound"] == "hbm"}
-    dom = max(hbm_kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"]) if hbm_kernels else None
+    dom_hbm = max(hbm_kernels, key=_share) if hbm_kernels else None
+    dom = max(kernels, key=_share) if kernels else None
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
+    tf_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if "bf16_tflops_sustained" in peaks
+              else "fallback 2250 TFLOP/s dense bf16 (B200_PROFILING.md)")
+
+    def _traffic(n):
+        return NCU_TRAFFIC_MB[n] * 1e6 if n in NCU_TRAFFIC_MB else None
+
+    def _hbm_obj(n):
+        return {"kernel": n, "bound": "hbm", "achieved": kernels[n]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+                "frac": kernels[n]["frac"], "traffic": _traffic(n), "peak_source": peak_src, "launch_ms": kernels[n]["ms_per_launch"],
+                "algorithmic_bytes": kernels[n]["algorithmic_bytes"], "share_of_step": kernels[n]["share_of_step"]}
     roofline = None
-    if dom:
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak_gbs,
-                    "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
-                    "launch_ms": kernels[dom]["ms_per_launch"]}
+    if dom and kernels[dom]["bound"] == "fp32_fma":
+        k = kernels[dom]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": k["tflops"] / peak_tf, "traffic": _traffic(dom), "peak_source": tf_src, "launch_ms": k["ms_per_launch"],
+                    "algorithmic_flops": k["tflops"] * 1e12 * k["ms_per_launch"] * 1e-3, "share_of_step": k["share_of_step"],
+                    "engine": net.mlp_engine}
+    elif dom:
+        roofline = _hbm_obj(dom)
+    roofline_hbm = _hbm_obj(dom_hbm) if dom_hbm else None
     hand_ms = sum(step_ms_stage.get(k, 0.0) for k in alg)
     eager = {"ms_per_step": ms, "value": world * rays_per_frame / (ms * 1e-3), "e2e_ms_per_step": ms_e2e,
              "e2e_value": world * rays_per_frame / (ms_e2e * 1e-3)}
@@ -540,7 +577,7 @@ def main_ours(args):
         "e2e": {"value": world * rays_per_frame / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "eager": eager, "cuda_graph": graph_res,
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels, "frame_sharded": sharded,
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_hbm": roofline_hbm, "kernels": kernels, "frame_sharded": sharded,
         "stage_ms_per_step": step_ms_stage, "hand_written_ms_per_step": hand_ms,
         "stage_ms_note": "eager instrumented pass: when the GPU outruns the Python enqueue (host_enqueue_ms_per_step >= "
                          "eager ms_per_step) the stage where the stream runs dry is inflated by the host gap; "

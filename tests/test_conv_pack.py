@@ -165,3 +165,49 @@ def test_cost_reg_plan_uses_cudnn_on_cpu_and_when_tf32_is_off():
         feat, logits = plan(x)
         ref_feat, ref_logits = net(x)
     assert torch.allclose(feat, ref_feat, atol=1e-5) and torch.allclose(logits, ref_logits, atol=1e-5)
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 9), (8, 16), (16, 8), (16, 12)])
+def test_umma_conv_packing_reproduces_conv3d(cin, cout):
+    """pack_conv3d_k3_umma read back through the kernel's descriptor arithmetic (stacked [W(dz,2); W(dz,1); W(dz,0)]
+    operands of 48 rows, K-major SWIZZLE_NONE: SBO 128 B, LBO 768 B) and applied the way csrc/conv3d_umma.cu issues its
+    MMAs — input row hy feeds output rows oy = hy-2..hy with the row range starting at block 2-(hy-oy_min); Cin 8 pairs
+    the taps (dx, dx+1) in one K = 16 step — gives torch's conv3d (fp16 operands)."""
+    import numpy as np
+    from boostmvsnerfs_b200.mlp_pack import pack_conv3d_k3_umma
+    torch.manual_seed(cin + cout)
+    w = (torch.randn(cout, cin, 3, 3, 3) * 0.2).half().float()
+    D, H, W = 3, 5, 7
+    x = torch.randn(1, cin, D, H, W).half().float()
+    ref = torch.nn.functional.conv3d(x, w, padding=1)[0].numpy()
+    raw = pack_conv3d_k3_umma(w).numpy().view(np.float16)
+    KS = 3 if cin == 16 else 2
+    assert raw.size == 3 * KS * 2 * 48 * 8
+
+    def operand(dz, j):                                       # (48, 16) via start + (n/8)*128 + (k/8)*768 + (n%8)*16 + (k%8)*2 bytes
+        base = (dz * KS + j) * 1536
+        m = np.zeros((48, 16), np.float32)
+        for n in range(48):
+            for k in range(16):
+                m[n, k] = raw[(base + (n // 8) * 128 + (k // 8) * 768 + (n % 8) * 16 + (k % 8) * 2) // 2]
+        return m
+
+    xp = np.zeros((cin, D + 2, H + 2, W + 4), np.float32)     # zero halo (what the TMA unit fills) + the pair partner of dx = 2
+    xp[:, 1:-1, 1:-1, 1:W + 1] = x[0].numpy()
+    TH = H
+    out = np.zeros((16, D, H, W), np.float32)
+    for od in range(D):
+        for dz in range(3):
+            for hy in range(TH + 2):
+                oy_min, oy_max = max(hy - 2, 0), min(hy, TH - 1)
+                cnt, b0 = oy_max - oy_min + 1, 2 - (hy - max(hy - 2, 0))
+                for j in range(KS):
+                    B = operand(dz, j)[16 * b0:16 * (b0 + cnt)]                   # (16 cnt, 16)
+                    row = xp[:, od + dz, hy]                                      # (cin, W+4)
+                    for xo in range(W):
+                        a = row[:, xo + j] if cin == 16 else np.concatenate([row[:, xo + 2 * j], row[:, xo + 2 * j + 1]])
+                        acc = B @ a
+                        for r in range(cnt):
+                            out[:, od, oy_min + r, xo] += acc[16 * r:16 * r + 16]
+    assert np.abs(out[:cout] - ref).max() < 1e-4 * np.abs(ref).max()
+    assert cout == 16 or np.abs(out[cout:]).max() == 0
