@@ -78,13 +78,17 @@ __device__ __forceinline__ float4 lds4f(const float* q) { return *reinterpret_ca
 
 // All 128 threads of a tile: publish the operand rows just written; ONE thread (`leader`) issues the MMAs.
 template <class Issue>
-__device__ __forceinline__ void tile_publish_and_issue(int wg, bool leader, Issue issue) {
+__device__ __forceinline__ void tile_publish_and_issue(int wg, bool leader_warp, bool elected, Issue issue) {
   proxy_fence_async();                 // generic-proxy st.shared -> visible to the tensor core (async proxy)
   tc_fence_before();                   // earlier tcgen05.ld of the columns about to be overwritten
   bar_sync_named(1 + wg, 128);
-  if (leader) {
+  // The WHOLE leader warp walks the issue code on warp-uniform operands and one elected lane executes the MMAs: under a
+  // per-thread `if (row == 0)` every tcgen05.mma cost an ELECT / R2UR.BROADCAST / branch sequence (~125 clk each, ncu on
+  // conv3d_umma.cu), i.e. 7-13 k clk per tile on the critical path of the tile's four warps.
+  if (leader_warp) {
     tc_fence_after();
-    issue();
+    if (elected) issue();
+    __syncwarp();
   }
 }
 // ... and everybody waits for the accumulators of that commit
@@ -230,8 +234,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
   __shared__ __align__(8) uint64_t s_mbar[kUmmaTiles][4];               // [tile][0: phases A-C, 1..3: color.0 of view v]
   __shared__ uint32_t s_tmem;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler too
   const int wg = warp >> 2, row = tid & 127;
+  const int wq = warp & 3;                                                       // warp within the tile
+  const bool elected = elect_one();
   for (int i = tid * 16; i < UMMA_PACK_BYTES; i += kUmmaThreads * 16)
     *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(rp.mlp_weights) + i));
   if (tid < V) s_view[tid] = p.view[tid];
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
       put_chunk(tile, CH_MEAN + 1, row, mean[8], mean[9], mean[10], 0.f, 0.f, 0.f, 0.f, 0.f);
     }
     // global_fc (+bias, folded): G_v = [var | mean] Wgs + x_v Wgv -> cols 32 v
-    tile_publish_and_issue(wg, row == 0, [&]() {
+    tile_publish_and_issue(wg, wq == 0, elected, [&]() {
       const uint32_t id = umma_idesc(32);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
       }
     }
     if (VEC && has_next) vox_consume(vt, vox);
-    tile_publish_and_issue(wg, row == 32, [&]() {
+    tile_publish_and_issue(wg, wq == 1, elected, [&]() {
       const uint32_t id = umma_idesc(16);
       umma_kstep(tcol0 + 96, aT + CH_IM * kChunkBytes, LBO_A, LO_A, wB + UW_FC, 16 * 16, LO_B, id, 0u);
       umma_kstep(tcol0 + 96, aT + (CH_IM + 2) * kChunkBytes, LBO_A, LO_A, wB + UW_FC + 2 * 16 * 16, 16 * 16, LO_B, id, 1u);
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
       put_chunk(tile, CH_POOLED + 1, row, pc[8], pc[9], pc[10], pc[11], pc[12], pc[13], pc[14], pc[15]);
     }
     if (VEC && has_next) view_consume(p, wt, f[0]);
-    tile_publish_and_issue(wg, row == 64, [&]() {
+    tile_publish_and_issue(wg, wq == 2, elected, [&]() {
       const uint32_t id = umma_idesc(64);
       umma_kstep(tcol0 + 112, aT + CH_POOLED * kChunkBytes, LBO_A, LO_A, wB + UW_L0, 64 * 16, LO_B, id, 0u);
       umma_kstep(tcol0 + 112, aT + CH_VOX * kChunkBytes, LBO_A, LO_A, wB + UW_L0 + 2 * 64 * 16, 64 * 16, LO_B, id, 1u);
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) render_rays_umma_kernel(bmv_r
     }
     if (VEC && has_next) view_consume(p, wt, f[1]);
     // color.0 (+bias, folded) per view: C_v = [hid | pooled | vox | 1] Wcs + f_v Wcv -> cols 64 v, one commit per view
-    tile_publish_and_issue(wg, row == 96, [&]() {
+    tile_publish_and_issue(wg, wq == 3, elected, [&]() {
       const uint32_t id = umma_idesc(64);
 #pragma unroll
       for (int v = 0; v < V; ++v) {

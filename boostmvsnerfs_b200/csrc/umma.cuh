@@ -40,6 +40,12 @@ __device__ __forceinline__ void umma_kstep(uint32_t d_tmem, uint32_t a_hi, uint3
   umma_f16(d_tmem, ah, bl, idesc, 1u);
   umma_f16(d_tmem, ah, bh, idesc, 1u);
 }
+// true in exactly one (elected) lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
