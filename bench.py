@@ -476,6 +476,16 @@ def main_ours(args):
              "bmv_render_rays_umma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_raygen_sample_fetch": [f"raygen_fetch_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_composite_blend": [f"composite_blend_l{i}" for i in range(rc.num) if rc.render_if[i]]}
+    if ksum.get("bmv_cost_volume_var_multi"):
+        # level 0: ONE launch for the K chains; every unique source view is read once, K volumes are written
+        order["bmv_cost_volume_var"] = ["cost_volume_l1"]
+        order["bmv_cost_volume_var_multi"] = ["cost_volume_l0"]
+        C0 = 32
+        hs0, ws0 = int(wl["H"] * rc.im_feat_scale[0]), int(wl["W"] * rc.im_feat_scale[0])
+        h0, w0, D0 = int(wl["H"] * rc.volume_scale[0]), int(wl["W"] * rc.volume_scale[0]), rc.volume_planes[0]
+        vb = 2 if vol_dtype == "float16" else 4
+        # stored per chain like the other entries (the accounting below multiplies by K)
+        alg["cost_volume_l0"] = (wl["n_views"] * C0 * hs0 * ws0 * 4) // wl["K"] + C0 * D0 * h0 * w0 * vb
     for entry, names in order.items():
         ts = ksum.get(entry, [])
         per_frame = len(ts) // max(1, args.steps)

@@ -29,6 +29,11 @@ class CostVolumeParams(C.Structure):
                 ("out_bf16", i32), ("exact_coords", i32)]
 
 
+class CostVolumeMultiParams(C.Structure):
+    _fields_ = [("b", CostVolumeParams), ("K", i32), ("views_per_chain", i32), ("chain_mask", i32 * MAX_VIEWS),
+                ("out_k_stride", i64)]
+
+
 class DepthPlanesFirstParams(C.Structure):
     _fields_ = [("near_far", C.c_void_p), ("t", C.c_void_p),
                 ("D", i32), ("h", i32), ("w", i32), ("depth_inv", i32),
@@ -156,6 +161,7 @@ class FpnStemParams(C.Structure):
 
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
+    "bmv_cost_volume_var_multi": CostVolumeMultiParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
     "bmv_depth_planes_next": DepthPlanesNextParams,
     "bmv_depth_regression": DepthRegressionParams,

@@ -383,6 +383,110 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
   }
 }
 
+// v5-multi: the K cost volumes of cascade level 0 in ONE launch.  They share the target frustum and the depth
+// hypotheses, and their view triples are drawn from the same N source views, so a warped feature of view u at
+// (voxel, plane) is identical in every chain that contains u: gather each of the U UNIQUE views once (U x 4 taps
+// instead of K x S x 4 — 24 instead of 48 for K = 4 triples out of 6 views) and keep one (sum, sum of squares) pair per
+// chain.  Same tap sharing through warp shuffles as v5; PB = 1.
+constexpr int kMultiMaxK = 4;
+template <int CG, typename OutT>
+__global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_volume_multi_params mp, int DG) {
+  const bmv_cost_volume_params& p = mp.b;
+  constexpr int VW = 32 / CG;                            // voxels per warp
+  const int U = p.S, K = mp.K;
+  __shared__ float sP[BMV_MAX_VIEWS * 12];
+  if (threadIdx.x < U * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x_base = (blockIdx.x * 8 + warp) * VW;
+  const int y = blockIdx.y;
+  if (x_base >= p.w) return;
+  const int d_begin = blockIdx.z * DG, d_end = min(p.D, d_begin + DG);
+  const float sx = 2.f / (float)(p.Ws - 1), sy = 2.f / (float)(p.Hs - 1);
+  const int ys = (int)p.feat_y_stride, xs = (int)p.feat_x_stride;
+  // ---- tap-task role: lane L computes the taps of (unique view L / VW, voxel L % VW)
+  const bool tapper = lane < VW * U;
+  const int t_u = tapper ? lane / VW : 0, t_v = lane % VW;
+  const int t_x = min(x_base + t_v, p.w - 1);
+  const float* tP = sP + t_u * 12;
+  const float ax = dot3_gemm(tP[0], tP[1], tP[2], (float)t_x, (float)y, 1.f);
+  const float ay = dot3_gemm(tP[4], tP[5], tP[6], (float)t_x, (float)y, 1.f);
+  const float az = dot3_gemm(tP[8], tP[9], tP[10], (float)t_x, (float)y, 1.f);
+  const float* t_planes = p.planes + ((int64_t)y * p.w + t_x) * p.planes_pix_stride;
+  // ---- consumer role: voxel v of the warp, 4 channels starting at c0
+  const int v = lane / CG, c0 = (lane % CG) * 4;
+  const int x = x_base + v;
+  const bool active = x < p.w;
+  OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
+  const float invS = 1.f / (float)mp.views_per_chain;
+  for (int d = d_begin; d < d_end; ++d) {
+    const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
+    const FastTap t = fast_taps(ax, ay, az, tP, idep, sx, sy, p.Hs, p.Ws, ys, xs);
+    float4 sum[kMultiMaxK], sq[kMultiMaxK];
+#pragma unroll
+    for (int k = 0; k < kMultiMaxK; ++k) { sum[k] = make_float4(0.f, 0.f, 0.f, 0.f); sq[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int u = 0; u < BMV_MAX_VIEWS; ++u) {
+      if (u < U) {                                       // uniform
+        const int src = u * VW + v;
+        const int o0 = __shfl_sync(0xffffffffu, t.off[0], src), o1 = __shfl_sync(0xffffffffu, t.off[1], src);
+        const int o2 = __shfl_sync(0xffffffffu, t.off[2], src), o3 = __shfl_sync(0xffffffffu, t.off[3], src);
+        const float w0 = __shfl_sync(0xffffffffu, t.w[0], src), w1 = __shfl_sync(0xffffffffu, t.w[1], src);
+        const float w2 = __shfl_sync(0xffffffffu, t.w[2], src), w3 = __shfl_sync(0xffffffffu, t.w[3], src);
+        const float* base = p.feat + (int64_t)p.view[u] * p.feat_view_stride + c0;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base + o0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(base + o1));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(base + o2));
+        const float4 e = __ldg(reinterpret_cast<const float4*>(base + o3));
+        const float v0 = fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x)));
+        const float v1 = fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y)));
+        const float v2 = fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z)));
+        const float v3 = fmaf(w3, e.w, fmaf(w2, c.w, fmaf(w1, b.w, w0 * a.w)));
+        const int mask = mp.chain_mask[u];
+#pragma unroll
+        for (int k = 0; k < kMultiMaxK; ++k)
+          if ((mask >> k) & 1) {                         // uniform
+            sum[k].x += v0; sum[k].y += v1; sum[k].z += v2; sum[k].w += v3;
+            sq[k].x = fmaf(v0, v0, sq[k].x); sq[k].y = fmaf(v1, v1, sq[k].y);
+            sq[k].z = fmaf(v2, v2, sq[k].z); sq[k].w = fmaf(v3, v3, sq[k].w);
+          }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < kMultiMaxK; ++k)
+        if (k < K) {
+          float4 var;
+          { const float m = sum[k].x * invS; var.x = fmaf(-m, m, sq[k].x * invS); }
+          { const float m = sum[k].y * invS; var.y = fmaf(-m, m, sq[k].y * invS); }
+          { const float m = sum[k].z * invS; var.z = fmaf(-m, m, sq[k].z * invS); }
+          { const float m = sum[k].w * invS; var.w = fmaf(-m, m, sq[k].w * invS); }
+          OutT* out = outp + (int64_t)k * mp.out_k_stride + (int64_t)d * p.out_d_stride;
+          if constexpr (sizeof(OutT) == 4) {
+            *reinterpret_cast<float4*>(out) = var;
+          } else {
+            uint2 pk;
+            pk.x = pack_out2<OutT>(var.x, var.y);
+            pk.y = pack_out2<OutT>(var.z, var.w);
+            *reinterpret_cast<uint2*>(out) = pk;
+          }
+        }
+    }
+  }
+}
+
+template <typename OutT>
+static int launch_cost_volume_multi(const bmv_cost_volume_multi_params& mp, cudaStream_t st) {
+  const bmv_cost_volume_params& p = mp.b;
+  const int CG = p.C / 4, threads = 256, vpb = threads / CG;
+  int DG = p.D;
+  while (DG > 2 && (int64_t)p.w * p.h * CG * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
+  dim3 grid((p.w + vpb - 1) / vpb, p.h, (p.D + DG - 1) / DG);
+  if (CG == 8) cost_volume_var_multi_kernel<8, OutT><<<grid, threads, 0, st>>>(mp, DG);
+  else cost_volume_var_multi_kernel<4, OutT><<<grid, threads, 0, st>>>(mp, DG);
+  return check_launch("bmv_cost_volume_var_multi");
+}
+
 // ---------------------------------------------------------------- depth hypotheses, level 0
 __global__ void depth_planes_first_kernel(bmv_depth_planes_first_params p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,6 +624,34 @@ extern "C" BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_
   if (p->out_bf16 == 1) return launch_cost_volume<__nv_bfloat16>(*p, st);
   if (p->out_bf16 == 2) return launch_cost_volume<__half>(*p, st);
   return launch_cost_volume<float>(*p, st);
+}
+
+extern "C" BMV_API int bmv_cost_volume_var_multi(const bmv_cost_volume_multi_params* mp, bmv_stream_t stream) {
+  using namespace bmv;
+  BMV_REQUIRE(mp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var_multi: null params");
+  const bmv_cost_volume_params* p = &mp->b;
+  BMV_REQUIRE(p->feat && p->proj && p->planes && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var_multi: null device pointer");
+  BMV_REQUIRE(p->S >= 1 && p->S <= BMV_MAX_VIEWS && p->Hs >= 2 && p->Ws >= 2 && p->D >= 1 && p->h >= 1 && p->w >= 1 && p->h <= 65535,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var_multi: bad size");
+  BMV_REQUIRE(mp->K >= 1 && mp->K <= kMultiMaxK && mp->views_per_chain >= 1, BMV_ERR_UNSUPPORTED_SHAPE,
+              "bmv_cost_volume_var_multi: K=%d chains not supported (1..%d)", mp->K, kMultiMaxK);
+  BMV_REQUIRE((p->C == 32 || p->C == 16) && (32 / (p->C / 4)) * p->S <= 32, BMV_ERR_UNSUPPORTED_SHAPE,
+              "bmv_cost_volume_var_multi: C=%d with %d unique views not instantiated (C 32: <= 8 views, C 16: <= 4)", p->C, p->S);
+  for (int s = 0; s < p->S; ++s)
+    BMV_REQUIRE(p->view[s] >= 0 && mp->chain_mask[s] >= 0 && mp->chain_mask[s] < (1 << mp->K), BMV_ERR_INVALID_ARGUMENT,
+                "bmv_cost_volume_var_multi: bad view / chain mask");
+  BMV_REQUIRE(p->feat_c_stride == 1 && p->out_c_stride == 1 && p->feat_x_stride % 4 == 0 && p->feat_y_stride % 4 == 0 &&
+                  p->feat_view_stride % 4 == 0 && ((uintptr_t)p->feat & 15) == 0 && p->out_x_stride % 4 == 0 &&
+                  p->out_y_stride % 4 == 0 && p->out_d_stride % 4 == 0 && mp->out_k_stride % 4 == 0 &&
+                  ((uintptr_t)p->out & 15) == 0 && p->exact_coords == 0,
+              BMV_ERR_UNSUPPORTED_SHAPE, "bmv_cost_volume_var_multi: channels-last, 16-byte aligned tensors and exact_coords = 0 only");
+  BMV_REQUIRE((int64_t)p->Hs * llabs(p->feat_y_stride) + (int64_t)p->Ws * llabs(p->feat_x_stride) < (1ll << 31),
+              BMV_ERR_UNSUPPORTED_SHAPE, "bmv_cost_volume_var_multi: source map too large for 32-bit tap offsets");
+  BMV_REQUIRE(p->out_bf16 >= 0 && p->out_bf16 <= 2, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var_multi: out_bf16 must be 0, 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->out_bf16 == 1) return launch_cost_volume_multi<__nv_bfloat16>(*mp, st);
+  if (p->out_bf16 == 2) return launch_cost_volume_multi<__half>(*mp, st);
+  return launch_cost_volume_multi<float>(*mp, st);
 }
 
 extern "C" BMV_API int bmv_depth_planes_first(const bmv_depth_planes_first_params* p, bmv_stream_t stream) {

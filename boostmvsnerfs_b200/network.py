@@ -49,6 +49,7 @@ class EnerfNetwork(nn.Module):
         self.fold_bn = True                    # eval-mode BN folded into the convolutions
         self.channels_last = True              # NHWC / NDHWC activations, volumes emitted channels-last
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
+        self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
         self.generate_rays = False             # True: rays of full target images are generated on the device
@@ -255,8 +256,15 @@ class EnerfNetwork(nn.Module):
                     planes0, nf0 = ops.depth_planes_first(near_far, D, h, w, rc.depth_inv[i])
                     planes = planes0                       # shared (D,)
                     nf = nf0                               # shared (2,h,w)
-                    for k in range(K):
-                        ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
+                    uniq = {int(v) for t in triples for v in t}
+                    if (self.channels_last and self.multi_chain_volume and f.stride(1) == 1 and len({len(t) for t in triples}) == 1
+                            and all(len(set(t)) == len(t) for t in triples) and ops.cost_volume_multi_supported(C, len(uniq), K)):
+                        # the chains share the hypotheses and draw their views from the same N maps: warp every
+                        # unique view once and feed all the variances it belongs to
+                        ops.cost_volume_var_shared_multi(f, triples, projs[i], planes0, h, w, out=vols)
+                    else:
+                        for k in range(K):
+                            ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
                 else:                                      # all K chains' hypotheses in one launch
                     planes, nf = ops.depth_planes_next_batched(depth, std, nf, D, h, w, rc.depth_inv[i])
                     for k in range(K):

@@ -104,6 +104,46 @@ def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dty
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
+def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out):
+    """The K level-0 cost volumes (shared depth hypotheses) in one launch: every unique source view is warped once
+    per (voxel, plane) and feeds the variance of each chain it belongs to (bmv_cost_volume_var_multi).
+    feats (N,C,Hs,Ws) channels-last, triples: K lists of view ids (equal lengths), out (K,C,D,h,w) with
+    channels-last-3d volumes (fp32 / bf16 / fp16), written in place."""
+    _f32(feats, "feats")
+    proj = _cf32(proj, "proj")
+    planes_d = _cf32(planes_d, "planes")
+    N, Cc, Hs, Ws = feats.shape
+    K, S = len(triples), len(triples[0])
+    if any(len(t) != S for t in triples):
+        raise BmvError("cost_volume_var_shared_multi: every chain needs the same number of views")
+    uniq = sorted({int(v) for t in triples for v in t})
+    D = planes_d.numel()
+    if out.shape != (K, Cc, D, h, w) or out.stride(1) != 1:
+        raise BmvError("cost_volume_var_shared_multi: out must be (K,C,D,h,w) with channels-last-3d volumes")
+    mp = _lib.CostVolumeMultiParams()
+    p = mp.b
+    p.feat = feats.data_ptr()
+    p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
+    _views(p.view, uniq)
+    p.S, p.C, p.Hs, p.Ws = len(uniq), Cc, Hs, Ws
+    p.proj, p.planes = proj.data_ptr(), planes_d.data_ptr()
+    p.planes_d_stride, p.planes_pix_stride = 1, 0
+    p.D, p.h, p.w = D, h, w
+    p.exact_coords = 0
+    p.out = out.data_ptr()
+    p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride(1), out.stride(2), out.stride(3), out.stride(4)
+    p.out_bf16 = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out.dtype]
+    mp.K, mp.views_per_chain, mp.out_k_stride = K, S, out.stride(0)
+    for i, u in enumerate(uniq):
+        mp.chain_mask[i] = sum(1 << k for k, t in enumerate(triples) if u in [int(v) for v in t])
+    _lib.call("bmv_cost_volume_var_multi", mp, _stream())
+    return out
+
+
+def cost_volume_multi_supported(C, n_unique, K):
+    return C in (16, 32) and (32 // (C // 4)) * n_unique <= 32 and 1 <= K <= 4
+
+
 def _cost_volume_launch(p, Cc, D, h, w, device, out, out_dtype, channels_last):
     if out is None:
         if channels_last:   # physical (D,h,w,C), logical (C,D,h,w)

@@ -86,6 +86,20 @@ typedef struct bmv_cost_volume_params {
 } bmv_cost_volume_params;
 BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream);
 
+/* The K cost volumes of one cascade level in ONE launch when they share the depth hypotheses (level 0 of the boost
+ * path: reference lib/networks/boost_enerf/network.py:189-201 builds them one chain at a time).  A warped source
+ * feature is identical in every chain that uses the view, so each UNIQUE view is gathered once per (voxel, plane).
+ * b: as above with view[0..S) = the unique views, planes common to all chains, out = the volume of chain 0;
+ * chain_mask[u] bit k = unique view u belongs to chain k; every chain has views_per_chain views; the volume of chain k
+ * starts out_k_stride elements after chain k-1's.  Channels-last tensors, C in {16, 32}, K <= 4, exact_coords = 0. */
+typedef struct bmv_cost_volume_multi_params {
+  bmv_cost_volume_params b;
+  int32_t K, views_per_chain;
+  int32_t chain_mask[BMV_MAX_VIEWS];
+  int64_t out_k_stride;
+} bmv_cost_volume_multi_params;
+BMV_API int bmv_cost_volume_var_multi(const bmv_cost_volume_multi_params* p, bmv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a3  depth hypotheses.
  * bmv_depth_planes_first: reference lib/networks/enerf/utils.py:103-111,149-153 — D planes shared by

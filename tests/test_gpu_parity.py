@@ -482,3 +482,29 @@ def test_on_device_ray_generation_matches_loader(ops):
         diff = (a[:, 3:6] != rays[:, 3:6]).float().mean().item()
         assert diff < 1e-4, f"{diff:.2e} of the direction components differ"
         close(a[:, 3:6], rays[:, 3:6], "directions", rtol=1e-7)
+
+
+@pytest.mark.parametrize("C,Hs,Ws,triples", [(32, 34, 60, [[0, 1, 2], [1, 2, 3], [3, 4, 5], [0, 2, 5]]),
+                                             (32, 20, 28, [[4, 1, 0], [2, 1, 5]]),
+                                             (16, 40, 36, [[0, 1, 2], [2, 3, 1], [3, 0, 1]])])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_multi_chain_cost_volume_matches_per_chain(ops, C, Hs, Ws, triples, dtype):
+    """bmv_cost_volume_var_multi (all K level-0 volumes in one launch, unique views warped once) against K launches
+    of bmv_cost_volume_var: same taps, only the order of the per-view sums differs."""
+    torch.manual_seed(C + Hs)
+    N = 6
+    feats = torch.randn(N, C, Hs, Ws, device="cuda").contiguous(memory_format=torch.channels_last)
+    h, w, D = Hs // 2, Ws // 2, 12
+    proj = torch.eye(3, 4, device="cuda").repeat(N, 1, 1)
+    proj[:, 0, 0] = 2.0; proj[:, 1, 1] = 2.0                         # target (volume) pixels -> source pixels at 2x
+    proj[:, :, 3] = torch.randn(N, 3, device="cuda") * torch.tensor([3.0, 2.0, 0.01], device="cuda")
+    proj[:, 2, :3] += torch.randn(N, 3, device="cuda") * 1e-3
+    planes = torch.linspace(0.5, 4.0, D, device="cuda")
+    K = len(triples)
+    ref = torch.empty((K, D, h, w, C), device="cuda", dtype=dtype).permute(0, 4, 1, 2, 3)
+    for k in range(K):
+        ops.cost_volume_var_shared(feats, triples[k], proj, planes, h, w, out=ref[k])
+    got = torch.empty((K, D, h, w, C), device="cuda", dtype=dtype).permute(0, 4, 1, 2, 3)
+    ops.cost_volume_var_shared_multi(feats, triples, proj, planes, h, w, out=got)
+    assert ref.float().abs().max() > 0.1
+    close(got, ref, "multi-chain cost volume vs per-chain launches", rtol=1e-5 if dtype == torch.float32 else 2e-3)
