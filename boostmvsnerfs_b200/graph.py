@@ -94,6 +94,40 @@ class FrameGraph:
             entry["ev_staged"].record(cs)
         entry["staged_for"] = batch
 
+    def read_back(self, out, host):
+        """Pipelined read-back of a frame's results: `out` (the dict __call__ returned; its tensors are the graph's
+        static outputs and are overwritten by the next replay) is copied device-to-device into a staging set on the
+        current stream, and from there into the pinned `host` tensors (same keys) on a read-back stream — so the
+        device-to-host transfer of frame i runs under the rendering of frame i+1, like prefetch() does for the upload.
+        Call wait_read_back() (or synchronise) before touching `host`."""
+        keys = [k for k in host if k in out]
+        dev = out[keys[0]].device
+        rb = self.__dict__.setdefault("_rb", {})
+        if rb.get("sig") != tuple((k, tuple(out[k].shape)) for k in keys):
+            rb.clear()
+            rb["sig"] = tuple((k, tuple(out[k].shape)) for k in keys)
+            rb["stage"] = {k: torch.empty_like(out[k]) for k in keys}
+            rb["stream"] = torch.cuda.Stream(device=dev)
+            rb["done"] = torch.cuda.Event()
+            rb["done"].record()
+        main = torch.cuda.current_stream()
+        main.wait_event(rb["done"])                         # the previous frame's transfer has read the staging set
+        for k in keys:
+            rb["stage"][k].copy_(out[k], non_blocking=True)
+        staged = main.record_event()
+        rb["stream"].wait_event(staged)
+        with torch.cuda.stream(rb["stream"]):
+            for k in keys:
+                host[k].copy_(rb["stage"][k], non_blocking=True)
+            rb["done"].record(rb["stream"])
+
+    def wait_read_back(self):
+        """Make the current stream wait for the last read_back() transfer (then an event / synchronise on it covers
+        the host copies too)."""
+        rb = self.__dict__.get("_rb")
+        if rb:
+            torch.cuda.current_stream().wait_event(rb["done"])
+
     def _load(self, entry, batch):
         net = self.net
         st = entry["static"]

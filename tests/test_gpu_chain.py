@@ -212,3 +212,33 @@ def test_training_mode_and_cpu_are_refused():
         net.eval()(scene)          # CPU tensors: there is no CPU path
     with pytest.raises(FileNotFoundError):
         network.BoostEnerfNetwork(preprocess=False, view_selection_file="/nonexistent/view_selection.json")
+
+
+def test_graph_read_back_pipelines_results(strict_fp32):
+    """FrameGraph.read_back(): a frame's results are staged device-to-device and copied to pinned host memory on a
+    read-back stream while the next frame renders; every frame's host copy equals that frame's own result."""
+    from boostmvsnerfs_b200 import network
+    from boostmvsnerfs_b200.graph import FrameGraph
+    from boostmvsnerfs_b200.synth import make_scene
+    torch.manual_seed(0)
+    net = network.BoostEnerfNetwork(preprocess=True, rc=RenderConfig.enerf_eval(2)).eval().cuda()
+    net.view_selection_outputs = {"synth_0": [1, 2]}
+    net.generate_rays = True
+    pin = lambda sc: {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in sc.items() if not k.startswith("rays_")}
+    frames = [pin(make_scene(H=64, W=96, n_views=4, seed=s, smooth=True, tar_offset=(0.02 * s, 0.0, 0.01 * s))) for s in range(4)]
+    fg = FrameGraph(net)
+    want = [{k: v.clone() for k, v in fg(f).items()} for f in frames]
+    keys = ("rgb_level1", "depth_level1")
+    hosts = [{k: torch.empty(want[0][k].shape, dtype=want[0][k].dtype).pin_memory() for k in keys} for _ in frames]
+    fg.prefetch(frames[0])
+    for i, f in enumerate(frames):
+        out = fg(f)
+        if i + 1 < len(frames):
+            fg.prefetch(frames[i + 1])
+        fg.read_back(out, hosts[i])                                          # no host sync inside the loop
+    fg.wait_read_back()
+    torch.cuda.synchronize()
+    for i in range(len(frames)):
+        for k in keys:
+            _report(hosts[i][k], want[i][k].cpu().numpy(), f"read-back frame {i} {k}", 1e-3)
+    assert (hosts[0]["rgb_level1"] - hosts[1]["rgb_level1"]).abs().max().item() > 1e-2
