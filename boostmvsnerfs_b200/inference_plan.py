@@ -111,6 +111,10 @@ class MergedHeadsCostReg(nn.Module):
     # Layers (by name) whose stride-1 convolution runs on the tcgen05 kernel (csrc/conv3d_umma.cu) when its input is
     # fp16: the merged heads (Cin 8) are ~1.7x faster there; the Cin-16 layers are not (profiles/round1l_tcgen05.md).
     umma_layers = ('heads',)
+    # The layers that stay on cuDNN (conv3..conv7, <= 1/4 resolution) with fp16 activations and weights (fp32
+    # accumulation) when the 3-level net is used: their input (conv2) and consumer (conv9T) are libbmv kernels that take
+    # fp16 anyway.  Measured on B200: 144 -> 96 us for cost_reg_1, no gain for the 2-level cost_reg_0 (32 -> 31 us).
+    lowres_half = True
 
     def __init__(self, net):
         super().__init__()
@@ -125,6 +129,15 @@ class MergedHeadsCostReg(nn.Module):
         return (self.tensor_core_convs and x.is_cuda and x.dtype in (torch.float32, torch.float16) and x.stride(1) == 1
                 and torch.backends.cudnn.allow_tf32 and x.shape[1] in CONV3D_K3_SHAPES
                 and isinstance(self.net.conv0.bn, nn.Identity))
+
+    def _half_lowres(self):
+        """fp16 copies of conv3..conv7 (folded), rebuilt with the plan (PlanCache keys on the parameter versions)."""
+        if getattr(self, '_low16', None) is None:
+            low = nn.Module()
+            for name in ('conv3', 'conv4', 'conv5', 'conv6', 'conv7'):
+                setattr(low, name, copy.deepcopy(getattr(self.net, name)).half())
+            self._low16 = low
+        return self._low16
 
     def _packed_weights(self, device):
         if self._packed is None or self._packed['device'] != device:
@@ -153,14 +166,18 @@ class MergedHeadsCostReg(nn.Module):
             h = torch.float16
             s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True, out_dtype=h)          # ConvBnReLU3D(C, 8)
             s1 = ops.conv3d_k3(s0, *pk['conv1'], 16, relu=True, stride=2, out_dtype=h)   # ConvBnReLU3D(8, 16, stride=2)
-            s1 = ops.conv3d_k3(s1, *pk['conv2'], 16, relu=True)                     # ConvBnReLU3D(16, 16); fp32: cuDNN reads it
+            half_low = self.lowres_half and n.depth_levels == 3
+            # ConvBnReLU3D(16, 16): fp32 where cuDNN's TF32 layers read it, fp16 when they run in fp16 too
+            s1 = ops.conv3d_k3(s1, *pk['conv2'], 16, relu=True, out_dtype=h if half_low else torch.float32)
         else:
+            half_low = False
             s0 = n.conv0(x)
             s1 = n.conv2(n.conv1(s0))
-        s2 = n.conv4(n.conv3(s1))
+        low = self._half_lowres() if half_low else n
+        s2 = low.conv4(low.conv3(s1))
         y = s2
         if n.depth_levels == 3:
-            y = s2 + n.conv7(n.conv6(n.conv5(s2)))
+            y = s2 + low.conv7(low.conv6(low.conv5(s2)))
         if fast and y.stride(1) == 1 and s1.stride(1) == 1:
             y = ops.convT3d_k3s2_add(y, *pk['conv9'], 16, skip=s1, out_dtype=torch.float16)
             # the full-resolution result only feeds the fp16-operand heads convolution: store it as fp16 (TMA-staged there)
