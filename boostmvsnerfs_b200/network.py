@@ -256,15 +256,18 @@ class EnerfNetwork(nn.Module):
                     planes0, nf0 = ops.depth_planes_first(near_far, D, h, w, rc.depth_inv[i])
                     planes = planes0                       # shared (D,)
                     nf = nf0                               # shared (2,h,w)
-                    uniq = {int(v) for t in triples for v in t}
-                    if (self.channels_last and self.multi_chain_volume and f.stride(1) == 1 and len({len(t) for t in triples}) == 1
-                            and all(len(set(t)) == len(t) for t in triples) and ops.cost_volume_multi_supported(C, len(uniq), K)):
-                        # the chains share the hypotheses and draw their views from the same N maps: warp every
-                        # unique view once and feed all the variances it belongs to
-                        ops.cost_volume_var_shared_multi(f, triples, projs[i], planes0, h, w, out=vols)
-                    else:
-                        for k in range(K):
-                            ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
+                    # the chains share the hypotheses and draw their views from the same N maps: warp every unique
+                    # view once per group of <= 4 chains and feed all the variances it belongs to
+                    for k0 in range(0, K, 4):
+                        grp = triples[k0:k0 + 4]
+                        uniq = {int(v) for t in grp for v in t}
+                        if (self.channels_last and self.multi_chain_volume and f.stride(1) == 1 and len(grp) > 1
+                                and len({len(t) for t in grp}) == 1 and all(len(set(t)) == len(t) for t in grp)
+                                and ops.cost_volume_multi_supported(C, len(uniq), len(grp))):
+                            ops.cost_volume_var_shared_multi(f, grp, projs[i], planes0, h, w, out=vols[k0:k0 + len(grp)])
+                        else:
+                            for k in range(k0, k0 + len(grp)):
+                                ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
                 else:                                      # all K chains' hypotheses in one launch
                     planes, nf = ops.depth_planes_next_batched(depth, std, nf, D, h, w, rc.depth_inv[i])
                     for k in range(K):
