@@ -26,7 +26,7 @@ class CostVolumeParams(C.Structure):
                 ("D", i32), ("h", i32), ("w", i32),
                 ("out", C.c_void_p),
                 ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
-                ("out_bf16", i32), ("exact_coords", i32)]
+                ("out_bf16", i32), ("exact_coords", i32), ("feat_half", i32), ("reserved0", i32)]
 
 
 class CostVolumeMultiParams(C.Structure):
@@ -149,7 +149,7 @@ class FpnFusedParams(C.Structure):
     _fields_ = [("prev", C.c_void_p), ("lateral_in", C.c_void_p), ("lat_weight", C.c_void_p), ("lat_bias", C.c_void_p),
                 ("wfrag", C.c_void_p), ("bias", C.c_void_p),
                 ("N", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
-                ("mid", C.c_void_p), ("out", C.c_void_p)]
+                ("mid", C.c_void_p), ("out", C.c_void_p), ("out16", C.c_void_p)]
 
 
 class FpnStemParams(C.Structure):

@@ -190,6 +190,18 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume
 // reference's own CPU-vs-CUDA difference (ATen multiplies by the reciprocal of scalar divisors on CUDA).
 struct FastTap { int off[4]; float w[4]; };
 
+// 4 consecutive channels of a source texel: fp32 maps (16-byte load) or fp16 maps (8-byte load, half the L1 wavefronts)
+template <typename FeatT>
+__device__ __forceinline__ float4 ld_feat4(const FeatT* q) {
+  if constexpr (sizeof(FeatT) == 4) {
+    return __ldg(reinterpret_cast<const float4*>(q));
+  } else {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(q));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
 __device__ __forceinline__ FastTap fast_taps(float ax, float ay, float az, const float* __restrict__ P, float idep,
                                              float sx, float sy, int Hs, int Ws, int ys, int xs) {
   const float cx = fmaf(P[3], idep, ax), cy = fmaf(P[7], idep, ay), cz = fmaf(P[11], idep, az);
@@ -296,7 +308,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volum
 // A warp owns VW = 32/CG consecutive x; per round it handles PB planes so that VW*S*PB <= 32 tap
 // tasks fill the warp: lane L computes task (plane slot, view, voxel) = (L / (VW*S), (L % (VW*S)) / VW,
 // L % VW); the consumer lane of voxel v fetches its 4 offsets + 4 weights per view with 8 shuffles.
-template <int S, int CG, int PB, typename OutT>
+template <int S, int CG, int PB, typename OutT, typename FeatT = float>
 __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volume_params p, int DG) {
   constexpr int VW = 32 / CG;                            // voxels per warp
   constexpr int TASKS = VW * S * PB;
@@ -324,9 +336,9 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
   const int v = lane / CG, c0 = (lane % CG) * 4;
   const int x = x_base + v;
   const bool active = x < p.w;
-  const float* base[S];
+  const FeatT* base[S];
 #pragma unroll
-  for (int s = 0; s < S; ++s) base[s] = p.feat + (int64_t)p.view[s] * p.feat_view_stride + c0;
+  for (int s = 0; s < S; ++s) base[s] = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)p.view[s] * p.feat_view_stride + c0;
   OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   constexpr float invS = 1.f / S;
   for (int d0 = d_begin; d0 < d_end; d0 += PB) {
@@ -347,10 +359,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
         const int o2 = __shfl_sync(0xffffffffu, t.off[2], src), o3 = __shfl_sync(0xffffffffu, t.off[3], src);
         const float w0 = __shfl_sync(0xffffffffu, t.w[0], src), w1 = __shfl_sync(0xffffffffu, t.w[1], src);
         const float w2 = __shfl_sync(0xffffffffu, t.w[2], src), w3 = __shfl_sync(0xffffffffu, t.w[3], src);
-        const float4 a = __ldg(reinterpret_cast<const float4*>(base[s] + o0));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(base[s] + o1));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(base[s] + o2));
-        const float4 e = __ldg(reinterpret_cast<const float4*>(base[s] + o3));
+        const float4 a = ld_feat4(base[s] + o0), b = ld_feat4(base[s] + o1), c = ld_feat4(base[s] + o2), e = ld_feat4(base[s] + o3);
         const float v0 = fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x)));
         const float v1 = fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y)));
         const float v2 = fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z)));
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
 // instead of K x S x 4 — 24 instead of 48 for K = 4 triples out of 6 views) and keep one (sum, sum of squares) pair per
 // chain.  Same tap sharing through warp shuffles as v5; PB = 1.
 constexpr int kMultiMaxK = 4;
-template <int CG, typename OutT>
+template <int CG, typename OutT, typename FeatT = float>
 __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_volume_multi_params mp, int DG) {
   const bmv_cost_volume_params& p = mp.b;
   constexpr int VW = 32 / CG;                            // voxels per warp
@@ -433,11 +442,8 @@ __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_vol
         const int o2 = __shfl_sync(0xffffffffu, t.off[2], src), o3 = __shfl_sync(0xffffffffu, t.off[3], src);
         const float w0 = __shfl_sync(0xffffffffu, t.w[0], src), w1 = __shfl_sync(0xffffffffu, t.w[1], src);
         const float w2 = __shfl_sync(0xffffffffu, t.w[2], src), w3 = __shfl_sync(0xffffffffu, t.w[3], src);
-        const float* base = p.feat + (int64_t)p.view[u] * p.feat_view_stride + c0;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(base + o0));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(base + o1));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(base + o2));
-        const float4 e = __ldg(reinterpret_cast<const float4*>(base + o3));
+        const FeatT* base = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)p.view[u] * p.feat_view_stride + c0;
+        const float4 a = ld_feat4(base + o0), b = ld_feat4(base + o1), c = ld_feat4(base + o2), e = ld_feat4(base + o3);
         const float v0 = fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x)));
         const float v1 = fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y)));
         const float v2 = fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z)));
@@ -482,7 +488,10 @@ static int launch_cost_volume_multi(const bmv_cost_volume_multi_params& mp, cuda
   int DG = p.D;
   while (DG > 2 && (int64_t)p.w * p.h * CG * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
   dim3 grid((p.w + vpb - 1) / vpb, p.h, (p.D + DG - 1) / DG);
-  if (CG == 8) cost_volume_var_multi_kernel<8, OutT><<<grid, threads, 0, st>>>(mp, DG);
+  if (p.feat_half) {
+    if (CG == 8) cost_volume_var_multi_kernel<8, OutT, __half><<<grid, threads, 0, st>>>(mp, DG);
+    else cost_volume_var_multi_kernel<4, OutT, __half><<<grid, threads, 0, st>>>(mp, DG);
+  } else if (CG == 8) cost_volume_var_multi_kernel<8, OutT><<<grid, threads, 0, st>>>(mp, DG);
   else cost_volume_var_multi_kernel<4, OutT><<<grid, threads, 0, st>>>(mp, DG);
   return check_launch("bmv_cost_volume_var_multi");
 }
@@ -563,6 +572,10 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
   const int CG3 = p.C / 4;                               // v3 always uses 4 channels per lane
   const bool v3 = cl && p.exact_coords == 0 && threads % CG3 == 0 && CG3 <= threads && p.h <= 65535 &&
                   (int64_t)p.Hs * p.feat_y_stride < (1ll << 31);
+  if (p.feat_half && !v3) {
+    set_error("bmv_cost_volume_var: fp16 feature maps need the channels-last fast path (exact_coords = 0, aligned tensors)");
+    return BMV_ERR_UNSUPPORTED_SHAPE;
+  }
   if (v3) {
     // plane groups as deep as possible (L1 reuse of the sliding texel window along d) while still
     // launching >= ~250k lanes (148 SMs x 2048 threads = 303k resident)
@@ -573,13 +586,19 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
     dim3 grid(xchunks, p.h, (p.D + DG - 1) / DG);
     if constexpr (S <= 4) {
       if (CG3 == 8) {              // C = 32: warp = 4 voxels x 8 lanes, 2 planes per round
-        cost_volume_var_cl5_kernel<S, 8, 2, OutT><<<grid, threads, 0, st>>>(p, DG);
+        if (p.feat_half) cost_volume_var_cl5_kernel<S, 8, 2, OutT, __half><<<grid, threads, 0, st>>>(p, DG);
+        else cost_volume_var_cl5_kernel<S, 8, 2, OutT><<<grid, threads, 0, st>>>(p, DG);
         return check_launch("bmv_cost_volume_var");
       }
       if (CG3 == 4) {              // C = 16: warp = 8 voxels x 4 lanes, 1 plane per round
-        cost_volume_var_cl5_kernel<S, 4, 1, OutT><<<grid, threads, 0, st>>>(p, DG);
+        if (p.feat_half) cost_volume_var_cl5_kernel<S, 4, 1, OutT, __half><<<grid, threads, 0, st>>>(p, DG);
+        else cost_volume_var_cl5_kernel<S, 4, 1, OutT><<<grid, threads, 0, st>>>(p, DG);
         return check_launch("bmv_cost_volume_var");
       }
+    }
+    if (p.feat_half) {
+      set_error("bmv_cost_volume_var: fp16 feature maps are instantiated for C = 16 / 32 with up to 4 views only");
+      return BMV_ERR_UNSUPPORTED_SHAPE;
     }
     cost_volume_var_cl3_kernel<S, 4, OutT><<<grid, threads, 0, st>>>(p, CG3, DG);
   } else if (cl) {

@@ -152,6 +152,11 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
         if (c + 1 < p.Cout + 1 && c < p.Cout) {                         // Cout is even (8 or 16): whole pairs
           if (gx0 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * p.Cout + c) = make_float2(acc[oy][nt][0], acc[oy][nt][1]);
           if (gx1 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * p.Cout + c) = make_float2(acc[oy][nt][2], acc[oy][nt][3]);
+          if (p.out16) {
+            __half* o16 = reinterpret_cast<__half*>(p.out16) + (int64_t)n * p.H * p.W * p.Cout;
+            if (gx0 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx0) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][0], acc[oy][nt][1]);
+            if (gx1 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx1) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][2], acc[oy][nt][3]);
+          }
         }
       }
     }

@@ -16,6 +16,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _feat(t, name):
+    """Source feature maps of the cost-volume kernels: CUDA float32, or float16 (half the bytes per tap; fast path only)."""
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype in (torch.float32, torch.float16)):
+        raise BmvError(f"{name}: expected a CUDA float32 / float16 tensor, got "
+                       f"{type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}")
+    return int(t.dtype == torch.float16)
+
+
 def _f32(t, name):
     if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
         raise BmvError(f"{name}: expected a CUDA float32 tensor, got "
@@ -61,7 +69,7 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
     planes (D,h,w) per-pixel hypotheses or (D,) shared
     -> (C,D,h,w) variance volume (reference lib/networks/enerf/utils.py:324-351)
     """
-    _f32(feats, "feats")
+    feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
     planes = _cf32(planes, "planes")
     N, Cc, Hs, Ws = feats.shape
@@ -69,6 +77,7 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
     assert proj.shape == (N, 3, 4), proj.shape
     p = _lib.CostVolumeParams()
     p.feat = feats.data_ptr()
+    p.feat_half = feat_half
     p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
     _views(p.view, views)
     p.S, p.C, p.Hs, p.Ws = S, Cc, Hs, Ws
@@ -86,13 +95,14 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
 def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dtype=torch.float32,
                            channels_last=False, exact_coords=False):
     """Same as cost_volume_var with D hypotheses shared by every pixel (cascade level 0)."""
-    _f32(feats, "feats")
+    feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
     planes_d = _cf32(planes_d, "planes")
     N, Cc, Hs, Ws = feats.shape
     S = len(views)
     p = _lib.CostVolumeParams()
     p.feat = feats.data_ptr()
+    p.feat_half = feat_half
     p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
     _views(p.view, views)
     p.S, p.C, p.Hs, p.Ws = S, Cc, Hs, Ws
@@ -109,7 +119,7 @@ def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out):
     per (voxel, plane) and feeds the variance of each chain it belongs to (bmv_cost_volume_var_multi).
     feats (N,C,Hs,Ws) channels-last, triples: K lists of view ids (equal lengths), out (K,C,D,h,w) with
     channels-last-3d volumes (fp32 / bf16 / fp16), written in place."""
-    _f32(feats, "feats")
+    feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
     planes_d = _cf32(planes_d, "planes")
     N, Cc, Hs, Ws = feats.shape
@@ -123,6 +133,7 @@ def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out):
     mp = _lib.CostVolumeMultiParams()
     p = mp.b
     p.feat = feats.data_ptr()
+    p.feat_half = feat_half
     p.feat_view_stride, p.feat_c_stride, p.feat_y_stride, p.feat_x_stride = feats.stride()
     _views(p.view, uniq)
     p.S, p.C, p.Hs, p.Ws = len(uniq), Cc, Hs, Ws
@@ -793,10 +804,11 @@ def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None, out_dtype=torch.float32):
     return out
 
 
-def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smooth_bias, cout, write_mid):
+def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smooth_bias, cout, write_mid, want_half=False):
     """mid = up2x(prev) + conv1x1(lateral_in) + lat_bias; out = conv3x3(mid) + smooth_bias in ONE launch
     (reference lib/networks/enerf/feature_net.py:24-47; the 3x3 runs on tensor cores with fp16 operands).
-    Returns (mid or None, out); tensors channels_last, smooth_wfrag from mlp_pack.pack_conv2d_k3_c32."""
+    Returns (mid or None, out); tensors channels_last, smooth_wfrag from mlp_pack.pack_conv2d_k3_c32.
+    want_half: also write an fp16 copy of out (returned as a third value) for the cost-volume kernel's fp16 taps."""
     _f32(prev, "prev"); _f32(lateral_in, "lateral_in")
     N, Cin, H, W = lateral_in.shape
     if not (prev.is_contiguous(memory_format=torch.channels_last) and lateral_in.is_contiguous(memory_format=torch.channels_last)):
@@ -817,8 +829,10 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, Cin, cout
     p.mid = mid.data_ptr() if mid is not None else 0
     p.out = out.data_ptr()
+    out16 = torch.empty((N, cout, H, W), device=prev.device, dtype=torch.float16, memory_format=torch.channels_last) if want_half else None
+    p.out16 = out16.data_ptr() if want_half else 0
     _lib.call("bmv_fpn_topdown_smooth", p, _stream())
-    return mid, out
+    return (mid, out, out16) if want_half else (mid, out)
 
 
 def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False):

@@ -83,6 +83,9 @@ typedef struct bmv_cost_volume_params {
   int32_t out_bf16;             /* 0: fp32 out, 1: out points to bf16 storage, 2: fp16 storage (round-to-nearest-even) */
   int32_t exact_coords;         /* 1: reproduce the reference's coordinate arithmetic op for op (IEEE divisions,
                                    slower); 0: reciprocal-multiply form, coordinates within 2 ulp (default) */
+  int32_t feat_half;            /* 1: feat points to fp16 storage (strides in fp16 elements): half the bytes per bilinear tap.
+                                   TF32-class (the maps come out of TF32-class convolutions): channels-last fast path only */
+  int32_t reserved0;
 } bmv_cost_volume_params;
 BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream);
 
@@ -433,6 +436,7 @@ typedef struct bmv_fpn_fused_params {
   int32_t N, H, W, Cin, Cout;
   float* mid;                   /* (N,H,W,32) or NULL */
   float* out;                   /* (N,H,W,Cout) */
+  void* out16;                  /* optional fp16 copy of out, (N,H,W,Cout) (for the cost-volume kernel's fp16 tap loads), or NULL */
 } bmv_fpn_fused_params;
 BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream);
 BMV_API int bmv_fpn_topdown_smooth_weight_words(int Cout);

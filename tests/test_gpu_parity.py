@@ -508,3 +508,25 @@ def test_multi_chain_cost_volume_matches_per_chain(ops, C, Hs, Ws, triples, dtyp
     ops.cost_volume_var_shared_multi(feats, triples, proj, planes, h, w, out=got)
     assert ref.float().abs().max() > 0.1
     close(got, ref, "multi-chain cost volume vs per-chain launches", rtol=1e-5 if dtype == torch.float32 else 2e-3)
+
+
+def test_cost_volume_fp16_feature_maps(ops):
+    """K1 with fp16 source feature maps (8-byte tap loads) == K1 on the same maps widened to fp32; the fused FPN step can
+    emit such a copy (ops.fpn_topdown_smooth(want_half=True))."""
+    torch.manual_seed(3)
+    N, C, Hs, Ws, D = 4, 16, 40, 56, 8
+    f16 = torch.randn(N, C, Hs, Ws, device="cuda").contiguous(memory_format=torch.channels_last).half()
+    proj = torch.eye(3, 4, device="cuda").repeat(N, 1, 1)
+    proj[:, :, 3] = torch.randn(N, 3, device="cuda") * torch.tensor([3.0, 2.0, 0.01], device="cuda")
+    planes = torch.rand(D, Hs, Ws, device="cuda") * 3 + 0.5
+    ref = ops.cost_volume_var(f16.float(), [0, 2, 3], proj, planes, channels_last=True)
+    got = ops.cost_volume_var(f16, [0, 2, 3], proj, planes, channels_last=True)
+    close(got, ref, "fp16 feature maps vs the same values in fp32", rtol=1e-6)
+    shared = torch.linspace(0.5, 4.0, D, device="cuda")
+    f32c = torch.randn(N, 32, 20, 28, device="cuda").contiguous(memory_format=torch.channels_last).half()
+    trip = [[0, 1, 2], [1, 2, 3]]
+    o1 = torch.empty((2, D, 10, 14, 32), device="cuda").permute(0, 4, 1, 2, 3)
+    o2 = torch.empty_like(o1)
+    ops.cost_volume_var_shared_multi(f32c.float(), trip, proj, shared, 10, 14, out=o1)
+    ops.cost_volume_var_shared_multi(f32c, trip, proj, shared, 10, 14, out=o2)
+    close(o2, o1, "multi-chain kernel, fp16 feature maps", rtol=1e-6)
