@@ -150,8 +150,10 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
       for (int nt = 0; nt < NT; ++nt) {
         const int c = nt * 8 + 2 * t;
         if (c + 1 < p.Cout + 1 && c < p.Cout) {                         // Cout is even (8 or 16): whole pairs
-          if (gx0 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * p.Cout + c) = make_float2(acc[oy][nt][0], acc[oy][nt][1]);
-          if (gx1 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * p.Cout + c) = make_float2(acc[oy][nt][2], acc[oy][nt][3]);
+          if (p.out) {
+            if (gx0 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * p.Cout + c) = make_float2(acc[oy][nt][0], acc[oy][nt][1]);
+            if (gx1 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * p.Cout + c) = make_float2(acc[oy][nt][2], acc[oy][nt][3]);
+          }
           if (p.out16) {
             __half* o16 = reinterpret_cast<__half*>(p.out16) + (int64_t)n * p.H * p.W * p.Cout;
             if (gx0 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx0) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][0], acc[oy][nt][1]);
@@ -188,8 +190,9 @@ static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
 
 extern "C" BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream) {
   using namespace bmv;
-  BMV_REQUIRE(p && p->prev && p->lateral_in && p->lat_weight && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT,
+  BMV_REQUIRE(p && p->prev && p->lateral_in && p->lat_weight && p->wfrag && (p->out || p->out16), BMV_ERR_INVALID_ARGUMENT,
               "bmv_fpn_topdown_smooth: null pointer");
+  BMV_REQUIRE(((uintptr_t)p->out16 & 3) == 0, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown_smooth: out16 must be 4-byte aligned");
   BMV_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 2 && p->W >= 2 && p->H % 2 == 0 && p->W % 2 == 0, BMV_ERR_INVALID_ARGUMENT,
               "bmv_fpn_topdown_smooth: H, W must be even and >= 2");
   BMV_REQUIRE(((uintptr_t)p->prev & 15) == 0 && ((uintptr_t)p->lateral_in & 15) == 0 && ((uintptr_t)p->out & 7) == 0 &&

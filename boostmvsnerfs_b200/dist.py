@@ -80,7 +80,9 @@ class ShardedFrameRenderer:
         """FeatureNet on the listed views -> dict level -> (len(views), C, h, w)."""
         if not views:
             return None
-        return self.net.forward_feat(inps[views])
+        feats = self.net.forward_feat(inps[views])
+        # the exchange buffers are fp32: widen maps the single-GPU plan keeps in fp16
+        return {k: (v.float() if torch.is_tensor(v) and v.dtype == torch.float16 else v) for k, v in feats.items()}
 
     def feature_shapes(self, inps):
         H, W = inps.shape[-2:]

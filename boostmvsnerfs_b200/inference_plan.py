@@ -205,8 +205,9 @@ class FusedTopDownFPN(nn.Module):
     # step AND its smoothing 3x3 convolution run as one launch (csrc/fpn_fused.cu): the 32-channel
     # full-resolution tensor never reaches HBM.
     fused_smooth = True
-    # also write an fp16 copy of the half-resolution features (for fp16 taps in the level-1 cost volumes).  Measured on
-    # B200: K1 level 1 288 -> 262 us, but the extra stores cost this kernel 26 us — no net gain, off by default.
+    # emit the half-resolution features (read only by the level-1 cost volumes) in fp16 instead of fp32: 8-byte taps in
+    # K1 (288 -> 263 us on B200), but this kernel's epilogue then stores 4 bytes per lane (half sectors) and gets 22 us
+    # slower (an additional copy next to the fp32 maps: +26 us) — net zero on the frame, so it is off by default.
     emit_half_features = False
 
     def __init__(self, fpn):
@@ -227,7 +228,6 @@ class FusedTopDownFPN(nn.Module):
         f = self.fpn
         fused = self.fused_smooth and torch.backends.cudnn.allow_tf32
         self.rgb_nhwc4 = None
-        self.feat1_half = None
         if fused and isinstance(f.conv0[0].bn, nn.Identity):
             a, b = f.conv0[0].conv, f.conv0[1].conv      # the stem reads x with any strides: no layout copy
             want_s2d = isinstance(f.conv1[0], S2DConv5x5) and x.shape[-1] % 2 == 0 and x.shape[-2] % 2 == 0
@@ -242,8 +242,7 @@ class FusedTopDownFPN(nn.Module):
         if fused:
             w1, w0, _ = self._smooth_weights(x.device)
             if self.emit_half_features:
-                half, feat1, self.feat1_half = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16,
-                                                                      True, want_half=True)
+                half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True, want_half='only')
             else:
                 half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
             _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)

@@ -49,8 +49,8 @@ class EnerfNetwork(nn.Module):
         self.fold_bn = True                    # eval-mode BN folded into the convolutions
         self.channels_last = True              # NHWC / NDHWC activations, volumes emitted channels-last
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
-        self.half_feature_taps = False         # level >= 1: K1 reads an fp16 copy of the feature maps (TF32-class path only;
-                                               # measured: -27 us in K1, +26 us in the FPN kernel that writes the copy)
+        self.half_feature_taps = False         # TF32-class path: the fused FPN step emits the level-1 maps in fp16 (8-byte taps in
+                                               # K1: -25 us there, +22 us in the FPN kernel's half-sector stores: off by default)
         self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
@@ -113,8 +113,6 @@ class EnerfNetwork(nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         quarter, half, full = plan(x)
         feats = {'level_0': quarter, 'level_1': half, 'level_2': full}
-        if fused_plan and getattr(plan, 'feat1_half', None) is not None:
-            feats['level_1_half'] = plan.feat1_half          # fp16 copy for the level-1 cost volumes (TF32-class path)
         if fused_plan and plan.rgb_nhwc4 is not None:
             feats['rgb_nhwc4'] = plan.rgb_nhwc4             # by-product of the stem kernel (see _render_level)
         return feats
@@ -276,12 +274,8 @@ class EnerfNetwork(nn.Module):
                                 ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
                 else:                                      # all K chains' hypotheses in one launch
                     planes, nf = ops.depth_planes_next_batched(depth, std, nf, D, h, w, rc.depth_inv[i])
-                    # fp16 feature maps (written by the fused FPN step next to the fp32 ones) where the volume itself
-                    # is fp16, i.e. on the TF32-class path: half the L1 wavefronts per bilinear tap (288 -> 236 us)
-                    fk = feats.get(f'level_{i}_half') if (vdt == torch.float16 and self.half_feature_taps) else None
-                    fk = f if fk is None else fk
-                    for k in range(K):
-                        ops.cost_volume_var(fk, triples[k], projs[i], planes[k], out=vols[k])
+                    for k in range(K):                     # (f may be fp16: half_feature_taps)
+                        ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k])
             with self._stage(f'cost_reg_{i}'):
                 feat_vol, logits = self._kept(f'cost_reg_{i}')(vols)
                 del vols
@@ -308,6 +302,8 @@ class EnerfNetwork(nn.Module):
         rs = rc.render_scale[i]
         H, W = int(Hh * rs), int(Ww * rs)
         im_feat = feats[f'level_{rc.render_im_feat_level[i]}']
+        if im_feat.dtype == torch.float16:           # maps the FPN plan keeps in fp16 for the cost volumes (half_feature_taps)
+            im_feat = im_feat.float()
         up = rs / rc.im_ibr_scale[i]
         if up != 1.:   # never taken by the shipped configs (reference boost_enerf/network.py:128-131)
             im_feat = torch.nn.functional.interpolate(

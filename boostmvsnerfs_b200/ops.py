@@ -808,7 +808,8 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     """mid = up2x(prev) + conv1x1(lateral_in) + lat_bias; out = conv3x3(mid) + smooth_bias in ONE launch
     (reference lib/networks/enerf/feature_net.py:24-47; the 3x3 runs on tensor cores with fp16 operands).
     Returns (mid or None, out); tensors channels_last, smooth_wfrag from mlp_pack.pack_conv2d_k3_c32.
-    want_half: also write an fp16 copy of out (returned as a third value) for the cost-volume kernel's fp16 taps."""
+    want_half: True = also write an fp16 copy of out (returned as a third value) for the cost-volume kernel's fp16
+    taps; 'only' = write out in fp16 ONLY (returned in place of out)."""
     _f32(prev, "prev"); _f32(lateral_in, "lateral_in")
     N, Cin, H, W = lateral_in.shape
     if not (prev.is_contiguous(memory_format=torch.channels_last) and lateral_in.is_contiguous(memory_format=torch.channels_last)):
@@ -819,7 +820,7 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     w = _cf32(lat_weight.reshape(32, Cin), "lat_weight")
     lb = _cf32(lat_bias, "lat_bias") if lat_bias is not None else None
     sb = _cf32(smooth_bias, "smooth_bias") if smooth_bias is not None else None
-    out = torch.empty((N, cout, H, W), device=prev.device, memory_format=torch.channels_last)
+    out = None if want_half == 'only' else torch.empty((N, cout, H, W), device=prev.device, memory_format=torch.channels_last)
     mid = torch.empty((N, 32, H, W), device=prev.device, memory_format=torch.channels_last) if write_mid else None
     p = _lib.FpnFusedParams()
     p.prev, p.lateral_in, p.lat_weight = prev.data_ptr(), lateral_in.data_ptr(), w.data_ptr()
@@ -828,10 +829,12 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     p.bias = sb.data_ptr() if sb is not None else 0
     p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, Cin, cout
     p.mid = mid.data_ptr() if mid is not None else 0
-    p.out = out.data_ptr()
+    p.out = out.data_ptr() if out is not None else 0
     out16 = torch.empty((N, cout, H, W), device=prev.device, dtype=torch.float16, memory_format=torch.channels_last) if want_half else None
     p.out16 = out16.data_ptr() if want_half else 0
     _lib.call("bmv_fpn_topdown_smooth", p, _stream())
+    if want_half == 'only':
+        return mid, out16
     return (mid, out, out16) if want_half else (mid, out)
 
 

@@ -435,8 +435,8 @@ typedef struct bmv_fpn_fused_params {
   const uint32_t* wfrag; const float* bias;
   int32_t N, H, W, Cin, Cout;
   float* mid;                   /* (N,H,W,32) or NULL */
-  float* out;                   /* (N,H,W,Cout) */
-  void* out16;                  /* optional fp16 copy of out, (N,H,W,Cout) (for the cost-volume kernel's fp16 tap loads), or NULL */
+  float* out;                   /* (N,H,W,Cout), or NULL when only out16 is wanted */
+  void* out16;                  /* optional fp16 version of out, (N,H,W,Cout) (for the cost-volume kernel's fp16 tap loads), or NULL */
 } bmv_fpn_fused_params;
 BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream);
 BMV_API int bmv_fpn_topdown_smooth_weight_words(int Cout);

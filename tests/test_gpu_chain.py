@@ -242,3 +242,17 @@ def test_graph_read_back_pipelines_results(strict_fp32):
         for k in keys:
             _report(hosts[i][k], want[i][k].cpu().numpy(), f"read-back frame {i} {k}", 1e-3)
     assert (hosts[0]["rgb_level1"] - hosts[1]["rgb_level1"]).abs().max().item() > 1e-2
+
+
+def test_half_feature_taps_option_matches_default():
+    """Network.half_feature_taps (the fused FPN step emits the level-1 maps in fp16, K1 reads them with 8-byte taps) is a
+    TF32-class variant of the default path: same frame within 1e-2."""
+    g = load_golden("enerf_chain_eval.npz")
+    net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
+    ref = net(dict(batch))
+    net.half_feature_taps = True
+    net.invalidate_plans() if hasattr(net, "invalidate_plans") else None
+    got = net(dict(batch))
+    net.half_feature_taps = False
+    for k in ("rgb_level1", "depth_level1"):
+        _report(got[k], ref[k].detach().cpu().numpy(), f"half feature taps {k}", 1e-2)
