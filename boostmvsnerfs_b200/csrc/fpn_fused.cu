@@ -25,7 +25,9 @@ constexpr int kFfTileBytes = kFfHY * kFfRowB;
 
 __device__ __forceinline__ int ff_swz(int v) { return (v >> 1) & 3; }
 
-template <int CIN, int NT, bool BREG>
+// OUT16: the instantiation that can write the fp16 version of the output (p.out16; p.out optional).  It is a template
+// switch, not a run-time test: the extra epilogue code cost the plain fp32 instantiation 16 us (321 -> 337 us, B200).
+template <int CIN, int NT, bool BREG, bool OUT16>
 __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smooth_kernel(bmv_fpn_fused_params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* tile = smem;
@@ -150,11 +152,11 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
       for (int nt = 0; nt < NT; ++nt) {
         const int c = nt * 8 + 2 * t;
         if (c + 1 < p.Cout + 1 && c < p.Cout) {                         // Cout is even (8 or 16): whole pairs
-          if (p.out) {
+          if (!OUT16 || p.out) {
             if (gx0 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * p.Cout + c) = make_float2(acc[oy][nt][0], acc[oy][nt][1]);
             if (gx1 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * p.Cout + c) = make_float2(acc[oy][nt][2], acc[oy][nt][3]);
           }
-          if (p.out16) {
+          if (OUT16 && p.out16) {
             __half* o16 = reinterpret_cast<__half*>(p.out16) + (int64_t)n * p.H * p.W * p.Cout;
             if (gx0 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx0) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][0], acc[oy][nt][1]);
             if (gx1 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx1) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][2], acc[oy][nt][3]);
@@ -165,16 +167,16 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
   }
 }
 
-template <int CIN, int NT, bool BREG>
-static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
+template <int CIN, int NT, bool BREG, bool OUT16>
+static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
   const size_t smem = (size_t)kFfTileBytes + (size_t)3 * 6 * NT * 32 * 8 + (size_t)(32 * CIN + 32) * 4;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       // 68 % of the 228 KB: room for the resident CTAs' tiles, the rest stays L1 for the prev / lateral taps
       // (measured on B200: 329 us with the maximum carve-out, 315 us with 64-72 %, 404 us at 50 %)
-      e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG>, cudaFuncAttributePreferredSharedMemoryCarveout, 68);
+      e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16>, cudaFuncAttributePreferredSharedMemoryCarveout, 68);
     if (e != cudaSuccess) {
       set_error("bmv_fpn_topdown_smooth: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -182,8 +184,13 @@ static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
     configured = true;
   }
   const dim3 grid((unsigned)(((p.W + kFfTX - 1) / kFfTX) * ((p.H + kFfTY - 1) / kFfTY)), (unsigned)p.N);
-  fpn_topdown_smooth_kernel<CIN, NT, BREG><<<grid, kFfThreads, smem, st>>>(p);
+  fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16><<<grid, kFfThreads, smem, st>>>(p);
   return check_launch("bmv_fpn_topdown_smooth");
+}
+
+template <int CIN, int NT, bool BREG>
+static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
+  return p.out16 ? launch_ff_t<CIN, NT, BREG, true>(p, st) : launch_ff_t<CIN, NT, BREG, false>(p, st);
 }
 
 }  // namespace bmv
