@@ -8,20 +8,22 @@
 // channels (Cout padded), K = 16 input values per instruction, and the A operand of tap (dz,dy,dx) is the
 // staged halo tile itself, addressed by a shared-memory descriptor whose start is shifted by the tap:
 //     Cin  8: voxels are 16 bytes = one K-chunk; rows (voxels) 16 B apart = the SWIZZLE_NONE core-matrix pitch,
-//             the second K-chunk is the NEXT voxel (LBO = 16): taps dx, dx+1 in one MMA, 2 MMAs per (dz,dy)
-//             (the partner of dx = 2 has zero weights), 18 MMAs per output row;
+//             the second K-chunk is the NEXT voxel (LBO = 16): taps dx, dx+1 in one MMA, 2 K-steps per (dz,dy)
+//             (the partner of dx = 2 has zero weights);
 //     Cin 16: voxels are 32 bytes = the SWIZZLE_32B row the TMA unit writes (absolute-address XOR, the same on
-//             the tensor-core side), one MMA per tap, 27 per output row.
+//             the tensor-core side), one K-step per tap.
 // An output row's accumulator is 16 TMEM columns (lane = voxel), the rows of an output plane are adjacent column
-// groups.  With N = 16 an MMA is bound by reading its 4 KB A operand from shared memory (128 B/clk: 32 clk against
-// 8 clk of math), so ONE MMA serves every output row an input row contributes to: input row hy of plane z' feeds
+// groups.  With N = 16 an MMA is bound by reading its 4 KB A operand from shared memory, not by its 8 clk of math
+// (ncu on the final kernel: tensor pipe 85 % busy, tensor-core shared-memory wavefronts 71 % of the L1 data pipe),
+// so ONE MMA serves every output row an input row contributes to: input row hy of plane z' feeds
 // output rows oy = hy-2 .. hy (dy = hy - oy) of plane z'-dz, whose accumulators are adjacent -> N = 16..48 with
 // B = a row range of the stacked weights [W(dz,2); W(dz,1); W(dz,0)].  That is 3 (TH+2) KS / TH MMAs per output
 // row instead of 9 KS.  Accumulators are zeroed by one MMA against a zero B operand (an MMA spans rows that were
 // and were not written before, so the accumulate flag cannot do it).  The epilogue thread of voxel x reads its
 // 16 columns with one tcgen05.ld, adds the bias, applies ReLU and writes the voxel's channels as 16/32-byte stores.
-// Two threads (different warps) issue half of the output planes each; a commit per plane lets the epilogue of
-// plane z run under the MMAs of plane z+1, and two CTAs per SM overlap one tile's TMA load with the other's MMAs.
+// The kernel is persistent and warp-specialised (TMA producer warp, one MMA-issuer warp per output plane, eight
+// epilogue warps; NSLOT staged tiles + accumulator sets in flight, mbarriers / tcgen05.commit between the roles) — see
+// the comment above the kernel.  Version history with the measurements that drove it: profiles/round1l_tcgen05.md.
 #include <cuda.h>
 
 #include <cstring>
@@ -34,9 +36,9 @@ namespace bmv {
 
 template <int CIN> struct UConv;
 template <> struct UConv<8> {
-  // TMA moves one box ROW per ~2.5 clk whatever its size (measured: 16-byte rows made the copy the bottleneck), so the
-  // (C, W) dimensions are merged into rows of 128 voxels = 256 8-byte elements (the box limit): 36 rows per tile instead
-  // of 4716.  An MMA still spans 128 voxels, of which the last two read past the row: 126 valid outputs per x tile.
+  // The (C, W) dimensions are merged into TMA box rows of 128 voxels = 256 8-byte elements (the box limit): 36 rows per
+  // tile instead of 4716 16-byte ones (measured: 100 -> 96 us — the copy was not the bottleneck, but the rows are also
+  // a power of two).  An MMA still spans 128 voxels, of which the last two read past the row: 126 valid outputs per x tile.
   static constexpr int VS = 16, KS = 2, TH = 4, TD = 4, ROWV = 128, TWV = 126, NSLOT = 2;
   static constexpr uint32_t LAYOUT = 0, A_LBO = 16, A_SBO = 128;
   __device__ static __forceinline__ uint32_t step_off(int j) { return (uint32_t)j * 32u; }      // voxels 2j, 2j+1
@@ -57,7 +59,7 @@ template <int CIN> struct UTile {
   static constexpr int ROWS = TD * TH, NSLOT = C::NSLOT;      // NSLOT tiles in flight (staged tile + accumulators each)
   static constexpr uint32_t TMEM_COLS = ROWS * 16 <= 32 ? 32 : (ROWS * 16 <= 64 ? 64 : (ROWS * 16 <= 128 ? 128 : 256));
   static constexpr int TILE_PAD = 64;                                          // zeros behind the last row (read by the MMA rows past it)
-  static constexpr int TILE_STRIDE = (TILE_BYTES + TILE_PAD + 1023) / 1024 * 1024;   // two staged tiles, each 1024-byte aligned
+  static constexpr int TILE_STRIDE = (TILE_BYTES + TILE_PAD + 1023) / 1024 * 1024;   // staged tiles, each 1024-byte aligned
   static constexpr size_t SMEM = (size_t)NSLOT * TILE_STRIDE + W_BYTES + Z_BYTES + 1024;
 };
 

@@ -5,12 +5,19 @@
 // with 221 M warp instructions per launch — a warp-level MMA needs its A fragments rebuilt in registers for
 // every layer and 3 x 112 mma.sync per 16 samples.  Here one thread owns one SAMPLE ROW of a 128-sample tile:
 // it gathers the sample, writes the row of each layer's A operand (fp16 hi + lo, 22 significant bits) into
-// shared memory in the UMMA canonical K-major layout, ONE thread of the tile's 4 warps issues the layer's
-// MMAs (M = 128, N = 16..64, K = 16 per instruction, three per product: lo*hi + hi*lo + hi*hi, fp32
-// accumulate in TMEM), and the row comes back with tcgen05.ld (lane = row) for bias / ReLU / soft-max.
-// Two tiles (2 x 4 warps) share a CTA and ping-pong: while one waits for its MMAs the other runs its
-// CUDA-core phase.  The shared [hid | pooled | vox] part of color.0 and the [var | mean] part of global_fc
-// are computed once per sample and added to the per-view parts in the epilogue.
+// shared memory in the UMMA canonical K-major layout, the tile's leader warp issues the layer's MMAs from
+// warp-uniform code through one elected lane (M = 128, N = 16..64, K = 16 per instruction, three per product:
+// lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM), and the row comes back with tcgen05.ld (lane = row) for
+// ReLU / soft-max.  Two tiles (2 x 4 warps) share a CTA and ping-pong: while one waits for its MMAs the other
+// runs its CUDA-core phase; the gather of tile i+1 is issued in four parts behind the MMA phases of tile i.
+// global_fc and color.0 accumulate their shared and per-view K ranges per view inside the tensor core
+// (accumulators G_v / C_v), the biases of global_fc, lr0 and color.0 ride in the MMAs through a constant-1 column.
+//
+// STATUS (measured, profiles/round1l_tcgen05.md): parity-green but 20 % SLOWER than render_mma.cu (510 vs 422 us
+// per launch): the per-sample CUDA-core work (~5.9 k instructions: gather, splits, activations) bounds both
+// kernels, the operand tiles (640 B of shared memory per sample) allow only two tiles = 8 warps per SM at 255
+// registers, and every layer has N <= 64 where an SS-mode MMA is bound by its operand reads.  It is an opt-in
+// engine (Network.mlp_engine = 'umma'); the default stays 'mma'.
 //
 // Shared-memory operand layout (SWIZZLE_NONE, K-major; reference for the descriptor fields:
 // cute/arch/mma_sm100_desc.hpp): an operand is a sequence of K-chunks of 8 fp16; chunk c is a slab of
@@ -18,6 +25,7 @@
 // K-chunks of one K=16 instruction LBO bytes apart (A: 4096, the hi and lo slabs of a chunk are adjacent;
 // B: N*16).  A thread writing its row's chunk stores 16 contiguous bytes next to its neighbours' (no bank
 // conflicts).  TMEM: 512 columns, tile w uses columns [256 w, 256 w + 256); accumulator row i = lane i.
+// Packed weights: mlp_pack.pack_nerf_weights_umma (CPU restatement of packing + dataflow: tests/test_umma_pack.py).
 //
 // Accuracy: identical split to render_mma.cu (dropped lo*lo term 2^-22), agrees with the fp32 kernels to
 // ~1e-5 (tests/test_gpu_umma.py); the gather is the same code (gather_sample_regs).
