@@ -190,7 +190,7 @@ def algorithmic_bytes(wl, rc, volume_bytes=4):
 # round1l_ncu_tcgen05.csv).  Traffic
 # below the algorithmic bytes = part of the input / output was served by the 126 MB L2 (producer and consumer adjacent).
 NCU_TRAFFIC_MB = {"render_fused_l1": 124.2, "fpn_topdown_smooth_full": 275.6, "fpn_topdown_smooth_half": 174.6, "fpn_stem": 81.2,
-                  "cost_volume_l0": 24.3, "cost_volume_l1": 46.1, "heads_l1": 159.8, "conv0_l1": 176.0, "conv0_l0": 156.0}
+                  "cost_volume_l1": 46.1, "heads_l1": 159.8, "conv0_l1": 176.0, "conv0_l0": 156.0}
 
 
 def conv_kernel_bytes(wl, rc, volume_bytes=4, heads_entry="bmv_conv3d_k3"):
