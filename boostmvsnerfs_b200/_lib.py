@@ -26,12 +26,17 @@ class CostVolumeParams(C.Structure):
                 ("D", i32), ("h", i32), ("w", i32),
                 ("out", C.c_void_p),
                 ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
-                ("out_bf16", i32), ("exact_coords", i32), ("feat_half", i32), ("reserved0", i32)]
+                ("out_bf16", i32), ("exact_coords", i32), ("feat_half", i32), ("reserved0", i32),
+                ("out_scale", C.c_void_p)]
 
 
 class CostVolumeMultiParams(C.Structure):
     _fields_ = [("b", CostVolumeParams), ("K", i32), ("views_per_chain", i32), ("chain_mask", i32 * MAX_VIEWS),
                 ("out_k_stride", i64)]
+
+
+class VolumeScaleParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("n", i64), ("x_half", i32), ("target", f32), ("scale", C.c_void_p)]
 
 
 class DepthPlanesFirstParams(C.Structure):
@@ -133,7 +138,8 @@ class Conv3dParams(C.Structure):
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("relu", i32),
                 ("out", C.c_void_p), ("o_n_stride", i64), ("o_d_stride", i64), ("o_y_stride", i64), ("o_x_stride", i64),
                 ("out2", C.c_void_p), ("o2_n_stride", i64), ("o2_d_stride", i64), ("o2_y_stride", i64),
-                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32), ("no_tma", i32), ("out_half", i32)]
+                ("o2_x_stride", i64), ("split", i32), ("stride", i32), ("in_half", i32), ("no_tma", i32), ("out_half", i32),
+                ("reserved0", i32), ("in_scale", C.c_void_p)]
 
 
 class ConvT3dParams(C.Structure):
@@ -162,6 +168,7 @@ class FpnStemParams(C.Structure):
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_cost_volume_var_multi": CostVolumeMultiParams,
+    "bmv_volume_scale": VolumeScaleParams,
     "bmv_depth_planes_first": DepthPlanesFirstParams,
     "bmv_depth_planes_next": DepthPlanesNextParams,
     "bmv_depth_regression": DepthRegressionParams,

@@ -25,6 +25,7 @@ extern "C" BMV_API int bmv_sizeof_params(const char* entry) {
   if (!entry) return -1;
   if (!strcmp(entry, "bmv_cost_volume_var")) return (int)sizeof(bmv_cost_volume_params);
   if (!strcmp(entry, "bmv_cost_volume_var_multi")) return (int)sizeof(bmv_cost_volume_multi_params);
+  if (!strcmp(entry, "bmv_volume_scale")) return (int)sizeof(bmv_volume_scale_params);
   if (!strcmp(entry, "bmv_depth_planes_first")) return (int)sizeof(bmv_depth_planes_first_params);
   if (!strcmp(entry, "bmv_depth_planes_next")) return (int)sizeof(bmv_depth_planes_next_params);
   if (!strcmp(entry, "bmv_depth_regression")) return (int)sizeof(bmv_depth_regression_params);

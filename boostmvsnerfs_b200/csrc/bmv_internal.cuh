@@ -2,9 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/bmv.h"
 
@@ -33,6 +36,28 @@ inline int check_launch(const char* what) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// One NVTX range per C-ABI entry (host side: argument checks + enqueue).  With no profiler attached the NVTX v3
+// header-only shim is a load + branch per call; under nsys / ncu --nvtx the frame reads as a list of named libbmv calls.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define BMV_NVTX_RANGE(name) ::bmv::NvtxRange bmv_nvtx_range_(name)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize / carve-out) is a PER-DEVICE attribute: a launcher configures its
+// kernel once per device it is used on (a process-wide flag would leave a second GPU of the same process unconfigured).
+// Thread-safe: concurrent first calls may both configure (idempotent), none skips it.
+struct DeviceOnce {
+  std::atomic<uint64_t> mask[2]{};                     // devices 0..127
+  // the current device if it has not been configured yet (configure, then call done(dev)); -1 otherwise
+  int needed() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return 0;   // let the configure call report it
+    return ((mask[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1u) ? -1 : dev;
+  }
+  void done(int dev) { mask[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ----------------------------------------------------------------------------- device helpers
@@ -58,6 +83,19 @@ __device__ __forceinline__ float dot4_gemm(float a0, float a1, float a2, float a
   acc = __fmaf_rn(a2, b2, acc);
   acc = __fmaf_rn(a3, b3, acc);
   return acc;
+}
+
+// fp32 -> fp16 conversions of every STORED activation / volume element saturate at +-65504 instead of producing inf
+// (one F2FP.SATFINITE instruction; NaN stays NaN): an out-of-range value then costs accuracy, not a NaN-poisoned frame.
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ __half half_sat(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
 }
 
 // ATen grid_sampler unnormalize with align_corners=True: ((g + 1) / 2) * (size - 1).

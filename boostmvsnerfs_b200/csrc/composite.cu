@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(256) composite_warp_kernel(bmv_composite_param
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_composite_blend(const bmv_composite_blend_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_composite_blend");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_composite_blend: null params");
   BMV_REQUIRE(p->K >= 1 && p->K <= BMV_MAX_VOLUMES, BMV_ERR_INVALID_ARGUMENT, "bmv_composite_blend: K=%d out of 1..%d",
@@ -301,6 +302,7 @@ extern "C" BMV_API int bmv_composite_blend(const bmv_composite_blend_params* p, 
 }
 
 extern "C" BMV_API int bmv_composite(const bmv_composite_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_composite");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_composite: null params");
   BMV_REQUIRE(p->S >= 1 && p->R >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_composite: bad S/R");

@@ -218,10 +218,9 @@ conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tm
           for (int k = 0; k < P; ++k) {
             const int hx = hx0 + VPP * k;
             if (hx < T::ROWV) {
-              __half2 lo = __floats2half2_rn(val[rr][k].x, val[rr][k].y), hi = __floats2half2_rn(val[rr][k].z, val[rr][k].w);
               uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              pk.x = pack_half2_sat(val[rr][k].x, val[rr][k].y);
+              pk.y = pack_half2_sat(val[rr][k].z, val[rr][k].w);
               *reinterpret_cast<uint2*>(tile + r * T::ROWB + hx * Cfg::VS + (((c4 >> 1) ^ Cfg::swz(hx)) << 4) + (c4 & 1) * 8) = pk;
             }
           }
@@ -241,12 +240,14 @@ conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tm
 #pragma unroll
     for (int i = 0; i < 9 * KS * NT; ++i) breg[i] = wfrag[i * 32 + lane];
   }
+  // the input may be stored pre-multiplied by a power of two (bmv_volume_scale): start from s*bias, undo with 1/s
+  const float in_sc = p.in_scale ? __ldg(p.in_scale) : 1.f, in_isc = p.in_scale ? __ldg(p.in_scale + 1) : 1.f;
   float bias0[NT], bias1[NT];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int c = nt * 8 + 2 * t;
-    bias0[nt] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
-    bias1[nt] = (p.bias && c + 1 < p.Cout) ? __ldg(p.bias + c + 1) : 0.f;
+    bias0[nt] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) * in_sc : 0.f;
+    bias1[nt] = (p.bias && c + 1 < p.Cout) ? __ldg(p.bias + c + 1) * in_sc : 0.f;
   }
   float* out = p.out + (int64_t)n * p.o_n_stride;
   float* out2 = p.out2 ? p.out2 + (int64_t)n * p.o2_n_stride : nullptr;
@@ -324,14 +325,14 @@ conv3d_k3_mma_kernel(bmv_conv3d_params p, const __grid_constant__ CUtensorMap tm
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int c = nt * 8 + 2 * t;
-          float v0 = acc[od][oy][nt][0], v1 = acc[od][oy][nt][1], v2 = acc[od][oy][nt][2], v3 = acc[od][oy][nt][3];
+          float v0 = acc[od][oy][nt][0] * in_isc, v1 = acc[od][oy][nt][1] * in_isc, v2 = acc[od][oy][nt][2] * in_isc, v3 = acc[od][oy][nt][3] * in_isc;
           if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
           if (p.out_half) {                                             // fp16 storage (launcher: even Cout, no split)
             __half* hrow = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + (int64_t)gd * p.o_d_stride +
                            (int64_t)gy * p.o_y_stride;
             if (c < p.Cout) {
-              if (gx0 < p.W) *reinterpret_cast<__half2*>(hrow + (int64_t)gx0 * p.o_x_stride + c) = __floats2half2_rn(v0, v1);
-              if (gx1 < p.W) *reinterpret_cast<__half2*>(hrow + (int64_t)gx1 * p.o_x_stride + c) = __floats2half2_rn(v2, v3);
+              if (gx0 < p.W) *reinterpret_cast<uint32_t*>(hrow + (int64_t)gx0 * p.o_x_stride + c) = pack_half2_sat(v0, v1);
+              if (gx1 < p.W) *reinterpret_cast<uint32_t*>(hrow + (int64_t)gx1 * p.o_x_stride + c) = pack_half2_sat(v2, v3);
             }
           } else if (vec_ok && nt * 8 + 8 <= split) {                   // whole n-tile lands in `out`: 8-byte stores
             if (gx0 < p.W) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
@@ -493,8 +494,8 @@ conv3d_k3s2_c8_mma_kernel(bmv_conv3d_params p, int Do, int Ho, int Wo, const __g
           if (p.out_half) {
             __half* hrow = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + (int64_t)(d0 + od) * p.o_d_stride +
                            (int64_t)gy * p.o_y_stride;
-            if (gx0 < Wo) *reinterpret_cast<__half2*>(hrow + (int64_t)gx0 * p.o_x_stride + c) = __floats2half2_rn(v0, v1);
-            if (gx1 < Wo) *reinterpret_cast<__half2*>(hrow + (int64_t)gx1 * p.o_x_stride + c) = __floats2half2_rn(v2, v3);
+            if (gx0 < Wo) *reinterpret_cast<uint32_t*>(hrow + (int64_t)gx0 * p.o_x_stride + c) = pack_half2_sat(v0, v1);
+            if (gx1 < Wo) *reinterpret_cast<uint32_t*>(hrow + (int64_t)gx1 * p.o_x_stride + c) = pack_half2_sat(v2, v3);
           } else {
             if (gx0 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx0 * p.o_x_stride + c) = make_float2(v0, v1);
             if (gx1 < Wo) *reinterpret_cast<float2*>(orow + (int64_t)gx1 * p.o_x_stride + c) = make_float2(v2, v3);
@@ -546,8 +547,8 @@ static int launch_conv_s2_t(const bmv_conv3d_params& p, cudaStream_t st, const C
   using T = ConvS2;
   const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4 + 128;
   g_last_conv3d_tma = TMA ? 1 : 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel<TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3d_k3s2_c8_mma_kernel<TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -555,7 +556,7 @@ static int launch_conv_s2_t(const bmv_conv3d_params& p, cudaStream_t st, const C
       set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int Do = (p.D - 1) / 2 + 1, Ho = (p.H - 1) / 2 + 1, Wo = (p.W - 1) / 2 + 1;
   const int64_t blocks = (int64_t)p.N * ((Do + T::TD - 1) / T::TD) * ((Ho + T::TH - 1) / T::TH) * ((Wo + T::TW - 1) / T::TW);
@@ -590,8 +591,8 @@ static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st, const CUte
   using T = ConvTile<CIN, NTILES>;
   const size_t smem = (size_t)T::TILE_BYTES + (size_t)T::W_WORDS * 4 + 128;
   g_last_conv3d_tma = TMA ? 1 : 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -599,7 +600,7 @@ static int launch_conv_t(const bmv_conv3d_params& p, cudaStream_t st, const CUte
       set_error("bmv_conv3d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int64_t blocks = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
   conv3d_k3_mma_kernel<CIN, NTILES, IN_HALF, TMA><<<(unsigned)blocks, kConvThreads, smem, st>>>(p, map);
@@ -619,6 +620,7 @@ static int launch_conv(const bmv_conv3d_params& p, cudaStream_t st) {
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_conv3d_k3");
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: bad size");
@@ -635,6 +637,7 @@ extern "C" BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t st
   cudaStream_t st = (cudaStream_t)stream;
   BMV_REQUIRE(p->stride == 0 || p->stride == 1 || p->stride == 2, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3: stride must be 1 or 2");
   if (p->stride == 2) {
+    BMV_REQUIRE(!p->in_scale, BMV_ERR_UNSUPPORTED_SHAPE, "bmv_conv3d_k3: in_scale is implemented by the stride-1 kernel only");
     BMV_REQUIRE(p->Cin == 8 && p->Cout % 2 == 0 && p->Cout <= 16 && !p->out2, BMV_ERR_UNSUPPORTED_SHAPE,
                 "bmv_conv3d_k3: stride 2 is instantiated for Cin=8, even Cout<=16, single output (got Cin=%d, Cout=%d)", p->Cin, p->Cout);
     BMV_REQUIRE(p->o_x_stride % 2 == 0 && p->o_y_stride % 2 == 0 && p->o_d_stride % 2 == 0 && p->o_n_stride % 2 == 0 &&

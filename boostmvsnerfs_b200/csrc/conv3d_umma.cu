@@ -137,10 +137,10 @@ __device__ __forceinline__ void uconv_epilogue(const bmv_conv3d_params& p, uint6
         } else if (MODE == 1) {
           __half* o = reinterpret_cast<__half*>(p.out) + ro;
           uint4 h;
-          { __half2 t2 = __floats2half2_rn(v[0], v[1]); h.x = *reinterpret_cast<uint32_t*>(&t2); }
-          { __half2 t2 = __floats2half2_rn(v[2], v[3]); h.y = *reinterpret_cast<uint32_t*>(&t2); }
-          { __half2 t2 = __floats2half2_rn(v[4], v[5]); h.z = *reinterpret_cast<uint32_t*>(&t2); }
-          { __half2 t2 = __floats2half2_rn(v[6], v[7]); h.w = *reinterpret_cast<uint32_t*>(&t2); }
+          h.x = pack_half2_sat(v[0], v[1]);
+          h.y = pack_half2_sat(v[2], v[3]);
+          h.z = pack_half2_sat(v[4], v[5]);
+          h.w = pack_half2_sat(v[6], v[7]);
           *reinterpret_cast<uint4*>(o) = h;
         } else if (MODE == 2) {
           float* o = p.out + ro;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void uconv_epilogue(const bmv_conv3d_params& p, uint6
           __half* o = reinterpret_cast<__half*>(p.out) + ro;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            if (2 * c < p.Cout) *reinterpret_cast<__half2*>(o + 2 * c) = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+            if (2 * c < p.Cout) *reinterpret_cast<uint32_t*>(o + 2 * c) = pack_half2_sat(v[2 * c], v[2 * c + 1]);
         } else {
           float* o = p.out + ro;
 #pragma unroll
@@ -344,8 +344,8 @@ static int launch_uconv(const bmv_conv3d_params& p, cudaStream_t st) {
             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   BMV_REQUIRE(r == CUDA_SUCCESS, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(conv3d_k3_umma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3d_k3_umma_kernel<CIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -353,7 +353,7 @@ static int launch_uconv(const bmv_conv3d_params& p, cudaStream_t st) {
       set_error("bmv_conv3d_k3_umma: cannot reserve %zu B shared memory: %s", (size_t)T::SMEM, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int64_t tiles = (int64_t)p.N * ((p.D + T::TD - 1) / T::TD) * ((p.H + T::TH - 1) / T::TH) * ((p.W + T::TW - 1) / T::TW);
   BMV_REQUIRE(tiles < (1ll << 31), BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: too many tiles");
@@ -365,7 +365,9 @@ static int launch_uconv(const bmv_conv3d_params& p, cudaStream_t st) {
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_conv3d_k3_umma(const bmv_conv3d_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_conv3d_k3_umma");
   using namespace bmv;
+  BMV_REQUIRE(!p || !p->in_scale, BMV_ERR_UNSUPPORTED_SHAPE, "bmv_conv3d_k3_umma: in_scale is not implemented here");
   BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_conv3d_k3_umma: bad size");
   BMV_REQUIRE(p->in_half && (p->stride == 0 || p->stride == 1) && p->x_x_stride == p->Cin, BMV_ERR_UNSUPPORTED_SHAPE,

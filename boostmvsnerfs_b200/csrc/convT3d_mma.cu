@@ -203,8 +203,7 @@ __global__ void __launch_bounds__(kCtThreads, (CIN == 16 ? 4 : 2)) convT3d_k3s2_
             }
           }
           if (p.out_half) {
-            __half2 hv = __floats2half2_rn(v.x, v.y);
-            *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + rowo + (int64_t)ox * p.o_x_stride + c) = hv;
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(p.out) + (int64_t)n * p.o_n_stride + rowo + (int64_t)ox * p.o_x_stride + c) = pack_half2_sat(v.x, v.y);
           } else {
             *reinterpret_cast<float2*>(out + rowo + (int64_t)ox * p.o_x_stride + c) = v;
           }
@@ -218,8 +217,8 @@ template <int CIN, int COUT>
 static int launch_convT(const bmv_convT3d_params& p, cudaStream_t st) {
   using C = CtCfg<CIN, COUT>;
   const size_t smem = (size_t)C::TILE_BYTES + (size_t)C::W_WORDS * 4;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(convT3d_k3s2_mma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(convT3d_k3s2_mma_kernel<CIN, COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -227,7 +226,7 @@ static int launch_convT(const bmv_convT3d_params& p, cudaStream_t st) {
       set_error("bmv_convT3d_k3s2: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int64_t blocks = (int64_t)p.N * ((p.D + C::TD - 1) / C::TD) * ((p.H + C::TH - 1) / C::TH) * ((p.W + C::TW - 1) / C::TW);
   convT3d_k3s2_mma_kernel<CIN, COUT><<<(unsigned)blocks, kCtThreads, smem, st>>>(p);
@@ -237,6 +236,7 @@ static int launch_convT(const bmv_convT3d_params& p, cudaStream_t st) {
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_convT3d_k3s2(const bmv_convT3d_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_convT3d_k3s2");
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->wfrag && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->D >= 1 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_convT3d_k3s2: bad size");

@@ -4,6 +4,8 @@
 
 #include <cstdint>
 
+#include "bmv_internal.cuh"
+
 namespace bmv {
 
 // four 8x8 b16 matrices; lane l supplies the row address of matrix l/8, row l%8
@@ -17,10 +19,9 @@ __device__ __forceinline__ void hmma16816(float (&c)[4], const uint32_t (&a)[4],
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint2 pack_half4(const float4& v) {
-  __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
   uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&lo);
-  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  pk.x = pack_half2_sat(v.x, v.y);
+  pk.y = pack_half2_sat(v.z, v.w);
   return pk;
 }
 

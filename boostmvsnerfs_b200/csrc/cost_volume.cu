@@ -50,7 +50,7 @@ __device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 template <>
-__device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = half_sat(v); }
 
 // two fp32 values -> one 32-bit word of 16-bit outputs
 template <typename OutT>
@@ -62,8 +62,7 @@ __device__ __forceinline__ uint32_t pack_out2<__nv_bfloat16>(float a, float b) {
 }
 template <>
 __device__ __forceinline__ uint32_t pack_out2<__half>(float a, float b) {
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return pack_half2_sat(a, b);
 }
 template <>
 __device__ __forceinline__ uint32_t pack_out2<float>(float a, float b) { return 0u; }   // never used (4-byte branch)
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_kernel(bmv_cost_volume_pa
     }
     float mean = div_rn(sum, (float)S);
     float var = sub_rn(div_rn(sq, (float)S), mul_rn(mean, mean));
-    store_out<OutT>(out + (int64_t)c * p.out_c_stride, var);
+    store_out<OutT>(out + (int64_t)c * p.out_c_stride, p.out_scale ? var * __ldg(p.out_scale) : var);
   }
 }
 
@@ -160,6 +159,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume
   for (int q = 0; q < CPT; ++q) {
     const float mean = div_rn(sum[q], (float)S);
     var[q] = sub_rn(div_rn(sq[q], (float)S), mul_rn(mean, mean));
+    if (p.out_scale) var[q] *= __ldg(p.out_scale);
   }
   OutT* out = reinterpret_cast<OutT*>(p.out) + (int64_t)d * p.out_d_stride + (int64_t)y * p.out_y_stride +
               (int64_t)x * p.out_x_stride + c0;
@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volum
     for (int q = 0; q < CPT; ++q) {
       const float mean = sum[q] * invS;
       var[q] = fmaf(-mean, mean, sq[q] * invS);
+      if (p.out_scale) var[q] *= __ldg(p.out_scale);
     }
     OutT* out = outp + (int64_t)d * p.out_d_stride;
     if constexpr (sizeof(OutT) == 4) {
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
   for (int s = 0; s < S; ++s) base[s] = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)p.view[s] * p.feat_view_stride + c0;
   OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   constexpr float invS = 1.f / S;
+  const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
   for (int d0 = d_begin; d0 < d_end; d0 += PB) {
     FastTap t;
     {
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
         { const float m = sum.y * invS; var.y = fmaf(-m, m, sq.y * invS); }
         { const float m = sum.z * invS; var.z = fmaf(-m, m, sq.z * invS); }
         { const float m = sum.w * invS; var.w = fmaf(-m, m, sq.w * invS); }
+        var.x *= osc; var.y *= osc; var.z *= osc; var.w *= osc;
         OutT* out = outp + (int64_t)d * p.out_d_stride;
         if constexpr (sizeof(OutT) == 4) {
           *reinterpret_cast<float4*>(out) = var;
@@ -428,6 +431,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_vol
   const bool active = x < p.w;
   OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   const float invS = 1.f / (float)mp.views_per_chain;
+  const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
   for (int d = d_begin; d < d_end; ++d) {
     const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
     const FastTap t = fast_taps(ax, ay, az, tP, idep, sx, sy, p.Hs, p.Ws, ys, xs);
@@ -467,6 +471,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_vol
           { const float m = sum[k].y * invS; var.y = fmaf(-m, m, sq[k].y * invS); }
           { const float m = sum[k].z * invS; var.z = fmaf(-m, m, sq[k].z * invS); }
           { const float m = sum[k].w * invS; var.w = fmaf(-m, m, sq[k].w * invS); }
+          var.x *= osc; var.y *= osc; var.z *= osc; var.w *= osc;
           OutT* out = outp + (int64_t)k * mp.out_k_stride + (int64_t)d * p.out_d_stride;
           if constexpr (sizeof(OutT) == 4) {
             *reinterpret_cast<float4*>(out) = var;
@@ -494,6 +499,56 @@ static int launch_cost_volume_multi(const bmv_cost_volume_multi_params& mp, cuda
   } else if (CG == 8) cost_volume_var_multi_kernel<8, OutT><<<grid, threads, 0, st>>>(mp, DG);
   else cost_volume_var_multi_kernel<4, OutT><<<grid, threads, 0, st>>>(mp, DG);
   return check_launch("bmv_cost_volume_var_multi");
+}
+
+// ---------------------------------------------------------------- range scale of an fp16 volume (bmv_volume_scale)
+template <typename T>
+__global__ void __launch_bounds__(256) volume_scale_kernel(bmv_volume_scale_params p) {
+  constexpr int VEC = 16 / sizeof(T);
+  float m = 0.f;
+  const int64_t nvec = p.n / VEC;
+  const uint4* src = reinterpret_cast<const uint4*>(p.x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(src + i);
+    if constexpr (sizeof(T) == 4) {
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(__uint_as_float(q.x)), fabsf(__uint_as_float(q.y))),
+                         fmaxf(fabsf(__uint_as_float(q.z)), fabsf(__uint_as_float(q.w)))));
+    } else {
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        m = fmaxf(m, fmaxf(fabsf(f.x), fabsf(f.y)));
+      }
+    }
+  }
+  m = fminf(m, 3.0e38f);                                 // inf -> finite; NaNs were dropped by fmaxf
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
+    unsigned* scratch = reinterpret_cast<unsigned*>(p.scale) + 2;
+    atomicMax(scratch, __float_as_uint(m));              // non-negative floats order like their bit patterns
+    __threadfence();
+    if (atomicAdd(scratch + 1, 1u) == gridDim.x - 1) {   // last block: every maximum has been merged
+      const float mx = __uint_as_float(atomicMax(scratch, 0u));
+      int k = 0;
+      if (mx > 0.f) {
+        int e;
+        frexpf(mx, &e);                                  // mx = f * 2^e, f in [0.5, 1)  ->  mx^2 < 2^(2e)
+        int te;
+        frexpf(p.target, &te);                           // target = g * 2^te, g in [0.5, 1) -> 2^(te-1) <= target
+        k = min(max(te - 1 - 2 * e, -40), 40);
+      }
+      p.scale[0] = ldexpf(1.f, k);
+      p.scale[1] = ldexpf(1.f, -k);
+      scratch[0] = 0u;
+      scratch[1] = 0u;
+    }
+  }
 }
 
 // ---------------------------------------------------------------- depth hypotheses, level 0
@@ -626,6 +681,7 @@ static int launch_cost_volume(const bmv_cost_volume_params& p, cudaStream_t st) 
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_cost_volume_var");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var: null params");
   BMV_REQUIRE(p->feat && p->proj && p->planes && p->out, BMV_ERR_INVALID_ARGUMENT,
@@ -646,6 +702,7 @@ extern "C" BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_
 }
 
 extern "C" BMV_API int bmv_cost_volume_var_multi(const bmv_cost_volume_multi_params* mp, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_cost_volume_var_multi");
   using namespace bmv;
   BMV_REQUIRE(mp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var_multi: null params");
   const bmv_cost_volume_params* p = &mp->b;
@@ -673,7 +730,23 @@ extern "C" BMV_API int bmv_cost_volume_var_multi(const bmv_cost_volume_multi_par
   return launch_cost_volume_multi<float>(*mp, st);
 }
 
+extern "C" BMV_API int bmv_volume_scale(const bmv_volume_scale_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_volume_scale");
+  using namespace bmv;
+  BMV_REQUIRE(p && p->x && p->scale, BMV_ERR_INVALID_ARGUMENT, "bmv_volume_scale: null pointer");
+  const int vec = p->x_half ? 8 : 4;
+  BMV_REQUIRE(p->n >= vec && p->n % vec == 0 && ((uintptr_t)p->x & 15) == 0, BMV_ERR_INVALID_ARGUMENT,
+              "bmv_volume_scale: n must be a positive multiple of %d and x 16-byte aligned", vec);
+  BMV_REQUIRE(p->target > 0.f && p->target <= 65504.f, BMV_ERR_INVALID_ARGUMENT, "bmv_volume_scale: target must be in (0, 65504]");
+  const int64_t want = ceil_div64(p->n / vec, 256 * 4);
+  const unsigned blocks = (unsigned)(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  if (p->x_half) volume_scale_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  else volume_scale_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("bmv_volume_scale");
+}
+
 extern "C" BMV_API int bmv_depth_planes_first(const bmv_depth_planes_first_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_depth_planes_first");
   using namespace bmv;
   BMV_REQUIRE(p && p->near_far && p->t && p->planes && p->near_far_out, BMV_ERR_INVALID_ARGUMENT,
               "bmv_depth_planes_first: null pointer");
@@ -684,6 +757,7 @@ extern "C" BMV_API int bmv_depth_planes_first(const bmv_depth_planes_first_param
 }
 
 extern "C" BMV_API int bmv_depth_planes_next(const bmv_depth_planes_next_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_depth_planes_next");
   using namespace bmv;
   BMV_REQUIRE(p && p->depth && p->std && p->near_far && p->t && p->planes && p->near_far_out,
               BMV_ERR_INVALID_ARGUMENT, "bmv_depth_planes_next: null pointer");

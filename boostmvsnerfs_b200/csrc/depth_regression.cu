@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(128) depth_regression_reg_kernel(bmv_depth_reg
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_depth_regression(const bmv_depth_regression_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_depth_regression");
   using namespace bmv;
   BMV_REQUIRE(p && p->logits && p->planes && p->depth && p->std, BMV_ERR_INVALID_ARGUMENT,
               "bmv_depth_regression: null pointer");

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) fpn_topdown_kernel(bmv_fpn_topdown_params
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_fpn_topdown(const bmv_fpn_topdown_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_fpn_topdown");
   using namespace bmv;
   BMV_REQUIRE(p && p->prev && p->lateral_in && p->weight && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->H >= 2 && p->W >= 2 && p->H % 2 == 0 && p->W % 2 == 0, BMV_ERR_INVALID_ARGUMENT,

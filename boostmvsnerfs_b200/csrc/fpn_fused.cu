@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
           }
           if (OUT16 && p.out16) {
             __half* o16 = reinterpret_cast<__half*>(p.out16) + (int64_t)n * p.H * p.W * p.Cout;
-            if (gx0 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx0) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][0], acc[oy][nt][1]);
-            if (gx1 < p.W) *reinterpret_cast<__half2*>(o16 + ((int64_t)gy * p.W + gx1) * p.Cout + c) = __floats2half2_rn(acc[oy][nt][2], acc[oy][nt][3]);
+            if (gx0 < p.W) *reinterpret_cast<uint32_t*>(o16 + ((int64_t)gy * p.W + gx0) * p.Cout + c) = pack_half2_sat(acc[oy][nt][0], acc[oy][nt][1]);
+            if (gx1 < p.W) *reinterpret_cast<uint32_t*>(o16 + ((int64_t)gy * p.W + gx1) * p.Cout + c) = pack_half2_sat(acc[oy][nt][2], acc[oy][nt][3]);
           }
         }
       }
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
 template <int CIN, int NT, bool BREG, bool OUT16>
 static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
   const size_t smem = (size_t)kFfTileBytes + (size_t)3 * 6 * NT * 32 * 8 + (size_t)(32 * CIN + 32) * 4;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       // 68 % of the 228 KB: room for the resident CTAs' tiles, the rest stays L1 for the prev / lateral taps
@@ -181,7 +181,7 @@ static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
       set_error("bmv_fpn_topdown_smooth: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   const dim3 grid((unsigned)(((p.W + kFfTX - 1) / kFfTX) * ((p.H + kFfTY - 1) / kFfTY)), (unsigned)p.N);
   fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16><<<grid, kFfThreads, smem, st>>>(p);
@@ -196,6 +196,7 @@ static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_fpn_topdown_smooth");
   using namespace bmv;
   BMV_REQUIRE(p && p->prev && p->lateral_in && p->lat_weight && p->wfrag && (p->out || p->out16), BMV_ERR_INVALID_ARGUMENT,
               "bmv_fpn_topdown_smooth: null pointer");

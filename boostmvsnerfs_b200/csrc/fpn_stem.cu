@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kStThreads, 3) fpn_stem_kernel(bmv_fpn_stem_pa
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_fpn_stem");
   using namespace bmv;
   BMV_REQUIRE(p && p->x && p->w0 && p->wfrag1 && p->out, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: null pointer");
   BMV_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 1 && p->W >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: bad size");

@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(128) mvs_march_fetch_kernel(bmv_mvs_march_para
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_cost_volume_var_img(const bmv_cost_volume_img_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_cost_volume_var_img");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_cost_volume_var_img: null params");
   BMV_REQUIRE(p->feat && p->img && p->proj && p->planes && p->out, BMV_ERR_INVALID_ARGUMENT,
@@ -286,6 +287,7 @@ extern "C" BMV_API int bmv_cost_volume_var_img(const bmv_cost_volume_img_params*
 }
 
 extern "C" BMV_API int bmv_mvs_march_fetch(const bmv_mvs_march_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_mvs_march_fetch");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_mvs_march_fetch: null params");
   BMV_REQUIRE(p->n_rays >= 0 && p->ray_begin >= 0 && p->S >= 1, BMV_ERR_INVALID_ARGUMENT, "bmv_mvs_march_fetch: bad range");

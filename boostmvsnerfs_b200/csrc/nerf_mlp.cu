@@ -49,14 +49,14 @@ template <int F, int V>
 static int launch_mlp(const bmv_nerf_mlp_params& p, cudaStream_t st) {
   using L = MlpLayout<F>;
   const size_t smem = (size_t)(L::TOTAL + kMlpThreads * V * (F + 4)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(nerf_mlp_kernel<F, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("bmv_nerf_mlp: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   nerf_mlp_kernel<F, V><<<(unsigned)ceil_div64(p.P, kMlpThreads), kMlpThreads, smem, st>>>(p);
   return check_launch("bmv_nerf_mlp");
@@ -73,6 +73,7 @@ extern "C" BMV_API int bmv_nerf_mlp_weight_count(int feat_ch) {
 }
 
 extern "C" BMV_API int bmv_nerf_mlp(const bmv_nerf_mlp_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_nerf_mlp");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_nerf_mlp: null params");
   BMV_REQUIRE(p->P >= 0, BMV_ERR_INVALID_ARGUMENT, "bmv_nerf_mlp: negative sample count");

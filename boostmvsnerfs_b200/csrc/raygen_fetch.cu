@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(256) mask_viewport_kernel(bmv_visibility_param
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_raygen_sample_fetch(const bmv_raygen_fetch_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_raygen_sample_fetch");
   using namespace bmv;
   BMV_REQUIRE(p != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_raygen_sample_fetch: null params");
   BMV_REQUIRE(p->src_exts && p->src_ixts, BMV_ERR_INVALID_ARGUMENT, "bmv_raygen_sample_fetch: null camera pointer");
@@ -215,6 +216,7 @@ extern "C" BMV_API int bmv_raygen_sample_fetch(const bmv_raygen_fetch_params* p,
 }
 
 extern "C" BMV_API int bmv_mask_viewport(const bmv_visibility_params* p, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_mask_viewport");
   using namespace bmv;
   BMV_REQUIRE(p && p->xyz && p->src_exts && p->src_ixts, BMV_ERR_INVALID_ARGUMENT, "bmv_mask_viewport: null pointer");
   BMV_REQUIRE(p->V >= 1 && p->V <= BMV_MAX_VIEWS, BMV_ERR_INVALID_ARGUMENT, "bmv_mask_viewport: bad V=%d", p->V);

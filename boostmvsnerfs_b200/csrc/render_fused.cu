@@ -52,14 +52,14 @@ template <int CF, int V>
 static int launch_render(const bmv_render_rays_params& rp, cudaStream_t st) {
   using L = MlpLayout<CF + 3>;
   const size_t smem = (size_t)L::TOTAL * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(render_rays_kernel<CF, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("bmv_render_rays: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   render_rays_kernel<CF, V><<<(unsigned)ceil_div64(rp.g.n_rays, kRenderThreads), kRenderThreads, smem, st>>>(rp);
   return check_launch("bmv_render_rays");
@@ -68,6 +68,7 @@ static int launch_render(const bmv_render_rays_params& rp, cudaStream_t st) {
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_render_rays(const bmv_render_rays_params* rp, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_render_rays");
   using namespace bmv;
   BMV_REQUIRE(rp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays: null params");
   const bmv_raygen_fetch_params* p = &rp->g;

@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) render_rays_mma_kernel(bmv_
 extern "C" BMV_API int bmv_render_rays_mma_weight_words(void) { return bmv::MMA_PACK_WORDS; }
 
 extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_render_rays_mma");
   using namespace bmv;
   BMV_REQUIRE(rp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_mma: null params");
   const bmv_raygen_fetch_params* p = &rp->g;
@@ -423,8 +424,8 @@ extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv
   BMV_REQUIRE(p->Cv == 8 && p->Cf == 8 && p->V == 3, BMV_ERR_UNSUPPORTED_SHAPE,
               "bmv_render_rays_mma: (Cv=%d, Cf=%d, V=%d) not instantiated (8, 8, 3)", p->Cv, p->Cf, p->V);
   const size_t smem = (size_t)(MMA_PACK_WORDS + kMmaWarps * 32 * kStageStride) * 4;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(render_rays_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(render_rays_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -432,7 +433,7 @@ extern "C" BMV_API int bmv_render_rays_mma(const bmv_render_rays_params* rp, bmv
       set_error("bmv_render_rays_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int64_t rounds = ceil_div64(p->n_rays * p->S, kMmaWarps * 32);
   const unsigned blocks = (unsigned)(rounds < kNumSMs ? rounds : kNumSMs);   // persistent: one CTA per SM

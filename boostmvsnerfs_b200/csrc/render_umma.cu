@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 extern "C" BMV_API int bmv_render_rays_umma_weight_words(void) { return bmv::UMMA_PACK_WORDS; }
 
 extern "C" BMV_API int bmv_umma_selftest(const float* A, const void* B_packed, float* D, int N, int K, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_umma_selftest");
   using namespace bmv;
   BMV_REQUIRE(A && B_packed && D, BMV_ERR_INVALID_ARGUMENT, "bmv_umma_selftest: null pointer");
   BMV_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K <= 96 && K % 16 == 0, BMV_ERR_UNSUPPORTED_SHAPE,
@@ -586,6 +587,7 @@ extern "C" BMV_API int bmv_umma_selftest(const float* A, const void* B_packed, f
 }
 
 extern "C" BMV_API int bmv_render_rays_umma(const bmv_render_rays_params* rp, bmv_stream_t stream) {
+  BMV_NVTX_RANGE("bmv_render_rays_umma");
   using namespace bmv;
   BMV_REQUIRE(rp != nullptr, BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: null params");
   const bmv_raygen_fetch_params* p = &rp->g;
@@ -604,8 +606,8 @@ extern "C" BMV_API int bmv_render_rays_umma(const bmv_render_rays_params* rp, bm
               BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_umma: bad grid size");
   BMV_REQUIRE(p->Cv == 8 && p->Cf == 8 && p->V == 3, BMV_ERR_UNSUPPORTED_SHAPE,
               "bmv_render_rays_umma: (Cv=%d, Cf=%d, V=%d) not instantiated (8, 8, 3)", p->Cv, p->Cf, p->V);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(render_rays_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(render_rays_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
@@ -613,7 +615,7 @@ extern "C" BMV_API int bmv_render_rays_umma(const bmv_render_rays_params* rp, bm
       set_error("bmv_render_rays_umma: cannot reserve %zu B shared memory: %s", kUmmaSmem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
     }
-    configured = true;
+    configured.done(cfg_dev);
   }
   // persistent: one CTA per SM owns all 512 TMEM columns (the shared-memory footprint keeps it alone on the SM)
   const int64_t tiles = ceil_div64(p->n_rays * p->S, 128);

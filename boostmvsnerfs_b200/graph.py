@@ -8,24 +8,47 @@ batch this IS the H2D upload), (2) runs the ~1 KB camera algebra and uploads it,
 Kernels read cameras from device memory (include/bmv.h conventions), which is what keeps the captured
 graph valid across frames.
 """
+from collections import OrderedDict
+
 import torch
 
+from .inference_plan import PlanCache
 from .network import BoostEnerfNetwork, _combinations
 
 _STATIC_KEYS = ("all_src_inps", "all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt", "near_far")
 
 
+# Network attributes that select kernels / precision: a captured graph bakes the routing in
+_ROUTING_FLAGS = ("fold_bn", "channels_last", "fused_mlp", "half_feature_taps", "multi_chain_volume", "mlp_engine",
+                  "volume_range_scale", "host_camera_algebra")
+
+
 class FrameGraph:
-    def __init__(self, net: BoostEnerfNetwork):
+    """max_entries bounds the number of captured graphs (each owns a full set of static buffers): least recently
+    used entries are dropped, so a sequence whose selected triples change from view to view cannot grow without
+    bound."""
+
+    def __init__(self, net: BoostEnerfNetwork, max_entries=8):
         if not isinstance(net, BoostEnerfNetwork):
             raise TypeError("FrameGraph wraps a BoostEnerfNetwork")
         self.net = net
-        self._cache = {}
+        self.max_entries = int(max_entries)
+        self._cache = OrderedDict()
 
     def _key(self, batch, triples):
-        return (tuple(batch["all_src_inps"].shape), tuple(triples), bool(self.net.generate_rays),
-                tuple(tuple(batch[f"rays_{i}"].shape) if f"rays_{i}" in batch else None
-                      for i in range(self.net.rc.num)))
+        """Everything a captured graph bakes in: shapes, the selected triples (kernel arguments), the weights (the graph
+        holds pointers to PlanCache's folded copies and to the packed MLP / convolution weights, which are rebuilt when a
+        parameter or buffer changes: same version-counter key as PlanCache) and the precision / kernel routing."""
+        net = self.net
+        return (tuple(batch["all_src_inps"].shape), tuple(triples), bool(net.generate_rays),
+                tuple(tuple(batch[f"rays_{i}"].shape) if f"rays_{i}" in batch else None for i in range(net.rc.num)),
+                PlanCache._key(net), id(net._plans),
+                bool(torch.backends.cudnn.allow_tf32), bool(torch.backends.cuda.matmul.allow_tf32),
+                tuple(getattr(net, f, None) for f in _ROUTING_FLAGS))
+
+    def invalidate(self):
+        """Drop every captured graph (after editing `param.data` directly, which bypasses the version counters)."""
+        self._cache.clear()
 
     def _triples(self, batch):
         net, rc = self.net, self.net.rc
@@ -61,6 +84,7 @@ class FrameGraph:
             return net._assemble([lv])
 
         self._load(entry, batch)
+        entry["cam_loaded"] = False                     # the first real call always loads its own cameras
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -128,7 +152,7 @@ class FrameGraph:
         if rb:
             torch.cuda.current_stream().wait_event(rb["done"])
 
-    def _load(self, entry, batch):
+    def _load(self, entry, batch, cameras_unchanged=False):
         net = self.net
         st = entry["static"]
         if entry.get("staged_for") is batch:                # uploaded by prefetch(): device-to-device only
@@ -145,12 +169,11 @@ class FrameGraph:
         if all(c.device.type == "cpu" for c in cams):
             flat = torch.cat([c.reshape(-1) for c in cams])
         else:
-            # device-resident cameras: reading them back costs a host sync per frame; the same (unmodified)
-            # tensors as last time mean the camera block already on the device is still valid
-            sig = tuple((c.data_ptr(), c._version, c.device) for c in cams)
-            if entry.get("cam_sig") == sig:
+            # Device-resident cameras are read back (one host sync per frame) unless the CALLER states that they are
+            # the cameras of the previous call.  Tensor identity (data_ptr / _version) is not content identity: the
+            # caching allocator hands the same block to the next frame's freshly uploaded cameras.
+            if cameras_unchanged and entry.get("cam_loaded"):
                 return
-            entry["cam_sig"] = sig
             flat = torch.cat([c.reshape(-1).to(st["near_far"].device) for c in cams]).cpu()
         # the pinned camera buffers are re-used every frame: wait until the previous frame's upload has executed
         # before overwriting them (the host may run a frame ahead of the GPU)
@@ -161,10 +184,13 @@ class FrameGraph:
         entry["gen_host"].copy_(net._raygen_host(flat, N))
         entry["gen_dev"].copy_(entry["gen_host"], non_blocking=True)
         entry.setdefault("cam_ev", torch.cuda.Event()).record()
+        entry["cam_loaded"] = True
 
-    def __call__(self, batch):
+    def __call__(self, batch, cameras_unchanged=False):
         """batch: tensors on the GPU or in (pinned) host memory; B must be 1.  Returns the output dict;
-        the tensors are the graph's static outputs and are overwritten by the next call."""
+        the tensors are the graph's static outputs and are overwritten by the next call.
+        cameras_unchanged=True: the caller guarantees the four camera tensors hold the same values as in the previous
+        call with this graph (skips the camera read-back of a device-resident batch)."""
         if self.net.training:
             raise RuntimeError("inference-only")
         if batch["all_src_inps"].shape[0] != 1:
@@ -173,7 +199,17 @@ class FrameGraph:
         key = self._key(batch, triples)
         entry = self._cache.get(key)
         if entry is None:
+            while len(self._cache) >= max(1, self.max_entries):
+                self._cache.popitem(last=False)              # least recently used graph + its static buffers
             entry = self._cache[key] = self._build(batch, triples)
-        self._load(entry, batch)
+            cameras_unchanged = False
+        else:
+            self._cache.move_to_end(key)
+        self._load(entry, batch, cameras_unchanged)
         entry["graph"].replay()
+        # the reference leaves the LAST triple's views in the batch (evaluators read batch['src_inps'].shape;
+        # reference lib/networks/boost_enerf/network.py:196-201): same contract as Network.forward
+        last = list(triples[-1])
+        for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts")):
+            batch[dst] = batch[src][:, last]
         return entry["out"]

@@ -156,15 +156,18 @@ class MergedHeadsCostReg(nn.Module):
             }
         return self._packed
 
-    def forward(self, x):
+    def forward(self, x, in_scale=None):
+        """in_scale: ops.volume_scale tensor when x was stored pre-multiplied by a power of two (fp16 cost volume)."""
         n = self.net
         fast = self._use_tensor_core_convs(x)
+        if in_scale is not None and not fast:
+            raise RuntimeError("a range-scaled volume needs the tensor-core convolution path (conv0 undoes the scale)")
         if fast:
             from . import ops
             pk = self._packed_weights(x.device)
             # activations that only feed other fp16-operand libbmv kernels are stored as fp16 and staged by TMA
             h = torch.float16
-            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True, out_dtype=h)          # ConvBnReLU3D(C, 8)
+            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True, out_dtype=h, in_scale=in_scale)   # ConvBnReLU3D(C, 8)
             s1 = ops.conv3d_k3(s0, *pk['conv1'], 16, relu=True, stride=2, out_dtype=h)   # ConvBnReLU3D(8, 16, stride=2)
             half_low = self.lowres_half and n.depth_levels == 3
             # ConvBnReLU3D(16, 16): fp32 where cuDNN's TF32 layers read it, fp16 when they run in fp16 too

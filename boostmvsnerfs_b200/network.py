@@ -51,6 +51,7 @@ class EnerfNetwork(nn.Module):
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
         self.half_feature_taps = False         # TF32-class path: the fused FPN step emits the level-1 maps in fp16 (8-byte taps in
                                                # K1: -25 us there, +22 us in the FPN kernel's half-sector stores: off by default)
+        self.volume_range_scale = True         # fp16 cost volumes are stored x 2^k (ops.volume_scale), undone by conv0
         self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
@@ -252,6 +253,9 @@ class EnerfNetwork(nn.Module):
                         and torch.backends.cudnn.allow_tf32 and C in (16, 32):
                     vdt = torch.float16
                 self.last_volume_dtype = vdt
+                # fp16 has 5 exponent bits: store s * variance with a power of two s derived from max|feature| so the
+                # volume cannot overflow and small-magnitude features stay out of the subnormals; conv0 undoes it
+                vsc = ops.volume_scale(f) if (vdt == torch.float16 and self.volume_range_scale) else None
                 if self.channels_last:
                     vols = torch.empty((K, D, h, w, C), device=dev, dtype=vdt).permute(0, 4, 1, 2, 3)
                 else:
@@ -268,16 +272,17 @@ class EnerfNetwork(nn.Module):
                         if (self.channels_last and self.multi_chain_volume and f.stride(1) == 1 and len(grp) > 1
                                 and len({len(t) for t in grp}) == 1 and all(len(set(t)) == len(t) for t in grp)
                                 and ops.cost_volume_multi_supported(C, len(uniq), len(grp))):
-                            ops.cost_volume_var_shared_multi(f, grp, projs[i], planes0, h, w, out=vols[k0:k0 + len(grp)])
+                            ops.cost_volume_var_shared_multi(f, grp, projs[i], planes0, h, w, out=vols[k0:k0 + len(grp)],
+                                                             out_scale=vsc)
                         else:
                             for k in range(k0, k0 + len(grp)):
-                                ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k])
+                                ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k], out_scale=vsc)
                 else:                                      # all K chains' hypotheses in one launch
                     planes, nf = ops.depth_planes_next_batched(depth, std, nf, D, h, w, rc.depth_inv[i])
                     for k in range(K):                     # (f may be fp16: half_feature_taps)
-                        ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k])
+                        ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k], out_scale=vsc)
             with self._stage(f'cost_reg_{i}'):
-                feat_vol, logits = self._kept(f'cost_reg_{i}')(vols)
+                feat_vol, logits = plan(vols, in_scale=vsc) if vsc is not None else plan(vols)
                 del vols
             with self._stage(f'depth_regression_l{i}'):
                 if logits.stride(-1) == 1 and logits.stride(-2) == w and logits.stride(-3) == h * w:

@@ -21,13 +21,23 @@ def _feat(t, name):
     if not (torch.is_tensor(t) and t.is_cuda and t.dtype in (torch.float32, torch.float16)):
         raise BmvError(f"{name}: expected a CUDA float32 / float16 tensor, got "
                        f"{type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}")
+    _on_current_device(t, name)
     return int(t.dtype == torch.float16)
+
+
+def _on_current_device(t, name):
+    # libbmv launches on the CURRENT device's current stream (one process per GPU): a tensor living on another
+    # device would be dereferenced by the wrong GPU
+    if t.device.index != torch.cuda.current_device():
+        raise BmvError(f"{name}: tensor is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                       "(call torch.cuda.set_device / use torch.cuda.device(...) around libbmv ops)")
 
 
 def _f32(t, name):
     if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
         raise BmvError(f"{name}: expected a CUDA float32 tensor, got "
                        f"{type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}")
+    _on_current_device(t, name)
     return t
 
 
@@ -58,8 +68,32 @@ def _linspace(n, device):
 
 
 # ------------------------------------------------------------------------------------------ K1
+def volume_scale(feats, target=16384.0):
+    """Power-of-two range scale for an fp16 cost volume built from `feats` (bmv_volume_scale): returns a device tensor
+    [s, 1/s, 0, 0] with s * max|feats|^2 <= target.  Pass it as `out_scale` to the cost-volume ops and as `in_scale`
+    to the convolution that consumes the volume."""
+    half = _feat(feats, "feats")
+    n = feats.numel()
+    # every element of the underlying storage span is a feature value: dense tensors only (any memory format)
+    if not (feats.is_contiguous() or feats.is_contiguous(memory_format=torch.channels_last)):
+        raise BmvError("volume_scale: feats must be dense (contiguous or channels_last)")
+    sc = torch.zeros(4, device=feats.device)
+    p = _lib.VolumeScaleParams()
+    p.x, p.n, p.x_half, p.target, p.scale = feats.data_ptr(), n, half, float(target), sc.data_ptr()
+    _lib.call("bmv_volume_scale", p, _stream())
+    return sc
+
+
+def _scale_ptr(t):
+    if t is None:
+        return 0
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.numel() >= 2 and t.is_contiguous()):
+        raise BmvError("scale: expected the device tensor returned by ops.volume_scale")
+    return t.data_ptr()
+
+
 def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float32, channels_last=False,
-                    exact_coords=False):
+                    exact_coords=False, out_scale=None):
     """Fused plane-sweep cost volume for ONE batch element.
 
     feats  (N,C,Hs,Ws) feature maps of all views, any strides (NCHW or channels_last)
@@ -89,11 +123,12 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
     p.planes_d_stride, p.planes_pix_stride = h * w, 1
     p.D, p.h, p.w = D, h, w
     p.exact_coords = int(exact_coords)
+    p.out_scale = _scale_ptr(out_scale)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
 def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dtype=torch.float32,
-                           channels_last=False, exact_coords=False):
+                           channels_last=False, exact_coords=False, out_scale=None):
     """Same as cost_volume_var with D hypotheses shared by every pixel (cascade level 0)."""
     feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
@@ -111,10 +146,11 @@ def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dty
     p.planes_d_stride, p.planes_pix_stride = 1, 0
     p.D, p.h, p.w = D, h, w
     p.exact_coords = int(exact_coords)
+    p.out_scale = _scale_ptr(out_scale)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
-def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out):
+def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_scale=None):
     """The K level-0 cost volumes (shared depth hypotheses) in one launch: every unique source view is warped once
     per (voxel, plane) and feeds the variance of each chain it belongs to (bmv_cost_volume_var_multi).
     feats (N,C,Hs,Ws) channels-last, triples: K lists of view ids (equal lengths), out (K,C,D,h,w) with
@@ -141,6 +177,7 @@ def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out):
     p.planes_d_stride, p.planes_pix_stride = 1, 0
     p.D, p.h, p.w = D, h, w
     p.exact_coords = 0
+    p.out_scale = _scale_ptr(out_scale)
     p.out = out.data_ptr()
     p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride(1), out.stride(2), out.stride(3), out.stride(4)
     p.out_bf16 = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out.dtype]
@@ -718,7 +755,7 @@ def fpn_topdown(prev, lateral_in, weight, bias):
 
 # ------------------------------------------------------------------------------------------ tensor-core 3-D convolution
 def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1, no_tma=False, out_dtype=torch.float32,
-              engine="mma"):
+              engine="mma", in_scale=None):
     """3x3x3 / stride 1 / pad 1 convolution (+bias, optional ReLU) of a channels_last_3d fp32 volume
     on tensor cores (fp16 operands, fp32 accumulation: TF32-class; reference ConvBnReLU3D / output heads,
     lib/networks/enerf/cost_reg_net.py:7-13,27-35).  x (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_k3;
@@ -755,6 +792,7 @@ def conv3d_k3(x, wfrag, bias, cout, relu, out=None, out2=None, split=0, stride=1
     p.in_half = int(x.dtype == torch.float16)
     p.no_tma = int(bool(no_tma))
     p.out_half = int(out.dtype == torch.float16)
+    p.in_scale = _scale_ptr(in_scale)
     p.out = out.data_ptr()
     p.o_n_stride, p.o_d_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3), out.stride(4)
     if out2 is not None:

@@ -86,8 +86,23 @@ typedef struct bmv_cost_volume_params {
   int32_t feat_half;            /* 1: feat points to fp16 storage (strides in fp16 elements): half the bytes per bilinear tap.
                                    TF32-class (the maps come out of TF32-class convolutions): channels-last fast path only */
   int32_t reserved0;
+  const float* out_scale;       /* DEVICE or NULL: every stored variance is multiplied by out_scale[0] (a power of two from
+                                   bmv_volume_scale): keeps an fp16 volume inside the fp16 range whatever the feature
+                                   magnitude; the consuming convolution undoes it (bmv_conv3d_params.in_scale) */
 } bmv_cost_volume_params;
 BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream);
+
+/* Range scale for an fp16 cost volume (no counterpart in the reference, which stores fp32): the variance of S values in
+ * [-m, m] is at most m^2, so with m = max|x| over the level's feature maps scale = 2^k, k = floor(log2(target / m^2)),
+ * bounds every stored variance by `target` (default use: 16384 of the 65504 fp16 maximum) and moves small-magnitude
+ * features up out of the fp16 subnormals.  One launch: block maxima -> atomicMax -> the last block writes
+ * scale[0] = 2^k, scale[1] = 2^-k.  scale[2..3] are scratch words that must be zero before the first use; the
+ * kernel leaves them zero.  x: fp32 or fp16 (x_half), n elements, 16-byte aligned, n % 4 == 0 (fp32) / 8 (fp16). */
+typedef struct bmv_volume_scale_params {
+  const void* x; int64_t n; int32_t x_half; float target;
+  float* scale;
+} bmv_volume_scale_params;
+BMV_API int bmv_volume_scale(const bmv_volume_scale_params* p, bmv_stream_t stream);
 
 /* The K cost volumes of one cascade level in ONE launch when they share the depth hypotheses (level 0 of the boost
  * path: reference lib/networks/boost_enerf/network.py:189-201 builds them one chain at a time).  A warped source
@@ -384,6 +399,10 @@ typedef struct bmv_conv3d_params {
   int32_t no_tma;               /* 1: force the register-staged path (A/B testing) */
   int32_t out_half;             /* 1: out points to fp16 storage (strides in fp16 elements; even Cout, no out2): for results
                                    that only feed other fp16-operand libbmv convolutions */
+  int32_t reserved0;
+  const float* in_scale;        /* DEVICE or NULL: [s, 1/s] written by bmv_volume_scale — x holds s * (the real input); the
+                                   accumulator starts at s*bias and the result is multiplied by 1/s (exact: s is a power
+                                   of two).  Stride-1 mma.sync kernel only. */
 } bmv_conv3d_params;
 BMV_API int bmv_conv3d_k3(const bmv_conv3d_params* p, bmv_stream_t stream);
 BMV_API int bmv_conv3d_k3_weight_words(int Cin, int Cout);

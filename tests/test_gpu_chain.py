@@ -256,3 +256,59 @@ def test_half_feature_taps_option_matches_default():
     net.half_feature_taps = False
     for k in ("rgb_level1", "depth_level1"):
         _report(got[k], ref[k].detach().cpu().numpy(), f"half feature taps {k}", 1e-2)
+
+
+def test_frame_graph_fresh_device_batches_get_their_own_cameras(strict_fp32):
+    """`for b in loader: fg(to_cuda(b))`: every frame's camera tensors are fresh device allocations that the caching
+    allocator may place at the previous frame's addresses.  The graph must use each frame's own
+    cameras — tensor identity is not content identity."""
+    from boostmvsnerfs_b200 import network
+    from boostmvsnerfs_b200.graph import FrameGraph
+    from boostmvsnerfs_b200.synth import make_scene, batch_to
+    torch.manual_seed(0)
+    net = network.BoostEnerfNetwork(preprocess=True, rc=RenderConfig.enerf_eval(2)).eval().cuda()
+    net.view_selection_outputs = {"synth_0": [1, 2]}
+    fg = FrameGraph(net)
+    ptrs = set()
+    for s in range(4):
+        scene = make_scene(H=64, W=96, n_views=4, seed=s, smooth=True, tar_offset=(0.05 * s, -0.02 * s, 0.03 * s))
+        want = {k: v.clone() for k, v in net(batch_to(scene, "cuda")).items()}
+        b = batch_to(scene, "cuda")                      # freed at the end of the iteration -> addresses are re-used
+        ptrs.add(b["tar_ext"].data_ptr())
+        got = fg(b)
+        for k in want:
+            _report(got[k], want[k].cpu().numpy(), f"frame {s} {k}", 1e-6)
+        del b, got
+    assert len(fg._cache) == 1
+
+
+def test_frame_graph_follows_weights_and_flags(strict_fp32):
+    """A captured graph bakes in pointers to the folded / packed weight copies and the precision routing: after
+    load_state_dict or a routing change the next call must re-capture instead of replaying stale weights
+    (ADVICE round 1, medium); the LRU bound keeps the number of live graphs fixed; batch['src_*'] is set like forward."""
+    from boostmvsnerfs_b200.graph import FrameGraph
+    g = load_golden("enerf_chain_eval.npz")
+    net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
+    fg = FrameGraph(net, max_entries=2)
+    b1 = dict(batch)
+    first = {k: v.clone() for k, v in fg(b1).items()}
+    for k in ("src_inps", "src_exts", "src_ixts"):
+        assert np.array_equal(b1[k].cpu().numpy(), g.np(f"after_{k}")), k
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        changed = {k: (v * 1.25 if k.startswith("nerf_1") and v.dtype.is_floating_point else v) for k, v in sd.items()}
+    net.load_state_dict(changed)
+    want = net(dict(batch))
+    got = fg(dict(batch))
+    assert len(fg._cache) == 2
+    for k in want:
+        _report(got[k], want[k].cpu().numpy(), f"after load_state_dict {k}", 1e-6)
+    assert (got["rgb_level1"] - first["rgb_level1"]).abs().max().item() > 1e-4
+    net.mlp_engine = "fma"
+    fg(dict(batch))
+    assert len(fg._cache) == 2                            # least recently used graph dropped
+    net.load_state_dict(sd)
+    net.mlp_engine = "mma"
+    back = fg(dict(batch))
+    for k in first:
+        _report(back[k], first[k].cpu().numpy(), f"weights restored {k}", 1e-6)
