@@ -684,8 +684,14 @@ def main_ours(args):
             a = out[k].float().cpu().reshape(-1)
             b = b.float().cpu().reshape(-1)
             rng = float(b.abs().max())
-            err = float((a - b).abs().max())
-            res[k] = {"max_abs_err": err, "ref_range": rng, "err_over_range": err / max(rng, 1e-30)}
+            d = (a - b).abs()
+            err = float(d.max())
+            # a sample on a frustum edge can flip its visibility count under a 1-ulp change of the depth map (SURVEY.md
+            # 10.13; tests/test_gpu_precision.py shows each flip sits on an edge): the element counts tell a handful of
+            # such rays from a systematic error
+            res[k] = {"max_abs_err": err, "ref_range": rng, "err_over_range": err / max(rng, 1e-30), "elements": d.numel(),
+                      "elements_over_1e-4_of_range": int((d > 1e-4 * rng).sum()), "elements_over_1e-2_of_range": int((d > 1e-2 * rng).sum()),
+                      "p99.99_err_over_range": float(torch.quantile(d[::max(1, d.numel() // 4000000)], 0.9999)) / max(rng, 1e-30)}
         return res
 
     cpu_frame = {}

@@ -165,6 +165,16 @@ class FpnStemParams(C.Structure):
                 ("out_s2d", C.c_void_p)]
 
 
+class FramePsnrParams(C.Structure):
+    _fields_ = [("pred", C.c_void_p), ("gt", C.c_void_p), ("mask", C.c_void_p),
+                ("H", i32), ("W", i32), ("crop_h", i32), ("crop_w", i32), ("sse", C.c_void_p), ("count", C.c_void_p)]
+
+
+class FrameToU8Params(C.Structure):
+    _fields_ = [("R", i64), ("rgb", C.c_void_p), ("rgb_u8", C.c_void_p), ("depth", C.c_void_p), ("depth_u8", C.c_void_p),
+                ("minmax_ord", C.c_void_p), ("minmax", C.c_void_p)]
+
+
 ENTRY_POINTS = {
     "bmv_cost_volume_var": CostVolumeParams,
     "bmv_cost_volume_var_multi": CostVolumeMultiParams,
@@ -188,6 +198,8 @@ ENTRY_POINTS = {
     "bmv_convT3d_k3s2": ConvT3dParams,
     "bmv_fpn_topdown_smooth": FpnFusedParams,
     "bmv_fpn_stem": FpnStemParams,
+    "bmv_frame_psnr_accumulate": FramePsnrParams,
+    "bmv_frame_to_u8": FrameToU8Params,
 }
 PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bmv_sizeof_params",
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",

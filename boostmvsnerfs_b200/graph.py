@@ -12,7 +12,6 @@ from collections import OrderedDict
 
 import torch
 
-from .inference_plan import PlanCache
 from .network import BoostEnerfNetwork, _combinations
 
 _STATIC_KEYS = ("all_src_inps", "all_src_exts", "all_src_ixts", "tar_ext", "tar_ixt", "near_far")
@@ -34,21 +33,28 @@ class FrameGraph:
         self.net = net
         self.max_entries = int(max_entries)
         self._cache = OrderedDict()
+        self._wtensors = None
 
     def _key(self, batch, triples):
         """Everything a captured graph bakes in: shapes, the selected triples (kernel arguments), the weights (the graph
         holds pointers to PlanCache's folded copies and to the packed MLP / convolution weights, which are rebuilt when a
         parameter or buffer changes: same version-counter key as PlanCache) and the precision / kernel routing."""
         net = self.net
+        # Walking the module tree costs ~0.3 ms per call; the tensor OBJECTS are collected once (again at every capture)
+        # and only their (data_ptr, version) pairs are read per call.  load_state_dict, optimiser steps, .to() / .cuda()
+        # all keep the Parameter objects; code that REPLACES a Parameter object must call invalidate().
+        if self._wtensors is None:
+            self._wtensors = list(net.parameters()) + list(net.buffers())
         return (tuple(batch["all_src_inps"].shape), tuple(triples), bool(net.generate_rays),
                 tuple(tuple(batch[f"rays_{i}"].shape) if f"rays_{i}" in batch else None for i in range(net.rc.num)),
-                PlanCache._key(net), id(net._plans),
+                tuple((t.data_ptr(), t._version) for t in self._wtensors), id(net._plans),
                 bool(torch.backends.cudnn.allow_tf32), bool(torch.backends.cuda.matmul.allow_tf32),
                 tuple(getattr(net, f, None) for f in _ROUTING_FLAGS))
 
     def invalidate(self):
         """Drop every captured graph (after editing `param.data` directly, which bypasses the version counters)."""
         self._cache.clear()
+        self._wtensors = None
 
     def _triples(self, batch):
         net, rc = self.net, self.net.rc
@@ -201,6 +207,8 @@ class FrameGraph:
         if entry is None:
             while len(self._cache) >= max(1, self.max_entries):
                 self._cache.popitem(last=False)              # least recently used graph + its static buffers
+            self._wtensors = None                            # re-collect the weight tensors with every capture
+            key = self._key(batch, triples)
             entry = self._cache[key] = self._build(batch, triples)
             cameras_unchanged = False
         else:
@@ -209,7 +217,9 @@ class FrameGraph:
         entry["graph"].replay()
         # the reference leaves the LAST triple's views in the batch (evaluators read batch['src_inps'].shape;
         # reference lib/networks/boost_enerf/network.py:196-201): same contract as Network.forward
+        # Gathered on the device from the uploaded copy (a host batch would pay an 18 MB CPU gather per frame); real
+        # copies, so the next call's upload does not change them.
         last = list(triples[-1])
         for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts")):
-            batch[dst] = batch[src][:, last]
+            batch[dst] = entry["static"][src][:, last]
         return entry["out"]

@@ -60,6 +60,8 @@ class EnerfNetwork(nn.Module):
         self._plans = PlanCache()
         self.stage_timer = None                # optional callable(name) -> context manager
         self._packed = {}                      # level -> (param versions, packed weight tensor)
+        self.keep_internals = False            # True: forward() leaves {level: per-chain visibility scores / z} of the
+        self.last_internals = None             # last frame in last_internals (parity diagnostics; references, no copies)
 
     # ------------------------------------------------------------------ helpers
     def _check_mode(self, batch):
@@ -227,6 +229,8 @@ class EnerfNetwork(nn.Module):
         for i, st in states.items():
             out[i] = self._render_level(i, feats, inps, st, rays_by_level[i], cams, triples, Hh, Ww)
             out[i]['depth0'], out[i]['std0'] = st['depth'][0], st['std'][0]
+        if self.keep_internals:
+            self.last_internals = {i: {'masks': torch.stack(o['masks']), 'zs': torch.stack(o['zs'])} for i, o in out.items()}
         return out
 
     def _chain_levels(self, feats, projs, near_far, triples, Hh, Ww):

@@ -480,6 +480,32 @@ typedef struct bmv_fpn_stem_params {
 } bmv_fpn_stem_params;
 BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f4  output sinks: what the reference's evaluator / visualiser consume, produced on the device.
+ * bmv_frame_psnr_accumulate: reference lib/evaluators/enerf.py:45-71 — pred / gt (H*W,3) fp32 row-major, optional
+ *   mask (H*W) uint8 (pixel counted when mask >= 1), optional centre crop (rows [crop_h, H-crop_h), columns
+ *   [crop_w, W-crop_w); the reference uses int(0.1*h), int(0.1*w) under cfg.enerf.eval_center).  Adds the sum of
+ *   squared differences (float64) to *sse and the number of compared ELEMENTS (3 per pixel) to *count; the caller
+ *   zeroes them.  PSNR = 10 log10(1 / (sse / count)) (skimage.metrics.peak_signal_noise_ratio, data_range 1).
+ * bmv_frame_to_u8: reference lib/visualizers/enerf.py:27-37 — rgb_u8 = (rgb * 255).astype(uint8);
+ *   depth_u8 = ((depth - min) / (max - min) * 255).astype(uint8), min / max over the frame written to minmax[0..1]
+ *   (optional).  minmax_ord: 2 words of device scratch.
+ */
+typedef struct bmv_frame_psnr_params {
+  const float* pred; const float* gt; const uint8_t* mask;   /* mask may be NULL */
+  int32_t H, W, crop_h, crop_w;
+  double* sse; unsigned long long* count;                    /* DEVICE accumulators */
+} bmv_frame_psnr_params;
+BMV_API int bmv_frame_psnr_accumulate(const bmv_frame_psnr_params* p, bmv_stream_t stream);
+
+typedef struct bmv_frame_to_u8_params {
+  int64_t R;
+  const float* rgb; uint8_t* rgb_u8;        /* (R,3) each, or both NULL */
+  const float* depth; uint8_t* depth_u8;    /* (R) each, or both NULL */
+  uint32_t* minmax_ord; float* minmax;      /* scratch (2 words); optional output (2 floats) */
+} bmv_frame_to_u8_params;
+BMV_API int bmv_frame_to_u8(const bmv_frame_to_u8_params* p, bmv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

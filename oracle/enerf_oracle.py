@@ -346,12 +346,15 @@ def view_triples(n_views, per_volume, device=None):
     return torch.combinations(torch.arange(n_views), per_volume).to(device)
 
 
-def boost_enerf_forward(net, batch, rc, k_best):
+def boost_enerf_forward(net, batch, rc, k_best, internals=None):
     """reference lib/networks/boost_enerf/network.py:172-237 (Network.forward).
     `net` supplies the kept NN modules: forward_feat-compatible `feature_net`, `cost_reg_{i}`,
     `nerf_{i}` (module objects are shared with the product so both sides use identical weights).
     `k_best`: (B,K) long tensor of indices into the triples table.  Mutates `batch` like the
-    reference does (src_inps/src_exts/src_ixts of the last triple)."""
+    reference does (src_inps/src_exts/src_ixts of the last triple).
+    internals: optional dict that receives, per rendered level, the per-chain visibility scores
+    `masks_level{i}` (B,K,R,S) before merge_masks, the sample positions `xyz_level{i}` (B,K,R,S,3) and `triples`
+    — what a parity test needs to tell a 1-ulp frustum-edge flip from an arithmetic error."""
     inps = batch['all_src_inps']
     B, N = inps.shape[:2]
     I, K = rc.cost_volume_input_views, rc.k_best
@@ -393,8 +396,14 @@ def boost_enerf_forward(net, batch, rc, k_best):
             per_k.append(render_chain(rays12, vol, feats[f'level_{lvl}'][bidx, vidx], batch['src_inps'],
                                       batch['src_exts'], batch['src_ixts'], batch['tar_ext'],
                                       getattr(net, f'nerf_{i}'), i, rc))
+            if internals is not None:
+                per_k[-1]['xyz'] = sample_along_depth(rays12, rc.num_samples[i], rc.depth_inv[i])[0]
         if not rc.render_if[i]:
             continue
+        if internals is not None:
+            internals[f'masks_level{i}'] = torch.stack([o['mask'] for o in per_k], dim=1)
+            internals[f'xyz_level{i}'] = torch.stack([o['xyz'] for o in per_k], dim=1)
+            internals['triples'] = triples
         raws = torch.stack([o['net_output'] for o in per_k], dim=1)
         masks = merge_masks(torch.stack([o['mask'] for o in per_k], dim=1), K)
         zs = torch.stack([o['z_vals'] for o in per_k], dim=1)
