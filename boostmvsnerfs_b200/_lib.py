@@ -36,7 +36,8 @@ class CostVolumeMultiParams(C.Structure):
 
 
 class VolumeScaleParams(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("n", i64), ("x_half", i32), ("target", f32), ("scale", C.c_void_p)]
+    _fields_ = [("x", C.c_void_p), ("n", i64), ("x_half", i32), ("target", f32), ("scale", C.c_void_p),
+                ("consumer_scale", f32), ("reserved0", i32)]
 
 
 class DepthPlanesFirstParams(C.Structure):

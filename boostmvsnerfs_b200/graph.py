@@ -78,7 +78,8 @@ class FrameGraph:
         gen_dev = torch.zeros(rc.num * 12, device=dev, dtype=torch.float64)
         gen_host = torch.zeros(rc.num * 12, dtype=torch.float64).pin_memory()
         H, W = st["all_src_inps"].shape[-2:]
-        entry = {"static": st, "cam_dev": cam_dev, "cam_host": cam_host, "gen_dev": gen_dev, "gen_host": gen_host,
+        last_idx = torch.tensor(list(triples[-1]), device=dev, dtype=torch.long)
+        entry = {"static": st, "last_idx": last_idx, "cam_dev": cam_dev, "cam_host": cam_host, "gen_dev": gen_dev, "gen_host": gen_host,
                  "graph": None, "out": None}
 
         def body():
@@ -219,7 +220,8 @@ class FrameGraph:
         # reference lib/networks/boost_enerf/network.py:196-201): same contract as Network.forward
         # Gathered on the device from the uploaded copy (a host batch would pay an 18 MB CPU gather per frame); real
         # copies, so the next call's upload does not change them.
-        last = list(triples[-1])
+        # (index_select with a device-resident index: indexing with a Python list uploads the indices with a blocking
+        # copy, i.e. one host sync per frame)
         for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts")):
-            batch[dst] = entry["static"][src][:, last]
+            batch[dst] = entry["static"][src].index_select(1, entry["last_idx"])
         return entry["out"]

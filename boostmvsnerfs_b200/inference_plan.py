@@ -141,12 +141,17 @@ class MergedHeadsCostReg(nn.Module):
 
     def _packed_weights(self, device):
         if self._packed is None or self._packed['device'] != device:
-            from .mlp_pack import pack_conv3d_k3, pack_conv3d_k3_umma, pack_convT3d_k3s2
+            from .mlp_pack import fp16_weight_scale, pack_conv3d_k3, pack_conv3d_k3_umma, pack_convT3d_k3s2
             n = self.net
             bias = lambda m: m.bias.detach().float().contiguous().to(device)
+            # conv0 consumes the variance volume, whose magnitude follows the feature magnitude squared: its weights are
+            # packed x 2^k (so that none of them falls into the fp16 subnormals) and the kernel divides by it
+            ws0 = fp16_weight_scale(n.conv0.conv.weight)
             self._packed = {
                 'device': device,
-                'conv0': (pack_conv3d_k3(n.conv0.conv.weight).to(device), bias(n.conv0.conv)),
+                'conv0': (pack_conv3d_k3(n.conv0.conv.weight, ws0).to(device), bias(n.conv0.conv)),
+                'conv0_ws': ws0,
+                'conv0_scale': torch.tensor([ws0, 1.0 / ws0], device=device),
                 'conv1': (pack_conv3d_k3(n.conv1.conv.weight).to(device), bias(n.conv1.conv)),
                 'conv2': (pack_conv3d_k3(n.conv2.conv.weight).to(device), bias(n.conv2.conv)),
                 'conv9': (pack_convT3d_k3s2(n.conv9[0].weight).to(device), bias(n.conv9[0])),
@@ -156,8 +161,13 @@ class MergedHeadsCostReg(nn.Module):
             }
         return self._packed
 
+    def input_weight_scale(self, device):
+        """The power of two conv0's fp16 weights are packed with (ops.volume_scale(consumer_scale=...))."""
+        return self._packed_weights(device)['conv0_ws']
+
     def forward(self, x, in_scale=None):
-        """in_scale: ops.volume_scale tensor when x was stored pre-multiplied by a power of two (fp16 cost volume)."""
+        """in_scale: ops.volume_scale(feats, consumer_scale=self.input_weight_scale(dev))[4:6] when x was stored
+        pre-multiplied by a power of two (fp16 cost volume)."""
         n = self.net
         fast = self._use_tensor_core_convs(x)
         if in_scale is not None and not fast:
@@ -167,7 +177,8 @@ class MergedHeadsCostReg(nn.Module):
             pk = self._packed_weights(x.device)
             # activations that only feed other fp16-operand libbmv kernels are stored as fp16 and staged by TMA
             h = torch.float16
-            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True, out_dtype=h, in_scale=in_scale)   # ConvBnReLU3D(C, 8)
+            s0 = ops.conv3d_k3(x, *pk['conv0'], 8, relu=True, out_dtype=h,                  # ConvBnReLU3D(C, 8)
+                               in_scale=in_scale if in_scale is not None else pk['conv0_scale'])
             s1 = ops.conv3d_k3(s0, *pk['conv1'], 16, relu=True, stride=2, out_dtype=h)   # ConvBnReLU3D(8, 16, stride=2)
             half_low = self.lowres_half and n.depth_levels == 3
             # ConvBnReLU3D(16, 16): fp32 where cuDNN's TF32 layers read it, fp16 when they run in fp16 too

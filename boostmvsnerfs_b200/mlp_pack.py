@@ -221,8 +221,21 @@ def _conv3d_ksteps(cin):
     raise ValueError(cin)
 
 
-def pack_conv3d_k3(weight):
-    """weight (Cout, Cin, 3, 3, 3) fp32 -> int32 tensor in the order bmv_conv3d_k3 reads:
+def fp16_weight_scale(weight):
+    """Power of two c with max|weight| * c in [512, 1024): weights packed as fp16(weight * c) keep 11 significant bits
+    down to ~1e-7 of the layer's largest weight whatever its absolute magnitude (a layer that consumes a large-valued
+    input, e.g. the variance volume of large features, has correspondingly tiny weights: below 6.1e-5 they would be
+    fp16 subnormals, below 6e-8 zero).  The kernel divides the result by c (bmv_conv3d_params.in_scale)."""
+    import math
+    m = float(weight.detach().abs().max())
+    if not (m > 0.0) or not math.isfinite(m):
+        return 1.0
+    return 2.0 ** (9 - math.floor(math.log2(m)))
+
+
+def pack_conv3d_k3(weight, scale=1.0):
+    """weight (Cout, Cin, 3, 3, 3) fp32 -> int32 tensor in the order bmv_conv3d_k3 reads (values multiplied by `scale`,
+    a power of two, before the fp16 rounding):
     [dz][dy][k-step j][n-tile][lane = 4g+t] x {b0, b1}; b0 = fp16 pair at K indices (2t, 2t+1) of the k-step,
     b1 at (2t+8, 2t+9), output channel n = nt*8+g (mma.sync.m16n8k16 B fragment); absent channels are zero."""
     Cout, Cin = weight.shape[:2]
@@ -231,7 +244,7 @@ def pack_conv3d_k3(weight):
     steps = _conv3d_ksteps(Cin)
     NT = _conv3d_ntiles(Cin, Cout)
     w = torch.zeros(NT * 8, Cin, 3, 3, 3)
-    w[:Cout] = weight.detach().float().cpu()
+    w[:Cout] = weight.detach().float().cpu() * float(scale)
     # B[dz][dy][j][k][n]
     B = torch.zeros(3, 3, len(steps), 16, NT * 8)
     for j, step in enumerate(steps):

@@ -259,7 +259,9 @@ class EnerfNetwork(nn.Module):
                 self.last_volume_dtype = vdt
                 # fp16 has 5 exponent bits: store s * variance with a power of two s derived from max|feature| so the
                 # volume cannot overflow and small-magnitude features stay out of the subnormals; conv0 undoes it
-                vsc = ops.volume_scale(f) if (vdt == torch.float16 and self.volume_range_scale) else None
+                vsc = None
+                if vdt == torch.float16 and self.volume_range_scale:
+                    vsc = ops.volume_scale(f, consumer_scale=plan.input_weight_scale(dev))
                 if self.channels_last:
                     vols = torch.empty((K, D, h, w, C), device=dev, dtype=vdt).permute(0, 4, 1, 2, 3)
                 else:
@@ -286,7 +288,7 @@ class EnerfNetwork(nn.Module):
                     for k in range(K):                     # (f may be fp16: half_feature_taps)
                         ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k], out_scale=vsc)
             with self._stage(f'cost_reg_{i}'):
-                feat_vol, logits = plan(vols, in_scale=vsc) if vsc is not None else plan(vols)
+                feat_vol, logits = plan(vols, in_scale=vsc[4:6]) if vsc is not None else plan(vols)
                 del vols
             with self._stage(f'depth_regression_l{i}'):
                 if logits.stride(-1) == 1 and logits.stride(-2) == w and logits.stride(-3) == h * w:

@@ -68,18 +68,20 @@ def _linspace(n, device):
 
 
 # ------------------------------------------------------------------------------------------ K1
-def volume_scale(feats, target=16384.0):
+def volume_scale(feats, target=16384.0, consumer_scale=1.0):
     """Power-of-two range scale for an fp16 cost volume built from `feats` (bmv_volume_scale): returns a device tensor
-    [s, 1/s, 0, 0] with s * max|feats|^2 <= target.  Pass it as `out_scale` to the cost-volume ops and as `in_scale`
-    to the convolution that consumes the volume."""
+    [s, 1/s, 0, 0, s*c, 1/(s*c)] with s * max|feats|^2 <= target and c = consumer_scale (the power of two the consuming
+    convolution's fp16 weights were packed with).  Pass it as `out_scale` to the cost-volume ops and `t[4:6]` as
+    `in_scale` to the convolution that consumes the volume."""
     half = _feat(feats, "feats")
     n = feats.numel()
     # every element of the underlying storage span is a feature value: dense tensors only (any memory format)
     if not (feats.is_contiguous() or feats.is_contiguous(memory_format=torch.channels_last)):
         raise BmvError("volume_scale: feats must be dense (contiguous or channels_last)")
-    sc = torch.zeros(4, device=feats.device)
+    sc = torch.zeros(6, device=feats.device)
     p = _lib.VolumeScaleParams()
     p.x, p.n, p.x_half, p.target, p.scale = feats.data_ptr(), n, half, float(target), sc.data_ptr()
+    p.consumer_scale = float(consumer_scale)
     _lib.call("bmv_volume_scale", p, _stream())
     return sc
 
@@ -909,3 +911,49 @@ def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False):
     if want_s2d:
         return out, rgb4, s2d
     return (out, rgb4) if want_rgb4 else out
+
+
+# ------------------------------------------------------------------------------------------ f4: output sinks
+def frame_psnr_accumulate(pred, gt, H, W, mask=None, crop=(0, 0), acc=None):
+    """Adds the masked / centre-cropped squared error of one frame to `acc` = (sse float64[1], count int64[1]) on the
+    device (allocated when None) and returns it (reference lib/evaluators/enerf.py:45-71).  pred, gt: (H*W,3) fp32;
+    mask: (H*W) uint8 or None; crop = (crop_h, crop_w) rows / columns dropped at each border."""
+    pred, gt = _cf32(pred.reshape(-1, 3), "pred"), _cf32(gt.reshape(-1, 3), "gt")
+    if pred.shape[0] != H * W or gt.shape[0] != H * W:
+        raise BmvError(f"frame_psnr_accumulate: expected {H * W} pixels, got {pred.shape[0]} / {gt.shape[0]}")
+    if acc is None:
+        acc = (torch.zeros(1, device=pred.device, dtype=torch.float64), torch.zeros(1, device=pred.device, dtype=torch.int64))
+    p = _lib.FramePsnrParams()
+    p.pred, p.gt = pred.data_ptr(), gt.data_ptr()
+    if mask is not None:
+        if not (mask.is_cuda and mask.dtype == torch.uint8 and mask.numel() == H * W and mask.is_contiguous()):
+            raise BmvError("frame_psnr_accumulate: mask must be a contiguous CUDA uint8 tensor with H*W elements")
+        p.mask = mask.data_ptr()
+    p.H, p.W, p.crop_h, p.crop_w = H, W, int(crop[0]), int(crop[1])
+    p.sse, p.count = acc[0].data_ptr(), acc[1].data_ptr()
+    _lib.call("bmv_frame_psnr_accumulate", p, _stream())
+    return acc
+
+
+def frame_to_u8(rgb=None, depth=None):
+    """rgb (R,3) fp32 -> uint8 `(rgb*255).astype(uint8)`; depth (R,) fp32 -> uint8 `((d-min)/(max-min)*255).astype(uint8)`
+    (reference lib/visualizers/enerf.py:27-37).  Returns (rgb_u8 or None, depth_u8 or None, minmax (2,) fp32 or None)."""
+    if rgb is None and depth is None:
+        raise BmvError("frame_to_u8: nothing to convert")
+    p = _lib.FrameToU8Params()
+    rgb_u8 = depth_u8 = minmax = None
+    if rgb is not None:
+        rgb = _cf32(rgb.reshape(-1, 3), "rgb")
+        rgb_u8 = torch.empty(rgb.shape, device=rgb.device, dtype=torch.uint8)
+        p.R, p.rgb, p.rgb_u8 = rgb.shape[0], rgb.data_ptr(), rgb_u8.data_ptr()
+    if depth is not None:
+        depth = _cf32(depth.reshape(-1), "depth")
+        if rgb is not None and depth.numel() != rgb.shape[0]:
+            raise BmvError("frame_to_u8: rgb and depth must cover the same rays")
+        depth_u8 = torch.empty(depth.shape, device=depth.device, dtype=torch.uint8)
+        scratch = torch.empty(2, device=depth.device, dtype=torch.int32)
+        minmax = torch.empty(2, device=depth.device)
+        p.R, p.depth, p.depth_u8 = depth.numel(), depth.data_ptr(), depth_u8.data_ptr()
+        p.minmax_ord, p.minmax = scratch.data_ptr(), minmax.data_ptr()
+    _lib.call("bmv_frame_to_u8", p, _stream())
+    return rgb_u8, depth_u8, minmax

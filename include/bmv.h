@@ -96,11 +96,14 @@ BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t st
  * [-m, m] is at most m^2, so with m = max|x| over the level's feature maps scale = 2^k, k = floor(log2(target / m^2)),
  * bounds every stored variance by `target` (default use: 16384 of the 65504 fp16 maximum) and moves small-magnitude
  * features up out of the fp16 subnormals.  One launch: block maxima -> atomicMax -> the last block writes
- * scale[0] = 2^k, scale[1] = 2^-k.  scale[2..3] are scratch words that must be zero before the first use; the
- * kernel leaves them zero.  x: fp32 or fp16 (x_half), n elements, 16-byte aligned, n % 4 == 0 (fp32) / 8 (fp16). */
+ * scale[0] = 2^k, scale[1] = 2^-k, and scale[4] = 2^k * consumer_scale, scale[5] = 1 / scale[4] for a consumer whose fp16
+ * weights were themselves packed pre-multiplied by consumer_scale (bmv_conv3d_params.in_scale = scale + 4; 0 is read
+ * as 1).  scale has 6 floats; scale[2..3] are scratch words that must be zero before the first use; the kernel
+ * leaves them zero.  x: fp32 or fp16 (x_half), n elements, 16-byte aligned, n % 4 == 0 (fp32) / 8 (fp16). */
 typedef struct bmv_volume_scale_params {
   const void* x; int64_t n; int32_t x_half; float target;
   float* scale;
+  float consumer_scale; int32_t reserved0;
 } bmv_volume_scale_params;
 BMV_API int bmv_volume_scale(const bmv_volume_scale_params* p, bmv_stream_t stream);
 

@@ -191,3 +191,18 @@ print("PLUGIN_OK")
 ''' % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "PLUGIN_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_sinks_oracle_arithmetic():
+    """oracle/sinks_oracle.py against an independent float64 evaluation of the published PSNR definition and numpy's
+    own casts (the reference's Evaluator cannot be imported here: lpips / skimage / cv2 are absent)."""
+    import numpy as np
+    from oracle import sinks_oracle as SO
+    rs = np.random.RandomState(1)
+    pred, gt = rs.rand(40, 50, 3).astype(np.float32), rs.rand(40, 50, 3).astype(np.float32)
+    mask = (rs.rand(40, 50) > 0.5).astype(np.uint8)
+    sel = mask[4:-4, 5:-5] >= 1
+    mse = ((gt[4:-4, 5:-5][sel].astype(np.float64) - pred[4:-4, 5:-5][sel].astype(np.float64)) ** 2).sum() / (sel.sum() * 3)
+    assert abs(SO.frame_psnr(pred, gt, mask, eval_center=True) - 10 * np.log10(1 / mse)) < 1e-12
+    rgb8, d8 = SO.frame_to_u8(np.array([[0.0, 0.999, 1.0]], np.float32), np.array([2.0, 3.0, 4.0], np.float32))
+    assert rgb8.tolist() == [[0, 254, 255]] and d8.tolist() == [0, 127, 255]
