@@ -109,6 +109,15 @@ class RenderRaysParams(C.Structure):
     _fields_ = [("g", RaygenFetchParams), ("mlp_weights", C.c_void_p), ("raw", C.c_void_p)]
 
 
+class RenderMultiParams(C.Structure):
+    _fields_ = [("g", RaygenFetchParams), ("K", i32), ("n_views", i32),
+                ("depth", C.c_void_p), ("depth_k_stride", i64), ("std", C.c_void_p), ("std_k_stride", i64),
+                ("near_far", C.c_void_p), ("nf_k_stride", i64), ("volume", C.c_void_p), ("vol_k_stride", i64),
+                ("views", C.c_void_p), ("views_host", i32 * (MAX_VOLUMES * 3)),
+                ("mlp_weights", C.c_void_p), ("raw", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p),
+                ("vis_count", C.c_void_p)]
+
+
 class CostVolumeImgParams(C.Structure):
     _fields_ = [("feat", C.c_void_p), ("feat_view_stride", i64), ("feat_c_stride", i64), ("feat_y_stride", i64),
                 ("feat_x_stride", i64), ("img", C.c_void_p), ("view", i32 * MAX_VIEWS),
@@ -191,6 +200,7 @@ ENTRY_POINTS = {
     "bmv_render_rays": RenderRaysParams,
     "bmv_render_rays_mma": RenderRaysParams,
     "bmv_render_rays_umma": RenderRaysParams,
+    "bmv_render_rays_multi": RenderMultiParams,
     "bmv_cost_volume_var_img": CostVolumeImgParams,
     "bmv_mvs_march_fetch": MvsMarchParams,
     "bmv_fpn_topdown": FpnTopdownParams,

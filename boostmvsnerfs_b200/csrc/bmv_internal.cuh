@@ -99,8 +99,9 @@ __device__ __forceinline__ __half half_sat(float v) {
 }
 
 // ATen grid_sampler unnormalize with align_corners=True: ((g + 1) / 2) * (size - 1).
+// (x / 2 is written x * 0.5: the same correctly rounded value for every x, without the IEEE division sequence.)
 __device__ __forceinline__ float unnormalize_ac(float g, int size) {
-  return mul_rn(div_rn(add_rn(g, 1.f), 2.f), (float)(size - 1));
+  return mul_rn(mul_rn(add_rn(g, 1.f), 0.5f), (float)(size - 1));
 }
 
 // A coordinate ATen's CUDA sampler would send to "-100" (non-finite or outside int range).

@@ -5,6 +5,12 @@
 
 namespace bmv {
 
+// view id s of the volume: from DEVICE memory when given (a captured CUDA graph then follows a changed view selection),
+// else from the params
+__device__ __forceinline__ int view_of(const bmv_cost_volume_params& p, int s) {
+  return p.view_dev ? __ldg(p.view_dev + s) : p.view[s];
+}
+
 struct WarpTap {
   int off[4];     // element offsets (x,y part) of nw, ne, sw, se taps, clamped in-bounds
   float w[4];     // bilinear weights, 0 for out-of-bounds taps (padding_mode='zeros')
@@ -72,7 +78,7 @@ __device__ __forceinline__ uint32_t pack_out2<float>(float a, float b) { return 
 template <int S, typename OutT>
 __global__ void __launch_bounds__(256) cost_volume_var_kernel(bmv_cost_volume_params p) {
   __shared__ float sP[S * 12];
-  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[view_of(p, threadIdx.x / 12) * 12 + threadIdx.x % 12];
   __syncthreads();
   const int64_t nvox = (int64_t)p.D * p.h * p.w;
   const int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_kernel(bmv_cost_volume_pa
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     tap[s] = homography_taps(sP + s * 12, (float)x, (float)y, dep, p.Hs, p.Ws, p.feat_y_stride, p.feat_x_stride);
-    base[s] = p.feat + (int64_t)p.view[s] * p.feat_view_stride;
+    base[s] = p.feat + (int64_t)view_of(p, s) * p.feat_view_stride;
   }
   OutT* out = reinterpret_cast<OutT*>(p.out) + (int64_t)d * p.out_d_stride + (int64_t)y * p.out_y_stride +
               (int64_t)x * p.out_x_stride;
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_kernel(bmv_cost_volume_pa
 template <int S, int CPT, typename OutT>
 __global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume_params p, int CG) {
   __shared__ float sP[S * 12];
-  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[view_of(p, threadIdx.x / 12) * 12 + threadIdx.x % 12];
   __syncthreads();
   const int64_t nvox = (int64_t)p.D * p.h * p.w;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl_kernel(bmv_cost_volume
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const WarpTap t = homography_taps(sP + s * 12, (float)x, (float)y, dep, p.Hs, p.Ws, p.feat_y_stride, p.feat_x_stride);
-    const float* base = p.feat + (int64_t)p.view[s] * p.feat_view_stride + c0;
+    const float* base = p.feat + (int64_t)view_of(p, s) * p.feat_view_stride + c0;
     float v[CPT];
 #pragma unroll
     for (int q = 0; q < CPT; q += 4) {
@@ -227,7 +233,7 @@ __device__ __forceinline__ FastTap fast_taps(float ax, float ay, float az, const
 template <int S, int CPT, typename OutT>
 __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volume_params p, int CG, int DG) {
   __shared__ float sP[S * 12];
-  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[view_of(p, threadIdx.x / 12) * 12 + threadIdx.x % 12];
   __syncthreads();
   const int vpb = blockDim.x / CG;                       // voxels (consecutive x) per CTA
   const int x = blockIdx.x * vpb + (int)threadIdx.x / CG;
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volum
     ax[s] = dot3_gemm(P[0], P[1], P[2], fx, fy, 1.f);
     ay[s] = dot3_gemm(P[4], P[5], P[6], fx, fy, 1.f);
     az[s] = dot3_gemm(P[8], P[9], P[10], fx, fy, 1.f);
-    base[s] = p.feat + (int64_t)p.view[s] * p.feat_view_stride + c0;
+    base[s] = p.feat + (int64_t)view_of(p, s) * p.feat_view_stride + c0;
   }
   const float sx = 2.f / (float)(p.Ws - 1), sy = 2.f / (float)(p.Hs - 1);
   const int ys = (int)p.feat_y_stride, xs = (int)p.feat_x_stride;
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
   constexpr int TASKS = VW * S * PB;
   static_assert(TASKS <= 32, "tap tasks must fit one warp");
   __shared__ float sP[S * 12];
-  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[view_of(p, threadIdx.x / 12) * 12 + threadIdx.x % 12];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x_base = (blockIdx.x * 8 + warp) * VW;
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
   const bool active = x < p.w;
   const FeatT* base[S];
 #pragma unroll
-  for (int s = 0; s < S; ++s) base[s] = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)p.view[s] * p.feat_view_stride + c0;
+  for (int s = 0; s < S; ++s) base[s] = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)view_of(p, s) * p.feat_view_stride + c0;
   OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   constexpr float invS = 1.f / S;
   const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
@@ -407,7 +413,21 @@ __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_vol
   constexpr int VW = 32 / CG;                            // voxels per warp
   const int U = p.S, K = mp.K;
   __shared__ float sP[BMV_MAX_VIEWS * 12];
-  if (threadIdx.x < U * 12) sP[threadIdx.x] = p.proj[p.view[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  __shared__ int s_uview[BMV_MAX_VIEWS], s_mask[BMV_MAX_VIEWS];
+  if (threadIdx.x < U) {
+    int vw = p.view[threadIdx.x], mask = mp.chain_mask[threadIdx.x];
+    if (mp.triples_dev) {                                // unique view u IS source view u; masks from the device table
+      vw = threadIdx.x;
+      mask = 0;
+      for (int k = 0; k < K; ++k)
+        for (int j = 0; j < mp.views_per_chain; ++j)
+          if (__ldg(mp.triples_dev + k * mp.views_per_chain + j) == vw) mask |= 1 << k;
+    }
+    s_uview[threadIdx.x] = vw;
+    s_mask[threadIdx.x] = mask;
+  }
+  __syncthreads();
+  if (threadIdx.x < U * 12) sP[threadIdx.x] = p.proj[s_uview[threadIdx.x / 12] * 12 + threadIdx.x % 12];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x_base = (blockIdx.x * 8 + warp) * VW;
@@ -446,13 +466,14 @@ __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_vol
         const int o2 = __shfl_sync(0xffffffffu, t.off[2], src), o3 = __shfl_sync(0xffffffffu, t.off[3], src);
         const float w0 = __shfl_sync(0xffffffffu, t.w[0], src), w1 = __shfl_sync(0xffffffffu, t.w[1], src);
         const float w2 = __shfl_sync(0xffffffffu, t.w[2], src), w3 = __shfl_sync(0xffffffffu, t.w[3], src);
-        const FeatT* base = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)p.view[u] * p.feat_view_stride + c0;
+        const int mask = s_mask[u];
+        if (mask == 0) continue;                         // view in no chain (device-resident selection): uniform
+        const FeatT* base = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)s_uview[u] * p.feat_view_stride + c0;
         const float4 a = ld_feat4(base + o0), b = ld_feat4(base + o1), c = ld_feat4(base + o2), e = ld_feat4(base + o3);
         const float v0 = fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x)));
         const float v1 = fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y)));
         const float v2 = fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z)));
         const float v3 = fmaf(w3, e.w, fmaf(w2, c.w, fmaf(w1, b.w, w0 * a.w)));
-        const int mask = mp.chain_mask[u];
 #pragma unroll
         for (int k = 0; k < kMultiMaxK; ++k)
           if ((mask >> k) & 1) {                         // uniform

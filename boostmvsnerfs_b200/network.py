@@ -51,6 +51,8 @@ class EnerfNetwork(nn.Module):
         self.fused_mlp = True                  # K3+MLP in one kernel when the shape is instantiated
         self.half_feature_taps = False         # TF32-class path: the fused FPN step emits the level-1 maps in fp16 (8-byte taps in
                                                # K1: -25 us there, +22 us in the FPN kernel's half-sector stores: off by default)
+        self.multi_chain_render = True         # K3+K5 of all K chains in one persistent launch (render_multi.cu)
+        self._views_dev = None                 # int32 (K,3) device tensor of the frame's triples (set by FrameGraph)
         self.volume_range_scale = True         # fp16 cost volumes are stored x 2^k (ops.volume_scale), undone by conv0
         self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
@@ -300,7 +302,8 @@ class EnerfNetwork(nn.Module):
             if rc.render_if[i]:
                 nf_k = [nf[k] for k in range(K)] if nf.dim() == 4 else [nf] * K
                 states[i] = {'feat_vol': feat_vol, 'depth': [depth[k] for k in range(K)],
-                             'std': [std[k] for k in range(K)], 'nf': nf_k}
+                             'std': [std[k] for k in range(K)], 'nf': nf_k,
+                             'depth_all': depth, 'std_all': std, 'nf_all': nf}      # K-stacked (one-launch render)
         return states
 
     def _render_level(self, i, feats, inps, state, rays, cams, triples, Hh, Ww, ray_begin=0, n_rays=None):
@@ -343,6 +346,16 @@ class EnerfNetwork(nn.Module):
         if self.fused_mlp and rc.viewdir_agg and ops.render_rays_supported(Cv, Cf, V):
             engine = self.mlp_engine if (Cf == 8 and V == 3) else 'fma'
             packed = self._packed_mlp(i, engine)
+            if (engine == 'mma' and self.multi_chain_render and state.get('depth_all') is not None and rs == 1.
+                    and all(len(tr) == 3 for tr in triples) and ops.render_rays_multi_supported(feat_vol, im_feat, rgb, V)):
+                # every chain in ONE persistent launch (csrc/render_multi.cu); view ids from device memory when the
+                # caller (FrameGraph) supplies them
+                with self._stage(f'render_fused_l{i}'):
+                    ops.render_rays_multi(state['depth_all'], state['std_all'], state['nf_all'], rays, H, W, rc.depth_inv[i], S,
+                                          feat_vol, im_feat, rgb, cams, triples, packed, render_scale=rs, rgb_affine=affine,
+                                          ray_begin=ray_begin, n_rays=R, views_dev=self._views_dev,
+                                          out={'raw': raw_all, 'z_vals': z_all, 'vis_mask': mask_all})
+                return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
             with self._stage(f'render_fused_l{i}'):
                 for k in range(K):
                     ops.render_rays(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S, feat_vol[k], im_feat,

@@ -957,3 +957,84 @@ def frame_to_u8(rgb=None, depth=None):
         p.minmax_ord, p.minmax = scratch.data_ptr(), minmax.data_ptr()
     _lib.call("bmv_frame_to_u8", p, _stream())
     return rgb_u8, depth_u8, minmax
+
+
+# ------------------------------------------------------------------------------------------ K3+K5, all chains in one launch
+def render_rays_multi_supported(volumes, im_feat, rgb, V):
+    """Layouts bmv_render_rays_multi is instantiated for: (K,8,D,h,w) dense channels-last-3d volumes, (N,8,Hf,Wf)
+    dense channels-last feature maps, (N,3,Hf,Wf) colours viewed from an (N,Hf,Wf,4) tensor, triples."""
+    if not (V == 3 and volumes.dim() == 5 and volumes.shape[1] == 8 and im_feat.shape[1] == 8 and volumes.shape[0] <= MAX_VOLUMES):
+        return False
+    K, _, D, h, w = volumes.shape
+    N, _, Hf, Wf = im_feat.shape
+    return (volumes.dtype == torch.float32 and tuple(volumes.stride()[1:]) == (1, h * w * 8, w * 8, 8) and volumes.stride(0) % 4 == 0
+            and im_feat.dtype == torch.float32 and tuple(im_feat.stride()[1:]) == (1, Wf * 8, 8) and im_feat.stride(0) % 4 == 0
+            and rgb.dtype == torch.float32 and tuple(rgb.stride()[1:]) == (1, Wf * 4, 4) and rgb.stride(0) % 4 == 0
+            and N <= MAX_VIEWS and D * h * w * 8 < 2 ** 31 and Hf * Wf * 8 < 2 ** 31)
+
+
+def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, im_feat, rgb, cams, triples, packed_weights,
+                      render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False,
+                      views_dev=None):
+    """K3 + per-sample MLP of ALL K chains in one persistent launch (bmv_render_rays_multi).
+    depth, std (K,hv,wv); near_far (K,2,hv,wv) or shared (2,hv,wv); volumes (K,8,D,hv,wv) channels-last-3d; triples: K
+    view triples (host list) — or views_dev, an int32 CUDA tensor (K,3) read by the kernel (graph-replay friendly);
+    packed_weights from mlp_pack.pack_nerf_weights_mma.
+    Returns dict(raw (K,n,S,4), z_vals (K,n,S), vis_mask (K,n,S) [, vis_count]); `out` may supply them."""
+    depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
+    K, hv, wv = depth.shape
+    w = packed_weights
+    if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()
+            and w.numel() == _lib.load().bmv_render_rays_mma_weight_words()):
+        raise BmvError("render_rays_multi: weights must come from mlp_pack.pack_nerf_weights_mma")
+    if volumes.shape[0] != K or std.shape != depth.shape:
+        raise BmvError("render_rays_multi: depth / std / volumes must agree on K")
+    dev = depth.device
+    mp = _lib.RenderMultiParams()
+    p = mp.g
+    R, _keep = _bind_rays(p, rays)
+    n = R - ray_begin if n_rays is None else n_rays
+    assert 0 <= ray_begin and ray_begin + n <= R
+    p.hv, p.wv, p.H, p.W, p.depth_inv = hv, wv, H, W, int(depth_inv)
+    p.ray_begin, p.n_rays = ray_begin, n
+    t = _linspace(S, dev) if S > 1 else None
+    p.t, p.S = (t.data_ptr() if t is not None else 0), S
+    V = 3
+    _fill_fetch_inputs(p, volumes[0], im_feat, rgb, cams, (0, 0, 0), render_scale, rgb_affine, ())
+    mp.K, mp.n_views = K, im_feat.shape[0]
+    mp.depth, mp.depth_k_stride = depth.data_ptr(), depth.stride(0)
+    mp.std, mp.std_k_stride = std.data_ptr(), std.stride(0)
+    if near_far.dim() == 4:
+        if near_far.shape[0] != K:
+            raise BmvError("render_rays_multi: near_far must be (K,2,hv,wv) or (2,hv,wv)")
+        mp.near_far, mp.nf_k_stride = near_far.data_ptr(), near_far.stride(0)
+    else:
+        mp.near_far, mp.nf_k_stride = near_far.data_ptr(), 0
+    mp.volume, mp.vol_k_stride = volumes.data_ptr(), volumes.stride(0)
+    if views_dev is not None:
+        if not (views_dev.is_cuda and views_dev.dtype == torch.int32 and views_dev.is_contiguous() and views_dev.numel() == K * V):
+            raise BmvError("render_rays_multi: views_dev must be a contiguous int32 CUDA tensor with K*3 elements")
+        mp.views = views_dev.data_ptr()
+    else:
+        if len(triples) != K or any(len(tr) != V for tr in triples):
+            raise BmvError("render_rays_multi: need K view triples")
+        for i, v in enumerate(v for tr in triples for v in tr):
+            mp.views_host[i] = int(v)
+    res = dict(out) if out else {}
+
+    def mk(name, shape, dtype=torch.float32):
+        if name in res:
+            tns = res[name]
+            if not (tns.is_cuda and tns.dtype == dtype and tns.is_contiguous() and tns.numel() == _numel(shape)):
+                raise BmvError(f"preallocated output {name}: need contiguous {dtype} with {_numel(shape)} elements")
+        else:
+            res[name] = torch.empty(shape, device=dev, dtype=dtype)
+        return res[name].data_ptr()
+    mp.raw = mk("raw", (K, n, S, 4))
+    mp.z_vals = mk("z_vals", (K, n, S))
+    mp.vis_mask = mk("vis_mask", (K, n, S))
+    if want_count or "vis_count" in res:
+        mp.vis_count = mk("vis_count", (K, n, S), torch.int32)
+    mp.mlp_weights = w.data_ptr()
+    _lib.call("bmv_render_rays_multi", mp, _stream())
+    return res

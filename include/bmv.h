@@ -484,6 +484,33 @@ typedef struct bmv_fpn_stem_params {
 BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K3+K5 for ALL K cost-volume chains of a frame in one persistent launch (csrc/render_multi.cu): the per-chain loop of
+ * reference lib/networks/boost_enerf/network.py:212-222 (render_rays of chain k = 0..K-1) as one kernel.
+ * g: the fields shared by the chains — rays / ray_gen, ray_begin, n_rays, H, W, hv, wv, depth_inv, t, S, the volume
+ *    GEOMETRY (Cv, Dv, vol_*_stride), V, im_feat, rgb, cameras, render_scale; its depth / std / near_far / volume / view
+ *    and output pointers are ignored.
+ * Chain k reads depth + k*depth_k_stride (hv,wv), std likewise, near_far + k*nf_k_stride (2,hv,wv; stride 0 = shared),
+ * volume + k*vol_k_stride, and views[3k..3k+2] — DEVICE memory when `views` is set (a captured graph then follows a
+ * changed view selection by rewriting 3K ints), else views_host.  n_views = number of source views behind src_exts.
+ * Outputs are K-stacked: raw (K,n_rays,S,4), z_vals / vis_mask / vis_count (K,n_rays,S) (the last three optional).
+ * Requires Cv = Cf = 8, V = 3, dense channels-last volumes / feature maps, (N,Hf,Wf,4) colours, < 2^31 elements.
+ * mlp_weights: mlp_pack.pack_nerf_weights_mma (bmv_render_rays_mma_weight_words words).
+ */
+typedef struct bmv_render_multi_params {
+  bmv_raygen_fetch_params g;
+  int32_t K, n_views;
+  const float* depth; int64_t depth_k_stride;
+  const float* std; int64_t std_k_stride;
+  const float* near_far; int64_t nf_k_stride;
+  const float* volume; int64_t vol_k_stride;
+  const int32_t* views;                            /* DEVICE (K,3) or NULL */
+  int32_t views_host[BMV_MAX_VOLUMES * 3];
+  const uint32_t* mlp_weights;
+  float* raw; float* z_vals; float* vis_mask; int32_t* vis_count;
+} bmv_render_multi_params;
+BMV_API int bmv_render_rays_multi(const bmv_render_multi_params* p, bmv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * f4  output sinks: what the reference's evaluator / visualiser consume, produced on the device.
  * bmv_frame_psnr_accumulate: reference lib/evaluators/enerf.py:45-71 — pred / gt (H*W,3) fp32 row-major, optional
  *   mask (H*W) uint8 (pixel counted when mask >= 1), optional centre crop (rows [crop_h, H-crop_h), columns
