@@ -27,12 +27,12 @@ class CostVolumeParams(C.Structure):
                 ("out", C.c_void_p),
                 ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
                 ("out_bf16", i32), ("exact_coords", i32), ("feat_half", i32), ("reserved0", i32),
-                ("out_scale", C.c_void_p)]
+                ("out_scale", C.c_void_p), ("view_dev", C.c_void_p)]
 
 
 class CostVolumeMultiParams(C.Structure):
     _fields_ = [("b", CostVolumeParams), ("K", i32), ("views_per_chain", i32), ("chain_mask", i32 * MAX_VIEWS),
-                ("out_k_stride", i64)]
+                ("out_k_stride", i64), ("triples_dev", C.c_void_p)]
 
 
 class VolumeScaleParams(C.Structure):

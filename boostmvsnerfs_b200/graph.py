@@ -36,6 +36,7 @@ class FrameGraph:
         self._wtensors = None
 
     def _key(self, batch, triples):
+        """triples=None: the selection-agnostic key (graphs whose kernels read the view ids from device memory)."""
         """Everything a captured graph bakes in: shapes, the selected triples (kernel arguments), the weights (the graph
         holds pointers to PlanCache's folded copies and to the packed MLP / convolution weights, which are rebuilt when a
         parameter or buffer changes: same version-counter key as PlanCache) and the precision / kernel routing."""
@@ -45,7 +46,7 @@ class FrameGraph:
         # all keep the Parameter objects; code that REPLACES a Parameter object must call invalidate().
         if self._wtensors is None:
             self._wtensors = list(net.parameters()) + list(net.buffers())
-        return (tuple(batch["all_src_inps"].shape), tuple(triples), bool(net.generate_rays),
+        return (tuple(batch["all_src_inps"].shape), None if triples is None else tuple(triples), bool(net.generate_rays),
                 tuple(tuple(batch[f"rays_{i}"].shape) if f"rays_{i}" in batch else None for i in range(net.rc.num)),
                 tuple((t.data_ptr(), t._version) for t in self._wtensors), id(net._plans),
                 bool(torch.backends.cudnn.allow_tf32), bool(torch.backends.cuda.matmul.allow_tf32),
@@ -78,18 +79,23 @@ class FrameGraph:
         gen_dev = torch.zeros(rc.num * 12, device=dev, dtype=torch.float64)
         gen_host = torch.zeros(rc.num * 12, dtype=torch.float64).pin_memory()
         H, W = st["all_src_inps"].shape[-2:]
-        last_idx = torch.tensor(list(triples[-1]), device=dev, dtype=torch.long)
-        entry = {"static": st, "last_idx": last_idx, "cam_dev": cam_dev, "cam_host": cam_host, "gen_dev": gen_dev, "gen_host": gen_host,
+        K, I = len(triples), len(triples[0])
+        views_dev = torch.zeros((K, I), device=dev, dtype=torch.int32)
+        views_host = torch.zeros((K, I), dtype=torch.int32).pin_memory()
+        entry = {"static": st, "views_dev": views_dev, "views_host": views_host, "triples": None, "cam_dev": cam_dev, "cam_host": cam_host, "gen_dev": gen_dev, "gen_host": gen_host,
                  "graph": None, "out": None}
 
         def body():
+            net._views_dev = views_dev                      # kernels read the view ids from here (replayable across selections)
             gens = net._raygen_views(gen_dev, (H, W)) if gen_rays else None
             camera = net._camera_views(cam_dev, st["all_src_exts"][0], st["all_src_ixts"][0]) + (gens,)
             rays = [None] * rc.num if gen_rays else [st[f"rays_{i}"][0] for i in range(rc.num)]
             lv = net._render_frame(st["all_src_inps"][0], st["all_src_exts"][0], st["all_src_ixts"][0], st["tar_ext"][0],
                                    st["tar_ixt"][0], st["near_far"][0], rays, triples, camera=camera)
+            net._views_dev = None
             return net._assemble([lv])
 
+        self._load_views(entry, triples)
         self._load(entry, batch)
         entry["cam_loaded"] = False                     # the first real call always loads its own cameras
         side = torch.cuda.Stream(device=dev)
@@ -99,17 +105,35 @@ class FrameGraph:
                 body()
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g), torch.no_grad():
-            entry["out"] = body()
+        net._baked_views = False
+        try:
+            with torch.cuda.graph(g), torch.no_grad():
+                entry["out"] = body()
+        finally:
+            net._views_dev = None
         entry["graph"] = g
+        # every launch read its view ids from views_dev: the graph serves ANY selection of K triples of this shape
+        entry["agnostic"] = not net._baked_views
         return entry
+
+    def _load_views(self, entry, triples):
+        """Upload the frame's triples (K x 3 ints) when they changed; pinned staging buffer guarded by an event."""
+        if entry["triples"] == triples:
+            return
+        if "views_ev" in entry:
+            entry["views_ev"].synchronize()
+        entry["views_host"].copy_(torch.tensor(triples, dtype=torch.int32))
+        entry["views_dev"].copy_(entry["views_host"], non_blocking=True)
+        entry.setdefault("views_ev", torch.cuda.Event()).record()
+        entry["triples"] = list(triples)
 
     def prefetch(self, batch):
         """Start uploading the NEXT frame's host batch on a copy stream while the current frame renders.
         The following __call__ with the same batch object only does a device-to-device copy of the staged
         tensors before the replay.  No-op until the graph for this batch signature exists."""
-        triples = self._triples(batch)
-        entry = self._cache.get(self._key(batch, triples))
+        entry = self._cache.get(self._key(batch, None))
+        if entry is None:
+            entry = self._cache.get(self._key(batch, self._triples(batch)))
         if entry is None:
             return
         if "stage" not in entry:
@@ -203,17 +227,22 @@ class FrameGraph:
         if batch["all_src_inps"].shape[0] != 1:
             raise ValueError("FrameGraph renders one frame (B=1) per call")
         triples = self._triples(batch)
-        key = self._key(batch, triples)
+        key = self._key(batch, None)                         # selection-agnostic graph first
         entry = self._cache.get(key)
+        if entry is None:
+            key = self._key(batch, triples)
+            entry = self._cache.get(key)
         if entry is None:
             while len(self._cache) >= max(1, self.max_entries):
                 self._cache.popitem(last=False)              # least recently used graph + its static buffers
             self._wtensors = None                            # re-collect the weight tensors with every capture
-            key = self._key(batch, triples)
-            entry = self._cache[key] = self._build(batch, triples)
+            entry = self._build(batch, triples)
+            key = self._key(batch, None if entry["agnostic"] else triples)
+            self._cache[key] = entry
             cameras_unchanged = False
         else:
             self._cache.move_to_end(key)
+        self._load_views(entry, triples)
         self._load(entry, batch, cameras_unchanged)
         entry["graph"].replay()
         # the reference leaves the LAST triple's views in the batch (evaluators read batch['src_inps'].shape;
@@ -222,6 +251,7 @@ class FrameGraph:
         # copies, so the next call's upload does not change them.
         # (index_select with a device-resident index: indexing with a Python list uploads the indices with a blocking
         # copy, i.e. one host sync per frame)
+        last_idx = entry["views_dev"][-1].long()
         for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts")):
-            batch[dst] = entry["static"][src].index_select(1, entry["last_idx"])
+            batch[dst] = entry["static"][src].index_select(1, last_idx)
         return entry["out"]

@@ -208,7 +208,10 @@ class MergedHeadsCostReg(nn.Module):
                 feat = ops.conv3d_k3(y, pk['heads'], None, 9, relu=False, out2=logits, split=8)
             return feat, logits[:, 0]
         out = self.heads(y)
-        return out[:, :8], out[:, 8]
+        feat = out[:, :8]
+        if out.stride(1) == 1:       # channels-last: 32-byte voxels (what the one-launch render kernel fetches from)
+            feat = feat.contiguous(memory_format=torch.channels_last_3d)
+        return feat, out[:, 8]
 
 
 class FusedTopDownFPN(nn.Module):

@@ -53,6 +53,8 @@ class EnerfNetwork(nn.Module):
                                                # K1: -25 us there, +22 us in the FPN kernel's half-sector stores: off by default)
         self.multi_chain_render = True         # K3+K5 of all K chains in one persistent launch (render_multi.cu)
         self._views_dev = None                 # int32 (K,3) device tensor of the frame's triples (set by FrameGraph)
+        self._baked_views = False              # set when a launch took its view ids from the host (graph not re-usable
+                                               # for another view selection)
         self.volume_range_scale = True         # fp16 cost volumes are stored x 2^k (ops.volume_scale), undone by conv0
         self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
@@ -274,21 +276,25 @@ class EnerfNetwork(nn.Module):
                     nf = nf0                               # shared (2,h,w)
                     # the chains share the hypotheses and draw their views from the same N maps: warp every unique
                     # view once per group of <= 4 chains and feed all the variances it belongs to
+                    vdev = self._views_dev                 # (K,3) int32 on the device, or None
                     for k0 in range(0, K, 4):
                         grp = triples[k0:k0 + 4]
-                        uniq = {int(v) for t in grp for v in t}
+                        uniq = set(range(f.shape[0])) if vdev is not None else {int(v) for t in grp for v in t}
                         if (self.channels_last and self.multi_chain_volume and f.stride(1) == 1 and len(grp) > 1
                                 and len({len(t) for t in grp}) == 1 and all(len(set(t)) == len(t) for t in grp)
                                 and ops.cost_volume_multi_supported(C, len(uniq), len(grp))):
                             ops.cost_volume_var_shared_multi(f, grp, projs[i], planes0, h, w, out=vols[k0:k0 + len(grp)],
-                                                             out_scale=vsc)
+                                                             out_scale=vsc,
+                                                             triples_dev=None if vdev is None else vdev[k0:k0 + len(grp)])
                         else:
                             for k in range(k0, k0 + len(grp)):
-                                ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k], out_scale=vsc)
+                                ops.cost_volume_var_shared(f, triples[k], projs[i], planes0, h, w, out=vols[k], out_scale=vsc,
+                                                           views_dev=None if vdev is None else vdev[k])
                 else:                                      # all K chains' hypotheses in one launch
                     planes, nf = ops.depth_planes_next_batched(depth, std, nf, D, h, w, rc.depth_inv[i])
                     for k in range(K):                     # (f may be fp16: half_feature_taps)
-                        ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k], out_scale=vsc)
+                        ops.cost_volume_var(f, triples[k], projs[i], planes[k], out=vols[k], out_scale=vsc,
+                                            views_dev=None if self._views_dev is None else self._views_dev[k])
             with self._stage(f'cost_reg_{i}'):
                 feat_vol, logits = plan(vols, in_scale=vsc[4:6]) if vsc is not None else plan(vols)
                 del vols
@@ -356,6 +362,7 @@ class EnerfNetwork(nn.Module):
                                           ray_begin=ray_begin, n_rays=R, views_dev=self._views_dev,
                                           out={'raw': raw_all, 'z_vals': z_all, 'vis_mask': mask_all})
                 return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
+            self._baked_views = True               # the per-chain launches carry their view ids as kernel arguments
             with self._stage(f'render_fused_l{i}'):
                 for k in range(K):
                     ops.render_rays(depth[k], std[k], nf[k], rays, H, W, rc.depth_inv[i], S, feat_vol[k], im_feat,
@@ -363,6 +370,7 @@ class EnerfNetwork(nn.Module):
                                     ray_begin=ray_begin, n_rays=R, engine=engine,
                                     out={'raw': raw_all[k], 'z_vals': z_all[k], 'vis_mask': mask_all[k]})
             return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
+        self._baked_views = True
         for r0 in range(0, R, rc.chunk_size):
             n = min(rc.chunk_size, R - r0)
             vox = torch.empty((K, n * S, Cv), device=dev)

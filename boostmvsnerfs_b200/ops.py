@@ -94,8 +94,16 @@ def _scale_ptr(t):
     return t.data_ptr()
 
 
+def _views_dev_ptr(t, n):
+    if t is None:
+        return 0
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and t.numel() == n):
+        raise BmvError(f"views_dev: expected a contiguous int32 CUDA tensor with {n} elements")
+    return t.data_ptr()
+
+
 def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float32, channels_last=False,
-                    exact_coords=False, out_scale=None):
+                    exact_coords=False, out_scale=None, views_dev=None):
     """Fused plane-sweep cost volume for ONE batch element.
 
     feats  (N,C,Hs,Ws) feature maps of all views, any strides (NCHW or channels_last)
@@ -126,11 +134,12 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
     p.D, p.h, p.w = D, h, w
     p.exact_coords = int(exact_coords)
     p.out_scale = _scale_ptr(out_scale)
+    p.view_dev = _views_dev_ptr(views_dev, S)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
 def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dtype=torch.float32,
-                           channels_last=False, exact_coords=False, out_scale=None):
+                           channels_last=False, exact_coords=False, out_scale=None, views_dev=None):
     """Same as cost_volume_var with D hypotheses shared by every pixel (cascade level 0)."""
     feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
@@ -149,10 +158,11 @@ def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dty
     p.D, p.h, p.w = D, h, w
     p.exact_coords = int(exact_coords)
     p.out_scale = _scale_ptr(out_scale)
+    p.view_dev = _views_dev_ptr(views_dev, S)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
-def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_scale=None):
+def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_scale=None, triples_dev=None):
     """The K level-0 cost volumes (shared depth hypotheses) in one launch: every unique source view is warped once
     per (voxel, plane) and feeds the variance of each chain it belongs to (bmv_cost_volume_var_multi).
     feats (N,C,Hs,Ws) channels-last, triples: K lists of view ids (equal lengths), out (K,C,D,h,w) with
@@ -164,7 +174,8 @@ def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_
     K, S = len(triples), len(triples[0])
     if any(len(t) != S for t in triples):
         raise BmvError("cost_volume_var_shared_multi: every chain needs the same number of views")
-    uniq = sorted({int(v) for t in triples for v in t})
+    # device-resident selection: every source view is a "unique view", the kernel derives the chain masks
+    uniq = list(range(N)) if triples_dev is not None else sorted({int(v) for t in triples for v in t})
     D = planes_d.numel()
     if out.shape != (K, Cc, D, h, w) or out.stride(1) != 1:
         raise BmvError("cost_volume_var_shared_multi: out must be (K,C,D,h,w) with channels-last-3d volumes")
@@ -184,6 +195,7 @@ def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_
     p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride(1), out.stride(2), out.stride(3), out.stride(4)
     p.out_bf16 = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out.dtype]
     mp.K, mp.views_per_chain, mp.out_k_stride = K, S, out.stride(0)
+    mp.triples_dev = _views_dev_ptr(triples_dev, K * S)
     for i, u in enumerate(uniq):
         mp.chain_mask[i] = sum(1 << k for k, t in enumerate(triples) if u in [int(v) for v in t])
     _lib.call("bmv_cost_volume_var_multi", mp, _stream())

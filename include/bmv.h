@@ -89,6 +89,8 @@ typedef struct bmv_cost_volume_params {
   const float* out_scale;       /* DEVICE or NULL: every stored variance is multiplied by out_scale[0] (a power of two from
                                    bmv_volume_scale): keeps an fp16 volume inside the fp16 range whatever the feature
                                    magnitude; the consuming convolution undoes it (bmv_conv3d_params.in_scale) */
+  const int32_t* view_dev;      /* DEVICE or NULL: S view ids read by the kernel instead of view[] — a captured CUDA graph
+                                   then follows a changed view selection by rewriting S ints (channels-last fast paths) */
 } bmv_cost_volume_params;
 BMV_API int bmv_cost_volume_var(const bmv_cost_volume_params* p, bmv_stream_t stream);
 
@@ -118,6 +120,9 @@ typedef struct bmv_cost_volume_multi_params {
   int32_t K, views_per_chain;
   int32_t chain_mask[BMV_MAX_VIEWS];
   int64_t out_k_stride;
+  const int32_t* triples_dev;   /* DEVICE (K, views_per_chain) or NULL.  When set: b.S = the number of source views N,
+                                   "unique view" u IS source view u (b.view / chain_mask ignored) and the chain masks are
+                                   derived in the kernel from this table; views used by no chain are skipped. */
 } bmv_cost_volume_multi_params;
 BMV_API int bmv_cost_volume_var_multi(const bmv_cost_volume_multi_params* p, bmv_stream_t stream);
 

@@ -312,3 +312,34 @@ def test_frame_graph_follows_weights_and_flags(strict_fp32):
     back = fg(dict(batch))
     for k in first:
         _report(back[k], first[k].cpu().numpy(), f"weights restored {k}", 1e-6)
+
+
+def test_frame_graph_is_selection_agnostic(strict_fp32):
+    """The kernels read the view ids of the K triples from device memory, so ONE captured graph renders frames whose
+    view selection differs (a 64-view sequence does not re-capture per view): same results as eager for every selection,
+    one cache entry, batch['src_*'] follows the frame's last triple."""
+    from boostmvsnerfs_b200 import network
+    from boostmvsnerfs_b200.graph import FrameGraph
+    from boostmvsnerfs_b200.synth import make_scene, batch_to
+    torch.manual_seed(0)
+    net = network.BoostEnerfNetwork(preprocess=True, rc=RenderConfig.enerf_eval(3)).eval().cuda()
+    fg = FrameGraph(net)
+    scene = make_scene(H=64, W=96, n_views=5, seed=4, smooth=True)
+    table = network._combinations(5, 3)
+    for sel in ([0, 4, 9], [9, 4, 0], [2, 3, 7], [1, 5, 8]):
+        net.view_selection_outputs = {"synth_0": sel}
+        want = {k: v.clone() for k, v in net(batch_to(scene, "cuda")).items()}
+        b = batch_to(scene, "cuda")
+        got = fg(b)
+        for k in want:
+            _report(got[k], want[k].cpu().numpy(), f"selection {sel} {k}", 1e-6)
+        assert torch.equal(b["src_exts"], b["all_src_exts"][:, list(table[sel[-1]])])
+    assert len(fg._cache) == 1 and next(iter(fg._cache.values()))["agnostic"]
+    net.multi_chain_render = False                 # per-chain launches bake their view ids: one graph per selection again
+    for sel in ([0, 4, 9], [2, 3, 7]):
+        net.view_selection_outputs = {"synth_0": sel}
+        want = {k: v.clone() for k, v in net(batch_to(scene, "cuda")).items()}
+        got = fg(batch_to(scene, "cuda"))
+        for k in want:
+            _report(got[k], want[k].cpu().numpy(), f"baked selection {sel} {k}", 1e-6)
+    assert len(fg._cache) == 3
