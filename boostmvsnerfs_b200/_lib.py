@@ -115,7 +115,7 @@ class RenderMultiParams(C.Structure):
                 ("near_far", C.c_void_p), ("nf_k_stride", i64), ("volume", C.c_void_p), ("vol_k_stride", i64),
                 ("views", C.c_void_p), ("views_host", i32 * (MAX_VOLUMES * 3)),
                 ("mlp_weights", C.c_void_p), ("raw", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p),
-                ("vis_count", C.c_void_p)]
+                ("vis_count", C.c_void_p), ("vol_row0", i32), ("map_row0", i32), ("nf_plane_stride", i64)]
 
 
 class CostVolumeImgParams(C.Structure):
@@ -135,6 +135,10 @@ class MvsMarchParams(C.Structure):
                 ("vol_c_stride", i64), ("vol_d_stride", i64), ("vol_y_stride", i64), ("vol_x_stride", i64),
                 ("rgb", C.c_void_p), ("rgb_scale", f32), ("rgb_shift", f32),
                 ("mlp_in", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
+
+
+class MvsRenderParams(C.Structure):
+    _fields_ = [("g", MvsMarchParams), ("weights", C.c_void_p), ("raw", C.c_void_p)]
 
 
 class FpnTopdownParams(C.Structure):
@@ -203,6 +207,7 @@ ENTRY_POINTS = {
     "bmv_render_rays_multi": RenderMultiParams,
     "bmv_cost_volume_var_img": CostVolumeImgParams,
     "bmv_mvs_march_fetch": MvsMarchParams,
+    "bmv_mvs_render_umma": MvsRenderParams,
     "bmv_fpn_topdown": FpnTopdownParams,
     "bmv_conv3d_k3": Conv3dParams,
     "bmv_conv3d_k3_umma": Conv3dParams,
@@ -216,7 +221,7 @@ PLAIN_SYMBOLS = ("bmv_version", "bmv_last_error_string", "bmv_launch_count", "bm
                  "bmv_nerf_mlp_weight_count", "bmv_render_rays_supported", "bmv_render_rays_mma_weight_words",
                  "bmv_render_rays_umma_weight_words", "bmv_umma_selftest",
                  "bmv_conv3d_k3_weight_words", "bmv_conv3d_k3_umma_weight_words", "bmv_conv3d_k3_last_used_tma", "bmv_convT3d_k3s2_weight_words",
-                 "bmv_fpn_topdown_smooth_weight_words")
+                 "bmv_fpn_topdown_smooth_weight_words", "bmv_mvs_render_umma_weight_bytes")
 
 _lib = None
 
@@ -254,6 +259,7 @@ def load():
     lib.bmv_convT3d_k3s2_weight_words.argtypes = [C.c_int, C.c_int]
     lib.bmv_fpn_topdown_smooth_weight_words.restype = C.c_int
     lib.bmv_fpn_topdown_smooth_weight_words.argtypes = [C.c_int]
+    lib.bmv_mvs_render_umma_weight_bytes.restype = C.c_int
     lib.bmv_sizeof_params.restype = C.c_int
     lib.bmv_sizeof_params.argtypes = [C.c_char_p]
     for name, struct in ENTRY_POINTS.items():

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kRmWarps * 32, 1) render_multi_kernel(bmv_rend
   c.r_wf = frcp(c.wf1); c.r_hf = frcp(c.hf1);
   c.wv1 = (float)(p.wv - 1); c.hv1 = (float)(p.hv - 1); c.dv1 = (float)(p.Dv - 1);
   c.up_sy = up_scale(p.hv, p.H); c.up_sx = up_scale(p.wv, p.W);
-  c.hwv = p.hv * p.wv;
+  c.hwv = mp.nf_plane_stride ? (int)mp.nf_plane_stride : p.hv * p.wv;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(kRmWarps * 32, 1) render_multi_kernel(bmv_rend
   const int vsx = (int)p.vol_x_stride, vsy = (int)p.vol_y_stride, vsd = (int)p.vol_d_stride;
   const float rgb_sc = p.rgb_scale, rgb_sf = p.rgb_shift;
   const bool unit_scale = p.render_scale == 1.f;
+  const int vol_row0 = mp.vol_row0, map_row0 = mp.map_row0;
 
   // Warps free-run over the work units (gathers are LSU-bound, the MLP is tensor / issue bound: they overlap).
   for (uint32_t u = blockIdx.x * kRmWarps + warp; u < total; u += gridDim.x * kRmWarps) {
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(kRmWarps * 32, 1) render_multi_kernel(bmv_rend
       float rn, rf, nf0, nf1;
       {
         const UpCoord uy = up_coord_scaled(py, hv, c.up_sy), ux = up_coord_scaled(px, wv, c.up_sx);
-        const int o00 = uy.i0 * wv + ux.i0, o01 = uy.i0 * wv + ux.i1, o10 = uy.i1 * wv + ux.i0, o11 = uy.i1 * wv + ux.i1;
+        const int r0 = (uy.i0 - map_row0) * wv, r1 = (uy.i1 - map_row0) * wv;    // rows relative to the slab
+        const int o00 = r0 + ux.i0, o01 = r0 + ux.i1, o10 = r1 + ux.i0, o11 = r1 + ux.i1;
         auto up = [&](const float* m) {
           const float a = __ldg(m + o00), b = __ldg(m + o01), cc = __ldg(m + o10), d = __ldg(m + o11);
           const float top = add_rn(mul_rn(ux.l0, a), mul_rn(ux.l1, b));
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kRmWarps * 32, 1) render_multi_kernel(bmv_rend
         const int xi = (int)xc, yi = (int)yc, zi = (int)zc;
         const int ox1 = (vx1 && vx0) ? vsx : 0, oy1 = (vy1 && vy0) ? vsy : 0, oz1 = (vz1 && vz0) ? vsd : 0;
         // when only the HIGH corner of an axis is valid (x0 = -1) the clamped index already is that corner
-        const float* b000 = vol_k + (zi * vsd + yi * vsy + xi * vsx);
+        const float* b000 = vol_k + (zi * vsd + (yi - vol_row0) * vsy + xi * vsx);
         float vox[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) vox[q] = 0.f;
@@ -381,13 +383,16 @@ extern "C" BMV_API int bmv_render_rays_multi(const bmv_render_multi_params* mp, 
               "bmv_render_rays_multi: (Cv=%d, Cf=%d, V=%d) not instantiated (8, 8, 3)", p->Cv, p->Cf, p->V);
   // dense channels-last layouts, 32-bit offsets
   BMV_REQUIRE(p->vol_c_stride == 1 && p->vol_x_stride == 8 && p->vol_y_stride == (int64_t)p->wv * 8 &&
-                  p->vol_d_stride == (int64_t)p->hv * p->wv * 8 && mp->vol_k_stride % 4 == 0,
-              BMV_ERR_UNSUPPORTED_SHAPE, "bmv_render_rays_multi: the volumes must be dense (D,h,w,8) channels-last");
+                  p->vol_d_stride % 4 == 0 && p->vol_d_stride > 0 && p->vol_d_stride <= (int64_t)p->hv * p->wv * 8 &&
+                  mp->vol_k_stride % 4 == 0,
+              BMV_ERR_UNSUPPORTED_SHAPE, "bmv_render_rays_multi: the volumes must be (D,rows,w,8) channels-last with dense rows");
+  BMV_REQUIRE(mp->vol_row0 >= 0 && mp->vol_row0 < p->hv && mp->map_row0 >= 0 && mp->map_row0 < p->hv && mp->nf_plane_stride >= 0,
+              BMV_ERR_INVALID_ARGUMENT, "bmv_render_rays_multi: bad slab rows");
   BMV_REQUIRE(p->imf_c_stride == 1 && p->imf_x_stride == 8 && p->imf_y_stride == (int64_t)p->Wf * 8 && p->imf_view_stride % 4 == 0,
               BMV_ERR_UNSUPPORTED_SHAPE, "bmv_render_rays_multi: im_feat must be dense (N,Hf,Wf,8) channels-last");
   BMV_REQUIRE(p->rgb_c_stride == 1 && p->rgb_x_stride == 4 && p->rgb_y_stride == (int64_t)p->Wf * 4 && p->rgb_view_stride % 4 == 0,
               BMV_ERR_UNSUPPORTED_SHAPE, "bmv_render_rays_multi: rgb must be dense (N,Hf,Wf,4)");
-  BMV_REQUIRE((int64_t)p->Dv * p->hv * p->wv * 8 < (1ll << 31) && (int64_t)p->Hf * p->Wf * 8 < (1ll << 31) &&
+  BMV_REQUIRE((int64_t)p->Dv * p->vol_d_stride < (1ll << 31) && (int64_t)p->Hf * p->Wf * 8 < (1ll << 31) &&
                   p->n_rays * p->S < (1ll << 31) && p->ray_begin + p->n_rays < (1ll << 31),
               BMV_ERR_UNSUPPORTED_SHAPE, "bmv_render_rays_multi: tensors too large for 32-bit offsets");
   for (int i = 0; !mp->views && i < mp->K * 3; ++i)

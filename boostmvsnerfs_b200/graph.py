@@ -27,13 +27,16 @@ class FrameGraph:
     used entries are dropped, so a sequence whose selected triples change from view to view cannot grow without
     bound."""
 
-    def __init__(self, net: BoostEnerfNetwork, max_entries=8):
+    def __init__(self, net: BoostEnerfNetwork, max_entries=8, frame_fn=None):
         if not isinstance(net, BoostEnerfNetwork):
             raise TypeError("FrameGraph wraps a BoostEnerfNetwork")
         self.net = net
         self.max_entries = int(max_entries)
         self._cache = OrderedDict()
         self._wtensors = None
+        # frame_fn(static_inputs, camera, rays, triples, views_dev) -> output dict replaces the single-GPU frame body
+        # (dist.make_sharded_graph: the multi-GPU frame with its NCCL collectives inside the captured graph)
+        self.frame_fn = frame_fn
 
     def _key(self, batch, triples):
         """triples=None: the selection-agnostic key (graphs whose kernels read the view ids from device memory)."""
@@ -56,6 +59,16 @@ class FrameGraph:
         """Drop every captured graph (after editing `param.data` directly, which bypasses the version counters)."""
         self._cache.clear()
         self._wtensors = None
+
+    def close(self):
+        """Release the captured graphs NOW.  Required before torch.distributed.destroy_process_group() when the graphs
+        hold NCCL collectives (dist.make_sharded_graph): tearing the communicator down under a live graph hangs."""
+        import gc
+        self.invalidate()
+        self.__dict__.pop("_rb", None)
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def _triples(self, batch):
         net, rc = self.net, self.net.rc
@@ -90,6 +103,11 @@ class FrameGraph:
             gens = net._raygen_views(gen_dev, (H, W)) if gen_rays else None
             camera = net._camera_views(cam_dev, st["all_src_exts"][0], st["all_src_ixts"][0]) + (gens,)
             rays = [None] * rc.num if gen_rays else [st[f"rays_{i}"][0] for i in range(rc.num)]
+            if self.frame_fn is not None:
+                try:
+                    return self.frame_fn(st, camera, rays, triples, views_dev)
+                finally:
+                    net._views_dev = None
             lv = net._render_frame(st["all_src_inps"][0], st["all_src_exts"][0], st["all_src_ixts"][0], st["tar_ext"][0],
                                    st["tar_ixt"][0], st["near_far"][0], rays, triples, camera=camera)
             net._views_dev = None

@@ -356,3 +356,54 @@ def pack_conv2d_k3_c8(weight):
         for e in range(2):
             out[:, :, :, r, e] = B[:, :, 2 * t + 8 * r + e, g]
     return out.reshape(-1).view(torch.int32).to(weight.device)
+
+
+# ------------------------------------------------------------------------------------------ MVSNeRF MLP (csrc/mvs_render_umma.cu)
+def _umma_b(w_pad):
+    """(N, K) fp32 -> fp16 (K/8, N, 8): the K-major SWIZZLE_NONE B operand (SBO 128 B, LBO N*16 B), flattened."""
+    N, K = w_pad.shape
+    assert K % 16 == 0 and N % 8 == 0
+    return w_pad.half().reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def pack_mvs_weights_umma(mlp):
+    """RendererOurs (modules_mvs.py; reference lib/networks/mvsnerf/network.py:152-229) -> the byte buffer
+    bmv_mvs_render_umma streams: 16 weight panels in issue order, the bias K-steps of L1..L4 and the feature layer, the
+    fp32 vectors of the CUDA-core heads.  Biases of the other layers sit in the column that multiplies the operands'
+    constant 1 (pts col 63, feats col 20, views col 3)."""
+    n = mlp.nerf if hasattr(mlp, 'nerf') else mlp
+    f32 = lambda t: t.detach().float().cpu()
+    W = [f32(l.weight) for l in n.pts_linears]
+    B = [f32(l.bias) for l in n.pts_linears]
+    if n.in_pts != 63 or n.in_feat != 20 or n.in_views != 3 or W[1].shape != (128, 128) or tuple(n.skips) != (4,) or len(W) != 6:
+        raise ValueError("pack_mvs_weights_umma: instantiated for D=6, W=128, in_pts=63, in_feat=20, in_views=3, skips=(4,)")
+    panels = []
+    wg = torch.zeros(128, 32); wg[:, :20] = f32(n.pts_bias.weight); wg[:, 20] = f32(n.pts_bias.bias)
+    panels.append(_umma_b(wg))
+    w0 = torch.zeros(128, 64); w0[:, :63] = W[0]; w0[:, 63] = B[0]
+    panels.append(_umma_b(w0))
+    for i in range(1, 5):
+        panels += [_umma_b(W[i][:, :64].contiguous()), _umma_b(W[i][:, 64:].contiguous())]
+    w5p = torch.zeros(128, 64); w5p[:, :63] = W[5][:, :63]; w5p[:, 63] = B[5]
+    panels.append(_umma_b(w5p))
+    w5h = W[5][:, 63:]
+    panels += [_umma_b(w5h[:, :64].contiguous()), _umma_b(w5h[:, 64:].contiguous())]
+    wf = f32(n.feature_linear.weight)
+    panels += [_umma_b(wf[:, :64].contiguous()), _umma_b(wf[:, 64:].contiguous())]
+    wv = torch.zeros(64, 144)
+    vw = f32(n.views_linears[0].weight)                     # (64, 128 + 3): [feature | views]
+    wv[:, :128] = vw[:, :128]; wv[:, 128:131] = vw[:, 128:131]; wv[:, 131] = f32(n.views_linears[0].bias)
+    panels.append(_umma_b(wv))
+    biases = []
+    for b in (B[1], B[2], B[3], B[4], f32(n.feature_linear.bias)):
+        m = torch.zeros(128, 16); m[:, 4] = b                # K index 4 of the step = feats column 20 (the constant 1)
+        biases.append(_umma_b(m))
+    vec = torch.zeros(328)
+    vec[0:128] = f32(n.alpha_linear.weight).reshape(-1)
+    vec[128:320] = f32(n.rgb_linear.weight).reshape(-1)
+    vec[320] = f32(n.alpha_linear.bias)[0]
+    vec[321:324] = f32(n.rgb_linear.bias)
+    half = torch.cat(panels + biases)
+    assert half.numel() * 2 == 256000 + 5 * 4096, half.numel()
+    packed = torch.cat([half.view(torch.int32), vec.view(torch.int32)])
+    return packed.to(next(n.parameters()).device)

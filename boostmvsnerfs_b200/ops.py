@@ -985,16 +985,29 @@ def render_rays_multi_supported(volumes, im_feat, rgb, V):
             and N <= MAX_VIEWS and D * h * w * 8 < 2 ** 31 and Hf * Wf * 8 < 2 ** 31)
 
 
+def _rows_f32(t, name):
+    """CUDA fp32 tensor whose trailing (rows, w) block is contiguous (any leading strides: slices of a stacked buffer)."""
+    _f32(t, name)
+    if t.stride(-1) != 1 or t.stride(-2) != t.shape[-1]:
+        t = t.contiguous()
+    return t
+
+
 def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, im_feat, rgb, cams, triples, packed_weights,
                       render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False,
-                      views_dev=None):
+                      views_dev=None, grid_rows=None, vol_row0=0, map_row0=0):
     """K3 + per-sample MLP of ALL K chains in one persistent launch (bmv_render_rays_multi).
     depth, std (K,hv,wv); near_far (K,2,hv,wv) or shared (2,hv,wv); volumes (K,8,D,hv,wv) channels-last-3d; triples: K
     view triples (host list) — or views_dev, an int32 CUDA tensor (K,3) read by the kernel (graph-replay friendly);
     packed_weights from mlp_pack.pack_nerf_weights_mma.
+    Row slabs (multi-GPU row tiles): depth / std / near_far hold map rows [map_row0, map_row0 + rows) and volumes volume
+    rows [vol_row0, ...) of a grid with `grid_rows` rows; the rays of [ray_begin, ray_begin + n_rays) must only touch them.
     Returns dict(raw (K,n,S,4), z_vals (K,n,S), vis_mask (K,n,S) [, vis_count]); `out` may supply them."""
-    depth, std, near_far = _cf32(depth, "depth"), _cf32(std, "std"), _cf32(near_far, "near_far")
-    K, hv, wv = depth.shape
+    depth, std, near_far = _rows_f32(depth, "depth"), _rows_f32(std, "std"), _rows_f32(near_far, "near_far")
+    K, map_rows, wv = depth.shape
+    hv = map_rows if grid_rows is None else int(grid_rows)
+    if std.shape != depth.shape or near_far.shape[-2:] != depth.shape[-2:]:
+        raise BmvError("render_rays_multi: depth / std / near_far must cover the same rows")
     w = packed_weights
     if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()
             and w.numel() == _lib.load().bmv_render_rays_mma_weight_words()):
@@ -1019,9 +1032,10 @@ def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, i
     if near_far.dim() == 4:
         if near_far.shape[0] != K:
             raise BmvError("render_rays_multi: near_far must be (K,2,hv,wv) or (2,hv,wv)")
-        mp.near_far, mp.nf_k_stride = near_far.data_ptr(), near_far.stride(0)
+        mp.near_far, mp.nf_k_stride, mp.nf_plane_stride = near_far.data_ptr(), near_far.stride(0), near_far.stride(1)
     else:
-        mp.near_far, mp.nf_k_stride = near_far.data_ptr(), 0
+        mp.near_far, mp.nf_k_stride, mp.nf_plane_stride = near_far.data_ptr(), 0, near_far.stride(0)
+    mp.vol_row0, mp.map_row0 = int(vol_row0), int(map_row0)
     mp.volume, mp.vol_k_stride = volumes.data_ptr(), volumes.stride(0)
     if views_dev is not None:
         if not (views_dev.is_cuda and views_dev.dtype == torch.int32 and views_dev.is_contiguous() and views_dev.numel() == K * V):

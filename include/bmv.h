@@ -367,6 +367,20 @@ typedef struct bmv_mvs_march_params {
 } bmv_mvs_march_params;
 BMV_API int bmv_mvs_march_fetch(const bmv_mvs_march_params* p, bmv_stream_t stream);
 
+/* K3b fused with the 6x128 MLP of the MVSNeRF backbone (reference lib/networks/mvsnerf/network.py:152-229 Renderer_ours,
+ * :945-1001 marcher, lib/networks/mvsnerf/renderer.py:111-137 feature assembly) on tcgen05 tensor cores: the
+ * (n_rays, S, 86) MLP input of bmv_mvs_march_fetch is never materialised.  g as for bmv_mvs_march_fetch (mlp_in ignored;
+ * z_vals / vis_mask / vis_count optional); raw (n_rays, S, 4) = [sigmoid rgb (3), relu alpha (1)].
+ * fp16 operands, fp32 accumulation, one MMA per product: TF32-class (BASELINE config 3, 1e-2).
+ * weights: bmv_mvs_render_umma_weight_bytes() bytes from mlp_pack.pack_mvs_weights_umma. */
+typedef struct bmv_mvs_render_params {
+  bmv_mvs_march_params g;
+  const uint32_t* weights;
+  float* raw;
+} bmv_mvs_render_params;
+BMV_API int bmv_mvs_render_umma(const bmv_mvs_render_params* p, bmv_stream_t stream);
+BMV_API int bmv_mvs_render_umma_weight_bytes(void);
+
 /* ------------------------------------------------------------------------------------------
  * Fused top-down step of the feature pyramid: out = up2x(prev) + conv1x1(lateral_in) + bias
  * (`_upsample_add(x, lat(c))`, reference lib/networks/enerf/feature_net.py:24-33).  All tensors
@@ -512,6 +526,12 @@ typedef struct bmv_render_multi_params {
   int32_t views_host[BMV_MAX_VOLUMES * 3];
   const uint32_t* mlp_weights;
   float* raw; float* z_vals; float* vis_mask; int32_t* vis_count;
+  /* Row slabs (multi-GPU row tiles: a rank holds only the volume / map rows its rays touch): `volume` points at volume
+   * row vol_row0 and `depth` / `std` / `near_far` at map row map_row0 (rows outside the slab must not be needed by
+   * rays [ray_begin, ray_begin + n_rays)); g.vol_d_stride is then the slab's plane stride and nf_plane_stride the
+   * distance between the two near_far planes (0: hv * wv).  All zero for whole tensors. */
+  int32_t vol_row0, map_row0;
+  int64_t nf_plane_stride;
 } bmv_render_multi_params;
 BMV_API int bmv_render_rays_multi(const bmv_render_multi_params* p, bmv_stream_t stream);
 

@@ -14,6 +14,30 @@ from boostmvsnerfs_b200 import dist as bdist
 from boostmvsnerfs_b200.config import RenderConfig
 
 
+def test_chain_blocks_and_slabs():
+    import numpy as np
+    for K in (1, 3, 4, 8, 9):
+        for g in (1, 2, 3, 4, 8):
+            blocks = [bdist.chain_block(K, g, r) for r in range(g)]
+            assert blocks[0][0] == 0 and max(b for _, b in blocks) == K
+            assert sorted(k for a, b in blocks for k in range(a, b)) == list(range(K))
+            assert all(blocks[i][1] == blocks[i + 1][0] or blocks[i + 1] == (K, K) for i in range(g - 1))
+    # every row a ray reads through the fp32 align_corners mapping lies inside its rank's slab
+    for H, hv in ((544, 272), (1088, 544), (96, 48), (64, 8), (33, 17)):
+        scale = np.float32(hv - 1) / np.float32(H - 1)
+        for g in (1, 2, 3, 8):
+            for r in range(g):
+                t0, t1 = bdist.row_tile(H, g, r)
+                y0, y1 = bdist.slab_rows(t0, t1, H, hv)
+                assert 0 <= y0 < y1 <= hv
+                rows = np.arange(t0, t1, dtype=np.float32)
+                i0 = (scale * rows).astype(np.int64)
+                i1 = np.minimum(i0 + 1, hv - 1)
+                if len(rows):
+                    assert i0.min() >= y0 and i1.max() < y1, (H, hv, g, r)
+            assert sum(b - a for a, b in (bdist.slab_rows(*bdist.row_tile(H, g, q), H, hv) for q in range(g))) <= hv + 4 * g
+
+
 def test_partitions_cover_everything_exactly_once():
     for n in (1, 4, 6, 8, 544, 545):
         for g in (1, 2, 3, 4, 8):
@@ -37,6 +61,7 @@ class _Ctx:
 
 class FakeNet:
     """Stands in for BoostEnerfNetwork: config + bookkeeping only."""
+    generate_rays = False
 
     def __init__(self, rc, k_best):
         self.rc = rc
@@ -48,7 +73,7 @@ class FakeNet:
     def _stage(self, name):
         return _Ctx()
 
-    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt):
+    def _camera_stage(self, exts, ixts, tar_ext, tar_ixt, image_hw=None):
         return None, None, None
 
     def parameters(self):
@@ -56,17 +81,17 @@ class FakeNet:
 
 
 class FakeRenderer(bdist.ShardedFrameRenderer):
-    """Deterministic stand-ins: features depend on the view id, chain state on the triple and the
-    (gathered) features, the tile on the gathered states and the ray ids."""
+    """Deterministic stand-ins: features depend on the view id, a chain's volume / maps on its triple, the features and the
+    ROW (so a wrong slab offset changes the result), the tile on the slab rows each ray reads and on the ray ids."""
 
     def compute_features(self, inps, views):
-        if not views:
+        if not len(views):
             return None
         shapes = self.feature_shapes(inps)
         return {n: torch.stack([inps[v].mean() + torch.arange(C * h * w, dtype=torch.float32).view(C, h, w) * (v + 1)
                                 for v in views]) for n, (C, h, w) in shapes.items()}
 
-    def compute_chains(self, feats, projs, near_far, triples, H, W):
+    def compute_chains(self, feats, projs, near_far, triples, H, W, views_dev=None):
         rc = self.net.rc
         out = {}
         for i in range(rc.num):
@@ -74,18 +99,33 @@ class FakeRenderer(bdist.ShardedFrameRenderer):
                 continue
             D, h, w = rc.volume_planes[i], int(H * rc.volume_scale[i]), int(W * rc.volume_scale[i])
             sig = [sum(float(feats['level_0'][v].sum()) for v in t) * 1e-6 + sum(t) for t in triples]
-            vol = torch.stack([torch.full((8, D, h, w), s) + torch.arange(8.).view(8, 1, 1, 1) for s in sig])
-            out[i] = {'feat_vol': vol, 'depth': [torch.full((h, w), s + 1) for s in sig],
-                      'std': [torch.full((h, w), s + 2) for s in sig],
-                      'nf': [torch.full((2, h, w), s + 3) for s in sig]}
+            row = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1)
+            vol = torch.stack([torch.full((8, D, h, w), s) + torch.arange(8.).view(8, 1, 1, 1) + 10 * row for s in sig])
+            vol = vol.contiguous(memory_format=torch.channels_last_3d)
+            out[i] = {'feat_vol': vol,
+                      'depth_all': torch.stack([torch.full((h, w), s + 1) + row[0, 0] for s in sig]),
+                      'std_all': torch.stack([torch.full((h, w), s + 2) + 2 * row[0, 0] for s in sig]),
+                      'nf_all': torch.stack([torch.stack([torch.full((h, w), s + 3) + 3 * row[0, 0],
+                                                          torch.full((h, w), s + 4) + 4 * row[0, 0]]) for s in sig])}
         return out
 
-    def render_tile(self, level, feats, inps, state, rays, cams, triples, H, W, ray_begin, n_rays):
-        S = self.net.rc.num_samples[level]
-        ids = rays[ray_begin:ray_begin + n_rays, 6] + 1000 * rays[ray_begin:ray_begin + n_rays, 7]
-        chain_sig = sum(float(v.sum()) for v in state['feat_vol']) + sum(float(d.mean()) for d in state['depth']) \
-            + sum(float(d.mean()) for d in state['std']) + sum(float(d.mean()) for d in state['nf'])
-        return torch.stack([ids + chain_sig * 1e-3 + c for c in range(4 + S)], dim=1)
+    def render_tile(self, level, feats, inps, vols, maps, y0, rays, cams, triples, H, W, ray_begin, n_rays, views_dev=None):
+        rc = self.net.rc
+        S = rc.num_samples[level]
+        hv = int(H * rc.volume_scale[level])
+        Hr = int(H * rc.render_scale[level])
+        r = rays[ray_begin:ray_begin + n_rays]
+        ids = r[:, 6] + 1000 * r[:, 7]
+        # the two map / volume rows a ray of image row py reads (align_corners upsample), relative to the slab
+        src = r[:, 7] * ((hv - 1) / max(Hr - 1, 1))
+        i0 = src.floor().long().clamp(0, hv - 1)
+        i1 = (i0 + 1).clamp(max=hv - 1)
+        assert int(i0.min()) >= y0 and int(i1.max()) < y0 + vols.shape[3], "slab does not cover the rays' rows"
+        val = torch.zeros(n_rays)
+        for k in range(vols.shape[0]):
+            per_row = vols[k].sum(dim=(0, 1, 3)) * 1e-4 + maps[k].sum(dim=(0, 2)) * 1e-2          # (rows,)
+            val = val + (k + 1) * (per_row[i0 - y0] + 0.5 * per_row[i1 - y0])
+        return torch.stack([ids + val * 1e-3 + c for c in range(4 + S)], dim=1)
 
 
 def _scene(N=5, H=32, W=64):

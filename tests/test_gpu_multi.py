@@ -22,27 +22,46 @@ def _free_port():
 def _worker(rank, world, port, ret):
     from boostmvsnerfs_b200 import network
     from boostmvsnerfs_b200.config import RenderConfig
-    from boostmvsnerfs_b200.dist import ShardedFrameRenderer
+    from boostmvsnerfs_b200.dist import ShardedFrameRenderer, make_sharded_graph
     from boostmvsnerfs_b200.synth import batch_to, make_scene
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
+        worst = {}
+
+        def compare(tag, out, single):
+            for k in single:
+                a, b = out[k].float(), single[k].float()
+                assert a.shape == b.shape, (tag, k, a.shape, b.shape)
+                worst[f"{tag}/{k}"] = float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+        # strict fp32, K=3 on 2 ranks (ragged chain blocks: 2 + 1), eager sharded frame
         torch.backends.cudnn.allow_tf32 = False
-        rc = RenderConfig.enerf_pretrain(3)          # K=3 on 2 ranks: ragged chain ownership, both levels rendered
+        rc = RenderConfig.enerf_eval(3)
         torch.manual_seed(0)
         net = network.BoostEnerfNetwork(preprocess=True, rc=rc).eval().to(dev)
         net.view_selection_outputs = {"synth_0": [1, 5, 8]}
         scene = make_scene(H=96, W=160, n_views=5, seed=1, smooth=True)
-        single = net(batch_to(scene, dev))
-        out = ShardedFrameRenderer(net).forward(batch_to(scene, dev))
-        worst = {}
-        for k in single:
-            a, b = out[k].float(), single[k].float()
-            assert a.shape == b.shape, (k, a.shape, b.shape)
-            worst[k] = float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+        single = {k: v.clone() for k, v in net(batch_to(scene, dev)).items()}
+        compare("strict_eager", ShardedFrameRenderer(net).forward(batch_to(scene, dev)), single)
+        # the captured sharded frame (kernels + NCCL collectives in one CUDA graph per rank), replayed for two selections
+        fg = make_sharded_graph(net)
+        compare("strict_graph", fg(batch_to(scene, dev)), single)
+        net.view_selection_outputs = {"synth_0": [0, 4, 9]}
+        single2 = {k: v.clone() for k, v in net(batch_to(scene, dev)).items()}
+        compare("strict_graph_selection2", fg(batch_to(scene, dev)), single2)
+        assert len(fg._cache) == 1
+        fg.close()                                           # graphs that hold NCCL work must go before the communicator
+        # TF32-class mode: fp16 slab exchange; and the view-sharded feature pyramid with its fp16 all-gather
+        torch.backends.cudnn.allow_tf32 = True
+        single3 = {k: v.clone() for k, v in net(batch_to(scene, dev)).items()}
+        compare("default_eager", ShardedFrameRenderer(net).forward(batch_to(scene, dev)), single3)
+        compare("default_sharded_features", ShardedFrameRenderer(net, shard_features=True).forward(batch_to(scene, dev)), single3)
         ret[rank] = worst
+        torch.cuda.synchronize()
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -52,6 +71,8 @@ def test_sharded_frame_matches_single_gpu():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     for r in (0, 1):
+        print(f"rank {r}: " + ", ".join(f"{k}={v:.1e}" for k, v in ret[r].items()))
         for k, v in ret[r].items():
-            # batch-size dependent cuDNN algorithm choices are the only difference
-            assert v < 1e-4, f"rank {r} {k}: rel err {v}"
+            # strict: batch-size dependent cuDNN algorithm choices are the only difference; default: fp16 slabs / features
+            tol = 1e-4 if k.startswith("strict") else (2e-3 if "sharded_features" not in k else 1e-2)
+            assert v < tol, f"rank {r} {k}: rel err {v}"
