@@ -26,6 +26,11 @@ WORKLOADS = {
     "C1": dict(H=256, W=320, n_views=3, K=1, k_best=[0]),
     "C2": dict(H=544, W=960, n_views=6, K=4, k_best=[0, 7, 12, 19]),
     "C4": dict(H=1088, W=1920, n_views=6, K=8, k_best=[0, 3, 7, 9, 12, 15, 17, 19]),
+    # MVSNeRF backbone + boost, 128 depth planes / samples, bf16 cost volume (BASELINE config 3)
+    "C3": dict(H=544, W=960, n_views=6, K=4, k_best=[0, 7, 12, 19], backbone="mvsnerf", D=128),
+    # ScanNet_plus-shaped sequence (BASELINE config 5): 1296x968 -> 1312x992, K=6; each step renders the NEXT novel view
+    # of a 64-view trajectory, every view with its own K selected triples (one selection-agnostic graph)
+    "C5": dict(H=992, W=1312, n_views=6, K=6, k_best=[0, 3, 7, 12, 15, 19], sequence=64),
 }
 CPU_SAMPLE_SIZES = [(544, 960), (384, 640), (288, 480), (256, 320), (128, 192), (64, 96)]
 
@@ -40,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=40.0)
     ap.add_argument("--stage-report", action="store_true", help="print the per-stage table to stderr")
-    ap.add_argument("--mlp-engine", default=None, choices=["mma", "fma", "umma"], help="override Network.mlp_engine")
+    ap.add_argument("--mlp-engine", default=None, choices=["mma", "fma", "umma", "cublas"], help="override Network.mlp_engine")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true",
                     help="skip timing the reference's op sequence (oracle restatement) as eager PyTorch on this GPU (N=1 leg)")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-fp32 timing / parity legs")
@@ -770,9 +775,194 @@ def main_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ MVSNeRF arm (config 3)
+def mvs_workload_config(name, wl):
+    return {"workload": f"{name}: MVSNeRF + BoostMVSNeRFs K={wl['K']} cost volumes, {wl['W']}x{wl['H']} (960x540 padded to /32), "
+                        f"N={wl['n_views']} source views, {wl['D']} depth planes and samples per ray, bf16 cost volume, "
+                        "random-init weights",
+            "e2e_inputs": "pinned host: N source images + cameras + rays (R,8), uploaded every step; rgb + depth read back",
+            "l2": "no explicit flush: one frame streams > 5 GB through HBM (4 x 556 MB cost volumes alone)",
+            "timing": "CUDA events on the launch stream around exactly `steps` frames, max over ranks"}
+
+
+def mvs_cpu_rate(wl, rc, budget_s, steps=1):
+    """oracle.boost_mvsnerf_forward on the host at the largest listed resolution that fits the budget (the full C3 frame
+    takes ~11 minutes on 8 cores: BASELINE.md)."""
+    import torch
+    from boostmvsnerfs_b200.modules_mvs import MvsnerfModules
+    from boostmvsnerfs_b200.synth import make_scene
+    from oracle import mvsnerf_oracle as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = MvsnerfModules().eval()
+    kb = torch.tensor([wl["k_best"]])
+
+    def run(h, w):
+        scene = make_scene(H=h, W=w, n_views=wl["n_views"], seed=0, render_scales=(1.0,), mvs_near_far_cols=True)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            M.boost_mvsnerf_forward(net, scene, rc, kb)
+        return time.perf_counter() - t0
+    t_probe = run(32, 64)
+    rate = 32 * 64 / t_probe
+    size = (32, 64)
+    for h, w in [(wl["H"], wl["W"]), (288, 480), (128, 192), (64, 96)]:
+        if 1.3 * h * w / rate <= budget_s / max(1, steps):
+            size = (h, w)
+            break
+    ts = [run(*size) for _ in range(steps)]
+    dt = sum(ts) / len(ts)
+    sample = (f"{steps} frame(s) of K={wl['K']} N={wl['n_views']} D=S={wl['D']} at {size[1]}x{size[0]} ({size[0] * size[1]} rays) "
+              f"through oracle.boost_mvsnerf_forward, torch {torch.__version__} CPU")
+    return size[0] * size[1] / dt, dt * 1e3, sample, cores, size
+
+
+def main_mvs(args):
+    import torch
+    from boostmvsnerfs_b200 import _lib
+    from boostmvsnerfs_b200.config import RenderConfig
+    from boostmvsnerfs_b200.network_mvs import BoostMvsnerfNetwork
+    from boostmvsnerfs_b200.synth import batch_to, make_scene
+    wl = WORKLOADS[args.workload]
+    rc = RenderConfig.mvsnerf_eval(wl["K"], wl["D"])
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            rate, ms, sample, cores, size = mvs_cpu_rate(wl, rc, args.ref_budget_s / max(1, args.steps + args.warmup), 1)
+            print(json.dumps({"impl": "reference", "metric": "rays_per_sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": mvs_workload_config(args.workload, wl),
+                              "step_sample": {"resolution": [size[1], size[0]], "full_workload_frame": size == (wl["H"], wl["W"])},
+                              "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+                              "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    torch.manual_seed(0)
+    net = BoostMvsnerfNetwork(preprocess=True, rc=rc).eval().to(dev)
+    net.view_selection_outputs = {"synth_0": wl["k_best"]}
+    net.volume_dtype = torch.bfloat16
+    net.mlp_engine = args.mlp_engine if args.mlp_engine in ("umma", "cublas") else "umma"
+    host = make_scene(H=wl["H"], W=wl["W"], n_views=wl["n_views"], seed=rank, render_scales=(1.0,), mvs_near_far_cols=True)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    batch = batch_to(host, dev)
+    rays_per_frame = wl["H"] * wl["W"]
+    timer = StageTimer()
+    ktimer = KernelTimer(torch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(1, args.warmup)):
+        out = net(dict(batch))
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = net(dict(batch))
+    e1.record()
+    barrier()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.launch_count() - l0) / args.steps
+    clk = clocks.stop(tw0, tw1)
+    # instrumented pass
+    net.stage_timer, _lib.kernel_timer = timer, ktimer
+    timer.enabled = ktimer.enabled = True
+    for _ in range(max(1, min(args.steps, 3))):
+        net(dict(batch))
+    barrier()
+    n_inst = max(1, min(args.steps, 3))
+    net.stage_timer, _lib.kernel_timer = None, None
+    stages = {k: v[0] / n_inst for k, v in timer.summary().items()}
+    ksum = {k: sum(v) / n_inst for k, v in ktimer.summary().items()}
+    kcnt = {k: len(v) / n_inst for k, v in ktimer.summary().items()}
+    # end to end: pinned host batch uploaded, rgb + depth read back, every step
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    res_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in ("rgb_level0", "depth_level0")}
+    d2h = sum(v.numel() * v.element_size() for v in res_host.values())
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        o = net(batch_to(host, dev, non_blocking=True))
+        for k, v in res_host.items():
+            v.copy_(o[k], non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    S, K = wl["D"], wl["K"]
+    h, w = wl["H"] // 4 + 48, wl["W"] // 4 + 48
+    kernels = {}
+    if ksum.get("bmv_mvs_render_umma"):
+        per = ksum["bmv_mvs_render_umma"] / K
+        flops = 2.0 * 125696.0 * rays_per_frame * S          # MACs per sample of the 6x128 MLP (unpadded), per chain
+        kernels["render_fused"] = {"ms_per_launch": per, "launches_per_step": K, "algorithmic_flops": flops,
+                                   "tflops": flops / (per * 1e-3) / 1e12, "frac": flops / (per * 1e-3) / 1e12 / peak_tf,
+                                   "bound": "tensor", "share_of_step": ksum["bmv_mvs_render_umma"] / ms}
+    if ksum.get("bmv_cost_volume_var_img"):
+        per = ksum["bmv_cost_volume_var_img"] / K
+        nbytes = 41 * S * h * w * 2 + 3 * (32 + 3) * (wl["H"] // 4) * (wl["W"] // 4) * 4
+        kernels["cost_volume_img"] = {"ms_per_launch": per, "launches_per_step": K, "algorithmic_bytes": nbytes,
+                                      "achieved_gbs": nbytes / (per * 1e-3) / 1e9, "frac": nbytes / (per * 1e-3) / 1e9 / peak_gbs,
+                                      "bound": "hbm", "share_of_step": ksum["bmv_cost_volume_var_img"] / ms}
+    dom = max(kernels, key=lambda n: kernels[n]["share_of_step"]) if kernels else None
+    roofline = None
+    if dom:
+        k = kernels[dom]
+        roofline = ({"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": k["frac"],
+                     "traffic": None, "launch_ms": k["ms_per_launch"], "share_of_step": k["share_of_step"]} if k["bound"] == "tensor" else
+                    {"kernel": dom, "bound": "hbm", "achieved": k["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": k["frac"],
+                     "traffic": None, "launch_ms": k["ms_per_launch"], "share_of_step": k["share_of_step"]})
+    line = {"metric": "rays_per_sec", "value": world * rays_per_frame / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "ms_per_frame": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 cost volume, f16-operand/f32-accum fused MLP (TF32-class), cuDNN TF32 convolutions, f32 elsewhere"
+                     if net.mlp_engine == "umma" else "bf16 cost volume, f32 MLP (cuBLAS)",
+            "data": "synthetic", "config": mvs_workload_config(args.workload, wl),
+            "run": {"mlp_engine": net.mlp_engine, "execution": "eager (stream launches)",
+                    "parallelism": "single GPU" if world == 1 else f"{world} frame replicas, no data-path collective"},
+            "e2e": {"value": world * rays_per_frame / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
+            "stage_ms_per_step": stages, "libbmv_kernel_ms_per_step": ksum, "libbmv_launches_per_step": kcnt,
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cms, sample, cores, size = mvs_cpu_rate(wl, rc, args.cpu_budget_s)
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if WORKLOADS[a.workload].get("backbone") == "mvsnerf":
+        main_mvs(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_ours(a)

@@ -121,7 +121,12 @@ class ShardedFrameRenderer:
         """FeatureNet on the listed views -> dict level -> (len(views), C, h, w)."""
         if not len(views):
             return None
-        return self.net.forward_feat(inps[views] if len(views) != inps.shape[0] else inps)
+        if len(views) == inps.shape[0]:
+            return self.net.forward_feat(inps)
+        # round-robin ownership = a strided slice (indexing with a Python list would upload an index tensor: a host
+        # sync, and illegal inside a CUDA-graph capture)
+        step = views[1] - views[0] if len(views) > 1 else inps.shape[0]
+        return self.net.forward_feat(inps[views[0]::step][:len(views)])
 
     def feature_shapes(self, inps):
         H, W = inps.shape[-2:]

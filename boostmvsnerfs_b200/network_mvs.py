@@ -30,6 +30,8 @@ class BoostMvsnerfNetwork(nn.Module):
         self.view_selection_outputs = {}
         self.mlp_chunk_bytes = 1 << 30         # bound on the materialised (chunk,S,86) MLP input
         self.volume_dtype = torch.float32      # torch.bfloat16: BASELINE config 3 (1e-2 tolerance)
+        self.mlp_engine = 'cublas'             # 'umma': K3b + MLP fused on tcgen05 (fp16 operands: TF32-class, config 3)
+        self._packed = None
         self.stage_timer = None
         if not preprocess:
             if view_selection_file is None or not os.path.exists(view_selection_file):
@@ -103,6 +105,18 @@ class BoostMvsnerfNetwork(nn.Module):
         raw = torch.empty((K, R, S, 4), device=dev)
         z = torch.empty((K, R, S), device=dev)
         mask = torch.empty((K, R, S), device=dev)
+        if self.mlp_engine == 'umma':
+            # nothing per-sample reaches HBM: marching, fetch and the whole MLP run in one kernel per chain
+            key = tuple((q.data_ptr(), q._version) for q in self.nerf.parameters())
+            if self._packed is None or self._packed[0] != key:
+                from .mlp_pack import pack_mvs_weights_umma
+                self._packed = (key, pack_mvs_weights_umma(self.nerf))
+            for k in range(K):
+                with self._stage('render_fused'):
+                    ops.mvs_render(rays, S, triples[k], batch['all_src_exts'][0], batch['all_src_ixts'][0], H, W,
+                                   float(nears[k]), float(fars[k]), reg[k], inps, self._packed[1], PAD,
+                                   out={'raw': raw[k], 'z_vals': z[k], 'vis_mask': mask[k]})
+            return raw, mask, z, nears, fars
         chunk = max(1, min(R, self.mlp_chunk_bytes // (S * 86 * 4)))
         for k in range(K):
             for r0 in range(0, R, chunk):

@@ -1064,3 +1064,53 @@ def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, i
     mp.mlp_weights = w.data_ptr()
     _lib.call("bmv_render_rays_multi", mp, _stream())
     return res
+
+
+# ------------------------------------------------------------------------------------------ K3b + MLP fused (MVSNeRF)
+def mvs_render(rays, S, views, src_exts, src_ixts, H, W, near, far, volume, rgb, packed_weights, pad=24,
+               rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False):
+    """MVSNeRF marching + fetch + the 6x128 MLP in one tcgen05 kernel (bmv_mvs_render_umma): same inputs as
+    mvs_march_fetch plus mlp_pack.pack_mvs_weights_umma(nerf); nothing per-sample is materialised.
+    Returns dict(raw (n,S,4), z_vals (n,S), vis_mask (n,S) [, vis_count]).  TF32-class (fp16 operands)."""
+    rays = _cf32(rays, "rays")
+    src_exts, src_ixts = _cf32(src_exts, "src_exts"), _cf32(src_ixts, "src_ixts")
+    _f32(volume, "volume")
+    rgb = _cf32(rgb, "rgb")
+    dev = rays.device
+    R = rays.shape[0]
+    n = R - ray_begin if n_rays is None else n_rays
+    w = packed_weights
+    if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()
+            and w.numel() * 4 == _lib.load().bmv_mvs_render_umma_weight_bytes()):
+        raise BmvError("mvs_render: weights must come from mlp_pack.pack_mvs_weights_umma")
+    rp = _lib.MvsRenderParams()
+    p = rp.g
+    p.rays, p.ray_begin, p.n_rays = rays.data_ptr(), ray_begin, n
+    t = _linspace(S, dev)
+    p.t, p.S, p.V = t.data_ptr(), S, len(views)
+    _views(p.view, views)
+    p.src_exts, p.src_ixts = src_exts.data_ptr(), src_ixts.data_ptr()
+    p.H, p.W, p.near, p.far, p.pad = H, W, float(near), float(far), pad
+    p.volume = volume.data_ptr()
+    p.Cv, p.Dv, p.hv, p.wv = volume.shape
+    p.vol_c_stride, p.vol_d_stride, p.vol_y_stride, p.vol_x_stride = volume.stride()
+    p.rgb = rgb.data_ptr()
+    p.rgb_scale, p.rgb_shift = rgb_affine
+    res = dict(out) if out else {}
+
+    def mk(name, shape, dtype=torch.float32):
+        if name in res:
+            tns = res[name]
+            if not (tns.is_cuda and tns.dtype == dtype and tns.is_contiguous() and tns.numel() == _numel(shape)):
+                raise BmvError(f"preallocated output {name}: need contiguous {dtype} with {_numel(shape)} elements")
+        else:
+            res[name] = torch.empty(shape, device=dev, dtype=dtype)
+        return res[name].data_ptr()
+    rp.raw = mk("raw", (n, S, 4))
+    p.z_vals = mk("z_vals", (n, S))
+    p.vis_mask = mk("vis_mask", (n, S))
+    if want_count or "vis_count" in res:
+        p.vis_count = mk("vis_count", (n, S), torch.int32)
+    rp.weights = w.data_ptr()
+    _lib.call("bmv_mvs_render_umma", rp, _stream())
+    return res

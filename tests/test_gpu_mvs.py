@@ -132,3 +132,39 @@ def test_bf16_volume_chain_within_1e2(strict_fp32):
     net.volume_dtype = torch.bfloat16
     out = net(batch)
     close(out["rgb_level0"], gc.np("out_rgb_level0"), "rgb with bf16 volume", rtol=1e-2)
+
+
+@pytest.mark.parametrize("S", [32, 128])
+def test_fused_mvs_render_matches_fetch_plus_mlp(S):
+    """bmv_mvs_render_umma (K3b + the 6x128 MLP on tcgen05, fp16 operands) against bmv_mvs_march_fetch + the fp32
+    torch module on the same inputs: z and visibility bit-exact, raw within the TF32-class bound of config 3."""
+    from boostmvsnerfs_b200 import mlp_pack, ops
+    from boostmvsnerfs_b200.modules_mvs import MvsNerfMlp
+    from boostmvsnerfs_b200.synth import batch_to, make_scene
+    H, W, N, D = 64, 96, 4, 16
+    scene = batch_to(make_scene(H=H, W=W, n_views=N, seed=5, smooth=True, render_scales=(1.0,), mvs_near_far_cols=True), "cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    vol = torch.randn(8, D, H // 4 + 48, W // 4 + 48, device="cuda", generator=g)
+    torch.manual_seed(2)
+    mlp = MvsNerfMlp().cuda().eval()
+    packed = mlp_pack.pack_mvs_weights_umma(mlp)
+    rays = scene["rays_0"][0]
+    views = (1, 0, 3)
+    args = (rays, S, views, scene["all_src_exts"][0], scene["all_src_ixts"][0], H, W, 1.6, 9.6, vol, scene["all_src_inps"][0])
+    ref = ops.mvs_march_fetch(*args, want=("mlp_in", "z_vals", "vis_mask", "vis_count"))
+    with torch.no_grad():
+        raw_ref = mlp(ref["mlp_in"])
+    for b, n in ((0, None), (37, 1001)):
+        got = ops.mvs_render(*args, packed, ray_begin=b, n_rays=n, want_count=True)
+        sl = slice(b, None if n is None else b + n)
+        assert torch.equal(got["z_vals"], ref["z_vals"][sl]) and torch.equal(got["vis_count"], ref["vis_count"][sl])
+        assert torch.equal(got["vis_mask"], ref["vis_mask"][sl])
+        err = float((got["raw"] - raw_ref[sl]).abs().max()) / float(raw_ref.abs().max())
+        assert err <= 1e-2, f"S={S} range=({b},{n}): raw differs by {err:.2e}"
+        assert float((got["raw"] - raw_ref[sl]).abs().mean()) / float(raw_ref.abs().mean()) <= 2e-3
+    # channels-last volume: same result through the 16-byte-load path
+    vol_cl = vol.permute(1, 2, 3, 0).contiguous().permute(3, 0, 1, 2)
+    got2 = ops.mvs_render(rays, S, views, scene["all_src_exts"][0], scene["all_src_ixts"][0], H, W, 1.6, 9.6, vol_cl,
+                          scene["all_src_inps"][0], packed)
+    got1 = ops.mvs_render(*args, packed)
+    assert float((got2["raw"] - got1["raw"]).abs().max()) <= 1e-5
