@@ -310,9 +310,11 @@ def main_reference(args):
 
 
 def workload_config(name, wl):
+    seq = (f"; sequence of {wl['sequence']} novel views over the same source images, a new target camera and a new selection "
+           f"of K triples per step" if wl.get("sequence") else "")
     return {"workload": f"{name}: ENeRF + BoostMVSNeRFs K={wl['K']} cost volumes, {wl['W']}x{wl['H']} "
                         f"(960x540 padded to /32 for C2), N={wl['n_views']} source views, 3 views per volume, "
-                        "levels (64 planes @1/8, 8 planes @1/2), 2 samples/ray, random-init weights",
+                        f"levels (64 planes @1/8, 8 planes @1/2), 2 samples/ray, random-init weights{seq}",
             "e2e_inputs": "pinned host: N source images + cameras + near/far, uploaded every step (graph mode: on a copy "
                           "stream while the previous frame renders, FrameGraph.prefetch); rays generated on device; "
                           "rgb + depth read back to pinned host memory every step",
@@ -356,6 +358,36 @@ def main_ours(args):
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     batch = batch_to(host, dev)
     rays_per_frame = wl["H"] * wl["W"]
+    # ---- sequence workloads (BASELINE config 5): every step renders the NEXT novel view of an n_seq-view trajectory over
+    # the same source images; each view has its own target camera and its own K selected triples
+    n_seq = int(wl.get("sequence", 0))
+    seq_host, seq_dev = [], []
+    if n_seq:
+        import itertools
+        import numpy as np
+        from boostmvsnerfs_b200.synth import _look_at
+        net.generate_rays = True                              # rays follow the per-view camera: generated on the device
+        n_tri = len(list(itertools.combinations(range(wl["n_views"]), 3)))
+        rs = np.random.RandomState(1234 + rank)
+        for j in range(n_seq):
+            ang = 2.0 * np.pi * j / n_seq
+            eye = np.array([0.25 * np.cos(ang), 0.1 * np.sin(ang), 0.15 * np.sin(2 * ang)])
+            tar_ext = torch.from_numpy(np.linalg.inv(_look_at(eye, np.array([0.0, 0.0, 5.0])))[None].astype(np.float32))
+            hj = {k: v for k, v in host.items() if not k.startswith("rays_")}
+            hj["tar_ext"] = tar_ext.pin_memory()
+            hj["meta"] = {"scene": ["synth"], "tar_view": torch.tensor([j]), "frame_id": torch.tensor([j])}
+            net.view_selection_outputs[f"synth_{j}"] = sorted(int(v) for v in rs.choice(n_tri, wl["K"], replace=False))
+            seq_host.append(hj)
+            dj = {k: v for k, v in batch.items() if not k.startswith("rays_")}
+            dj["tar_ext"] = tar_ext.to(dev)
+            dj["meta"] = hj["meta"]
+            seq_dev.append(dj)
+
+    def dev_batch(j):
+        return seq_dev[j % n_seq] if n_seq else batch
+
+    def host_batch(j):
+        return seq_host[j % n_seq] if n_seq else host
 
     def barrier():
         if world > 1:
@@ -369,8 +401,8 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        net(batch)
+    for j in range(args.warmup):
+        net(dev_batch(j))
     vol_dtype = str(getattr(net, "last_volume_dtype", torch.float32)).replace("torch.", "")
     # ---- device-resident timing: NO profiling hooks inside this region
     clocks = ClockSampler(local)
@@ -382,8 +414,8 @@ def main_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    for _ in range(args.steps):
-        out = net(batch)
+    for j in range(args.steps):
+        out = net(dev_batch(j))
     e1.record()
     t_host = (time.time() - t_wall0) / args.steps * 1e3        # host time to ENQUEUE one frame
     barrier()
@@ -400,8 +432,8 @@ def main_ours(args):
     barrier()
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
-    for _ in range(args.steps):
-        net(batch)
+    for j in range(args.steps):
+        net(dev_batch(j))
     pe1.record()
     barrier()
     ms_instrumented = pe0.elapsed_time(pe1) / args.steps
@@ -419,12 +451,12 @@ def main_ours(args):
     h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v))
     res_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in ("rgb_level1", "depth_level1")}
     d2h = sum(v.numel() * v.element_size() for v in res_host.values())
-    for _ in range(2):
-        o = net(batch_to(host, dev, non_blocking=True))
+    for j in range(2):
+        o = net(batch_to(host_batch(j), dev, non_blocking=True))
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        o = net(batch_to(host, dev, non_blocking=True))
+    for j in range(args.steps):
+        o = net(batch_to(host_batch(j), dev, non_blocking=True))
         for k, v in res_host.items():
             v.copy_(o[k], non_blocking=True)
     e1.record()
@@ -436,31 +468,34 @@ def main_ours(args):
     try:
         from boostmvsnerfs_b200.graph import FrameGraph
         fg = FrameGraph(net)
-        for _ in range(max(2, args.warmup)):
-            fg(batch)
+        for j in range(max(2, args.warmup)):
+            fg(dev_batch(j))
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            og = fg(batch, cameras_unchanged=True)           # same batch object every step; includes the D2D refresh of the static inputs
+        for j in range(args.steps):
+            # single frame: same batch object every step; sequence: a new camera + selection per step (device-resident
+            # cameras are read back: one host sync per frame); includes the D2D refresh of the static inputs
+            og = fg(dev_batch(j), cameras_unchanged=not n_seq)
         e1.record()
         barrier()
         ms_graph = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         default_out = {k: v.detach().float().cpu() for k, v in og.items()}
-        for _ in range(2):
-            og = fg(host)
+        for j in range(2):
+            og = fg(host_batch(j))
         barrier()
-        fg.prefetch(host)
+        fg.prefetch(host_batch(0))
         e0.record()
-        for _ in range(args.steps):
-            og = fg(host)                                    # waits for this frame's upload, D2D into the static buffers, replay
-            fg.prefetch(host)                                # H2D upload of the NEXT frame (pinned host batch) overlaps this replay
+        for j in range(args.steps):
+            og = fg(host_batch(j))                           # waits for this frame's upload, D2D into the static buffers, replay
+            fg.prefetch(host_batch(j + 1))                   # H2D upload of the NEXT frame (pinned host batch) overlaps this replay
             fg.read_back(og, res_host)                       # D2H of THIS frame's rgb + depth overlaps the next replay
         fg.wait_read_back()                                  # the last frame's transfer is inside the timed region
         e1.record()
         barrier()
         ms_graph_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         graph_res = {"ms_per_step": ms_graph, "value": world * rays_per_frame / (ms_graph * 1e-3),
-                     "e2e_ms_per_step": ms_graph_e2e, "e2e_value": world * rays_per_frame / (ms_graph_e2e * 1e-3)}
+                     "e2e_ms_per_step": ms_graph_e2e, "e2e_value": world * rays_per_frame / (ms_graph_e2e * 1e-3),
+                     "captured_graphs": len(fg._cache)}
     except Exception as exc:                                 # report, never hide
         graph_res = {"error": f"{type(exc).__name__}: {exc}"}
         default_out = None
@@ -468,7 +503,7 @@ def main_ours(args):
     # ---- strict-fp32 leg: the SAME frame with TF32-class arithmetic switched off (cuDNN fp32 convolutions, fp32 cost
     # volume): the path the 1e-4 parity tests check.  Timed through the same FrameGraph entry point.
     strict_res, strict_out = None, None
-    if not args.no_strict:
+    if not args.no_strict and not n_seq:
         old_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -853,7 +888,7 @@ def main_mvs(args):
     host = make_scene(H=wl["H"], W=wl["W"], n_views=wl["n_views"], seed=rank, render_scales=(1.0,), mvs_near_far_cols=True)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     batch = batch_to(host, dev)
-    rays_per_frame = wl["H"] * wl["W"]
+    rays_per_frame = wl["W"] * wl["H"]
     timer = StageTimer()
     ktimer = KernelTimer(torch)
 

@@ -9,6 +9,8 @@ Run in the build container (the GPU box has no /root/reference):
     python oracle/gen_golden.py single         # enerf.Network      -> tests/golden/enerf_single.npz
     python oracle/gen_golden.py mvs_ops        # MVSNeRF op-level   -> tests/golden/mvsnerf_ops.npz
     python oracle/gen_golden.py mvs_chain      # boost_mvsnerf.Network.forward -> tests/golden/mvsnerf_chain.npz
+    python oracle/gen_golden.py mvs_chain_d32  # same at 32 / 128 depth planes -> tests/golden/mvsnerf_chain_d{32,128}.npz
+    python oracle/gen_golden.py mvs_chain_d128
     python oracle/gen_golden.py all            # each of the above in its own process
 
 Every stored array is either an INPUT handed to a reference function or the OUTPUT the reference
@@ -315,11 +317,33 @@ def gen_mvs_chain():
     _save("mvsnerf_chain.npz", out)
 
 
+def gen_mvs_chain_planes(D):
+    """boost_mvsnerf.Network.forward at D = S = 32 (the shipped setting) / 128 (BASELINE config 3) depth planes: same
+    network (seed), scene and selection as mvsnerf_chain.npz, so only the outputs are stored (weights of every 8th ray)."""
+    ns = load_reference(MVS_CFG, ["enerf.cas_config.k_best", 2, "enerf.cas_config.num_samples", f"[{D}]"])
+    torch.manual_seed(13)
+    net = ns["boost_mvs_network"].Network(preprocess=True).eval()
+    g = torch.Generator().manual_seed(17)
+    for name, buf in net.named_buffers():
+        if name.endswith("running_mean"):
+            buf.copy_(torch.randn(buf.shape, generator=g) * 0.1)
+        elif name.endswith("running_var"):
+            buf.copy_(torch.rand(buf.shape, generator=g) * 0.5 + 0.75)
+    scene = _mvs_scene(9)
+    net.view_selection_outputs = {"synth_0": [2, 1]}
+    batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in scene.items()}
+    with torch.no_grad(), _ZeroedEmpty():
+        ret = net(batch)
+    out = {"out_rgb_level0": _np(ret["rgb_level0"]), "out_depth_level0": _np(ret["depth_level0"]),
+           "out_weights_level0_every8": _np(ret["weights_level0"][:, ::8].contiguous()), "planes": np.array([D], dtype=np.int64)}
+    _save(f"mvsnerf_chain_d{D}.npz", out)
+
+
 if __name__ == "__main__":
     case = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if case == "all":
-        for c in ("ops", "chain_eval", "chain_pretrain", "single", "mvs_ops", "mvs_chain"):
+        for c in ("ops", "chain_eval", "chain_pretrain", "single", "mvs_ops", "mvs_chain", "mvs_chain_d32", "mvs_chain_d128"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), c])
     elif case == "ops":
         gen_ops()
@@ -331,5 +355,7 @@ if __name__ == "__main__":
         gen_mvs_ops()
     elif case == "mvs_chain":
         gen_mvs_chain()
+    elif case in ("mvs_chain_d32", "mvs_chain_d128"):
+        gen_mvs_chain_planes(int(case.split("_d")[1]))
     else:
         raise SystemExit(f"unknown case {case}")

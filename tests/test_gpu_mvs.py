@@ -168,3 +168,23 @@ def test_fused_mvs_render_matches_fetch_plus_mlp(S):
                           scene["all_src_inps"][0], packed)
     got1 = ops.mvs_render(*args, packed)
     assert float((got2["raw"] - got1["raw"]).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("D", [32, 128])
+def test_boost_mvsnerf_forward_at_32_and_128_planes(D, strict_fp32):
+    """The shipped setting (32 planes) and BASELINE config 3 (128 planes) against outputs of the UNMODIFIED reference
+    (tests/golden/mvsnerf_chain_d{D}.npz; inputs, weights and selection are those of mvsnerf_chain.npz): the strict
+    path at 1e-4; the config-3 engine (bf16 cost volume + the fused fp16-operand tcgen05 render) at 1e-2."""
+    gc = load_golden("mvsnerf_chain.npz")
+    gd = load_golden(f"mvsnerf_chain_d{D}.npz")
+    net, batch = _net_and_batch(gc)
+    net.rc = RenderConfig.mvsnerf_eval(2, D)
+    out = net({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    close(out["rgb_level0"], gd.np("out_rgb_level0"), f"D={D} strict rgb")
+    close(out["depth_level0"], gd.np("out_depth_level0"), f"D={D} strict depth")
+    close(out["weights_level0"][:, ::8], gd.np("out_weights_level0_every8"), f"D={D} strict weights")
+    net.volume_dtype = torch.bfloat16
+    net.mlp_engine = "umma"
+    out2 = net({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    close(out2["rgb_level0"], gd.np("out_rgb_level0"), f"D={D} config-3 engine rgb", rtol=1e-2)
+    close(out2["depth_level0"], gd.np("out_depth_level0"), f"D={D} config-3 engine depth", rtol=1e-2)

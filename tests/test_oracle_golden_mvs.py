@@ -82,3 +82,20 @@ def test_boost_mvsnerf_forward_chain():
     for t in E.view_triples(4, 3):
         masks.append(M.visibility_mask_2d(batch["rays_0"], batch["all_src_exts"][:, t], batch["all_src_ixts"][:, t], H, W))
     assert M.search_k_best_views(masks, 2) == g.np("view_selection").tolist()
+
+
+def test_boost_mvsnerf_forward_chain_32_planes():
+    """The oracle at the shipped 32 planes / samples against the reference's outputs (mvsnerf_chain_d32.npz: same
+    network, scene and selection as mvsnerf_chain.npz)."""
+    g = load_golden("mvsnerf_chain.npz")
+    gd = load_golden("mvsnerf_chain_d32.npz")
+    rc = RenderConfig.mvsnerf_eval(2, 32)
+    net = MvsnerfModules().eval()
+    net.load_state_dict({k[3:]: g.t(k) for k in g.keys() if k.startswith("sd_")}, strict=True)
+    batch = {k[3:]: g.t(k) for k in g.keys() if k.startswith("in_")}
+    batch["meta"] = {"scene": ["synth"], "tar_view": torch.tensor([0])}
+    with torch.no_grad():
+        out = M.boost_mvsnerf_forward(net, batch, rc, g.t("k_best")[None])
+    same(out["rgb_level0"], gd.np("out_rgb_level0"), "rgb, 32 planes")
+    same(out["depth_level0"], gd.np("out_depth_level0"), "depth, 32 planes")
+    same(out["weights_level0"][:, ::8], gd.np("out_weights_level0_every8"), "weights, 32 planes")
