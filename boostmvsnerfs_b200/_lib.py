@@ -134,7 +134,8 @@ class MvsMarchParams(C.Structure):
                 ("volume", C.c_void_p), ("Cv", i32), ("Dv", i32), ("hv", i32), ("wv", i32),
                 ("vol_c_stride", i64), ("vol_d_stride", i64), ("vol_y_stride", i64), ("vol_x_stride", i64),
                 ("rgb", C.c_void_p), ("rgb_scale", f32), ("rgb_shift", f32),
-                ("mlp_in", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p)]
+                ("mlp_in", C.c_void_p), ("z_vals", C.c_void_p), ("vis_mask", C.c_void_p), ("vis_count", C.c_void_p),
+                ("rgb_nhwc4", i32), ("reserved0", i32)]
 
 
 class MvsRenderParams(C.Structure):

@@ -179,6 +179,17 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
     const float u = div_rn(add_rn(div_rn(qx, qz), 0.f), isx), w = div_rn(add_rn(div_rn(qy, qz), 0.f), isy);
     const float gx = sub_rn(mul_rn(u, 2.f), 1.f), gy = sub_rn(mul_rn(w, 2.f), 1.f);
     const bool inside = (gx > -1.f) && (gx < 1.f) && (gy > -1.f) && (gy < 1.f);
+    if (p.rgb_nhwc4) {                                     // (N,H,W,4): one 16-byte load per tap
+      const Tap2 tp = border_taps(gx, gy, p.H, p.W, (int64_t)p.W * 4, 4);
+      const float* fi = p.rgb + (int64_t)views[v] * 4 * plane;
+      const float4 a = ldg4(fi + tp.o00), b = ldg4(fi + tp.o01), cc = ldg4(fi + tp.o10), d = ldg4(fi + tp.o11);
+      const float sc = p.rgb_scale, sf = p.rgb_shift;
+      f[8 + v * 4 + 0] = fmaf(tp.w11, fmaf(d.x, sc, sf), fmaf(tp.w10, fmaf(cc.x, sc, sf), fmaf(tp.w01, fmaf(b.x, sc, sf), tp.w00 * fmaf(a.x, sc, sf))));
+      f[8 + v * 4 + 1] = fmaf(tp.w11, fmaf(d.y, sc, sf), fmaf(tp.w10, fmaf(cc.y, sc, sf), fmaf(tp.w01, fmaf(b.y, sc, sf), tp.w00 * fmaf(a.y, sc, sf))));
+      f[8 + v * 4 + 2] = fmaf(tp.w11, fmaf(d.z, sc, sf), fmaf(tp.w10, fmaf(cc.z, sc, sf), fmaf(tp.w01, fmaf(b.z, sc, sf), tp.w00 * fmaf(a.z, sc, sf))));
+      f[8 + v * 4 + 3] = inside ? 1.f : 0.f;
+      continue;
+    }
     const Tap2 tp = border_taps(gx, gy, p.H, p.W, p.W, 1);
     const float* fi = p.rgb + (int64_t)views[v] * 3 * plane;
 #pragma unroll

@@ -94,12 +94,19 @@ class BoostMvsnerfNetwork(nn.Module):
             projs = torch.stack(projs).to(dev)
             planes = torch.stack(planes).to(dev)
         with self._stage('cost_volume_img'):
-            vols = torch.empty((K, 9 + 32, D, h + 2 * PAD, w + 2 * PAD), device=dev, dtype=self.volume_dtype)
+            if self.mlp_engine == 'umma':
+                # channels-last volumes: K1b's 41 stores per voxel are contiguous, cuDNN keeps the layout, and the fused
+                # render kernel fetches a regularised voxel with two 16-byte loads
+                vols = torch.empty((K, D, h + 2 * PAD, w + 2 * PAD, 9 + 32), device=dev, dtype=self.volume_dtype).permute(0, 4, 1, 2, 3)
+            else:
+                vols = torch.empty((K, 9 + 32, D, h + 2 * PAD, w + 2 * PAD), device=dev, dtype=self.volume_dtype)
             for k in range(K):
                 ops.cost_volume_var_img(feats, small, triples[k], projs[k], planes[k], PAD, out=vols[k])
         with self._stage('cost_reg_2'):
             reg = self.cost_reg_2(vols.float() if vols.dtype != torch.float32 else vols)   # (K,8,D,hp,wp)
             del vols
+            if self.mlp_engine == 'umma' and reg.stride(1) != 1:
+                reg = reg.contiguous(memory_format=torch.channels_last_3d)
         rays = batch['rays_0'][0]
         R = rays.shape[0]
         raw = torch.empty((K, R, S, 4), device=dev)
@@ -111,10 +118,12 @@ class BoostMvsnerfNetwork(nn.Module):
             if self._packed is None or self._packed[0] != key:
                 from .mlp_pack import pack_mvs_weights_umma
                 self._packed = (key, pack_mvs_weights_umma(self.nerf))
+            rgb4 = inps.new_zeros((N, H, W, 4))                # (N,H,W,4): one 16-byte load per colour tap
+            rgb4[..., :3] = inps.permute(0, 2, 3, 1)
             for k in range(K):
                 with self._stage('render_fused'):
                     ops.mvs_render(rays, S, triples[k], batch['all_src_exts'][0], batch['all_src_ixts'][0], H, W,
-                                   float(nears[k]), float(fars[k]), reg[k], inps, self._packed[1], PAD,
+                                   float(nears[k]), float(fars[k]), reg[k], rgb4, self._packed[1], PAD,
                                    out={'raw': raw[k], 'z_vals': z[k], 'vis_mask': mask[k]})
             return raw, mask, z, nears, fars
         chunk = max(1, min(R, self.mlp_chunk_bytes // (S * 86 * 4)))

@@ -1075,7 +1075,10 @@ def mvs_render(rays, S, views, src_exts, src_ixts, H, W, near, far, volume, rgb,
     rays = _cf32(rays, "rays")
     src_exts, src_ixts = _cf32(src_exts, "src_exts"), _cf32(src_ixts, "src_ixts")
     _f32(volume, "volume")
-    rgb = _cf32(rgb, "rgb")
+    rgb = _cf32(rgb, "rgb")                                  # (N,3,H,W) planar, or (N,H,W,4) [r,g,b,x]
+    nhwc4 = rgb.dim() == 4 and rgb.shape[-1] == 4 and rgb.shape[1] == H and rgb.shape[2] == W
+    if not nhwc4 and tuple(rgb.shape[1:]) != (3, H, W):
+        raise BmvError(f"mvs_render: rgb must be (N,3,{H},{W}) or (N,{H},{W},4), got {tuple(rgb.shape)}")
     dev = rays.device
     R = rays.shape[0]
     n = R - ray_begin if n_rays is None else n_rays
@@ -1095,6 +1098,7 @@ def mvs_render(rays, S, views, src_exts, src_ixts, H, W, near, far, volume, rgb,
     p.Cv, p.Dv, p.hv, p.wv = volume.shape
     p.vol_c_stride, p.vol_d_stride, p.vol_y_stride, p.vol_x_stride = volume.stride()
     p.rgb = rgb.data_ptr()
+    p.rgb_nhwc4 = int(nhwc4)
     p.rgb_scale, p.rgb_shift = rgb_affine
     res = dict(out) if out else {}
 

@@ -364,6 +364,9 @@ typedef struct bmv_mvs_march_params {
   float* z_vals;                /* (n_rays,S) or NULL */
   float* vis_mask;              /* (n_rays,S) or NULL */
   int32_t* vis_count;           /* (n_rays,S) or NULL */
+  int32_t rgb_nhwc4;            /* 1: rgb is (N,H,W,4) [r,g,b,x] instead of planar (one 16-byte load per bilinear tap);
+                                   honoured by bmv_mvs_render_umma only */
+  int32_t reserved0;
 } bmv_mvs_march_params;
 BMV_API int bmv_mvs_march_fetch(const bmv_mvs_march_params* p, bmv_stream_t stream);
 
