@@ -556,9 +556,17 @@ def main_ours(args):
                 e1.record()
                 barrier()
                 ms_sh = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-                err = {k: max_over_ranks(float((so[k].float() - one[k].float()).abs().max() / one[k].float().abs().max().clamp_min(1e-12)))
-                       for k in one}
-                sharded[label] = {"ms_per_frame": ms_sh, "rays_per_sec": rays_per_frame / (ms_sh * 1e-3), "max_err_vs_single": err}
+                err, over = {}, {}
+                for k in one:
+                    d = (so[k].float() - one[k].float()).abs()
+                    rng = one[k].float().abs().max().clamp_min(1e-12)
+                    err[k] = max_over_ranks(float(d.max() / rng))
+                    # a sample on a frustum edge flips its visibility count under a 1-ulp change of the depth map (a chain
+                    # computed alone on a rank takes other cuDNN algorithms than in a batch of K): the count tells a
+                    # handful of such rays from a systematic difference
+                    over[k] = int(max_over_ranks(float((d > 1e-4 * rng).sum())))
+                sharded[label] = {"ms_per_frame": ms_sh, "rays_per_sec": rays_per_frame / (ms_sh * 1e-3), "max_err_vs_single": err,
+                                  "elements_over_1e-4_of_range": over}
                 so = None
                 sg.close()                                   # a live graph with NCCL work would hang destroy_process_group
                 del sg
