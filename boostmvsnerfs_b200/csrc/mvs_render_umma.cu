@@ -6,14 +6,17 @@
 // the TF32-class engine of BASELINE config 3 (bf16 cost volume, 1e-2 tolerance).  The strict path keeps the fp32
 // cuBLAS module (network_mvs.py).
 //
-// Structure (one CTA per SM, persistent, 10 warps):
-//   warps 0-3 / 4-7  own the 128 sample rows of tile 0 / tile 1 (thread = row): gather (march, NDC, positional encoding,
-//                    trilinear volume fetch, per-view colour, 3-D visibility), write the row of each layer's A operand
-//                    (fp16, UMMA K-major SWIZZLE_NONE: K-chunk c = 128 rows x 16 B), read accumulators back with
-//                    tcgen05.ld (lane = row) for gate * ReLU, alpha, rgb;
-//   warp 8           issues every tcgen05.mma (M = 128, N = 128 / 64, K = 16) of both tiles, ping-pong: while tile 0 is
+// Structure (one CTA per SM, persistent, 18 warps):
+//   warps 0-7 / 8-15 own the 128 sample rows of tile 0 / tile 1, TWO threads per row (warp w and w + 4 of a tile read the
+//                    same TMEM lane quarter): the gather is split between them (march + NDC by both; visibility,
+//                    positional encoding and view direction by half 0; trilinear volume fetch and per-view colours by
+//                    half 1), each writes its K-chunks of the layer's A operand (fp16, UMMA K-major SWIZZLE_NONE: chunk c =
+//                    128 rows x 16 B) and handles 64 of the 128 accumulator columns in the epilogues (tcgen05.ld, gate *
+//                    ReLU); partial alpha / rgb sums meet in shared memory.  (First version: one thread per row, 8
+//                    row-owner warps: issue 20 %, tensor pipe 15 %, long scoreboard 8 per issue — latency bound.)
+//   warp 16          issues every tcgen05.mma (M = 128, N = 128 / 64, K = 16) of both tiles, ping-pong: while tile 0 is
 //                    in its epilogue the tensor core works on tile 1;
-//   warp 9           streams the weights (256 KB per pass, more than fits) through a 4-slot ring of 18 KB panels with
+//   warp 17          streams the weights (256 KB per pass, more than fits) through a 4-slot ring of 18 KB panels with
 //                    cp.async.bulk + mbarrier transaction counts; a panel is used by BOTH tiles before its slot is
 //                    released by tcgen05.commit.
 // Layers as MMAs (biases ride on constant-1 columns of the operands):
@@ -38,7 +41,7 @@ constexpr int MR_BIAS_BYTES = 5 * 4096;                           // bias K-step
 constexpr int MR_VEC_FLOATS = 328;                                // wa[128], Wr[3][64], ba, br[3], pad
 constexpr int MR_V_WA = 0, MR_V_WR = 128, MR_V_BA = 320, MR_V_BR = 321;
 constexpr int MR_PACK_BYTES = MR_PANEL_BYTES_TOTAL + MR_BIAS_BYTES + MR_VEC_FLOATS * 4;
-constexpr int MR_THREADS = 320;
+constexpr int MR_THREADS = 576;                       // 16 row-owner warps + MMA issuer + weight producer
 constexpr size_t MR_SMEM = (size_t)2 * MR_TILE_BYTES + (size_t)MR_SLOTS * MR_SLOT + MR_BIAS_BYTES + MR_VEC_FLOATS * 4 + 128;
 
 __host__ __device__ constexpr int mr_panel_bytes(int p) { return p == 0 ? 8192 : (p == 15 ? 18432 : 16384); }
@@ -75,9 +78,11 @@ __device__ __forceinline__ void mr_put(unsigned char* tile, int chunk, int row, 
 
 // ---- the per-sample gather of bmv_mvs_march_fetch (same arithmetic; the positional encoding by angle doubling:
 // sin / cos of 2^k x from those of x, error < 2^k ulp, far below the fp16 rounding of the operand)
+// part 0: visibility + outputs, P and V operands; part 1: F operand (volume fetch, colours).  Both recompute the march
+// and the NDC coordinates (cheap) instead of exchanging them.
 template <int V>
 __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const ViewCam* cams, const int* views, int64_t i, bool live,
-                                          unsigned char* tile, int row) {
+                                          unsigned char* tile, int row, int part) {
   const int64_t li = i / p.S;
   const int s = (int)(i - li * p.S);
   const int64_t r = p.ray_begin + li;
@@ -88,13 +93,15 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
   const float z = add_rn(mul_rn(near, sub_rn(1.f, t)), mul_rn(far, t));
   const float x = add_rn(ra.x, mul_rn(ra.w, z)), y = add_rn(ra.y, mul_rn(rb.x, z)), zz = add_rn(ra.z, mul_rn(rb.y, z));
   const float isx = (float)(p.W - 1), isy = (float)(p.H - 1);
-  int cnt = 0;
+  if (part == 0) {
+    int cnt = 0;
 #pragma unroll
-  for (int v = 0; v < V; ++v) cnt += point_visible(cams[v], x, y, zz, isx, isy) ? 1 : 0;
-  if (live) {
-    if (p.z_vals) p.z_vals[i] = z;
-    if (p.vis_mask) p.vis_mask[i] = div_rn((float)cnt, (float)V);
-    if (p.vis_count) p.vis_count[i] = cnt;
+    for (int v = 0; v < V; ++v) cnt += point_visible(cams[v], x, y, zz, isx, isy) ? 1 : 0;
+    if (live) {
+      if (p.z_vals) p.z_vals[i] = z;
+      if (p.vis_mask) p.vis_mask[i] = div_rn((float)cnt, (float)V);
+      if (p.vis_count) p.vis_count[i] = cnt;
+    }
   }
   const ViewCam& c0 = cams[0];
   float ndc[3];
@@ -114,7 +121,7 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
     ndc[0] = u; ndc[1] = w; ndc[2] = dz;
   }
   // ---- P operand: [ndc(3), sin(2^k ndc) k = 0..9 (30), cos (30), 1]
-  {
+  if (part == 0) {
     float pe[64];
     pe[0] = ndc[0]; pe[1] = ndc[1]; pe[2] = ndc[2];
 #pragma unroll
@@ -132,6 +139,21 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
     pe[63] = 1.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) mr_put(tile, MR_P + c, row, pe + 8 * c);
+  }
+  if (part == 0) {
+    // ---- V operand: view direction in the reference camera frame, then the constant 1
+    float vd[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) vd[c] = 0.f;
+    const float n = sqrtf(ra.w * ra.w + rb.x * rb.x + rb.y * rb.y);
+    const float ux = div_rn(ra.w, n), uy = div_rn(rb.x, n), uz = div_rn(rb.y, n);
+    vd[0] = dot3_gemm(ux, uy, uz, c0.E[0], c0.E[1], c0.E[2]);
+    vd[1] = dot3_gemm(ux, uy, uz, c0.E[4], c0.E[5], c0.E[6]);
+    vd[2] = dot3_gemm(ux, uy, uz, c0.E[8], c0.E[9], c0.E[10]);
+    vd[3] = 1.f;
+    mr_put(tile, MR_V, row, vd);
+    mr_put(tile, MR_V + 1, row, vd + 8);
+    return;
   }
   // ---- F operand: [vox(8), (rgb, in) x 3 (12), 1, 0 ...]
   float f[32];
@@ -205,20 +227,6 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) mr_put(tile, MR_F + c, row, f + 8 * c);
-  // ---- V operand: view direction in the reference camera frame, then the constant 1
-  {
-    float vd[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) vd[c] = 0.f;
-    const float n = sqrtf(ra.w * ra.w + rb.x * rb.x + rb.y * rb.y);
-    const float ux = div_rn(ra.w, n), uy = div_rn(rb.x, n), uz = div_rn(rb.y, n);
-    vd[0] = dot3_gemm(ux, uy, uz, c0.E[0], c0.E[1], c0.E[2]);
-    vd[1] = dot3_gemm(ux, uy, uz, c0.E[4], c0.E[5], c0.E[6]);
-    vd[2] = dot3_gemm(ux, uy, uz, c0.E[8], c0.E[9], c0.E[10]);
-    vd[3] = 1.f;
-    mr_put(tile, MR_V, row, vd);
-    mr_put(tile, MR_V + 1, row, vd + 8);
-  }
 }
 
 __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_render_params rp) {
@@ -234,6 +242,8 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
   __shared__ int s_view[V];
   __shared__ __align__(8) uint64_t s_full[MR_SLOTS], s_empty[MR_SLOTS], s_acc[2], s_aready[2];
   __shared__ uint32_t s_tmem;
+  __shared__ float s_alpha[2][2][128];                 // [tile][half][row]: partial alpha dots over 64 columns each
+  __shared__ float s_rgb[2][128][4];                   // [tile][row]: half 1's partial rgb sums
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const unsigned char* gw = reinterpret_cast<const unsigned char*>(rp.weights);
@@ -243,10 +253,10 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
   if (tid < V) s_view[tid] = p.view[tid];
   if (tid == 0) {
     for (int s = 0; s < MR_SLOTS; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(smem_u32(&s_acc[w]), 1); mbar_init(smem_u32(&s_aready[w]), 128); }
+    for (int w = 0; w < 2; ++w) { mbar_init(smem_u32(&s_acc[w]), 1); mbar_init(smem_u32(&s_aready[w]), 256); }
   }
   __syncwarp();
-  if (warp == 8) tmem_alloc_512(smem_u32(&s_tmem));
+  if (warp == 16) tmem_alloc_512(smem_u32(&s_tmem));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -259,9 +269,9 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const uint32_t idesc128 = umma_idesc(128), idesc64 = umma_idesc(64);
 
-  if (warp < 8) {
+  if (warp < 16) {
     // =============================================================== row owners: gather + epilogues
-    const int tile_id = warp >> 2, row = tid & 127;
+    const int tile_id = warp >> 3, half = (warp >> 2) & 1, row = (warp & 3) * 32 + (tid & 31);
     unsigned char* tile = sA + tile_id * MR_TILE_BYTES;
     const uint32_t acc_col = tmem_base + (uint32_t)(tile_id * 256) + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t gate_col = acc_col + 128;
@@ -271,10 +281,9 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
       const int64_t si_raw = (pair * 2 + tile_id) * 128 + row;
       const bool live = si_raw < n_samples;
       const int64_t si = live ? si_raw : n_samples - 1;
-      mr_gather<V>(p, cams, s_view, si, live, tile, row);
+      mr_gather<V>(p, cams, s_view, si, live, tile, row, half);
       proxy_fence_async();
       mbar_arrive(mb_ready);
-      float alpha = 0.f;
 #pragma unroll 1
       for (int phase = 0; phase < 8; ++phase) {
         mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
         if (phase < 7) {
           float dot = 0.f;
 #pragma unroll 1
-          for (int c4 = 0; c4 < 4; ++c4) {
+          for (int c4 = 2 * half; c4 < 2 * half + 2; ++c4) {      // this thread's 64 of the 128 columns
             float a[32];
             tmem_ld32(acc_col + 32 * c4, a);
             if (phase < 6) {
@@ -302,34 +311,43 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
 #pragma unroll
             for (int q = 0; q < 4; ++q) mr_put(tile, MR_H + 4 * c4 + q, row, a + 8 * q);
           }
-          if (phase == 5) alpha = fmaxf(dot + sVec[MR_V_BA], 0.f);
+          if (phase == 5) s_alpha[tile_id][half][row] = dot;
           proxy_fence_async();
           tc_fence_before();
           mbar_arrive(mb_ready);
         } else {
-          float r0 = sVec[MR_V_BR], r1 = sVec[MR_V_BR + 1], r2 = sVec[MR_V_BR + 2];
-#pragma unroll 1
-          for (int c2 = 0; c2 < 2; ++c2) {
+          // 64 output columns: 32 per thread, partial rgb sums meet in shared memory
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+          {
             float a[32];
-            tmem_ld32(acc_col + 32 * c2, a);
+            tmem_ld32(acc_col + 32 * half, a);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = fmaxf(a[j], 0.f);
-              r0 = fmaf(sVec[MR_V_WR + 32 * c2 + j], v, r0);
-              r1 = fmaf(sVec[MR_V_WR + 64 + 32 * c2 + j], v, r1);
-              r2 = fmaf(sVec[MR_V_WR + 128 + 32 * c2 + j], v, r2);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w0 = *reinterpret_cast<const float4*>(sVec + MR_V_WR + 32 * half + j);
+              const float4 w1 = *reinterpret_cast<const float4*>(sVec + MR_V_WR + 64 + 32 * half + j);
+              const float4 w2 = *reinterpret_cast<const float4*>(sVec + MR_V_WR + 128 + 32 * half + j);
+              const float v0 = fmaxf(a[j], 0.f), v1 = fmaxf(a[j + 1], 0.f), v2 = fmaxf(a[j + 2], 0.f), v3 = fmaxf(a[j + 3], 0.f);
+              r0 = fmaf(w0.w, v3, fmaf(w0.z, v2, fmaf(w0.y, v1, fmaf(w0.x, v0, r0))));
+              r1 = fmaf(w1.w, v3, fmaf(w1.z, v2, fmaf(w1.y, v1, fmaf(w1.x, v0, r1))));
+              r2 = fmaf(w2.w, v3, fmaf(w2.z, v2, fmaf(w2.y, v1, fmaf(w2.x, v0, r2))));
             }
           }
           tc_fence_before();
-          if (live) {
+          if (half == 1) *reinterpret_cast<float4*>(s_rgb[tile_id][row]) = make_float4(r0, r1, r2, 0.f);
+          bar_sync_named(1 + tile_id, 256);                  // the two halves of every row of this tile
+          if (half == 0 && live) {
+            const float4 q = *reinterpret_cast<const float4*>(s_rgb[tile_id][row]);
+            r0 += q.x + sVec[MR_V_BR]; r1 += q.y + sVec[MR_V_BR + 1]; r2 += q.z + sVec[MR_V_BR + 2];
             float4 o;
-            o.x = 1.f / (1.f + expf(-r0)); o.y = 1.f / (1.f + expf(-r1)); o.z = 1.f / (1.f + expf(-r2)); o.w = alpha;
+            o.x = 1.f / (1.f + expf(-r0)); o.y = 1.f / (1.f + expf(-r1)); o.z = 1.f / (1.f + expf(-r2));
+            o.w = fmaxf(s_alpha[tile_id][0][row] + s_alpha[tile_id][1][row] + sVec[MR_V_BA], 0.f);
             reinterpret_cast<float4*>(rp.raw)[si] = o;
           }
+          bar_sync_named(1 + tile_id, 256);                  // s_rgb / s_alpha are rewritten by the next pass
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // =============================================================== MMA issuer
     const bool elected = elect_one();
     uint32_t par_ready[2] = {0u, 0u};
@@ -402,7 +420,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc_512(tmem_base);
+  if (warp == 16) tmem_dealloc_512(tmem_base);
 }
 
 }  // namespace bmv
