@@ -206,6 +206,7 @@ ENTRY_POINTS = {
     "bmv_render_rays_mma": RenderRaysParams,
     "bmv_render_rays_umma": RenderRaysParams,
     "bmv_render_rays_multi": RenderMultiParams,
+    "bmv_render_rays_multi_umma": RenderMultiParams,
     "bmv_cost_volume_var_img": CostVolumeImgParams,
     "bmv_mvs_march_fetch": MvsMarchParams,
     "bmv_mvs_render_umma": MvsRenderParams,

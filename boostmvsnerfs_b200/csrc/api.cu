@@ -47,6 +47,7 @@ extern "C" BMV_API int bmv_sizeof_params(const char* entry) {
   if (!strcmp(entry, "bmv_fpn_stem")) return (int)sizeof(bmv_fpn_stem_params);
   if (!strcmp(entry, "bmv_mvs_render_umma")) return (int)sizeof(bmv_mvs_render_params);
   if (!strcmp(entry, "bmv_render_rays_multi")) return (int)sizeof(bmv_render_multi_params);
+  if (!strcmp(entry, "bmv_render_rays_multi_umma")) return (int)sizeof(bmv_render_multi_params);
   if (!strcmp(entry, "bmv_frame_psnr_accumulate")) return (int)sizeof(bmv_frame_psnr_params);
   if (!strcmp(entry, "bmv_frame_to_u8")) return (int)sizeof(bmv_frame_to_u8_params);
   return -1;

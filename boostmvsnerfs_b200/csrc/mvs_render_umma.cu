@@ -26,6 +26,8 @@
 //   L5    = PE63 . W5p + h . W5h   K 64 + 128 (skip connection)               ;  h = relu(acc * gate), alpha = relu(wa.h + ba)
 //   FL    = h . Wf + 1 . bf        K 128 + 16                                 ;  feature (no activation)
 //   VL    = [feature | dir3 1] . Wv  K 128 + 16, N 64                         ;  rgb = sigmoid(Wr . relu(acc) + br)
+#include <stdlib.h>
+
 #include "raygen_common.cuh"
 #include "umma.cuh"
 
@@ -46,17 +48,6 @@ constexpr size_t MR_SMEM = (size_t)2 * MR_TILE_BYTES + (size_t)MR_SLOTS * MR_SLO
 
 __host__ __device__ constexpr int mr_panel_bytes(int p) { return p == 0 ? 8192 : (p == 15 ? 18432 : 16384); }
 __host__ __device__ constexpr int mr_panel_offset(int p) { return p == 0 ? 0 : 8192 + (p - 1) * 16384; }
-
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
 
 // n_ksteps K = 16 steps: D (+)= A[chunks a0, a0+1, ...] . B[chunks b0, ...]
 __device__ __forceinline__ void mr_issue(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_chunk, int n_ksteps,
@@ -164,27 +155,45 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
     const int wp = p.wv, hp = p.hv;
     const float gx = sub_rn(mul_rn(ndc[0], 2.f), 1.f), gy = sub_rn(mul_rn(ndc[1], 2.f), 1.f), gz = sub_rn(mul_rn(ndc[2], 2.f), 1.f);
     const float ix = unnormalize_ac(gx, wp), iy = unnormalize_ac(gy, hp), iz = unnormalize_ac(gz, p.Dv);
-    if (coord_ok(ix) && coord_ok(iy) && coord_ok(iz)) {
-      const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
-      const float fx1 = ix - x0, fy1 = iy - y0, fz1 = iz - z0;
-      const float fx0 = (x0 + 1.f) - ix, fy0 = (y0 + 1.f) - iy, fz0 = (z0 + 1.f) - iz;
+    // branch-free: validity folded into the weights, invalid corners read a clamped (valid) address with weight 0 — all 16
+    // loads of a channels-last voxel set are in flight together (with `if (!ok) continue` per corner they were eight
+    // dependent round trips: 30 % of this kernel's stall samples, ncu round2j)
+    const bool fin = coord_ok(ix) && coord_ok(iy) && coord_ok(iz);
+    const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+    const float fx1 = ix - x0, fy1 = iy - y0, fz1 = iz - z0;
+    const float fx0 = (x0 + 1.f) - ix, fy0 = (y0 + 1.f) - iy, fz0 = (z0 + 1.f) - iz;
+    const float wm = (float)(wp - 1), hm = (float)(hp - 1), dm = (float)(p.Dv - 1);
+    const bool vx0 = fin && x0 >= 0.f && x0 <= wm, vx1 = fin && x0 + 1.f >= 0.f && x0 + 1.f <= wm;
+    const bool vy0 = fin && y0 >= 0.f && y0 <= hm, vy1 = fin && y0 + 1.f >= 0.f && y0 + 1.f <= hm;
+    const bool vz0 = fin && z0 >= 0.f && z0 <= dm, vz1 = fin && z0 + 1.f >= 0.f && z0 + 1.f <= dm;
+    const float wx[2] = {vx0 ? fx0 : 0.f, vx1 ? fx1 : 0.f};
+    const float wy[2] = {vy0 ? fy0 : 0.f, vy1 ? fy1 : 0.f};
+    const float wz[2] = {vz0 ? fz0 : 0.f, vz1 ? fz1 : 0.f};
+    const int64_t xi = fin ? (int64_t)fminf(fmaxf(x0, 0.f), wm) : 0, yi = fin ? (int64_t)fminf(fmaxf(y0, 0.f), hm) : 0;
+    const int64_t zi = fin ? (int64_t)fminf(fmaxf(z0, 0.f), dm) : 0;
+    const int64_t ox1 = (vx0 && vx1) ? p.vol_x_stride : 0, oy1 = (vy0 && vy1) ? p.vol_y_stride : 0, oz1 = (vz0 && vz1) ? p.vol_d_stride : 0;
+    const float* b000 = p.volume + zi * p.vol_d_stride + yi * p.vol_y_stride + xi * p.vol_x_stride;
+    if (p.vol_c_stride == 1) {                            // channels-last volume: two 16-byte loads per corner
+      float4 va[8], vb[8];
 #pragma unroll
       for (int corner = 0; corner < 8; ++corner) {
-        const int bx = corner & 1, by = (corner >> 1) & 1, bz = corner >> 2;
-        const float cxf = x0 + bx, cyf = y0 + by, czf = z0 + bz;
-        const bool ok = cxf >= 0.f && cxf <= (float)(wp - 1) && cyf >= 0.f && cyf <= (float)(hp - 1) &&
-                        czf >= 0.f && czf <= (float)(p.Dv - 1);
-        if (!ok) continue;
-        const float wgt = (bx ? fx1 : fx0) * (by ? fy1 : fy0) * (bz ? fz1 : fz0);
-        const float* src = p.volume + (int64_t)czf * p.vol_d_stride + (int64_t)cyf * p.vol_y_stride + (int64_t)cxf * p.vol_x_stride;
-        if (p.vol_c_stride == 1) {                        // channels-last volume: two 16-byte loads per corner
-          const float4 a = ldg4(src), b = ldg4(src + 4);
-          f[0] = fmaf(wgt, a.x, f[0]); f[1] = fmaf(wgt, a.y, f[1]); f[2] = fmaf(wgt, a.z, f[2]); f[3] = fmaf(wgt, a.w, f[3]);
-          f[4] = fmaf(wgt, b.x, f[4]); f[5] = fmaf(wgt, b.y, f[5]); f[6] = fmaf(wgt, b.z, f[6]); f[7] = fmaf(wgt, b.w, f[7]);
-        } else {
+        const float* src = b000 + ((corner & 1) ? ox1 : 0) + (((corner >> 1) & 1) ? oy1 : 0) + ((corner >> 2) ? oz1 : 0);
+        va[corner] = ldg4(src); vb[corner] = ldg4(src + 4);
+      }
 #pragma unroll
-          for (int c = 0; c < 8; ++c) f[c] = fmaf(wgt, __ldg(src + (int64_t)c * p.vol_c_stride), f[c]);
-        }
+      for (int corner = 0; corner < 8; ++corner) {
+        const float wgt = (wx[corner & 1] * wy[(corner >> 1) & 1]) * wz[corner >> 2];
+        const float4 a = va[corner], b = vb[corner];
+        f[0] = fmaf(wgt, a.x, f[0]); f[1] = fmaf(wgt, a.y, f[1]); f[2] = fmaf(wgt, a.z, f[2]); f[3] = fmaf(wgt, a.w, f[3]);
+        f[4] = fmaf(wgt, b.x, f[4]); f[5] = fmaf(wgt, b.y, f[5]); f[6] = fmaf(wgt, b.z, f[6]); f[7] = fmaf(wgt, b.w, f[7]);
+      }
+    } else {
+#pragma unroll
+      for (int corner = 0; corner < 8; ++corner) {
+        const float wgt = (wx[corner & 1] * wy[(corner >> 1) & 1]) * wz[corner >> 2];
+        const float* src = b000 + ((corner & 1) ? ox1 : 0) + (((corner >> 1) & 1) ? oy1 : 0) + ((corner >> 2) ? oz1 : 0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = fmaf(wgt, __ldg(src + (int64_t)c * p.vol_c_stride), f[c]);
       }
     }
   }
@@ -229,7 +238,10 @@ __device__ __forceinline__ void mr_gather(const bmv_mvs_march_params& p, const V
   for (int c = 0; c < 4; ++c) mr_put(tile, MR_F + c, row, f + 8 * c);
 }
 
-__global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_render_params rp) {
+// dbg_panel_bytes (environment BMV_MR_DEBUG_PANEL, measurement only: WRONG results) takes the kernel apart: low 20 bits > 0:
+// copy only that many bytes of every weight panel; bit 20: skip the gather; bit 21: skip the MMAs (commits only); bit 22:
+// skip the epilogue arithmetic
+__global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_render_params rp, int dbg_panel_bytes) {
   constexpr int V = 3;
   const bmv_mvs_march_params& p = rp.g;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -243,7 +255,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
   __shared__ __align__(8) uint64_t s_full[MR_SLOTS], s_empty[MR_SLOTS], s_acc[2], s_aready[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_alpha[2][2][128];                 // [tile][half][row]: partial alpha dots over 64 columns each
-  __shared__ float s_rgb[2][128][4];                   // [tile][row]: half 1's partial rgb sums
+  __shared__ __align__(16) float s_rgb[2][128][4];                   // [tile][row]: half 1's partial rgb sums
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const unsigned char* gw = reinterpret_cast<const unsigned char*>(rp.weights);
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
       const int64_t si_raw = (pair * 2 + tile_id) * 128 + row;
       const bool live = si_raw < n_samples;
       const int64_t si = live ? si_raw : n_samples - 1;
-      mr_gather<V>(p, cams, s_view, si, live, tile, row, half);
+      if (!(dbg_panel_bytes & (1 << 20))) mr_gather<V>(p, cams, s_view, si, live, tile, row, half);
       proxy_fence_async();
       mbar_arrive(mb_ready);
 #pragma unroll 1
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
         if (phase < 7) {
           float dot = 0.f;
 #pragma unroll 1
-          for (int c4 = 2 * half; c4 < 2 * half + 2; ++c4) {      // this thread's 64 of the 128 columns
+          for (int c4 = 2 * half; c4 < 2 * half + 2 && !(dbg_panel_bytes & (4 << 20)); ++c4) {      // this thread's 64 of the 128 columns
             float a[32];
             tmem_ld32(acc_col + 32 * c4, a);
             if (phase < 6) {
@@ -349,53 +361,103 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
     }
   } else if (warp == 16) {
     // =============================================================== MMA issuer
+    // The whole warp walks the issue code on warp-uniform values and ONE elected lane executes the MMAs; every descriptor
+    // is a (low word, constant high word) pair whose low word is computed OUTSIDE the elected branch (uniform datapath)
+    // and only advanced by compile-time constants inside it.  The first version built the 64-bit descriptors inside
+    // `if (elected)`: ~290 clk per tcgen05.mma (R2UR / elect sequences per operand), i.e. the issuer — not the tensor
+    // pipe (15 % busy), not the row owners, not the weight stream (measured: 1 KB panels, two threads per row and a
+    // branch-free gather all left the 39 ms unchanged) — bounded the kernel.
     const bool elected = elect_one();
+    constexpr uint32_t HI = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
+    constexpr uint32_t LBO_A = (uint32_t)(MR_CHUNK >> 4) << 16;         // K-chunks of an A operand are 2048 B apart
+    constexpr uint32_t LBO_B128 = (2048u >> 4) << 16, LBO_B64 = (1024u >> 4) << 16;
     uint32_t par_ready[2] = {0u, 0u};
-    uint32_t panel_n = 0;                                   // panels consumed so far (ring position)
-    const uint32_t aT[2] = {smem_u32(sA), smem_u32(sA + MR_TILE_BYTES)};
-    const uint32_t ring = smem_u32(sRing), bias = smem_u32(sBias);
-    // panels used per phase: {first panel, count}
-    const int ph_first[8] = {0, 2, 4, 6, 8, 10, 13, 15}, ph_count[8] = {2, 2, 2, 2, 2, 3, 2, 1};
+    uint32_t panel_n = 0;                                               // panels consumed so far (ring position)
+    const uint32_t ring = smem_u32(sRing);
+    const uint32_t bias_lo = ((smem_u32(sBias) & 0x3FFFFu) >> 4) | LBO_B128;
+    uint32_t aP[2], aF[2], aFb[2], aV[2], aH[2], aH2[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const uint32_t base = smem_u32(sA + w * MR_TILE_BYTES);
+      aP[w] = (((base + MR_P * MR_CHUNK) & 0x3FFFFu) >> 4) | LBO_A;
+      aF[w] = (((base + MR_F * MR_CHUNK) & 0x3FFFFu) >> 4) | LBO_A;
+      aFb[w] = (((base + (MR_F + 2) * MR_CHUNK) & 0x3FFFFu) >> 4) | LBO_A;
+      aV[w] = (((base + MR_V * MR_CHUNK) & 0x3FFFFu) >> 4) | LBO_A;
+      aH[w] = (((base + MR_H * MR_CHUNK) & 0x3FFFFu) >> 4) | LBO_A;
+      aH2[w] = (((base + (MR_H + 8) * MR_CHUNK) & 0x3FFFFu) >> 4) | LBO_A;
+    }
+    const int ph_count[8] = {2, 2, 2, 2, 2, 3, 2, 1};
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll 1
       for (int phase = 0; phase < 8; ++phase) {
+        // ring slots of this phase's panels as descriptor low words (uniform: the shuffle pins it for the compiler)
+        const uint32_t pn = __shfl_sync(0xffffffffu, panel_n, 0);
+        const uint32_t s0 = (((ring + ((pn + 0) % MR_SLOTS) * MR_SLOT) & 0x3FFFFu) >> 4);
+        const uint32_t s1 = (((ring + ((pn + 1) % MR_SLOTS) * MR_SLOT) & 0x3FFFFu) >> 4);
+        const uint32_t s2 = (((ring + ((pn + 2) % MR_SLOTS) * MR_SLOT) & 0x3FFFFu) >> 4);
+        const uint32_t bias_p = bias_lo + (uint32_t)(((phase == 6 ? 4 : phase - 1) * 4096) >> 4);
 #pragma unroll 1
         for (int w = 0; w < 2; ++w) {
           mbar_wait(smem_u32(&s_aready[w]), par_ready[w]); par_ready[w] ^= 1u;
           if (w == 0) {
             for (int q = 0; q < ph_count[phase]; ++q) {
-              const uint32_t n = panel_n + q;
+              const uint32_t n = pn + q;
               mbar_wait(smem_u32(&s_full[n % MR_SLOTS]), (n / MR_SLOTS) & 1u);
             }
           }
           __syncwarp();
           tc_fence_after();
-          if (elected) {
-            const uint32_t acc = tmem_base + (uint32_t)(w * 256), gate = acc + 128;
-            const uint32_t a = aT[w];
-            auto slot = [&](int q) { return ring + ((panel_n + q) % MR_SLOTS) * MR_SLOT; };
+          const uint32_t acc = tmem_base + (uint32_t)(w * 256), gate = acc + 128;
+          const uint32_t ap = aP[w], af = aF[w], afb = aFb[w], av = aV[w], ah = aH[w], ah2 = aH2[w];
+          if (elected && (dbg_panel_bytes & (2 << 20))) {
+            umma_commit(smem_u32(&s_acc[w]));
+            if (w == 1) {
+              umma_commit(smem_u32(&s_empty[(pn + 0) % MR_SLOTS]));
+              if (ph_count[phase] > 1) umma_commit(smem_u32(&s_empty[(pn + 1) % MR_SLOTS]));
+              if (ph_count[phase] > 2) umma_commit(smem_u32(&s_empty[(pn + 2) % MR_SLOTS]));
+            }
+          } else if (elected) {
             if (phase == 0) {
-              mr_issue(gate, a + MR_F * MR_CHUNK, slot(0), 2048, 2, idesc128, false);
-              mr_issue(acc, a + MR_P * MR_CHUNK, slot(1), 2048, 4, idesc128, false);
-            } else if (phase <= 4) {
-              mr_issue(acc, a + MR_H * MR_CHUNK, slot(0), 2048, 4, idesc128, false);
-              mr_issue(acc, a + (MR_H + 8) * MR_CHUNK, slot(1), 2048, 4, idesc128, true);
-              mr_issue(acc, a + (MR_F + 2) * MR_CHUNK, bias + (phase - 1) * 4096, 2048, 1, idesc128, true);
+              umma_f16_lohi<false>(gate, af, HI, s0 | LBO_B128, HI, idesc128);
+              umma_f16_lohi<true>(gate, af + 256, HI, (s0 | LBO_B128) + 256, HI, idesc128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks == 0) umma_f16_lohi<false>(acc, ap, HI, s1 | LBO_B128, HI, idesc128);
+                else umma_f16_lohi<true>(acc, ap + 256 * ks, HI, (s1 | LBO_B128) + 256 * ks, HI, idesc128);
+              }
             } else if (phase == 5) {
-              mr_issue(acc, a + MR_P * MR_CHUNK, slot(0), 2048, 4, idesc128, false);
-              mr_issue(acc, a + MR_H * MR_CHUNK, slot(1), 2048, 4, idesc128, true);
-              mr_issue(acc, a + (MR_H + 8) * MR_CHUNK, slot(2), 2048, 4, idesc128, true);
-            } else if (phase == 6) {
-              mr_issue(acc, a + MR_H * MR_CHUNK, slot(0), 2048, 4, idesc128, false);
-              mr_issue(acc, a + (MR_H + 8) * MR_CHUNK, slot(1), 2048, 4, idesc128, true);
-              mr_issue(acc, a + (MR_F + 2) * MR_CHUNK, bias + 4 * 4096, 2048, 1, idesc128, true);
-            } else {
-              mr_issue(acc, a + MR_H * MR_CHUNK, slot(0), 1024, 8, idesc64, false);
-              mr_issue(acc, a + MR_V * MR_CHUNK, slot(0) + 16 * 1024, 1024, 1, idesc64, true);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks == 0) umma_f16_lohi<false>(acc, ap, HI, s0 | LBO_B128, HI, idesc128);
+                else umma_f16_lohi<true>(acc, ap + 256 * ks, HI, (s0 | LBO_B128) + 256 * ks, HI, idesc128);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_f16_lohi<true>(acc, ah + 256 * ks, HI, (s1 | LBO_B128) + 256 * ks, HI, idesc128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_f16_lohi<true>(acc, ah2 + 256 * ks, HI, (s2 | LBO_B128) + 256 * ks, HI, idesc128);
+            } else if (phase == 7) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                if (ks == 0) umma_f16_lohi<false>(acc, ah, HI, s0 | LBO_B64, HI, idesc64);
+                else umma_f16_lohi<true>(acc, ah + 256 * ks, HI, (s0 | LBO_B64) + 128 * ks, HI, idesc64);
+              }
+              umma_f16_lohi<true>(acc, av, HI, (s0 | LBO_B64) + 128 * 8, HI, idesc64);
+            } else {                                        // L1..L4 and the feature layer: h . W + 1 . b
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks == 0) umma_f16_lohi<false>(acc, ah, HI, s0 | LBO_B128, HI, idesc128);
+                else umma_f16_lohi<true>(acc, ah + 256 * ks, HI, (s0 | LBO_B128) + 256 * ks, HI, idesc128);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_f16_lohi<true>(acc, ah2 + 256 * ks, HI, (s1 | LBO_B128) + 256 * ks, HI, idesc128);
+              umma_f16_lohi<true>(acc, afb, HI, bias_p, HI, idesc128);
             }
             umma_commit(smem_u32(&s_acc[w]));
-            if (w == 1)                                       // both tiles have read this phase's panels
-              for (int q = 0; q < ph_count[phase]; ++q) umma_commit(smem_u32(&s_empty[(panel_n + q) % MR_SLOTS]));
+            if (w == 1) {                                   // both tiles have read this phase's panels
+              umma_commit(smem_u32(&s_empty[(pn + 0) % MR_SLOTS]));
+              if (ph_count[phase] > 1) umma_commit(smem_u32(&s_empty[(pn + 1) % MR_SLOTS]));
+              if (ph_count[phase] > 2) umma_commit(smem_u32(&s_empty[(pn + 2) % MR_SLOTS]));
+            }
           }
           __syncwarp();
         }
@@ -409,8 +471,17 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int q = 0; q < MR_NPANEL; ++q, ++n) {
           const uint32_t s = n % MR_SLOTS;
-          if (n >= MR_SLOTS) mbar_wait(smem_u32(&s_empty[s]), ((n / MR_SLOTS) - 1) & 1u);
-          const uint32_t bytes = (uint32_t)mr_panel_bytes(q);
+          if (n >= MR_SLOTS) {                               // back off between polls: this lane only feeds the ring
+            const uint32_t mb = smem_u32(&s_empty[s]), par = ((n / MR_SLOTS) - 1) & 1u;
+            uint32_t done = 0;
+            while (true) {
+              asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                           : "=r"(done) : "r"(mb), "r"(par) : "memory");
+              if (done) break;
+              __nanosleep(64);
+            }
+          }
+          const uint32_t bytes = (dbg_panel_bytes & 0xFFFFF) > 0 ? (uint32_t)(dbg_panel_bytes & 0xFFFFF) : (uint32_t)mr_panel_bytes(q);
           mbar_expect_tx(smem_u32(&s_full[s]), bytes);
           bulk_g2s(smem_u32(sRing + s * MR_SLOT), gw + mr_panel_offset(q), bytes, smem_u32(&s_full[s]));
         }
@@ -454,6 +525,7 @@ extern "C" BMV_API int bmv_mvs_render_umma(const bmv_mvs_render_params* rp, bmv_
   }
   const int64_t pairs = ceil_div64(ceil_div64(p->n_rays * p->S, 128), 2);
   const unsigned blocks = (unsigned)(pairs < kNumSMs ? pairs : kNumSMs);   // persistent: the CTA owns all 512 TMEM columns
-  mvs_render_umma_kernel<<<blocks, MR_THREADS, MR_SMEM, (cudaStream_t)stream>>>(*rp);
+  static const int dbg_panel = getenv("BMV_MR_DEBUG_PANEL") ? atoi(getenv("BMV_MR_DEBUG_PANEL")) : 0;
+  mvs_render_umma_kernel<<<blocks, MR_THREADS, MR_SMEM, (cudaStream_t)stream>>>(*rp, dbg_panel);
   return check_launch("bmv_mvs_render_umma");
 }

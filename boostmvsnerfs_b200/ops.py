@@ -979,8 +979,9 @@ def render_rays_multi_supported(volumes, im_feat, rgb, V):
         return False
     K, _, D, h, w = volumes.shape
     N, _, Hf, Wf = im_feat.shape
-    return (volumes.dtype == torch.float32 and tuple(volumes.stride()[1:]) == (1, h * w * 8, w * 8, 8) and volumes.stride(0) % 4 == 0
-            and im_feat.dtype == torch.float32 and tuple(im_feat.stride()[1:]) == (1, Wf * 8, 8) and im_feat.stride(0) % 4 == 0
+    return (volumes.dtype == torch.float32 and tuple(volumes.stride()[1:]) == (1, h * w * 8, w * 8, 8) and volumes.stride(0) % 8 == 0
+            and volumes.data_ptr() % 32 == 0 and im_feat.data_ptr() % 32 == 0
+            and im_feat.dtype == torch.float32 and tuple(im_feat.stride()[1:]) == (1, Wf * 8, 8) and im_feat.stride(0) % 8 == 0
             and rgb.dtype == torch.float32 and tuple(rgb.stride()[1:]) == (1, Wf * 4, 4) and rgb.stride(0) % 4 == 0
             and N <= MAX_VIEWS and D * h * w * 8 < 2 ** 31 and Hf * Wf * 8 < 2 ** 31)
 
@@ -995,8 +996,10 @@ def _rows_f32(t, name):
 
 def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, im_feat, rgb, cams, triples, packed_weights,
                       render_scale=1.0, rgb_affine=(0.5, 0.5), ray_begin=0, n_rays=None, out=None, want_count=False,
-                      views_dev=None, grid_rows=None, vol_row0=0, map_row0=0):
-    """K3 + per-sample MLP of ALL K chains in one persistent launch (bmv_render_rays_multi).
+                      views_dev=None, grid_rows=None, vol_row0=0, map_row0=0, engine=None):
+    """K3 + per-sample MLP of ALL K chains in one persistent launch: bmv_render_rays_multi (engine 'mma': warp-level
+    mma.sync MLP, weights from mlp_pack.pack_nerf_weights_mma) or bmv_render_rays_multi_umma (engine 'umma': tcgen05 MLP
+    with accumulators in tensor memory, weights from mlp_pack.pack_nerf_weights_umma).  engine=None: told by the packing.
     depth, std (K,hv,wv); near_far (K,2,hv,wv) or shared (2,hv,wv); volumes (K,8,D,hv,wv) channels-last-3d; triples: K
     view triples (host list) — or views_dev, an int32 CUDA tensor (K,3) read by the kernel (graph-replay friendly);
     packed_weights from mlp_pack.pack_nerf_weights_mma.
@@ -1009,9 +1012,14 @@ def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, i
     if std.shape != depth.shape or near_far.shape[-2:] != depth.shape[-2:]:
         raise BmvError("render_rays_multi: depth / std / near_far must cover the same rows")
     w = packed_weights
-    if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()
-            and w.numel() == _lib.load().bmv_render_rays_mma_weight_words()):
-        raise BmvError("render_rays_multi: weights must come from mlp_pack.pack_nerf_weights_mma")
+    words = {"mma": _lib.load().bmv_render_rays_mma_weight_words(), "umma": _lib.load().bmv_render_rays_umma_weight_words()}
+    if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.int32 and w.is_contiguous()):
+        raise BmvError("render_rays_multi: weights must be a contiguous int32 CUDA tensor from mlp_pack")
+    if engine is None:
+        engine = next((e for e, n_ in words.items() if w.numel() == n_), None)
+    if engine not in words or w.numel() != words[engine]:
+        raise BmvError("render_rays_multi: weights must come from mlp_pack.pack_nerf_weights_mma (engine 'mma') or "
+                       "pack_nerf_weights_umma (engine 'umma')")
     if volumes.shape[0] != K or std.shape != depth.shape:
         raise BmvError("render_rays_multi: depth / std / volumes must agree on K")
     dev = depth.device
@@ -1062,7 +1070,7 @@ def render_rays_multi(depth, std, near_far, rays, H, W, depth_inv, S, volumes, i
     if want_count or "vis_count" in res:
         mp.vis_count = mk("vis_count", (K, n, S), torch.int32)
     mp.mlp_weights = w.data_ptr()
-    _lib.call("bmv_render_rays_multi", mp, _stream())
+    _lib.call("bmv_render_rays_multi_umma" if engine == "umma" else "bmv_render_rays_multi", mp, _stream())
     return res
 
 

@@ -537,6 +537,10 @@ typedef struct bmv_render_multi_params {
   int64_t nf_plane_stride;
 } bmv_render_multi_params;
 BMV_API int bmv_render_rays_multi(const bmv_render_multi_params* p, bmv_stream_t stream);
+/* Same contract with the MLP on the 5th-generation tensor cores (csrc/render_multi_umma.cu: tcgen05.mma, accumulators in
+ * tensor memory, a dedicated issuer warp, two threads per sample row); mlp_weights: mlp_pack.pack_nerf_weights_umma
+ * (bmv_render_rays_umma_weight_words words).  z / visibility bit-identical to bmv_render_rays_multi, raw to ~1e-5. */
+BMV_API int bmv_render_rays_multi_umma(const bmv_render_multi_params* p, bmv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * f4  output sinks: what the reference's evaluator / visualiser consume, produced on the device.

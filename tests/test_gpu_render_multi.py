@@ -129,3 +129,54 @@ def test_network_uses_the_multi_launch_and_matches_per_chain(monkeypatch):
     for k in a:
         err = float((a[k] - b[k]).abs().max()) / float(b[k].abs().max())
         assert err <= 2e-5, (k, err)
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 engine
+@pytest.mark.parametrize("H,W,K,smooth,depth_inv", [(64, 96, 4, True, False), (64, 96, 1, False, False), (96, 160, 8, False, False),
+                                                    (64, 96, 3, True, True), (32, 40, 2, True, False)])
+def test_umma_engine_matches_the_mma_engine(H, W, K, smooth, depth_inv):
+    """bmv_render_rays_multi_umma (MLP as tcgen05.mma, accumulators in tensor memory, two threads per sample row) against
+    bmv_render_rays_multi: the gather is the same code (z / visibility bit-identical), the MLP the same hi / lo split
+    products in another summation order."""
+    from boostmvsnerfs_b200 import mlp_pack, ops
+    N, S = 4, 2
+    scene, depth, std, nf, vols, feat, rgb, cams, nerf, packed, triples = _setup(H, W, N, K, 11 + K, smooth, depth_inv)
+    packed_u = mlp_pack.pack_nerf_weights_umma(nerf)
+    rays = scene["rays_1"][0]
+    ref = ops.render_rays_multi(depth, std, nf, rays, H, W, depth_inv, S, vols, feat, rgb, cams, triples, packed, want_count=True)
+    got = ops.render_rays_multi(depth, std, nf, rays, H, W, depth_inv, S, vols, feat, rgb, cams, triples, packed_u, want_count=True)
+    for k_ in ("z_vals", "vis_count", "vis_mask"):
+        assert torch.equal(got[k_], ref[k_]), k_
+    for k in range(K):
+        err = float((got["raw"][k] - ref["raw"][k]).abs().max()) / float(ref["raw"][k].abs().max())
+        assert err <= (3e-5 if smooth else 2e-4), f"chain {k}: raw differs by {err:.2e}"
+    # and against the fp32 FMA kernel (no tensor cores at all)
+    packed_f = mlp_pack.pack_nerf_weights(nerf)
+    one = ops.render_rays(depth[0], std[0], nf[0], rays, H, W, depth_inv, S, vols[0], feat, rgb, cams, triples[0], packed_f, engine="fma")
+    err = float((got["raw"][0] - one["raw"]).abs().max()) / float(one["raw"].abs().max())
+    assert err <= (3e-5 if smooth else 2e-4), f"vs fp32 FMA kernel: {err:.2e}"
+
+
+def test_umma_engine_device_views_ragged_range_generated_rays_and_replay():
+    from boostmvsnerfs_b200 import mlp_pack, ops
+    H, W, N, K, S = 64, 96, 4, 4, 2
+    scene, depth, std, nf, vols, feat, rgb, cams, nerf, packed, triples = _setup(H, W, N, K, 5, True)
+    packed_u = mlp_pack.pack_nerf_weights_umma(nerf)
+    rays = scene["rays_1"][0]
+    full = ops.render_rays_multi(depth, std, nf, rays, H, W, False, S, vols, feat, rgb, cams, triples, packed_u)
+    again = ops.render_rays_multi(depth, std, nf, rays, H, W, False, S, vols, feat, rgb, cams, triples, packed_u)
+    assert torch.equal(again["raw"], full["raw"]), "not deterministic"
+    vdev = torch.tensor(triples, device="cuda", dtype=torch.int32)
+    got = ops.render_rays_multi(depth, std, nf, rays, H, W, False, S, vols, feat, rgb, cams, None, packed_u, views_dev=vdev)
+    for k_ in ("raw", "z_vals", "vis_mask"):
+        assert torch.equal(got[k_], full[k_]), k_
+    b, n = 37, 1001                                  # ragged: tiles with dead rows, a second tile slot without work
+    part = ops.render_rays_multi(depth, std, nf[0], rays, H, W, False, S, vols, feat, rgb, cams, triples, packed_u, ray_begin=b, n_rays=n)
+    assert torch.equal(part["raw"], full["raw"][:, b:b + n]) and torch.equal(part["vis_mask"], full["vis_mask"][:, b:b + n])
+    tiny = ops.render_rays_multi(depth[:1], std[:1], nf[:1], rays, H, W, False, S, vols[:1], feat, rgb, cams, triples[:1], packed_u,
+                                 ray_begin=5, n_rays=17)          # a single 128-sample tile: one CTA, tile slot 1 idle
+    assert torch.equal(tiny["raw"][0], full["raw"][0, 5:22])
+    gen = ops.RayGenerator.from_cameras(scene["tar_ext"][0].cpu(), scene["tar_ixt"][0].cpu(), H, W, 1.0, "cuda")
+    g = ops.render_rays_multi(depth, std, nf, gen, H, W, False, S, vols, feat, rgb, cams, triples, packed_u)
+    assert torch.equal(g["z_vals"], full["z_vals"]) and torch.equal(g["vis_mask"], full["vis_mask"])
+    assert float((g["raw"] - full["raw"]).abs().max()) <= 1e-6
