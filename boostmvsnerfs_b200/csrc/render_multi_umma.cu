@@ -75,7 +75,7 @@ __device__ __forceinline__ void ru_kstep(uint32_t d, uint32_t a, uint32_t b, uin
 
 // every tcgen05.mma of one phase of one tile (executed by one elected lane); acc: the tile's TMEM base, a: descriptor low
 // word of the tile's chunk 0, wB: shared-memory address of the packed weights
-template <int PHASE>
+template <int PHASE, bool COLOR_PER_VIEW = false>
 __device__ __forceinline__ void ru_issue_phase(uint32_t acc, uint32_t a, uint32_t wB) {
   constexpr uint32_t CH = RU_CHUNK >> 4;                   // one K-chunk in descriptor address units
   auto desc_lo = [](uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); };
@@ -96,6 +96,18 @@ __device__ __forceinline__ void ru_issue_phase(uint32_t acc, uint32_t a, uint32_
     const uint32_t id = umma_idesc(64), bL0 = desc_lo(wB + UW_L0, 64 * 16);
     ru_kstep<false>(acc + RU_T_L0, a + RU_POOLED * CH, bL0, id);
     ru_kstep<true>(acc + RU_T_L0, a + RU_VOX * CH, bL0 + 2 * 64, id);
+  } else if constexpr (COLOR_PER_VIEW) {                   // color.0, all of K per view: C_v at columns 64 v (192 in all)
+    const uint32_t id = umma_idesc(64), bCS = desc_lo(wB + UW_CS, 64 * 16), bCV = desc_lo(wB + UW_CV, 64 * 16);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const uint32_t d = acc + 64 * v;
+      ru_kstep<false>(d, a + RU_HID * CH, bCS, id);
+#pragma unroll
+      for (int ks = 1; ks < 4; ++ks) ru_kstep<true>(d, a + (RU_HID + 2 * ks) * CH, bCS + ks * 2 * 64, id);
+      ru_kstep<true>(d, a + RU_POOLED * CH, bCS + 4 * 2 * 64, id);
+      ru_kstep<true>(d, a + RU_VOX * CH, bCS + 5 * 2 * 64, id);
+      ru_kstep<true>(d, a + (RU_F + 2 * v) * CH, bCV, id);
+    }
   } else {                                                 // color.0: shared part once, per-view parts next to it
     const uint32_t id = umma_idesc(64), bCS = desc_lo(wB + UW_CS, 64 * 16), bCV = desc_lo(wB + UW_CV, 64 * 16);
     ru_kstep<false>(acc + RU_T_CS, a + RU_HID * CH, bCS, id);
@@ -110,7 +122,7 @@ __device__ __forceinline__ void ru_issue_phase(uint32_t acc, uint32_t a, uint32_
 
 // All 8 warps of a tile: publish the operand rows just written (and retire the TMEM loads of the columns about to be
 // overwritten); the warp that arrives LAST issues the phase's MMAs and commits them to the tile's accumulator barrier.
-template <int PHASE>
+template <int PHASE, int WARPS = RU_ROW_WARPS / 2, bool COLOR_PER_VIEW = false>
 __device__ __forceinline__ void ru_publish_and_issue(uint32_t* cnt, uint32_t mb_acc, uint32_t acc, uint32_t a, uint32_t wB,
                                                      bool no_mma, int lane) {
   proxy_fence_async();                 // generic-proxy st.shared -> visible to the tensor core (async proxy)
@@ -119,7 +131,7 @@ __device__ __forceinline__ void ru_publish_and_issue(uint32_t* cnt, uint32_t mb_
   uint32_t last = 0;
   if (lane == 0) {
     __threadfence_block();             // release: this warp's rows before the count
-    last = atomicAdd(cnt, 1u) == (uint32_t)(RU_ROW_WARPS / 2 - 1);
+    last = atomicAdd(cnt, 1u) == (uint32_t)(WARPS - 1);
   }
   last = __shfl_sync(0xffffffffu, last, 0);
   if (last) {                          // warp-uniform
@@ -127,7 +139,7 @@ __device__ __forceinline__ void ru_publish_and_issue(uint32_t* cnt, uint32_t mb_
     __threadfence_block();             // acquire: the other warps' rows
     tc_fence_after();
     if (elect_one()) {
-      if (!no_mma) ru_issue_phase<PHASE>(acc, a, wB);
+      if (!no_mma) ru_issue_phase<PHASE, COLOR_PER_VIEW>(acc, a, wB);
       umma_commit(mb_acc);
     }
     __syncwarp();
@@ -425,6 +437,312 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
   if (warp == 0) tmem_dealloc_512(tmem_base);
 }
 
+
+// ----------------------------------------------------------------------------------------- warp-specialised variant
+// The two-threads-per-row kernel above runs two latency-bound chains per SM (measured: per tile 13.6 k clk gather + 14.9 k
+// clk MLP phases, the gather of one tile under the phases of the other and nothing else to fill the waits).  Here the
+// gather is taken OFF the chain: per tile 4 MLP warps (thread = sample row: operand rows, MMA issue, epilogues) and 4
+// gather warps (thread = sample of the NEXT unit) that hand the 53 gathered values of a row over through 56 spare columns
+// of the row's own TMEM lane (tcgen05.st / tcgen05.ld; both warps sit on the same lane quarter) — shared memory is full
+// (two 80 KB operand tiles + weights), tensor memory is not once the colour layer accumulates all of K per view
+// (3 x 64 columns, 63 MMAs) instead of keeping the shared part apart (256 columns, 27 MMAs).
+//   TMEM per tile: G_v 32v | fc 96 | lr0 112..175 ; colour C_v 64v (0..191) ; staging 192..247: f_v at 192 + 16 v, vox at 240.
+constexpr int RU_T_STAGE = 192;
+
+template <bool GEN, bool INV>
+__global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_ws_kernel(bmv_render_multi_params mp, int dbg) {
+  constexpr int V = 3;
+  const bmv_raygen_fetch_params& p = mp.g;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  unsigned char* sW = smem;                                              // hi block, lo block
+  const float* sV = reinterpret_cast<const float*>(smem + 2 * UW_BLOCK);  // fp32 vectors
+  unsigned char* sA = smem + RU_PACK_PADDED;                             // two operand tiles
+  __shared__ LeanCam cams[BMV_MAX_VIEWS];
+  __shared__ float s_tar_c[4];
+  __shared__ int s_view[BMV_MAX_VOLUMES * V];
+  __shared__ __align__(8) uint64_t s_acc[2], s_staged[2], s_free[2];
+  __shared__ uint32_t s_cnt[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  for (int i = tid * 16; i < UMMA_PACK_BYTES; i += RU_THREADS * 16)
+    *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(mp.mlp_weights) + i));
+  if (tid < mp.K * V) {                                    // device-resident ids are clamped: they index shared memory
+    const int id = mp.views ? __ldg(mp.views + tid) : mp.views_host[tid];
+    s_view[tid] = min(max(id, 0), mp.n_views - 1);
+  }
+  if (tid < mp.n_views) cams[tid] = lean_cam_load(p, tid);
+  if (tid < 3) s_tar_c[tid] = p.tar_center[tid];
+  if (tid == 0) {
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(smem_u32(&s_acc[w]), 1); mbar_init(smem_u32(&s_staged[w]), 128); mbar_init(smem_u32(&s_free[w]), 128);
+      s_cnt[w] = 0u;
+    }
+  }
+  if (tid < 256) {                                         // the constant K-chunk (1, 0, ..., 0) of both tiles
+    unsigned char* q = sA + (tid >> 7) * RU_TILE_BYTES + RU_ONE * RU_CHUNK + (tid & 127) * 16;
+    *reinterpret_cast<uint4*>(q) = make_uint4(0x00003C00u, 0, 0, 0);
+    *reinterpret_cast<uint4*>(q + RU_LO) = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc_512(smem_u32(&s_tmem));
+  proxy_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t S = (uint32_t)p.S;
+  const uint32_t n_samples = (uint32_t)(p.n_rays * p.S);
+  const uint32_t tiles = (n_samples + 127u) / 128u;        // per chain
+  const uint32_t total = tiles * (uint32_t)mp.K;           // work units: (chain, 128-sample tile)
+  const int tile_id = warp >> 3, wq = warp & 3, row = wq * 32 + lane;
+  const bool is_gather = (warp >> 2) & 1;
+  const uint32_t tcol = tmem_base + (uint32_t)(tile_id * 256) + ((uint32_t)(wq * 32) << 16);
+  const uint32_t mb_staged = smem_u32(&s_staged[tile_id]), mb_free = smem_u32(&s_free[tile_id]);
+
+  if (is_gather) {
+    // =============================================================== gather warps: one unit ahead of the tile's MLP warps
+    const RmCtx c = lean_ctx(p, mp.nf_plane_stride);
+    const bool unit_scale = p.render_scale == 1.f;
+    const int vol_row0 = mp.vol_row0, map_row0 = mp.map_row0;
+    const bool skip_gather = dbg & 1;
+    uint32_t par_free = 0;
+    bool first = true;
+    for (uint32_t u = blockIdx.x * 2u + (uint32_t)tile_id; u < total; u += gridDim.x * 2u) {
+      const uint32_t k = u / tiles;                        // chain (uniform over the tile's warps)
+      const uint32_t base = (u - k * tiles) * 128u;
+      const int* views = s_view + k * V;
+      const uint32_t si_raw = base + (uint32_t)row;
+      const bool live = si_raw < n_samples;
+      const uint32_t si = live ? si_raw : n_samples - 1u;
+      float vox[8], f[V][16];
+      if (!skip_gather) {
+        const uint32_t li = S == 2u ? (si >> 1) : si / S;
+        const int s = (int)(si - li * S);
+        const LeanPoint q = lean_sample_point<GEN, INV>(p, c, (uint32_t)p.ray_begin + li, s, mp.depth + (int64_t)k * mp.depth_k_stride,
+                                                        mp.std + (int64_t)k * mp.std_k_stride, mp.near_far + (int64_t)k * mp.nf_k_stride,
+                                                        map_row0);
+        lean_vox_fetch(p, c, mp.volume + (int64_t)k * mp.vol_k_stride, vol_row0, q, vox);
+        const float3 tt = lean_target_dir(q, s_tar_c);
+        int cnt = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int view = views[v];
+          const LeanCam& cam = cams[view];
+          const LeanTaps tp = lean_project(p, c, cam, q, unit_scale);
+          cnt += tp.visible ? 1 : 0;
+          lean_fetch_feat(p, view, tp, f[v]);
+          lean_fetch_rgb(p, view, tp, f[v] + 8);
+          lean_dir_feat(cam, q, tt, f[v] + 11);
+          f[v][15] = 0.f;
+        }
+        if (live) {
+          const int64_t oi = (int64_t)k * n_samples + si;
+          if (mp.z_vals) mp.z_vals[oi] = q.z;
+          if (mp.vis_mask) mp.vis_mask[oi] = lean_vis_score3(cnt);
+          if (mp.vis_count) mp.vis_count[oi] = cnt;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[v][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vox[j] = 0.f;
+      }
+      if (!first) {                                        // the MLP warps have read the previous unit's values
+        mbar_wait(mb_free, par_free); par_free ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+      }
+      first = false;
+#pragma unroll
+      for (int v = 0; v < V; ++v) tmem_st16(tcol + RU_T_STAGE + 16 * v, f[v]);
+      tmem_st8(tcol + RU_T_STAGE + 48, vox);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(mb_staged);
+    }
+  } else {
+    // =============================================================== MLP warps: thread = sample row
+    unsigned char* tile = sA + tile_id * RU_TILE_BYTES;
+    const uint32_t mb_acc = smem_u32(&s_acc[tile_id]);
+    uint32_t* cnt = &s_cnt[tile_id];
+    const uint32_t acc_t = tmem_base + (uint32_t)(tile_id * 256);
+    const uint32_t a_lo = ((smem_u32(tile) & 0x3FFFFu) >> 4) | ((uint32_t)(RU_CHUNK >> 4) << 16), wB = smem_u32(sW);
+    const bool no_mma = dbg & 2, skip_epi = dbg & 4;
+    const float ba = sV[UV_SC], bs = sV[UV_SC + 1], b2 = sV[UV_SC + 2];
+    uint32_t par_acc = 0, par_staged = 0;
+    for (uint32_t u = blockIdx.x * 2u + (uint32_t)tile_id; u < total; u += gridDim.x * 2u) {
+      const uint32_t k = u / tiles;
+      const uint32_t si_raw = (u - k * tiles) * 128u + (uint32_t)row;
+      const bool live = si_raw < n_samples;
+      // ------------------------------------------------------------ phase A: staged sample -> operand rows
+      mbar_wait(mb_staged, par_staged); par_staged ^= 1u;
+      __syncwarp();
+      tc_fence_after();
+      float rgbv[V][3];
+      {
+        float x[V][11];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float f[16];
+          tmem_ld16(tcol + RU_T_STAGE + 16 * v, f);
+          rgbv[v][0] = f[8]; rgbv[v][1] = f[9]; rgbv[v][2] = f[10];
+          ru_put(tile, RU_F + 2 * v, row, f);
+          ru_put(tile, RU_F + 2 * v + 1, row, f + 8);
+#pragma unroll
+          for (int ch = 0; ch < 11; ++ch) {
+            const float4 w = *reinterpret_cast<const float4*>(sV + UV_WV + ch * 4);
+            const float e = fmaf(w.w, f[14], fmaf(w.z, f[13], fmaf(w.y, f[12], fmaf(w.x, f[11], sV[UV_BV + ch]))));
+            x[v][ch] = f[ch] + fmaxf(e, 0.f);
+          }
+          ru_put(tile, RU_X + 2 * v, row, x[v]);
+          ru_put(tile, RU_X + 2 * v + 1, row, x[v][8], x[v][9], x[v][10], 0.f, 0.f, 0.f, 0.f, 0.f);
+        }
+        {
+          float vox[8];
+          tmem_ld8(tcol + RU_T_STAGE + 48, vox);
+          ru_put(tile, RU_VOX, row, vox);
+        }
+        tc_fence_before();
+        mbar_arrive(mb_free);                              // the staging columns may be rewritten
+        float var[11], mean[11];
+#pragma unroll
+        for (int ch = 0; ch < 11; ++ch) {
+          const float m = (x[0][ch] + x[1][ch] + x[2][ch]) * (1.f / 3.f);
+          const float e0 = x[0][ch] - m, e1 = x[1][ch] - m, e2 = x[2][ch] - m;
+          mean[ch] = m;
+          var[ch] = fmaf(e2, e2, fmaf(e1, e1, e0 * e0)) * 0.5f;
+        }
+        ru_put(tile, RU_VAR, row, var);
+        ru_put(tile, RU_VAR + 1, row, var[8], var[9], var[10], 0.f, 0.f, 0.f, 0.f, 1.f);       // K index 15: global_fc bias column
+        ru_put(tile, RU_MEAN, row, mean);
+        ru_put(tile, RU_MEAN + 1, row, mean[8], mean[9], mean[10], 0.f, 0.f, 0.f, 0.f, 0.f);
+      }
+      ru_publish_and_issue<0, 4, true>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      // ------------------------------------------------------------ phase B: ReLU, view soft-max, im = input of agg.fc
+      mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
+      __syncwarp();
+      tc_fence_after();
+      if (!skip_epi) {
+        float lg[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float G[32];
+          tmem_ld32(tcol + RU_T_G + 32 * v, G);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(sV + UV_WA + j);
+            a0 = fmaf(w.x, fmaxf(G[j], 0.f), a0); a1 = fmaf(w.y, fmaxf(G[j + 1], 0.f), a1);
+            a2 = fmaf(w.z, fmaxf(G[j + 2], 0.f), a2); a3 = fmaf(w.w, fmaxf(G[j + 3], 0.f), a3);
+          }
+          lg[v] = fmaxf((a0 + a1) + (a2 + a3) + ba, 0.f);
+        }
+        const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
+        const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
+        const float inv = 1.f / (e0 + e1 + e2);
+        const float w0 = e0 * inv, w1 = e1 * inv, w2 = e2 * inv;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float g0[16], g1[16], g2[16];
+          tmem_ld16(tcol + RU_T_G + 16 * h, g0);
+          tmem_ld16(tcol + RU_T_G + 32 + 16 * h, g1);
+          tmem_ld16(tcol + RU_T_G + 64 + 16 * h, g2);
+          float im[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) im[j] = fmaf(w2, fmaxf(g2[j], 0.f), fmaf(w1, fmaxf(g1[j], 0.f), w0 * fmaxf(g0[j], 0.f)));
+          ru_put(tile, RU_IM + 2 * h, row, im);
+          ru_put(tile, RU_IM + 2 * h + 1, row, im + 8);
+        }
+      }
+      ru_publish_and_issue<1, 4, true>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      // ------------------------------------------------------------ phase C: pooled = relu(fc + b)
+      mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
+      __syncwarp();
+      tc_fence_after();
+      if (!skip_epi) {
+        float pc[16];
+        tmem_ld16(tcol + RU_T_FC, pc);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(sV + UV_BFC + j);
+          pc[j] = fmaxf(pc[j] + b.x, 0.f); pc[j + 1] = fmaxf(pc[j + 1] + b.y, 0.f);
+          pc[j + 2] = fmaxf(pc[j + 2] + b.z, 0.f); pc[j + 3] = fmaxf(pc[j + 3] + b.w, 0.f);
+        }
+        ru_put(tile, RU_POOLED, row, pc);
+        ru_put(tile, RU_POOLED + 1, row, pc + 8);
+      }
+      ru_publish_and_issue<2, 4, true>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      // ------------------------------------------------------------ phase D: hid = relu(lr0), sigma
+      mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
+      __syncwarp();
+      tc_fence_after();
+      float sig = 0.f;
+      if (!skip_epi) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          float h[16];
+          tmem_ld16(tcol + RU_T_L0 + 16 * cb, h);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(sV + UV_WS + 16 * cb + j);
+            h[j] = fmaxf(h[j], 0.f); h[j + 1] = fmaxf(h[j + 1], 0.f); h[j + 2] = fmaxf(h[j + 2], 0.f); h[j + 3] = fmaxf(h[j + 3], 0.f);
+            a0 = fmaf(w.x, h[j], a0); a1 = fmaf(w.y, h[j + 1], a1); a2 = fmaf(w.z, h[j + 2], a2); a3 = fmaf(w.w, h[j + 3], a3);
+          }
+          ru_put(tile, RU_HID + 2 * cb, row, h);
+          ru_put(tile, RU_HID + 2 * cb + 1, row, h + 8);
+        }
+        sig = (a0 + a1) + (a2 + a3) + bs;
+        sig = sig > 20.f ? sig : log1pf(expf(sig));
+      }
+      ru_publish_and_issue<3, 4, true>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      // ------------------------------------------------------------ phase E: color.2 logits, view soft-max, rgb
+      mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
+      __syncwarp();
+      tc_fence_after();
+      float cl[V] = {0.f, 0.f, 0.f};
+      if (!skip_epi) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float cv[32];
+            tmem_ld32(tcol + 64 * v + 32 * h, cv);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(sV + UV_W2 + 32 * h + j);
+              a0 = fmaf(w.x, fmaxf(cv[j], 0.f), a0); a1 = fmaf(w.y, fmaxf(cv[j + 1], 0.f), a1);
+              a2 = fmaf(w.z, fmaxf(cv[j + 2], 0.f), a2); a3 = fmaf(w.w, fmaxf(cv[j + 3], 0.f), a3);
+            }
+          }
+          cl[v] = fmaxf((a0 + a1) + (a2 + a3) + b2, 0.f);
+        }
+      }
+      tc_fence_before();                                   // retire the loads before the next unit's MMAs rewrite the columns
+      if (live) {
+        const float mx = fmaxf(cl[0], fmaxf(cl[1], cl[2]));
+        const float e0 = expf(cl[0] - mx), e1 = expf(cl[1] - mx), e2 = expf(cl[2] - mx);
+        const float inv = 1.f / (e0 + e1 + e2);
+        float4 o;
+        o.x = (e0 * rgbv[0][0] + e1 * rgbv[1][0] + e2 * rgbv[2][0]) * inv;
+        o.y = (e0 * rgbv[0][1] + e1 * rgbv[1][1] + e2 * rgbv[2][1]) * inv;
+        o.z = (e0 * rgbv[0][2] + e1 * rgbv[1][2] + e2 * rgbv[2][2]) * inv;
+        o.w = sig;
+        reinterpret_cast<float4*>(mp.raw)[(int64_t)k * n_samples + si_raw] = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_512(tmem_base);
+}
+
 }  // namespace bmv
 
 extern "C" BMV_API int bmv_render_rays_multi_umma(const bmv_render_multi_params* mp, bmv_stream_t stream) {
@@ -438,6 +756,10 @@ extern "C" BMV_API int bmv_render_rays_multi_umma(const bmv_render_multi_params*
   if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
     const int smem = (int)RU_SMEM;
     cudaError_t e = cudaFuncSetAttribute(render_multi_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_ws_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(render_multi_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -453,6 +775,13 @@ extern "C" BMV_API int bmv_render_rays_multi_umma(const bmv_render_multi_params*
   const unsigned blocks = (unsigned)(want < kNumSMs ? want : kNumSMs);
   cudaStream_t st = (cudaStream_t)stream;
   static const int dbg = getenv("BMV_RU_DEBUG") ? atoi(getenv("BMV_RU_DEBUG")) : 0;
+  if (!(dbg & 16)) {                                       // default: the warp-specialised kernel
+    if (gen && invd) render_multi_umma_ws_kernel<true, true><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
+    else if (gen) render_multi_umma_ws_kernel<true, false><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
+    else if (invd) render_multi_umma_ws_kernel<false, true><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
+    else render_multi_umma_ws_kernel<false, false><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
+    return check_launch("bmv_render_rays_multi_umma");
+  }
   if (gen && invd) render_multi_umma_kernel<true, true><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
   else if (gen) render_multi_umma_kernel<true, false><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
   else if (invd) render_multi_umma_kernel<false, true><<<blocks, RU_THREADS, RU_SMEM, st>>>(*mp, dbg);
