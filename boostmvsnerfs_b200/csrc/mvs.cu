@@ -117,6 +117,98 @@ __global__ void __launch_bounds__(256) cost_volume_var_img_kernel(bmv_cost_volum
   }
 }
 
+// Channels-last variant (C = 32 dense (N,h,w,32) feature maps, channels-last output): a warp = 4 consecutive voxels x 8
+// lanes of 4 channels.  The tap set of a (voxel, source view) — nine IEEE divisions in mvs_taps — is computed by ONE of
+// the voxel's lanes and handed to the others with warp shuffles; a feature tap is one 16-byte load per lane (a whole
+// 128-byte texel per voxel and tap); the nine colour channels are spread over the voxel's lanes.  Same arithmetic, op for
+// op, as the thread-per-voxel kernel above (bit-identical output; tests/test_gpu_mvs.py).
+// The thread-per-voxel kernel did 32 scalar loads per tap: 2.2 ms per chain at C3 (D = 128, 184 x 288 padded grid).
+template <typename OutT>
+__global__ void __launch_bounds__(256) cost_volume_var_img_cl_kernel(bmv_cost_volume_img_params p) {
+  constexpr int V = 3, C = 32;
+  __shared__ float sP[V * 12];
+  if (threadIdx.x < V * 12) sP[threadIdx.x] = p.proj[threadIdx.x];
+  __syncthreads();
+  const int hp = p.h + 2 * p.pad, wp = p.w + 2 * p.pad;
+  const int lane = threadIdx.x & 31, cg = lane & 7;
+  const int xp_raw = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool live = xp_raw < wp;
+  const int xp = live ? xp_raw : wp - 1, yp = blockIdx.y, d = blockIdx.z;
+  const int x = xp - p.pad, y = yp - p.pad;
+  const float dep = __ldg(p.planes + d);
+  const bool in_ref = x >= 0 && x < p.w && y >= 0 && y < p.h;
+  // lane cg = i (1, 2) of a voxel computes the taps of source view i; everybody receives both sets
+  MvsTap mine;
+  {
+    const int i = (cg == 2) ? 2 : 1;
+    mine = mvs_taps(sP + i * 12, (float)x, (float)y, dep, p.h, p.w, (int64_t)p.w * C, C);
+  }
+  MvsTap tap[V];
+  float cnt = 1.f;
+#pragma unroll
+  for (int i = 1; i < V; ++i) {
+    const int src = (lane & ~7) + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tap[i].off[j] = __shfl_sync(0xffffffffu, mine.off[j], src);
+      tap[i].w[j] = __shfl_sync(0xffffffffu, mine.w[j], src);
+    }
+    tap[i].inside = __shfl_sync(0xffffffffu, mine.inside ? 1 : 0, src) != 0;
+    cnt = add_rn(cnt, tap[i].inside ? 1.f : 0.f);
+  }
+  const float inv_cnt = div_rn(1.f, cnt);
+  OutT* out = reinterpret_cast<OutT*>(p.out) + (int64_t)d * p.out_d_stride + (int64_t)yp * p.out_y_stride + (int64_t)xp * p.out_x_stride;
+  // ---- colour channels 0..8 (reference rgb, then each source image warped): lane cg takes channel cg, lane 0 also 8
+  const int64_t plane = (int64_t)p.h * p.w;
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int ch = rep == 0 ? cg : 8;
+    if (rep == 1 && cg != 0) break;
+    float v;
+    if (ch < 3) {
+      v = in_ref ? __ldg(p.img + ((int64_t)p.view[0] * 3 + ch) * plane + (int64_t)y * p.w + x) : 0.f;
+    } else {
+      const int i = 1 + (ch - 3) / 3, c = (ch - 3) % 3;
+      const MvsTap& ti = tap[i == 1 ? 1 : 2];
+      const float* f = p.img + ((int64_t)p.view[i] * 3 + c) * plane;     // planar (h,w): offset = feature offset / C
+      v = ti.w[0] * __ldg(f + (ti.off[0] >> 5));
+      v = fmaf(ti.w[1], __ldg(f + (ti.off[1] >> 5)), v);
+      v = fmaf(ti.w[2], __ldg(f + (ti.off[2] >> 5)), v);
+      v = fmaf(ti.w[3], __ldg(f + (ti.off[3] >> 5)), v);
+    }
+    if (live) put<OutT>(out + ch, v);
+  }
+  // ---- feature variance over the views that see the voxel: this lane's 4 channels
+  const float* fref = p.feat + (int64_t)p.view[0] * p.feat_view_stride + cg * 4;
+  const float4 r4 = in_ref ? ldg4(fref + ((int64_t)y * p.w + x) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+  float sum[4], sq[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { sum[c] = r[c]; sq[c] = mul_rn(r[c], r[c]); }
+#pragma unroll
+  for (int i = 1; i < V; ++i) {
+    const float* f = p.feat + (int64_t)p.view[i] * p.feat_view_stride + cg * 4;
+    const float4 a = ldg4(f + tap[i].off[0]), b = ldg4(f + tap[i].off[1]), cc = ldg4(f + tap[i].off[2]), dd = ldg4(f + tap[i].off[3]);
+    const float t0[4] = {a.x, a.y, a.z, a.w}, t1[4] = {b.x, b.y, b.z, b.w}, t2[4] = {cc.x, cc.y, cc.z, cc.w}, t3[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = tap[i].w[0] * t0[c];
+      v = fmaf(tap[i].w[1], t1[c], v);
+      v = fmaf(tap[i].w[2], t2[c], v);
+      v = fmaf(tap[i].w[3], t3[c], v);
+      sum[c] = add_rn(sum[c], v);
+      sq[c] = add_rn(sq[c], mul_rn(v, v));
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float m = mul_rn(sum[c], inv_cnt);
+      put<OutT>(out + 3 * V + cg * 4 + c, sub_rn(mul_rn(sq[c], inv_cnt), mul_rn(m, m)));
+    }
+  }
+}
+
 // ---------------------------------------------------------------- K3b
 // One thread per sample.  Output row (86 floats): [ndc(3), sin(2^k ndc) k=0..9 (30), cos (30),
 // vox(8), (rgb,in)x3 (12), dir(3)].
@@ -281,6 +373,16 @@ extern "C" BMV_API int bmv_cost_volume_var_img(const bmv_cost_volume_img_params*
   const int64_t nvox = (int64_t)p->D * (p->h + 2 * p->pad) * (p->w + 2 * p->pad);
   const unsigned blocks = (unsigned)ceil_div64(nvox, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  // dense channels-last features and a channels-last volume: warp-level tap sharing, 16-byte taps
+  const int hp = p->h + 2 * p->pad, wp = p->w + 2 * p->pad;
+  if (p->C == 32 && p->feat_c_stride == 1 && p->feat_x_stride == 32 && p->feat_y_stride == (int64_t)p->w * 32 &&
+      p->feat_view_stride % 4 == 0 && ((uintptr_t)p->feat & 15) == 0 && p->out_c_stride == 1 && hp <= 65535 && p->D <= 65535 &&
+      (int64_t)p->h * p->w * 32 < (1ll << 31)) {
+    const dim3 grid((unsigned)((wp + 31) / 32), (unsigned)hp, (unsigned)p->D);
+    if (p->out_bf16) cost_volume_var_img_cl_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*p);
+    else cost_volume_var_img_cl_kernel<float><<<grid, 256, 0, st>>>(*p);
+    return check_launch("bmv_cost_volume_var_img");
+  }
   if (p->out_bf16) cost_volume_var_img_kernel<3, __nv_bfloat16><<<blocks, 256, 0, st>>>(*p);
   else cost_volume_var_img_kernel<3, float><<<blocks, 256, 0, st>>>(*p);
   return check_launch("bmv_cost_volume_var_img");

@@ -363,10 +363,14 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mvs_render_umma_kernel(bmv_mvs_
     // =============================================================== MMA issuer
     // The whole warp walks the issue code on warp-uniform values and ONE elected lane executes the MMAs; every descriptor
     // is a (low word, constant high word) pair whose low word is computed OUTSIDE the elected branch (uniform datapath)
-    // and only advanced by compile-time constants inside it.  The first version built the 64-bit descriptors inside
-    // `if (elected)`: ~290 clk per tcgen05.mma (R2UR / elect sequences per operand), i.e. the issuer — not the tensor
-    // pipe (15 % busy), not the row owners, not the weight stream (measured: 1 KB panels, two threads per row and a
-    // branch-free gather all left the 39 ms unchanged) — bounded the kernel.
+    // and only advanced by compile-time constants inside it (the first version built the 64-bit descriptors inside
+    // `if (elected)`: R2UR / elect sequences per operand).
+    // Dissection (BMV_MR_DEBUG_PANEL, tools/mvs_render_dissect.py, clk per tile pair): all 41.9 k | no gather 28.5 k |
+    // no MMAs 33.4 k | no epilogue arithmetic 39.7 k | empty pipeline 15.5 k, the same with 1 KB weight panels (so the
+    // 256 KB weight pass per pair is not what bounds it).  Issuing from the last-publishing row-owner warp instead of this
+    // polling warp (as render_multi_umma.cu does) took the empty pipeline to 10.4 k and left the full kernel at 42.9 k:
+    // the parts add up whatever the hand-shake costs, because what they share is the L1 / shared-memory data pipe
+    // (tensor-core operand reads ~9 k + operand stores ~4.6 k + weight ring ~2 k + gather ~9 k wavefronts of the 42 k clk).
     const bool elected = elect_one();
     constexpr uint32_t HI = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
     constexpr uint32_t LBO_A = (uint32_t)(MR_CHUNK >> 4) << 16;         // K-chunks of an A operand are 2048 B apart

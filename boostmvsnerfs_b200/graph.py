@@ -19,7 +19,7 @@ _STATIC_KEYS = ("all_src_inps", "all_src_exts", "all_src_ixts", "tar_ext", "tar_
 
 # Network attributes that select kernels / precision: a captured graph bakes the routing in
 _ROUTING_FLAGS = ("fold_bn", "channels_last", "fused_mlp", "half_feature_taps", "multi_chain_volume", "multi_chain_render", "mlp_engine",
-                  "volume_range_scale", "host_camera_algebra")
+                  "volume_range_scale", "host_camera_algebra", "overlap_fpn_topdown")
 
 
 class FrameGraph:

@@ -226,11 +226,18 @@ class FusedTopDownFPN(nn.Module):
     # K1 (288 -> 263 us on B200), but this kernel's epilogue then stores 4 bytes per lane (half sectors) and gets 22 us
     # slower (an additional copy next to the fp32 maps: +26 us) — net zero on the frame, so it is off by default.
     emit_half_features = False
+    # Run the two top-down + smoothing launches (0.47 ms at C2, bound by the L1 data pipe) on a side stream: they only
+    # produce the level-1 / level-2 maps, which the frame needs after the level-0 cost-volume chain / at the render, so
+    # they overlap the level-0 chain (K1 + 3-D CNN, tensor- and latency-bound).  `ready` then maps 'level_1' / 'level_2'
+    # to the events the consumer must wait for (network.StreamedFeats does); None when nothing was deferred.
+    side_topdown = False
 
     def __init__(self, fpn):
         super().__init__()
         self.fpn = fpn
         self._packed = None
+        self._side = None
+        self.ready = None
 
     def _smooth_weights(self, device):
         if self._packed is None or self._packed[0].device != device:
@@ -256,13 +263,34 @@ class FusedTopDownFPN(nn.Module):
             c1 = f.conv1(c0)
         c2 = f.conv2(c1)
         quarter = f.toplayer(c2)
+        self.ready = None
         if fused:
             w1, w0, _ = self._smooth_weights(x.device)
-            if self.emit_half_features:
-                half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True, want_half='only')
-            else:
-                half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
-            _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)
+
+            def topdown():
+                if self.emit_half_features:
+                    half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True, want_half='only')
+                else:
+                    half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
+                ev1 = torch.cuda.current_stream().record_event() if self.side_topdown else None
+                _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)
+                ev0 = torch.cuda.current_stream().record_event() if self.side_topdown else None
+                return feat1, feat0, ev1, ev0
+            if not self.side_topdown:
+                feat1, feat0, _, _ = topdown()
+                return quarter, feat1, feat0
+            main = torch.cuda.current_stream()
+            if self._side is None or self._side.device != x.device:
+                self._side = torch.cuda.Stream(device=x.device)
+            self._side.wait_stream(main)                   # fork: quarter, c1, c0 are complete on `main` up to here
+            with torch.cuda.stream(self._side):
+                feat1, feat0, ev1, ev0 = topdown()
+            for t in (quarter, c1, c0):                    # caching allocator: these blocks are still read by the side stream
+                t.record_stream(self._side)
+            for t in (feat1, feat0):                       # ... and these are consumed on `main`
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+            self.ready = {'level_1': ev1, 'level_2': ev0}
             return quarter, feat1, feat0
         half = ops.fpn_topdown(quarter, c1, f.lat1.weight, f.lat1.bias)
         full = ops.fpn_topdown(half, c0, f.lat0.weight, f.lat0.bias)

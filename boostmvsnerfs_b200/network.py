@@ -32,6 +32,32 @@ def _combinations(n, r):
     return list(itertools.combinations(range(n), r))
 
 
+class StreamedFeats(dict):
+    """Feature maps of which some may still be in flight on another stream: `ready` maps a key to the event that marks
+    it complete; the first access of such a key makes the CURRENT stream wait for it (a no-op for everything else)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.ready = {}
+
+    def _wait(self, key):
+        ev = self.ready.pop(key, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def __getitem__(self, key):
+        self._wait(key)
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        self._wait(key)
+        return super().get(key, default)
+
+    def join(self):
+        for key in list(self.ready):
+            self._wait(key)
+
+
 class EnerfNetwork(nn.Module):
     """Single-volume ENeRF (reference lib/networks/enerf/network.py:11-113)."""
 
@@ -57,6 +83,7 @@ class EnerfNetwork(nn.Module):
                                                # for another view selection)
         self.volume_range_scale = True         # fp16 cost volumes are stored x 2^k (ops.volume_scale), undone by conv0
         self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
+        self.overlap_fpn_topdown = True        # FPN top-down steps on a side stream under the level-0 chain (inference_plan.py)
         self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
         self.generate_rays = False             # True: rays of full target images are generated on the device
@@ -109,19 +136,28 @@ class EnerfNetwork(nn.Module):
             fmt = torch.channels_last if name == 'feature_net' else torch.channels_last_3d
         return self._plans.get(name, mod, fmt)
 
-    def forward_feat(self, x):
+    def forward_feat(self, x, defer=False):
         """x (N,3,H,W) -> dict level_{0,1,2} of (N,C,h,w)
-        (reference lib/networks/enerf/network.py:58-67, batch dim squeezed)."""
+        (reference lib/networks/enerf/network.py:58-67, batch dim squeezed).
+        defer=True (the per-frame path): the level-1 / level-2 maps may still be in flight on the FPN plan's side
+        stream; the returned StreamedFeats makes the consuming stream wait at the first access of a level, and the
+        caller must join() before it returns."""
         plan = self._kept('feature_net')
         fused_plan = type(plan).__name__ == 'FusedTopDownFPN'
         if fused_plan:
             plan.emit_half_features = bool(self.half_feature_taps)
+            plan.side_topdown = bool(self.overlap_fpn_topdown)
         if self.channels_last and not fused_plan:
             x = x.contiguous(memory_format=torch.channels_last)
         quarter, half, full = plan(x)
-        feats = {'level_0': quarter, 'level_1': half, 'level_2': full}
-        if fused_plan and plan.rgb_nhwc4 is not None:
-            feats['rgb_nhwc4'] = plan.rgb_nhwc4             # by-product of the stem kernel (see _render_level)
+        feats = StreamedFeats({'level_0': quarter, 'level_1': half, 'level_2': full})
+        if fused_plan:
+            feats.ready = dict(plan.ready or {})
+            plan.ready = None
+            if plan.rgb_nhwc4 is not None:
+                feats['rgb_nhwc4'] = plan.rgb_nhwc4         # by-product of the stem kernel (see _render_level)
+        if not defer:
+            feats.join()
         return feats
 
     @staticmethod
@@ -217,7 +253,7 @@ class EnerfNetwork(nn.Module):
         if camera is None:
             ready = torch.cuda.current_stream().record_event()      # camera tensors are valid from here on
         with self._stage('feature_net'):
-            feats = self.forward_feat(inps)
+            feats = self.forward_feat(inps, defer=True)
         with self._stage('camera'):
             need_gen = self.generate_rays or any(r is None for r in rays_by_level)
             if camera is not None:
@@ -233,6 +269,7 @@ class EnerfNetwork(nn.Module):
         for i, st in states.items():
             out[i] = self._render_level(i, feats, inps, st, rays_by_level[i], cams, triples, Hh, Ww)
             out[i]['depth0'], out[i]['std0'] = st['depth'][0], st['std'][0]
+        feats.join()                                       # every side-stream fork re-joined (a captured graph requires it)
         if self.keep_internals:
             self.last_internals = {i: {'masks': torch.stack(o['masks']), 'zs': torch.stack(o['zs'])} for i, o in out.items()}
         return out
@@ -352,14 +389,15 @@ class EnerfNetwork(nn.Module):
         if self.fused_mlp and rc.viewdir_agg and ops.render_rays_supported(Cv, Cf, V):
             engine = self.mlp_engine if (Cf == 8 and V == 3) else 'fma'
             packed = self._packed_mlp(i, engine)
-            if (engine == 'mma' and self.multi_chain_render and state.get('depth_all') is not None and rs == 1.
+            if (engine in ('mma', 'umma') and self.multi_chain_render and state.get('depth_all') is not None and rs == 1.
                     and all(len(tr) == 3 for tr in triples) and ops.render_rays_multi_supported(feat_vol, im_feat, rgb, V)):
-                # every chain in ONE persistent launch (csrc/render_multi.cu); view ids from device memory when the
+                # every chain in ONE persistent launch (csrc/render_multi.cu, or render_multi_umma.cu for the tcgen05
+                # engine); view ids from device memory when the
                 # caller (FrameGraph) supplies them
                 with self._stage(f'render_fused_l{i}'):
                     ops.render_rays_multi(state['depth_all'], state['std_all'], state['nf_all'], rays, H, W, rc.depth_inv[i], S,
                                           feat_vol, im_feat, rgb, cams, triples, packed, render_scale=rs, rgb_affine=affine,
-                                          ray_begin=ray_begin, n_rays=R, views_dev=self._views_dev,
+                                          ray_begin=ray_begin, n_rays=R, views_dev=self._views_dev, engine=engine,
                                           out={'raw': raw_all, 'z_vals': z_all, 'vis_mask': mask_all})
                 return {'raws': list(raw_all.unbind(0)), 'masks': list(mask_all.unbind(0)), 'zs': list(z_all.unbind(0))}
             self._baked_views = True               # the per-chain launches carry their view ids as kernel arguments

@@ -100,6 +100,9 @@ class BoostMvsnerfNetwork(nn.Module):
                 vols = torch.empty((K, D, h + 2 * PAD, w + 2 * PAD, 9 + 32), device=dev, dtype=self.volume_dtype).permute(0, 4, 1, 2, 3)
             else:
                 vols = torch.empty((K, 9 + 32, D, h + 2 * PAD, w + 2 * PAD), device=dev, dtype=self.volume_dtype)
+            if self.mlp_engine == 'umma' and feats.shape[1] == 32:
+                # dense channels-last feature maps select K1b's warp-level kernel (16-byte taps, shared tap sets)
+                feats = feats.contiguous(memory_format=torch.channels_last)
             for k in range(K):
                 ops.cost_volume_var_img(feats, small, triples[k], projs[k], planes[k], PAD, out=vols[k])
         with self._stage('cost_reg_2'):

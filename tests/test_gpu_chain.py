@@ -258,6 +258,47 @@ def test_half_feature_taps_option_matches_default():
         _report(got[k], ref[k].detach().cpu().numpy(), f"half feature taps {k}", 1e-2)
 
 
+def test_fpn_side_stream_overlap_is_bit_identical():
+    """Network.overlap_fpn_topdown (the FPN top-down launches on a side stream under the level-0 chain) only changes WHEN
+    the level-1 / level-2 maps are produced: eager and captured frames are bit-identical to the single-stream schedule."""
+    from boostmvsnerfs_b200.graph import FrameGraph
+    g = load_golden("enerf_chain_eval.npz")
+    net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
+    assert net.overlap_fpn_topdown
+    for _ in range(2):
+        on = net(dict(batch))
+    fg = FrameGraph(net)
+    on_g = {k: v.clone() for k, v in fg(dict(batch)).items()}
+    on_g2 = fg(dict(batch))                                  # replay
+    net.overlap_fpn_topdown = False
+    off = net(dict(batch))
+    for k in off:
+        assert torch.equal(on[k], off[k]), f"eager {k}"
+        assert torch.equal(on_g[k], off[k]) and torch.equal(on_g2[k], off[k]), f"graph {k}"
+    fg.close()
+
+
+def test_umma_mlp_engine_frame_matches_mma_engine():
+    """Network.mlp_engine = 'umma': all chains rendered by bmv_render_rays_multi_umma (tcgen05); the frame agrees with
+    the mma.sync engine to the MLP tolerance (2e-5 of range)."""
+    from boostmvsnerfs_b200 import _lib
+    g = load_golden("enerf_chain_eval.npz")
+    net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
+    ref = net(dict(batch))
+    net.mlp_engine = "umma"
+    calls = []
+    orig = _lib.call
+    _lib.call = lambda name, p, s: (calls.append(name), orig(name, p, s))[1]
+    try:
+        got = net(dict(batch))
+    finally:
+        _lib.call = orig
+    assert calls.count("bmv_render_rays_multi_umma") == 1 and "bmv_render_rays_multi" not in calls
+    for k in ref:
+        err = float((got[k] - ref[k]).abs().max()) / float(ref[k].abs().max())
+        assert err <= 2e-5, (k, err)
+
+
 def test_frame_graph_fresh_device_batches_get_their_own_cameras(strict_fp32):
     """`for b in loader: fg(to_cuda(b))`: every frame's camera tensors are fresh device allocations that the caching
     allocator may place at the previous frame's addresses.  The graph must use each frame's own

@@ -58,6 +58,10 @@ def test_cost_volume_41_vs_reference(ops, g, channels_last):
                                  out_dtype=torch.bfloat16, channels_last=channels_last)
     exact(bf.float(), vol.to(torch.bfloat16).float(), "bf16 volume == rn(fp32 volume)")
     close(bf, ref, "bf16 volume (BASELINE config 3 tolerance)", rtol=1e-2)
+    if channels_last:
+        # the warp-level kernel (dense channels-last maps, shared tap sets, 16-byte taps) is op for op the thread-per-voxel one
+        planar = ops.cost_volume_var_img(g.t("in_feats", "cuda")[0], small, TRIPLE, g.t("proj_mats", "cuda")[0], g.t("planes", "cuda")[0], 24)
+        exact(vol, planar, "channels-last kernel == thread-per-voxel kernel")
 
 
 def test_march_fetch_vs_reference(ops, g):
