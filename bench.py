@@ -601,6 +601,9 @@ def main_ours(args):
              "bmv_render_rays": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_render_rays_mma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_render_rays_umma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
+             # all K chains of a level in ONE launch (csrc/render_multi.cu / render_multi_umma.cu)
+             "bmv_render_rays_multi": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
+             "bmv_render_rays_multi_umma": [f"render_fused_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_raygen_sample_fetch": [f"raygen_fetch_l{i}" for i in range(rc.num) if rc.render_if[i]],
              "bmv_composite_blend": [f"composite_blend_l{i}" for i in range(rc.num) if rc.render_if[i]]}
     if ksum.get("bmv_cost_volume_var_multi"):
@@ -652,10 +655,10 @@ def main_ours(args):
         if name.startswith("render_fused"):
             # the fused gather+MLP kernel is compute bound, not HBM bound: 14.6 kFMA per sample (csrc/nerf_mlp.cuh).
             # Reported as fp32-equivalent FLOP/s against the fp32 FMA peak (148 SMs x 128 FMA/clk x clocks.max.sm);
-            # the tensor-core engine spends 3 fp16 MMAs per fp32 product (csrc/render_mma.cu).
+            # the tensor-core engines spend 3 fp16 MMAs per fp32 product (csrc/render_multi_umma.cu, render_multi.cu).
             lvl = int(name[-1])
             samples = int(wl["H"] * rc.render_scale[lvl]) * int(wl["W"] * rc.render_scale[lvl]) * rc.num_samples[lvl]
-            flops = samples * 2 * 14600.0
+            flops = samples * 2 * 14600.0 * (wl["K"] / k["launches_per_step"])      # a launch renders K / launches chains
             peak_tf = 148 * 128 * 2 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
             k.update({"bound": "fp32_fma", "tflops": flops / (k["ms_per_launch"] * 1e-3) / 1e12,
                       "peak_tflops_fp32": peak_tf})

@@ -1,6 +1,8 @@
 // K1: fused plane-sweep cost volume (homography warp of S source maps + variance) and the
 // depth-hypothesis generators that feed it.  Reference semantics: lib/networks/enerf/utils.py
 // :57-95 (homo_warp), :98-153 (get_depth_values), :324-351 (build_feature_volume).
+#include <stdlib.h>
+
 #include "bmv_internal.cuh"
 
 namespace bmv {
@@ -315,8 +317,11 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl3_kernel(bmv_cost_volum
 // A warp owns VW = 32/CG consecutive x; per round it handles PB planes so that VW*S*PB <= 32 tap
 // tasks fill the warp: lane L computes task (plane slot, view, voxel) = (L / (VW*S), (L % (VW*S)) / VW,
 // L % VW); the consumer lane of voxel v fetches its 4 offsets + 4 weights per view with 8 shuffles.
+// dbg (environment BMV_K1_DEBUG, measurement only — WRONG results): what a staged source tile could buy at most.  Bit 0:
+// every tap reads texel 0 of its view (the loads stay, they all hit L1 and coalesce: no scatter, no misses); bit 1: no
+// tap loads at all (the instruction floor of everything else).
 template <int S, int CG, int PB, typename OutT, typename FeatT = float>
-__global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volume_params p, int DG) {
+__global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volume_params p, int DG, int dbg) {
   constexpr int VW = 32 / CG;                            // voxels per warp
   constexpr int TASKS = VW * S * PB;
   static_assert(TASKS <= 32, "tap tasks must fit one warp");
@@ -367,7 +372,13 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
         const int o2 = __shfl_sync(0xffffffffu, t.off[2], src), o3 = __shfl_sync(0xffffffffu, t.off[3], src);
         const float w0 = __shfl_sync(0xffffffffu, t.w[0], src), w1 = __shfl_sync(0xffffffffu, t.w[1], src);
         const float w2 = __shfl_sync(0xffffffffu, t.w[2], src), w3 = __shfl_sync(0xffffffffu, t.w[3], src);
-        const float4 a = ld_feat4(base[s] + o0), b = ld_feat4(base[s] + o1), c = ld_feat4(base[s] + o2), e = ld_feat4(base[s] + o3);
+        float4 a, b, c, e;
+        if (dbg & 2) {
+          a = make_float4(w0, w1, w2, w3); b = a; c = a; e = a;
+        } else {
+          const int m = (dbg & 1) ? 0 : -1;
+          a = ld_feat4(base[s] + (o0 & m)); b = ld_feat4(base[s] + (o1 & m)); c = ld_feat4(base[s] + (o2 & m)); e = ld_feat4(base[s] + (o3 & m));
+        }
         const float v0 = fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x)));
         const float v1 = fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y)));
         const float v2 = fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z)));
@@ -673,15 +684,16 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
     int DG = p.D;
     while (DG > 2 && (int64_t)p.w * p.h * CG3 * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
     dim3 grid(xchunks, p.h, (p.D + DG - 1) / DG);
+    static const int dbg = getenv("BMV_K1_DEBUG") ? atoi(getenv("BMV_K1_DEBUG")) : 0;
     if constexpr (S <= 4) {
       if (CG3 == 8) {              // C = 32: warp = 4 voxels x 8 lanes, 2 planes per round
-        if (p.feat_half) cost_volume_var_cl5_kernel<S, 8, 2, OutT, __half><<<grid, threads, 0, st>>>(p, DG);
-        else cost_volume_var_cl5_kernel<S, 8, 2, OutT><<<grid, threads, 0, st>>>(p, DG);
+        if (p.feat_half) cost_volume_var_cl5_kernel<S, 8, 2, OutT, __half><<<grid, threads, 0, st>>>(p, DG, dbg);
+        else cost_volume_var_cl5_kernel<S, 8, 2, OutT><<<grid, threads, 0, st>>>(p, DG, dbg);
         return check_launch("bmv_cost_volume_var");
       }
       if (CG3 == 4) {              // C = 16: warp = 8 voxels x 4 lanes, 1 plane per round
-        if (p.feat_half) cost_volume_var_cl5_kernel<S, 4, 1, OutT, __half><<<grid, threads, 0, st>>>(p, DG);
-        else cost_volume_var_cl5_kernel<S, 4, 1, OutT><<<grid, threads, 0, st>>>(p, DG);
+        if (p.feat_half) cost_volume_var_cl5_kernel<S, 4, 1, OutT, __half><<<grid, threads, 0, st>>>(p, DG, dbg);
+        else cost_volume_var_cl5_kernel<S, 4, 1, OutT><<<grid, threads, 0, st>>>(p, DG, dbg);
         return check_launch("bmv_cost_volume_var");
       }
     }

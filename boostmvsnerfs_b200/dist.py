@@ -169,7 +169,7 @@ class ShardedFrameRenderer:
         out = {'raw': torch.empty((K, n_rays, S, 4), device=dev), 'z_vals': torch.empty((K, n_rays, S), device=dev),
                'vis_mask': torch.empty((K, n_rays, S), device=dev)}
         ops.render_rays_multi(maps[:, 0], maps[:, 1], maps[:, 2:4], rays, H, W, rc.depth_inv[level], S, vols, im_feat, rgb, cams,
-                              triples, net._packed_mlp(level, 'mma'), ray_begin=ray_begin, n_rays=n_rays, out=out,
+                              triples, net._packed_mlp(level, 'umma' if net.mlp_engine == 'umma' else 'mma'), ray_begin=ray_begin, n_rays=n_rays, out=out,
                               views_dev=views_dev, grid_rows=hv, vol_row0=y0, map_row0=y0)
         rgbo, depth, weights = ops.composite_blend(list(out['raw'].unbind(0)), list(out['vis_mask'].unbind(0)),
                                                    list(out['z_vals'].unbind(0)))

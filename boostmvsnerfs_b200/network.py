@@ -84,7 +84,10 @@ class EnerfNetwork(nn.Module):
         self.volume_range_scale = True         # fp16 cost volumes are stored x 2^k (ops.volume_scale), undone by conv0
         self.multi_chain_volume = True         # level 0: all K cost volumes in one launch, unique views warped once
         self.overlap_fpn_topdown = True        # FPN top-down steps on a side stream under the level-0 chain (inference_plan.py)
-        self.mlp_engine = 'mma'                # 'mma': tensor-core MLP (render_mma.cu); 'fma': fp32 FMA (render_fused.cu)
+        # per-sample MLP engine of the fused render: 'umma' — tcgen05.mma with accumulators in tensor memory, all chains in
+        # one launch (render_multi_umma.cu; single chains: render_umma.cu); 'mma' — warp-level mma.sync (render_multi.cu,
+        # render_mma.cu); 'fma' — fp32 FMA (render_fused.cu).  Same fp16 hi + lo split in both tensor-core engines.
+        self.mlp_engine = 'umma'
         self.host_camera_algebra = True        # 4x4 inverses etc. on the host (one D2H of ~1 KB)
         self.generate_rays = False             # True: rays of full target images are generated on the device
                                                # from tar_ext/tar_ixt; batch['rays_i'] may be absent

@@ -81,14 +81,17 @@ def test_single_volume_forward_vs_reference(strict_fp32):
 def test_fused_and_unfused_network_paths_agree(strict_fp32):
     g = load_golden("enerf_chain_eval.npz")
     net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
-    assert net.fused_mlp and net.mlp_engine == "mma"
+    assert net.fused_mlp and net.mlp_engine == "umma"
     fused = net(dict(batch))
+    net.mlp_engine = "mma"
+    mma = net(dict(batch))
     net.mlp_engine = "fma"
     fma = net(dict(batch))
     net.fused_mlp = False
     unfused = net(dict(batch))
     for k in fused:
-        _report(fused[k], unfused[k].cpu().numpy(), f"tensor-core fused vs unfused {k}", 2e-5)
+        _report(fused[k], unfused[k].cpu().numpy(), f"tcgen05 fused vs unfused {k}", 2e-5)
+        _report(mma[k], unfused[k].cpu().numpy(), f"mma.sync fused vs unfused {k}", 2e-5)
         _report(fma[k], unfused[k].cpu().numpy(), f"fp32-FMA fused vs unfused {k}", 2e-5)
 
 
@@ -279,11 +282,12 @@ def test_fpn_side_stream_overlap_is_bit_identical():
 
 
 def test_umma_mlp_engine_frame_matches_mma_engine():
-    """Network.mlp_engine = 'umma': all chains rendered by bmv_render_rays_multi_umma (tcgen05); the frame agrees with
-    the mma.sync engine to the MLP tolerance (2e-5 of range)."""
+    """Network.mlp_engine = 'umma' (the default): all chains rendered by bmv_render_rays_multi_umma (tcgen05); the frame
+    agrees with the mma.sync engine to the MLP tolerance (2e-5 of range)."""
     from boostmvsnerfs_b200 import _lib
     g = load_golden("enerf_chain_eval.npz")
     net, batch = _net_and_batch(g, RenderConfig.enerf_eval(2), "boost")
+    net.mlp_engine = "mma"
     ref = net(dict(batch))
     net.mlp_engine = "umma"
     calls = []

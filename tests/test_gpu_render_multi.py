@@ -121,11 +121,18 @@ def test_network_uses_the_multi_launch_and_matches_per_chain(monkeypatch):
     orig = _lib.call
     monkeypatch.setattr(_lib, "call", lambda name, p, s: (calls.append(name), orig(name, p, s))[1])
     a = net(dict(batch))
+    assert calls.count("bmv_render_rays_multi_umma") == 1 and "bmv_render_rays_umma" not in calls
+    net.mlp_engine = "mma"
+    calls.clear()
+    a2 = net(dict(batch))
     assert calls.count("bmv_render_rays_multi") == 1 and "bmv_render_rays_mma" not in calls
     net.multi_chain_render = False
     calls.clear()
     b = net(dict(batch))
     assert calls.count("bmv_render_rays_mma") == 4
+    for k in a:
+        err = float((a2[k] - b[k]).abs().max()) / float(b[k].abs().max())
+        assert err <= 2e-5, (k, err)
     for k in a:
         err = float((a[k] - b[k]).abs().max()) / float(b[k].abs().max())
         assert err <= 2e-5, (k, err)
