@@ -6,8 +6,8 @@
 // = 0.42 ms gather + 1.06 ms mma.sync MLP, the two do NOT overlap: both are issue-slot work of the same 16 warps; and
 // the first tcgen05 version, render_umma.cu: 510 us per chain with ~100 MMAs per 128-sample tile each costing ~290 clk
 // of descriptor construction inside the elected branch, i.e. the single issuing thread bounded it):
-//   * the MMAs of a phase are issued by the LAST warp of the tile to publish its operand rows (a shared-memory arrival
-//     counter tells it): warp-uniform code, one elected lane; every descriptor is a (low word, constant high word) pair
+//   * the MMAs of a phase are issued by the LAST warp of the tile to publish its operand rows (all arrive on an mbarrier,
+//     a shared-memory counter elects the last): warp-uniform code, one elected lane; every descriptor is a (low word, constant high word) pair
 //     with the low words advanced by compile-time constants (2 uniform-datapath instructions per MMA).  No issuer warp:
 //     a 17th warp costs a whole 4-warp register allocation (96 instead of 128 registers per thread for the gather), its
 //     polling loop costs issue slots, and the extra hop costs latency on a chain that is latency-bound (measured: the
@@ -114,22 +114,23 @@ __device__ __forceinline__ void ru_issue_phase(uint32_t acc, uint32_t a, uint32_
 }
 
 // All 8 warps of a tile: publish the operand rows just written (and retire the TMEM loads of the columns about to be
-// overwritten); the warp that arrives LAST issues the phase's MMAs and commits them to the tile's accumulator barrier.
+// overwritten) by arriving on the tile's `ready` barrier; the warp that arrives LAST (a shared-memory counter elects it)
+// waits for that barrier — complete by then: the wait is the acquire side of the 256 arrivals — issues the phase's MMAs
+// and commits them to the tile's accumulator barrier.
 template <int PHASE>
-__device__ __forceinline__ void ru_publish_and_issue(uint32_t* cnt, uint32_t mb_acc, uint32_t acc, uint32_t a, uint32_t wB,
-                                                     bool no_mma, int lane) {
+__device__ __forceinline__ void ru_publish_and_issue(uint32_t* cnt, uint32_t mb_ready, uint32_t& par_ready, uint32_t mb_acc, uint32_t acc,
+                                                     uint32_t a, uint32_t wB, bool no_mma, int lane) {
   proxy_fence_async();                 // generic-proxy st.shared -> visible to the tensor core (async proxy)
   tc_fence_before();
+  mbar_arrive(mb_ready);
   __syncwarp();
   uint32_t last = 0;
-  if (lane == 0) {
-    __threadfence_block();             // release: this warp's rows before the count
-    last = atomicAdd(cnt, 1u) == (uint32_t)(RU_ROW_WARPS / 2 - 1);
-  }
+  if (lane == 0) last = atomicAdd(cnt, 1u) == (uint32_t)(RU_ROW_WARPS / 2 - 1);
   last = __shfl_sync(0xffffffffu, last, 0);
   if (last) {                          // warp-uniform
     if (lane == 0) *cnt = 0u;          // nobody arrives again before these MMAs have completed
-    __threadfence_block();             // acquire: the other warps' rows
+    mbar_wait(mb_ready, par_ready);
+    __syncwarp();
     tc_fence_after();
     if (elect_one()) {
       if (!no_mma) ru_issue_phase<PHASE>(acc, a, wB);
@@ -137,6 +138,7 @@ __device__ __forceinline__ void ru_publish_and_issue(uint32_t* cnt, uint32_t mb_
     }
     __syncwarp();
   }
+  par_ready ^= 1u;
 }
 
 // dbg (environment BMV_RU_DEBUG, measurement only — bits 0..2 give WRONG results): bit 0 skips the gather arithmetic,
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
   __shared__ float s_tar_c[4];
   __shared__ int s_view[BMV_MAX_VOLUMES * V];
   __shared__ __align__(16) float4 s_xe[2][128];                          // phase-E exchange: half 0's partial sums
-  __shared__ __align__(8) uint64_t s_acc[2], s_skew;
+  __shared__ __align__(8) uint64_t s_acc[2], s_ready[2], s_skew;
   __shared__ uint32_t s_cnt[2];                                          // warps of a tile that have published the current phase
   __shared__ uint32_t s_tmem;
 
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
   if (tid < mp.n_views) cams[tid] = lean_cam_load(p, tid);
   if (tid < 3) s_tar_c[tid] = p.tar_center[tid];
   if (tid == 0) {
-    for (int w = 0; w < 2; ++w) { mbar_init(smem_u32(&s_acc[w]), 1); s_cnt[w] = 0u; }
+    for (int w = 0; w < 2; ++w) { mbar_init(smem_u32(&s_acc[w]), 1); mbar_init(smem_u32(&s_ready[w]), 256); s_cnt[w] = 0u; }
     mbar_init(smem_u32(&s_skew), 256);
   }
   if (tid < 256) {                                         // the constant K-chunk (1, 0, ..., 0) of both tiles
@@ -194,8 +196,9 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
     const int tile_id = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3, row = wq * 32 + lane;
     unsigned char* tile = sA + tile_id * RU_TILE_BYTES;
     const uint32_t tcol = tmem_base + (uint32_t)(tile_id * 256) + ((uint32_t)(wq * 32) << 16);
-    const uint32_t mb_acc = smem_u32(&s_acc[tile_id]);
+    const uint32_t mb_acc = smem_u32(&s_acc[tile_id]), mb_ready = smem_u32(&s_ready[tile_id]);
     uint32_t* cnt = &s_cnt[tile_id];
+    uint32_t par_ready = 0;
     const uint32_t acc_t = tmem_base + (uint32_t)(tile_id * 256);
     const uint32_t a_lo = ((smem_u32(tile) & 0x3FFFFu) >> 4) | ((uint32_t)(RU_CHUNK >> 4) << 16), wB = smem_u32(sW);
     const bool no_mma = dbg & 2;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
 #pragma unroll
         for (int v = 0; v < V; ++v) rgbv[v][0] = rgbv[v][1] = rgbv[v][2] = 0.f;
       }
-      ru_publish_and_issue<0>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      ru_publish_and_issue<0>(cnt, mb_ready, par_ready, mb_acc, acc_t, a_lo, wB, no_mma, lane);
       if (first && tile_id == 0) mbar_arrive(smem_u32(&s_skew));
       first = false;
       // ------------------------------------------------------------ phase B: ReLU, view soft-max, im = input of agg.fc
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
         ru_put(tile, RU_IM + 2 * half, row, im);
         ru_put(tile, RU_IM + 2 * half + 1, row, im + 8);
       }
-      ru_publish_and_issue<1>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      ru_publish_and_issue<1>(cnt, mb_ready, par_ready, mb_acc, acc_t, a_lo, wB, no_mma, lane);
       // ------------------------------------------------------------ phase C: pooled = relu(fc + b)
       mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
       __syncwarp();
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
         ru_put(tile, RU_POOLED + half, row, fmaxf(pc[0] + b0.x, 0.f), fmaxf(pc[1] + b0.y, 0.f), fmaxf(pc[2] + b0.z, 0.f), fmaxf(pc[3] + b0.w, 0.f),
                fmaxf(pc[4] + b1.x, 0.f), fmaxf(pc[5] + b1.y, 0.f), fmaxf(pc[6] + b1.z, 0.f), fmaxf(pc[7] + b1.w, 0.f));
       }
-      ru_publish_and_issue<2>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      ru_publish_and_issue<2>(cnt, mb_ready, par_ready, mb_acc, acc_t, a_lo, wB, no_mma, lane);
       // ------------------------------------------------------------ phase D: hid = relu(lr0), partial sigma
       mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
       __syncwarp();
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) render_multi_umma_kernel(bmv_re
         }
         sig_part = (a0 + a1) + (a2 + a3);
       }
-      ru_publish_and_issue<3>(cnt, mb_acc, acc_t, a_lo, wB, no_mma, lane);
+      ru_publish_and_issue<3>(cnt, mb_ready, par_ready, mb_acc, acc_t, a_lo, wB, no_mma, lane);
       // ------------------------------------------------------------ phase E: color.2 logits, view soft-max, rgb, sigma
       mbar_wait(mb_acc, par_acc); par_acc ^= 1u;
       __syncwarp();

@@ -60,12 +60,24 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// A broken pipeline must fault, not hang the GPU: a wait that lasts longer than 20 s of wall clock traps.  (Wall clock,
+// not a spin count: under compute-sanitizer a kernel runs hundreds of times slower while try_wait returns at once.)
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    if (spins > (1u << 26)) __trap();                                   // a broken pipeline must fault, not hang the GPU
+    if ((spins & 0xFFFu) == 0xFFFu) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {

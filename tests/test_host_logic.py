@@ -55,6 +55,24 @@ def test_invalid_arguments_return_status_not_crash():
     assert lib.bmv_nerf_mlp_weight_count(7) == -1
     with pytest.raises(_lib.BmvError):
         _lib.call("bmv_composite_blend", p, 0)
+    # the two multi-chain render entries share one argument check (render_multi_check.cuh): same status, own name in the text
+    for entry in ("bmv_render_rays_multi", "bmv_render_rays_multi_umma"):
+        m = _lib.RenderMultiParams()
+        m.K, m.n_views = 0, 3
+        assert getattr(lib, entry)(ctypes.byref(m), None) == -1
+        assert entry.encode() + b": K must be" in lib.bmv_last_error_string()
+        assert getattr(lib, entry)(None, None) == -1
+        m.K = 2                                            # n_rays = 0: nothing to do, whatever the pointers are
+        assert getattr(lib, entry)(ctypes.byref(m), None) == 0
+
+
+def test_streamed_feats_is_a_dict_when_nothing_is_in_flight():
+    from boostmvsnerfs_b200.network import StreamedFeats
+    f = StreamedFeats({"level_0": 1, "level_1": 2})
+    f["rgb_nhwc4"] = 3
+    assert f["level_1"] == 2 and f.get("rgb_nhwc4") == 3 and f.get("missing") is None and sorted(f) == ["level_0", "level_1", "rgb_nhwc4"]
+    f.join()                                               # no events recorded: nothing to wait for
+    assert f.ready == {}
 
 
 def test_ops_refuse_cpu_tensors():
