@@ -80,7 +80,7 @@ def main():
         from boostmvsnerfs_b200 import build as _b
         cur["csrc_digest"] = _b._digest()[:16]
         cur["capture"] = sorted(set(cur["sources"].values()))
-        cur["when"] = datetime.datetime.utcnow().strftime("%Y-%m-%dT%H:%MZ")
+        cur["when"] = datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ")
         json.dump(cur, open(path, "w"), indent=1)
 
 
