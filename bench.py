@@ -207,6 +207,10 @@ def load_ncu_traffic():
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(path))
+        from boostmvsnerfs_b200 import build as _build
+        if d.get("csrc_digest") != _build._digest()[:16]:          # a capture of ANOTHER build says nothing about this one
+            NCU_TRAFFIC_MB, NCU_TRAFFIC_SOURCE = {}, {"stale": True, "captured_for": d.get("csrc_digest")}
+            return
         NCU_TRAFFIC_MB = {k: float(v) for k, v in d.get("traffic_mb", {}).items()}
         NCU_TRAFFIC_SOURCE = {k: d.get(k) for k in ("capture", "csrc_digest", "when")}
     except (OSError, ValueError):
