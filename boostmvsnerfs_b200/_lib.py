@@ -26,7 +26,7 @@ class CostVolumeParams(C.Structure):
                 ("D", i32), ("h", i32), ("w", i32),
                 ("out", C.c_void_p),
                 ("out_c_stride", i64), ("out_d_stride", i64), ("out_y_stride", i64), ("out_x_stride", i64),
-                ("out_bf16", i32), ("exact_coords", i32), ("feat_half", i32), ("reserved0", i32),
+                ("out_bf16", i32), ("exact_coords", i32), ("feat_half", i32), ("variant", i32),
                 ("out_scale", C.c_void_p), ("view_dev", C.c_void_p)]
 
 

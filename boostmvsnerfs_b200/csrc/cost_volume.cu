@@ -412,6 +412,128 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl5_kernel(bmv_cost_volum
   }
 }
 
+// 8 consecutive channels of a source texel: ONE 256-bit load for fp32 maps (LDG.E.ENL2.256, 32-byte aligned), one
+// 128-bit load for fp16 maps
+template <typename FeatT>
+__device__ __forceinline__ void ld_feat8(const FeatT* q, float4& lo, float4& hi) {
+  if constexpr (sizeof(FeatT) == 4) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(q));
+  } else {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(q));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&r.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
+    lo = make_float4(a.x, a.y, b.x, b.y);
+    hi = make_float4(c.x, c.y, d.x, d.y);
+  }
+}
+
+// bilinear blend of 4 channels (the FMA order of every K1 generation: w0*a, +w1*b, +w2*c, +w3*e)
+__device__ __forceinline__ float4 blend4(float w0, float w1, float w2, float w3, const float4& a, const float4& b, const float4& c,
+                                         const float4& e) {
+  return make_float4(fmaf(w3, e.x, fmaf(w2, c.x, fmaf(w1, b.x, w0 * a.x))), fmaf(w3, e.y, fmaf(w2, c.y, fmaf(w1, b.y, w0 * a.y))),
+                     fmaf(w3, e.z, fmaf(w2, c.z, fmaf(w1, b.z, w0 * a.z))), fmaf(w3, e.w, fmaf(w2, c.w, fmaf(w1, b.w, w0 * a.w))));
+}
+__device__ __forceinline__ void acc_first(float4& sum, float4& sq, const float4& v) {
+  sum = v;
+  sq = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+}
+__device__ __forceinline__ void acc_next(float4& sum, float4& sq, const float4& v) {
+  sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+  sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+}
+__device__ __forceinline__ float4 variance4(const float4& sum, const float4& sq, float invS, float osc) {
+  float4 var;
+  { const float m = sum.x * invS; var.x = fmaf(-m, m, sq.x * invS) * osc; }
+  { const float m = sum.y * invS; var.y = fmaf(-m, m, sq.y * invS) * osc; }
+  { const float m = sum.z * invS; var.z = fmaf(-m, m, sq.z * invS) * osc; }
+  { const float m = sum.w * invS; var.w = fmaf(-m, m, sq.w * invS) * osc; }
+  return var;
+}
+// 8 output channels of a voxel: one 32-byte (fp32) / 16-byte (16-bit) store
+template <typename OutT>
+__device__ __forceinline__ void store_var8(OutT* out, const float4& lo, const float4& hi) {
+  if constexpr (sizeof(OutT) == 4) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w),
+                 "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+  } else {
+    uint4 pk;
+    pk.x = pack_out2<OutT>(lo.x, lo.y); pk.y = pack_out2<OutT>(lo.z, lo.w);
+    pk.z = pack_out2<OutT>(hi.x, hi.y); pk.w = pack_out2<OutT>(hi.z, hi.w);
+    *reinterpret_cast<uint4*>(out) = pk;
+  }
+}
+
+// v6: v5 with EIGHT channels per lane.  ncu on v5 (profiles/round2t_k1_staging_whatif.md): the kernel is bound by its
+// ~1.2 k thread instructions per voxel, most of them per-LANE overhead (the warp-wide tap computation, 8 shuffles and 4
+// address computations per view) that 4 channels of payload amortise badly.  With 8 channels per lane a warp covers
+// VW = 32 / (C / 8) voxels (16 at C = 16, 8 at C = 32), every tap is one 256-bit load and the result one 16- / 32-byte
+// store: the same loads, blends and stores per voxel, half the overhead.  VW * S tap tasks no longer fit 32 lanes: the
+// lanes compute them in NP passes (task T = pass * 32 + lane = (view T / VW, voxel T % VW); VW divides 32, so the voxel
+// of a lane's tasks — and its depth hypothesis — is the same in every pass, and the pass of (view s, voxel v) is the
+// compile-time constant s * VW / 32).  Same arithmetic per channel as v5: bit-identical volumes (tests).
+template <int S, int CG, typename OutT, typename FeatT = float>
+__global__ void __launch_bounds__(256) cost_volume_var_cl6_kernel(bmv_cost_volume_params p, int DG) {
+  constexpr int VW = 32 / CG;                            // voxels per warp
+  constexpr int NP = (VW * S + 31) / 32;                 // tap passes per plane
+  __shared__ float sP[S * 12];
+  if (threadIdx.x < S * 12) sP[threadIdx.x] = p.proj[view_of(p, threadIdx.x / 12) * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x_base = (blockIdx.x * 8 + warp) * VW;
+  const int y = blockIdx.y;
+  if (x_base >= p.w) return;                             // whole warp out of the row
+  const int d_begin = blockIdx.z * DG, d_end = min(p.D, d_begin + DG);
+  const float sx = 2.f / (float)(p.Ws - 1), sy = 2.f / (float)(p.Hs - 1);
+  const int ys = (int)p.feat_y_stride, xs = (int)p.feat_x_stride;
+  // ---- tap-task roles of this lane
+  const int t_v = lane % VW;
+  const int t_x = min(x_base + t_v, p.w - 1);
+  const float* tP[NP];
+  float ax[NP], ay[NP], az[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const int t_s = min((q * 32 + lane) / VW, S - 1);
+    tP[q] = sP + t_s * 12;
+    ax[q] = dot3_gemm(tP[q][0], tP[q][1], tP[q][2], (float)t_x, (float)y, 1.f);
+    ay[q] = dot3_gemm(tP[q][4], tP[q][5], tP[q][6], (float)t_x, (float)y, 1.f);
+    az[q] = dot3_gemm(tP[q][8], tP[q][9], tP[q][10], (float)t_x, (float)y, 1.f);
+  }
+  const float* t_planes = p.planes + ((int64_t)y * p.w + t_x) * p.planes_pix_stride;
+  // ---- consumer role: voxel v of the warp, 8 channels starting at c0
+  const int v = lane / CG, c0 = (lane % CG) * 8;
+  const int x = x_base + v;
+  const bool active = x < p.w;
+  const FeatT* base[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) base[s] = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)view_of(p, s) * p.feat_view_stride + c0;
+  OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
+  constexpr float invS = 1.f / S;
+  const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
+  for (int d = d_begin; d < d_end; ++d) {
+    const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
+    FastTap t[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) t[q] = fast_taps(ax[q], ay[q], az[q], tP[q], idep, sx, sy, p.Hs, p.Ws, ys, xs);
+    float4 sum0, sq0, sum1, sq1;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int q = (s * VW) / 32;                       // compile-time after unrolling
+      const int src = (s * VW) % 32 + v;
+      const int o0 = __shfl_sync(0xffffffffu, t[q].off[0], src), o1 = __shfl_sync(0xffffffffu, t[q].off[1], src);
+      const int o2 = __shfl_sync(0xffffffffu, t[q].off[2], src), o3 = __shfl_sync(0xffffffffu, t[q].off[3], src);
+      const float w0 = __shfl_sync(0xffffffffu, t[q].w[0], src), w1 = __shfl_sync(0xffffffffu, t[q].w[1], src);
+      const float w2 = __shfl_sync(0xffffffffu, t[q].w[2], src), w3 = __shfl_sync(0xffffffffu, t[q].w[3], src);
+      float4 a0, a1, b0, b1, c0v, c1v, e0, e1;
+      ld_feat8(base[s] + o0, a0, a1); ld_feat8(base[s] + o1, b0, b1); ld_feat8(base[s] + o2, c0v, c1v); ld_feat8(base[s] + o3, e0, e1);
+      const float4 v0 = blend4(w0, w1, w2, w3, a0, b0, c0v, e0), v1 = blend4(w0, w1, w2, w3, a1, b1, c1v, e1);
+      if (s == 0) { acc_first(sum0, sq0, v0); acc_first(sum1, sq1, v1); }
+      else { acc_next(sum0, sq0, v0); acc_next(sum1, sq1, v1); }
+    }
+    if (active) store_var8<OutT>(outp + (int64_t)d * p.out_d_stride, variance4(sum0, sq0, invS, osc), variance4(sum1, sq1, invS, osc));
+  }
+}
+
 // v5-multi: the K cost volumes of cascade level 0 in ONE launch.  They share the target frustum and the depth
 // hypotheses, and their view triples are drawn from the same N source views, so a warped feature of view u at
 // (voxel, plane) is identical in every chain that contains u: gather each of the U UNIQUE views once (U x 4 taps
@@ -518,12 +640,134 @@ __global__ void __launch_bounds__(256) cost_volume_var_multi_kernel(bmv_cost_vol
   }
 }
 
+// v6-multi: v5-multi with eight channels per lane (see v6): VW = 32 / (C / 8) voxels per warp, the VW * U tap tasks
+// computed in up to two passes, 2 x K (sum, sum of squares) float4 pairs per lane.
+template <int CG, typename OutT, typename FeatT = float>
+__global__ void __launch_bounds__(256, 2) cost_volume_var_multi6_kernel(bmv_cost_volume_multi_params mp, int DG) {
+  const bmv_cost_volume_params& p = mp.b;
+  constexpr int VW = 32 / CG;                            // voxels per warp
+  constexpr int MAXU = 64 / VW;                          // unique views: the VW * U tap tasks take two passes at most
+  constexpr int NP = 2;
+  const int U = p.S, K = mp.K;
+  __shared__ float sP[BMV_MAX_VIEWS * 12];
+  __shared__ int s_uview[BMV_MAX_VIEWS], s_mask[BMV_MAX_VIEWS];
+  if (threadIdx.x < U) {
+    int vw = p.view[threadIdx.x], mask = mp.chain_mask[threadIdx.x];
+    if (mp.triples_dev) {                                // unique view u IS source view u; masks from the device table
+      vw = threadIdx.x;
+      mask = 0;
+      for (int k = 0; k < K; ++k)
+        for (int j = 0; j < mp.views_per_chain; ++j)
+          if (__ldg(mp.triples_dev + k * mp.views_per_chain + j) == vw) mask |= 1 << k;
+    }
+    s_uview[threadIdx.x] = vw;
+    s_mask[threadIdx.x] = mask;
+  }
+  __syncthreads();
+  if (threadIdx.x < U * 12) sP[threadIdx.x] = p.proj[s_uview[threadIdx.x / 12] * 12 + threadIdx.x % 12];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x_base = (blockIdx.x * 8 + warp) * VW;
+  const int y = blockIdx.y;
+  if (x_base >= p.w) return;
+  const int d_begin = blockIdx.z * DG, d_end = min(p.D, d_begin + DG);
+  const float sx = 2.f / (float)(p.Ws - 1), sy = 2.f / (float)(p.Hs - 1);
+  const int ys = (int)p.feat_y_stride, xs = (int)p.feat_x_stride;
+  // ---- tap-task roles: in pass q lane L computes the taps of (unique view (q * 32 + L) / VW, voxel L % VW)
+  const int t_v = lane % VW;
+  const int t_x = min(x_base + t_v, p.w - 1);
+  const float* tP[NP];
+  float ax[NP], ay[NP], az[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const int t_u = min((q * 32 + lane) / VW, U - 1);
+    tP[q] = sP + t_u * 12;
+    ax[q] = dot3_gemm(tP[q][0], tP[q][1], tP[q][2], (float)t_x, (float)y, 1.f);
+    ay[q] = dot3_gemm(tP[q][4], tP[q][5], tP[q][6], (float)t_x, (float)y, 1.f);
+    az[q] = dot3_gemm(tP[q][8], tP[q][9], tP[q][10], (float)t_x, (float)y, 1.f);
+  }
+  const bool pass1 = NP > 1 && VW * U > 32;              // uniform
+  const float* t_planes = p.planes + ((int64_t)y * p.w + t_x) * p.planes_pix_stride;
+  // ---- consumer role: voxel v of the warp, 8 channels starting at c0
+  const int v = lane / CG, c0 = (lane % CG) * 8;
+  const int x = x_base + v;
+  const bool active = x < p.w;
+  OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
+  const float invS = 1.f / (float)mp.views_per_chain;
+  const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
+  for (int d = d_begin; d < d_end; ++d) {
+    const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
+    FastTap t[NP];
+    t[0] = fast_taps(ax[0], ay[0], az[0], tP[0], idep, sx, sy, p.Hs, p.Ws, ys, xs);
+    if (NP > 1) {
+      if (pass1) t[NP - 1] = fast_taps(ax[NP - 1], ay[NP - 1], az[NP - 1], tP[NP - 1], idep, sx, sy, p.Hs, p.Ws, ys, xs);
+      else t[NP - 1] = t[0];
+    }
+    float4 sum[kMultiMaxK][2], sq[kMultiMaxK][2];
+#pragma unroll
+    for (int k = 0; k < kMultiMaxK; ++k)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { sum[k][h] = make_float4(0.f, 0.f, 0.f, 0.f); sq[k][h] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      if (u < U) {                                       // uniform
+        const int q = (u * VW) / 32;                     // compile-time after unrolling
+        const int src = (u * VW) % 32 + v;
+        const int o0 = __shfl_sync(0xffffffffu, t[q].off[0], src), o1 = __shfl_sync(0xffffffffu, t[q].off[1], src);
+        const int o2 = __shfl_sync(0xffffffffu, t[q].off[2], src), o3 = __shfl_sync(0xffffffffu, t[q].off[3], src);
+        const float w0 = __shfl_sync(0xffffffffu, t[q].w[0], src), w1 = __shfl_sync(0xffffffffu, t[q].w[1], src);
+        const float w2 = __shfl_sync(0xffffffffu, t[q].w[2], src), w3 = __shfl_sync(0xffffffffu, t[q].w[3], src);
+        const int mask = s_mask[u];
+        if (mask == 0) continue;                         // view in no chain (device-resident selection): uniform
+        const FeatT* base = reinterpret_cast<const FeatT*>(p.feat) + (int64_t)s_uview[u] * p.feat_view_stride + c0;
+        float4 a0, a1, b0, b1, c0v, c1v, e0, e1;
+        ld_feat8(base + o0, a0, a1); ld_feat8(base + o1, b0, b1); ld_feat8(base + o2, c0v, c1v); ld_feat8(base + o3, e0, e1);
+        const float4 v0 = blend4(w0, w1, w2, w3, a0, b0, c0v, e0), v1 = blend4(w0, w1, w2, w3, a1, b1, c1v, e1);
+#pragma unroll
+        for (int k = 0; k < kMultiMaxK; ++k)
+          if ((mask >> k) & 1) {                         // uniform
+            acc_next(sum[k][0], sq[k][0], v0);
+            acc_next(sum[k][1], sq[k][1], v1);
+          }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < kMultiMaxK; ++k)
+        if (k < K)
+          store_var8<OutT>(outp + (int64_t)k * mp.out_k_stride + (int64_t)d * p.out_d_stride, variance4(sum[k][0], sq[k][0], invS, osc),
+                           variance4(sum[k][1], sq[k][1], invS, osc));
+    }
+  }
+}
+
 template <typename OutT>
 static int launch_cost_volume_multi(const bmv_cost_volume_multi_params& mp, cudaStream_t st) {
   const bmv_cost_volume_params& p = mp.b;
   const int CG = p.C / 4, threads = 256, vpb = threads / CG;
   int DG = p.D;
   while (DG > 2 && (int64_t)p.w * p.h * CG * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
+  // v6 (eight channels per lane) when every voxel's 8-channel group is 32-byte (fp32) / 16-byte (16-bit) addressable
+  const int esz = p.feat_half ? 2 : 4;
+  static const int variant_env = getenv("BMV_K1_VARIANT") ? atoi(getenv("BMV_K1_VARIANT")) : 0;   // measurements
+  const bool wide = p.variant != 5 && variant_env != 5 && p.C % 8 == 0 && (64 / (32 / (p.C / 8))) >= p.S && p.feat_x_stride % 8 == 0 && p.feat_y_stride % 8 == 0 &&
+                    p.feat_view_stride % 8 == 0 && ((uintptr_t)p.feat & (8 * esz - 1)) == 0 && p.out_x_stride % 8 == 0 &&
+                    p.out_y_stride % 8 == 0 && p.out_d_stride % 8 == 0 && mp.out_k_stride % 8 == 0 &&
+                    ((uintptr_t)p.out & (8 * sizeof(OutT) - 1)) == 0;
+  if (wide) {
+    const int CG6 = p.C / 8, vpb6 = threads / CG6;
+    int DG6 = p.D;
+    while (DG6 > 2 && (int64_t)p.w * p.h * CG6 * ((p.D + DG6 - 1) / DG6) < 250000) DG6 = (DG6 + 1) / 2;
+    static const int dg_env = getenv("BMV_K1_DG") ? atoi(getenv("BMV_K1_DG")) : 0;
+    if (dg_env > 0) DG6 = dg_env;
+    dim3 grid6((p.w + vpb6 - 1) / vpb6, p.h, (p.D + DG6 - 1) / DG6);
+    if (p.feat_half) {
+      if (CG6 == 4) cost_volume_var_multi6_kernel<4, OutT, __half><<<grid6, threads, 0, st>>>(mp, DG6);
+      else cost_volume_var_multi6_kernel<2, OutT, __half><<<grid6, threads, 0, st>>>(mp, DG6);
+    } else if (CG6 == 4) cost_volume_var_multi6_kernel<4, OutT><<<grid6, threads, 0, st>>>(mp, DG6);
+    else cost_volume_var_multi6_kernel<2, OutT><<<grid6, threads, 0, st>>>(mp, DG6);
+    return check_launch("bmv_cost_volume_var_multi");
+  }
   dim3 grid((p.w + vpb - 1) / vpb, p.h, (p.D + DG - 1) / DG);
   if (p.feat_half) {
     if (CG == 8) cost_volume_var_multi_kernel<8, OutT, __half><<<grid, threads, 0, st>>>(mp, DG);
@@ -685,6 +929,30 @@ static int launch_cost_volume_s(const bmv_cost_volume_params& p, cudaStream_t st
     while (DG > 2 && (int64_t)p.w * p.h * CG3 * ((p.D + DG - 1) / DG) < 250000) DG = (DG + 1) / 2;
     dim3 grid(xchunks, p.h, (p.D + DG - 1) / DG);
     static const int dbg = getenv("BMV_K1_DEBUG") ? atoi(getenv("BMV_K1_DEBUG")) : 0;
+    // v6 (eight channels per lane) when every voxel's 8-channel group is 32-byte (fp32) / 16-byte (16-bit) addressable
+    const int esz = p.feat_half ? 2 : 4;
+    static const int variant_env = getenv("BMV_K1_VARIANT") ? atoi(getenv("BMV_K1_VARIANT")) : 0;   // measurements
+    const bool wide = p.variant != 5 && variant_env != 5 && dbg == 0 && (p.C == 16 || p.C == 32) && S <= 4 && p.feat_x_stride % 8 == 0 && p.feat_y_stride % 8 == 0 &&
+                      p.feat_view_stride % 8 == 0 && ((uintptr_t)p.feat & (8 * esz - 1)) == 0 && p.out_x_stride % 8 == 0 &&
+                      p.out_y_stride % 8 == 0 && p.out_d_stride % 8 == 0 && ((uintptr_t)p.out & (8 * sizeof(OutT) - 1)) == 0;
+    if constexpr (S <= 4) {
+      if (wide) {
+        const int CG6 = p.C / 8, vpb6 = threads / CG6;
+        int DG6 = p.D;
+        while (DG6 > 2 && (int64_t)p.w * p.h * CG6 * ((p.D + DG6 - 1) / DG6) < 250000) DG6 = (DG6 + 1) / 2;
+        static const int dg_env = getenv("BMV_K1_DG") ? atoi(getenv("BMV_K1_DG")) : 0;
+        if (dg_env > 0) DG6 = dg_env;
+        dim3 grid6((p.w + vpb6 - 1) / vpb6, p.h, (p.D + DG6 - 1) / DG6);
+        if (CG6 == 4) {
+          if (p.feat_half) cost_volume_var_cl6_kernel<S, 4, OutT, __half><<<grid6, threads, 0, st>>>(p, DG6);
+          else cost_volume_var_cl6_kernel<S, 4, OutT><<<grid6, threads, 0, st>>>(p, DG6);
+        } else {
+          if (p.feat_half) cost_volume_var_cl6_kernel<S, 2, OutT, __half><<<grid6, threads, 0, st>>>(p, DG6);
+          else cost_volume_var_cl6_kernel<S, 2, OutT><<<grid6, threads, 0, st>>>(p, DG6);
+        }
+        return check_launch("bmv_cost_volume_var");
+      }
+    }
     if constexpr (S <= 4) {
       if (CG3 == 8) {              // C = 32: warp = 4 voxels x 8 lanes, 2 planes per round
         if (p.feat_half) cost_volume_var_cl5_kernel<S, 8, 2, OutT, __half><<<grid, threads, 0, st>>>(p, DG, dbg);

@@ -9,9 +9,12 @@
 // writing the 8-channel output.  At half resolution `mid` is also the next step's `prev`, so it is
 // additionally written out (exact fp32) when p.mid is given.
 //
-// `mid` is computed in fp32 with exactly the arithmetic of fpn.cu; the 3x3 convolution runs on tensor
-// cores (mma.sync.m16n8k16, fp16 operands, fp32 accumulation: TF32-class — the host routes here only
-// when torch.backends.cudnn.allow_tf32 is set, see inference_plan.py).
+// `mid` is computed to fp32 accuracy (upsample: the arithmetic of fpn.cu; 1x1 lateral: tensor cores with both operands
+// split into fp16 hi + lo, ~1e-6 relative); the 3x3 convolution runs on tensor cores with plain fp16 operands
+// (mma.sync.m16n8k16, fp32 accumulation: TF32-class — the host routes here only when
+// torch.backends.cudnn.allow_tf32 is set, see inference_plan.py).
+#include <stdlib.h>
+
 #include "bmv_internal.cuh"
 #include "conv_mma.cuh"
 
@@ -25,10 +28,16 @@ constexpr int kFfTileBytes = kFfHY * kFfRowB;
 
 __device__ __forceinline__ int ff_swz(int v) { return (v >> 1) & 3; }
 
+// 8 consecutive fp32 channels with one 256-bit load (32-byte aligned)
+__device__ __forceinline__ void ldg8_f32(const float* q, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(q));
+}
+
 // OUT16: the instantiation that can write the fp16 version of the output (p.out16; p.out optional).  It is a template
 // switch, not a run-time test: the extra epilogue code cost the plain fp32 instantiation 16 us (321 -> 337 us, B200).
-template <int CIN, int NT, bool BREG, bool OUT16>
-__global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smooth_kernel(bmv_fpn_fused_params p) {
+template <int CIN, int NT, bool BREG, bool OUT16, int MINB>
+__global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bmv_fpn_fused_params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* tile = smem;
   uint2* wfrag = reinterpret_cast<uint2*>(smem + kFfTileBytes);
@@ -45,52 +54,107 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
   const int tiles_x = (p.W + kFfTX - 1) / kFfTX;
   const int x0 = (blockIdx.x % tiles_x) * kFfTX, y0 = (blockIdx.x / tiles_x) * kFfTY, n = blockIdx.y;
   const int Hp = p.H / 2, Wp = p.W / 2;
-  // ---- phase 1: mid tile (+1 halo; zero outside the image = the convolution's padding) -> fp16 in shared memory
+  // ---- phase 1: mid tile (+1 halo; zero outside the image = the convolution's padding) -> fp16 in shared memory.
+  // The 1x1 lateral convolution runs on the tensor cores too (round 2; the CUDA-core version spent ~1.2 k thread
+  // instructions per pixel here, 8 lanes x 150, and made the kernel issue-bound at 62 %): a warp takes 16 consecutive
+  // halo pixels as the M dimension of mma.sync.m16n8k16, 4 n-tiles = the 32 channels.  fp32 accuracy is kept by
+  // splitting both operands into fp16 hi + lo (lo pre-multiplied by 2^11 so that it stays a normal number):
+  //     lat = [x_hi * W_hi] + 2^-11 * [x_lo' * W_hi + x_hi * W_lo']     (the dropped lo * lo term is ~2^-22 relative)
+  // in two fp32 accumulators.  The columns of n-tile nt are PERMUTED (column n <-> channel (n / 2) * 8 + nt * 2 + n % 2)
+  // so that a lane's C fragments hold 8 CONSECUTIVE channels 8t .. 8t+7 of its two pixels: every `prev` tap is one
+  // 256-bit load, the fp16 tile entry one 16-byte store.
   {
     const float* lat = p.lateral_in + (int64_t)n * p.H * p.W * CIN;
     const float* prev = p.prev + (int64_t)n * Hp * Wp * 32;
     float* mid = p.mid ? p.mid + (int64_t)n * p.H * p.W * 32 : nullptr;
-    const int cg = threadIdx.x & 7;
-    const float4 bb = *reinterpret_cast<const float4*>(sW + 32 * CIN + cg * 4);
-    // the lane's 4 x CIN lateral weights live in registers: as shared-memory operands (one LDS.128 per input
-    // channel per item, 4 wavefronts each) they were 47 % of the L1 data-pipe wavefronts of this kernel (ncu)
-    float4 wreg[CIN];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int KK = CIN / 8;                                         // 8-channel groups of the lateral input
+    constexpr float kLoUp = 2048.f, kLoDown = 1.f / 2048.f;
+    uint32_t whi[4][KK], wlo[4][KK];
 #pragma unroll
-    for (int i = 0; i < CIN; ++i) wreg[i] = *reinterpret_cast<const float4*>(sW + i * 32 + cg * 4);
-    const float sy = up_scale(Hp, p.H), sx = up_scale(Wp, p.W);
-    for (int pi = threadIdx.x >> 3; pi < kFfHY * kFfHX; pi += kFfThreads / 8) {
-      const int hy = pi / kFfHX, hx = pi - hy * kFfHX;
-      const int y = y0 + hy - 1, x = x0 + hx - 1;
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-        const float* in = lat + ((int64_t)y * p.W + x) * CIN;
-        float v[CIN];
+    for (int nt = 0; nt < 4; ++nt) {
+      const int ch = (g >> 1) * 8 + nt * 2 + (g & 1);                   // channel of B-fragment column g
 #pragma unroll
-        for (int i = 0; i < CIN; i += 4) {
-          const float4 tt = __ldg(reinterpret_cast<const float4*>(in + i));
-          v[i] = tt.x; v[i + 1] = tt.y; v[i + 2] = tt.z; v[i + 3] = tt.w;
-        }
-        const UpCoord uy = up_coord_scaled(y, Hp, sy), ux = up_coord_scaled(x, Wp, sx);
-        const float* pb = prev + cg * 4;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)uy.i0 * Wp + ux.i0) * 32));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)uy.i0 * Wp + ux.i1) * 32));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)uy.i1 * Wp + ux.i0) * 32));
-        const float4 d = __ldg(reinterpret_cast<const float4*>(pb + ((int64_t)uy.i1 * Wp + ux.i1) * 32));
-        float acc[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-        for (int i = 0; i < CIN; ++i) {
-          const float4 w = wreg[i];
-          acc[0] = fmaf(w.x, v[i], acc[0]); acc[1] = fmaf(w.y, v[i], acc[1]);
-          acc[2] = fmaf(w.z, v[i], acc[2]); acc[3] = fmaf(w.w, v[i], acc[3]);
-        }
-        r.x = (uy.l0 * (ux.l0 * a.x + ux.l1 * b.x) + uy.l1 * (ux.l0 * c.x + ux.l1 * d.x)) + acc[0];
-        r.y = (uy.l0 * (ux.l0 * a.y + ux.l1 * b.y) + uy.l1 * (ux.l0 * c.y + ux.l1 * d.y)) + acc[1];
-        r.z = (uy.l0 * (ux.l0 * a.z + ux.l1 * b.z) + uy.l1 * (ux.l0 * c.z + ux.l1 * d.z)) + acc[2];
-        r.w = (uy.l0 * (ux.l0 * a.w + ux.l1 * b.w) + uy.l1 * (ux.l0 * c.w + ux.l1 * d.w)) + acc[3];
-        if (mid && hy >= 1 && hy <= kFfTY && hx >= 1 && hx <= kFfTX)
-          *reinterpret_cast<float4*>(mid + ((int64_t)y * p.W + x) * 32 + cg * 4) = r;
+      for (int kk = 0; kk < KK; ++kk) {
+        const float w0 = sW[(2 * t + 8 * kk) * 32 + ch], w1 = sW[(2 * t + 8 * kk + 1) * 32 + ch];
+        const __half h0 = half_sat(w0), h1 = half_sat(w1);
+        whi[nt][kk] = pack_half2_sat(w0, w1);
+        wlo[nt][kk] = pack_half2_sat((w0 - __half2float(h0)) * kLoUp, (w1 - __half2float(h1)) * kLoUp);
       }
-      *reinterpret_cast<uint2*>(tile + hy * kFfRowB + hx * 64 + (((cg >> 1) ^ ff_swz(hx)) << 4) + (cg & 1) * 8) = pack_half4(r);
+    }
+    const float sy = up_scale(Hp, p.H), sx = up_scale(Wp, p.W);
+    constexpr int NPIX = kFfHY * kFfHX, NSEG = (NPIX + 15) / 16;
+    for (int seg = warp; seg < NSEG; seg += kFfThreads / 32) {
+      int py[2], px[2], hyv[2], hxv[2];
+      bool ok[2];
+      uint32_t ahi[2][KK], alo[2][KK];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int pi = seg * 16 + g + 8 * e;
+        hyv[e] = pi / kFfHX; hxv[e] = pi - hyv[e] * kFfHX;
+        py[e] = y0 + hyv[e] - 1; px[e] = x0 + hxv[e] - 1;
+        ok[e] = pi < NPIX && py[e] >= 0 && py[e] < p.H && px[e] >= 0 && px[e] < p.W;
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          float2 vv = make_float2(0.f, 0.f);
+          if (ok[e]) vv = __ldg(reinterpret_cast<const float2*>(lat + ((int64_t)py[e] * p.W + px[e]) * CIN + 2 * t + 8 * kk));
+          const __half h0 = half_sat(vv.x), h1 = half_sat(vv.y);
+          ahi[e][kk] = pack_half2_sat(vv.x, vv.y);
+          alo[e][kk] = pack_half2_sat((vv.x - __half2float(h0)) * kLoUp, (vv.y - __half2float(h1)) * kLoUp);
+        }
+      }
+      float chi[4][4], clo[4][4];
+      const float4 lb0 = *reinterpret_cast<const float4*>(sW + 32 * CIN + t * 8), lb1 = *reinterpret_cast<const float4*>(sW + 32 * CIN + t * 8 + 4);
+      const float lbias[4][2] = {{lb0.x, lb0.y}, {lb0.z, lb0.w}, {lb1.x, lb1.y}, {lb1.z, lb1.w}};
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        chi[nt][0] = lbias[nt][0]; chi[nt][1] = lbias[nt][1]; chi[nt][2] = lbias[nt][0]; chi[nt][3] = lbias[nt][1];
+        clo[nt][0] = 0.f; clo[nt][1] = 0.f; clo[nt][2] = 0.f; clo[nt][3] = 0.f;
+        if (KK == 1) {        // K = 16 holds [x_hi (8) | x_lo' (8)]: B = [W_hi ; 0] and [W_lo' ; W_hi]
+          const uint32_t a[4] = {ahi[0][0], ahi[1][0], alo[0][0], alo[1][0]};
+          hmma16816(chi[nt], a, whi[nt][0], 0u);
+          hmma16816(clo[nt], a, wlo[nt][0], whi[nt][0]);
+        } else {              // K = 16 channels: x_hi * W_hi, x_lo' * W_hi, x_hi * W_lo'
+          const uint32_t a_h[4] = {ahi[0][0], ahi[1][0], ahi[0][KK - 1], ahi[1][KK - 1]};
+          const uint32_t a_l[4] = {alo[0][0], alo[1][0], alo[0][KK - 1], alo[1][KK - 1]};
+          hmma16816(chi[nt], a_h, whi[nt][0], whi[nt][KK - 1]);
+          hmma16816(clo[nt], a_l, whi[nt][0], whi[nt][KK - 1]);
+          hmma16816(clo[nt], a_h, wlo[nt][0], wlo[nt][KK - 1]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (seg * 16 + g + 8 * e >= NPIX) continue;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (ok[e]) {
+          const UpCoord uy = up_coord_scaled(py[e], Hp, sy), ux = up_coord_scaled(px[e], Wp, sx);
+          const float* pb = prev + t * 8;
+          float4 a0, a1, b0, b1, c0, c1, d0, d1;
+          ldg8_f32(pb + ((int64_t)uy.i0 * Wp + ux.i0) * 32, a0, a1);
+          ldg8_f32(pb + ((int64_t)uy.i0 * Wp + ux.i1) * 32, b0, b1);
+          ldg8_f32(pb + ((int64_t)uy.i1 * Wp + ux.i0) * 32, c0, c1);
+          ldg8_f32(pb + ((int64_t)uy.i1 * Wp + ux.i1) * 32, d0, d1);
+          const int o = 2 * e;
+          r0.x = (uy.l0 * (ux.l0 * a0.x + ux.l1 * b0.x) + uy.l1 * (ux.l0 * c0.x + ux.l1 * d0.x)) + fmaf(clo[0][o], kLoDown, chi[0][o]);
+          r0.y = (uy.l0 * (ux.l0 * a0.y + ux.l1 * b0.y) + uy.l1 * (ux.l0 * c0.y + ux.l1 * d0.y)) + fmaf(clo[0][o + 1], kLoDown, chi[0][o + 1]);
+          r0.z = (uy.l0 * (ux.l0 * a0.z + ux.l1 * b0.z) + uy.l1 * (ux.l0 * c0.z + ux.l1 * d0.z)) + fmaf(clo[1][o], kLoDown, chi[1][o]);
+          r0.w = (uy.l0 * (ux.l0 * a0.w + ux.l1 * b0.w) + uy.l1 * (ux.l0 * c0.w + ux.l1 * d0.w)) + fmaf(clo[1][o + 1], kLoDown, chi[1][o + 1]);
+          r1.x = (uy.l0 * (ux.l0 * a1.x + ux.l1 * b1.x) + uy.l1 * (ux.l0 * c1.x + ux.l1 * d1.x)) + fmaf(clo[2][o], kLoDown, chi[2][o]);
+          r1.y = (uy.l0 * (ux.l0 * a1.y + ux.l1 * b1.y) + uy.l1 * (ux.l0 * c1.y + ux.l1 * d1.y)) + fmaf(clo[2][o + 1], kLoDown, chi[2][o + 1]);
+          r1.z = (uy.l0 * (ux.l0 * a1.z + ux.l1 * b1.z) + uy.l1 * (ux.l0 * c1.z + ux.l1 * d1.z)) + fmaf(clo[3][o], kLoDown, chi[3][o]);
+          r1.w = (uy.l0 * (ux.l0 * a1.w + ux.l1 * b1.w) + uy.l1 * (ux.l0 * c1.w + ux.l1 * d1.w)) + fmaf(clo[3][o + 1], kLoDown, chi[3][o + 1]);
+          if (mid && hyv[e] >= 1 && hyv[e] <= kFfTY && hxv[e] >= 1 && hxv[e] <= kFfTX) {
+            float* m = mid + ((int64_t)py[e] * p.W + px[e]) * 32 + t * 8;
+            *reinterpret_cast<float4*>(m) = r0;
+            *reinterpret_cast<float4*>(m + 4) = r1;
+          }
+        }
+        uint4 pk;
+        pk.x = pack_half2_sat(r0.x, r0.y); pk.y = pack_half2_sat(r0.z, r0.w);
+        pk.z = pack_half2_sat(r1.x, r1.y); pk.w = pack_half2_sat(r1.z, r1.w);
+        *reinterpret_cast<uint4*>(tile + hyv[e] * kFfRowB + hxv[e] * 64 + ((t ^ ff_swz(hxv[e])) << 4)) = pk;
+      }
     }
   }
   __syncthreads();
@@ -167,16 +231,16 @@ __global__ void __launch_bounds__(kFfThreads, NT == 1 ? 3 : 2) fpn_topdown_smoot
   }
 }
 
-template <int CIN, int NT, bool BREG, bool OUT16>
+template <int CIN, int NT, bool BREG, bool OUT16, int MINB>
 static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
   const size_t smem = (size_t)kFfTileBytes + (size_t)3 * 6 * NT * 32 * 8 + (size_t)(32 * CIN + 32) * 4;
   static DeviceOnce configured;
   if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       // 68 % of the 228 KB: room for the resident CTAs' tiles, the rest stays L1 for the prev / lateral taps
       // (measured on B200: 329 us with the maximum carve-out, 315 us with 64-72 %, 404 us at 50 %)
-      e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16>, cudaFuncAttributePreferredSharedMemoryCarveout, 68);
+      e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 68);
     if (e != cudaSuccess) {
       set_error("bmv_fpn_topdown_smooth: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -184,13 +248,19 @@ static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
     configured.done(cfg_dev);
   }
   const dim3 grid((unsigned)(((p.W + kFfTX - 1) / kFfTX) * ((p.H + kFfTY - 1) / kFfTY)), (unsigned)p.N);
-  fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16><<<grid, kFfThreads, smem, st>>>(p);
+  fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB><<<grid, kFfThreads, smem, st>>>(p);
   return check_launch("bmv_fpn_topdown_smooth");
 }
 
 template <int CIN, int NT, bool BREG>
 static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
-  return p.out16 ? launch_ff_t<CIN, NT, BREG, true>(p, st) : launch_ff_t<CIN, NT, BREG, false>(p, st);
+  // resident CTAs per SM the kernel is compiled for: 3 (80 registers) or 2 (128); BMV_FF_MINB overrides (measurements)
+  static const int minb_env = getenv("BMV_FF_MINB") ? atoi(getenv("BMV_FF_MINB")) : 0;
+  const int minb = minb_env ? minb_env : (NT == 1 ? 3 : 2);
+  if constexpr (NT == 1) {
+    if (minb == 3) return p.out16 ? launch_ff_t<CIN, NT, BREG, true, 3>(p, st) : launch_ff_t<CIN, NT, BREG, false, 3>(p, st);
+  }
+  return p.out16 ? launch_ff_t<CIN, NT, BREG, true, 2>(p, st) : launch_ff_t<CIN, NT, BREG, false, 2>(p, st);
 }
 
 }  // namespace bmv
@@ -203,9 +273,9 @@ extern "C" BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv
   BMV_REQUIRE(((uintptr_t)p->out16 & 3) == 0, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown_smooth: out16 must be 4-byte aligned");
   BMV_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 2 && p->W >= 2 && p->H % 2 == 0 && p->W % 2 == 0, BMV_ERR_INVALID_ARGUMENT,
               "bmv_fpn_topdown_smooth: H, W must be even and >= 2");
-  BMV_REQUIRE(((uintptr_t)p->prev & 15) == 0 && ((uintptr_t)p->lateral_in & 15) == 0 && ((uintptr_t)p->out & 7) == 0 &&
+  BMV_REQUIRE(((uintptr_t)p->prev & 31) == 0 && ((uintptr_t)p->lateral_in & 15) == 0 && ((uintptr_t)p->out & 7) == 0 &&
                   ((uintptr_t)p->wfrag & 15) == 0 && ((uintptr_t)p->mid & 15) == 0,
-              BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown_smooth: tensors must be 16-byte aligned");
+              BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown_smooth: tensors must be 16-byte aligned (prev: 32-byte)");
   cudaStream_t st = (cudaStream_t)stream;
   if (p->Cin == 8 && p->Cout == 8) return launch_ff<8, 1, true>(*p, st);
   if (p->Cin == 16 && p->Cout == 16) return launch_ff<16, 2, false>(*p, st);

@@ -103,7 +103,7 @@ def _views_dev_ptr(t, n):
 
 
 def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float32, channels_last=False,
-                    exact_coords=False, out_scale=None, views_dev=None):
+                    exact_coords=False, out_scale=None, views_dev=None, variant=0):
     """Fused plane-sweep cost volume for ONE batch element.
 
     feats  (N,C,Hs,Ws) feature maps of all views, any strides (NCHW or channels_last)
@@ -112,6 +112,8 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
            (get_proj_mats, reference lib/networks/enerf/utils.py:35-55)
     planes (D,h,w) per-pixel hypotheses or (D,) shared
     -> (C,D,h,w) variance volume (reference lib/networks/enerf/utils.py:324-351)
+    variant 0: the fastest kernel generation the layout allows; 5: four channels per lane even where the
+    eight-channels-per-lane generation applies (bit-identical; A/B tests)
     """
     feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
@@ -133,13 +135,14 @@ def cost_volume_var(feats, views, proj, planes, out=None, out_dtype=torch.float3
     p.planes_d_stride, p.planes_pix_stride = h * w, 1
     p.D, p.h, p.w = D, h, w
     p.exact_coords = int(exact_coords)
+    p.variant = int(variant)
     p.out_scale = _scale_ptr(out_scale)
     p.view_dev = _views_dev_ptr(views_dev, S)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
 def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dtype=torch.float32,
-                           channels_last=False, exact_coords=False, out_scale=None, views_dev=None):
+                           channels_last=False, exact_coords=False, out_scale=None, views_dev=None, variant=0):
     """Same as cost_volume_var with D hypotheses shared by every pixel (cascade level 0)."""
     feat_half = _feat(feats, "feats")
     proj = _cf32(proj, "proj")
@@ -157,12 +160,13 @@ def cost_volume_var_shared(feats, views, proj, planes_d, h, w, out=None, out_dty
     p.planes_d_stride, p.planes_pix_stride = 1, 0
     p.D, p.h, p.w = D, h, w
     p.exact_coords = int(exact_coords)
+    p.variant = int(variant)
     p.out_scale = _scale_ptr(out_scale)
     p.view_dev = _views_dev_ptr(views_dev, S)
     return _cost_volume_launch(p, Cc, D, h, w, feats.device, out, out_dtype, channels_last)
 
 
-def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_scale=None, triples_dev=None):
+def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_scale=None, triples_dev=None, variant=0):
     """The K level-0 cost volumes (shared depth hypotheses) in one launch: every unique source view is warped once
     per (voxel, plane) and feeds the variance of each chain it belongs to (bmv_cost_volume_var_multi).
     feats (N,C,Hs,Ws) channels-last, triples: K lists of view ids (equal lengths), out (K,C,D,h,w) with
@@ -190,6 +194,7 @@ def cost_volume_var_shared_multi(feats, triples, proj, planes_d, h, w, out, out_
     p.planes_d_stride, p.planes_pix_stride = 1, 0
     p.D, p.h, p.w = D, h, w
     p.exact_coords = 0
+    p.variant = int(variant)
     p.out_scale = _scale_ptr(out_scale)
     p.out = out.data_ptr()
     p.out_c_stride, p.out_d_stride, p.out_y_stride, p.out_x_stride = out.stride(1), out.stride(2), out.stride(3), out.stride(4)

@@ -85,7 +85,9 @@ typedef struct bmv_cost_volume_params {
                                    slower); 0: reciprocal-multiply form, coordinates within 2 ulp (default) */
   int32_t feat_half;            /* 1: feat points to fp16 storage (strides in fp16 elements): half the bytes per bilinear tap.
                                    TF32-class (the maps come out of TF32-class convolutions): channels-last fast path only */
-  int32_t reserved0;
+  int32_t variant;              /* 0: the fastest kernel generation that fits the layout; 5: the four-channels-per-lane
+                                   generation (v5) even where the eight-channels-per-lane one (v6) applies (A/B tests:
+                                   the two are bit-identical) */
   const float* out_scale;       /* DEVICE or NULL: every stored variance is multiplied by out_scale[0] (a power of two from
                                    bmv_volume_scale): keeps an fp16 volume inside the fp16 range whatever the feature
                                    magnitude; the consuming convolution undoes it (bmv_conv3d_params.in_scale) */

@@ -36,6 +36,8 @@ def close(a, b, what, rtol=RTOL, scale=None):
 
 
 def exact(a, b, what):
+    if torch.is_tensor(a) and a.dtype == torch.bfloat16:      # numpy has no bf16; widening is injective
+        a, b = a.float(), b.float()
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
     b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
@@ -530,3 +532,43 @@ def test_cost_volume_fp16_feature_maps(ops):
     ops.cost_volume_var_shared_multi(f32c.float(), trip, proj, shared, 10, 14, out=o1)
     ops.cost_volume_var_shared_multi(f32c, trip, proj, shared, 10, 14, out=o2)
     close(o2, o1, "multi-chain kernel, fp16 feature maps", rtol=1e-6)
+
+
+@pytest.mark.parametrize("C", [16, 32])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("feat_half", [False, True])
+def test_cost_volume_wide_lane_generation_is_bit_identical(ops, C, dtype, feat_half):
+    """K1 v6 (eight channels per lane, 256-bit taps; the default where the layout allows) against v5 (four channels per
+    lane, variant=5): same taps, same FMA order per channel -> identical volumes, for per-pixel and shared hypotheses,
+    ragged widths (w not a multiple of the warp's voxel count) and the multi-chain kernel."""
+    torch.manual_seed(C)
+    N, Hs, Ws, D = 6, 36, 52, 8
+    feats = torch.randn(N, C, Hs, Ws, device="cuda").contiguous(memory_format=torch.channels_last)
+    if feat_half:
+        feats = feats.half()
+    h, w = 35, 45
+    proj = torch.eye(3, 4, device="cuda").repeat(N, 1, 1)
+    proj[:, :, 3] = torch.randn(N, 3, device="cuda") * torch.tensor([3.0, 2.0, 0.01], device="cuda")
+    proj[:, 2, :3] += torch.randn(N, 3, device="cuda") * 1e-3
+    planes = torch.rand(D, h, w, device="cuda") * 3 + 0.5
+    for views in ([0, 2, 3], [5, 1], [4, 3, 2, 0]):
+        a = ops.cost_volume_var(feats, views, proj, planes, channels_last=True, out_dtype=dtype)
+        b = ops.cost_volume_var(feats, views, proj, planes, channels_last=True, out_dtype=dtype, variant=5)
+        assert float(a.float().abs().max()) > 0.1
+        exact(a, b, f"v6 == v5, per-pixel planes, views {views}")
+    shared = torch.linspace(0.5, 4.0, 12, device="cuda")
+    a = ops.cost_volume_var_shared(feats, [1, 2, 4], proj, shared, h, w, channels_last=True, out_dtype=dtype)
+    b = ops.cost_volume_var_shared(feats, [1, 2, 4], proj, shared, h, w, channels_last=True, out_dtype=dtype, variant=5)
+    exact(a, b, "v6 == v5, shared planes")
+    triples = [[0, 1, 2], [1, 2, 3], [3, 4, 5], [0, 2, 5]] if C == 32 else [[0, 1, 2], [2, 3, 1], [3, 0, 1]]
+    K = len(triples)
+    o6 = torch.empty((K, 12, h, w, C), device="cuda", dtype=dtype).permute(0, 4, 1, 2, 3)
+    o5 = torch.empty_like(o6)
+    ops.cost_volume_var_shared_multi(feats, triples, proj, shared, h, w, out=o6)
+    ops.cost_volume_var_shared_multi(feats, triples, proj, shared, h, w, out=o5, variant=5)
+    exact(o6, o5, "multi-chain v6 == v5")
+    tdev = torch.tensor(triples, dtype=torch.int32, device="cuda").reshape(-1)
+    if C == 32:                                    # device-resident selection: every source view is a unique view (6 <= 8)
+        o6d = torch.empty_like(o6)
+        ops.cost_volume_var_shared_multi(feats, triples, proj, shared, h, w, out=o6d, triples_dev=tdev)
+        exact(o6d, o6, "multi-chain v6, device-resident triples")
