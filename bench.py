@@ -217,17 +217,21 @@ def load_ncu_traffic():
         NCU_TRAFFIC_MB, NCU_TRAFFIC_SOURCE = {}, None
 
 
-def conv_kernel_bytes(wl, rc, volume_bytes=4, heads_entry="bmv_conv3d_k3"):
+def conv_kernel_bytes(wl, rc, volume_bytes=4, heads_entry="bmv_conv3d_k3", fpn_mid=False):
     """Compulsory HBM bytes of each libbmv convolution launch of one frame, keyed by entry point, in launch
     order (FPN: stem, half-resolution step, full-resolution step; per cascade level: conv0, conv1, conv2, heads /
     conv9T, conv11T).  All K chains (N views) are batched in one launch.  heads_entry: the entry point the merged
     heads run on (bmv_conv3d_k3_umma when the inference plan routes them to the tcgen05 kernel)."""
     H, W, K, N = wl["H"], wl["W"], wl["K"], wl["n_views"]
     px = N * H * W
-    out = {"bmv_fpn_stem": [("fpn_stem", px * 4 * (3 + 8 + 4 + 8))],
+    # stem: image in, c0 + the (N,H,W,4) colour image out (+ the space-to-depth copy of c0 when conv1.0 runs on cuDNN)
+    out = {"bmv_fpn_stem": [("fpn_stem", px * 4 * (3 + 8 + 4 + (0 if fpn_mid else 8)))],
            "bmv_fpn_topdown_smooth": [("fpn_topdown_smooth_half", px // 4 * 4 * (32 // 4 + 16 + 32 + 16)),
                                       ("fpn_topdown_smooth_full", px * 4 * (32 // 4 + 8 + 8))],
            "bmv_conv3d_k3": [], "bmv_convT3d_k3s2": []}
+    if fpn_mid:      # csrc/conv2d_mma.cu: conv1.0 (reads c0 through space-to-depth), conv1.1, conv2.0, conv2.1 + top layer
+        out["bmv_conv2d_k3"] = [("fpn_conv1_0", px * 8 * 4 + px // 4 * 16 * 2), ("fpn_conv1_1", px // 4 * 16 * (2 + 4)),
+                                ("fpn_conv2_0", px // 4 * 16 * 4 + px // 16 * 32 * 2), ("fpn_conv2_1_top", px // 16 * 32 * (2 + 4))]
     out.setdefault(heads_entry, [])
     for i in range(rc.num):
         C = int(32 * 2 ** (-i))
@@ -646,7 +650,7 @@ def main_ours(args):
                              "share_of_step": per_launch_ms * launches_per_stage[name] / ms}
     # libbmv convolution kernels (one launch each per frame), same accounting
     heads_entry = "bmv_conv3d_k3_umma" if ksum.get("bmv_conv3d_k3_umma") else "bmv_conv3d_k3"
-    for entry, layers in conv_kernel_bytes(wl, rc, 2 if vol_dtype == "float16" else 4, heads_entry).items():
+    for entry, layers in conv_kernel_bytes(wl, rc, 2 if vol_dtype == "float16" else 4, heads_entry, bool(ksum.get("bmv_conv2d_k3"))).items():
         ts = ksum.get(entry, [])
         if len(ts) != len(layers) * args.steps:
             continue

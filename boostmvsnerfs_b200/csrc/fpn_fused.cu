@@ -36,7 +36,7 @@ __device__ __forceinline__ void ldg8_f32(const float* q, float4& a, float4& b) {
 
 // OUT16: the instantiation that can write the fp16 version of the output (p.out16; p.out optional).  It is a template
 // switch, not a run-time test: the extra epilogue code cost the plain fp32 instantiation 16 us (321 -> 337 us, B200).
-template <int CIN, int NT, bool BREG, bool OUT16, int MINB>
+template <int CIN, int NT, bool BREG, bool OUT16, int MINB, bool LAT16>
 __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bmv_fpn_fused_params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* tile = smem;
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
   // so that a lane's C fragments hold 8 CONSECUTIVE channels 8t .. 8t+7 of its two pixels: every `prev` tap is one
   // 256-bit load, the fp16 tile entry one 16-byte store.
   {
-    const float* lat = p.lateral_in + (int64_t)n * p.H * p.W * CIN;
+    const float* lat = p.lateral_in + (LAT16 ? 0 : (int64_t)n * p.H * p.W * CIN);
+    const __half* lat16 = reinterpret_cast<const __half*>(p.lateral_in) + (int64_t)n * p.H * p.W * CIN;
     const float* prev = p.prev + (int64_t)n * Hp * Wp * 32;
     float* mid = p.mid ? p.mid + (int64_t)n * p.H * p.W * 32 : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,11 +98,16 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
         ok[e] = pi < NPIX && py[e] >= 0 && py[e] < p.H && px[e] >= 0 && px[e] < p.W;
 #pragma unroll
         for (int kk = 0; kk < KK; ++kk) {
-          float2 vv = make_float2(0.f, 0.f);
-          if (ok[e]) vv = __ldg(reinterpret_cast<const float2*>(lat + ((int64_t)py[e] * p.W + px[e]) * CIN + 2 * t + 8 * kk));
-          const __half h0 = half_sat(vv.x), h1 = half_sat(vv.y);
-          ahi[e][kk] = pack_half2_sat(vv.x, vv.y);
-          alo[e][kk] = pack_half2_sat((vv.x - __half2float(h0)) * kLoUp, (vv.y - __half2float(h1)) * kLoUp);
+          if (LAT16) {          // fp16 lateral input (what the stem / bmv_conv2d_k3 emit): exact operands, no lo part
+            ahi[e][kk] = ok[e] ? __ldg(reinterpret_cast<const uint32_t*>(lat16 + ((int64_t)py[e] * p.W + px[e]) * CIN + 2 * t + 8 * kk)) : 0u;
+            alo[e][kk] = 0u;
+          } else {
+            float2 vv = make_float2(0.f, 0.f);
+            if (ok[e]) vv = __ldg(reinterpret_cast<const float2*>(lat + ((int64_t)py[e] * p.W + px[e]) * CIN + 2 * t + 8 * kk));
+            const __half h0 = half_sat(vv.x), h1 = half_sat(vv.y);
+            ahi[e][kk] = pack_half2_sat(vv.x, vv.y);
+            alo[e][kk] = pack_half2_sat((vv.x - __half2float(h0)) * kLoUp, (vv.y - __half2float(h1)) * kLoUp);
+          }
         }
       }
       float chi[4][4], clo[4][4];
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
           const uint32_t a_h[4] = {ahi[0][0], ahi[1][0], ahi[0][KK - 1], ahi[1][KK - 1]};
           const uint32_t a_l[4] = {alo[0][0], alo[1][0], alo[0][KK - 1], alo[1][KK - 1]};
           hmma16816(chi[nt], a_h, whi[nt][0], whi[nt][KK - 1]);
-          hmma16816(clo[nt], a_l, whi[nt][0], whi[nt][KK - 1]);
+          if (!LAT16) hmma16816(clo[nt], a_l, whi[nt][0], whi[nt][KK - 1]);
           hmma16816(clo[nt], a_h, wlo[nt][0], wlo[nt][KK - 1]);
         }
       }
@@ -231,16 +237,16 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
   }
 }
 
-template <int CIN, int NT, bool BREG, bool OUT16, int MINB>
-static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
+template <int CIN, int NT, bool BREG, bool OUT16, int MINB, bool LAT16>
+static int launch_ff_l(const bmv_fpn_fused_params& p, cudaStream_t st) {
   const size_t smem = (size_t)kFfTileBytes + (size_t)3 * 6 * NT * 32 * 8 + (size_t)(32 * CIN + 32) * 4;
   static DeviceOnce configured;
   if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB, LAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       // 68 % of the 228 KB: room for the resident CTAs' tiles, the rest stays L1 for the prev / lateral taps
       // (measured on B200: 329 us with the maximum carve-out, 315 us with 64-72 %, 404 us at 50 %)
-      e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 68);
+      e = cudaFuncSetAttribute(fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB, LAT16>, cudaFuncAttributePreferredSharedMemoryCarveout, 68);
     if (e != cudaSuccess) {
       set_error("bmv_fpn_topdown_smooth: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -248,8 +254,13 @@ static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
     configured.done(cfg_dev);
   }
   const dim3 grid((unsigned)(((p.W + kFfTX - 1) / kFfTX) * ((p.H + kFfTY - 1) / kFfTY)), (unsigned)p.N);
-  fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB><<<grid, kFfThreads, smem, st>>>(p);
+  fpn_topdown_smooth_kernel<CIN, NT, BREG, OUT16, MINB, LAT16><<<grid, kFfThreads, smem, st>>>(p);
   return check_launch("bmv_fpn_topdown_smooth");
+}
+
+template <int CIN, int NT, bool BREG, bool OUT16, int MINB>
+static int launch_ff_t(const bmv_fpn_fused_params& p, cudaStream_t st) {
+  return p.lat_half ? launch_ff_l<CIN, NT, BREG, OUT16, MINB, true>(p, st) : launch_ff_l<CIN, NT, BREG, OUT16, MINB, false>(p, st);
 }
 
 template <int CIN, int NT, bool BREG>

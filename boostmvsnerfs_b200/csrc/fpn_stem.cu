@@ -9,7 +9,7 @@
 // Stage B: first convolution on CUDA cores in fp32 (K = 27 is too ragged for an MMA tile), ReLU, stored
 //          as fp16 with a 1-pixel halo (zero outside the image = the second convolution's padding).
 // Stage C: second convolution on tensor cores (mma.sync.m16n8k16, 8 input channels: two horizontal taps
-//          per MMA as in conv3d_mma.cu), bias + ReLU, fp32 channels-last output.
+//          per MMA as in conv3d_mma.cu), bias + ReLU, fp32 (or fp16: out_half) channels-last output.
 // fp16 operands in stage C make the result TF32-class: the host uses this kernel only when
 // torch.backends.cudnn.allow_tf32 is set (inference_plan.py).
 #include "bmv_internal.cuh"
@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(kStThreads, 3) fpn_stem_kernel(bmv_fpn_stem_pa
       if (gy >= p.H) continue;
       const float2 r0 = make_float2(fmaxf(acc[oy][0], 0.f), fmaxf(acc[oy][1], 0.f));
       const float2 r1 = make_float2(fmaxf(acc[oy][2], 0.f), fmaxf(acc[oy][3], 0.f));
+      if (p.out_half) {             // 4 bytes per lane; the 8 pixels of a warp-level store are 128 contiguous bytes
+        __half* o16 = reinterpret_cast<__half*>(p.out) + (int64_t)n * p.H * p.W * 8;
+        if (gx0 < p.W) *reinterpret_cast<uint32_t*>(o16 + ((int64_t)gy * p.W + gx0) * 8 + 2 * t) = pack_half2_sat(r0.x, r0.y);
+        if (gx1 < p.W) *reinterpret_cast<uint32_t*>(o16 + ((int64_t)gy * p.W + gx1) * 8 + 2 * t) = pack_half2_sat(r1.x, r1.y);
+        continue;
+      }
       if (gx0 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx0) * 8 + 2 * t) = r0;
       if (gx1 < p.W) *reinterpret_cast<float2*>(out + ((int64_t)gy * p.W + gx1) * 8 + 2 * t) = r1;
       if (p.out_s2d) {                                                  // (N, H/2, W/2, [py][px][8])
@@ -143,6 +149,7 @@ extern "C" BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t s
   BMV_REQUIRE(((uintptr_t)p->out & 7) == 0 && ((uintptr_t)p->wfrag1 & 7) == 0 && ((uintptr_t)p->rgb4 & 15) == 0 &&
                   ((uintptr_t)p->out_s2d & 7) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: out / out_s2d / wfrag1 must be 8-byte, rgb4 16-byte aligned");
+  BMV_REQUIRE(!p->out_half || !p->out_s2d, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_stem: the fp16 output has no space-to-depth copy");
   BMV_REQUIRE(!p->out_s2d || (p->H % 2 == 0 && p->W % 2 == 0), BMV_ERR_INVALID_ARGUMENT,
               "bmv_fpn_stem: the space-to-depth output needs even H and W");
   const dim3 grid((unsigned)(((p->W + kStTX - 1) / kStTX) * ((p->H + kStTY - 1) / kStTY)), (unsigned)p->N);

@@ -231,13 +231,43 @@ class FusedTopDownFPN(nn.Module):
     # they overlap the level-0 chain (K1 + 3-D CNN, tensor- and latency-bound).  `ready` then maps 'level_1' / 'level_2'
     # to the events the consumer must wait for (network.StreamedFeats does); None when nothing was deferred.
     side_topdown = False
+    # conv1.x, conv2.x and the top layer on libbmv's tensor-core kernel (csrc/conv2d_mma.cu) instead of cuDNN: four
+    # launches instead of seven (the 5x5 / stride-2 layers read their input through space-to-depth in the staging loop,
+    # the 1x1 top layer runs in conv2.1's epilogue), fp16 intermediates between them.  TF32-class like the rest.
+    tensor_core_mid = True
 
     def __init__(self, fpn):
         super().__init__()
         self.fpn = fpn
         self._packed = None
+        self._mid = None
         self._side = None
         self.ready = None
+
+    def _mid_weights(self, device):
+        if self._mid is None or self._mid['device'] != device:
+            from .mlp_pack import pack_conv1x1_after, pack_conv2d_k3
+            f = self.fpn
+            b = lambda m: m.bias.detach().float().contiguous().to(device)
+            self._mid = {
+                'device': device,
+                'c10': (pack_conv2d_k3(f.conv1[0].weight).to(device), b(f.conv1[0])),
+                'c11': (pack_conv2d_k3(f.conv1[1].conv.weight).to(device), b(f.conv1[1].conv)),
+                'c20': (pack_conv2d_k3(f.conv2[0].weight).to(device), b(f.conv2[0])),
+                'c21': (pack_conv2d_k3(f.conv2[1].conv.weight).to(device), b(f.conv2[1].conv)),
+                'top': (pack_conv1x1_after(f.toplayer.weight).to(device), b(f.toplayer)),
+            }
+        return self._mid
+
+    def _mid_ok(self, x):
+        f = self.fpn
+        return (self.tensor_core_mid and x.shape[-1] % 4 == 0 and x.shape[-2] % 4 == 0
+                and isinstance(f.conv1[0], S2DConv5x5) and isinstance(f.conv2[0], S2DConv5x5)
+                and f.conv1[0].relu and f.conv2[0].relu and f.conv1[0].bias is not None and f.conv2[0].bias is not None
+                and isinstance(f.conv1[1].bn, nn.Identity) and isinstance(f.conv2[1].bn, nn.Identity)
+                and f.conv1[1].conv.bias is not None and f.conv2[1].conv.bias is not None
+                and tuple(f.conv1[0].weight.shape) == (16, 32, 3, 3) and tuple(f.conv2[0].weight.shape) == (32, 64, 3, 3)
+                and tuple(f.toplayer.weight.shape[:2]) == (32, 32) and f.toplayer.bias is not None)
 
     def _smooth_weights(self, device):
         if self._packed is None or self._packed[0].device != device:
@@ -252,17 +282,35 @@ class FusedTopDownFPN(nn.Module):
         f = self.fpn
         fused = self.fused_smooth and torch.backends.cudnn.allow_tf32
         self.rgb_nhwc4 = None
+        quarter = None
         if fused and isinstance(f.conv0[0].bn, nn.Identity):
             a, b = f.conv0[0].conv, f.conv0[1].conv      # the stem reads x with any strides: no layout copy
-            want_s2d = isinstance(f.conv1[0], S2DConv5x5) and x.shape[-1] % 2 == 0 and x.shape[-2] % 2 == 0
-            c0, self.rgb_nhwc4, z0 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias,
-                                                  want_rgb4=True, want_s2d=want_s2d)
-            c1 = f.conv1[1](f.conv1[0].forward_s2d(z0)) if want_s2d else f.conv1(c0)
+            if self._mid_ok(x):
+                # every tensor between the stem and the top layer is an MMA operand of its consumers (conv1.0 / conv2.0, the
+                # 1x1 laterals of the top-down steps): stored as fp16 = the rounding those consumers apply anyway
+                h = torch.float16
+                c0, self.rgb_nhwc4 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias, want_rgb4=True,
+                                                  out_dtype=h)
+                mw = self._mid_weights(x.device)
+                c1 = ops.conv2d_k3(c0, *mw['c10'], 16, relu=True, s2d=True, out_dtype=h)          # conv1.0: 5x5 / stride 2
+                c1 = ops.conv2d_k3(c1, *mw['c11'], 16, relu=True, out_dtype=h)                     # conv1.1 (also read by lat1)
+                c2 = ops.conv2d_k3(c1, *mw['c20'], 32, relu=True, s2d=True, out_dtype=h)          # conv2.0: 5x5 / stride 2
+                quarter = ops.conv2d_k3(c2, *mw['c21'], 32, relu=True, wfrag1x1=mw['top'][0], bias1x1=mw['top'][1])   # conv2.1 + toplayer
+            else:
+                want_s2d = isinstance(f.conv1[0], S2DConv5x5) and x.shape[-1] % 2 == 0 and x.shape[-2] % 2 == 0
+                if want_s2d:
+                    c0, self.rgb_nhwc4, z0 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias,
+                                                          want_rgb4=True, want_s2d=True)
+                    c1 = f.conv1[1](f.conv1[0].forward_s2d(z0))
+                else:
+                    c0, self.rgb_nhwc4 = ops.fpn_stem(x, a.weight, a.bias, self._smooth_weights(x.device)[2], b.bias, want_rgb4=True)
+                    c1 = f.conv1(c0)
         else:
             c0 = f.conv0(x.contiguous(memory_format=torch.channels_last))
             c1 = f.conv1(c0)
-        c2 = f.conv2(c1)
-        quarter = f.toplayer(c2)
+        if quarter is None:
+            c2 = f.conv2(c1)
+            quarter = f.toplayer(c2)
         self.ready = None
         if fused:
             w1, w0, _ = self._smooth_weights(x.device)

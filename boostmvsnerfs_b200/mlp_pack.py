@@ -338,6 +338,48 @@ def pack_conv2d_k3_c32(weight):
     return out.reshape(-1).view(torch.int32).to(weight.device)
 
 
+def pack_conv2d_k3(weight):
+    """Conv2d weight (Cout, Cin, 3, 3), Cin in {16, 32, 64}, Cout in {16, 32} -> int32 tensor in the order bmv_conv2d_k3
+    reads: [dy][j = dx * (Cin/16) + part][n-tile][lane = 4g+t] x {b0, b1}; K index kk of k-step j is input channel
+    part*16 + kk; column g of n-tile nt is output channel (g//2) * 2NT + 2nt + g%2 (a lane's C fragments then hold 2NT
+    consecutive channels of a pixel)."""
+    Cout, Cin = weight.shape[:2]
+    if Cin not in (16, 32, 64) or Cout not in (16, 32) or tuple(weight.shape[2:]) != (3, 3):
+        raise ValueError(f"conv2d_k3 is not instantiated for weight {tuple(weight.shape)}")
+    w = weight.detach().float().cpu().half()                  # (Cout, Cin, dy, dx)
+    NT, KPD = Cout // 8, Cin // 16
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((3, 3 * KPD, NT, 32, 2, 2), dtype=torch.float16)
+    for j in range(3 * KPD):
+        dx, part = j // KPD, j % KPD
+        for nt in range(NT):
+            ch = (g // 2) * (2 * NT) + nt * 2 + (g % 2)
+            for r in range(2):
+                for e in range(2):
+                    out[:, j, nt, :, r, e] = w[ch, part * 16 + 2 * t + 8 * r + e, :, dx].T
+    return out.reshape(-1).view(torch.int32).to(weight.device)
+
+
+def pack_conv1x1_after(weight):
+    """1x1 Conv2d weight (32, 32[, 1, 1]) applied to the output of a 32-channel bmv_conv2d_k3 layer inside its epilogue:
+    [k-step kk][n-tile][lane] x {b0, b1}.  The A fragments are that layer's C fragments, so K index 2t+e (+8 for r = 1)
+    of k-step kk is ITS channel t*8 + (2kk + r)*2 + e; output columns permuted like pack_conv2d_k3's."""
+    w = weight.detach().float().cpu().reshape(weight.shape[0], weight.shape[1]).half()
+    if tuple(w.shape) != (32, 32):
+        raise ValueError(f"conv1x1_after is instantiated for 32 -> 32 channels, got {tuple(weight.shape)}")
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    out = torch.empty((2, 4, 32, 2, 2), dtype=torch.float16)
+    for kk in range(2):
+        for nt in range(4):
+            ch = (g // 2) * 8 + nt * 2 + (g % 2)
+            for r in range(2):
+                for e in range(2):
+                    out[kk, nt, :, r, e] = w[ch, t * 8 + (2 * kk + r) * 2 + e]
+    return out.reshape(-1).view(torch.int32).to(weight.device)
+
+
 def pack_conv2d_k3_c8(weight):
     """Conv2d weight (8, 8, 3, 3) -> int32 tensor (384,) in the order bmv_fpn_stem reads: [dy][k-step j][lane] x {b0, b1};
     k-step 0 holds taps dx = 0 (K 0..7) and dx = 1 (K 8..15), k-step 1 holds dx = 2 and zeros."""

@@ -866,8 +866,13 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     (reference lib/networks/enerf/feature_net.py:24-47; the 3x3 runs on tensor cores with fp16 operands).
     Returns (mid or None, out); tensors channels_last, smooth_wfrag from mlp_pack.pack_conv2d_k3_c32.
     want_half: True = also write an fp16 copy of out (returned as a third value) for the cost-volume kernel's fp16
-    taps; 'only' = write out in fp16 ONLY (returned in place of out)."""
-    _f32(prev, "prev"); _f32(lateral_in, "lateral_in")
+    taps; 'only' = write out in fp16 ONLY (returned in place of out).  lateral_in: fp32 or fp16 (what fpn_stem /
+    conv2d_k3 emit with out_dtype=float16: the 1x1 lateral then takes it as an exact tensor-core operand)."""
+    _f32(prev, "prev")
+    if lateral_in.dtype != torch.float16:
+        _f32(lateral_in, "lateral_in")
+    elif not lateral_in.is_cuda:
+        raise BmvError("fpn_topdown_smooth: lateral_in must be a CUDA tensor")
     N, Cin, H, W = lateral_in.shape
     if not (prev.is_contiguous(memory_format=torch.channels_last) and lateral_in.is_contiguous(memory_format=torch.channels_last)):
         raise BmvError("fpn_topdown_smooth: inputs must be channels_last")
@@ -885,6 +890,7 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     p.wfrag = smooth_wfrag.data_ptr()
     p.bias = sb.data_ptr() if sb is not None else 0
     p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, Cin, cout
+    p.lat_half = int(lateral_in.dtype == torch.float16)
     p.mid = mid.data_ptr() if mid is not None else 0
     p.out = out.data_ptr() if out is not None else 0
     out16 = torch.empty((N, cout, H, W), device=prev.device, dtype=torch.float16, memory_format=torch.channels_last) if want_half else None
@@ -895,7 +901,7 @@ def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smo
     return (mid, out, out16) if want_half else (mid, out)
 
 
-def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False):
+def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False, out_dtype=torch.float32):
     """relu(conv3x3_{8->8}(relu(conv3x3_{3->8}(x) + b0)) + b1) in one launch (reference
     lib/networks/enerf/feature_net.py:7-9; BN already folded into w/b).  x (N,3,H,W) fp32, any strides;
     returns (N,8,H,W) channels_last — and, with want_rgb4, also x as an (N,H,W,4) [r,g,b,0] tensor (the layout
@@ -909,8 +915,11 @@ def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False):
     if wfrag1.dtype != torch.int32 or wfrag1.numel() != 384:
         raise BmvError("fpn_stem: wfrag1 must come from mlp_pack.pack_conv2d_k3_c8")
     w0c, b0c, b1c = _cf32(w0.reshape(8, 27), "w0"), _cf32(b0, "b0"), _cf32(b1, "b1")
-    out = torch.empty((N, 8, H, W), device=x.device, memory_format=torch.channels_last)
+    if out_dtype not in (torch.float32, torch.float16) or (out_dtype == torch.float16 and want_s2d):
+        raise BmvError("fpn_stem: out_dtype is fp32 or fp16 (fp16 without the space-to-depth copy)")
+    out = torch.empty((N, 8, H, W), device=x.device, dtype=out_dtype, memory_format=torch.channels_last)
     p = _lib.FpnStemParams()
+    p.out_half = int(out_dtype == torch.float16)
     p.x = x.data_ptr()
     p.x_n_stride, p.x_c_stride, p.x_y_stride, p.x_x_stride = x.stride()
     p.w0, p.b0, p.wfrag1, p.b1 = w0c.data_ptr(), b0c.data_ptr(), wfrag1.data_ptr(), b1c.data_ptr()
@@ -928,6 +937,50 @@ def fpn_stem(x, w0, b0, wfrag1, b1, want_rgb4=False, want_s2d=False):
     if want_s2d:
         return out, rgb4, s2d
     return (out, rgb4) if want_rgb4 else out
+
+
+def conv2d_k3(x, wfrag, bias, cout, relu=True, s2d=False, out_dtype=torch.float32, wfrag1x1=None, bias1x1=None, cout1x1=32):
+    """3x3 / pad-1 convolution (+bias, +ReLU) of the FPN's middle layers on tensor cores (bmv_conv2d_k3; fp16 operands,
+    fp32 accumulation: TF32-class).  x channels-last: fp16 (N,Cin,H,W), or with s2d=True fp32 (N,Cin/4,2H,2W) read
+    through space-to-depth(2) (a 5x5 / stride-2 layer regrouped by inference_plan.S2DConv5x5).  wfrag from
+    mlp_pack.pack_conv2d_k3.  With wfrag1x1 (mlp_pack.pack_conv1x1_after) a 1x1 convolution is applied to the ReLU'd
+    result inside the epilogue and only ITS output (fp32) is written."""
+    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.stride(1) == 1):
+        raise BmvError("conv2d_k3: x must be a channels-last CUDA tensor (N,C,H,W)")
+    _on_current_device(x, "x")
+    if s2d:
+        if x.dtype not in (torch.float32, torch.float16) or x.shape[2] % 2 or x.shape[3] % 2:
+            raise BmvError("conv2d_k3: the space-to-depth mode reads an fp32 / fp16 tensor with even H and W")
+        N, cin, H, W = x.shape[0], 4 * x.shape[1], x.shape[2] // 2, x.shape[3] // 2
+    else:
+        if x.dtype != torch.float16:
+            raise BmvError("conv2d_k3: the dense mode reads fp16")
+        N, cin, H, W = x.shape
+    words = _lib.load().bmv_conv2d_k3_weight_words(cin, cout)
+    if words < 0 or wfrag.dtype != torch.int32 or wfrag.numel() != words:
+        raise BmvError(f"conv2d_k3: ({cin} -> {cout}) not instantiated or wfrag is not from mlp_pack.pack_conv2d_k3")
+    fuse = wfrag1x1 is not None
+    co = cout1x1 if fuse else cout
+    if fuse and out_dtype != torch.float32:
+        raise BmvError("conv2d_k3: the fused 1x1 layer writes fp32")
+    out = torch.empty((N, co, H, W), device=x.device, dtype=out_dtype, memory_format=torch.channels_last)
+    p = _lib.Conv2dParams()
+    p.x = x.data_ptr()
+    p.x_n_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3)
+    p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, cin, cout
+    p.s2d, p.in_half, p.out_half, p.relu = int(s2d), int(x.dtype == torch.float16), int(out_dtype == torch.float16), int(relu)
+    p.wfrag = wfrag.data_ptr()
+    p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
+    p.out = out.data_ptr()
+    p.o_n_stride, p.o_y_stride, p.o_x_stride = out.stride(0), out.stride(2), out.stride(3)
+    if fuse:
+        if wfrag1x1.dtype != torch.int32 or wfrag1x1.numel() != 2 * 4 * 32 * 2:
+            raise BmvError("conv2d_k3: wfrag1x1 must come from mlp_pack.pack_conv1x1_after")
+        p.wfrag1x1 = wfrag1x1.data_ptr()
+        p.bias1x1 = _cf32(bias1x1, "bias1x1").data_ptr() if bias1x1 is not None else 0
+        p.C1x1_out = cout1x1
+    _lib.call("bmv_conv2d_k3", p, _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------ f4: output sinks

@@ -483,9 +483,37 @@ typedef struct bmv_fpn_fused_params {
   float* mid;                   /* (N,H,W,32) or NULL */
   float* out;                   /* (N,H,W,Cout), or NULL when only out16 is wanted */
   void* out16;                  /* optional fp16 version of out, (N,H,W,Cout) (for the cost-volume kernel's fp16 tap loads), or NULL */
+  int32_t lat_half;             /* 1: lateral_in points to fp16 storage (N,H,W,Cin) */
+  int32_t reserved0;
 } bmv_fpn_fused_params;
 BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv_stream_t stream);
 BMV_API int bmv_fpn_topdown_smooth_weight_words(int Cout);
+
+/* ------------------------------------------------------------------------------------------
+ * 3x3 / pad-1 convolution (+bias, +ReLU) of the 2-D feature pyramid's middle layers on tensor cores (fp16 operands,
+ * fp32 accumulation: TF32-class, same gating as bmv_conv3d_k3): conv1.x / conv2.x and, fused behind conv2.1, the 1x1 top
+ * layer (reference lib/networks/enerf/feature_net.py:10-21,29-31; BN folded by the caller).
+ *   x    channels-last input.  in_half = 1, s2d = 0: fp16 (N,H,W,Cin).  s2d = 1: fp32 or fp16 (N,2H,2W,Cin/4) read
+ *        through space-to-depth(2) — conv channel (py*2 + px) * Cin/4 + c is source pixel (2y+py, 2x+px), channel c: a
+ *        5x5 / stride-2 / pad-2 layer regrouped as a 3x3 one (weights zero-padded to 6x6, mlp_pack.pack_conv2d_k3).
+ *   out  channels-last (N,H,W,Cout), fp32 or fp16 (out_half).
+ *   wfrag: bmv_conv2d_k3_weight_words(Cin, Cout) words in B-fragment order [dy][k-step][n-tile][lane][2] with the output
+ *        channels permuted across the n-tiles (mlp_pack.pack_conv2d_k3); bias (Cout) by channel, or NULL.
+ *   wfrag1x1 / bias1x1 / C1x1_out: optional fused 1x1 convolution applied to relu(conv) (mlp_pack.pack_conv1x1_after);
+ *        out is then (N,H,W,C1x1_out) fp32 and the 3x3 result is never stored.
+ * Instantiated: (Cin 32 -> 16, s2d), (64 -> 32, s2d), (16 -> 16, fp16 dense), (32 -> 32, fp16 dense [+ 1x1 32 -> 32]).
+ */
+typedef struct bmv_conv2d_params {
+  const void* x; int64_t x_n_stride, x_y_stride, x_x_stride;   /* elements of x's dtype */
+  int32_t N, H, W, Cin, Cout;
+  int32_t s2d, in_half, out_half, relu;
+  int32_t C1x1_out;
+  const uint32_t* wfrag; const float* bias;
+  void* out; int64_t o_n_stride, o_y_stride, o_x_stride;
+  const uint32_t* wfrag1x1; const float* bias1x1;
+} bmv_conv2d_params;
+BMV_API int bmv_conv2d_k3(const bmv_conv2d_params* p, bmv_stream_t stream);
+BMV_API int bmv_conv2d_k3_weight_words(int Cin, int Cout);
 
 /* ------------------------------------------------------------------------------------------
  * Fused stem of the feature pyramid: ConvBnReLU(3,8,3) -> ConvBnReLU(8,8,3) at full resolution
@@ -504,6 +532,9 @@ typedef struct bmv_fpn_stem_params {
                                    bmv_raygen_fetch_params), or NULL */
   float* out_s2d;               /* optional second copy of the output in space-to-depth(2) layout (N,H/2,W/2,32), channel
                                    (y&1)*16 + (x&1)*8 + c: the input of the regrouped 5x5/stride-2 conv1.0; H, W even; or NULL */
+  int32_t out_half;             /* 1: out points to fp16 storage (N,H,W,8): its consumers (bmv_conv2d_k3, the lateral of
+                                   bmv_fpn_topdown_smooth) round it to fp16 anyway; out_s2d must be NULL */
+  int32_t reserved0;
 } bmv_fpn_stem_params;
 BMV_API int bmv_fpn_stem(const bmv_fpn_stem_params* p, bmv_stream_t stream);
 

@@ -211,3 +211,71 @@ def test_umma_conv_packing_reproduces_conv3d(cin, cout):
                             out[:, od, oy_min + r, xo] += acc[16 * r:16 * r + 16]
     assert np.abs(out[:cout] - ref).max() < 1e-4 * np.abs(ref).max()
     assert cout == 16 or np.abs(out[cout:]).max() == 0
+
+
+def _conv2d_k3_emulate(x, words, cin, cout):
+    """Restates csrc/conv2d_mma.cu: k-step j = dx * (Cin/16) + part reads channels part*16 .. +15 of pixel x+dx; column g
+    of n-tile nt is output channel (g//2) * 2NT + 2nt + g%2.  x (Cin,H,W) -> (Cout,H,W)."""
+    NT, KPD = cout // 8, cin // 16
+    B = unpack_b(words, (3, 3 * KPD, NT))                                # [dy][j][nt][k][n]
+    xp = F.pad(x, (1, 1, 1, 1))
+    H, W = x.shape[1:]
+    out = torch.zeros(cout, H, W)
+    for dy in range(3):
+        for j in range(3 * KPD):
+            dx, part = j // KPD, j % KPD
+            for k in range(16):
+                a = xp[part * 16 + k, dy:dy + H, dx:dx + W]
+                for nt in range(NT):
+                    for n in range(8):
+                        out[(n // 2) * 2 * NT + nt * 2 + n % 2] += B[dy, j, nt, k, n] * a
+    return out
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (32, 16), (64, 32)])
+def test_pack_conv2d_k3_reproduces_conv2d(cin, cout):
+    g = torch.Generator().manual_seed(cin + cout)
+    w = (torch.randn((cout, cin, 3, 3), generator=g) * 0.2).half().float()
+    x = torch.randn((cin, 6, 11), generator=g).half().float()
+    out = _conv2d_k3_emulate(x, mlp_pack.pack_conv2d_k3(w), cin, cout)
+    ref = F.conv2d(x[None], w, padding=1)[0]
+    assert torch.allclose(out, ref, atol=2e-4), (out - ref).abs().max()
+
+
+def test_conv2d_k3_space_to_depth_mode_is_the_5x5_stride2_layer():
+    """The kernel's s2d staging (conv channel (py*2+px)*Cs + c = source pixel (2y+py, 2x+px), channel c) + the regrouped
+    weights of inference_plan.S2DConv5x5 == the reference's 5x5 / stride-2 / pad-2 convolution."""
+    from boostmvsnerfs_b200.inference_plan import S2DConv5x5
+    g = torch.Generator().manual_seed(3)
+    conv = torch.nn.Conv2d(8, 16, 5, stride=2, padding=2)
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn(conv.weight.shape, generator=g) * 0.1).half().float())
+    src = torch.randn((8, 12, 20), generator=g).half().float()
+    s2d = S2DConv5x5(conv, relu=False)
+    Cs, H2, W2 = src.shape
+    z = torch.zeros(4 * Cs, H2 // 2, W2 // 2)
+    for py in range(2):
+        for px in range(2):
+            z[(py * 2 + px) * Cs:(py * 2 + px + 1) * Cs] = src[:, py::2, px::2]
+    out = _conv2d_k3_emulate(z, mlp_pack.pack_conv2d_k3(s2d.weight), 32, 16) + conv.bias.detach()[:, None, None]
+    ref = conv(src[None])[0].detach()
+    assert torch.allclose(out, ref, atol=2e-4), (out - ref).abs().max()
+
+
+def test_pack_conv1x1_after_matches_the_fragment_chaining():
+    """The fused top layer: A fragments = the 3x3 layer's C fragments (lane t holds channels 8t + 2nt + e of n-tile nt),
+    k-step kk takes n-tiles 2kk (K 0..7) and 2kk+1 (K 8..15)."""
+    g = torch.Generator().manual_seed(9)
+    w1 = (torch.randn((32, 32, 1, 1), generator=g) * 0.2).half().float()
+    c = torch.randn(32, generator=g).half().float()                      # one pixel's 32 channels
+    B = unpack_b(mlp_pack.pack_conv1x1_after(w1), (2, 4))                 # [kk][nt][k][n]
+    out = torch.zeros(32)
+    for kk in range(2):
+        for k in range(16):
+            t, e, r = (k % 8) // 2, k % 2, k // 8
+            a = c[t * 8 + (2 * kk + r) * 2 + e]                          # what the chained A fragment holds at K index k
+            for nt in range(4):
+                for n in range(8):
+                    out[(n // 2) * 8 + nt * 2 + n % 2] += B[kk, nt, k, n] * a
+    ref = w1[:, :, 0, 0] @ c
+    assert torch.allclose(out, ref, atol=2e-4), (out - ref).abs().max()

@@ -309,3 +309,140 @@ def test_conv3d_k3_umma_matches_cudnn(shape, exact_operands):
     assert (got.float() - ref).abs().max().item() <= tol, ((got.float() - ref).abs().max().item(), scale)
     old = ops.conv3d_k3(xh, pack_conv3d_k3(w), b, Cout, relu)
     assert (got.float() - old).abs().max().item() <= max(tol, 2e-5 * scale)
+
+
+# ------------------------------------------------------------------------------------------ FPN middle layers (conv2d_mma.cu)
+def _ref_conv(x, w, b, **kw):
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return torch.nn.functional.conv2d(x, w, b, **kw)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(16, 16, (40, 64)), (32, 32, (37, 45)), (16, 16, (5, 9))])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.float16])
+def test_conv2d_k3_dense_vs_torch(cin, cout, hw, out_dtype):
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3
+    H, W = hw
+    torch.manual_seed(cin + H)
+    x = torch.randn(3, cin, H, W, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") * 0.1).half().float()       # fp16-representable operands: 1e-5 class
+    b = torch.randn(cout, device="cuda")
+    for relu in (True, False):
+        ref = _ref_conv(x.float(), w, b, padding=1)
+        ref = torch.relu(ref) if relu else ref
+        got = ops.conv2d_k3(x, pack_conv2d_k3(w), b, cout, relu=relu, out_dtype=out_dtype)
+        assert got.shape == ref.shape and got.dtype == out_dtype and got.is_contiguous(memory_format=torch.channels_last)
+        tol = 2e-5 if out_dtype == torch.float32 else 1e-3
+        assert (got.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("cs,cout,hw", [(8, 16, (36, 72)), (16, 32, (20, 44)), (8, 16, (4, 8))])
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.float16])
+def test_conv2d_k3_space_to_depth_is_the_5x5_stride2_layer(cs, cout, hw, src_dtype):
+    """fp32 source read through space-to-depth in the staging loop + S2DConv5x5's regrouped weights == the reference
+    layer (5x5, stride 2, pad 2) on the fp16-rounded source."""
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.inference_plan import S2DConv5x5
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3
+    H2, W2 = hw
+    torch.manual_seed(cs + H2)
+    conv = torch.nn.Conv2d(cs, cout, 5, stride=2, padding=2).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.half().float())
+    src = torch.randn(2, cs, H2, W2, device="cuda").contiguous(memory_format=torch.channels_last)
+    ref = torch.relu(_ref_conv(src.half().float(), conv.weight, conv.bias, stride=2, padding=2))
+    s2d = S2DConv5x5(conv, relu=True)
+    got = ops.conv2d_k3(src.to(src_dtype), pack_conv2d_k3(s2d.weight), s2d.bias, cout, relu=True, s2d=True, out_dtype=torch.float32)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_conv2d_k3_fused_top_layer_vs_torch():
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv1x1_after, pack_conv2d_k3
+    torch.manual_seed(11)
+    x = torch.randn(2, 32, 35, 50, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(32, 32, 3, 3, device="cuda") * 0.1).half().float()
+    b = torch.randn(32, device="cuda")
+    w1 = (torch.randn(32, 32, 1, 1, device="cuda") * 0.2).half().float()
+    b1 = torch.randn(32, device="cuda")
+    mid = torch.relu(_ref_conv(x.float(), w, b, padding=1))
+    ref = _ref_conv(mid, w1, b1)
+    got = ops.conv2d_k3(x, pack_conv2d_k3(w), b, 32, relu=True, wfrag1x1=pack_conv1x1_after(w1), bias1x1=b1)
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    # the intermediate is rounded to fp16 between the two layers (TF32-class)
+    assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    ref16 = _ref_conv(mid.half().float(), w1, b1)
+    assert (got - ref16).abs().max().item() <= 3e-4 * ref.abs().max().item()
+
+
+def test_fpn_plan_tensor_core_mid_layers_match_cudnn_route():
+    """FeatureNet plan with conv1.x / conv2.x / top layer on bmv_conv2d_k3 against the same plan with those layers on cuDNN
+    (both TF32-class): all three pyramid levels."""
+    from boostmvsnerfs_b200.inference_plan import PlanCache
+    from boostmvsnerfs_b200.modules import FeatureNet
+    torch.manual_seed(2)
+    net = FeatureNet().cuda().eval()
+    x = torch.randn(3, 3, 64, 96, device="cuda")
+    plan = PlanCache().get("feature_net", net, torch.channels_last)
+    with torch.no_grad():
+        plan.tensor_core_mid = True
+        got = [t.clone() for t in plan(x)]
+        plan.tensor_core_mid = False
+        ref = plan(x)
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            strict = plan(x)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+    for a, b, s in zip(got, ref, strict):
+        assert a.shape == b.shape
+        assert (a - s).abs().max().item() <= 1e-2 * s.abs().max().item()
+        assert (a - b).abs().max().item() <= 1e-2 * s.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(8, 8, (64, 96)), (16, 16, (34, 50))])
+def test_fpn_topdown_smooth_fp16_lateral_input(cin, cout, hw):
+    """fp16 lateral input (what the stem / bmv_conv2d_k3 emit) == the fp32-input kernel on the same values: the fp16
+    operand is exact, only the summation order inside the tensor core differs."""
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3_c32
+    H, W = hw
+    torch.manual_seed(cin)
+    prev = torch.randn(2, 32, H // 2, W // 2, device="cuda").contiguous(memory_format=torch.channels_last)
+    lat16 = torch.randn(2, cin, H, W, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    lat = torch.nn.Conv2d(cin, 32, 1).cuda()
+    smooth = torch.nn.Conv2d(32, cout, 3, padding=1).cuda()
+    wf = pack_conv2d_k3_c32(smooth.weight)
+    mid32, out32 = ops.fpn_topdown_smooth(prev, lat16.float(), lat.weight, lat.bias, wf, smooth.bias, cout, True)
+    mid16, out16 = ops.fpn_topdown_smooth(prev, lat16, lat.weight, lat.bias, wf, smooth.bias, cout, True)
+    assert (mid16 - mid32).abs().max().item() <= 2e-6 * mid32.abs().max().item()
+    assert (out16 - out32).abs().max().item() <= 1e-3 * out32.abs().max().item()
+    with torch.no_grad():
+        prev_flag = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            mid_ref = torch.nn.functional.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=True) + lat(lat16.float())
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev_flag
+    assert torch.allclose(mid16, mid_ref, rtol=1e-5, atol=1e-5 * mid_ref.abs().max().item())
+
+
+def test_fpn_stem_fp16_output_is_the_rounded_fp32_output():
+    from boostmvsnerfs_b200 import ops
+    from boostmvsnerfs_b200.mlp_pack import pack_conv2d_k3_c8
+    torch.manual_seed(4)
+    x = torch.randn(2, 3, 40, 72, device="cuda")
+    c0 = torch.nn.Conv2d(3, 8, 3, padding=1).cuda()
+    c1 = torch.nn.Conv2d(8, 8, 3, padding=1).cuda()
+    wf = pack_conv2d_k3_c8(c1.weight)
+    o32, rgb_a = ops.fpn_stem(x, c0.weight, c0.bias, wf, c1.bias, want_rgb4=True)
+    o16, rgb_b = ops.fpn_stem(x, c0.weight, c0.bias, wf, c1.bias, want_rgb4=True, out_dtype=torch.float16)
+    assert o16.dtype == torch.float16 and o16.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(o16, o32.half()) and torch.equal(rgb_a, rgb_b)
