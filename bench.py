@@ -224,14 +224,16 @@ def conv_kernel_bytes(wl, rc, volume_bytes=4, heads_entry="bmv_conv3d_k3", fpn_m
     heads run on (bmv_conv3d_k3_umma when the inference plan routes them to the tcgen05 kernel)."""
     H, W, K, N = wl["H"], wl["W"], wl["K"], wl["n_views"]
     px = N * H * W
-    # stem: image in, c0 + the (N,H,W,4) colour image out (+ the space-to-depth copy of c0 when conv1.0 runs on cuDNN)
-    out = {"bmv_fpn_stem": [("fpn_stem", px * 4 * (3 + 8 + 4 + (0 if fpn_mid else 8)))],
-           "bmv_fpn_topdown_smooth": [("fpn_topdown_smooth_half", px // 4 * 4 * (32 // 4 + 16 + 32 + 16)),
-                                      ("fpn_topdown_smooth_full", px * 4 * (32 // 4 + 8 + 8))],
+    # stem: image in, c0 + the (N,H,W,4) colour image out.  cuDNN route of conv1.x / conv2.x: c0 fp32 + its space-to-depth
+    # copy; tensor-core route (csrc/conv2d_mma.cu): c0 and every tensor up to the top layer in fp16, laterals read fp16
+    lat = 2 if fpn_mid else 4                     # bytes per lateral-input element of the two top-down steps
+    out = {"bmv_fpn_stem": [("fpn_stem", px * (3 * 4 + 4 * 4 + (8 * 2 if fpn_mid else 16 * 4)))],
+           "bmv_fpn_topdown_smooth": [("fpn_topdown_smooth_half", px // 4 * (32 // 4 * 4 + 16 * lat + 32 * 4 + 16 * 4)),
+                                      ("fpn_topdown_smooth_full", px * (32 // 4 * 4 + 8 * lat + 8 * 4))],
            "bmv_conv3d_k3": [], "bmv_convT3d_k3s2": []}
-    if fpn_mid:      # csrc/conv2d_mma.cu: conv1.0 (reads c0 through space-to-depth), conv1.1, conv2.0, conv2.1 + top layer
-        out["bmv_conv2d_k3"] = [("fpn_conv1_0", px * 8 * 4 + px // 4 * 16 * 2), ("fpn_conv1_1", px // 4 * 16 * (2 + 4)),
-                                ("fpn_conv2_0", px // 4 * 16 * 4 + px // 16 * 32 * 2), ("fpn_conv2_1_top", px // 16 * 32 * (2 + 4))]
+    if fpn_mid:      # conv1.0 (reads c0 through space-to-depth), conv1.1, conv2.0, conv2.1 + top layer (fp32 out)
+        out["bmv_conv2d_k3"] = [("fpn_conv1_0", px * 8 * 2 + px // 4 * 16 * 2), ("fpn_conv1_1", px // 4 * 16 * (2 + 2)),
+                                ("fpn_conv2_0", px // 4 * 16 * 2 + px // 16 * 32 * 2), ("fpn_conv2_1_top", px // 16 * 32 * (2 + 4))]
     out.setdefault(heads_entry, [])
     for i in range(rc.num):
         C = int(32 * 2 ** (-i))

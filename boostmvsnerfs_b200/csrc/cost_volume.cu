@@ -510,8 +510,12 @@ __global__ void __launch_bounds__(256) cost_volume_var_cl6_kernel(bmv_cost_volum
   OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   constexpr float invS = 1.f / S;
   const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
+  // the hypothesis of plane d + 1 is loaded while plane d is processed: hypothesis -> taps -> texel loads would otherwise
+  // be two memory latencies in a row per plane (ncu: 4.5 long-scoreboard stalls per issue)
+  float dep_next = __ldg(t_planes + (int64_t)d_begin * p.planes_d_stride);
   for (int d = d_begin; d < d_end; ++d) {
-    const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
+    const float idep = __frcp_rn(dep_next);
+    dep_next = __ldg(t_planes + (int64_t)min(d + 1, d_end - 1) * p.planes_d_stride);
     FastTap t[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) t[q] = fast_taps(ax[q], ay[q], az[q], tP[q], idep, sx, sy, p.Hs, p.Ws, ys, xs);
@@ -695,8 +699,10 @@ __global__ void __launch_bounds__(256, 2) cost_volume_var_multi6_kernel(bmv_cost
   OutT* outp = reinterpret_cast<OutT*>(p.out) + (int64_t)y * p.out_y_stride + (int64_t)min(x, p.w - 1) * p.out_x_stride + c0;
   const float invS = 1.f / (float)mp.views_per_chain;
   const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
+  float dep_next = __ldg(t_planes + (int64_t)d_begin * p.planes_d_stride);
   for (int d = d_begin; d < d_end; ++d) {
-    const float idep = __frcp_rn(__ldg(t_planes + (int64_t)d * p.planes_d_stride));
+    const float idep = __frcp_rn(dep_next);
+    dep_next = __ldg(t_planes + (int64_t)min(d + 1, d_end - 1) * p.planes_d_stride);
     FastTap t[NP];
     t[0] = fast_taps(ax[0], ay[0], az[0], tP[0], idep, sx, sy, p.Hs, p.Ws, ys, xs);
     if (NP > 1) {

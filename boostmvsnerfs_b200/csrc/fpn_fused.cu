@@ -9,8 +9,8 @@
 // writing the 8-channel output.  At half resolution `mid` is also the next step's `prev`, so it is
 // additionally written out (exact fp32) when p.mid is given.
 //
-// `mid` is computed to fp32 accuracy (upsample: the arithmetic of fpn.cu; 1x1 lateral: tensor cores with both operands
-// split into fp16 hi + lo, ~1e-6 relative); the 3x3 convolution runs on tensor cores with plain fp16 operands
+// `mid` is computed to fp32 accuracy (upsample: fp32 with product weights, the value of fpn.cu up to the last ulps; 1x1
+// lateral: tensor cores with both operands split into fp16 hi + lo, ~1e-6 relative); the 3x3 convolution runs on tensor cores with plain fp16 operands
 // (mma.sync.m16n8k16, fp32 accumulation: TF32-class — the host routes here only when
 // torch.backends.cudnn.allow_tf32 is set, see inference_plan.py).
 #include <stdlib.h>
@@ -50,10 +50,28 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
     for (int i = threadIdx.x; i < 32 * CIN; i += kFfThreads) sW[(i % CIN) * 32 + i / CIN] = __ldg(p.lat_weight + i);
     if (threadIdx.x < 32) sW[32 * CIN + threadIdx.x] = p.lat_bias ? __ldg(p.lat_bias + threadIdx.x) : 0.f;
   }
-  __syncthreads();
   const int tiles_x = (p.W + kFfTX - 1) / kFfTX;
   const int x0 = (blockIdx.x % tiles_x) * kFfTX, y0 = (blockIdx.x / tiles_x) * kFfTY, n = blockIdx.y;
   const int Hp = p.H / 2, Wp = p.W / 2;
+  // Per-CTA coordinate tables of the 10 halo rows / 66 halo columns (clamped into the image): element offsets of the two
+  // `prev` rows / columns a pixel interpolates between, the two weights, and the offset of its lateral-input row / column.
+  // ncu of the version that derived all this per pixel: 186 of the ~380 instructions of a 16-pixel segment were index
+  // arithmetic (64-bit address chains, clamps, int <-> float conversions of the align_corners coordinates).
+  __shared__ int4 s_row[kFfHY], s_col[kFfHX];
+  __shared__ int s_rowlat[kFfHY], s_collat[kFfHX];
+  if (threadIdx.x < kFfHY) {
+    const int cy = min(max(y0 + (int)threadIdx.x - 1, 0), p.H - 1);
+    const UpCoord u = up_coord_scaled(cy, Hp, up_scale(Hp, p.H));
+    s_row[threadIdx.x] = make_int4(u.i0 * Wp * 32, u.i1 * Wp * 32, __float_as_int(u.l0), __float_as_int(u.l1));
+    s_rowlat[threadIdx.x] = cy * p.W * CIN;
+  } else if (threadIdx.x >= 32 && threadIdx.x < 32 + kFfHX) {
+    const int hx = threadIdx.x - 32;
+    const int cx = min(max(x0 + hx - 1, 0), p.W - 1);
+    const UpCoord u = up_coord_scaled(cx, Wp, up_scale(Wp, p.W));
+    s_col[hx] = make_int4(u.i0 * 32, u.i1 * 32, __float_as_int(u.l0), __float_as_int(u.l1));
+    s_collat[hx] = cx * CIN;
+  }
+  __syncthreads();
   // ---- phase 1: mid tile (+1 halo; zero outside the image = the convolution's padding) -> fp16 in shared memory.
   // The 1x1 lateral convolution runs on the tensor cores too (round 2; the CUDA-core version spent ~1.2 k thread
   // instructions per pixel here, 8 lanes x 150, and made the kernel issue-bound at 62 %): a warp takes 16 consecutive
@@ -84,32 +102,53 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
         wlo[nt][kk] = pack_half2_sat((w0 - __half2float(h0)) * kLoUp, (w1 - __half2float(h1)) * kLoUp);
       }
     }
-    const float sy = up_scale(Hp, p.H), sx = up_scale(Wp, p.W);
     constexpr int NPIX = kFfHY * kFfHX, NSEG = (NPIX + 15) / 16;
+    const float* prevb = prev + t * 8;
     for (int seg = warp; seg < NSEG; seg += kFfThreads / 32) {
-      int py[2], px[2], hyv[2], hxv[2];
+      // Every global load of the segment is issued up front with CLAMPED (always valid) addresses — the lateral inputs of
+      // both pixels and their 2 x 4 `prev` taps; out-of-image pixels are zeroed when the tile entry is built.
+      int hyv[2], hxv[2], poff[2];
       bool ok[2];
+      float w00[2], w01[2], w10[2], w11[2];
       uint32_t ahi[2][KK], alo[2][KK];
+      float2 lv[2][KK];
+      uint32_t lh[2][KK];
+      float4 tap[2][4][2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int pi = seg * 16 + g + 8 * e;
+        const int pi = min(seg * 16 + g + 8 * e, NPIX - 1);
         hyv[e] = pi / kFfHX; hxv[e] = pi - hyv[e] * kFfHX;
-        py[e] = y0 + hyv[e] - 1; px[e] = x0 + hxv[e] - 1;
-        ok[e] = pi < NPIX && py[e] >= 0 && py[e] < p.H && px[e] >= 0 && px[e] < p.W;
+        const int py = y0 + hyv[e] - 1, px = x0 + hxv[e] - 1;
+        ok[e] = (unsigned)py < (unsigned)p.H && (unsigned)px < (unsigned)p.W;
+        poff[e] = (py * p.W + px) * 32 + t * 8;                         // `mid` element (used for in-image pixels only)
+        const int4 r = s_row[hyv[e]], c = s_col[hxv[e]];
+        const int loff = s_rowlat[hyv[e]] + s_collat[hxv[e]] + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          if (LAT16) lh[e][kk] = __ldg(reinterpret_cast<const uint32_t*>(lat16 + loff + 8 * kk));
+          else lv[e][kk] = __ldg(reinterpret_cast<const float2*>(lat + loff + 8 * kk));
+        }
+        ldg8_f32(prevb + (r.x + c.x), tap[e][0][0], tap[e][0][1]);
+        ldg8_f32(prevb + (r.x + c.y), tap[e][1][0], tap[e][1][1]);
+        ldg8_f32(prevb + (r.y + c.x), tap[e][2][0], tap[e][2][1]);
+        ldg8_f32(prevb + (r.y + c.y), tap[e][3][0], tap[e][3][1]);
+        const float yl0 = __int_as_float(r.z), yl1 = __int_as_float(r.w), xl0 = __int_as_float(c.z), xl1 = __int_as_float(c.w);
+        w00[e] = yl0 * xl0; w01[e] = yl0 * xl1; w10[e] = yl1 * xl0; w11[e] = yl1 * xl1;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int kk = 0; kk < KK; ++kk) {
           if (LAT16) {          // fp16 lateral input (what the stem / bmv_conv2d_k3 emit): exact operands, no lo part
-            ahi[e][kk] = ok[e] ? __ldg(reinterpret_cast<const uint32_t*>(lat16 + ((int64_t)py[e] * p.W + px[e]) * CIN + 2 * t + 8 * kk)) : 0u;
+            ahi[e][kk] = lh[e][kk];
             alo[e][kk] = 0u;
           } else {
-            float2 vv = make_float2(0.f, 0.f);
-            if (ok[e]) vv = __ldg(reinterpret_cast<const float2*>(lat + ((int64_t)py[e] * p.W + px[e]) * CIN + 2 * t + 8 * kk));
+            const float2 vv = lv[e][kk];
             const __half h0 = half_sat(vv.x), h1 = half_sat(vv.y);
             ahi[e][kk] = pack_half2_sat(vv.x, vv.y);
             alo[e][kk] = pack_half2_sat((vv.x - __half2float(h0)) * kLoUp, (vv.y - __half2float(h1)) * kLoUp);
           }
         }
-      }
       float chi[4][4], clo[4][4];
       const float4 lb0 = *reinterpret_cast<const float4*>(sW + 32 * CIN + t * 8), lb1 = *reinterpret_cast<const float4*>(sW + 32 * CIN + t * 8 + 4);
       const float lbias[4][2] = {{lb0.x, lb0.y}, {lb0.z, lb0.w}, {lb1.x, lb1.y}, {lb1.z, lb1.w}};
@@ -134,26 +173,18 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fpn_topdown_smooth_kernel(bm
         if (seg * 16 + g + 8 * e >= NPIX) continue;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         if (ok[e]) {
-          const UpCoord uy = up_coord_scaled(py[e], Hp, sy), ux = up_coord_scaled(px[e], Wp, sx);
-          const float* pb = prev + t * 8;
-          float4 a0, a1, b0, b1, c0, c1, d0, d1;
-          ldg8_f32(pb + ((int64_t)uy.i0 * Wp + ux.i0) * 32, a0, a1);
-          ldg8_f32(pb + ((int64_t)uy.i0 * Wp + ux.i1) * 32, b0, b1);
-          ldg8_f32(pb + ((int64_t)uy.i1 * Wp + ux.i0) * 32, c0, c1);
-          ldg8_f32(pb + ((int64_t)uy.i1 * Wp + ux.i1) * 32, d0, d1);
+          // bilinear blend with the four PRODUCT weights (5 FMAs per channel incl. the lateral term; the nested form of
+          // fpn.cu takes 8): same value up to the last ulps
           const int o = 2 * e;
-          r0.x = (uy.l0 * (ux.l0 * a0.x + ux.l1 * b0.x) + uy.l1 * (ux.l0 * c0.x + ux.l1 * d0.x)) + fmaf(clo[0][o], kLoDown, chi[0][o]);
-          r0.y = (uy.l0 * (ux.l0 * a0.y + ux.l1 * b0.y) + uy.l1 * (ux.l0 * c0.y + ux.l1 * d0.y)) + fmaf(clo[0][o + 1], kLoDown, chi[0][o + 1]);
-          r0.z = (uy.l0 * (ux.l0 * a0.z + ux.l1 * b0.z) + uy.l1 * (ux.l0 * c0.z + ux.l1 * d0.z)) + fmaf(clo[1][o], kLoDown, chi[1][o]);
-          r0.w = (uy.l0 * (ux.l0 * a0.w + ux.l1 * b0.w) + uy.l1 * (ux.l0 * c0.w + ux.l1 * d0.w)) + fmaf(clo[1][o + 1], kLoDown, chi[1][o + 1]);
-          r1.x = (uy.l0 * (ux.l0 * a1.x + ux.l1 * b1.x) + uy.l1 * (ux.l0 * c1.x + ux.l1 * d1.x)) + fmaf(clo[2][o], kLoDown, chi[2][o]);
-          r1.y = (uy.l0 * (ux.l0 * a1.y + ux.l1 * b1.y) + uy.l1 * (ux.l0 * c1.y + ux.l1 * d1.y)) + fmaf(clo[2][o + 1], kLoDown, chi[2][o + 1]);
-          r1.z = (uy.l0 * (ux.l0 * a1.z + ux.l1 * b1.z) + uy.l1 * (ux.l0 * c1.z + ux.l1 * d1.z)) + fmaf(clo[3][o], kLoDown, chi[3][o]);
-          r1.w = (uy.l0 * (ux.l0 * a1.w + ux.l1 * b1.w) + uy.l1 * (ux.l0 * c1.w + ux.l1 * d1.w)) + fmaf(clo[3][o + 1], kLoDown, chi[3][o + 1]);
+#define BMV_FF_BLEND(dst, f, q, nt, j)                                                                                         \
+          dst = fmaf(w00[e], tap[e][0][q].f, fmaf(w01[e], tap[e][1][q].f, fmaf(w10[e], tap[e][2][q].f,                       \
+                     fmaf(w11[e], tap[e][3][q].f, fmaf(clo[nt][o + j], kLoDown, chi[nt][o + j])))))
+          BMV_FF_BLEND(r0.x, x, 0, 0, 0); BMV_FF_BLEND(r0.y, y, 0, 0, 1); BMV_FF_BLEND(r0.z, z, 0, 1, 0); BMV_FF_BLEND(r0.w, w, 0, 1, 1);
+          BMV_FF_BLEND(r1.x, x, 1, 2, 0); BMV_FF_BLEND(r1.y, y, 1, 2, 1); BMV_FF_BLEND(r1.z, z, 1, 3, 0); BMV_FF_BLEND(r1.w, w, 1, 3, 1);
+#undef BMV_FF_BLEND
           if (mid && hyv[e] >= 1 && hyv[e] <= kFfTY && hxv[e] >= 1 && hxv[e] <= kFfTX) {
-            float* m = mid + ((int64_t)py[e] * p.W + px[e]) * 32 + t * 8;
-            *reinterpret_cast<float4*>(m) = r0;
-            *reinterpret_cast<float4*>(m + 4) = r1;
+            *reinterpret_cast<float4*>(mid + poff[e]) = r0;
+            *reinterpret_cast<float4*>(mid + poff[e] + 4) = r1;
           }
         }
         uint4 pk;
@@ -267,7 +298,7 @@ template <int CIN, int NT, bool BREG>
 static int launch_ff(const bmv_fpn_fused_params& p, cudaStream_t st) {
   // resident CTAs per SM the kernel is compiled for: 3 (80 registers) or 2 (128); BMV_FF_MINB overrides (measurements)
   static const int minb_env = getenv("BMV_FF_MINB") ? atoi(getenv("BMV_FF_MINB")) : 0;
-  const int minb = minb_env ? minb_env : (NT == 1 ? 3 : 2);
+  const int minb = minb_env ? minb_env : 2;
   if constexpr (NT == 1) {
     if (minb == 3) return p.out16 ? launch_ff_t<CIN, NT, BREG, true, 3>(p, st) : launch_ff_t<CIN, NT, BREG, false, 3>(p, st);
   }
@@ -284,6 +315,7 @@ extern "C" BMV_API int bmv_fpn_topdown_smooth(const bmv_fpn_fused_params* p, bmv
   BMV_REQUIRE(((uintptr_t)p->out16 & 3) == 0, BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown_smooth: out16 must be 4-byte aligned");
   BMV_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 2 && p->W >= 2 && p->H % 2 == 0 && p->W % 2 == 0, BMV_ERR_INVALID_ARGUMENT,
               "bmv_fpn_topdown_smooth: H, W must be even and >= 2");
+  BMV_REQUIRE((int64_t)p->H * p->W <= (1ll << 25), BMV_ERR_UNSUPPORTED_SHAPE, "bmv_fpn_topdown_smooth: image too large for 32-bit offsets");
   BMV_REQUIRE(((uintptr_t)p->prev & 31) == 0 && ((uintptr_t)p->lateral_in & 15) == 0 && ((uintptr_t)p->out & 7) == 0 &&
                   ((uintptr_t)p->wfrag & 15) == 0 && ((uintptr_t)p->mid & 15) == 0,
               BMV_ERR_INVALID_ARGUMENT, "bmv_fpn_topdown_smooth: tensors must be 16-byte aligned (prev: 32-byte)");

@@ -6,8 +6,11 @@
 // lives in shared memory and the step is bounded by the output write.
 //
 // Stage A: image tile (+2 halo) -> shared memory (fp32).
-// Stage B: first convolution on CUDA cores in fp32 (K = 27 is too ragged for an MMA tile), ReLU, stored
-//          as fp16 with a 1-pixel halo (zero outside the image = the second convolution's padding).
+// Stage B: first convolution on tensor cores as well (round 2; on CUDA cores it was ~300 instructions per pixel — 27
+//          taps x (one pixel load, two weight-vector loads, 8 FMAs) — and the kernel sat at 81 % of the L1 / shared-memory
+//          pipe): M = 16 consecutive pixels, K = 32 = the 27 (tap, colour) products + zero padding, N = 8, fp32 bias
+//          in the accumulators; every lane gathers its A-fragment entries straight from the fp32 image tile (8 fixed
+//          offsets), ReLU, stored as fp16 with a 1-pixel halo (zero outside the image = the second convolution's padding).
 // Stage C: second convolution on tensor cores (mma.sync.m16n8k16, 8 input channels: two horizontal taps
 //          per MMA as in conv3d_mma.cu), bias + ReLU, fp32 (or fp16: out_half) channels-last output.
 // fp16 operands in stage C make the result TF32-class: the host uses this kernel only when
@@ -24,15 +27,10 @@ constexpr int kStMY = kStTY + 2, kStMX = kStTX + 2;                      // inte
 constexpr int kStMRowB = (kStMX + 1) * 16;                               // +1 pixel: the unpaired tap reads x+3
 
 __global__ void __launch_bounds__(kStThreads, 3) fpn_stem_kernel(bmv_fpn_stem_params p) {
-  __shared__ __align__(16) float s_img[kStIY * kStIX * 3];
+  __shared__ __align__(16) float s_img[kStIY * kStIX * 3 + 2];            // + {1.0, 0.0}: constant slots for the padding columns of stage B
   __shared__ __align__(16) unsigned char s_mid[kStMY * kStMRowB];
-  __shared__ __align__(16) float s_w0[27 * 8 + 8];                       // [tap*3+c][8 outputs], bias
   __shared__ __align__(16) uint2 s_w1[3 * 2 * 32];
-  for (int i = threadIdx.x; i < 216; i += kStThreads) {
-    const int o = i / 27, r = i - o * 27, c = r / 9, tap = r - c * 9;    // weight (8,3,3,3) row-major: o, c, ky, kx
-    s_w0[(tap * 3 + c) * 8 + o] = __ldg(p.w0 + i);
-  }
-  if (threadIdx.x < 8) s_w0[216 + threadIdx.x] = p.b0 ? __ldg(p.b0 + threadIdx.x) : 0.f;
+  if (threadIdx.x == 0) { s_img[kStIY * kStIX * 3] = 1.f; s_img[kStIY * kStIX * 3 + 1] = 0.f; }
   if (threadIdx.x < 3 * 2 * 32) s_w1[threadIdx.x] = __ldg(reinterpret_cast<const uint2*>(p.wfrag1) + threadIdx.x);
   const int tiles_x = (p.W + kStTX - 1) / kStTX;
   const int x0 = (blockIdx.x % tiles_x) * kStTX, y0 = (blockIdx.x / tiles_x) * kStTY, n = blockIdx.y;
@@ -54,33 +52,64 @@ __global__ void __launch_bounds__(kStThreads, 3) fpn_stem_kernel(bmv_fpn_stem_pa
     }
   }
   __syncthreads();
-  // ---- stage B: one thread per intermediate pixel, all 8 channels
-  for (int i = threadIdx.x; i < kStMY * (kStMX + 1); i += kStThreads) {
-    const int my = i / (kStMX + 1), mx = i - my * (kStMX + 1);
-    const int y = y0 + my - 1, x = x0 + mx - 1;
-    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-    if (mx < kStMX && y >= 0 && y < p.H && x >= 0 && x < p.W) {
-      lo = *reinterpret_cast<const float4*>(s_w0 + 216);
-      hi = *reinterpret_cast<const float4*>(s_w0 + 220);
-#pragma unroll 1
-      for (int ky = 0; ky < 3; ++ky)
+  // ---- stage B: 3 -> 8 convolution on tensor cores; a warp takes 16 consecutive intermediate pixels (row-major over the
+  // kStMY x kStMX tile).  K index k < 27 is (tap = k / 3, colour = k % 3), k >= 27 zero.
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // B fragments (weights (8,3,3,3) row-major: o, c, ky, kx) and the lane's 8 A-fragment sources: element offset in
+    // s_img relative to the pixel's window origin (mul = 1), or the absolute slot of the constant 1 / 0 (mul = 0)
+    uint32_t bw[2][2];
+    int koff[2][2][2], kmul[2][2][2];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float* px = s_img + ((my + ky) * kStIX + (mx + kx)) * 3;
+    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float v = px[c];
-            const float4 wl = *reinterpret_cast<const float4*>(s_w0 + ((ky * 3 + kx) * 3 + c) * 8);
-            const float4 wh = *reinterpret_cast<const float4*>(s_w0 + ((ky * 3 + kx) * 3 + c) * 8 + 4);
-            lo.x = fmaf(wl.x, v, lo.x); lo.y = fmaf(wl.y, v, lo.y); lo.z = fmaf(wl.z, v, lo.z); lo.w = fmaf(wl.w, v, lo.w);
-            hi.x = fmaf(wh.x, v, hi.x); hi.y = fmaf(wh.y, v, hi.y); hi.z = fmaf(wh.z, v, hi.z); hi.w = fmaf(wh.w, v, hi.w);
-          }
+      for (int r = 0; r < 2; ++r) {
+        float wv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = ks * 16 + r * 8 + 2 * t + e;
+          const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+          wv[e] = k < 27 ? __ldg(p.w0 + g * 27 + c * 9 + tap) : 0.f;
+          koff[ks][r][e] = k < 27 ? (ky * kStIX + kx) * 3 + c : kStIY * kStIX * 3 + 1;
+          kmul[ks][r][e] = k < 27 ? 1 : 0;
         }
-      lo.x = fmaxf(lo.x, 0.f); lo.y = fmaxf(lo.y, 0.f); lo.z = fmaxf(lo.z, 0.f); lo.w = fmaxf(lo.w, 0.f);
-      hi.x = fmaxf(hi.x, 0.f); hi.y = fmaxf(hi.y, 0.f); hi.z = fmaxf(hi.z, 0.f); hi.w = fmaxf(hi.w, 0.f);
+        bw[ks][r] = pack_half2_sat(wv[0], wv[1]);
+      }
+    const float bias_a = p.b0 ? __ldg(p.b0 + 2 * t) : 0.f, bias_b = p.b0 ? __ldg(p.b0 + 2 * t + 1) : 0.f;
+    constexpr int NPIX = kStMY * kStMX, NSEG = (NPIX + 15) / 16;
+    for (int seg = warp; seg < NSEG; seg += kStThreads / 32) {
+      int base3[2], myv[2], mxv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pi = min(seg * 16 + g + 8 * h, NPIX - 1);
+        myv[h] = pi / kStMX; mxv[h] = pi - myv[h] * kStMX;
+        base3[h] = (myv[h] * kStIX + mxv[h]) * 3;
+      }
+      float acc[4] = {bias_a, bias_b, bias_a, bias_b};                  // fp32 bias, as cuDNN adds it
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float v0 = s_img[base3[h] * kmul[ks][r][0] + koff[ks][r][0]], v1 = s_img[base3[h] * kmul[ks][r][1] + koff[ks][r][1]];
+            a[r * 2 + h] = pack_half2_sat(v0, v1);
+          }
+        hmma16816(acc, a, bw[ks][0], bw[ks][1]);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (seg * 16 + g + 8 * h >= NPIX) continue;
+        const int y = y0 + myv[h] - 1, x = x0 + mxv[h] - 1;
+        const bool ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
+        const uint32_t pk = ok ? pack_half2_sat(fmaxf(acc[2 * h], 0.f), fmaxf(acc[2 * h + 1], 0.f)) : 0u;
+        *reinterpret_cast<uint32_t*>(s_mid + myv[h] * kStMRowB + mxv[h] * 16 + t * 4) = pk;
+      }
     }
-    const uint2 a = pack_half4(lo), b = pack_half4(hi);
-    *reinterpret_cast<uint4*>(s_mid + my * kStMRowB + mx * 16) = make_uint4(a.x, a.y, b.x, b.y);
+    // the extra column the unpaired tap of stage C reads (x + 3): zeros
+    if (threadIdx.x < kStMY) *reinterpret_cast<uint4*>(s_mid + threadIdx.x * kStMRowB + kStMX * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
   // ---- stage C: 8 -> 8 convolution on tensor cores; a warp owns kStWY rows x 16 pixels
