@@ -24,31 +24,35 @@
 //   * Optional fused 1x1 convolution (the FPN top layer on conv2.1's output): the ReLU'd C fragments are re-packed as A
 //     fragments (registers only) and multiplied by the 32 x 32 matrix; the intermediate never reaches memory.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "bmv_internal.cuh"
 #include "conv_mma.cuh"
 
 namespace bmv {
 
-constexpr int kC2Threads = 256;
-constexpr int kC2TY = 16, kC2TX = 32, kC2WY = 4;
-constexpr int kC2HY = kC2TY + 2, kC2HX = kC2TX + 2;
+constexpr int kC2TX = 32, kC2WY = 4;
+constexpr int kC2HX = kC2TX + 2;
 
-template <int CIN> struct C2Cfg {
+// TY: output rows per CTA (16: 8 warps, 8: 4 warps — the quarter-resolution layers launch too few 16-row tiles to balance
+// 148 SMs: 432 CTAs on 296 slots)
+template <int CIN, int TY> struct C2Cfg {
+  static constexpr int HY = TY + 2, THREADS = (TY / kC2WY) * 2 * 32;
   static constexpr int VS = 2 * CIN;                                     // bytes per staged pixel
   static constexpr int CH8 = CIN / 8;                                    // 16-byte chunks per pixel
   static constexpr int KPD = CIN / 16;                                   // k-steps per dx
   static constexpr int KS = 3 * KPD;
   static constexpr int ROWB = kC2HX * VS;
-  static constexpr int TILE_BYTES = kC2HY * ROWB;
+  static constexpr int TILE_BYTES = HY * ROWB;
   // chunk c of pixel v lives at chunk c ^ swz(v): the 8 rows of an ldmatrix 8x8 block hit 8 distinct bank groups
   __device__ static __forceinline__ int swz(int v) { return CIN == 16 ? ((v >> 2) & 1) : (CIN == 32 ? ((v >> 1) & 3) : (v & 7)); }
 };
 
 // MODE 1: fp16 dense input; MODE 2 / 3: fp32 / fp16 input read through space-to-depth(2)
-template <int CIN, int NT, int MODE, bool FUSE>
-__global__ void __launch_bounds__(kC2Threads, 2) conv2d_k3_mma_kernel(bmv_conv2d_params p) {
-  using Cfg = C2Cfg<CIN>;
+template <int CIN, int NT, int MODE, bool FUSE, int TY>
+__global__ void __launch_bounds__(C2Cfg<CIN, TY>::THREADS, TY == 16 ? 2 : 4) conv2d_k3_mma_kernel(bmv_conv2d_params p) {
+  using Cfg = C2Cfg<CIN, TY>;
+  constexpr int kC2Threads = Cfg::THREADS, kC2HY = Cfg::HY, kC2TY = TY;
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* tile = smem;
   // weight fragments straight from global memory (<= 36 KB, L1-resident after the first tile of an SM): every k-step
@@ -233,15 +237,16 @@ __global__ void __launch_bounds__(kC2Threads, 2) conv2d_k3_mma_kernel(bmv_conv2d
   }
 }
 
-template <int CIN, int NT, int MODE, bool FUSE>
-static int launch_c2(const bmv_conv2d_params& p, cudaStream_t st) {
-  using Cfg = C2Cfg<CIN>;
+template <int CIN, int NT, int MODE, bool FUSE, int TY>
+static int launch_c2t(const bmv_conv2d_params& p, cudaStream_t st) {
+  using Cfg = C2Cfg<CIN, TY>;
+  constexpr int kC2Threads = Cfg::THREADS, kC2TY = TY;
   const size_t smem = (size_t)Cfg::TILE_BYTES;
   static DeviceOnce configured;
   if (const int cfg_dev = configured.needed(); cfg_dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(conv2d_k3_mma_kernel<CIN, NT, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv2d_k3_mma_kernel<CIN, NT, MODE, FUSE, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv2d_k3_mma_kernel<CIN, NT, MODE, FUSE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      e = cudaFuncSetAttribute(conv2d_k3_mma_kernel<CIN, NT, MODE, FUSE, TY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       set_error("bmv_conv2d_k3: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
       return BMV_ERR_CUDA_LAUNCH;
@@ -249,8 +254,17 @@ static int launch_c2(const bmv_conv2d_params& p, cudaStream_t st) {
     configured.done(cfg_dev);
   }
   const dim3 grid((unsigned)(((p.W + kC2TX - 1) / kC2TX) * ((p.H + kC2TY - 1) / kC2TY)), (unsigned)p.N);
-  conv2d_k3_mma_kernel<CIN, NT, MODE, FUSE><<<grid, kC2Threads, smem, st>>>(p);
+  conv2d_k3_mma_kernel<CIN, NT, MODE, FUSE, TY><<<grid, kC2Threads, smem, st>>>(p);
   return check_launch("bmv_conv2d_k3");
+}
+
+// 16-row tiles while they fill the GPU at least ~3 times over, 8-row tiles (twice as many CTAs of half the size) below that
+template <int CIN, int NT, int MODE, bool FUSE>
+static int launch_c2(const bmv_conv2d_params& p, cudaStream_t st) {
+  static const int ty_env = getenv("BMV_C2_TY") ? atoi(getenv("BMV_C2_TY")) : 0;   // measurements
+  const int64_t tiles16 = (int64_t)((p.W + kC2TX - 1) / kC2TX) * ((p.H + 15) / 16) * p.N;
+  const bool small = ty_env ? ty_env == 8 : tiles16 < 900;
+  return small ? launch_c2t<CIN, NT, MODE, FUSE, 8>(p, st) : launch_c2t<CIN, NT, MODE, FUSE, 16>(p, st);
 }
 
 }  // namespace bmv

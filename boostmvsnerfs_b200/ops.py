@@ -861,6 +861,40 @@ def convT3d_k3s2_add(x, wfrag, bias, cout, skip=None, out_dtype=torch.float32):
     return out
 
 
+def conv3d_small(x, wfrag, bias, cout, stride=1, relu=True, transposed=False, skip=None, out_dtype=torch.float16):
+    """3x3x3 convolution (+bias, +ReLU) — or ConvTranspose3d(k3, s2, p1, op1) + bias + skip with transposed=True — for
+    the low-resolution core of the cost regularisers (bmv_conv3d_small; fp16 operands, fp32 accumulation).  x fp16
+    channels_last_3d (N,Cin,D,H,W); wfrag from mlp_pack.pack_conv3d_small; skip fp16, dense, of the output's shape."""
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float16 and x.dim() == 5 and x.stride(1) == 1):
+        raise BmvError("conv3d_small: x must be a channels_last_3d fp16 CUDA tensor (N,C,D,H,W)")
+    _on_current_device(x, "x")
+    N, Cin, D, H, W = x.shape
+    need = _lib.load().bmv_conv3d_small_weight_words(Cin, cout, int(transposed))
+    if need < 0 or wfrag.dtype != torch.int32 or wfrag.numel() != need:
+        raise BmvError(f"conv3d_small: ({Cin} -> {cout}, transposed={transposed}) not instantiated or wfrag does not match")
+    if transposed:
+        stride = 2
+        osz = (2 * D, 2 * H, 2 * W)
+    else:
+        osz = ((D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1)
+    out = torch.empty((N, cout) + osz, device=x.device, dtype=out_dtype, memory_format=torch.channels_last_3d)
+    p = _lib.Conv3dSmallParams()
+    p.x = x.data_ptr()
+    p.x_n_stride, p.x_d_stride, p.x_y_stride, p.x_x_stride = x.stride(0), x.stride(2), x.stride(3), x.stride(4)
+    p.N, p.D, p.H, p.W, p.Cin, p.Cout = N, D, H, W, Cin, cout
+    p.stride, p.transposed, p.relu, p.out_half = stride, int(transposed), int(relu), int(out_dtype == torch.float16)
+    p.wfrag = wfrag.data_ptr()
+    p.bias = _cf32(bias, "bias").data_ptr() if bias is not None else 0
+    if skip is not None:
+        if not (skip.is_cuda and skip.dtype == torch.float16 and tuple(skip.shape) == tuple(out.shape)
+                and skip.is_contiguous(memory_format=torch.channels_last_3d)):
+            raise BmvError(f"conv3d_small: skip must be a dense channels_last_3d fp16 tensor of shape {tuple(out.shape)}")
+        p.skip = skip.data_ptr()
+    p.out = out.data_ptr()
+    _lib.call("bmv_conv3d_small", p, _stream())
+    return out
+
+
 def fpn_topdown_smooth(prev, lateral_in, lat_weight, lat_bias, smooth_wfrag, smooth_bias, cout, write_mid, want_half=False):
     """mid = up2x(prev) + conv1x1(lateral_in) + lat_bias; out = conv3x3(mid) + smooth_bias in ONE launch
     (reference lib/networks/enerf/feature_net.py:24-47; the 3x3 runs on tensor cores with fp16 operands).

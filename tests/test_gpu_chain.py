@@ -144,8 +144,11 @@ def test_frame_graph_replay_matches_eager(strict_fp32):
     fg = FrameGraph(net)
     eager = net(dict(batch))
     replay = {k: v.clone() for k, v in fg(batch).items()}
+    # Normally bit-identical.  This test runs the strict-fp32 route, whose convolutions are cuDNN's: on some boxes its
+    # algorithm choice differs between the eager call and the captured one (seen: 3 of 18432 rgb values off by 4e-6 of
+    # range), so the bar is 1e-5 of range; a stale buffer or a camera mix-up is off by the difference between two frames.
     for k in eager:
-        _report(replay[k], eager[k].cpu().numpy(), f"graph vs eager {k}", 1e-6)
+        _report(replay[k], eager[k].cpu().numpy(), f"graph vs eager {k}", 1e-5)
     _report(replay["rgb_level1"], g.np("out_rgb_level1"), "graph vs reference rgb", 1e-4)
     # a different frame (new images, new cameras) through the SAME captured graph, from host memory
     scene2 = make_scene(H=64, W=96, n_views=4, seed=77, smooth=True, tar_offset=(0.2, -0.05, 0.1))
@@ -153,7 +156,7 @@ def test_frame_graph_replay_matches_eager(strict_fp32):
     replay2 = fg(scene2)
     assert len(fg._cache) == 1
     for k in eager2:
-        _report(replay2[k], eager2[k].cpu().numpy(), f"graph vs eager, second frame {k}", 1e-6)
+        _report(replay2[k], eager2[k].cpu().numpy(), f"graph vs eager, second frame {k}", 1e-5)
 
 
 def test_graph_prefetch_streams_different_frames(strict_fp32):
