@@ -212,7 +212,7 @@ def load_ncu_traffic():
             NCU_TRAFFIC_MB, NCU_TRAFFIC_SOURCE = {}, {"stale": True, "captured_for": d.get("csrc_digest")}
             return
         NCU_TRAFFIC_MB = {k: float(v) for k, v in d.get("traffic_mb", {}).items()}
-        NCU_TRAFFIC_SOURCE = {k: d.get(k) for k in ("capture", "csrc_digest", "when")}
+        NCU_TRAFFIC_SOURCE = {k: d.get(k) for k in ("capture", "csrc_digest", "when", "workload")}
     except (OSError, ValueError):
         NCU_TRAFFIC_MB, NCU_TRAFFIC_SOURCE = {}, None
 
@@ -696,6 +696,9 @@ def main_ours(args):
     load_ncu_traffic()
 
     def _traffic(n):
+        # the capture is of ONE workload (C2 unless the file says otherwise): no traffic figure for another frame size
+        if (NCU_TRAFFIC_SOURCE or {}).get("workload", "C2") != args.workload:
+            return None
         return NCU_TRAFFIC_MB[n] * 1e6 if n in NCU_TRAFFIC_MB else None
 
     def _hbm_obj(n):
@@ -725,6 +728,13 @@ def main_ours(args):
         ms_e2e, execution = graph_res["e2e_ms_per_step"], execution + "; e2e: cuda_graph replay (FrameGraph)"
     else:
         execution += "; e2e: eager (stream launches)"
+    # kernel shares refer to the REPORTED step (the graph replay when it is the faster entry point): the per-launch times
+    # were taken in the eager instrumented pass (same kernels, same durations), whose step is longer by the host gaps
+    for k in kernels.values():
+        k["share_of_step"] = k["ms_per_launch"] * k["launches_per_step"] / ms
+    for obj in (roofline, roofline_hbm, roofline_hbm_dominant):
+        if obj:
+            obj["share_of_step"] = kernels[obj["kernel"]]["share_of_step"]
     line = {
         "metric": "rays_per_sec", "value": world * rays_per_frame / (ms * 1e-3), "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "ms_per_frame": ms,

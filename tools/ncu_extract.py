@@ -79,6 +79,7 @@ def main():
         sys.path.insert(0, ROOT)
         from boostmvsnerfs_b200 import build as _b
         cur["csrc_digest"] = _b._digest()[:16]
+        cur["workload"] = os.environ.get("WORKLOAD", "C2")          # what tools/frame_ab.py rendered under ncu
         cur["capture"] = sorted(set(cur["sources"].values()))
         cur["when"] = datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ")
         json.dump(cur, open(path, "w"), indent=1)
