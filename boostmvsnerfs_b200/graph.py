@@ -32,6 +32,9 @@ class FrameGraph:
             raise TypeError("FrameGraph wraps a BoostEnerfNetwork")
         self.net = net
         self.max_entries = int(max_entries)
+        # Network.forward leaves the LAST triple's views in the batch (batch['src_inps'] / ['src_exts'] / ['src_ixts'],
+        # read by the reference's evaluator); a caller that does not read them can switch the three gathers off
+        self.set_batch_views = True
         self._cache = OrderedDict()
         self._wtensors = None
         # frame_fn(static_inputs, camera, rays, triples, views_dev) -> output dict replaces the single-GPU frame body
@@ -98,7 +101,7 @@ class FrameGraph:
         entry = {"static": st, "views_dev": views_dev, "views_host": views_host, "triples": None, "cam_dev": cam_dev, "cam_host": cam_host, "gen_dev": gen_dev, "gen_host": gen_host,
                  "graph": None, "out": None}
 
-        def body():
+        def frame():
             net._views_dev = views_dev                      # kernels read the view ids from here (replayable across selections)
             gens = net._raygen_views(gen_dev, (H, W)) if gen_rays else None
             camera = net._camera_views(cam_dev, st["all_src_exts"][0], st["all_src_ixts"][0]) + (gens,)
@@ -113,6 +116,18 @@ class FrameGraph:
             net._views_dev = None
             return net._assemble([lv])
 
+        def body():
+            out = frame()
+            # batch['src_*'] of the LAST triple (see __call__), gathered INSIDE the graph: as three eager launches after
+            # every replay they cost 36-43 us per frame (19 us of kernels + the gaps they open between consecutive graph
+            # launches; tools/e2e_dissect.py)
+            srcv = None
+            if self.set_batch_views:
+                last_idx = views_dev[-1].long()
+                srcv = {dst: st[src].index_select(1, last_idx)
+                        for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts"))}
+            return out, srcv
+
         self._load_views(entry, triples)
         self._load(entry, batch)
         entry["cam_loaded"] = False                     # the first real call always loads its own cameras
@@ -126,7 +141,7 @@ class FrameGraph:
         net._baked_views = False
         try:
             with torch.cuda.graph(g), torch.no_grad():
-                entry["out"] = body()
+                entry["out"], entry["src_views"] = body()
         finally:
             net._views_dev = None
         entry["graph"] = g
@@ -265,11 +280,15 @@ class FrameGraph:
         entry["graph"].replay()
         # the reference leaves the LAST triple's views in the batch (evaluators read batch['src_inps'].shape;
         # reference lib/networks/boost_enerf/network.py:196-201): same contract as Network.forward
-        # Gathered on the device from the uploaded copy (a host batch would pay an 18 MB CPU gather per frame); real
-        # copies, so the next call's upload does not change them.
+        # Gathered on the device from the uploaded copy (a host batch would pay an 18 MB CPU gather per frame) into
+        # static tensors of the graph: like the returned outputs they are overwritten by the next call.
         # (index_select with a device-resident index: indexing with a Python list uploads the indices with a blocking
         # copy, i.e. one host sync per frame)
-        last_idx = entry["views_dev"][-1].long()
-        for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts")):
-            batch[dst] = entry["static"][src].index_select(1, last_idx)
+        if self.set_batch_views:
+            if entry.get("src_views") is not None:           # gathered by the replay: static tensors, like `out`
+                batch.update(entry["src_views"])
+            else:                                            # graph captured with set_batch_views off
+                last_idx = entry["views_dev"][-1].long()
+                for src, dst in (("all_src_inps", "src_inps"), ("all_src_exts", "src_exts"), ("all_src_ixts", "src_ixts")):
+                    batch[dst] = entry["static"][src].index_select(1, last_idx)
         return entry["out"]

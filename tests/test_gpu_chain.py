@@ -19,6 +19,13 @@ from oracle import enerf_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+# Captured-graph replay against the eager call of the same frame on the strict-fp32 route (cuDNN convolutions): normally
+# bit-identical, but cuDNN's algorithm choice can differ between the two on some boxes (seen once: 3 of 18432 rgb values
+# off by 4e-6 of range).  1e-5 of range still catches what these tests are after — stale buffers, wrong weights, a
+# camera or selection mix-up are off by the difference between two frames (>= 1e-4, asserted where it matters).
+GRAPH_VS_EAGER = 1e-5
+
+
 def _report(a, b, what, rtol):
     a = a.detach().float().cpu().numpy()
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
@@ -148,7 +155,7 @@ def test_frame_graph_replay_matches_eager(strict_fp32):
     # algorithm choice differs between the eager call and the captured one (seen: 3 of 18432 rgb values off by 4e-6 of
     # range), so the bar is 1e-5 of range; a stale buffer or a camera mix-up is off by the difference between two frames.
     for k in eager:
-        _report(replay[k], eager[k].cpu().numpy(), f"graph vs eager {k}", 1e-5)
+        _report(replay[k], eager[k].cpu().numpy(), f"graph vs eager {k}", GRAPH_VS_EAGER)
     _report(replay["rgb_level1"], g.np("out_rgb_level1"), "graph vs reference rgb", 1e-4)
     # a different frame (new images, new cameras) through the SAME captured graph, from host memory
     scene2 = make_scene(H=64, W=96, n_views=4, seed=77, smooth=True, tar_offset=(0.2, -0.05, 0.1))
@@ -156,7 +163,7 @@ def test_frame_graph_replay_matches_eager(strict_fp32):
     replay2 = fg(scene2)
     assert len(fg._cache) == 1
     for k in eager2:
-        _report(replay2[k], eager2[k].cpu().numpy(), f"graph vs eager, second frame {k}", 1e-5)
+        _report(replay2[k], eager2[k].cpu().numpy(), f"graph vs eager, second frame {k}", GRAPH_VS_EAGER)
 
 
 def test_graph_prefetch_streams_different_frames(strict_fp32):
@@ -203,7 +210,7 @@ def test_generated_rays_give_the_same_frame(strict_fp32):
     net.generate_rays = True
     out2 = FrameGraph(net)(dict(batch))
     for k in ref:
-        _report(out2[k], ref[k].cpu().numpy(), f"generated rays, graph {k}", 1e-6)
+        _report(out2[k], ref[k].cpu().numpy(), f"generated rays, graph {k}", GRAPH_VS_EAGER)
 
 
 def test_training_mode_and_cpu_are_refused():
@@ -325,7 +332,7 @@ def test_frame_graph_fresh_device_batches_get_their_own_cameras(strict_fp32):
         ptrs.add(b["tar_ext"].data_ptr())
         got = fg(b)
         for k in want:
-            _report(got[k], want[k].cpu().numpy(), f"frame {s} {k}", 1e-6)
+            _report(got[k], want[k].cpu().numpy(), f"frame {s} {k}", GRAPH_VS_EAGER)
         del b, got
     assert len(fg._cache) == 1
 
@@ -350,7 +357,7 @@ def test_frame_graph_follows_weights_and_flags(strict_fp32):
     got = fg(dict(batch))
     assert len(fg._cache) == 2
     for k in want:
-        _report(got[k], want[k].cpu().numpy(), f"after load_state_dict {k}", 1e-6)
+        _report(got[k], want[k].cpu().numpy(), f"after load_state_dict {k}", GRAPH_VS_EAGER)
     assert (got["rgb_level1"] - first["rgb_level1"]).abs().max().item() > 1e-4
     net.mlp_engine = "fma"
     fg(dict(batch))
@@ -359,7 +366,7 @@ def test_frame_graph_follows_weights_and_flags(strict_fp32):
     net.mlp_engine = "mma"
     back = fg(dict(batch))
     for k in first:
-        _report(back[k], first[k].cpu().numpy(), f"weights restored {k}", 1e-6)
+        _report(back[k], first[k].cpu().numpy(), f"weights restored {k}", GRAPH_VS_EAGER)
 
 
 def test_frame_graph_is_selection_agnostic(strict_fp32):
@@ -380,7 +387,7 @@ def test_frame_graph_is_selection_agnostic(strict_fp32):
         b = batch_to(scene, "cuda")
         got = fg(b)
         for k in want:
-            _report(got[k], want[k].cpu().numpy(), f"selection {sel} {k}", 1e-6)
+            _report(got[k], want[k].cpu().numpy(), f"selection {sel} {k}", GRAPH_VS_EAGER)
         assert torch.equal(b["src_exts"], b["all_src_exts"][:, list(table[sel[-1]])])
     assert len(fg._cache) == 1 and next(iter(fg._cache.values()))["agnostic"]
     net.multi_chain_render = False                 # per-chain launches bake their view ids: one graph per selection again
@@ -389,5 +396,5 @@ def test_frame_graph_is_selection_agnostic(strict_fp32):
         want = {k: v.clone() for k, v in net(batch_to(scene, "cuda")).items()}
         got = fg(batch_to(scene, "cuda"))
         for k in want:
-            _report(got[k], want[k].cpu().numpy(), f"baked selection {sel} {k}", 1e-6)
+            _report(got[k], want[k].cpu().numpy(), f"baked selection {sel} {k}", GRAPH_VS_EAGER)
     assert len(fg._cache) == 3
