@@ -273,6 +273,10 @@ class FusedTopDownFPN(nn.Module):
     # launches instead of seven (the 5x5 / stride-2 layers read their input through space-to-depth in the staging loop,
     # the 1x1 top layer runs in conv2.1's epilogue), fp16 intermediates between them.  TF32-class like the rest.
     tensor_core_mid = True
+    # {'level_1': consumer_scale}: the caller wants the fp16 cost volume's range scale of that level (ops.volume_scale)
+    # computed right behind the launch that produces the level — on the side stream when the top-down steps run there,
+    # i.e. under the level-0 chain instead of in front of the level-1 cost volumes (13 us at C2).  Results in `scales`.
+    scale_requests = None
 
     def __init__(self, fpn):
         super().__init__()
@@ -281,6 +285,7 @@ class FusedTopDownFPN(nn.Module):
         self._mid = None
         self._side = None
         self.ready = None
+        self.scales = {}
 
     def _mid_weights(self, device):
         if self._mid is None or self._mid['device'] != device:
@@ -350,6 +355,7 @@ class FusedTopDownFPN(nn.Module):
             c2 = f.conv2(c1)
             quarter = f.toplayer(c2)
         self.ready = None
+        self.scales = {}
         if fused:
             w1, w0, _ = self._smooth_weights(x.device)
 
@@ -358,6 +364,8 @@ class FusedTopDownFPN(nn.Module):
                     half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True, want_half='only')
                 else:
                     half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
+                if self.scale_requests and 'level_1' in self.scale_requests:
+                    self.scales['level_1'] = ops.volume_scale(feat1, consumer_scale=self.scale_requests['level_1'])
                 ev1 = torch.cuda.current_stream().record_event() if self.side_topdown else None
                 _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)
                 ev0 = torch.cuda.current_stream().record_event() if self.side_topdown else None
@@ -373,7 +381,7 @@ class FusedTopDownFPN(nn.Module):
                 feat1, feat0, ev1, ev0 = topdown()
             for t in (quarter, c1, c0):                    # caching allocator: these blocks are still read by the side stream
                 t.record_stream(self._side)
-            for t in (feat1, feat0):                       # ... and these are consumed on `main`
+            for t in (feat1, feat0) + tuple(self.scales.values()):     # ... and these are consumed on `main`
                 if torch.is_tensor(t):
                     t.record_stream(main)
             self.ready = {'level_1': ev1, 'level_2': ev0}

@@ -150,6 +150,7 @@ class EnerfNetwork(nn.Module):
         if fused_plan:
             plan.emit_half_features = bool(self.half_feature_taps)
             plan.side_topdown = bool(self.overlap_fpn_topdown)
+            plan.scale_requests = self._volume_scale_requests(x.device)
         if self.channels_last and not fused_plan:
             x = x.contiguous(memory_format=torch.channels_last)
         quarter, half, full = plan(x)
@@ -159,9 +160,27 @@ class EnerfNetwork(nn.Module):
             plan.ready = None
             if plan.rgb_nhwc4 is not None:
                 feats['rgb_nhwc4'] = plan.rgb_nhwc4         # by-product of the stem kernel (see _render_level)
+            for lvl, sc in plan.scales.items():             # range scales computed behind their level (same event)
+                feats[f'vscale_{lvl}'] = sc
         if not defer:
             feats.join()
         return feats
+
+    def _fp16_volume(self, i, C, dev):
+        """Whether level i's cost volume is stored as (range-scaled) fp16: conv0 of its regulariser runs on libbmv's
+        tensor-core kernel, whose operands are fp16 anyway."""
+        plan = self._kept(f'cost_reg_{i}')
+        return bool(self.channels_last and dev.type == 'cuda' and getattr(plan, 'tensor_core_convs', False)
+                    and torch.backends.cudnn.allow_tf32 and C in (16, 32))
+
+    def _volume_scale_requests(self, dev):
+        """Levels >= 1 whose fp16 volume needs a range scale, with the consumer's weight scale (see FusedTopDownFPN)."""
+        req = {}
+        if self.volume_range_scale:
+            for i in range(1, self.rc.num):
+                if self._fp16_volume(i, int(32 * 2 ** (-i)), dev):
+                    req[f'level_{i}'] = self._kept(f'cost_reg_{i}').input_weight_scale(dev)
+        return req or None
 
     @staticmethod
     def _proj_all(exts, ixts, tar_ext, tar_ixt, src_scale, tar_scale):
@@ -296,16 +315,15 @@ class EnerfNetwork(nn.Module):
                 # When conv0 of the regulariser runs on libbmv's tensor-core kernel its operands are rounded to
                 # fp16 anyway: K1 then emits the volume in fp16 (same result, half the write + read traffic).
                 plan = self._kept(f'cost_reg_{i}')
-                vdt = torch.float32
-                if self.channels_last and dev.type == 'cuda' and getattr(plan, 'tensor_core_convs', False) \
-                        and torch.backends.cudnn.allow_tf32 and C in (16, 32):
-                    vdt = torch.float16
+                vdt = torch.float16 if self._fp16_volume(i, C, dev) else torch.float32
                 self.last_volume_dtype = vdt
                 # fp16 has 5 exponent bits: store s * variance with a power of two s derived from max|feature| so the
                 # volume cannot overflow and small-magnitude features stay out of the subnormals; conv0 undoes it
                 vsc = None
                 if vdt == torch.float16 and self.volume_range_scale:
-                    vsc = ops.volume_scale(f, consumer_scale=plan.input_weight_scale(dev))
+                    vsc = feats.get(f'vscale_level_{i}')   # computed behind the FPN launch that produced the level
+                    if vsc is None:
+                        vsc = ops.volume_scale(f, consumer_scale=plan.input_weight_scale(dev))
                 if self.channels_last:
                     vols = torch.empty((K, D, h, w, C), device=dev, dtype=vdt).permute(0, 4, 1, 2, 3)
                 else:
