@@ -224,3 +224,24 @@ def test_sinks_oracle_arithmetic():
     assert abs(SO.frame_psnr(pred, gt, mask, eval_center=True) - 10 * np.log10(1 / mse)) < 1e-12
     rgb8, d8 = SO.frame_to_u8(np.array([[0.0, 0.999, 1.0]], np.float32), np.array([2.0, 3.0, 4.0], np.float32))
     assert rgb8.tolist() == [[0, 254, 255]] and d8.tolist() == [0, 127, 255]
+
+
+def test_bench_accounts_the_tensor_core_fpn_route():
+    """bench.conv_kernel_bytes: compulsory HBM bytes of the FPN launches for the cuDNN route of conv1.x / conv2.x (fp32 c0 +
+    its space-to-depth copy; pinned to the figures of DESIGN.md section 3) and for the bmv_conv2d_k3 route (fp16 tensors
+    between the stem and the top layer, four extra launches)."""
+    import bench
+    from boostmvsnerfs_b200.config import RenderConfig
+    wl = bench.WORKLOADS["C2"]
+    rc = RenderConfig.enerf_eval(wl["K"])
+    px = wl["n_views"] * wl["H"] * wl["W"]
+    old = bench.conv_kernel_bytes(wl, rc, 2, "bmv_conv3d_k3_umma", False)
+    new = bench.conv_kernel_bytes(wl, rc, 2, "bmv_conv3d_k3_umma", True)
+    assert "bmv_conv2d_k3" not in old and [n for n, _ in new["bmv_conv2d_k3"]] == ["fpn_conv1_0", "fpn_conv1_1", "fpn_conv2_0", "fpn_conv2_1_top"]
+    assert dict(old["bmv_fpn_stem"])["fpn_stem"] == px * 4 * (3 + 8 + 4 + 8)
+    assert dict(new["bmv_fpn_stem"])["fpn_stem"] == px * (12 + 16 + 16)                    # image in, rgb4 + fp16 c0 out
+    assert dict(new["bmv_conv2d_k3"])["fpn_conv1_0"] == px * 16 + px // 4 * 32             # fp16 c0 in, fp16 (N,16,H/2,W/2) out
+    assert dict(new["bmv_conv2d_k3"])["fpn_conv2_1_top"] == px // 16 * 32 * 6              # fp16 in, fp32 top-layer out
+    for (n0, b0), (n1, b1) in zip(old["bmv_fpn_topdown_smooth"], new["bmv_fpn_topdown_smooth"]):
+        assert n0 == n1 and b1 < b0                                                         # fp16 lateral inputs
+    assert old["bmv_conv3d_k3"] == new["bmv_conv3d_k3"]
