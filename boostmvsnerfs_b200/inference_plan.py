@@ -121,6 +121,9 @@ class MergedHeadsCostReg(nn.Module):
     # 4 L1 wavefronts each, ~6 wavefronts per MMA; only the transposed layer + its skip add wins (23 vs 43 us).  Kept as
     # a function-level kernel with its parity tests.
     small_convs = False
+    # only the transposed conv7 + its skip add on that kernel (one launch instead of cuDNN's dgrad kernel + an add; the
+    # layer where the direct kernel won in the per-layer timing); needs the fp16 low-resolution route (lowres_half)
+    small_transposed = False
 
     def __init__(self, net):
         super().__init__()
@@ -229,7 +232,13 @@ class MergedHeadsCostReg(nn.Module):
             s2 = low.conv4(low.conv3(s1))
             y = s2
             if n.depth_levels == 3:
-                y = s2 + low.conv7(low.conv6(low.conv5(s2)))
+                y6 = low.conv6(low.conv5(s2))
+                if (half_low and self.small_transposed and self._small_ok() and y6.dtype == torch.float16
+                        and y6.is_contiguous(memory_format=torch.channels_last_3d)
+                        and s2.is_contiguous(memory_format=torch.channels_last_3d)):
+                    y = ops.conv3d_small(y6, *self._small_weights(x.device)['conv7'], 32, transposed=True, relu=False, skip=s2)
+                else:
+                    y = s2 + low.conv7(y6)
         if fast and y.stride(1) == 1 and s1.stride(1) == 1:
             y = ops.convT3d_k3s2_add(y, *pk['conv9'], 16, skip=s1, out_dtype=torch.float16)
             # the full-resolution result only feeds the fp16-operand heads convolution: store it as fp16 (TMA-staged there)
@@ -286,6 +295,14 @@ class FusedTopDownFPN(nn.Module):
         self._side = None
         self.ready = None
         self.scales = {}
+
+    def _scale_buf(self, level, device):
+        """Persistent 6-float result / scratch buffer of ops.volume_scale for one level (zeroed once)."""
+        bufs = self.__dict__.setdefault('_scale_bufs', {})
+        key = (level, device)
+        if key not in bufs:
+            bufs[key] = torch.zeros(6, device=device)
+        return bufs[key]
 
     def _mid_weights(self, device):
         if self._mid is None or self._mid['device'] != device:
@@ -365,7 +382,8 @@ class FusedTopDownFPN(nn.Module):
                 else:
                     half, feat1 = ops.fpn_topdown_smooth(quarter, c1, f.lat1.weight, f.lat1.bias, w1, f.smooth1.bias, 16, True)
                 if self.scale_requests and 'level_1' in self.scale_requests:
-                    self.scales['level_1'] = ops.volume_scale(feat1, consumer_scale=self.scale_requests['level_1'])
+                    self.scales['level_1'] = ops.volume_scale(feat1, consumer_scale=self.scale_requests['level_1'],
+                                                              out=self._scale_buf('level_1', feat1.device))
                 ev1 = torch.cuda.current_stream().record_event() if self.side_topdown else None
                 _, feat0 = ops.fpn_topdown_smooth(half, c0, f.lat0.weight, f.lat0.bias, w0, f.smooth0.bias, 8, False)
                 ev0 = torch.cuda.current_stream().record_event() if self.side_topdown else None

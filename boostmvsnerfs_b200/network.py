@@ -323,7 +323,10 @@ class EnerfNetwork(nn.Module):
                 if vdt == torch.float16 and self.volume_range_scale:
                     vsc = feats.get(f'vscale_level_{i}')   # computed behind the FPN launch that produced the level
                     if vsc is None:
-                        vsc = ops.volume_scale(f, consumer_scale=plan.input_weight_scale(dev))
+                        bufs = self.__dict__.setdefault('_vsc_bufs', {})
+                        if (i, dev) not in bufs:
+                            bufs[(i, dev)] = torch.zeros(6, device=dev)      # result + zeroed scratch words, re-used per frame
+                        vsc = ops.volume_scale(f, consumer_scale=plan.input_weight_scale(dev), out=bufs[(i, dev)])
                 if self.channels_last:
                     vols = torch.empty((K, D, h, w, C), device=dev, dtype=vdt).permute(0, 4, 1, 2, 3)
                 else:

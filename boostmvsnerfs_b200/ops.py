@@ -68,7 +68,7 @@ def _linspace(n, device):
 
 
 # ------------------------------------------------------------------------------------------ K1
-def volume_scale(feats, target=16384.0, consumer_scale=1.0):
+def volume_scale(feats, target=16384.0, consumer_scale=1.0, out=None):
     """Power-of-two range scale for an fp16 cost volume built from `feats` (bmv_volume_scale): returns a device tensor
     [s, 1/s, 0, 0, s*c, 1/(s*c)] with s * max|feats|^2 <= target and c = consumer_scale (the power of two the consuming
     convolution's fp16 weights were packed with).  Pass it as `out_scale` to the cost-volume ops and `t[4:6]` as
@@ -78,7 +78,14 @@ def volume_scale(feats, target=16384.0, consumer_scale=1.0):
     # every element of the underlying storage span is a feature value: dense tensors only (any memory format)
     if not (feats.is_contiguous() or feats.is_contiguous(memory_format=torch.channels_last)):
         raise BmvError("volume_scale: feats must be dense (contiguous or channels_last)")
-    sc = torch.zeros(6, device=feats.device)
+    # out: a 6-float buffer from an earlier call on this device (the kernel leaves its two scratch words zero, so it can be
+    # re-used call after call in stream order: saves the fill launch of a fresh one)
+    if out is not None:
+        if not (out.is_cuda and out.dtype == torch.float32 and out.numel() == 6 and out.is_contiguous() and out.device == feats.device):
+            raise BmvError("volume_scale: out must be a contiguous 6-float CUDA tensor on feats' device")
+        sc = out
+    else:
+        sc = torch.zeros(6, device=feats.device)
     p = _lib.VolumeScaleParams()
     p.x, p.n, p.x_half, p.target, p.scale = feats.data_ptr(), n, half, float(target), sc.data_ptr()
     p.consumer_scale = float(consumer_scale)
