@@ -245,3 +245,34 @@ def test_bench_accounts_the_tensor_core_fpn_route():
     for (n0, b0), (n1, b1) in zip(old["bmv_fpn_topdown_smooth"], new["bmv_fpn_topdown_smooth"]):
         assert n0 == n1 and b1 < b0                                                         # fp16 lateral inputs
     assert old["bmv_conv3d_k3"] == new["bmv_conv3d_k3"]
+
+
+def test_fpn_plan_routes_mid_layers_only_for_shapes_it_supports():
+    """FusedTopDownFPN._mid_ok: conv1.x / conv2.x / top layer go to bmv_conv2d_k3 only when the folded plan has the
+    regrouped 5x5 layers, biases everywhere and H, W are multiples of 4 (two space-to-depth steps); everything else keeps
+    the cuDNN route.  Host logic only (no launch)."""
+    import torch
+    from boostmvsnerfs_b200.inference_plan import FusedTopDownFPN, folded_copy
+    from boostmvsnerfs_b200.modules import FeatureNet
+    torch.manual_seed(0)
+    plan = FusedTopDownFPN(folded_copy(FeatureNet().eval(), torch.channels_last))
+    assert plan._mid_ok(torch.empty(2, 3, 64, 96))
+    assert not plan._mid_ok(torch.empty(2, 3, 66, 96)) and not plan._mid_ok(torch.empty(2, 3, 64, 98))
+    plan.tensor_core_mid = False
+    assert not plan._mid_ok(torch.empty(2, 3, 64, 96))
+    plan.tensor_core_mid = True
+    unfolded = FusedTopDownFPN(FeatureNet().eval())                     # BN not folded, 5x5 layers not regrouped
+    assert not unfolded._mid_ok(torch.empty(2, 3, 64, 96))
+
+
+def test_volume_scale_requests_follow_the_fp16_volume_gating():
+    """Network._volume_scale_requests: a range scale is requested from the FPN plan only for levels >= 1 whose cost volume is
+    stored in fp16 (CUDA, channels-last, TF32-class convolutions allowed, range scaling on) — never on the CPU."""
+    import torch
+    from boostmvsnerfs_b200 import network
+    from boostmvsnerfs_b200.config import RenderConfig
+    net = network.BoostEnerfNetwork(preprocess=True, rc=RenderConfig.enerf_eval(2)).eval()
+    assert net._volume_scale_requests(torch.device("cpu")) is None
+    assert not net._fp16_volume(1, 16, torch.device("cpu"))
+    net.volume_range_scale = False
+    assert net._volume_scale_requests(torch.device("cpu")) is None
